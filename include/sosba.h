@@ -1,0 +1,300 @@
+/*
+ * sosba.h — C ABI of the B200-native photometric bundle-adjustment / direct-alignment path.
+ *
+ * Drop-in boundary for the hot path of IRVLab/SOS-SLAM.  The reference has no
+ * FFI: the "operator surface" is a set of C++ member functions that FullSystem calls directly.
+ * Every entry point below names the reference member it replaces (file:line, relative to the
+ * reference tree).  Plain pointers and sizes only; all buffers are caller-owned HOST memory
+ * unless a name ends in `_dev`.  Every function returns 0 on success, a negative SOSBA_E_* code
+ * otherwise; nothing throws, nothing aborts (reference convention: flags + non-finite sentinels,
+ * SURVEY.md §8b "Error conventions").  One handle per FullSystem, single caller thread.
+ *
+ * Index conventions (verbatim from the reference):
+ *   block index  = host + target*nf           (AccumulatedTopHessian.cpp:66, EnergyFunctional.cpp:82)
+ *   precalc      = host*nf + target           (FrameHessian::targetPrecalc[target->idx])
+ *   state order  = [tx ty tz rx ry rz a b]    (8 per frame), calib = [fx fy cx cy] (CPARS=4)
+ *   D            = 4 + 8*nf, H row-major D x D double
+ */
+#ifndef SOSBA_H_
+#define SOSBA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOSBA_CPARS 4
+#define SOSBA_PATTERN 8            /* patternNum, settings.h:187 */
+#define SOSBA_MAX_LEVELS 6         /* PYR_LEVELS, settings.h:34 */
+#define SOSBA_PRECALC_FLOATS 32    /* packed FrameFramePrecalc, see sosba_precalc_layout */
+#define SOSBA_J_FLOATS 74          /* RawResidualJacobian dump, member order of RawResidualJacobian.h:29-55 */
+
+/* ResState, Residuals.h:43 */
+enum { SOSBA_RES_IN = 0, SOSBA_RES_OOB = 1, SOSBA_RES_OUTLIER = 2 };
+
+enum {
+  SOSBA_OK = 0,
+  SOSBA_E_ARG = -1,      /* bad argument / shape */
+  SOSBA_E_CUDA = -2,     /* CUDA runtime error (message via sosba_last_error) */
+  SOSBA_E_STATE = -3,    /* call order violated (reference asserts EFDeltaValid/EFIndicesValid) */
+  SOSBA_E_NOGPU = -4,    /* no CUDA device: the product has no CPU fallback */
+  SOSBA_E_NCCL = -5,
+  SOSBA_E_NONFINITE = -6 /* a non-finite value reached the solver (reference: isLost) */
+};
+
+/* Offsets inside one packed FrameFramePrecalc record (HessianBlocks.h:109-134), row-major 3x3. */
+enum sosba_precalc_layout {
+  SOSBA_PC_RTLL0 = 0,   /* PRE_RTll_0   [9] */
+  SOSBA_PC_TTLL0 = 9,   /* PRE_tTll_0   [3] */
+  SOSBA_PC_KRKI = 12,   /* PRE_KRKiTll  [9] */
+  SOSBA_PC_KT = 21,     /* PRE_KtTll    [3] */
+  SOSBA_PC_AFF = 24,    /* PRE_aff_mode [2] */
+  SOSBA_PC_B0 = 26,     /* PRE_b0_mode      */
+  SOSBA_PC_DIST = 27    /* distanceLL       */
+};
+
+/* The setting_* globals the path reads (util/settings.cpp:28-204) + compile-time sizes. */
+typedef struct sosba_config {
+  int32_t w, h;               /* wG[0], hG[0] */
+  int32_t pyr_levels;         /* 0 = derive like setGlobalCalib (globalCalib.cpp:39-49) */
+  int32_t max_frames;         /* image slots to allocate (live KFs + tracked frame + cam1) */
+  int32_t num_threads;        /* CPU oracle only: IndexThreadReduce workers; <=1 = the reference's nomt path */
+  int32_t gamma_weights_pixel_select; /* setting_gammaWeightsPixelSelect */
+  int32_t min_opt_iterations; /* setting_minOptIterations */
+  int32_t reserved0;
+  float huber_th;                 /* setting_huberTH = 9 */
+  float outlier_th_sum_component; /* setting_outlierTHSumComponent = 2500 */
+  float affine_opt_mode_a;        /* setting_affineOptModeA (mode 1 -> 0) */
+  float affine_opt_mode_b;
+  float coarse_cutoff_th;         /* setting_coarseCutoffTH = 20 */
+  float idepth_fix_prior;         /* 2500 */
+  float idepth_fix_prior_marg_fac;/* 360000 */
+  float frame_energy_th_const_weight; /* 0.5 */
+  float frame_energy_th_n;            /* 0.7 */
+  float frame_energy_th_fac_median;   /* 1.5 */
+  float overall_energy_th_weight;     /* 1 */
+  float initial_calib_hessian;        /* 5e9 */
+  float initial_rot_prior, initial_trans_prior, initial_aff_a_prior, initial_aff_b_prior;
+  float marg_weight_fac;          /* 0.25 */
+  float th_opt_iterations;        /* 1.2 */
+} sosba_config;
+
+/* Fills the defaults of settings.cpp after settingsDefault(preset=0, mode=1) (main.cpp:27-90). */
+void sosba_config_default(sosba_config *cfg, int32_t w, int32_t h);
+
+/* Window tables: what FullSystem::setPrecalcValues (FullSystem.cpp:1099-1107),
+ * EnergyFunctional::setAdjointsF (EnergyFunctional.cpp:42-103) and setDeltaF (:163-194) produce. */
+typedef struct sosba_window {
+  int32_t nf;
+  int32_t reserved0;
+  const int32_t *frame_slot;       /* [nf] image slot holding frame i's pyramid */
+  const float *precalc;            /* [nf*nf*SOSBA_PRECALC_FLOATS], host*nf+target */
+  const double *adHost;            /* [nf*nf*64] host+target*nf, row-major 8x8 */
+  const double *adTarget;          /* [nf*nf*64] */
+  const float *adHTdeltaF;         /* [nf*nf*8]  host+target*nf */
+  const float *frame_energy_th;    /* [nf] FrameHessian::frameEnergyTH */
+  float calib[4];                  /* fxl fyl cxl cyl = CalibHessian::value_scaledf */
+  float cDeltaF[4];                /* EnergyFunctional::cDeltaF */
+  double cPrior[4];                /* EnergyFunctional::cPrior */
+  const double *frame_prior;       /* [nf*8] EFFrame::prior */
+  const double *frame_delta_prior; /* [nf*8] EFFrame::delta_prior */
+  const double *frame_delta;       /* [nf*8] EFFrame::delta (state - state_zero) */
+} sosba_window;
+
+/* Active points (PointHessian + EFPoint), SoA.  SCALE_IDEPTH == 1 so idepth_scaled == idepth. */
+typedef struct sosba_points {
+  int32_t n;
+  int32_t reserved0;
+  const float *u, *v;              /* host pixel */
+  const float *idepth;             /* PointHessian::idepth(_scaled) */
+  const float *idepth_zero;        /* PointHessian::idepth_zero(_scaled) */
+  const float *color;              /* [n*8] */
+  const float *weights;            /* [n*8] */
+  const int32_t *host;             /* [n] dense frame index (EFFrame::idx) */
+  const float *priorF;             /* [n] EFPoint::priorF */
+  const float *deltaF;             /* [n] EFPoint::deltaF */
+} sosba_points;
+
+/* PointFrameResidual + EFResidual bookkeeping, point-major (residuals of one point contiguous, in
+ * EFPoint::residualsAll order; `point` non-decreasing).  Dense ids as after makeIDX()
+ * (EnergyFunctional.cpp:1186-1202). */
+typedef struct sosba_residuals {
+  int32_t n;
+  int32_t reserved0;
+  const int32_t *point;            /* [n] */
+  const int32_t *target;           /* [n] dense frame index */
+  const uint8_t *state;            /* [n] state_state (ResState) */
+  const uint8_t *is_linearized;    /* [n] EFResidual::isLinearized */
+  const uint8_t *is_active;        /* [n] EFResidual::isActiveAndIsGoodNEW */
+  const uint8_t *is_new;           /* [n] PointFrameResidual::isNew */
+  const float *state_energy;       /* [n] or NULL (=0) */
+} sosba_residuals;
+
+typedef struct sosba_linearize_out {
+  double energy;            /* stats[0]: sum of linearize() return values (FullSystemOptimize.cpp:49) */
+  float new_frame_energy_th;/* frameEnergyTH of the newest frame after setNewFrameEnergyTH (:84-124) */
+  int32_t n_in, n_oob, n_outlier; /* histogram of state_NewState over the linearized residuals */
+  int32_t n_removed;        /* fixLinearization: residuals that turned inactive (toRemove, :148-179) */
+  int32_t reserved0;
+} sosba_linearize_out;
+
+typedef struct sosba sosba_t;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int sosba_create(const sosba_config *cfg, int32_t device, sosba_t **out);
+void sosba_destroy(sosba_t *h);
+const char *sosba_last_error(void);
+/* Launch everything on this cudaStream_t (0 = the handle's own stream). */
+int sosba_set_stream(sosba_t *h, void *cuda_stream);
+int sosba_synchronize(sosba_t *h);
+/* Number of kernel launches issued by this handle since creation (bench `gpu_launches`). */
+int64_t sosba_launch_count(const sosba_t *h);
+int32_t sosba_pyr_levels(const sosba_t *h);
+
+/* ---- a1: FrameHessian::makeImages (HessianBlocks.cpp:121-176) -------------------------------- */
+/* color: w*h irradiance; B: 256-entry response (CalibHessian::B) or NULL (HCalib==0 branch). */
+int sosba_frame_make_images(sosba_t *h, int32_t slot, const float *color, const float *B);
+/* dIp[lvl] as Eigen::Vector3f AoS (w_l*h_l*3) and absSquaredGrad[lvl] (w_l*h_l); either may be NULL.
+ * First/last row of dx,dy,absSquaredGrad are uninitialised in the reference; here they are 0. */
+int sosba_frame_get_level(sosba_t *h, int32_t slot, int32_t lvl, float *dI3, float *abs_sq_grad);
+
+/* ---- window / point / residual upload ------------------------------------------------------- */
+int sosba_window_set(sosba_t *h, const sosba_window *w);
+int sosba_points_set(sosba_t *h, const sosba_points *p);
+int sosba_residuals_set(sosba_t *h, const sosba_residuals *r);
+/* Only the per-iteration part of a window (precalc, adHTdeltaF, cDeltaF, calib, delta, delta_prior,
+ * frame_energy_th): FullSystem::setPrecalcValues + setDeltaF after doStepFromBackup. */
+int sosba_window_update(sosba_t *h, const sosba_window *w);
+/* PointHessian::setIdepth/setIdepthZero + EFPoint::deltaF for all points (doStepFromBackup). */
+int sosba_points_update(sosba_t *h, const float *idepth, const float *idepth_zero, const float *deltaF);
+
+/* ---- a3/a4/a5: linearize / applyRes --------------------------------------------------------- */
+/* PointFrameResidual::resetOOB over all non-linearized residuals (FullSystemOptimize.cpp:316-329). */
+int sosba_reset_oob(sosba_t *h);
+/* FullSystem::linearizeAll(fixLinearization) (FullSystemOptimize.cpp:125-182) over activeResiduals
+ * (= residuals with !is_linearized), including setNewFrameEnergyTH. */
+int sosba_linearize_all(sosba_t *h, int32_t fix_linearization, sosba_linearize_out *out);
+/* FullSystem::applyRes_Reductor(true) (FullSystemOptimize.cpp:79-83 -> Residuals.cpp:304-321). */
+int sosba_apply_res(sosba_t *h);
+/* EFResidual::fixLinearizationF for the listed residuals (EnergyFunctionalStructs.cpp:75-103). */
+int sosba_fix_linearization(sosba_t *h, const int32_t *residual_ids, int32_t n);
+
+/* per-residual read-back (any pointer may be NULL) */
+int sosba_residuals_get_state(sosba_t *h, uint8_t *state, uint8_t *new_state, float *energy,
+                              float *new_energy, float *new_energy_with_outlier, uint8_t *is_active,
+                              uint8_t *is_linearized);
+/* committed=1: EFResidual::J (after applyRes); 0: PointFrameResidual::J (candidate). [n*74] */
+int sosba_residuals_get_jacobians(sosba_t *h, int32_t committed, float *J);
+int sosba_residuals_get_aux(sosba_t *h, float *JpJdF /*[n*8]*/, float *res_to_zero /*[n*8]*/,
+                            float *projected_to /*[n*16]*/, float *center_projected_to /*[n*3]*/);
+/* fixLinearization bookkeeping (FullSystemOptimize.cpp:55-70): per point maxRelBaseline,
+ * numGoodResiduals increments; per residual removal flag. */
+int sosba_points_get_stats(sosba_t *h, float *max_rel_baseline, int32_t *num_good_residuals);
+
+/* ---- a6-a9: accumulate + stitch ------------------------------------------------------------- */
+/* EnergyFunctional::accumulateAF_MT / accumulateLF_MT / accumulateSCF_MT (EnergyFunctional.cpp:197-254)
+ * HA,HL,Hsc: D*D row-major; bA,bL,bsc: D.  Any output may be NULL.  With a communicator attached the
+ * result is the all-reduced sum over ranks (identical on every rank). */
+int sosba_accumulate(sosba_t *h, double *HA, double *bA, double *HL, double *bL, double *Hsc,
+                     double *bsc, int32_t *resInA, int32_t *resInL);
+/* EFPoint accumulators after sosba_accumulate (any may be NULL): Hdd_accAF,bd_accAF,Hcd_accAF[4],
+ * Hdd_accLF,bd_accLF,Hcd_accLF[4],HdiF,bdSumF,idepth_hessian */
+int sosba_points_get_acc(sosba_t *h, float *HddA, float *bdA, float *HcdA, float *HddL, float *bdL,
+                         float *HcdL, float *HdiF, float *bdSumF);
+
+/* ---- a10/a11: EnergyFunctional::solveSystemF (EnergyFunctional.cpp:1029-1184), IMU off -------- */
+/* accumulate A/L/SC, add marginalisation prior (HM,bM of dim D, may be NULL = 0), damp, solve,
+ * resubstitute.  x: D doubles (= lastX).  H_final/b_final: optional copies of the solved system. */
+int sosba_solve_system(sosba_t *h, const double *HM, const double *bM, double *x, double *H_final,
+                       double *b_final);
+/* EnergyFunctional::resubstituteF_MT (EnergyFunctional.cpp:496-551) with a caller-provided x. */
+int sosba_resubstitute(sosba_t *h, const double *x, float *point_step /*[P] or NULL*/);
+
+/* ---- marginalisation of points: EnergyFunctional::marginalizePointsF (:891-936) --------------- */
+/* addPoint<2> + SC addPoint(false) over the listed points; H,b = M - Msc (not yet * margWeightFac). */
+int sosba_marginalize_points(sosba_t *h, const int32_t *point_ids, int32_t n, double *H, double *b,
+                             int32_t *resInM);
+
+/* ---- a14/a15: CoarseTracker::calcResPose / calcGSSSEPose (CoarseTracker.cpp:612-764, 554-610) -- */
+/* makeK (ScaleOptimizer.cpp:95-118): per-level intrinsics from level-0 fx,fy,cx,cy. */
+int sosba_tracker_make_k(sosba_t *h, const float calib[4]);
+/* pc_u/pc_v/pc_idepth/pc_color of one level (output of makeCoarseDepthL0, CoarseTracker.cpp:56-230) */
+int sosba_tracker_set_ref(sosba_t *h, int32_t lvl, int32_t n, const float *pc_u, const float *pc_v,
+                          const float *pc_idepth, const float *pc_color);
+/* refToNew: row-major 3x4 [R|t] double; affLL = AffLight::fromToVecExposure(...) as float[2].
+ * out6 = Vec6 {E, numTermsInE, flowT, 0, flowRT, numSaturated/numTermsInE};
+ * counts = {numTermsInE, numTermsInWarped (unpadded), numSaturated}. */
+int sosba_tracker_calc_res_pose(sosba_t *h, int32_t lvl, int32_t new_frame_slot,
+                                const double refToNew[12], const float affLL[2], float cutoff_th,
+                                double out6[6], int32_t counts[3]);
+/* Uses the warped buffers of the last calc_res_pose at this level.  a = affLL[0], b0 =
+ * lastRef_aff_g2l.b.  H: 8x8 row-major, b: 8 — already divided by n and SCALE_*-scaled. */
+int sosba_tracker_calc_gs_pose(sosba_t *h, int32_t lvl, float a, float b0, double H[64], double b[8]);
+
+/* ---- a17: ScaleOptimizer::calcResScale / calcGSSSEScale (ScaleOptimizer.cpp:273-437, 232-271) -- */
+/* T10: tfmF0ToF1 row-major 3x4; K1: fx1,fy1,cx1,cy1 of camera 1 (level 0). */
+int sosba_scale_set_stereo(sosba_t *h, const double T10[12], const float K1[4]);
+int sosba_scale_calc_res(sosba_t *h, int32_t lvl, int32_t stereo_slot, float scale, float cutoff_th,
+                         double out6[6], int32_t counts[3]);
+int sosba_scale_calc_gs(sosba_t *h, int32_t lvl, float scale, float *H, float *b);
+
+/* ---- a4/a10/a11 composed: the Gauss-Newton loop body of FullSystem::optimize ------------------ */
+/* Frame state as FullSystem keeps it (HessianBlocks.h:136-424). */
+typedef struct sosba_frame_state {
+  double camToWorld_evalPT[12]; /* row-major 3x4 */
+  double state[10];             /* unscaled; [8],[9] unused */
+  double state_zero[10];
+  float ab_exposure;
+  float frame_energy_th;
+  int32_t frame_id;             /* FrameHessian::frameID (0 => gauge priors) */
+  int32_t slot;
+} sosba_frame_state;
+
+typedef struct sosba_ba_problem {
+  int32_t nf;
+  int32_t reserved0;
+  sosba_frame_state *frames;    /* [nf] in/out */
+  double calib_value[4];        /* CalibHessian::value (unscaled), in/out */
+  double calib_value_zero[4];
+  sosba_points points;          /* in: initial idepth/idepth_zero; deltaF/priorF as given */
+  sosba_residuals residuals;
+  const double *HM;             /* [D*D] or NULL */
+  const double *bM;             /* [D] or NULL */
+  float *idepth_out;            /* [P] optimised idepth (may be NULL) */
+} sosba_ba_problem;
+
+typedef struct sosba_optimize_out {
+  int32_t iterations;           /* GN iterations actually run */
+  int32_t res_in_a;             /* ef->resInA of the last solve */
+  double energy_initial;        /* linearizeAll(false) before the loop */
+  double energy_final;          /* linearizeAll(true) */
+  float rmse;                   /* sqrt(energy_final / (patternNum * resInA)) */
+  int32_t n_removed;
+  double last_x_norm;
+  int32_t reserved0, reserved1;
+} sosba_optimize_out;
+
+/* FullSystem::optimize(mnumOptIts) (FullSystemOptimize.cpp:305-489) without IMU: resetOOB,
+ * linearizeAll(false), applyRes, then per iteration backupState / solveSystem / doStepFromBackup /
+ * linearizeAll(false) / applyRes / break test, then the new evalPT for the newest frame and
+ * linearizeAll(true).  Host buffers in, host buffers out. */
+int sosba_optimize(sosba_t *h, sosba_ba_problem *prob, int32_t max_iterations, sosba_optimize_out *out);
+
+/* The same loop with the problem already resident on the device: uploads `prob` once ... */
+int sosba_ba_upload(sosba_t *h, const sosba_ba_problem *prob);
+/* ... and runs `n` loop bodies (solveSystem + doStepFromBackup + linearizeAll(false) + applyRes)
+ * without touching host problem buffers.  n_res_linearized: residuals linearized per body. */
+int sosba_ba_iterate(sosba_t *h, int32_t n, int32_t *n_res_linearized);
+int sosba_ba_download(sosba_t *h, sosba_ba_problem *prob);
+
+/* ---- multi-GPU: points shard across ranks, one all-reduce of [H,b] per GN iteration ----------- */
+/* 128-byte NCCL unique id (rank 0 creates, caller broadcasts, every rank inits). */
+int sosba_comm_unique_id(uint8_t id[128]);
+int sosba_comm_init(sosba_t *h, const uint8_t id[128], int32_t rank, int32_t world);
+int sosba_comm_destroy(sosba_t *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOSBA_H_ */

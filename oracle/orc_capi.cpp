@@ -1,0 +1,384 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.h header).  PARITY UNPINNED.
+//
+// orc_capi.cpp: the oracle behind the same C signatures as include/sosba.h with an `orc_` prefix, so
+// the parity tests drive product and oracle through one Python binding.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "orc_core.h"
+#include "orc_host.h"
+
+using namespace orc;
+
+struct orc_handle {
+  Oracle o;
+  BAState ba;
+  bool ba_loaded = false;
+  std::vector<double> HM, bM;
+};
+
+#define ORC_API extern "C" __attribute__((visibility("default")))
+
+ORC_API void orc_config_default(sosba_config *c, int32_t w, int32_t h) {
+  memset(c, 0, sizeof(*c));
+  c->w = w; c->h = h; c->pyr_levels = 0; c->max_frames = 16; c->num_threads = 1;
+  c->gamma_weights_pixel_select = 1; c->min_opt_iterations = 1;
+  c->huber_th = 9; c->outlier_th_sum_component = 50 * 50;
+  c->affine_opt_mode_a = 0; c->affine_opt_mode_b = 0;  // settingsDefault(mode=1), main.cpp:75-80
+  c->coarse_cutoff_th = 20; c->idepth_fix_prior = 50 * 50; c->idepth_fix_prior_marg_fac = 600 * 600;
+  c->frame_energy_th_const_weight = 0.5f; c->frame_energy_th_n = 0.7f; c->frame_energy_th_fac_median = 1.5f;
+  c->overall_energy_th_weight = 1; c->initial_calib_hessian = 5e9f;
+  c->initial_rot_prior = 1e11f; c->initial_trans_prior = 1e10f; c->initial_aff_a_prior = 1e14f; c->initial_aff_b_prior = 1e14f;
+  c->marg_weight_fac = 0.5f * 0.5f; c->th_opt_iterations = 1.2f;
+}
+
+ORC_API int orc_create(const sosba_config *cfg, int32_t /*device*/, orc_handle **out) {
+  if (!cfg || !out || cfg->w <= 0 || cfg->h <= 0) return SOSBA_E_ARG;
+  orc_handle *h = new (std::nothrow) orc_handle();
+  if (!h) return SOSBA_E_ARG;
+  Oracle &o = h->o;
+  o.cfg = *cfg;
+  // setGlobalCalib (globalCalib.cpp:39-49)
+  int wlvl = cfg->w, hlvl = cfg->h, lv = 1;
+  while (wlvl % 2 == 0 && hlvl % 2 == 0 && wlvl * hlvl > 5000 && lv < SOSBA_MAX_LEVELS) { wlvl /= 2; hlvl /= 2; lv++; }
+  o.levels = cfg->pyr_levels > 0 ? cfg->pyr_levels : lv;
+  for (int l = 0; l < o.levels; l++) { o.wl[l] = cfg->w >> l; o.hl[l] = cfg->h >> l; }
+  o.wM3G = cfg->w - 3; o.hM3G = cfg->h - 3;
+  o.slots.resize(cfg->max_frames > 0 ? cfg->max_frames : 16);
+  o.T = cfg->num_threads > 1 ? cfg->num_threads : 1;
+  o.MT = cfg->num_threads > 1;
+  if (o.MT) o.red.reset(new ThreadReduce(o.T));
+  o.accA.resize(o.T); o.accL.resize(o.T); o.nresA.assign(o.T, 0); o.nresL.assign(o.T, 0);
+  o.accE.resize(o.T); o.accEB.resize(o.T); o.accD.resize(o.T); o.accHcc.resize(o.T); o.accbc.resize(o.T);
+  *out = h;
+  return SOSBA_OK;
+}
+ORC_API void orc_destroy(orc_handle *h) { delete h; }
+ORC_API const char *orc_last_error(void) { return ""; }
+ORC_API int32_t orc_pyr_levels(const orc_handle *h) { return h->o.levels; }
+
+ORC_API int orc_frame_make_images(orc_handle *h, int32_t slot, const float *color, const float *B) {
+  if (slot < 0 || slot >= (int)h->o.slots.size() || !color) return SOSBA_E_ARG;
+  make_images(h->o, slot, color, B);
+  return SOSBA_OK;
+}
+ORC_API int orc_frame_get_level(orc_handle *h, int32_t slot, int32_t lvl, float *dI3, float *absg) {
+  if (slot < 0 || slot >= (int)h->o.slots.size() || lvl < 0 || lvl >= h->o.levels || !h->o.slots[slot].valid) return SOSBA_E_ARG;
+  const Level &L = h->o.slots[slot].lvl[lvl];
+  if (dI3) memcpy(dI3, L.dI.data(), L.dI.size() * sizeof(float));
+  if (absg) memcpy(absg, L.absg.data(), L.absg.size() * sizeof(float));
+  return SOSBA_OK;
+}
+
+static int window_apply(Oracle &o, const sosba_window *w, bool full) {
+  const int nf = w->nf;
+  if (nf <= 0) return SOSBA_E_ARG;
+  if (!full && nf != o.nf) return SOSBA_E_STATE;
+  o.nf = nf;
+  if (full) {
+    o.frame_slot.assign(w->frame_slot, w->frame_slot + nf);
+    o.adHost.assign(w->adHost, w->adHost + (size_t)nf * nf * 64);
+    o.adTarget.assign(w->adTarget, w->adTarget + (size_t)nf * nf * 64);
+    o.adHostF.resize(o.adHost.size()); o.adTargetF.resize(o.adTarget.size());
+    for (size_t i = 0; i < o.adHost.size(); i++) { o.adHostF[i] = (float)o.adHost[i]; o.adTargetF[i] = (float)o.adTarget[i]; }
+    for (int i = 0; i < 4; i++) o.cPrior[i] = w->cPrior[i];
+    o.fprior.assign(w->frame_prior, w->frame_prior + (size_t)nf * 8);
+  }
+  o.pre.resize((size_t)nf * nf);
+  for (int i = 0; i < nf * nf; i++) {
+    const float *p = w->precalc + (size_t)i * SOSBA_PRECALC_FLOATS;
+    Precalc &pc = o.pre[i];
+    memcpy(pc.RTll_0, p + SOSBA_PC_RTLL0, 9 * sizeof(float)); memcpy(pc.tTll_0, p + SOSBA_PC_TTLL0, 3 * sizeof(float));
+    memcpy(pc.KRKi, p + SOSBA_PC_KRKI, 9 * sizeof(float)); memcpy(pc.Kt, p + SOSBA_PC_KT, 3 * sizeof(float));
+    pc.aff[0] = p[SOSBA_PC_AFF]; pc.aff[1] = p[SOSBA_PC_AFF + 1]; pc.b0 = p[SOSBA_PC_B0]; pc.dist = p[SOSBA_PC_DIST];
+  }
+  o.adHTdeltaF.assign(w->adHTdeltaF, w->adHTdeltaF + (size_t)nf * nf * 8);
+  o.frameEnergyTH.assign(w->frame_energy_th, w->frame_energy_th + nf);
+  o.fxl = w->calib[0]; o.fyl = w->calib[1]; o.cxl = w->calib[2]; o.cyl = w->calib[3];
+  o.fxli = 1.0f / o.fxl; o.fyli = 1.0f / o.fyl;  // CalibHessian::setValue, HessianBlocks.h:495-496
+  for (int i = 0; i < 4; i++) o.cDeltaF[i] = w->cDeltaF[i];
+  o.fdelta_prior.assign(w->frame_delta_prior, w->frame_delta_prior + (size_t)nf * 8);
+  o.fdelta.assign(w->frame_delta, w->frame_delta + (size_t)nf * 8);
+  return SOSBA_OK;
+}
+ORC_API int orc_window_set(orc_handle *h, const sosba_window *w) { return window_apply(h->o, w, true); }
+ORC_API int orc_window_update(orc_handle *h, const sosba_window *w) { return window_apply(h->o, w, false); }
+
+ORC_API int orc_points_set(orc_handle *h, const sosba_points *p) {
+  Oracle &o = h->o;
+  o.pts.assign(p->n, Pt());
+  for (int i = 0; i < p->n; i++) {
+    Pt &q = o.pts[i];
+    memset(&q, 0, sizeof(q));
+    q.u = p->u[i]; q.v = p->v[i];
+    q.idepth = p->idepth[i]; q.idepth_scaled = SCALE_IDEPTH * q.idepth;
+    q.idepth_zero = p->idepth_zero[i]; q.idepth_zero_scaled = SCALE_IDEPTH * q.idepth_zero;
+    memcpy(q.color, p->color + 8 * (size_t)i, 8 * sizeof(float)); memcpy(q.weights, p->weights + 8 * (size_t)i, 8 * sizeof(float));
+    q.host = p->host[i]; q.priorF = p->priorF ? p->priorF[i] : 0; q.deltaF = p->deltaF ? p->deltaF[i] : 0;
+    q.res_begin = q.res_end = 0;
+  }
+  return SOSBA_OK;
+}
+ORC_API int orc_points_update(orc_handle *h, const float *idepth, const float *idepth_zero, const float *deltaF) {
+  Oracle &o = h->o;
+  for (size_t i = 0; i < o.pts.size(); i++) {
+    Pt &q = o.pts[i];
+    if (idepth) { q.idepth = idepth[i]; q.idepth_scaled = SCALE_IDEPTH * q.idepth; }
+    if (idepth_zero) { q.idepth_zero = idepth_zero[i]; q.idepth_zero_scaled = SCALE_IDEPTH * q.idepth_zero; }
+    if (deltaF) q.deltaF = deltaF[i];
+  }
+  return SOSBA_OK;
+}
+ORC_API int orc_residuals_set(orc_handle *h, const sosba_residuals *r) {
+  Oracle &o = h->o;
+  o.res.assign(r->n, Res());
+  int prev = -1;
+  for (auto &p : o.pts) p.res_begin = p.res_end = 0;
+  for (int i = 0; i < r->n; i++) {
+    Res &q = o.res[i];
+    memset(&q, 0, sizeof(q));
+    q.point = r->point[i];
+    if (q.point < prev || q.point >= (int)o.pts.size()) return SOSBA_E_ARG;
+    if (q.point != prev) { o.pts[q.point].res_begin = i; prev = q.point; }
+    o.pts[q.point].res_end = i + 1;
+    q.host = o.pts[q.point].host; q.target = r->target[i];
+    q.state_state = r->state ? r->state[i] : SOSBA_RES_IN;
+    q.state_NewState = SOSBA_RES_OUTLIER;
+    q.state_energy = r->state_energy ? r->state_energy[i] : 0; q.state_NewEnergy = q.state_energy; q.state_NewEnergyWithOutlier = -1;
+    q.isLinearized = r->is_linearized ? r->is_linearized[i] != 0 : false;
+    q.isActive = r->is_active ? r->is_active[i] != 0 : false;
+    q.isNew = r->is_new ? r->is_new[i] != 0 : true;
+    q.dropped = false; q.sel = 0;
+  }
+  // empty points: res_begin == res_end
+  o.activeResiduals.clear();
+  for (int i = 0; i < r->n; i++) if (!o.res[i].isLinearized) o.activeResiduals.push_back(i);
+  return SOSBA_OK;
+}
+
+ORC_API int orc_reset_oob(orc_handle *h) {
+  Oracle &o = h->o;
+  o.activeResiduals.clear();
+  for (int i = 0; i < (int)o.res.size(); i++) {
+    Res &r = o.res[i];
+    if (r.dropped || r.isLinearized) continue;
+    o.activeResiduals.push_back(i);
+    r.state_NewEnergy = r.state_energy = 0; r.state_NewState = SOSBA_RES_OUTLIER; r.state_state = SOSBA_RES_IN;  // Residuals.h:81-86
+  }
+  return SOSBA_OK;
+}
+ORC_API int orc_linearize_all(orc_handle *h, int32_t fix, sosba_linearize_out *out) { linearizeAll(h->o, fix != 0, out); return SOSBA_OK; }
+ORC_API int orc_apply_res(orc_handle *h) {
+  Oracle &o = h->o;
+  auto fn = [&](int a, int b) { for (int k = a; k < b; k++) applyRes(o.res[o.activeResiduals[k]], true); };
+  if (o.MT) o.red->reduce([&](int a, int b, Stats10 *, int) { fn(a, b); }, 0, (int)o.activeResiduals.size(), 50);
+  else fn(0, (int)o.activeResiduals.size());
+  return SOSBA_OK;
+}
+ORC_API int orc_fix_linearization(orc_handle *h, const int32_t *ids, int32_t n) {
+  for (int i = 0; i < n; i++) { if (ids[i] < 0 || ids[i] >= (int)h->o.res.size()) return SOSBA_E_ARG; fixLinearizationF(h->o, h->o.res[ids[i]]); }
+  return SOSBA_OK;
+}
+
+ORC_API int orc_residuals_get_state(orc_handle *h, uint8_t *state, uint8_t *new_state, float *energy, float *new_energy, float *new_energy_wo,
+                                    uint8_t *is_active, uint8_t *is_linearized) {
+  Oracle &o = h->o;
+  for (size_t i = 0; i < o.res.size(); i++) {
+    const Res &r = o.res[i];
+    if (state) state[i] = (uint8_t)r.state_state;
+    if (new_state) new_state[i] = (uint8_t)r.state_NewState;
+    if (energy) energy[i] = (float)r.state_energy;
+    if (new_energy) new_energy[i] = (float)r.state_NewEnergy;
+    if (new_energy_wo) new_energy_wo[i] = (float)r.state_NewEnergyWithOutlier;
+    if (is_active) is_active[i] = r.isActive;
+    if (is_linearized) is_linearized[i] = r.isLinearized;
+  }
+  return SOSBA_OK;
+}
+static void dumpJ(const RawJ &J, float *o) {
+  int k = 0;
+  for (int i = 0; i < 8; i++) o[k++] = J.resF[i];
+  for (int a = 0; a < 2; a++) for (int i = 0; i < 6; i++) o[k++] = J.Jpdxi[a][i];
+  for (int a = 0; a < 2; a++) for (int i = 0; i < 4; i++) o[k++] = J.Jpdc[a][i];
+  o[k++] = J.Jpdd[0]; o[k++] = J.Jpdd[1];
+  for (int a = 0; a < 2; a++) for (int i = 0; i < 8; i++) o[k++] = J.JIdx[a][i];
+  for (int a = 0; a < 2; a++) for (int i = 0; i < 8; i++) o[k++] = J.JabF[a][i];
+  for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) o[k++] = J.JIdx2[a][b];
+  for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) o[k++] = J.JabJIdx[a][b];
+  for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) o[k++] = J.Jab2[a][b];
+}
+ORC_API int orc_residuals_get_jacobians(orc_handle *h, int32_t committed, float *J) {
+  Oracle &o = h->o;
+  for (size_t i = 0; i < o.res.size(); i++) dumpJ(committed ? o.res[i].Jef() : o.res[i].Jdata(), J + SOSBA_J_FLOATS * i);
+  return SOSBA_OK;
+}
+ORC_API int orc_residuals_get_aux(orc_handle *h, float *JpJdF, float *rtz, float *proj, float *center) {
+  Oracle &o = h->o;
+  for (size_t i = 0; i < o.res.size(); i++) {
+    const Res &r = o.res[i];
+    if (JpJdF) memcpy(JpJdF + 8 * i, r.JpJdF, 8 * sizeof(float));
+    if (rtz) memcpy(rtz + 8 * i, r.res_toZeroF, 8 * sizeof(float));
+    if (proj) memcpy(proj + 16 * i, r.projectedTo, 16 * sizeof(float));
+    if (center) memcpy(center + 3 * i, r.centerProjectedTo, 3 * sizeof(float));
+  }
+  return SOSBA_OK;
+}
+ORC_API int orc_points_get_stats(orc_handle *h, float *mrb, int32_t *ngr) {
+  Oracle &o = h->o;
+  for (size_t i = 0; i < o.pts.size(); i++) { if (mrb) mrb[i] = o.pts[i].maxRelBaseline; if (ngr) ngr[i] = o.pts[i].numGoodResiduals; }
+  return SOSBA_OK;
+}
+
+ORC_API int orc_accumulate(orc_handle *h, double *HA, double *bA, double *HL, double *bL, double *Hsc, double *bsc, int32_t *resInA, int32_t *resInL) {
+  Oracle &o = h->o;
+  const int D = CPARS + 8 * o.nf;
+  std::vector<double> H((size_t)D * D), b(D);
+  accumulateAF(o, H.data(), b.data());
+  if (HA) memcpy(HA, H.data(), sizeof(double) * D * D);
+  if (bA) memcpy(bA, b.data(), sizeof(double) * D);
+  accumulateLF(o, H.data(), b.data());
+  if (HL) memcpy(HL, H.data(), sizeof(double) * D * D);
+  if (bL) memcpy(bL, b.data(), sizeof(double) * D);
+  accumulateSCF(o, H.data(), b.data());
+  if (Hsc) memcpy(Hsc, H.data(), sizeof(double) * D * D);
+  if (bsc) memcpy(bsc, b.data(), sizeof(double) * D);
+  if (resInA) *resInA = o.resInA;
+  if (resInL) *resInL = o.resInL;
+  return SOSBA_OK;
+}
+ORC_API int orc_points_get_acc(orc_handle *h, float *HddA, float *bdA, float *HcdA, float *HddL, float *bdL, float *HcdL, float *HdiF, float *bdSumF) {
+  Oracle &o = h->o;
+  for (size_t i = 0; i < o.pts.size(); i++) {
+    const Pt &p = o.pts[i];
+    if (HddA) HddA[i] = p.Hdd_accAF;
+    if (bdA) bdA[i] = p.bd_accAF;
+    if (HcdA) memcpy(HcdA + 4 * i, p.Hcd_accAF, 4 * sizeof(float));
+    if (HddL) HddL[i] = p.Hdd_accLF;
+    if (bdL) bdL[i] = p.bd_accLF;
+    if (HcdL) memcpy(HcdL + 4 * i, p.Hcd_accLF, 4 * sizeof(float));
+    if (HdiF) HdiF[i] = p.HdiF;
+    if (bdSumF) bdSumF[i] = p.bdSumF;
+  }
+  return SOSBA_OK;
+}
+ORC_API int orc_solve_system(orc_handle *h, const double *HM, const double *bM, double *x, double *Hf, double *bf) {
+  solveSystemF(h->o, HM, bM, x, Hf, bf);
+  return SOSBA_OK;
+}
+ORC_API int orc_resubstitute(orc_handle *h, const double *x, float *step) {
+  resubstituteF(h->o, x);
+  if (step) for (size_t i = 0; i < h->o.pts.size(); i++) step[i] = h->o.pts[i].step;
+  return SOSBA_OK;
+}
+ORC_API int orc_marginalize_points(orc_handle *h, const int32_t *ids, int32_t n, double *H, double *b, int32_t *resInM) {
+  int r = 0;
+  marginalizePoints(h->o, ids, n, H, b, &r);
+  if (resInM) *resInM = r;
+  return SOSBA_OK;
+}
+
+ORC_API int orc_tracker_make_k(orc_handle *h, const float calib[4]) { tracker_makeK(h->o, calib); return SOSBA_OK; }
+ORC_API int orc_tracker_set_ref(orc_handle *h, int32_t lvl, int32_t n, const float *u, const float *v, const float *id, const float *c) {
+  if (lvl < 0 || lvl >= h->o.levels) return SOSBA_E_ARG;
+  h->o.pc_u[lvl].assign(u, u + n); h->o.pc_v[lvl].assign(v, v + n); h->o.pc_idepth[lvl].assign(id, id + n); h->o.pc_color[lvl].assign(c, c + n);
+  return SOSBA_OK;
+}
+ORC_API int orc_tracker_calc_res_pose(orc_handle *h, int32_t lvl, int32_t slot, const double refToNew[12], const float affLL[2], float cutoff,
+                                      double out6[6], int32_t counts[3]) {
+  tracker_calcResPose(h->o, lvl, slot, refToNew, affLL, cutoff, out6, counts);
+  return SOSBA_OK;
+}
+ORC_API int orc_tracker_calc_gs_pose(orc_handle *h, int32_t lvl, float a, float b0, double H[64], double b[8]) {
+  tracker_calcGSSSEPose(h->o, lvl, a, b0, H, b);
+  return SOSBA_OK;
+}
+ORC_API int orc_scale_set_stereo(orc_handle *h, const double T10[12], const float K1[4]) {
+  Oracle &o = h->o;
+  o.tfmF0ToF1 = SE3::from_rowmajor34(T10);
+  o.fx1[0] = K1[0]; o.fy1[0] = K1[1]; o.cx1[0] = K1[2]; o.cy1[0] = K1[3];
+  for (int level = 1; level < o.levels; ++level) {  // ScaleOptimizer.cpp:72-77
+    o.fx1[level] = o.fx1[level - 1] * 0.5; o.fy1[level] = o.fy1[level - 1] * 0.5;
+    o.cx1[level] = (o.cx1[0] + 0.5) / ((int)1 << level) - 0.5; o.cy1[level] = (o.cy1[0] + 0.5) / ((int)1 << level) - 0.5;
+  }
+  return SOSBA_OK;
+}
+ORC_API int orc_scale_calc_res(orc_handle *h, int32_t lvl, int32_t slot, float scale, float cutoff, double out6[6], int32_t counts[3]) {
+  scale_calcRes(h->o, lvl, slot, scale, cutoff, out6, counts);
+  return SOSBA_OK;
+}
+ORC_API int orc_scale_calc_gs(orc_handle *h, int32_t lvl, float scale, float *H, float *b) { scale_calcGSSSE(h->o, lvl, scale, H, b); return SOSBA_OK; }
+
+// ---- composed GN loop ---------------------------------------------------------------------------
+ORC_API int orc_ba_upload(orc_handle *h, const sosba_ba_problem *prob) {
+  int rc = orc_points_set(h, &prob->points);
+  if (rc) return rc;
+  rc = orc_residuals_set(h, &prob->residuals);
+  if (rc) return rc;
+  Oracle &o = h->o;
+  o.nf = prob->nf;
+  o.frame_slot.resize(prob->nf);
+  for (int i = 0; i < prob->nf; i++) o.frame_slot[i] = prob->frames[i].slot;
+  h->ba.load(o, prob);
+  const int D = CPARS + 8 * prob->nf;
+  if (prob->HM && prob->bM) { h->HM.assign(prob->HM, prob->HM + (size_t)D * D); h->bM.assign(prob->bM, prob->bM + D); }
+  else { h->HM.clear(); h->bM.clear(); }
+  h->ba.setAdjoints(o);
+  h->ba.setPrecalcValues(o);
+  h->ba_loaded = true;
+  return SOSBA_OK;
+}
+ORC_API int orc_optimize(orc_handle *h, sosba_ba_problem *prob, int32_t max_it, sosba_optimize_out *out) {
+  int rc = orc_ba_upload(h, prob);
+  if (rc) return rc;
+  h->ba.optimize(h->o, h->HM.empty() ? nullptr : h->HM.data(), h->bM.empty() ? nullptr : h->bM.data(), max_it, out);
+  h->ba.store(h->o, prob);
+  return SOSBA_OK;
+}
+ORC_API int orc_ba_iterate(orc_handle *h, int32_t n, int32_t *n_res) {
+  if (!h->ba_loaded) return SOSBA_E_STATE;
+  sosba_linearize_out lo;
+  for (int i = 0; i < n; i++) h->ba.iterate(h->o, h->HM.empty() ? nullptr : h->HM.data(), h->bM.empty() ? nullptr : h->bM.data(), &lo);
+  if (n_res) *n_res = (int)h->o.activeResiduals.size();
+  return SOSBA_OK;
+}
+ORC_API int orc_ba_download(orc_handle *h, sosba_ba_problem *prob) {
+  if (!h->ba_loaded) return SOSBA_E_STATE;
+  h->ba.store(h->o, prob);
+  return SOSBA_OK;
+}
+
+// host-side table helpers exposed for the tests (restated FrameFramePrecalc::set / setAdjointsF / setDeltaF)
+ORC_API int orc_host_tables(orc_handle *h, const sosba_ba_problem *prob, float *precalc, double *adHost, double *adTarget, float *adHTdeltaF) {
+  Oracle &o = h->o;
+  BAState ba;
+  ba.load(o, prob);
+  const int nf = prob->nf;
+  std::vector<double> aH, aT;
+  set_adjoints(ba.frames, aH, aT);
+  std::vector<float> aHF(aH.size()), aTF(aT.size()), dF;
+  for (size_t i = 0; i < aH.size(); i++) { aHF[i] = (float)aH[i]; aTF[i] = (float)aT[i]; }
+  set_delta(ba.frames, aHF, aTF, dF);
+  if (adHost) memcpy(adHost, aH.data(), aH.size() * sizeof(double));
+  if (adTarget) memcpy(adTarget, aT.data(), aT.size() * sizeof(double));
+  if (adHTdeltaF) memcpy(adHTdeltaF, dF.data(), dF.size() * sizeof(float));
+  if (precalc) {
+    memset(precalc, 0, sizeof(float) * nf * nf * SOSBA_PRECALC_FLOATS);
+    for (int hh = 0; hh < nf; hh++)
+      for (int t = 0; t < nf; t++) {
+        Precalc pc;
+        precalc_set(ba.frames[hh], ba.frames[t], ba.calib, pc);
+        float *p = precalc + (size_t)(hh * nf + t) * SOSBA_PRECALC_FLOATS;
+        memcpy(p + SOSBA_PC_RTLL0, pc.RTll_0, 9 * sizeof(float)); memcpy(p + SOSBA_PC_TTLL0, pc.tTll_0, 3 * sizeof(float));
+        memcpy(p + SOSBA_PC_KRKI, pc.KRKi, 9 * sizeof(float)); memcpy(p + SOSBA_PC_KT, pc.Kt, 3 * sizeof(float));
+        p[SOSBA_PC_AFF] = pc.aff[0]; p[SOSBA_PC_AFF + 1] = pc.aff[1]; p[SOSBA_PC_B0] = pc.b0; p[SOSBA_PC_DIST] = pc.dist;
+      }
+  }
+  return SOSBA_OK;
+}
+
+// SE3 helpers for the Sophus-property tests (tests/test_oracle_se3.py)
+ORC_API void orc_se3_exp(const double a[6], double T[12]) { se3_exp(a).to_rowmajor34(T); }
+ORC_API void orc_se3_log(const double T[12], double a[6]) { se3_log(SE3::from_rowmajor34(T), a); }
+ORC_API void orc_se3_adj(const double T[12], double A[36]) { se3_adj(SE3::from_rowmajor34(T), A); }
+ORC_API void orc_ldlt_solve(const double *A, const double *b, double *x, int32_t n) { ldlt_solve(A, b, x, n); }

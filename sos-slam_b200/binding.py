@@ -1,0 +1,469 @@
+"""ctypes binding of the C ABI in include/sosba.h.
+
+`Lib(path, prefix)` binds one shared library exporting `<prefix>_*` with the sosba.h signatures; the
+product is `prefix="sosba"` (libsosba.so, CUDA).  The parity tests bind the CPU oracle with the same
+class (`prefix="orc"`), which is why nothing in here names the oracle.  numpy arrays in, numpy arrays
+out; every call checks the status code and raises `SosbaError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PRECALC_FLOATS = 32
+J_FLOATS = 74
+PC_RTLL0, PC_TTLL0, PC_KRKI, PC_KT, PC_AFF, PC_B0, PC_DIST = 0, 9, 12, 21, 24, 26, 27
+RES_IN, RES_OOB, RES_OUTLIER = 0, 1, 2
+
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+i32p = C.POINTER(C.c_int32)
+u8p = C.POINTER(C.c_uint8)
+
+
+class SosbaError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("w", C.c_int32), ("h", C.c_int32), ("pyr_levels", C.c_int32), ("max_frames", C.c_int32),
+                ("num_threads", C.c_int32), ("gamma_weights_pixel_select", C.c_int32),
+                ("min_opt_iterations", C.c_int32), ("reserved0", C.c_int32),
+                ("huber_th", C.c_float), ("outlier_th_sum_component", C.c_float),
+                ("affine_opt_mode_a", C.c_float), ("affine_opt_mode_b", C.c_float),
+                ("coarse_cutoff_th", C.c_float), ("idepth_fix_prior", C.c_float),
+                ("idepth_fix_prior_marg_fac", C.c_float), ("frame_energy_th_const_weight", C.c_float),
+                ("frame_energy_th_n", C.c_float), ("frame_energy_th_fac_median", C.c_float),
+                ("overall_energy_th_weight", C.c_float), ("initial_calib_hessian", C.c_float),
+                ("initial_rot_prior", C.c_float), ("initial_trans_prior", C.c_float),
+                ("initial_aff_a_prior", C.c_float), ("initial_aff_b_prior", C.c_float),
+                ("marg_weight_fac", C.c_float), ("th_opt_iterations", C.c_float)]
+
+
+class Window(C.Structure):
+    _fields_ = [("nf", C.c_int32), ("reserved0", C.c_int32), ("frame_slot", i32p), ("precalc", f32p),
+                ("adHost", f64p), ("adTarget", f64p), ("adHTdeltaF", f32p), ("frame_energy_th", f32p),
+                ("calib", C.c_float * 4), ("cDeltaF", C.c_float * 4), ("cPrior", C.c_double * 4),
+                ("frame_prior", f64p), ("frame_delta_prior", f64p), ("frame_delta", f64p)]
+
+
+class Points(C.Structure):
+    _fields_ = [("n", C.c_int32), ("reserved0", C.c_int32), ("u", f32p), ("v", f32p), ("idepth", f32p),
+                ("idepth_zero", f32p), ("color", f32p), ("weights", f32p), ("host", i32p), ("priorF", f32p),
+                ("deltaF", f32p)]
+
+
+class Residuals(C.Structure):
+    _fields_ = [("n", C.c_int32), ("reserved0", C.c_int32), ("point", i32p), ("target", i32p), ("state", u8p),
+                ("is_linearized", u8p), ("is_active", u8p), ("is_new", u8p), ("state_energy", f32p)]
+
+
+class LinearizeOut(C.Structure):
+    _fields_ = [("energy", C.c_double), ("new_frame_energy_th", C.c_float), ("n_in", C.c_int32),
+                ("n_oob", C.c_int32), ("n_outlier", C.c_int32), ("n_removed", C.c_int32), ("reserved0", C.c_int32)]
+
+
+class FrameState(C.Structure):
+    _fields_ = [("camToWorld_evalPT", C.c_double * 12), ("state", C.c_double * 10), ("state_zero", C.c_double * 10),
+                ("ab_exposure", C.c_float), ("frame_energy_th", C.c_float), ("frame_id", C.c_int32), ("slot", C.c_int32)]
+
+
+class BAProblem(C.Structure):
+    _fields_ = [("nf", C.c_int32), ("reserved0", C.c_int32), ("frames", C.POINTER(FrameState)),
+                ("calib_value", C.c_double * 4), ("calib_value_zero", C.c_double * 4), ("points", Points),
+                ("residuals", Residuals), ("HM", f64p), ("bM", f64p), ("idepth_out", f32p)]
+
+
+class OptimizeOut(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("res_in_a", C.c_int32), ("energy_initial", C.c_double),
+                ("energy_final", C.c_double), ("rmse", C.c_float), ("n_removed", C.c_int32),
+                ("last_x_norm", C.c_double), ("reserved0", C.c_int32), ("reserved1", C.c_int32)]
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _p(a, typ):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+class Lib:
+    """One loaded shared library exporting `<prefix>_*`."""
+
+    def __init__(self, path: str, prefix: str = "sosba"):
+        if not os.path.exists(path):
+            raise SosbaError(f"{path} is missing - run `python -c 'import __graft_entry__ as g; g.build()'`")
+        self.path = path
+        self.prefix = prefix
+        self.dll = C.CDLL(path, mode=C.RTLD_GLOBAL if prefix == "sosba" else C.RTLD_LOCAL)
+        self._bind()
+
+    def f(self, name):
+        return getattr(self.dll, f"{self.prefix}_{name}")
+
+    def has(self, name):
+        return hasattr(self.dll, f"{self.prefix}_{name}")
+
+    def _bind(self):
+        self.f("last_error").restype = C.c_char_p
+        self.f("config_default").restype = None
+        for n in ("create", "frame_make_images", "frame_get_level", "window_set", "window_update", "points_set",
+                  "points_update", "residuals_set", "reset_oob", "linearize_all", "apply_res", "fix_linearization",
+                  "residuals_get_state", "residuals_get_jacobians", "residuals_get_aux", "points_get_stats",
+                  "accumulate", "points_get_acc", "solve_system", "resubstitute", "marginalize_points",
+                  "tracker_make_k", "tracker_set_ref", "tracker_calc_res_pose", "tracker_calc_gs_pose",
+                  "scale_set_stereo", "scale_calc_res", "scale_calc_gs", "optimize", "ba_upload", "ba_iterate",
+                  "ba_download", "pyr_levels"):
+            self.f(n).restype = C.c_int
+        self.f("destroy").restype = None
+        if self.has("launch_count"):
+            self.f("launch_count").restype = C.c_int64
+
+    def config_default(self, w, h) -> Config:
+        cfg = Config()
+        self.f("config_default")(C.byref(cfg), C.c_int32(w), C.c_int32(h))
+        return cfg
+
+    def last_error(self) -> str:
+        s = self.f("last_error")()
+        return s.decode() if s else ""
+
+
+class Handle:
+    def __init__(self, lib: Lib, cfg: Config, device: int = 0):
+        self.lib = lib
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        self._keep = {}
+        self._ck(lib.f("create")(C.byref(cfg), C.c_int32(device), C.byref(self.h)), "create")
+        self.levels = int(lib.f("pyr_levels")(self.h))
+        self.nf = 0
+        self.P = 0
+        self.R = 0
+
+    def close(self):
+        if self.h:
+            self.lib.f("destroy")(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise SosbaError(f"{self.lib.prefix}_{what} failed: rc={rc} {self.lib.last_error()}")
+
+    def level_size(self, lvl):
+        return self.cfg.w >> lvl, self.cfg.h >> lvl
+
+    @property
+    def D(self):
+        return 4 + 8 * self.nf
+
+    # ---- stream / sync / comm (product only) ----
+    def set_stream(self, stream_ptr: int):
+        self._ck(self.lib.f("set_stream")(self.h, C.c_void_p(stream_ptr)), "set_stream")
+
+    def synchronize(self):
+        self._ck(self.lib.f("synchronize")(self.h), "synchronize")
+
+    def launch_count(self) -> int:
+        return int(self.lib.f("launch_count")(self.h))
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._ck(self.lib.f("comm_init")(self.h, buf, C.c_int32(rank), C.c_int32(world)), "comm_init")
+
+    # ---- a1 ----
+    def frame_make_images(self, slot, color, B=None):
+        color = _f32(color)
+        assert color.size == self.cfg.w * self.cfg.h
+        Bc = None if B is None else _f32(B)
+        self._ck(self.lib.f("frame_make_images")(self.h, C.c_int32(slot), _p(color, f32p), _p(Bc, f32p)), "frame_make_images")
+
+    def frame_get_level(self, slot, lvl):
+        w, h = self.level_size(lvl)
+        dI = np.empty((h, w, 3), np.float32)
+        ab = np.empty((h, w), np.float32)
+        self._ck(self.lib.f("frame_get_level")(self.h, C.c_int32(slot), C.c_int32(lvl), _p(dI, f32p), _p(ab, f32p)), "frame_get_level")
+        return dI, ab
+
+    # ---- uploads ----
+    def _window_struct(self, win: dict):
+        nf = int(win["nf"])
+        k = {"frame_slot": _i32(win["frame_slot"]), "precalc": _f32(win["precalc"]), "adHost": _f64(win["adHost"]),
+             "adTarget": _f64(win["adTarget"]), "adHTdeltaF": _f32(win["adHTdeltaF"]),
+             "frame_energy_th": _f32(win["frame_energy_th"]), "frame_prior": _f64(win["frame_prior"]),
+             "frame_delta_prior": _f64(win["frame_delta_prior"]), "frame_delta": _f64(win["frame_delta"])}
+        assert k["precalc"].size == nf * nf * PRECALC_FLOATS and k["adHost"].size == nf * nf * 64
+        W = Window()
+        W.nf = nf
+        W.frame_slot = _p(k["frame_slot"], i32p)
+        W.precalc = _p(k["precalc"], f32p)
+        W.adHost = _p(k["adHost"], f64p)
+        W.adTarget = _p(k["adTarget"], f64p)
+        W.adHTdeltaF = _p(k["adHTdeltaF"], f32p)
+        W.frame_energy_th = _p(k["frame_energy_th"], f32p)
+        W.calib = (C.c_float * 4)(*[float(x) for x in win["calib"]])
+        W.cDeltaF = (C.c_float * 4)(*[float(x) for x in win["cDeltaF"]])
+        W.cPrior = (C.c_double * 4)(*[float(x) for x in win["cPrior"]])
+        W.frame_prior = _p(k["frame_prior"], f64p)
+        W.frame_delta_prior = _p(k["frame_delta_prior"], f64p)
+        W.frame_delta = _p(k["frame_delta"], f64p)
+        return W, k
+
+    def window_set(self, win: dict):
+        W, keep = self._window_struct(win)
+        self._ck(self.lib.f("window_set")(self.h, C.byref(W)), "window_set")
+        self.nf = int(win["nf"])
+
+    def window_update(self, win: dict):
+        W, keep = self._window_struct(win)
+        self._ck(self.lib.f("window_update")(self.h, C.byref(W)), "window_update")
+
+    @staticmethod
+    def _points_struct(pts: dict):
+        n = int(len(pts["u"]))
+        k = {"u": _f32(pts["u"]), "v": _f32(pts["v"]), "idepth": _f32(pts["idepth"]),
+             "idepth_zero": _f32(pts["idepth_zero"]), "color": _f32(pts["color"]), "weights": _f32(pts["weights"]),
+             "host": _i32(pts["host"]), "priorF": _f32(pts.get("priorF", np.zeros(n))),
+             "deltaF": _f32(pts.get("deltaF", np.zeros(n)))}
+        S = Points()
+        S.n = n
+        for name in ("u", "v", "idepth", "idepth_zero", "color", "weights", "priorF", "deltaF"):
+            setattr(S, name, _p(k[name], f32p))
+        S.host = _p(k["host"], i32p)
+        return S, k
+
+    @staticmethod
+    def _residuals_struct(res: dict):
+        n = int(len(res["point"]))
+        k = {"point": _i32(res["point"]), "target": _i32(res["target"]),
+             "state": _u8(res.get("state", np.zeros(n))), "is_linearized": _u8(res.get("is_linearized", np.zeros(n))),
+             "is_active": _u8(res.get("is_active", np.zeros(n))), "is_new": _u8(res.get("is_new", np.ones(n))),
+             "state_energy": _f32(res.get("state_energy", np.zeros(n)))}
+        S = Residuals()
+        S.n = n
+        S.point = _p(k["point"], i32p)
+        S.target = _p(k["target"], i32p)
+        for name in ("state", "is_linearized", "is_active", "is_new"):
+            setattr(S, name, _p(k[name], u8p))
+        S.state_energy = _p(k["state_energy"], f32p)
+        return S, k
+
+    def points_set(self, pts: dict):
+        S, keep = self._points_struct(pts)
+        self._ck(self.lib.f("points_set")(self.h, C.byref(S)), "points_set")
+        self.P = S.n
+
+    def points_update(self, idepth=None, idepth_zero=None, deltaF=None):
+        a = None if idepth is None else _f32(idepth)
+        b = None if idepth_zero is None else _f32(idepth_zero)
+        c = None if deltaF is None else _f32(deltaF)
+        self._ck(self.lib.f("points_update")(self.h, _p(a, f32p), _p(b, f32p), _p(c, f32p)), "points_update")
+
+    def residuals_set(self, res: dict):
+        S, keep = self._residuals_struct(res)
+        self._ck(self.lib.f("residuals_set")(self.h, C.byref(S)), "residuals_set")
+        self.R = S.n
+
+    # ---- a3-a5, a13 ----
+    def reset_oob(self):
+        self._ck(self.lib.f("reset_oob")(self.h), "reset_oob")
+
+    def linearize_all(self, fix=False) -> dict:
+        out = LinearizeOut()
+        self._ck(self.lib.f("linearize_all")(self.h, C.c_int32(1 if fix else 0), C.byref(out)), "linearize_all")
+        return {n: getattr(out, n) for n, _ in LinearizeOut._fields_ if n != "reserved0"}
+
+    def apply_res(self):
+        self._ck(self.lib.f("apply_res")(self.h), "apply_res")
+
+    def fix_linearization(self, ids):
+        ids = _i32(ids)
+        self._ck(self.lib.f("fix_linearization")(self.h, _p(ids, i32p), C.c_int32(ids.size)), "fix_linearization")
+
+    def get_state(self) -> dict:
+        R = self.R
+        o = {"state": np.empty(R, np.uint8), "new_state": np.empty(R, np.uint8), "energy": np.empty(R, np.float32),
+             "new_energy": np.empty(R, np.float32), "new_energy_wo": np.empty(R, np.float32),
+             "is_active": np.empty(R, np.uint8), "is_linearized": np.empty(R, np.uint8)}
+        self._ck(self.lib.f("residuals_get_state")(self.h, _p(o["state"], u8p), _p(o["new_state"], u8p), _p(o["energy"], f32p),
+                                                   _p(o["new_energy"], f32p), _p(o["new_energy_wo"], f32p),
+                                                   _p(o["is_active"], u8p), _p(o["is_linearized"], u8p)), "residuals_get_state")
+        return o
+
+    def get_jacobians(self, committed: bool) -> np.ndarray:
+        J = np.zeros((self.R, J_FLOATS), np.float32)
+        self._ck(self.lib.f("residuals_get_jacobians")(self.h, C.c_int32(1 if committed else 0), _p(J, f32p)), "residuals_get_jacobians")
+        return J
+
+    def get_aux(self) -> dict:
+        R = self.R
+        o = {"JpJdF": np.zeros((R, 8), np.float32), "res_toZeroF": np.zeros((R, 8), np.float32),
+             "projectedTo": np.zeros((R, 8, 2), np.float32), "centerProjectedTo": np.zeros((R, 3), np.float32)}
+        self._ck(self.lib.f("residuals_get_aux")(self.h, _p(o["JpJdF"], f32p), _p(o["res_toZeroF"], f32p),
+                                                 _p(o["projectedTo"], f32p), _p(o["centerProjectedTo"], f32p)), "residuals_get_aux")
+        return o
+
+    def points_get_stats(self):
+        mrb = np.zeros(self.P, np.float32)
+        ngr = np.zeros(self.P, np.int32)
+        self._ck(self.lib.f("points_get_stats")(self.h, _p(mrb, f32p), _p(ngr, i32p)), "points_get_stats")
+        return mrb, ngr
+
+    # ---- a6-a11 ----
+    def accumulate(self) -> dict:
+        D = self.D
+        o = {k: np.zeros((D, D)) for k in ("HA", "HL", "Hsc")}
+        o.update({k: np.zeros(D) for k in ("bA", "bL", "bsc")})
+        ra, rl = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.f("accumulate")(self.h, _p(o["HA"], f64p), _p(o["bA"], f64p), _p(o["HL"], f64p), _p(o["bL"], f64p),
+                                          _p(o["Hsc"], f64p), _p(o["bsc"], f64p), C.byref(ra), C.byref(rl)), "accumulate")
+        o["resInA"], o["resInL"] = ra.value, rl.value
+        return o
+
+    def points_get_acc(self) -> dict:
+        P = self.P
+        o = {"HddA": np.zeros(P, np.float32), "bdA": np.zeros(P, np.float32), "HcdA": np.zeros((P, 4), np.float32),
+             "HddL": np.zeros(P, np.float32), "bdL": np.zeros(P, np.float32), "HcdL": np.zeros((P, 4), np.float32),
+             "HdiF": np.zeros(P, np.float32), "bdSumF": np.zeros(P, np.float32)}
+        self._ck(self.lib.f("points_get_acc")(self.h, *[_p(o[k], f32p) for k in ("HddA", "bdA", "HcdA", "HddL", "bdL", "HcdL", "HdiF", "bdSumF")]),
+                 "points_get_acc")
+        return o
+
+    def solve_system(self, HM=None, bM=None):
+        D = self.D
+        x, Hf, bf = np.zeros(D), np.zeros((D, D)), np.zeros(D)
+        hm = None if HM is None else _f64(HM)
+        bm = None if bM is None else _f64(bM)
+        self._ck(self.lib.f("solve_system")(self.h, _p(hm, f64p), _p(bm, f64p), _p(x, f64p), _p(Hf, f64p), _p(bf, f64p)), "solve_system")
+        return x, Hf, bf
+
+    def resubstitute(self, x):
+        x = _f64(x)
+        step = np.zeros(self.P, np.float32)
+        self._ck(self.lib.f("resubstitute")(self.h, _p(x, f64p), _p(step, f32p)), "resubstitute")
+        return step
+
+    def marginalize_points(self, ids):
+        ids = _i32(ids)
+        D = self.D
+        H, b = np.zeros((D, D)), np.zeros(D)
+        n = C.c_int32(0)
+        self._ck(self.lib.f("marginalize_points")(self.h, _p(ids, i32p), C.c_int32(ids.size), _p(H, f64p), _p(b, f64p), C.byref(n)), "marginalize_points")
+        return H, b, n.value
+
+    # ---- tracker / scale ----
+    def tracker_make_k(self, calib):
+        c = (C.c_float * 4)(*[float(x) for x in calib])
+        self._ck(self.lib.f("tracker_make_k")(self.h, c), "tracker_make_k")
+
+    def tracker_set_ref(self, lvl, u, v, idepth, color):
+        u, v, idepth, color = _f32(u), _f32(v), _f32(idepth), _f32(color)
+        self._ck(self.lib.f("tracker_set_ref")(self.h, C.c_int32(lvl), C.c_int32(u.size), _p(u, f32p), _p(v, f32p), _p(idepth, f32p), _p(color, f32p)), "tracker_set_ref")
+
+    def tracker_calc_res_pose(self, lvl, slot, refToNew34, affLL, cutoff):
+        T = _f64(refToNew34).reshape(12)
+        a = (C.c_float * 2)(float(affLL[0]), float(affLL[1]))
+        out6 = np.zeros(6)
+        cnt = np.zeros(3, np.int32)
+        self._ck(self.lib.f("tracker_calc_res_pose")(self.h, C.c_int32(lvl), C.c_int32(slot), _p(T, f64p), a, C.c_float(cutoff), _p(out6, f64p), _p(cnt, i32p)),
+                 "tracker_calc_res_pose")
+        return out6, cnt
+
+    def tracker_calc_gs_pose(self, lvl, a, b0):
+        H, b = np.zeros((8, 8)), np.zeros(8)
+        self._ck(self.lib.f("tracker_calc_gs_pose")(self.h, C.c_int32(lvl), C.c_float(a), C.c_float(b0), _p(H, f64p), _p(b, f64p)), "tracker_calc_gs_pose")
+        return H, b
+
+    def scale_set_stereo(self, T10_34, K1):
+        T = _f64(T10_34).reshape(12)
+        k = (C.c_float * 4)(*[float(x) for x in K1])
+        self._ck(self.lib.f("scale_set_stereo")(self.h, _p(T, f64p), k), "scale_set_stereo")
+
+    def scale_calc_res(self, lvl, slot, scale, cutoff):
+        out6 = np.zeros(6)
+        cnt = np.zeros(3, np.int32)
+        self._ck(self.lib.f("scale_calc_res")(self.h, C.c_int32(lvl), C.c_int32(slot), C.c_float(scale), C.c_float(cutoff), _p(out6, f64p), _p(cnt, i32p)), "scale_calc_res")
+        return out6, cnt
+
+    def scale_calc_gs(self, lvl, scale):
+        H, b = C.c_float(0), C.c_float(0)
+        self._ck(self.lib.f("scale_calc_gs")(self.h, C.c_int32(lvl), C.c_float(scale), C.byref(H), C.byref(b)), "scale_calc_gs")
+        return H.value, b.value
+
+    # ---- composed GN loop ----
+    def make_problem(self, frames: list, calib_value, calib_value_zero, pts: dict, res: dict, HM=None, bM=None):
+        """frames: list of dicts {evalPT (3x4 or 4x4), state, state_zero, ab_exposure, frame_energy_th, frame_id, slot}."""
+        nf = len(frames)
+        arr = (FrameState * nf)()
+        for i, f in enumerate(frames):
+            T = np.asarray(f["evalPT"], np.float64)[:3, :4].reshape(12)
+            arr[i].camToWorld_evalPT = (C.c_double * 12)(*T)
+            arr[i].state = (C.c_double * 10)(*np.asarray(f["state"], np.float64))
+            arr[i].state_zero = (C.c_double * 10)(*np.asarray(f["state_zero"], np.float64))
+            arr[i].ab_exposure = float(f.get("ab_exposure", 1.0))
+            arr[i].frame_energy_th = float(f.get("frame_energy_th", 8 * 8 * 8))
+            arr[i].frame_id = int(f.get("frame_id", i))
+            arr[i].slot = int(f.get("slot", i))
+        P = BAProblem()
+        P.nf = nf
+        P.frames = arr
+        P.calib_value = (C.c_double * 4)(*[float(x) for x in calib_value])
+        P.calib_value_zero = (C.c_double * 4)(*[float(x) for x in calib_value_zero])
+        ps, pk = self._points_struct(pts)
+        rs, rk = self._residuals_struct(res)
+        P.points, P.residuals = ps, rs
+        hm = None if HM is None else _f64(HM)
+        bm = None if bM is None else _f64(bM)
+        P.HM, P.bM = _p(hm, f64p), _p(bm, f64p)
+        idout = np.zeros(ps.n, np.float32)
+        P.idepth_out = _p(idout, f32p)
+        keep = (arr, pk, rk, hm, bm, idout)
+        self.nf, self.P, self.R = nf, ps.n, rs.n
+        return P, keep
+
+    @staticmethod
+    def problem_result(P, keep) -> dict:
+        arr = keep[0]
+        nf = P.nf
+        return {"evalPT": np.array([list(arr[i].camToWorld_evalPT) for i in range(nf)]).reshape(nf, 3, 4),
+                "state": np.array([list(arr[i].state) for i in range(nf)]),
+                "state_zero": np.array([list(arr[i].state_zero) for i in range(nf)]),
+                "frame_energy_th": np.array([arr[i].frame_energy_th for i in range(nf)], np.float32),
+                "calib_value": np.array(list(P.calib_value)), "idepth": keep[5].copy()}
+
+    def optimize(self, P, max_iterations: int) -> dict:
+        out = OptimizeOut()
+        self._ck(self.lib.f("optimize")(self.h, C.byref(P), C.c_int32(max_iterations), C.byref(out)), "optimize")
+        return {n: getattr(out, n) for n, _ in OptimizeOut._fields_ if not n.startswith("reserved")}
+
+    def ba_upload(self, P):
+        self._ck(self.lib.f("ba_upload")(self.h, C.byref(P)), "ba_upload")
+
+    def ba_iterate(self, n: int) -> int:
+        nres = C.c_int32(0)
+        self._ck(self.lib.f("ba_iterate")(self.h, C.c_int32(n), C.byref(nres)), "ba_iterate")
+        return nres.value
+
+    def ba_download(self, P):
+        self._ck(self.lib.f("ba_download")(self.h, C.byref(P)), "ba_download")

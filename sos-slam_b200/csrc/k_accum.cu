@@ -1,0 +1,479 @@
+// k_accum.cu — block-Hessian accumulation, Schur complement and back-substitution.
+//
+//   top_accumulate   AccumulatedTopHessianSSE::addPoint<mode> block part + AccumulatorApprox::update /
+//                    updateTopRight / updateBotRight     AccumulatedTopHessian.cpp:35-147, MatrixAccumulators.h:928-1112
+//   point_sums       the per-point Hdd/bd/Hcd sums of addPoint<mode>            AccumulatedTopHessian.cpp:124-146
+//   sc_accumulate    AccumulatedSCHessianSSE::addPoint                          AccumulatedSCHessian.cpp:32-79
+//   stitch_top       AccumulatedTopHessianSSE::stitchDoubleInternal + MT epilogue  AccumulatedTopHessian.cpp:231-301, .h:80-127
+//   finalize_sc      AccumulatedSCHessianSSE::stitchDoubleInternal + MT epilogue   AccumulatedSCHessian.cpp:80-158, .h:88-124
+//   resubstitute     EnergyFunctional::resubstituteFPt                          EnergyFunctional.cpp:526-551
+//
+// Re-design notes: the reference keeps 6 thread-private copies of nf^2 13x13 float blocks with
+// 3-tier float buffers and sums them in the stitch.  Here residuals are visited in (host,target)-block order by
+// warps that own the 91 upper-triangle entries of one block in registers (3 per lane), so a block change is the
+// only time anything leaves the SM: one fp64 red.global per entry into the nf^2 x 92 fp64 block table.  The
+// Schur term is accumulated directly in stitched space: every point contributes w * g g^T with
+// g = [Hcd ; sum_r adHost*JpJdF (host rows) ; adTarget*JpJdF (target rows) ; bdSum], a (D+1)^2 rank-1 update
+// done as a register-tiled SYRK over 32-point tiles in shared memory — nf^3 8x8 blocks never exist.
+#include <math.h>
+
+#include "kernels.h"
+
+namespace {
+
+// entry e of the 91 (10x10 upper triangle row-major, then 10x3 TopRight, then 6 BotRight)
+struct EntryDesc { int p, q, kind; };  // kind 0: 10x10 (r=p,c=q)  1: TopRight (i=p,j=q)  2: BotRight (k=p)  3: none
+__device__ __forceinline__ EntryDesc entry_desc(int e) {
+  EntryDesc d;
+  if (e < 55) {
+    int r = 0, base = 0;
+    while (e >= base + (10 - r)) { base += 10 - r; r++; }
+    d.p = r; d.q = r + (e - base); d.kind = 0;
+  } else if (e < 85) { d.p = (e - 55) / 3; d.q = (e - 55) % 3; d.kind = 1; }
+  else if (e < 91) { d.p = e - 85; d.q = 0; d.kind = 2; }
+  else { d.p = d.q = 0; d.kind = 3; }
+  return d;
+}
+
+__device__ __forceinline__ float entry_value(const float *s, const EntryDesc &d) {
+  if (d.kind == 0) {
+    const float xr = s[CR_X + d.p], yr = s[CR_Y + d.p], xc = s[CR_X + d.q], yc = s[CR_Y + d.q];
+    const float a = s[CR_A], b = s[CR_A + 1], c = s[CR_A + 2];
+    return a * xc * xr + c * yc * yr + b * (xc * yr + yc * xr);
+  }
+  if (d.kind == 1) return s[CR_X + d.p] * s[CR_TR + 2 * d.q] + s[CR_Y + d.p] * s[CR_TR + 2 * d.q + 1];
+  if (d.kind == 2) return s[CR_BR + d.p];
+  return 0.f;
+}
+
+// One warp walks a contiguous chunk of the block-ordered residual list.
+constexpr int TOP_WARPS = 8;
+__global__ void __launch_bounds__(TOP_WARPS * 32) k_top_accumulate(AccArgs a, int chunk) {
+  __shared__ __align__(16) float s_rec[TOP_WARPS][SOSBA_CREC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * TOP_WARPS + warp;
+  const int k0 = gw * chunk, k1 = min(k0 + chunk, a.n_list);
+  if (k0 >= k1) return;
+  const EntryDesc d0 = entry_desc(lane), d1 = entry_desc(lane + 32), d2 = entry_desc(lane + 64);
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  int cur = -1, nacc = 0, ntotal = 0;
+  float *s = s_rec[warp];
+
+  auto flush = [&]() {
+    if (cur >= 0 && nacc > 0) {
+      double *dst = a.accTop + (size_t)cur * SOSBA_TOPB;
+      atomicAdd(dst + lane, (double)acc0);
+      atomicAdd(dst + lane + 32, (double)acc1);
+      if (lane + 64 < 91) atomicAdd(dst + lane + 64, (double)acc2);
+      if (lane == 31) atomicAdd(dst + 91, (double)nacc);
+    }
+    acc0 = acc1 = acc2 = 0.f; nacc = 0;
+  };
+
+  // software prefetch: the record of residual k+1 is in flight while k is accumulated
+  auto wanted = [&](int r) -> bool {
+    if (a.r_dropped[r] || !a.r_is_active[r]) return false;
+    if (a.mode == 0) return !a.r_is_lin[r];
+    if (a.mode == 1) return a.r_is_lin[r];
+    return true;
+  };
+  int r = a.list ? a.list[k0] : k0;
+  bool use = wanted(r);
+  float v0 = 0.f, v1 = 0.f;
+  if (use) { const float *rec = a.rec + (size_t)r * SOSBA_CREC; v0 = rec[lane]; if (lane < SOSBA_CREC - 32) v1 = rec[32 + lane]; }
+  for (int k = k0; k < k1; k++) {
+    const int rc = r; const bool usec = use; const float c0 = v0, c1 = v1;
+    if (k + 1 < k1) {
+      r = a.list ? a.list[k + 1] : k + 1;
+      use = wanted(r);
+      if (use) { const float *rec = a.rec + (size_t)r * SOSBA_CREC; v0 = rec[lane]; if (lane < SOSBA_CREC - 32) v1 = rec[32 + lane]; }
+    }
+    if (!usec) continue;
+    const int blk = a.r_host[rc] + a.r_target[rc] * a.nf;
+    if (blk != cur) { flush(); cur = blk; }
+    __syncwarp();
+    s[lane] = c0;
+    if (lane < SOSBA_CREC - 32) s[32 + lane] = c1;
+    __syncwarp();
+    acc0 += entry_value(s, d0);
+    acc1 += entry_value(s, d1);
+    acc2 += entry_value(s, d2);
+    nacc++; ntotal++;
+  }
+  flush();
+  if (lane == 0 && ntotal) atomicAdd(&a.counts[5], ntotal);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-point sums: G lanes per point, lane j owns residual res_begin[p] + j; sums run in residual order.
+template <int G>
+__global__ void __launch_bounds__(256) k_point_sums(PointArgs a) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = gid / G, j = gid % G;
+  const int np = a.plist ? a.n_plist : a.P;
+  if (k >= np) return;
+  const int p = a.plist ? a.plist[k] : k;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+  const int rb = a.res_begin[p], re = a.res_begin[p + 1];
+  float bd = 0.f, Hdd = 0.f, Hcd[4] = {0.f, 0.f, 0.f, 0.f};
+  float c_bd = 0.f, c_Hdd = 0.f, c_Hcd[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int base = rb; base < re; base += G) {  // a point has <= nf-1 residuals; the loop runs once
+    const int r = base + j;
+    bool use = r < re;
+    if (use) {
+      use = a.r_is_active[r] && !a.r_dropped[r];
+      if (a.mode == 0) use = use && !a.r_is_lin[r];
+      if (a.mode == 1) use = use && a.r_is_lin[r];
+    }
+    c_bd = c_Hdd = 0.f; c_Hcd[0] = c_Hcd[1] = c_Hcd[2] = c_Hcd[3] = 0.f;
+    if (use) {
+      const float *rec = a.rec + (size_t)r * SOSBA_CREC;
+      const float a00 = rec[CR_A], a01 = rec[CR_A + 1], a11 = rec[CR_A + 2];
+      const float Jpdd0 = rec[CR_JPDD], Jpdd1 = rec[CR_JPDD + 1];
+      const float JI_r0 = rec[CR_TR + 4], JI_r1 = rec[CR_TR + 5];
+      const float v0 = a00 * Jpdd0 + a01 * Jpdd1, v1 = a01 * Jpdd0 + a11 * Jpdd1;  // JIdx2 * Jpdd
+      c_bd = JI_r0 * Jpdd0 + JI_r1 * Jpdd1;
+      c_Hdd = v0 * Jpdd0 + v1 * Jpdd1;
+#pragma unroll
+      for (int i = 0; i < 4; i++) c_Hcd[i] = rec[CR_X + i] * v0 + rec[CR_Y + i] * v1;
+    }
+    const int cnt = min(G, re - base);
+    for (int q = 0; q < cnt; q++) {
+      bd += __shfl_sync(gmask, c_bd, q, G);
+      Hdd += __shfl_sync(gmask, c_Hdd, q, G);
+#pragma unroll
+      for (int i = 0; i < 4; i++) Hcd[i] += __shfl_sync(gmask, c_Hcd[i], q, G);
+    }
+  }
+  if (j == 0) {
+    if (a.mode == 0) {
+      a.HddA[p] = Hdd; a.bdA[p] = bd;
+      for (int i = 0; i < 4; i++) a.HcdA[4 * p + i] = Hcd[i];
+    } else {
+      a.HddL[p] = Hdd; a.bdL[p] = bd;
+      for (int i = 0; i < 4; i++) a.HcdL[4 * p + i] = Hcd[i];
+      if (a.mode == 2) { a.HddA[p] = 0.f; a.bdA[p] = 0.f; for (int i = 0; i < 4; i++) a.HcdA[4 * p + i] = 0.f; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Schur complement in stitched space.  CTA = 256 threads, tiles of 32 points.
+//   phase 1 (8 lanes... one warp per 4 points x 8 residual lanes for nf<=9, generic loop otherwise):
+//           HdiF, bdSumF, g -> shared Gs[32][DPAD]
+//   phase 2 register-tiled SYRK: thread owns 4x4 tiles of the (D+1)^2 upper triangle
+constexpr int SC_TP = 32;       // points per tile
+constexpr int SC_MAXT = 3;      // 4x4 tiles per thread (nf <= 16)
+__global__ void __launch_bounds__(256) k_sc_accumulate(SCArgs a, int DP, int DPAD, int ntiles4, int tiles_total) {
+  extern __shared__ float smem[];
+  float *Gs = smem;                    // [SC_TP][DPAD]
+  float *Ws = smem + SC_TP * DPAD;     // [SC_TP]
+  const int tid = threadIdx.x;
+  const int nt4 = DPAD / 4;
+  // tile assignment: linear index over upper-triangular 4x4 tiles (ti <= tj)
+  int my_ti[SC_MAXT], my_tj[SC_MAXT];
+  float acc[SC_MAXT][16];
+#pragma unroll
+  for (int m = 0; m < SC_MAXT; m++) {
+    int t = tid + m * 256;
+    my_ti[m] = -1; my_tj[m] = 0;
+    if (t < ntiles4) {
+      int ti = 0, base = 0;
+      while (t >= base + (nt4 - ti)) { base += nt4 - ti; ti++; }
+      my_ti[m] = ti; my_tj[m] = ti + (t - base);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q++) acc[m][q] = 0.f;
+  }
+  const int np = a.plist ? a.n_plist : a.P;
+  const int D = a.D;
+
+  for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+    for (int i = tid; i < SC_TP * DPAD; i += 256) Gs[i] = 0.f;
+    if (tid < SC_TP) Ws[tid] = 0.f;
+    __syncthreads();
+    // phase 1: 8 threads per point
+    {
+      const int lp = tid >> 3, sub = tid & 7;
+      const int k = tile * SC_TP + lp;
+      if (k < np) {
+        const int p = a.plist ? a.plist[k] : k;
+        const int rb = a.res_begin[p], re = a.res_begin[p + 1];
+        int ngood = 0;
+        for (int r = rb; r < re; r++) ngood += (a.r_is_active[r] && !a.r_dropped[r]) ? 1 : 0;
+        if (ngood == 0) {
+          if (sub == 0) { a.HdiF[p] = 0.f; a.bdSumF[p] = 0.f; a.idepth_hessian[p] = 0.f; a.maxRelBaseline[p] = 0.f; }
+        } else {
+          float H = a.HddA[p] + a.HddL[p] + a.priorF[p];
+          if (H < 1e-10) H = 1e-10;
+          const float HdiF = (float)(1.0 / (double)H);
+          float bdSum = a.bdA[p] + a.bdL[p];
+          if (a.shiftPriorToZero) bdSum += a.priorF[p] * a.deltaF[p];
+          float *g = Gs + lp * DPAD;
+          if (sub == 0) {
+            a.HdiF[p] = HdiF; a.bdSumF[p] = bdSum; a.idepth_hessian[p] = H;
+            Ws[lp] = HdiF;
+            for (int i = 0; i < 4; i++) g[i] = a.HcdA[4 * p + i] + a.HcdL[4 * p + i];
+            g[D] = bdSum;
+          }
+          const int host = a.p_host[p];
+          for (int r = rb; r < re; r++) {  // thread `sub` computes row `sub` of adHost*v and adTarget*v
+            if (!(a.r_is_active[r] && !a.r_dropped[r])) continue;
+            const int t = a.r_target[r];
+            const float *v = a.rec + (size_t)r * SOSBA_CREC + CR_JPJDF;
+            const float *Ah = a.adHostF + 64 * (size_t)(host + t * a.nf) + 8 * sub;
+            const float *At = a.adTargetF + 64 * (size_t)(host + t * a.nf) + 8 * sub;
+            float sh = 0.f, st = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; q++) { const float vq = v[q]; sh += Ah[q] * vq; st += At[q] * vq; }
+            g[4 + 8 * host + sub] += sh;   // only this thread touches (lp, host row sub)
+            g[4 + 8 * t + sub] += st;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // phase 2
+#pragma unroll
+    for (int m = 0; m < SC_MAXT; m++) {
+      if (my_ti[m] < 0) continue;
+      const int i0 = my_ti[m] * 4, j0 = my_tj[m] * 4;
+      for (int k = 0; k < SC_TP; k++) {
+        const float w = Ws[k];
+        if (w == 0.f) continue;
+        const float4 gi = *(const float4 *)(Gs + k * DPAD + i0);
+        const float4 gj = *(const float4 *)(Gs + k * DPAD + j0);
+        const float wi[4] = {gi.x * w, gi.y * w, gi.z * w, gi.w * w};
+        const float gjv[4] = {gj.x, gj.y, gj.z, gj.w};
+#pragma unroll
+        for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++) acc[m][ii * 4 + jj] += wi[ii] * gjv[jj];
+      }
+    }
+    __syncthreads();
+  }
+  // flush
+#pragma unroll
+  for (int m = 0; m < SC_MAXT; m++) {
+    if (my_ti[m] < 0) continue;
+    const int i0 = my_ti[m] * 4, j0 = my_tj[m] * 4;
+#pragma unroll
+    for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        const int i = i0 + ii, j = j0 + jj;
+        if (i < DP && j < DP && acc[m][ii * 4 + jj] != 0.f) atomicAdd(a.accSC + (size_t)i * DP + j, (double)acc[m][ii * 4 + jj]);
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One CTA (64 threads) per (host,target) block: accH (13x13 fp64) -> H, b with the adjoint sandwich.
+__global__ void __launch_bounds__(64) k_stitch_top(const double *__restrict__ accTop, const double *__restrict__ adHost,
+                                                   const double *__restrict__ adTarget, int nf, double *__restrict__ H, double *__restrict__ b) {
+  __shared__ double accH[13][13];
+  __shared__ double Ah[64], At[64], AhP[64], AtP[64];
+  const int blk = blockIdx.x;          // = h + nf*t
+  const int h = blk % nf, t = blk / nf;
+  const double *src = accTop + (size_t)blk * SOSBA_TOPB;
+  if (src[91] == 0.0) return;          // num == 0 (AccumulatedTopHessian.cpp:168-170)
+  const int tid = threadIdx.x;
+  const int D = 4 + 8 * nf;
+  for (int e = tid; e < 91; e += 64) {
+    const EntryDesc d = entry_desc(e);
+    int r, c;
+    if (d.kind == 0) { r = d.p; c = d.q; }
+    else if (d.kind == 1) { r = d.p; c = 10 + d.q; }
+    else { const int rr[6] = {10, 10, 10, 11, 11, 12}, cc[6] = {10, 11, 12, 11, 12, 12}; r = rr[d.p]; c = cc[d.p]; }
+    accH[r][c] = src[e]; accH[c][r] = src[e];
+  }
+  Ah[tid] = adHost[64 * (size_t)blk + tid];
+  At[tid] = adTarget[64 * (size_t)blk + tid];
+  __syncthreads();
+  const int i = tid >> 3, j = tid & 7;
+  {  // AhP = Ah * P, AtP = At * P with P = accH[4:12, 4:12]
+    double sh = 0, st = 0;
+    for (int k = 0; k < 8; k++) { sh += Ah[i * 8 + k] * accH[4 + k][4 + j]; st += At[i * 8 + k] * accH[4 + k][4 + j]; }
+    AhP[tid] = sh; AtP[tid] = st;
+  }
+  __syncthreads();
+  const int hIdx = 4 + 8 * h, tIdx = 4 + 8 * t;
+  {
+    double hh = 0, tt = 0, ht = 0;
+    for (int k = 0; k < 8; k++) { hh += AhP[i * 8 + k] * Ah[j * 8 + k]; tt += AtP[i * 8 + k] * At[j * 8 + k]; ht += AhP[i * 8 + k] * At[j * 8 + k]; }
+    atomicAdd(&H[(size_t)(hIdx + i) * D + hIdx + j], hh);
+    atomicAdd(&H[(size_t)(tIdx + i) * D + tIdx + j], tt);
+    atomicAdd(&H[(size_t)(hIdx + i) * D + tIdx + j], ht);
+  }
+  if (j < 4) {  // frame-calib blocks
+    double sh = 0, st = 0;
+    for (int k = 0; k < 8; k++) { sh += Ah[i * 8 + k] * accH[4 + k][j]; st += At[i * 8 + k] * accH[4 + k][j]; }
+    atomicAdd(&H[(size_t)(hIdx + i) * D + j], sh);
+    atomicAdd(&H[(size_t)(tIdx + i) * D + j], st);
+  }
+  if (j == 4) {  // b
+    double sh = 0, st = 0;
+    for (int k = 0; k < 8; k++) { sh += Ah[i * 8 + k] * accH[4 + k][12]; st += At[i * 8 + k] * accH[4 + k][12]; }
+    atomicAdd(&b[hIdx + i], sh);
+    atomicAdd(&b[tIdx + i], st);
+  }
+  if (tid < 16) atomicAdd(&H[(size_t)(tid >> 2) * D + (tid & 3)], accH[tid >> 2][tid & 3]);
+  if (tid >= 16 && tid < 20) atomicAdd(&b[tid - 16], accH[tid - 16][12]);
+}
+
+// priors + symmetrisation epilogue of stitchDoubleMT (AccumulatedTopHessian.h:107-126, .cpp:292-300). One CTA.
+__global__ void __launch_bounds__(256) k_finalize_top(int nf, double *__restrict__ H, double *__restrict__ b, int usePrior,
+                                                      const double *__restrict__ wprior, const float *__restrict__ cDeltaF) {
+  const int D = 4 + 8 * nf, tid = threadIdx.x;
+  if (usePrior) {
+    const double *cPrior = wprior, *fprior = wprior + 4, *fdp = wprior + 4 + 8 * nf;
+    for (int i = tid; i < D; i += 256) {
+      if (i < 4) { H[(size_t)i * D + i] += cPrior[i]; b[i] += cPrior[i] * (double)cDeltaF[i]; }
+      else { H[(size_t)i * D + i] += fprior[i - 4]; b[i] += fprior[i - 4] * fdp[i - 4]; }
+    }
+  }
+  __syncthreads();
+  // calib-frame blocks: H[0:4, hIdx+j] = H[hIdx+j, 0:4]
+  for (int e = tid; e < 4 * 8 * nf; e += 256) {
+    const int i = e / (8 * nf), c = 4 + e % (8 * nf);
+    H[(size_t)i * D + c] = H[(size_t)c * D + i];
+  }
+  // off-diagonal frame blocks: H[h,t] += H[t,h]^T ; H[t,h] = H[h,t]^T   (h < t)
+  for (int e = tid; e < 64 * nf * nf; e += 256) {
+    const int blk = e >> 6, i = (e >> 3) & 7, j = e & 7;
+    const int h = blk % nf, t = blk / nf;
+    if (h >= t) continue;
+    const size_t ht = (size_t)(4 + 8 * h + i) * D + 4 + 8 * t + j, th = (size_t)(4 + 8 * t + j) * D + 4 + 8 * h + i;
+    const double v = H[ht] + H[th];
+    H[ht] = v; H[th] = v;
+  }
+}
+
+// accSC (upper tiles of the (D+1)^2 Gram matrix) -> full symmetric Hsc and bsc. One CTA.
+__global__ void __launch_bounds__(256) k_finalize_sc(const double *__restrict__ accSC, int D, double *__restrict__ H, double *__restrict__ b) {
+  const int DP = D + 1;
+  for (int e = threadIdx.x; e < D * D; e += 256) {
+    const int i = e / D, j = e % D;
+    // tiles with ti <= tj are stored; read the upper triangle only so that the result is exactly symmetric
+    H[e] = i <= j ? accSC[(size_t)i * DP + j] : accSC[(size_t)j * DP + i];
+  }
+  for (int i = threadIdx.x; i < D; i += 256) b[i] = accSC[(size_t)i * DP + D];
+}
+
+// ------------------------------------------------------------------------------------------------
+// a11  resubstituteFPt (+ the point part of backupState / doStepFromBackup when do_step)
+__global__ void __launch_bounds__(256) k_resubstitute(ResubArgs a) {
+  __shared__ double s_sum[3];
+  if (threadIdx.x < 3) s_sum[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  float st2 = 0.f, absid = 0.f, one = 0.f;
+  if (p < a.P) {
+    const int rb = a.res_begin[p], re = a.res_begin[p + 1];
+    int ngood = 0;
+    for (int r = rb; r < re; r++) ngood += (a.r_is_active[r] && !a.r_dropped[r]) ? 1 : 0;
+    float step = 0.f;
+    if (ngood > 0) {
+      const float *xc = a.xAd + (size_t)a.nf * a.nf * 8;
+      float b = a.bdSumF[p];
+      float dotc = 0.f;
+      for (int i = 0; i < 4; i++) dotc += xc[i] * (a.HcdA[4 * p + i] + a.HcdL[4 * p + i]);
+      b -= dotc;
+      const int host = a.p_host[p];
+      for (int r = rb; r < re; r++) {
+        if (!(a.r_is_active[r] && !a.r_dropped[r])) continue;
+        const float *xa = a.xAd + 8 * (size_t)(host * a.nf + a.r_target[r]);
+        const float *v = a.rec + (size_t)r * SOSBA_CREC + CR_JPJDF;
+        float s = 0.f;
+        for (int i = 0; i < 8; i++) s += xa[i] * v[i];
+        b -= s;
+      }
+      step = -b * a.HdiF[p];
+    }
+    a.step[p] = step;
+    if (a.do_step) {
+      const float backup = a.idepth[p];       // backupState: idepth_backup = idepth
+      a.idepth_backup[p] = backup;
+      const float nid = backup + step;        // stepfacD = 1
+      a.idepth[p] = nid; a.idepth_zero[p] = nid; a.deltaF[p] = 0.f;
+      st2 = step * step; absid = fabsf(backup); one = 1.f;
+    }
+  }
+  if (a.do_step) {
+    for (int o = 16; o > 0; o >>= 1) {
+      st2 += __shfl_xor_sync(0xffffffffu, st2, o); absid += __shfl_xor_sync(0xffffffffu, absid, o); one += __shfl_xor_sync(0xffffffffu, one, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_sum[0], (double)st2); atomicAdd(&s_sum[1], (double)absid); atomicAdd(&s_sum[2], (double)one); }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicAdd(&a.stats[1 + threadIdx.x], s_sum[threadIdx.x]);
+  }
+}
+
+// EnergyFunctional::marginalizePointsF: p->priorF *= setting_idepthFixPriorMargFac (EnergyFunctional.cpp:901)
+__global__ void k_scale_prior(float *__restrict__ priorF, const int *__restrict__ ids, int n, float fac) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) priorF[ids[i]] *= fac;
+}
+
+}  // namespace
+
+void launch_scale_prior(sosba *h, float *priorF, const int *ids, int n, float fac) {
+  if (n == 0) return;
+  k_scale_prior<<<(n + 255) / 256, 256, 0, h->stream>>>(priorF, ids, n, fac);
+  h->launches++;
+}
+
+// ------------------------------------------------------------------------------------------------
+void launch_top_accumulate(sosba *h, const AccArgs &a) {
+  if (a.n_list == 0) return;
+  // enough warps to fill the machine, at least 4 residuals per warp so a flush is amortised
+  int warps = h->sm_count * TOP_WARPS * 2;
+  int chunk = (a.n_list + warps - 1) / warps;
+  if (chunk < 4) chunk = 4;
+  warps = (a.n_list + chunk - 1) / chunk;
+  const int blocks = (warps + TOP_WARPS - 1) / TOP_WARPS;
+  k_top_accumulate<<<blocks, TOP_WARPS * 32, 0, h->stream>>>(a, chunk);
+  h->launches++;
+}
+
+void launch_point_sums(sosba *h, const PointArgs &a) {
+  const int np = a.plist ? a.n_plist : a.P;
+  if (np == 0) return;
+  const int maxres = a.nf - 1;
+  if (maxres <= 8) k_point_sums<8><<<(np * 8 + 255) / 256, 256, 0, h->stream>>>(a);
+  else if (maxres <= 16) k_point_sums<16><<<(np * 16 + 255) / 256, 256, 0, h->stream>>>(a);
+  else k_point_sums<32><<<(np * 32 + 255) / 256, 256, 0, h->stream>>>(a);
+  h->launches++;
+}
+
+void launch_sc_accumulate(sosba *h, const SCArgs &a) {
+  const int np = a.plist ? a.n_plist : a.P;
+  if (np == 0) return;
+  const int DP = a.D + 1, DPAD = (DP + 3) / 4 * 4, nt4 = DPAD / 4;
+  const int ntiles4 = nt4 * (nt4 + 1) / 2;
+  const int tiles_total = (np + SC_TP - 1) / SC_TP;
+  int blocks = tiles_total < h->sm_count ? tiles_total : h->sm_count;
+  const size_t smem = (size_t)(SC_TP * DPAD + SC_TP) * sizeof(float);
+  k_sc_accumulate<<<blocks, 256, smem, h->stream>>>(a, DP, DPAD, ntiles4, tiles_total);
+  h->launches++;
+}
+
+void launch_stitch_top(sosba *h, const double *accTop, const double *adHost, const double *adTarget, int nf, double *H, double *b, int usePrior,
+                       const double *wprior, const float *cDeltaF) {
+  k_stitch_top<<<nf * nf, 64, 0, h->stream>>>(accTop, adHost, adTarget, nf, H, b);
+  k_finalize_top<<<1, 256, 0, h->stream>>>(nf, H, b, usePrior, wprior, cDeltaF);
+  h->launches += 2;
+}
+
+void launch_finalize_sc(sosba *h, const double *accSC, int nf, double *H, double *b) {
+  k_finalize_sc<<<1, 256, 0, h->stream>>>(accSC, 4 + 8 * nf, H, b);
+  h->launches++;
+}
+
+void launch_resubstitute(sosba *h, const ResubArgs &a) {
+  if (a.P == 0) return;
+  k_resubstitute<<<(a.P + 255) / 256, 256, 0, h->stream>>>(a);
+  h->launches++;
+}

@@ -1,0 +1,620 @@
+// k_exact.cu — kernels whose per-element float expressions decide integer bookkeeping (residual state,
+// counts) and therefore follow the reference's operation order with no FMA contraction.  This file is
+// compiled with -fmad=false (the parity definition pins -ffp-contract=off on the CPU side).
+//
+//   make_images          FrameHessian::makeImages                     src/FullSystem/HessianBlocks.cpp:121-176
+//   linearize            PointFrameResidual::linearize                src/FullSystem/Residuals.cpp:77-271
+//                        projectPoint x2                              src/FullSystem/ResidualProjections.h:43-73
+//                        getInterpolatedElement33                     src/util/globalFuncs.h:68-82
+//   apply_res            PointFrameResidual::applyRes + takeDataF     Residuals.cpp:304-321, EnergyFunctionalStructs.cpp:36-45
+//                        + the fixLinearization bookkeeping of linearizeAll_Reductor  FullSystemOptimize.cpp:52-74
+//   fix_linearization    EFResidual::fixLinearizationF                EnergyFunctionalStructs.cpp:75-103
+//   prep_records         resApprox / JI_r / Jab_r / rr of addPoint<1>, addPoint<2>   AccumulatedTopHessian.cpp:68-110
+//   energy_th            FullSystem::setNewFrameEnergyTH              FullSystemOptimize.cpp:84-124
+//   track_res            CoarseTracker::calcResPose / ScaleOptimizer::calcResScale   CoarseTracker.cpp:612-764, ScaleOptimizer.cpp:273-437
+#include <math.h>
+
+#include "kernels.h"
+
+namespace {
+
+__constant__ int c_pattern[8][2] = {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 0}, {-1, 1}, {0, 2}};  // settings.cpp:307-309
+
+constexpr float kSCALE_IDEPTH = 1.0f, kSCALE_F = 50.0f, kSCALE_C = 50.0f;  // HessianBlocks.h:53-60
+
+// ------------------------------------------------------------------------------------------------
+// a1  image pyramid.  Level 0 reads the irradiance plane; level l recomputes the 2x2 means of level l-1
+// for the pixel and its 4 flat-index neighbours (the reference differentiates over a flat index, so the
+// first/last column difference reaches into the neighbouring row — reproduced here).  Rows 0 and h-1
+// keep dx = dy = absSquaredGrad = 0 (uninitialised in the reference).
+__device__ __forceinline__ float down4(const float *__restrict__ prev, int wm, int wl, int j) {
+  int x = j % wl, y = j / wl;
+  const float *p = prev + 2 * x + 2 * y * wm;
+  return 0.25f * (((p[0] + p[1]) + p[wm]) + p[1 + wm]);
+}
+
+__global__ void __launch_bounds__(256) k_pyr(const float *__restrict__ src, int wm, float4 *__restrict__ img, float *__restrict__ plane, int w, int h,
+                                             int lvl, const float *__restrict__ B, int gamma) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= w * h) return;
+  float I, dx = 0.f, dy = 0.f, ab = 0.f;
+  const bool inner = idx >= w && idx < w * (h - 1);
+  if (lvl == 0) {
+    I = src[idx];
+    if (inner) {
+      dx = 0.5f * (src[idx + 1] - src[idx - 1]);
+      dy = 0.5f * (src[idx + w] - src[idx - w]);
+    }
+  } else {
+    I = down4(src, wm, w, idx);
+    if (inner) {
+      dx = 0.5f * (down4(src, wm, w, idx + 1) - down4(src, wm, w, idx - 1));
+      dy = 0.5f * (down4(src, wm, w, idx + w) - down4(src, wm, w, idx - w));
+    }
+  }
+  if (inner) {
+    if (!isfinite(dx)) dx = 0.f;
+    if (!isfinite(dy)) dy = 0.f;
+    ab = dx * dx + dy * dy;
+    if (gamma == 1 && B != nullptr) {  // CalibHessian::getBGradOnly, HessianBlocks.h:519-526
+      int c = (int)(I + 0.5f);
+      if (c < 5) c = 5;
+      if (c > 250) c = 250;
+      float gw = B[c + 1] - B[c];
+      ab *= gw * gw;
+    }
+  }
+  img[idx] = make_float4(I, dx, dy, ab);
+  plane[idx] = I;
+}
+
+// ------------------------------------------------------------------------------------------------
+// globalFuncs.h:68-82 on the float4 image: weights and summation order verbatim.
+__device__ __forceinline__ float3 interp33(const float4 *__restrict__ img, float x, float y, int width) {
+  int ix = (int)x, iy = (int)y;
+  float dx = x - ix, dy = y - iy;
+  float dxdy = dx * dy;
+  const float4 *bp = img + ix + iy * width;
+  float4 t11 = __ldg(bp + 1 + width), t01 = __ldg(bp + width), t10 = __ldg(bp + 1), t00 = __ldg(bp);
+  float w11 = dxdy, w01 = dy - dxdy, w10 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
+  float3 o;
+  o.x = w11 * t11.x + w01 * t01.x + w10 * t10.x + w00 * t00.x;
+  o.y = w11 * t11.y + w01 * t01.y + w10 * t10.y + w00 * t00.y;
+  o.z = w11 * t11.z + w01 * t01.z + w10 * t10.z + w00 * t00.z;
+  return o;
+}
+
+// sequential (index-order) sum of one value per pattern lane, identical on all 8 lanes of the group
+__device__ __forceinline__ float seqsum8(unsigned mask, float v) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s += __shfl_sync(mask, v, j, 8);
+  return s;
+}
+
+__device__ __forceinline__ float4 pick4(int k, float4 c0, float4 c1, float4 c2, float4 c3, float4 c4, float4 c5, float4 c6, float4 c7) {
+  float4 r = c0;
+  r = k == 1 ? c1 : r; r = k == 2 ? c2 : r; r = k == 3 ? c3 : r; r = k == 4 ? c4 : r;
+  r = k == 5 ? c5 : r; r = k == 6 ? c6 : r; r = k == 7 ? c7 : r;
+  return r;
+}
+
+// a3  one residual = 8 consecutive lanes (one per pattern sample); 32 residuals per 256-thread block.
+__global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
+  __shared__ double s_energy;
+  __shared__ int s_cnt[3];
+  if (threadIdx.x == 0) { s_energy = 0.0; s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; }
+  __syncthreads();
+
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = gid >> 3, idx = gid & 7;
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+  bool live = r < a.R;
+  if (live) live = !(a.r_is_lin[r] | a.r_dropped[r]);
+  int outcome = -1;       // state_NewState once decided
+  float ret_energy = 0.f; // linearize() return value
+  if (live) {
+    const int pt = a.r_point[r], host = a.r_host[r], target = a.r_target[r];
+    const float old_energy = a.r_energy[r];
+    float energyWO = -1.f;
+    bool done = false;
+    if (a.r_state[r] == SOSBA_RES_OOB) { outcome = SOSBA_RES_OOB; ret_energy = old_energy; done = true; }
+
+    if (!done) {
+      const float *pc = a.precalc + (size_t)(host * a.nf + target) * SOSBA_PRECALC_FLOATS;
+      const float4 q0 = __ldg((const float4 *)pc), q1 = __ldg((const float4 *)pc + 1), q2 = __ldg((const float4 *)pc + 2),
+                   q3 = __ldg((const float4 *)pc + 3), q4 = __ldg((const float4 *)pc + 4), q5 = __ldg((const float4 *)pc + 5),
+                   q6 = __ldg((const float4 *)pc + 6);
+      const float R0[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+      const float t0[3] = {q2.y, q2.z, q2.w};
+      const float KRKi[9] = {q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w, q5.x};
+      const float Kt[3] = {q5.y, q5.z, q5.w};
+      const float affLL0 = q6.x, affLL1 = q6.y, b0 = q6.z;
+      const float fxl = a.calib[0], fyl = a.calib[1], cxl = a.calib[2], cyl = a.calib[3], fxli = a.calib[4], fyli = a.calib[5];
+      const float pu = a.p_u[pt], pv = a.p_v[pt], idepth = a.p_idepth[pt] * kSCALE_IDEPTH, idepth_zero = a.p_idepth_zero[pt] * kSCALE_IDEPTH;
+      const float color = a.p_color[(size_t)pt * 8 + idx], weight = a.p_weights[(size_t)pt * 8 + idx];
+
+      float d_xi_x[6], d_xi_y[6], d_C_x[4], d_C_y[4], d_d_x, d_d_y;
+      float cKu = 0.f, cKv = 0.f, c_new_idepth = 0.f;
+      {  // centre projection at the evaluation point (Residuals.cpp:102-169)
+        float KliP[3] = {(pu + 0 - cxl) * fxli, (pv + 0 - cyl) * fyli, 1.f};
+        float ptp[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) ptp[i] = ((R0[3 * i] * KliP[0] + R0[3 * i + 1] * KliP[1]) + R0[3 * i + 2] * KliP[2]) + t0[i] * idepth_zero;
+        float drescale = 1.0f / ptp[2];
+        float new_idepth = idepth_zero * drescale;
+        float u = ptp[0] * drescale, v = ptp[1] * drescale;
+        float Ku = u * fxl + cxl, Kv = v * fyl + cyl;
+        if (!(drescale > 0) || !(Ku > 1.1f && Kv > 1.1f && Ku < a.wM3G && Kv < a.hM3G)) {
+          outcome = SOSBA_RES_OOB; ret_energy = old_energy; done = true;
+        }
+        cKu = Ku; cKv = Kv; c_new_idepth = new_idepth;
+        d_d_x = drescale * (t0[0] - t0[2] * u) * kSCALE_IDEPTH * fxl;
+        d_d_y = drescale * (t0[1] - t0[2] * v) * kSCALE_IDEPTH * fyl;
+
+        d_C_x[2] = drescale * (R0[6] * u - R0[0]);
+        d_C_x[3] = fxl * drescale * (R0[7] * u - R0[1]) * fyli;
+        d_C_x[0] = KliP[0] * d_C_x[2];
+        d_C_x[1] = KliP[1] * d_C_x[3];
+
+        d_C_y[2] = fyl * drescale * (R0[6] * v - R0[3]) * fxli;
+        d_C_y[3] = drescale * (R0[7] * v - R0[4]);
+        d_C_y[0] = KliP[0] * d_C_y[2];
+        d_C_y[1] = KliP[1] * d_C_y[3];
+
+        d_C_x[0] = (d_C_x[0] + u) * kSCALE_F;
+        d_C_x[1] *= kSCALE_F;
+        d_C_x[2] = (d_C_x[2] + 1) * kSCALE_C;
+        d_C_x[3] *= kSCALE_C;
+
+        d_C_y[0] *= kSCALE_F;
+        d_C_y[1] = (d_C_y[1] + v) * kSCALE_F;
+        d_C_y[2] *= kSCALE_C;
+        d_C_y[3] = (d_C_y[3] + 1) * kSCALE_C;
+
+        d_xi_x[0] = new_idepth * fxl;
+        d_xi_x[1] = 0;
+        d_xi_x[2] = -new_idepth * u * fxl;
+        d_xi_x[3] = -u * v * fxl;
+        d_xi_x[4] = (1 + u * u) * fxl;
+        d_xi_x[5] = -v * fxl;
+
+        d_xi_y[0] = 0;
+        d_xi_y[1] = new_idepth * fyl;
+        d_xi_y[2] = -new_idepth * v * fyl;
+        d_xi_y[3] = -(1 + v * v) * fyl;
+        d_xi_y[4] = u * v * fyl;
+        d_xi_y[5] = u * fyl;
+      }
+
+      if (!done) {
+        // pattern sample idx at the current state (Residuals.cpp:177-256)
+        const float up = pu + c_pattern[idx][0], vp = pv + c_pattern[idx][1];
+        float ptp[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) ptp[i] = ((KRKi[3 * i] * up + KRKi[3 * i + 1] * vp) + KRKi[3 * i + 2] * 1.0f) + Kt[i] * idepth;
+        const float Ku = ptp[0] / ptp[2], Kv = ptp[1] / ptp[2];
+        bool bad = !(Ku > 1.1f && Kv > 1.1f && Ku < a.wM3G && Kv < a.hM3G);
+        float3 hit = make_float3(0.f, 0.f, 0.f);
+        if (!bad) {
+          hit = interp33(a.img0[target], Ku, Kv, a.w);
+          if (!isfinite(hit.x)) bad = true;
+        }
+        if (__any_sync(gmask, bad)) {
+          outcome = SOSBA_RES_OOB; ret_energy = old_energy; done = true;
+        } else {
+          const float residual = hit.x - (float)(affLL0 * color + affLL1);
+          const float drdA = (color - b0);
+          float w = sqrtf(a.outlierTHSum / (a.outlierTHSum + (hit.y * hit.y + hit.z * hit.z)));
+          w = 0.5f * (w + weight);
+          float hw = fabsf(residual) < a.huberTH ? 1 : a.huberTH / fabsf(residual);
+          const float e_term = w * w * hw * residual * residual * (2 - hw);
+          if (hw < 1) hw = sqrtf(hw);
+          hw = hw * w;
+          const float hx = hit.y * hw, hy = hit.z * hw;
+          const float resF = residual * hw;
+          float jab0 = drdA * hw, jab1 = hw;
+
+          const float energyLeft0 = seqsum8(gmask, e_term);
+          const float JIdxJIdx_00 = seqsum8(gmask, hx * hx);
+          const float JIdxJIdx_11 = seqsum8(gmask, hy * hy);
+          const float JIdxJIdx_10 = seqsum8(gmask, hx * hy);
+          const float JabJIdx_00 = seqsum8(gmask, drdA * hw * hx);
+          const float JabJIdx_01 = seqsum8(gmask, drdA * hw * hy);
+          const float JabJIdx_10 = seqsum8(gmask, hw * hx);
+          const float JabJIdx_11 = seqsum8(gmask, hw * hy);
+          const float JabJab_00 = seqsum8(gmask, drdA * drdA * hw * hw);
+          const float JabJab_01 = seqsum8(gmask, drdA * hw * hw);
+          const float JabJab_11 = seqsum8(gmask, hw * hw);
+          const float wJI2_sum = seqsum8(gmask, hw * hw * (hx * hx + hy * hy));
+          if (a.affModeA < 0) jab0 = 0;
+          if (a.affModeB < 0) jab1 = 0;
+
+          // candidate record: PointFrameResidual::J
+          float *J = (a.r_sel[r] ? a.J1 : a.J0) + (size_t)r * SOSBA_JREC;
+          J[JR_RES + idx] = resF;
+          J[JR_JIDX0 + idx] = hx;
+          J[JR_JIDX1 + idx] = hy;
+          J[JR_JAB0 + idx] = jab0;
+          J[JR_JAB1 + idx] = jab1;
+          {
+            const float4 g0 = make_float4(d_xi_x[0], d_xi_x[1], d_xi_x[2], d_xi_x[3]);
+            const float4 g1 = make_float4(d_xi_x[4], d_xi_x[5], d_xi_y[0], d_xi_y[1]);
+            const float4 g2 = make_float4(d_xi_y[2], d_xi_y[3], d_xi_y[4], d_xi_y[5]);
+            const float4 g3 = make_float4(d_C_x[0], d_C_x[1], d_C_x[2], d_C_x[3]);
+            const float4 g4 = make_float4(d_C_y[0], d_C_y[1], d_C_y[2], d_C_y[3]);
+            const float4 g5 = make_float4(d_d_x, d_d_y, JIdxJIdx_00, JIdxJIdx_10);
+            const float4 g6 = make_float4(JIdxJIdx_10, JIdxJIdx_11, JabJIdx_00, JabJIdx_01);
+            const float4 g7 = make_float4(JabJIdx_10, JabJIdx_11, JabJab_00, JabJab_01);
+            ((float4 *)(J + JR_GEO))[idx] = pick4(idx, g0, g1, g2, g3, g4, g5, g6, g7);
+            if (idx == 0) J[JR_JAB2 + 2] = JabJab_01;
+            if (idx == 1) J[JR_JAB2 + 3] = JabJab_11;
+          }
+          a.proj[(size_t)r * 16 + idx * 2] = Ku;
+          a.proj[(size_t)r * 16 + idx * 2 + 1] = Kv;
+
+          energyWO = energyLeft0;
+          float energyLeft = energyLeft0;
+          const float th = fmaxf(a.frameEnergyTH[host], a.frameEnergyTH[target]);
+          if (energyLeft > th || wJI2_sum < 2) { energyLeft = th; outcome = SOSBA_RES_OUTLIER; }
+          else outcome = SOSBA_RES_IN;
+          ret_energy = energyLeft;
+          if (idx == 0) {
+            a.r_new_energy[r] = energyLeft;
+            a.center[(size_t)r * 3 + 0] = cKu; a.center[(size_t)r * 3 + 1] = cKv; a.center[(size_t)r * 3 + 2] = c_new_idepth;
+            if (target == a.nf - 1) {  // input of setNewFrameEnergyTH
+              int pos = atomicAdd(&a.counts[4], 1);
+              a.newE[pos] = energyWO;
+            }
+          }
+        }
+      }
+    }
+    if (idx == 0) {
+      a.r_new_state[r] = (uint8_t)outcome;
+      a.r_new_energy_wo[r] = energyWO;
+      atomicAdd(&s_energy, (double)ret_energy);
+      atomicAdd(&s_cnt[outcome], 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_energy != 0.0) atomicAdd(&a.stats[0], s_energy);
+    if (s_cnt[0]) atomicAdd(&a.counts[0], s_cnt[0]);
+    if (s_cnt[1]) atomicAdd(&a.counts[1], s_cnt[1]);
+    if (s_cnt[2]) atomicAdd(&a.counts[2], s_cnt[2]);
+  }
+}
+
+__device__ __forceinline__ float bfly8(unsigned mask, float v) {
+  v += __shfl_xor_sync(mask, v, 1, 8);
+  v += __shfl_xor_sync(mask, v, 2, 8);
+  v += __shfl_xor_sync(mask, v, 4, 8);
+  return v;
+}
+
+// writes the 48-float commit record from a committed J record and the (JI_r, Jab_r, rr) of resApprox
+__device__ __forceinline__ void write_commit_record(const float *__restrict__ J, float *__restrict__ rec, int idx, float JI_r0, float JI_r1,
+                                                    float Jab_r0, float Jab_r1, float rr) {
+  // lanes 0..5 copy x/y (20 floats, 4 per lane: lane k -> floats 4k..4k+3), lane 5 the 2x2 sums, lane 6/7 the rest
+  const float *g = J + JR_GEO;  // Jpdxi0[6] Jpdxi1[6] Jpdc0[4] Jpdc1[4] Jpdd[2] JIdx2[4] JabJIdx[4] Jab2[4]
+  const float Jpdd0 = g[20], Jpdd1 = g[21];
+  const float a00 = g[22], a01 = g[23], a11 = g[25];
+  if (idx == 0) { rec[CR_X + 0] = g[12]; rec[CR_X + 1] = g[13]; rec[CR_X + 2] = g[14]; rec[CR_X + 3] = g[15]; }          // Jpdc0
+  if (idx == 1) { rec[CR_X + 4] = g[0]; rec[CR_X + 5] = g[1]; rec[CR_X + 6] = g[2]; rec[CR_X + 7] = g[3]; rec[CR_X + 8] = g[4]; rec[CR_X + 9] = g[5]; }
+  if (idx == 2) { rec[CR_Y + 0] = g[16]; rec[CR_Y + 1] = g[17]; rec[CR_Y + 2] = g[18]; rec[CR_Y + 3] = g[19]; }          // Jpdc1
+  if (idx == 3) { rec[CR_Y + 4] = g[6]; rec[CR_Y + 5] = g[7]; rec[CR_Y + 6] = g[8]; rec[CR_Y + 7] = g[9]; rec[CR_Y + 8] = g[10]; rec[CR_Y + 9] = g[11]; }
+  if (idx == 4) {
+    rec[CR_A + 0] = a00; rec[CR_A + 1] = a01; rec[CR_A + 2] = a11;
+    rec[CR_TR + 0] = g[26]; rec[CR_TR + 1] = g[27]; rec[CR_TR + 2] = g[28]; rec[CR_TR + 3] = g[29]; rec[CR_TR + 4] = JI_r0; rec[CR_TR + 5] = JI_r1;
+  }
+  if (idx == 5) {
+    rec[CR_BR + 0] = g[30]; rec[CR_BR + 1] = g[31]; rec[CR_BR + 2] = Jab_r0; rec[CR_BR + 3] = g[33]; rec[CR_BR + 4] = Jab_r1; rec[CR_BR + 5] = rr;
+    rec[CR_JPDD + 0] = Jpdd0; rec[CR_JPDD + 1] = Jpdd1;
+  }
+  // EFResidual::takeDataF: JpJdF = [Jpdxi^T (JIdx2 Jpdd) ; JabJIdx Jpdd]
+  const float v0 = a00 * Jpdd0 + a01 * Jpdd1, v1 = g[24] * Jpdd0 + a11 * Jpdd1;
+  if (idx < 6) rec[CR_JPJDF + idx] = g[idx] * v0 + g[6 + idx] * v1;
+  if (idx == 6) rec[CR_JPJDF + 6] = g[26] * Jpdd0 + g[27] * Jpdd1;
+  if (idx == 7) rec[CR_JPJDF + 7] = g[28] * Jpdd0 + g[29] * Jpdd1;
+}
+
+// a5 (+ a4 bookkeeping when fix != 0): 8 lanes per residual
+__global__ void __launch_bounds__(256) k_apply_res(LinArgs a, int fix) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = gid >> 3, idx = gid & 7;
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+  if (r >= a.R) return;
+  if (a.r_is_lin[r] | a.r_dropped[r]) return;
+  if (a.r_state[r] == SOSBA_RES_OOB) {  // applyRes(true): "can never go back from OOB" — nothing changes
+    if (fix && idx == 0 && !a.r_is_active[r]) { a.r_dropped[r] = 1; atomicAdd(&a.counts[3], 1); }
+    return;
+  }
+  const int ns = a.r_new_state[r];
+  bool active = false;
+  if (ns == SOSBA_RES_IN) {
+    active = true;
+    const int sel = a.r_sel[r];
+    const float *J = (sel ? a.J1 : a.J0) + (size_t)r * SOSBA_JREC;  // candidate becomes the committed record
+    const float res = J[JR_RES + idx], jx = J[JR_JIDX0 + idx], jy = J[JR_JIDX1 + idx], ja = J[JR_JAB0 + idx], jb = J[JR_JAB1 + idx];
+    const float JI_r0 = bfly8(gmask, res * jx), JI_r1 = bfly8(gmask, res * jy);
+    const float Jab_r0 = bfly8(gmask, res * ja), Jab_r1 = bfly8(gmask, res * jb), rr = bfly8(gmask, res * res);
+    write_commit_record(J, a.rec + (size_t)r * SOSBA_CREC, idx, JI_r0, JI_r1, Jab_r0, Jab_r1, rr);
+    __syncwarp(gmask);
+    if (idx == 0) a.r_sel[r] = (uint8_t)(sel ^ 1);  // std::swap(J, data->J)
+  }
+  if (idx == 0) {
+    a.r_is_active[r] = active ? 1 : 0;
+    a.r_state[r] = (uint8_t)ns;
+    a.r_energy[r] = a.r_new_energy[r];
+    if (fix) {
+      if (active) {
+        if (a.r_is_new[r]) {  // FullSystemOptimize.cpp:55-66
+          const int pt = a.r_point[r];
+          const float *pc = a.precalc + (size_t)(a.r_host[r] * a.nf + a.r_target[r]) * SOSBA_PRECALC_FLOATS;
+          const float *KRKi = pc + SOSBA_PC_KRKI, *Kt = pc + SOSBA_PC_KT;
+          const float pu = a.p_u[pt], pv = a.p_v[pt], id = a.p_idepth[pt] * kSCALE_IDEPTH;
+          float inf[3], ptp[3];
+          for (int i = 0; i < 3; i++) inf[i] = (KRKi[3 * i] * pu + KRKi[3 * i + 1] * pv) + KRKi[3 * i + 2] * 1.0f;
+          for (int i = 0; i < 3; i++) ptp[i] = inf[i] + Kt[i] * id;
+          const float ex = inf[0] / inf[2] - ptp[0] / ptp[2], ey = inf[1] / inf[2] - ptp[1] / ptp[2];
+          const float relBS = (float)(0.01 * (double)sqrtf(ex * ex + ey * ey));
+          if (relBS > 0.f) atomicMax((int *)&a.p_maxRelBaseline[pt], __float_as_int(relBS));  // positive floats order like ints
+          atomicAdd(&a.p_numGood[pt], 1);
+        }
+      } else {
+        a.r_dropped[r] = 1;  // toRemove -> ef->dropResidual (FullSystemOptimize.cpp:148-179)
+        atomicAdd(&a.counts[3], 1);
+      }
+    }
+  }
+}
+
+// PointFrameResidual::resetOOB (Residuals.h:81-86) over activeResiduals (FullSystemOptimize.cpp:316-329)
+__global__ void k_reset_oob(LinArgs a) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.R) return;
+  if (a.r_is_lin[r] | a.r_dropped[r]) return;
+  a.r_new_energy[r] = 0.f; a.r_energy[r] = 0.f;
+  a.r_new_state[r] = SOSBA_RES_OUTLIER; a.r_state[r] = SOSBA_RES_IN;
+}
+
+__device__ __forceinline__ float dot6(const float *x, const float *y) {
+  float s = x[0] * y[0];
+  for (int i = 1; i < 6; i++) s += x[i] * y[i];
+  return s;
+}
+__device__ __forceinline__ float dot4(const float *x, const float *y) {
+  float s = x[0] * y[0];
+  for (int i = 1; i < 4; i++) s += x[i] * y[i];
+  return s;
+}
+
+// a13  res_toZeroF = resF - J*delta ; isLinearized = true
+__global__ void __launch_bounds__(256) k_fix_linearization(LinArgs a, const int *__restrict__ ids, int n) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = gid >> 3, idx = gid & 7;
+  if (k >= n) return;
+  const int r = ids[k];
+  const float *J = (a.r_sel[r] ? a.J0 : a.J1) + (size_t)r * SOSBA_JREC;  // committed record = EFResidual::J
+  const float *dp = a.adHTdeltaF + 8 * (size_t)(a.r_host[r] + a.nf * a.r_target[r]);
+  const float *cD = a.calib + 6;
+  const float deltaF = a.p_deltaF[a.r_point[r]];
+  const float Jp_delta_x = dot6(J + JR_JPDXI0, dp) + dot4(J + JR_JPDC0, cD) + J[JR_JPDD] * deltaF;
+  const float Jp_delta_y = dot6(J + JR_JPDXI1, dp) + dot4(J + JR_JPDC1, cD) + J[JR_JPDD + 1] * deltaF;
+  float rtz = J[JR_RES + idx];
+  rtz = rtz - J[JR_JIDX0 + idx] * Jp_delta_x;
+  rtz = rtz - J[JR_JIDX1 + idx] * Jp_delta_y;
+  rtz = rtz - J[JR_JAB0 + idx] * dp[6];
+  rtz = rtz - J[JR_JAB1 + idx] * dp[7];
+  a.rtz[(size_t)r * 8 + idx] = rtz;
+  if (idx == 0) a.r_is_lin[r] = 1;
+}
+
+// commit records of linearised (mode 1) / to-be-marginalised (mode 2) residuals
+__global__ void __launch_bounds__(256) k_prep_records(LinArgs a, int mode, const int *__restrict__ list, int n) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = gid >> 3, idx = gid & 7;
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+  if (k >= n) return;
+  const int r = list ? list[k] : k;
+  if (a.r_dropped[r] || !a.r_is_active[r]) return;
+  if (mode == 1 && !a.r_is_lin[r]) return;
+  const float *J = (a.r_sel[r] ? a.J0 : a.J1) + (size_t)r * SOSBA_JREC;
+  float res = a.rtz[(size_t)r * 8 + idx];
+  const float jx = J[JR_JIDX0 + idx], jy = J[JR_JIDX1 + idx], ja = J[JR_JAB0 + idx], jb = J[JR_JAB1 + idx];
+  if (mode == 1) {  // AccumulatedTopHessian.cpp:76-97
+    const float *dp = a.adHTdeltaF + 8 * (size_t)(a.r_host[r] + a.nf * a.r_target[r]);
+    const float *cD = a.calib + 6;
+    const float dd = a.p_deltaF[a.r_point[r]];
+    const float Jp_delta_x = dot6(J + JR_JPDXI0, dp) + dot4(J + JR_JPDC0, cD) + J[JR_JPDD] * dd;
+    const float Jp_delta_y = dot6(J + JR_JPDXI1, dp) + dot4(J + JR_JPDC1, cD) + J[JR_JPDD + 1] * dd;
+    res = res + jx * Jp_delta_x;
+    res = res + jy * Jp_delta_y;
+    res = res + ja * dp[6];
+    res = res + jb * dp[7];
+  }
+  const float JI_r0 = bfly8(gmask, res * jx), JI_r1 = bfly8(gmask, res * jy);
+  const float Jab_r0 = bfly8(gmask, res * ja), Jab_r1 = bfly8(gmask, res * jb), rr = bfly8(gmask, res * res);
+  write_commit_record(J, a.rec + (size_t)r * SOSBA_CREC, idx, JI_r0, JI_r1, Jab_r0, Jab_r1, rr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// setNewFrameEnergyTH: exact k-th smallest (nth_element) by 4-pass radix select on the bit patterns of the
+// (non-negative) energies.  One CTA; the list is at most one entry per active point.
+__global__ void __launch_bounds__(1024) k_energy_th(ThArgs a) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_prefix, s_k;
+  const int n = a.counts[4];
+  const unsigned *v = (const unsigned *)a.newE;
+  if (n == 0) {
+    if (threadIdx.x == 0) { a.frameEnergyTH[a.nf - 1] = 12 * 12 * 8; a.thOut[0] = 12 * 12 * 8; }
+    return;
+  }
+  if (threadIdx.x == 0) { s_prefix = 0; s_k = (unsigned)(int)(a.thN * n); }
+  for (int pass = 3; pass >= 0; pass--) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix, shift = 8 * pass;
+    const unsigned himask = pass == 3 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      unsigned x = v[i];
+      if ((x & himask) == prefix) atomicAdd(&hist[(x >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned k = s_k, b = 0;
+      for (; b < 256; b++) { if (k < hist[b]) break; k -= hist[b]; }
+      s_k = k; s_prefix = prefix | (b << shift);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float nthElement = sqrtf(__uint_as_float(s_prefix));
+    float th = nthElement * a.thFacMedian;
+    th = 26.0f * a.thConstWeight + th * (1 - a.thConstWeight);
+    th = th * th;
+    th *= a.overallWeight * a.overallWeight;
+    a.frameEnergyTH[a.nf - 1] = th;
+    a.thOut[0] = th;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a14 / a17  one thread per reference point.  The warped buffers are written in place (index i) with
+// weight 0 for rejected points instead of being compacted: calcGSSSE sums them, zero rows add nothing.
+__device__ __forceinline__ float3 mul33(const float *M, float x, float y, float z) {
+  return make_float3((M[0] * x + M[1] * y) + M[2] * z, (M[3] * x + M[4] * y) + M[5] * z, (M[6] * x + M[7] * y) + M[8] * z);
+}
+
+__global__ void __launch_bounds__(256) k_track_res(TrackResArgs a) {
+  __shared__ float s_E, s_T, s_RT, s_N;
+  __shared__ int s_c[3];
+  if (threadIdx.x == 0) { s_E = s_T = s_RT = s_N = 0.f; s_c[0] = s_c[1] = s_c[2] = 0; }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float E = 0.f, sT = 0.f, sRT = 0.f, sN = 0.f;
+  int inE = 0, inW = 0, sat = 0;
+  if (i < a.n) {
+    const float x = a.pc[i], y = a.pc[a.n + i], id = a.pc[2 * a.n + i], refColor = a.pc[3 * a.n + i];
+    float3 pt;
+    float rx0 = 0.f, rx1 = 0.f, rx2 = 0.f;
+    if (a.kind == 0) {
+      pt = mul33(a.RKi, x, y, 1.f);
+    } else {  // scale * RKi (ScaleOptimizer.cpp:296-297): the matrix entries are scaled first
+      float sRKi[9];
+      for (int k = 0; k < 9; k++) sRKi[k] = a.scale * a.RKi[k];
+      pt = mul33(sRKi, x, y, 1.f);
+      float3 rx = mul33(a.RKi, x, y, 1.f);
+      rx0 = rx.x / id; rx1 = rx.y / id; rx2 = rx.z / id;
+    }
+    pt.x = pt.x + a.t[0] * id; pt.y = pt.y + a.t[1] * id; pt.z = pt.z + a.t[2] * id;
+    const float u = pt.x / pt.z, v = pt.y / pt.z;
+    const float Ku = a.fx * u + a.cx, Kv = a.fy * v + a.cy;
+    const float new_idepth = id / pt.z;
+    if (a.lvl == 0 && i % 32 == 0) {  // flow indicators (CoarseTracker.cpp:666-696)
+      float sKi[9];
+      for (int k = 0; k < 9; k++) sKi[k] = a.kind == 0 ? a.Ki[k] : a.scale * a.Ki[k];
+      float3 kp = mul33(sKi, x, y, 1.f);
+      float3 ptT = make_float3(kp.x + a.t[0] * id, kp.y + a.t[1] * id, kp.z + a.t[2] * id);
+      float KuT = a.fx * (ptT.x / ptT.z) + a.cx, KvT = a.fy * (ptT.y / ptT.z) + a.cy;
+      float3 ptT2 = make_float3(kp.x - a.t[0] * id, kp.y - a.t[1] * id, kp.z - a.t[2] * id);
+      float KuT2 = a.fx * (ptT2.x / ptT2.z) + a.cx, KvT2 = a.fy * (ptT2.y / ptT2.z) + a.cy;
+      float3 rp;
+      if (a.kind == 0) rp = mul33(a.RKi, x, y, 1.f);
+      else { float sRKi[9]; for (int k = 0; k < 9; k++) sRKi[k] = a.scale * a.RKi[k]; rp = mul33(sRKi, x, y, 1.f); }
+      float3 pt3 = make_float3(rp.x - a.t[0] * id, rp.y - a.t[1] * id, rp.z - a.t[2] * id);
+      float Ku3 = a.fx * (pt3.x / pt3.z) + a.cx, Kv3 = a.fy * (pt3.y / pt3.z) + a.cy;
+      sT += (KuT - x) * (KuT - x) + (KvT - y) * (KvT - y);
+      sT += (KuT2 - x) * (KuT2 - x) + (KvT2 - y) * (KvT2 - y);
+      sRT += (Ku - x) * (Ku - x) + (Kv - y) * (Kv - y);
+      sRT += (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
+      sN += 2;
+    }
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, o4 = 0.f, o5 = 0.f, o6 = 0.f, o7 = 0.f;
+    if (Ku > 2 && Kv > 2 && Ku < a.w - 3 && Kv < a.h - 3 && new_idepth > 0) {
+      float3 hit = interp33(a.img, Ku, Kv, a.w);
+      if (isfinite(hit.x)) {
+        const float residual = a.kind == 0 ? hit.x - (float)(a.aff0 * refColor + a.aff1) : hit.x - refColor;
+        const float hw = fabsf(residual) < a.huberTH ? 1 : a.huberTH / fabsf(residual);
+        if (fabsf(residual) > a.cutoffTH) {
+          E += a.maxEnergy; inE++; sat++;
+        } else {
+          E += hw * residual * residual * (2 - hw);
+          inE++; inW++;
+          if (a.kind == 0) { o0 = new_idepth; o1 = u; o2 = v; }
+          else { o0 = rx0; o1 = rx1; o2 = rx2; }
+          o3 = hit.y; o4 = hit.z; o5 = residual; o6 = hw; o7 = refColor;
+        }
+      }
+    }
+    const size_t c = a.cap;
+    a.warp[i] = o0; a.warp[c + i] = o1; a.warp[2 * c + i] = o2; a.warp[3 * c + i] = o3;
+    a.warp[4 * c + i] = o4; a.warp[5 * c + i] = o5; a.warp[6 * c + i] = o6; a.warp[7 * c + i] = o7;
+  }
+  // block reduction
+  for (int o = 16; o > 0; o >>= 1) {
+    E += __shfl_xor_sync(0xffffffffu, E, o); sT += __shfl_xor_sync(0xffffffffu, sT, o);
+    sRT += __shfl_xor_sync(0xffffffffu, sRT, o); sN += __shfl_xor_sync(0xffffffffu, sN, o);
+    inE += __shfl_xor_sync(0xffffffffu, inE, o); inW += __shfl_xor_sync(0xffffffffu, inW, o); sat += __shfl_xor_sync(0xffffffffu, sat, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&s_E, E); atomicAdd(&s_T, sT); atomicAdd(&s_RT, sRT); atomicAdd(&s_N, sN);
+    atomicAdd(&s_c[0], inE); atomicAdd(&s_c[1], inW); atomicAdd(&s_c[2], sat);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&a.acc[0], (double)s_E); atomicAdd(&a.acc[1], (double)s_T); atomicAdd(&a.acc[2], (double)s_RT); atomicAdd(&a.acc[3], (double)s_N);
+    atomicAdd(&a.icnt[0], s_c[0]); atomicAdd(&a.icnt[1], s_c[1]); atomicAdd(&a.icnt[2], s_c[2]);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+void launch_make_images(sosba *h, int slot, const float *d_color, const float *d_B) {
+  for (int l = 0; l < h->levels; l++) {
+    const int w = h->wl[l], hh = h->hl[l], n = w * hh;
+    const float *src = l == 0 ? d_color : h->slot_plane[slot] + h->lvl_off[l - 1];
+    const int wm = l == 0 ? w : h->wl[l - 1];
+    k_pyr<<<(n + 255) / 256, 256, 0, h->stream>>>(src, wm, h->slot_img[slot] + h->lvl_off[l], h->slot_plane[slot] + h->lvl_off[l], w, hh, l, d_B,
+                                                  h->cfg.gamma_weights_pixel_select);
+    h->launches++;
+  }
+}
+
+void launch_linearize(sosba *h, const LinArgs &a) {
+  if (a.R == 0) return;
+  const int blocks = (a.R * 8 + 255) / 256;
+  k_linearize<<<blocks, 256, 0, h->stream>>>(a);
+  h->launches++;
+}
+void launch_apply_res(sosba *h, const LinArgs &a, int fix) {
+  if (a.R == 0) return;
+  k_apply_res<<<(a.R * 8 + 255) / 256, 256, 0, h->stream>>>(a, fix);
+  h->launches++;
+}
+void launch_reset_oob(sosba *h, const LinArgs &a) {
+  if (a.R == 0) return;
+  k_reset_oob<<<(a.R + 255) / 256, 256, 0, h->stream>>>(a);
+  h->launches++;
+}
+void launch_fix_linearization(sosba *h, const LinArgs &a, const int *d_ids, int n) {
+  if (n == 0) return;
+  k_fix_linearization<<<(n * 8 + 255) / 256, 256, 0, h->stream>>>(a, d_ids, n);
+  h->launches++;
+}
+void launch_prep_records(sosba *h, const LinArgs &a, int mode, const int *d_list, int n) {
+  if (n == 0) return;
+  k_prep_records<<<(n * 8 + 255) / 256, 256, 0, h->stream>>>(a, mode, d_list, n);
+  h->launches++;
+}
+void launch_energy_th(sosba *h, const ThArgs &a) {
+  k_energy_th<<<1, 1024, 0, h->stream>>>(a);
+  h->launches++;
+}
+void launch_track_res(sosba *h, const TrackResArgs &a) {
+  if (a.n == 0) return;
+  k_track_res<<<(a.n + 255) / 256, 256, 0, h->stream>>>(a);
+  h->launches++;
+}

@@ -1,0 +1,146 @@
+// kernels.h — launchers of the sm_100a kernels (k_exact.cu: built with -fmad=false so per-residual float
+// expressions round exactly like the parity definition; k_accum.cu / k_solve.cu / k_tracker.cu).
+#pragma once
+#include "sosba_internal.h"
+
+// ---- k_exact.cu ---------------------------------------------------------------------------------
+struct LinArgs {
+  int R, nf;
+  const int *r_point, *r_target, *r_host;
+  uint8_t *r_state, *r_new_state, *r_is_lin, *r_is_active, *r_is_new, *r_sel, *r_dropped;
+  float *r_energy, *r_new_energy, *r_new_energy_wo;
+  float *J0, *J1, *rec, *rtz, *proj, *center;
+  const float *p_u, *p_v, *p_idepth, *p_idepth_zero, *p_color, *p_weights;
+  const float *p_deltaF;
+  float *p_maxRelBaseline;
+  int *p_numGood;
+  const float *precalc, *frameEnergyTH, *calib, *adHTdeltaF;  // calib: fxl fyl cxl cyl fxli fyli | cDeltaF[4]
+  const float4 *const *img0;
+  int w;              // level-0 width
+  float wM3G, hM3G;   // globalCalib.cpp:63-64
+  float huberTH, outlierTHSum, affModeA, affModeB;
+  double *stats;      // [0] energy
+  int *counts;        // 0 in, 1 oob, 2 outlier, 3 removed, 4 n newest-frame energies
+  float *newE;        // newest-frame energies (unordered)
+};
+
+void launch_make_images(sosba *h, int slot, const float *d_color, const float *d_B);
+void launch_linearize(sosba *h, const LinArgs &a);
+void launch_apply_res(sosba *h, const LinArgs &a, int fix);
+void launch_reset_oob(sosba *h, const LinArgs &a);
+void launch_fix_linearization(sosba *h, const LinArgs &a, const int *d_ids, int n);
+// mode 1: linearised residuals (resApprox = res_toZeroF + J*delta), mode 2: marginalisation (res_toZeroF);
+// list==nullptr -> all residuals.  Rewrites the commit record of every selected residual.
+void launch_prep_records(sosba *h, const LinArgs &a, int mode, const int *d_list, int n);
+// setNewFrameEnergyTH: k-th smallest of newE[0..counts[4]) -> frameEnergyTH[nf-1], thOut[0]
+struct ThArgs {
+  const float *newE;
+  int *counts;
+  float *frameEnergyTH;
+  int nf;
+  float thN, thFacMedian, thConstWeight, overallWeight;
+  float *thOut;
+};
+void launch_energy_th(sosba *h, const ThArgs &a);
+
+// tracker / scale optimizer (calcResPose / calcResScale): writes the 8 warped SoA arrays (masked, not
+// compacted: invalid points carry weight 0) and the sums
+struct TrackResArgs {
+  int n, lvl, w, h, cap;
+  const float *pc;        // u | v | idepth | color  (4 arrays of n)
+  const float4 *img;      // level image of the new frame
+  float RKi[9], Ki[9], t[3];
+  float fx, fy, cx, cy;
+  float aff0, aff1;
+  float huberTH, cutoffTH, maxEnergy;
+  float scale;            // scale variant only
+  int kind;               // 0 pose, 1 scale
+  float *warp;            // 8 arrays of cap floats
+  double *acc;            // [0] E [1] shiftT [2] shiftRT [3] shiftNum ; ints in icnt
+  int *icnt;              // [0] numTermsInE [1] numTermsInWarped [2] numSaturated
+};
+void launch_track_res(sosba *h, const TrackResArgs &a);
+
+// ---- k_accum.cu ---------------------------------------------------------------------------------
+struct AccArgs {
+  int R, P, nf, n_list;
+  const int *list;   // residual ids ordered by (host + target*nf)
+  int mode;          // 0 active, 1 linearised, 2 marginalisation (list = residuals of the chosen points)
+  const int *r_point, *r_target, *r_host;
+  const uint8_t *r_is_lin, *r_is_active, *r_dropped;
+  const float *rec;
+  double *accTop;    // [nf*nf*92]
+  int *counts;       // [5] += residuals accumulated
+};
+void launch_top_accumulate(sosba *h, const AccArgs &a);
+
+struct PointArgs {
+  int P, nf, D;
+  const int *plist;  // nullptr = all points, else the points to process (marginalisation)
+  int n_plist;
+  int mode;          // 0: A sums (non-linearised)  1: L sums (linearised)  2: marginalisation sums (-> L, A = 0)
+  const int *res_begin, *r_target, *p_host;
+  const uint8_t *r_is_lin, *r_is_active, *r_dropped;
+  const float *rec;
+  float *HddA, *bdA, *HcdA, *HddL, *bdL, *HcdL;
+};
+void launch_point_sums(sosba *h, const PointArgs &a);
+
+struct SCArgs {
+  int P, nf, D;
+  const int *plist;
+  int n_plist;
+  int shiftPriorToZero;
+  const int *res_begin, *r_target, *p_host;
+  const uint8_t *r_is_active, *r_dropped;
+  const float *rec;
+  const float *HddA, *bdA, *HcdA, *HddL, *bdL, *HcdL, *priorF, *deltaF;
+  float *HdiF, *bdSumF, *idepth_hessian, *maxRelBaseline;
+  const float *adHostF, *adTargetF;
+  double *accSC;     // [(D+1)*(D+1)] upper tiles
+};
+void launch_sc_accumulate(sosba *h, const SCArgs &a);
+
+// top blocks -> H (D*D), b (D): AccumulatedTopHessianSSE::stitchDoubleInternal + stitchDoubleMT epilogue
+void launch_stitch_top(sosba *h, const double *accTop, const double *adHost, const double *adTarget, int nf, double *H, double *b,
+                       int usePrior, const double *wprior, const float *cDeltaF);
+// accSC -> Hsc (D*D), bsc (D)
+void launch_finalize_sc(sosba *h, const double *accSC, int nf, double *H, double *b);
+
+// ---- k_solve.cu ---------------------------------------------------------------------------------
+struct SolveArgs {
+  int nf, D;
+  const double *HA, *bA, *HL, *bL, *Hsc, *bsc;   // stitched
+  const double *HM, *bM;                          // may be null
+  const double *wprior;                           // frame_delta at 4 + 16*nf
+  const float *cDeltaF;
+  double *x, *Hfinal, *bfinal;                    // out
+  const float *adHostF, *adTargetF;
+  float *xAd;                                     // [nf*nf*8] then xc[4]
+  int *status;                                    // [0] non-finite flag
+};
+void launch_solve(sosba *h, const SolveArgs &a);
+
+struct ResubArgs {
+  int P, nf;
+  const int *res_begin, *r_target, *p_host;
+  const uint8_t *r_is_active, *r_dropped;
+  const float *rec, *xAd;
+  const float *HcdA, *HcdL, *bdSumF, *HdiF;
+  float *step;
+  // doStepFromBackup for points (only when do_step): idepth_backup = idepth; idepth = idepth_zero = backup + step
+  int do_step;
+  float *idepth, *idepth_zero, *idepth_backup, *deltaF;
+  double *stats;  // [1] sum step^2  [2] sum |idepth_backup|  [3] count
+};
+void launch_resubstitute(sosba *h, const ResubArgs &a);
+
+// ---- k_tracker.cu -------------------------------------------------------------------------------
+struct TrackGSArgs {
+  int n, cap, kind;
+  const float *warp;
+  float fx, fy, a, b0;
+  float scale, tx, ty, tz;
+  double *acc;  // pose: 45 upper-tri sums at [8..53) ; scale: 3 sums at [8..11)
+};
+void launch_track_gs(sosba *h, const TrackGSArgs &a);

@@ -1,0 +1,1100 @@
+// sosba_api.cu — the C ABI of include/sosba.h on top of the sm_100a kernels.  Host C++ only orchestrates:
+// uploads, launch order, small read-backs.  There is no CPU implementation of any entry point: without a CUDA
+// device sosba_create fails with SOSBA_E_NOGPU.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "host_ba.h"
+#include "kernels.h"
+
+size_t solve_smem_bytes(int D);
+void launch_make_xad(sosba *h, const double *d_x, int nf, const float *adHostF, const float *adTargetF, float *xAd);
+void launch_scale_prior(sosba *h, float *priorF, const int *ids, int n, float fac);
+
+using sosba_host::BAState;
+using sosba_host::WindowTables;
+
+static thread_local char g_err[512] = "";
+void sosba_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct BA {
+  BAState st;
+  WindowTables wt;
+  double *d_HM = nullptr, *d_bM = nullptr;
+  bool have_HM = false;
+  int iterations_done = 0;
+};
+
+// per-handle host mirrors that the device kernels never read
+struct HostSide {
+  std::vector<int> p_host, res_begin, r_point, r_target;
+  std::vector<void *> allocs;
+  int n_lin = 0;
+  double *pin_d = nullptr;   // pinned scratch: [4096] doubles
+  int *pin_i = nullptr;      // pinned scratch: [64] ints
+  float *pin_f = nullptr;    // pinned scratch: [4096] floats
+  double *d_HMtmp = nullptr, *d_bMtmp = nullptr;
+  int *d_ids = nullptr; int ids_cap = 0;
+  int *d_status = nullptr;
+};
+static HostSide *HS(sosba *h);
+
+#define API extern "C" __attribute__((visibility("default")))
+#define CHECK_H(h) do { if (!(h)) { sosba_set_error("null handle"); return SOSBA_E_ARG; } cudaSetDevice((h)->device); } while (0)
+
+template <class T> static int dalloc(sosba *h, T **p, size_t n) {
+  if (n == 0) n = 1;
+  void *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+  if (e != cudaSuccess) { sosba_set_error("cudaMalloc(%zu) -> %s", n * sizeof(T), cudaGetErrorString(e)); return SOSBA_E_CUDA; }
+  cudaMemsetAsync(q, 0, n * sizeof(T), h->stream);
+  *p = (T *)q;
+  HS(h)->allocs.push_back(q);
+  return SOSBA_OK;
+}
+template <class T> static void dfree(sosba *h, T *&p) {
+  if (!p) return;
+  auto &v = HS(h)->allocs;
+  v.erase(std::remove(v.begin(), v.end(), (void *)p), v.end());
+  cudaFree((void *)p);
+  p = nullptr;
+}
+#define DALLOC(h, p, n) do { int rc__ = dalloc(h, &(p), (size_t)(n)); if (rc__) return rc__; } while (0)
+template <class T> static int up(sosba *h, T *dst, const T *src, size_t n) {
+  if (n == 0) return SOSBA_OK;
+  SOSBA_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  return SOSBA_OK;
+}
+template <class T> static int down(sosba *h, T *dst, const T *src, size_t n) {
+  if (n == 0) return SOSBA_OK;
+  SOSBA_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  return SOSBA_OK;
+}
+static int sync(sosba *h) {
+  SOSBA_CUDA(cudaStreamSynchronize(h->stream));
+  SOSBA_CUDA(cudaGetLastError());
+  return SOSBA_OK;
+}
+
+// the HostSide object is stored behind sosba::ba's neighbour: keep a side table keyed by handle
+#include <map>
+#include <mutex>
+static std::mutex g_mu;
+static std::map<sosba *, HostSide *> g_side;
+static HostSide *HS(sosba *h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_side.find(h);
+  if (it != g_side.end()) return it->second;
+  HostSide *s = new HostSide();
+  g_side[h] = s;
+  return s;
+}
+
+// ---- config -------------------------------------------------------------------------------------
+API void sosba_config_default(sosba_config *c, int32_t w, int32_t h) {
+  // util/settings.cpp:28-204 after settingsDefault(preset 0, mode 1) (main.cpp:27-90)
+  memset(c, 0, sizeof(*c));
+  c->w = w; c->h = h; c->pyr_levels = 0; c->max_frames = 16; c->num_threads = 1;
+  c->gamma_weights_pixel_select = 1; c->min_opt_iterations = 1;
+  c->huber_th = 9; c->outlier_th_sum_component = 50 * 50;
+  c->affine_opt_mode_a = 0; c->affine_opt_mode_b = 0;
+  c->coarse_cutoff_th = 20; c->idepth_fix_prior = 50 * 50; c->idepth_fix_prior_marg_fac = 600 * 600;
+  c->frame_energy_th_const_weight = 0.5f; c->frame_energy_th_n = 0.7f; c->frame_energy_th_fac_median = 1.5f;
+  c->overall_energy_th_weight = 1; c->initial_calib_hessian = 5e9f;
+  c->initial_rot_prior = 1e11f; c->initial_trans_prior = 1e10f; c->initial_aff_a_prior = 1e14f; c->initial_aff_b_prior = 1e14f;
+  c->marg_weight_fac = 0.5f * 0.5f; c->th_opt_iterations = 1.2f;
+}
+
+API const char *sosba_last_error(void) { return g_err; }
+
+// ---- lifetime -----------------------------------------------------------------------------------
+API int sosba_create(const sosba_config *cfg, int32_t device, sosba_t **out) {
+  if (!cfg || !out || cfg->w <= 0 || cfg->h <= 0) { sosba_set_error("bad config"); return SOSBA_E_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    sosba_set_error("no CUDA device: libsosba has no CPU fallback");
+    return SOSBA_E_NOGPU;
+  }
+  if (device < 0 || device >= ndev) { sosba_set_error("device %d out of range (%d devices)", device, ndev); return SOSBA_E_ARG; }
+  SOSBA_CUDA(cudaSetDevice(device));
+  sosba *h = new (std::nothrow) sosba();
+  if (!h) return SOSBA_E_ARG;
+  h->cfg = *cfg;
+  h->device = device;
+  cudaDeviceProp prop;
+  SOSBA_CUDA(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  SOSBA_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  // setGlobalCalib (globalCalib.cpp:39-49)
+  int wlvl = cfg->w, hlvl = cfg->h, lv = 1;
+  while (wlvl % 2 == 0 && hlvl % 2 == 0 && wlvl * hlvl > 5000 && lv < SOSBA_MAX_LEVELS) { wlvl /= 2; hlvl /= 2; lv++; }
+  h->levels = cfg->pyr_levels > 0 ? std::min<int>(cfg->pyr_levels, SOSBA_MAX_LEVELS) : lv;
+  size_t off = 0;
+  for (int l = 0; l < h->levels; l++) {
+    h->wl[l] = cfg->w >> l; h->hl[l] = cfg->h >> l;
+    h->lvl_off[l] = off;
+    off += ((size_t)h->wl[l] * h->hl[l] + 31) / 32 * 32;  // keep every level 512-byte aligned
+  }
+  h->lvl_off[h->levels] = off;
+  const int nslots = cfg->max_frames > 0 ? cfg->max_frames : 16;
+  h->slot_img.assign(nslots, nullptr);
+  h->slot_plane.assign(nslots, nullptr);
+  h->slot_valid.assign(nslots, 0);
+  HostSide *hs = HS(h);
+  for (int s = 0; s < nslots; s++) { DALLOC(h, h->slot_img[s], off); DALLOC(h, h->slot_plane[s], off); }
+  DALLOC(h, h->d_stage, (size_t)cfg->w * cfg->h);
+  DALLOC(h, h->d_B, 256);
+  h->h_pinned_bytes = (size_t)cfg->w * cfg->h * 4 * sizeof(float);
+  SOSBA_CUDA(cudaMallocHost((void **)&h->h_pinned, h->h_pinned_bytes));
+  SOSBA_CUDA(cudaMallocHost((void **)&hs->pin_d, 4096 * sizeof(double)));
+  SOSBA_CUDA(cudaMallocHost((void **)&hs->pin_i, 64 * sizeof(int)));
+  SOSBA_CUDA(cudaMallocHost((void **)&hs->pin_f, 4096 * sizeof(float)));
+  DALLOC(h, h->d_stats, 16);
+  DALLOC(h, h->d_counts, 16);
+  DALLOC(h, h->d_thOut, 4);
+  DALLOC(h, h->t_acc, 64);
+  DALLOC(h, hs->d_status, 4);
+  h->ba = new BA();
+  int rc = sync(h);
+  if (rc) return rc;
+  *out = h;
+  return SOSBA_OK;
+}
+
+int sosba_comm_destroy(sosba_t *h);
+
+API void sosba_destroy(sosba_t *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  sosba_comm_destroy(h);
+  HostSide *hs = HS(h);
+  for (void *p : hs->allocs) cudaFree(p);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (hs->pin_d) cudaFreeHost(hs->pin_d);
+  if (hs->pin_i) cudaFreeHost(hs->pin_i);
+  if (hs->pin_f) cudaFreeHost(hs->pin_f);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h->ba;
+  { std::lock_guard<std::mutex> lk(g_mu); g_side.erase(h); }
+  delete hs;
+  delete h;
+}
+
+API int sosba_set_stream(sosba_t *h, void *s) { CHECK_H(h); h->stream = s ? (cudaStream_t)s : h->own_stream; return SOSBA_OK; }
+API int sosba_synchronize(sosba_t *h) { CHECK_H(h); return sync(h); }
+API int64_t sosba_launch_count(const sosba_t *h) { return h ? h->launches : 0; }
+API int32_t sosba_pyr_levels(const sosba_t *h) { return h ? h->levels : 0; }
+
+// ---- a1 -----------------------------------------------------------------------------------------
+API int sosba_frame_make_images(sosba_t *h, int32_t slot, const float *color, const float *B) {
+  CHECK_H(h);
+  if (slot < 0 || slot >= (int)h->slot_img.size() || !color) { sosba_set_error("bad slot/color"); return SOSBA_E_ARG; }
+  const size_t n = (size_t)h->cfg.w * h->cfg.h;
+  int rc = sync(h);  // the pinned staging buffer is reused
+  if (rc) return rc;
+  memcpy(h->h_pinned, color, n * sizeof(float));
+  if ((rc = up(h, h->d_stage, h->h_pinned, n))) return rc;
+  if (B && (rc = up(h, h->d_B, B, 256))) return rc;
+  launch_make_images(h, slot, h->d_stage, B ? h->d_B : nullptr);
+  h->slot_valid[slot] = 1;
+  SOSBA_CUDA(cudaGetLastError());
+  return SOSBA_OK;
+}
+
+// device-resident input (bench: inputs already in HBM)
+API int sosba_frame_make_images_dev(sosba_t *h, int32_t slot, const float *color_dev, const float *B_dev) {
+  CHECK_H(h);
+  if (slot < 0 || slot >= (int)h->slot_img.size() || !color_dev) return SOSBA_E_ARG;
+  launch_make_images(h, slot, color_dev, B_dev);
+  h->slot_valid[slot] = 1;
+  SOSBA_CUDA(cudaGetLastError());
+  return SOSBA_OK;
+}
+
+API int sosba_frame_get_level(sosba_t *h, int32_t slot, int32_t lvl, float *dI3, float *absg) {
+  CHECK_H(h);
+  if (slot < 0 || slot >= (int)h->slot_img.size() || lvl < 0 || lvl >= h->levels || !h->slot_valid[slot]) { sosba_set_error("bad slot/level"); return SOSBA_E_ARG; }
+  const size_t n = (size_t)h->wl[lvl] * h->hl[lvl];
+  int rc = sync(h);
+  if (rc) return rc;
+  if (n * sizeof(float4) > h->h_pinned_bytes) return SOSBA_E_ARG;
+  if ((rc = down(h, (float4 *)h->h_pinned, h->slot_img[slot] + h->lvl_off[lvl], n))) return rc;
+  if ((rc = sync(h))) return rc;
+  const float *p = h->h_pinned;
+  for (size_t i = 0; i < n; i++) {
+    if (dI3) { dI3[3 * i] = p[4 * i]; dI3[3 * i + 1] = p[4 * i + 1]; dI3[3 * i + 2] = p[4 * i + 2]; }
+    if (absg) absg[i] = p[4 * i + 3];
+  }
+  return SOSBA_OK;
+}
+
+// ---- uploads ------------------------------------------------------------------------------------
+static int ensure_window(sosba *h, int nf) {
+  if (nf <= h->nf_alloc) return SOSBA_OK;
+  dfree(h, h->d_precalc); dfree(h, h->d_adHostF); dfree(h, h->d_adTargetF); dfree(h, h->d_adHTdeltaF); dfree(h, h->d_frameEnergyTH);
+  dfree(h, h->d_adHost); dfree(h, h->d_adTarget); dfree(h, h->d_calib); dfree(h, h->d_wprior); dfree(h, h->d_img0);
+  dfree(h, h->d_accTop); dfree(h, h->d_accSC); dfree(h, h->d_H); dfree(h, h->d_x); dfree(h, h->d_xAd);
+  HostSide *hs = HS(h);
+  dfree(h, hs->d_HMtmp); dfree(h, hs->d_bMtmp);
+  const size_t n2 = (size_t)nf * nf;
+  const int D = 4 + 8 * nf;
+  DALLOC(h, h->d_precalc, n2 * SOSBA_PRECALC_FLOATS);
+  DALLOC(h, h->d_adHostF, n2 * 64); DALLOC(h, h->d_adTargetF, n2 * 64); DALLOC(h, h->d_adHTdeltaF, n2 * 8);
+  DALLOC(h, h->d_frameEnergyTH, nf);
+  DALLOC(h, h->d_adHost, n2 * 64); DALLOC(h, h->d_adTarget, n2 * 64);
+  DALLOC(h, h->d_calib, 16);
+  DALLOC(h, h->d_wprior, 4 + 24 * (size_t)nf);
+  DALLOC(h, h->d_img0, nf);
+  DALLOC(h, h->d_accTop, 2 * n2 * SOSBA_TOPB);             // A | L
+  DALLOC(h, h->d_accSC, (size_t)(D + 1) * (D + 1));
+  DALLOC(h, h->d_H, 4 * ((size_t)D * D + D));              // A | L | SC | final
+  DALLOC(h, h->d_x, D);
+  DALLOC(h, h->d_xAd, n2 * 8 + 8);
+  DALLOC(h, hs->d_HMtmp, (size_t)D * D); DALLOC(h, hs->d_bMtmp, D);
+  h->nf_alloc = nf; h->D_alloc = D;
+  return SOSBA_OK;
+}
+
+static int window_apply(sosba *h, const sosba_window *w, bool full) {
+  const int nf = w->nf;
+  if (nf <= 0 || nf > 16) { sosba_set_error("nf=%d out of range", nf); return SOSBA_E_ARG; }
+  if (!full && nf != h->nf) { sosba_set_error("window_update before window_set"); return SOSBA_E_STATE; }
+  int rc;
+  if (full) {
+    if ((rc = ensure_window(h, nf))) return rc;
+    h->nf = nf;
+    h->frame_slot.assign(w->frame_slot, w->frame_slot + nf);
+    std::vector<const float4 *> img(nf);
+    for (int i = 0; i < nf; i++) {
+      const int s = w->frame_slot[i];
+      if (s < 0 || s >= (int)h->slot_img.size()) { sosba_set_error("frame_slot[%d]=%d", i, s); return SOSBA_E_ARG; }
+      img[i] = h->slot_img[s];
+    }
+    if ((rc = up(h, h->d_img0, img.data(), nf))) return rc;
+    const size_t n64 = (size_t)nf * nf * 64;
+    if ((rc = up(h, h->d_adHost, w->adHost, n64))) return rc;
+    if ((rc = up(h, h->d_adTarget, w->adTarget, n64))) return rc;
+    std::vector<float> f(2 * n64);
+    for (size_t i = 0; i < n64; i++) { f[i] = (float)w->adHost[i]; f[n64 + i] = (float)w->adTarget[i]; }
+    if ((rc = up(h, h->d_adHostF, f.data(), n64))) return rc;
+    if ((rc = up(h, h->d_adTargetF, f.data() + n64, n64))) return rc;
+    if ((rc = sync(h))) return rc;  // `img`, `f` are stack-owned
+  }
+  const size_t n2 = (size_t)nf * nf;
+  if ((rc = up(h, h->d_precalc, w->precalc, n2 * SOSBA_PRECALC_FLOATS))) return rc;
+  if ((rc = up(h, h->d_adHTdeltaF, w->adHTdeltaF, n2 * 8))) return rc;
+  if ((rc = up(h, h->d_frameEnergyTH, w->frame_energy_th, nf))) return rc;
+  float *c = h->h_calib;
+  for (int i = 0; i < 4; i++) c[i] = w->calib[i];
+  c[4] = 1.0f / c[0]; c[5] = 1.0f / c[1];  // CalibHessian::setValue, HessianBlocks.h:495-496
+  for (int i = 0; i < 4; i++) c[6 + i] = w->cDeltaF[i];
+  if ((rc = up(h, h->d_calib, c, 10))) return rc;
+  h->h_wprior.resize(4 + 24 * (size_t)nf);
+  double *wp = h->h_wprior.data();
+  if (full) { for (int i = 0; i < 4; i++) wp[i] = w->cPrior[i]; memcpy(wp + 4, w->frame_prior, sizeof(double) * 8 * nf); }
+  memcpy(wp + 4 + 8 * nf, w->frame_delta_prior, sizeof(double) * 8 * nf);
+  memcpy(wp + 4 + 16 * nf, w->frame_delta, sizeof(double) * 8 * nf);
+  if ((rc = up(h, h->d_wprior, wp, 4 + 24 * (size_t)nf))) return rc;
+  return sync(h);
+}
+API int sosba_window_set(sosba_t *h, const sosba_window *w) { CHECK_H(h); if (!w) return SOSBA_E_ARG; return window_apply(h, w, true); }
+API int sosba_window_update(sosba_t *h, const sosba_window *w) { CHECK_H(h); if (!w) return SOSBA_E_ARG; return window_apply(h, w, false); }
+
+static int ensure_points(sosba *h, int P) {
+  if (P <= h->P_alloc) return SOSBA_OK;
+  float **fl[] = {&h->p_u, &h->p_v, &h->p_idepth, &h->p_idepth_zero, &h->p_priorF, &h->p_deltaF, &h->p_HddA, &h->p_bdA, &h->p_HddL, &h->p_bdL,
+                  &h->p_HdiF, &h->p_bdSumF, &h->p_step, &h->p_idepth_backup, &h->p_idepth_hessian, &h->p_maxRelBaseline};
+  for (auto p : fl) dfree(h, *p);
+  dfree(h, h->p_color); dfree(h, h->p_weights); dfree(h, h->p_HcdA); dfree(h, h->p_HcdL); dfree(h, h->p_host); dfree(h, h->p_res_begin); dfree(h, h->p_numGood);
+  const size_t n = (size_t)P + (size_t)P / 4 + 64;
+  for (auto p : fl) DALLOC(h, *p, n);
+  DALLOC(h, h->p_color, n * 8); DALLOC(h, h->p_weights, n * 8); DALLOC(h, h->p_HcdA, n * 4); DALLOC(h, h->p_HcdL, n * 4);
+  DALLOC(h, h->p_host, n); DALLOC(h, h->p_res_begin, n + 1); DALLOC(h, h->p_numGood, n);
+  h->P_alloc = (int)n;
+  return SOSBA_OK;
+}
+
+API int sosba_points_set(sosba_t *h, const sosba_points *p) {
+  CHECK_H(h);
+  if (!p || p->n < 0) return SOSBA_E_ARG;
+  int rc = ensure_points(h, p->n);
+  if (rc) return rc;
+  const size_t n = p->n;
+  h->P = p->n;
+  HostSide *hs = HS(h);
+  hs->p_host.assign(p->host, p->host + n);
+  if ((rc = up(h, h->p_u, p->u, n)) || (rc = up(h, h->p_v, p->v, n)) || (rc = up(h, h->p_idepth, p->idepth, n)) ||
+      (rc = up(h, h->p_idepth_zero, p->idepth_zero, n)) || (rc = up(h, h->p_color, p->color, n * 8)) ||
+      (rc = up(h, h->p_weights, p->weights, n * 8)) || (rc = up(h, h->p_host, p->host, n)))
+    return rc;
+  if (p->priorF) { if ((rc = up(h, h->p_priorF, p->priorF, n))) return rc; } else cudaMemsetAsync(h->p_priorF, 0, n * 4, h->stream);
+  if (p->deltaF) { if ((rc = up(h, h->p_deltaF, p->deltaF, n))) return rc; } else cudaMemsetAsync(h->p_deltaF, 0, n * 4, h->stream);
+  float *z[] = {h->p_HddA, h->p_bdA, h->p_HddL, h->p_bdL, h->p_HdiF, h->p_bdSumF, h->p_step, h->p_idepth_backup, h->p_idepth_hessian, h->p_maxRelBaseline};
+  for (float *q : z) cudaMemsetAsync(q, 0, n * 4, h->stream);
+  cudaMemsetAsync(h->p_HcdA, 0, n * 16, h->stream); cudaMemsetAsync(h->p_HcdL, 0, n * 16, h->stream);
+  cudaMemsetAsync(h->p_numGood, 0, n * 4, h->stream);
+  cudaMemsetAsync(h->p_res_begin, 0, (n + 1) * 4, h->stream);
+  hs->res_begin.assign(n + 1, 0);
+  h->R = 0;
+  return sync(h);
+}
+
+API int sosba_points_update(sosba_t *h, const float *idepth, const float *idepth_zero, const float *deltaF) {
+  CHECK_H(h);
+  int rc;
+  if (idepth && (rc = up(h, h->p_idepth, idepth, h->P))) return rc;
+  if (idepth_zero && (rc = up(h, h->p_idepth_zero, idepth_zero, h->P))) return rc;
+  if (deltaF && (rc = up(h, h->p_deltaF, deltaF, h->P))) return rc;
+  return sync(h);
+}
+
+static int ensure_residuals(sosba *h, int R) {
+  if (R <= h->R_alloc) return SOSBA_OK;
+  int **il[] = {&h->r_point, &h->r_target, &h->r_host, &h->r_by_block};
+  uint8_t **ul[] = {&h->r_state, &h->r_new_state, &h->r_is_lin, &h->r_is_active, &h->r_is_new, &h->r_sel, &h->r_dropped};
+  float **fl[] = {&h->r_energy, &h->r_new_energy, &h->r_new_energy_wo};
+  for (auto p : il) dfree(h, *p);
+  for (auto p : ul) dfree(h, *p);
+  for (auto p : fl) dfree(h, *p);
+  dfree(h, h->r_J[0]); dfree(h, h->r_J[1]); dfree(h, h->r_rec); dfree(h, h->r_rtz); dfree(h, h->r_proj); dfree(h, h->r_center); dfree(h, h->d_newE);
+  const size_t n = (size_t)R + (size_t)R / 4 + 64;
+  for (auto p : il) DALLOC(h, *p, n);
+  for (auto p : ul) DALLOC(h, *p, n);
+  for (auto p : fl) DALLOC(h, *p, n);
+  DALLOC(h, h->r_J[0], n * SOSBA_JREC); DALLOC(h, h->r_J[1], n * SOSBA_JREC); DALLOC(h, h->r_rec, n * SOSBA_CREC);
+  DALLOC(h, h->r_rtz, n * 8); DALLOC(h, h->r_proj, n * 16); DALLOC(h, h->r_center, n * 3); DALLOC(h, h->d_newE, n);
+  h->R_alloc = (int)n;
+  return SOSBA_OK;
+}
+
+API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
+  CHECK_H(h);
+  if (!r || r->n < 0 || h->nf <= 0) { sosba_set_error("residuals_set needs window_set/points_set first"); return SOSBA_E_STATE; }
+  int rc = ensure_residuals(h, r->n);
+  if (rc) return rc;
+  HostSide *hs = HS(h);
+  const int n = r->n, nf = h->nf, P = h->P;
+  h->R = n;
+  hs->r_point.assign(r->point, r->point + n);
+  hs->r_target.assign(r->target, r->target + n);
+  std::vector<int> host(n), by_block(n), cnt(nf * nf + 1, 0);
+  hs->res_begin.assign(P + 1, 0);
+  int prev = -1;
+  for (int i = 0; i < n; i++) {
+    const int p = r->point[i], t = r->target[i];
+    if (p < prev || p >= P || t < 0 || t >= nf) { sosba_set_error("residual %d: point %d / target %d invalid or not point-major", i, p, t); return SOSBA_E_ARG; }
+    prev = p;
+    host[i] = hs->p_host[p];
+    if (host[i] < 0 || host[i] >= nf) { sosba_set_error("point %d: host %d invalid", p, host[i]); return SOSBA_E_ARG; }
+    hs->res_begin[p + 1]++;
+    cnt[host[i] + t * nf + 1]++;
+  }
+  for (int p = 0; p < P; p++) hs->res_begin[p + 1] += hs->res_begin[p];
+  for (int b = 0; b < nf * nf; b++) cnt[b + 1] += cnt[b];
+  for (int i = 0; i < n; i++) by_block[cnt[host[i] + r->target[i] * nf]++] = i;   // stable counting sort by block
+  std::vector<uint8_t> u8(n);
+  std::vector<float> e(n, 0.f);
+  hs->n_lin = 0;
+  if ((rc = up(h, h->r_point, r->point, n)) || (rc = up(h, h->r_target, r->target, n)) || (rc = up(h, h->r_host, host.data(), n)) ||
+      (rc = up(h, h->r_by_block, by_block.data(), n)) || (rc = up(h, h->p_res_begin, hs->res_begin.data(), P + 1)))
+    return rc;
+  auto upflag = [&](uint8_t *dst, const uint8_t *src, uint8_t dflt) -> int {
+    if (src) return up(h, dst, src, n);
+    cudaMemsetAsync(dst, dflt, n, h->stream);
+    return SOSBA_OK;
+  };
+  if ((rc = upflag(h->r_state, r->state, SOSBA_RES_IN)) || (rc = upflag(h->r_is_lin, r->is_linearized, 0)) ||
+      (rc = upflag(h->r_is_active, r->is_active, 0)) || (rc = upflag(h->r_is_new, r->is_new, 1)))
+    return rc;
+  if (r->is_linearized) for (int i = 0; i < n; i++) hs->n_lin += r->is_linearized[i] ? 1 : 0;
+  cudaMemsetAsync(h->r_new_state, SOSBA_RES_OUTLIER, n, h->stream);
+  cudaMemsetAsync(h->r_sel, 0, n, h->stream);
+  cudaMemsetAsync(h->r_dropped, 0, n, h->stream);
+  if (r->state_energy) { if ((rc = up(h, h->r_energy, r->state_energy, n)) || (rc = up(h, h->r_new_energy, r->state_energy, n))) return rc; }
+  else { cudaMemsetAsync(h->r_energy, 0, (size_t)n * 4, h->stream); cudaMemsetAsync(h->r_new_energy, 0, (size_t)n * 4, h->stream); }
+  for (int i = 0; i < n; i++) e[i] = -1.f;
+  if ((rc = up(h, h->r_new_energy_wo, e.data(), n))) return rc;
+  return sync(h);
+}
+
+static LinArgs lin_args(sosba *h) {
+  LinArgs a;
+  a.R = h->R; a.nf = h->nf;
+  a.r_point = h->r_point; a.r_target = h->r_target; a.r_host = h->r_host;
+  a.r_state = h->r_state; a.r_new_state = h->r_new_state; a.r_is_lin = h->r_is_lin; a.r_is_active = h->r_is_active; a.r_is_new = h->r_is_new;
+  a.r_sel = h->r_sel; a.r_dropped = h->r_dropped;
+  a.r_energy = h->r_energy; a.r_new_energy = h->r_new_energy; a.r_new_energy_wo = h->r_new_energy_wo;
+  a.J0 = h->r_J[0]; a.J1 = h->r_J[1]; a.rec = h->r_rec; a.rtz = h->r_rtz; a.proj = h->r_proj; a.center = h->r_center;
+  a.p_u = h->p_u; a.p_v = h->p_v; a.p_idepth = h->p_idepth; a.p_idepth_zero = h->p_idepth_zero; a.p_color = h->p_color; a.p_weights = h->p_weights;
+  a.p_deltaF = h->p_deltaF; a.p_maxRelBaseline = h->p_maxRelBaseline; a.p_numGood = h->p_numGood;
+  a.precalc = h->d_precalc; a.frameEnergyTH = h->d_frameEnergyTH; a.calib = h->d_calib; a.adHTdeltaF = h->d_adHTdeltaF;
+  a.img0 = (const float4 *const *)h->d_img0;
+  a.w = h->cfg.w; a.wM3G = (float)(h->cfg.w - 3); a.hM3G = (float)(h->cfg.h - 3);
+  a.huberTH = h->cfg.huber_th; a.outlierTHSum = h->cfg.outlier_th_sum_component; a.affModeA = h->cfg.affine_opt_mode_a; a.affModeB = h->cfg.affine_opt_mode_b;
+  a.stats = h->d_stats; a.counts = h->d_counts; a.newE = h->d_newE;
+  return a;
+}
+
+// ---- a3/a4/a5 -----------------------------------------------------------------------------------
+API int sosba_reset_oob(sosba_t *h) {
+  CHECK_H(h);
+  launch_reset_oob(h, lin_args(h));
+  SOSBA_CUDA(cudaGetLastError());
+  return SOSBA_OK;
+}
+
+// enqueue linearizeAll on the stream (no host sync)
+static void enqueue_linearize(sosba *h, int fix) {
+  cudaMemsetAsync(h->d_stats, 0, sizeof(double) * 1, h->stream);
+  cudaMemsetAsync(h->d_counts, 0, sizeof(int) * 5, h->stream);
+  LinArgs a = lin_args(h);
+  launch_linearize(h, a);
+  ThArgs t;
+  t.newE = h->d_newE; t.counts = h->d_counts; t.frameEnergyTH = h->d_frameEnergyTH; t.nf = h->nf;
+  t.thN = h->cfg.frame_energy_th_n; t.thFacMedian = h->cfg.frame_energy_th_fac_median; t.thConstWeight = h->cfg.frame_energy_th_const_weight;
+  t.overallWeight = h->cfg.overall_energy_th_weight; t.thOut = h->d_thOut;
+  launch_energy_th(h, t);
+  if (fix) launch_apply_res(h, a, 1);
+}
+
+static int read_linearize_out(sosba *h, sosba_linearize_out *out) {
+  HostSide *hs = HS(h);
+  int rc;
+  if ((rc = down(h, hs->pin_d, h->d_stats, 1)) || (rc = down(h, hs->pin_i, h->d_counts, 5)) || (rc = down(h, hs->pin_f, h->d_thOut, 1))) return rc;
+  if ((rc = sync(h))) return rc;
+  if (out) {
+    out->energy = hs->pin_d[0];
+    out->new_frame_energy_th = hs->pin_f[0];
+    out->n_in = hs->pin_i[0]; out->n_oob = hs->pin_i[1]; out->n_outlier = hs->pin_i[2]; out->n_removed = hs->pin_i[3];
+    out->reserved0 = 0;
+  }
+  return SOSBA_OK;
+}
+
+API int sosba_linearize_all(sosba_t *h, int32_t fix, sosba_linearize_out *out) {
+  CHECK_H(h);
+  if (h->nf <= 0) { sosba_set_error("no window"); return SOSBA_E_STATE; }
+  enqueue_linearize(h, fix != 0);
+  SOSBA_CUDA(cudaGetLastError());
+  return read_linearize_out(h, out);
+}
+
+API int sosba_apply_res(sosba_t *h) {
+  CHECK_H(h);
+  launch_apply_res(h, lin_args(h), 0);
+  SOSBA_CUDA(cudaGetLastError());
+  return SOSBA_OK;
+}
+
+static int upload_ids(sosba *h, const int32_t *ids, int n) {
+  HostSide *hs = HS(h);
+  if (n > hs->ids_cap) {
+    dfree(h, hs->d_ids);
+    DALLOC(h, hs->d_ids, (size_t)n * 2 + 64);
+    hs->ids_cap = n * 2 + 64;
+  }
+  int rc = up(h, hs->d_ids, ids, n);
+  if (rc) return rc;
+  return sync(h);
+}
+
+API int sosba_fix_linearization(sosba_t *h, const int32_t *ids, int32_t n) {
+  CHECK_H(h);
+  if (n < 0 || (n > 0 && !ids)) return SOSBA_E_ARG;
+  HostSide *hs = HS(h);
+  for (int i = 0; i < n; i++) if (ids[i] < 0 || ids[i] >= h->R) { sosba_set_error("residual id %d", ids[i]); return SOSBA_E_ARG; }
+  int rc = upload_ids(h, ids, n);
+  if (rc) return rc;
+  launch_fix_linearization(h, lin_args(h), hs->d_ids, n);
+  hs->n_lin += n;
+  SOSBA_CUDA(cudaGetLastError());
+  return sync(h);
+}
+
+// ---- read-back ----------------------------------------------------------------------------------
+template <class T> static int fetch(sosba *h, T *dst, const T *src, size_t n) {
+  if (!dst) return SOSBA_OK;
+  return down(h, dst, src, n);
+}
+
+API int sosba_residuals_get_state(sosba_t *h, uint8_t *state, uint8_t *new_state, float *energy, float *new_energy, float *new_energy_wo,
+                                  uint8_t *is_active, uint8_t *is_linearized) {
+  CHECK_H(h);
+  const size_t n = h->R;
+  int rc;
+  if ((rc = fetch(h, state, h->r_state, n)) || (rc = fetch(h, new_state, h->r_new_state, n)) || (rc = fetch(h, energy, h->r_energy, n)) ||
+      (rc = fetch(h, new_energy, h->r_new_energy, n)) || (rc = fetch(h, new_energy_wo, h->r_new_energy_wo, n)) ||
+      (rc = fetch(h, is_active, h->r_is_active, n)) || (rc = fetch(h, is_linearized, h->r_is_lin, n)))
+    return rc;
+  return sync(h);
+}
+
+API int sosba_residuals_get_jacobians(sosba_t *h, int32_t committed, float *J) {
+  CHECK_H(h);
+  if (!J) return SOSBA_E_ARG;
+  const size_t n = h->R;
+  std::vector<float> j0(n * SOSBA_JREC), j1(n * SOSBA_JREC);
+  std::vector<uint8_t> sel(n);
+  int rc;
+  if ((rc = down(h, j0.data(), h->r_J[0], n * SOSBA_JREC)) || (rc = down(h, j1.data(), h->r_J[1], n * SOSBA_JREC)) || (rc = down(h, sel.data(), h->r_sel, n)))
+    return rc;
+  if ((rc = sync(h))) return rc;
+  for (size_t i = 0; i < n; i++) {
+    const int which = committed ? 1 - sel[i] : sel[i];  // PointFrameResidual::J == J[sel], EFResidual::J == J[1-sel]
+    const float *s = (which ? j1.data() : j0.data()) + i * SOSBA_JREC;
+    float *o = J + i * SOSBA_J_FLOATS;
+    int k = 0;
+    for (int q = 0; q < 8; q++) o[k++] = s[JR_RES + q];
+    for (int q = 0; q < 12; q++) o[k++] = s[JR_JPDXI0 + q];
+    for (int q = 0; q < 8; q++) o[k++] = s[JR_JPDC0 + q];
+    o[k++] = s[JR_JPDD]; o[k++] = s[JR_JPDD + 1];
+    for (int q = 0; q < 16; q++) o[k++] = s[JR_JIDX0 + q];
+    for (int q = 0; q < 16; q++) o[k++] = s[JR_JAB0 + q];
+    for (int q = 0; q < 12; q++) o[k++] = s[JR_JIDX2 + q];
+  }
+  return SOSBA_OK;
+}
+
+API int sosba_residuals_get_aux(sosba_t *h, float *JpJdF, float *rtz, float *proj, float *center) {
+  CHECK_H(h);
+  const size_t n = h->R;
+  int rc;
+  std::vector<float> rec;
+  if (JpJdF) { rec.resize(n * SOSBA_CREC); if ((rc = down(h, rec.data(), h->r_rec, n * SOSBA_CREC))) return rc; }
+  if ((rc = fetch(h, rtz, h->r_rtz, n * 8)) || (rc = fetch(h, proj, h->r_proj, n * 16)) || (rc = fetch(h, center, h->r_center, n * 3))) return rc;
+  if ((rc = sync(h))) return rc;
+  if (JpJdF) for (size_t i = 0; i < n; i++) memcpy(JpJdF + 8 * i, rec.data() + i * SOSBA_CREC + CR_JPJDF, 8 * sizeof(float));
+  return SOSBA_OK;
+}
+
+API int sosba_points_get_stats(sosba_t *h, float *mrb, int32_t *ngr) {
+  CHECK_H(h);
+  int rc;
+  if ((rc = fetch(h, mrb, h->p_maxRelBaseline, h->P)) || (rc = fetch(h, ngr, h->p_numGood, h->P))) return rc;
+  return sync(h);
+}
+
+API int sosba_points_get_acc(sosba_t *h, float *HddA, float *bdA, float *HcdA, float *HddL, float *bdL, float *HcdL, float *HdiF, float *bdSumF) {
+  CHECK_H(h);
+  const size_t n = h->P;
+  int rc;
+  if ((rc = fetch(h, HddA, h->p_HddA, n)) || (rc = fetch(h, bdA, h->p_bdA, n)) || (rc = fetch(h, HcdA, h->p_HcdA, 4 * n)) ||
+      (rc = fetch(h, HddL, h->p_HddL, n)) || (rc = fetch(h, bdL, h->p_bdL, n)) || (rc = fetch(h, HcdL, h->p_HcdL, 4 * n)) ||
+      (rc = fetch(h, HdiF, h->p_HdiF, n)) || (rc = fetch(h, bdSumF, h->p_bdSumF, n)))
+    return rc;
+  return sync(h);
+}
+
+// ---- a6-a9 --------------------------------------------------------------------------------------
+static inline double *Hpart(sosba *h, int which) { const int D = 4 + 8 * h->nf; return h->d_H + (size_t)which * ((size_t)D * D + D); }
+static inline double *bpart(sosba *h, int which) { const int D = 4 + 8 * h->nf; return Hpart(h, which) + (size_t)D * D; }
+
+int sosba_allreduce_acc(sosba *h);  // comm.cu: no-op without a communicator
+
+// accumulateAF_MT + accumulateLF_MT + accumulateSCF_MT on the stream; results stay in d_H parts 0..2, counts[5..6]
+static int enqueue_accumulate(sosba *h) {
+  HostSide *hs = HS(h);
+  const int nf = h->nf, D = 4 + 8 * nf;
+  const size_t n2 = (size_t)nf * nf, HB = (size_t)D * D + D;
+  cudaMemsetAsync(h->d_accTop, 0, sizeof(double) * 2 * n2 * SOSBA_TOPB, h->stream);
+  cudaMemsetAsync(h->d_accSC, 0, sizeof(double) * (size_t)(D + 1) * (D + 1), h->stream);
+  cudaMemsetAsync(h->d_H, 0, sizeof(double) * 3 * HB, h->stream);
+  cudaMemsetAsync(h->d_counts + 5, 0, sizeof(int) * 2, h->stream);
+  LinArgs la = lin_args(h);
+  AccArgs a;
+  a.R = h->R; a.P = h->P; a.nf = nf; a.n_list = h->R; a.list = h->r_by_block; a.mode = 0;
+  a.r_point = h->r_point; a.r_target = h->r_target; a.r_host = h->r_host;
+  a.r_is_lin = h->r_is_lin; a.r_is_active = h->r_is_active; a.r_dropped = h->r_dropped;
+  a.rec = h->r_rec; a.accTop = h->d_accTop; a.counts = h->d_counts;
+  launch_top_accumulate(h, a);
+  PointArgs pa;
+  pa.P = h->P; pa.nf = nf; pa.D = D; pa.plist = nullptr; pa.n_plist = 0; pa.mode = 0;
+  pa.res_begin = h->p_res_begin; pa.r_target = h->r_target; pa.p_host = h->p_host;
+  pa.r_is_lin = h->r_is_lin; pa.r_is_active = h->r_is_active; pa.r_dropped = h->r_dropped; pa.rec = h->r_rec;
+  pa.HddA = h->p_HddA; pa.bdA = h->p_bdA; pa.HcdA = h->p_HcdA; pa.HddL = h->p_HddL; pa.bdL = h->p_bdL; pa.HcdL = h->p_HcdL;
+  launch_point_sums(h, pa);
+  if (hs->n_lin > 0) {
+    launch_prep_records(h, la, 1, nullptr, h->R);
+    AccArgs l = a;
+    l.mode = 1; l.accTop = h->d_accTop + n2 * SOSBA_TOPB; l.counts = h->d_counts + 1;  // counts[6]
+    launch_top_accumulate(h, l);
+    pa.mode = 1;
+    launch_point_sums(h, pa);
+  } else {
+    cudaMemsetAsync(h->p_HddL, 0, sizeof(float) * h->P, h->stream);
+    cudaMemsetAsync(h->p_bdL, 0, sizeof(float) * h->P, h->stream);
+    cudaMemsetAsync(h->p_HcdL, 0, sizeof(float) * 4 * h->P, h->stream);
+  }
+  SCArgs s;
+  s.P = h->P; s.nf = nf; s.D = D; s.plist = nullptr; s.n_plist = 0; s.shiftPriorToZero = 1;
+  s.res_begin = h->p_res_begin; s.r_target = h->r_target; s.p_host = h->p_host; s.r_is_active = h->r_is_active; s.r_dropped = h->r_dropped;
+  s.rec = h->r_rec; s.HddA = h->p_HddA; s.bdA = h->p_bdA; s.HcdA = h->p_HcdA; s.HddL = h->p_HddL; s.bdL = h->p_bdL; s.HcdL = h->p_HcdL;
+  s.priorF = h->p_priorF; s.deltaF = h->p_deltaF; s.HdiF = h->p_HdiF; s.bdSumF = h->p_bdSumF; s.idepth_hessian = h->p_idepth_hessian;
+  s.maxRelBaseline = h->p_maxRelBaseline; s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.accSC = h->d_accSC;
+  launch_sc_accumulate(h, s);
+  int rc = sosba_allreduce_acc(h);   // points are sharded across ranks: sum the block tables (identical on every rank afterwards)
+  if (rc) return rc;
+  launch_stitch_top(h, h->d_accTop, h->d_adHost, h->d_adTarget, nf, Hpart(h, 0), bpart(h, 0), 0, h->d_wprior, h->d_calib + 6);
+  launch_stitch_top(h, h->d_accTop + n2 * SOSBA_TOPB, h->d_adHost, h->d_adTarget, nf, Hpart(h, 1), bpart(h, 1), 1, h->d_wprior, h->d_calib + 6);
+  launch_finalize_sc(h, h->d_accSC, nf, Hpart(h, 2), bpart(h, 2));
+  SOSBA_CUDA(cudaGetLastError());
+  return SOSBA_OK;
+}
+
+API int sosba_accumulate(sosba_t *h, double *HA, double *bA, double *HL, double *bL, double *Hsc, double *bsc, int32_t *resInA, int32_t *resInL) {
+  CHECK_H(h);
+  if (h->nf <= 0) return SOSBA_E_STATE;
+  int rc = enqueue_accumulate(h);
+  if (rc) return rc;
+  const int D = 4 + 8 * h->nf;
+  HostSide *hs = HS(h);
+  if ((rc = fetch(h, HA, Hpart(h, 0), (size_t)D * D)) || (rc = fetch(h, bA, bpart(h, 0), D)) || (rc = fetch(h, HL, Hpart(h, 1), (size_t)D * D)) ||
+      (rc = fetch(h, bL, bpart(h, 1), D)) || (rc = fetch(h, Hsc, Hpart(h, 2), (size_t)D * D)) || (rc = fetch(h, bsc, bpart(h, 2), D)) ||
+      (rc = down(h, hs->pin_i, h->d_counts + 5, 2)))
+    return rc;
+  if ((rc = sync(h))) return rc;
+  if (resInA) *resInA = hs->pin_i[0];
+  if (resInL) *resInL = hs->pin_i[1];
+  return SOSBA_OK;
+}
+
+// ---- a10/a11 ------------------------------------------------------------------------------------
+static ResubArgs resub_args(sosba *h, int do_step) {
+  ResubArgs r;
+  r.P = h->P; r.nf = h->nf; r.res_begin = h->p_res_begin; r.r_target = h->r_target; r.p_host = h->p_host;
+  r.r_is_active = h->r_is_active; r.r_dropped = h->r_dropped; r.rec = h->r_rec; r.xAd = h->d_xAd;
+  r.HcdA = h->p_HcdA; r.HcdL = h->p_HcdL; r.bdSumF = h->p_bdSumF; r.HdiF = h->p_HdiF; r.step = h->p_step;
+  r.do_step = do_step; r.idepth = h->p_idepth; r.idepth_zero = h->p_idepth_zero; r.idepth_backup = h->p_idepth_backup; r.deltaF = h->p_deltaF;
+  r.stats = h->d_stats;
+  return r;
+}
+
+static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int do_step) {
+  HostSide *hs = HS(h);
+  const int nf = h->nf, D = 4 + 8 * nf;
+  int rc = enqueue_accumulate(h);
+  if (rc) return rc;
+  cudaMemsetAsync(hs->d_status, 0, sizeof(int), h->stream);
+  cudaMemsetAsync(h->d_stats + 1, 0, sizeof(double) * 3, h->stream);
+  SolveArgs s;
+  s.nf = nf; s.D = D;
+  s.HA = Hpart(h, 0); s.bA = bpart(h, 0); s.HL = Hpart(h, 1); s.bL = bpart(h, 1); s.Hsc = Hpart(h, 2); s.bsc = bpart(h, 2);
+  s.HM = d_HM; s.bM = d_bM; s.wprior = h->d_wprior; s.cDeltaF = h->d_calib + 6;
+  s.x = h->d_x; s.Hfinal = Hpart(h, 3); s.bfinal = bpart(h, 3);
+  s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.xAd = h->d_xAd; s.status = hs->d_status;
+  launch_solve(h, s);
+  launch_resubstitute(h, resub_args(h, do_step));
+  SOSBA_CUDA(cudaGetLastError());
+  return SOSBA_OK;
+}
+
+API int sosba_solve_system(sosba_t *h, const double *HM, const double *bM, double *x, double *Hf, double *bf) {
+  CHECK_H(h);
+  if (h->nf <= 0) return SOSBA_E_STATE;
+  HostSide *hs = HS(h);
+  const int D = 4 + 8 * h->nf;
+  int rc;
+  const bool prior = HM && bM;
+  if (prior) {
+    if ((rc = up(h, hs->d_HMtmp, HM, (size_t)D * D)) || (rc = up(h, hs->d_bMtmp, bM, D))) return rc;
+    if ((rc = sync(h))) return rc;
+  }
+  if ((rc = enqueue_solve(h, prior ? hs->d_HMtmp : nullptr, prior ? hs->d_bMtmp : nullptr, 0))) return rc;
+  if ((rc = fetch(h, x, h->d_x, D)) || (rc = fetch(h, Hf, Hpart(h, 3), (size_t)D * D)) || (rc = fetch(h, bf, bpart(h, 3), D)) ||
+      (rc = down(h, hs->pin_i, hs->d_status, 1)))
+    return rc;
+  if ((rc = sync(h))) return rc;
+  if (hs->pin_i[0]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
+  return SOSBA_OK;
+}
+
+API int sosba_resubstitute(sosba_t *h, const double *x, float *step) {
+  CHECK_H(h);
+  if (!x || h->nf <= 0) return SOSBA_E_ARG;
+  const int D = 4 + 8 * h->nf;
+  int rc;
+  if ((rc = up(h, h->d_x, x, D))) return rc;
+  if ((rc = sync(h))) return rc;
+  launch_make_xad(h, h->d_x, h->nf, h->d_adHostF, h->d_adTargetF, h->d_xAd);
+  launch_resubstitute(h, resub_args(h, 0));
+  SOSBA_CUDA(cudaGetLastError());
+  if ((rc = fetch(h, step, h->p_step, h->P))) return rc;
+  return sync(h);
+}
+
+// ---- marginalizePointsF ---------------------------------------------------------------------------
+API int sosba_marginalize_points(sosba_t *h, const int32_t *ids, int32_t n, double *H, double *b, int32_t *resInM) {
+  CHECK_H(h);
+  if (n < 0 || (n > 0 && !ids) || !H || !b || h->nf <= 0) return SOSBA_E_ARG;
+  HostSide *hs = HS(h);
+  const int nf = h->nf, D = 4 + 8 * nf;
+  const size_t n2 = (size_t)nf * nf, HB = (size_t)D * D + D;
+  // residual list of the chosen points, ordered by block
+  std::vector<int> rl;
+  for (int i = 0; i < n; i++) {
+    if (ids[i] < 0 || ids[i] >= h->P) { sosba_set_error("point id %d", ids[i]); return SOSBA_E_ARG; }
+    for (int r = hs->res_begin[ids[i]]; r < hs->res_begin[ids[i] + 1]; r++) rl.push_back(r);
+  }
+  std::stable_sort(rl.begin(), rl.end(), [&](int a, int c) {
+    return hs->p_host[hs->r_point[a]] + hs->r_target[a] * nf < hs->p_host[hs->r_point[c]] + hs->r_target[c] * nf;
+  });
+  std::vector<int> all(ids, ids + n);
+  all.insert(all.end(), rl.begin(), rl.end());
+  int rc = upload_ids(h, all.data(), (int)all.size());
+  if (rc) return rc;
+  const int *d_pl = hs->d_ids, *d_rl = hs->d_ids + n;
+  launch_scale_prior(h, h->p_priorF, d_pl, n, h->cfg.idepth_fix_prior_marg_fac);  // EnergyFunctional.cpp:901
+  cudaMemsetAsync(h->d_accTop, 0, sizeof(double) * n2 * SOSBA_TOPB, h->stream);
+  cudaMemsetAsync(h->d_accSC, 0, sizeof(double) * (size_t)(D + 1) * (D + 1), h->stream);
+  cudaMemsetAsync(h->d_H, 0, sizeof(double) * 3 * HB, h->stream);
+  cudaMemsetAsync(h->d_counts + 5, 0, sizeof(int) * 2, h->stream);
+  LinArgs la = lin_args(h);
+  launch_prep_records(h, la, 2, d_rl, (int)rl.size());
+  AccArgs a;
+  a.R = h->R; a.P = h->P; a.nf = nf; a.n_list = (int)rl.size(); a.list = d_rl; a.mode = 2;
+  a.r_point = h->r_point; a.r_target = h->r_target; a.r_host = h->r_host;
+  a.r_is_lin = h->r_is_lin; a.r_is_active = h->r_is_active; a.r_dropped = h->r_dropped;
+  a.rec = h->r_rec; a.accTop = h->d_accTop; a.counts = h->d_counts;
+  launch_top_accumulate(h, a);
+  PointArgs pa;
+  pa.P = h->P; pa.nf = nf; pa.D = D; pa.plist = d_pl; pa.n_plist = n; pa.mode = 2;
+  pa.res_begin = h->p_res_begin; pa.r_target = h->r_target; pa.p_host = h->p_host;
+  pa.r_is_lin = h->r_is_lin; pa.r_is_active = h->r_is_active; pa.r_dropped = h->r_dropped; pa.rec = h->r_rec;
+  pa.HddA = h->p_HddA; pa.bdA = h->p_bdA; pa.HcdA = h->p_HcdA; pa.HddL = h->p_HddL; pa.bdL = h->p_bdL; pa.HcdL = h->p_HcdL;
+  launch_point_sums(h, pa);
+  SCArgs s;
+  s.P = h->P; s.nf = nf; s.D = D; s.plist = d_pl; s.n_plist = n; s.shiftPriorToZero = 0;
+  s.res_begin = h->p_res_begin; s.r_target = h->r_target; s.p_host = h->p_host; s.r_is_active = h->r_is_active; s.r_dropped = h->r_dropped;
+  s.rec = h->r_rec; s.HddA = h->p_HddA; s.bdA = h->p_bdA; s.HcdA = h->p_HcdA; s.HddL = h->p_HddL; s.bdL = h->p_bdL; s.HcdL = h->p_HcdL;
+  s.priorF = h->p_priorF; s.deltaF = h->p_deltaF; s.HdiF = h->p_HdiF; s.bdSumF = h->p_bdSumF; s.idepth_hessian = h->p_idepth_hessian;
+  s.maxRelBaseline = h->p_maxRelBaseline; s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.accSC = h->d_accSC;
+  launch_sc_accumulate(h, s);
+  if ((rc = sosba_allreduce_acc(h))) return rc;
+  launch_stitch_top(h, h->d_accTop, h->d_adHost, h->d_adTarget, nf, Hpart(h, 0), bpart(h, 0), 0, h->d_wprior, h->d_calib + 6);
+  launch_finalize_sc(h, h->d_accSC, nf, Hpart(h, 2), bpart(h, 2));
+  SOSBA_CUDA(cudaGetLastError());
+  std::vector<double> M(HB), Msc(HB);
+  if ((rc = down(h, M.data(), Hpart(h, 0), HB)) || (rc = down(h, Msc.data(), Hpart(h, 2), HB)) || (rc = down(h, hs->pin_i, h->d_counts + 5, 1))) return rc;
+  if ((rc = sync(h))) return rc;
+  for (size_t i = 0; i < (size_t)D * D; i++) H[i] = M[i] - Msc[i];
+  for (int i = 0; i < D; i++) b[i] = M[(size_t)D * D + i] - Msc[(size_t)D * D + i];
+  if (resInM) *resInM = hs->pin_i[0];
+  return SOSBA_OK;
+}
+
+// ---- tracker / scale optimizer ----------------------------------------------------------------------
+API int sosba_tracker_make_k(sosba_t *h, const float calib[4]) {  // ScaleOptimizer::makeK (ScaleOptimizer.cpp:95-118)
+  CHECK_H(h);
+  float (*K)[4] = h->t_K;
+  for (int i = 0; i < 4; i++) K[0][i] = calib[i];
+  for (int l = 1; l < h->levels; l++) {
+    K[l][0] = K[l - 1][0] * 0.5;
+    K[l][1] = K[l - 1][1] * 0.5;
+    K[l][2] = (K[0][2] + 0.5) / ((int)1 << l) - 0.5;
+    K[l][3] = (K[0][3] + 0.5) / ((int)1 << l) - 0.5;
+  }
+  h->t_haveK = true;
+  return SOSBA_OK;
+}
+
+static void make_Ki(const float K[4], float Ki[9]) {
+  for (int i = 0; i < 9; i++) Ki[i] = 0.f;
+  Ki[0] = 1.0f / K[0]; Ki[4] = 1.0f / K[1]; Ki[2] = -K[2] / K[0]; Ki[5] = -K[3] / K[1]; Ki[8] = 1.f;
+}
+static void mul33f(const float *A, const float *B, float *C) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) C[3 * i + j] = (A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j]) + A[3 * i + 2] * B[6 + j];
+}
+
+API int sosba_tracker_set_ref(sosba_t *h, int32_t lvl, int32_t n, const float *u, const float *v, const float *id, const float *c) {
+  CHECK_H(h);
+  if (lvl < 0 || lvl >= h->levels || n < 0) return SOSBA_E_ARG;
+  if (n > h->t_cap[lvl]) {
+    dfree(h, h->t_pc[lvl]);
+    h->t_cap[lvl] = n + n / 4 + 64;
+    DALLOC(h, h->t_pc[lvl], 4 * (size_t)h->t_cap[lvl]);
+  }
+  if (n > h->t_warp_cap) {
+    dfree(h, h->t_warp);
+    h->t_warp_cap = n + n / 4 + 64;
+    DALLOC(h, h->t_warp, 8 * (size_t)h->t_warp_cap);
+  }
+  h->t_n[lvl] = n;
+  int rc;
+  if ((rc = up(h, h->t_pc[lvl], u, n)) || (rc = up(h, h->t_pc[lvl] + n, v, n)) || (rc = up(h, h->t_pc[lvl] + 2 * (size_t)n, id, n)) ||
+      (rc = up(h, h->t_pc[lvl] + 3 * (size_t)n, c, n)))
+    return rc;
+  return sync(h);
+}
+
+static int track_res_common(sosba *h, int kind, int lvl, int slot, const float R[9], const float t[3], const float K[4], float aff0, float aff1,
+                            float scale, float cutoff, double out6[6], int32_t counts[3]) {
+  HostSide *hs = HS(h);
+  if (!h->t_haveK) { sosba_set_error("tracker_make_k first"); return SOSBA_E_STATE; }
+  if (lvl < 0 || lvl >= h->levels || slot < 0 || slot >= (int)h->slot_img.size() || !h->slot_valid[slot]) { sosba_set_error("bad level/slot"); return SOSBA_E_ARG; }
+  TrackResArgs a;
+  a.n = h->t_n[lvl]; a.lvl = lvl; a.w = h->wl[lvl]; a.h = h->hl[lvl]; a.cap = h->t_warp_cap;
+  a.pc = h->t_pc[lvl]; a.img = h->slot_img[slot] + h->lvl_off[lvl];
+  make_Ki(h->t_K[lvl], a.Ki);
+  mul33f(R, a.Ki, a.RKi);
+  for (int i = 0; i < 3; i++) a.t[i] = t[i];
+  a.fx = K[0]; a.fy = K[1]; a.cx = K[2]; a.cy = K[3];
+  a.aff0 = aff0; a.aff1 = aff1;
+  a.huberTH = h->cfg.huber_th; a.cutoffTH = cutoff; a.maxEnergy = 2 * a.huberTH * cutoff - a.huberTH * a.huberTH;
+  a.scale = scale; a.kind = kind; a.warp = h->t_warp; a.acc = h->t_acc; a.icnt = h->d_counts + 8;
+  cudaMemsetAsync(h->t_acc, 0, sizeof(double) * 8, h->stream);
+  cudaMemsetAsync(h->d_counts + 8, 0, sizeof(int) * 3, h->stream);
+  launch_track_res(h, a);
+  SOSBA_CUDA(cudaGetLastError());
+  int rc;
+  if ((rc = down(h, hs->pin_d, h->t_acc, 4)) || (rc = down(h, hs->pin_i, h->d_counts + 8, 3))) return rc;
+  if ((rc = sync(h))) return rc;
+  const float E = (float)hs->pin_d[0], sT = (float)hs->pin_d[1], sRT = (float)hs->pin_d[2], sN = (float)hs->pin_d[3];
+  const int nE = hs->pin_i[0], nW = hs->pin_i[1], nS = hs->pin_i[2];
+  if (counts) { counts[0] = nE; counts[1] = nW; counts[2] = nS; }
+  h->t_warp_n[lvl] = (nW + 3) / 4 * 4;  // padded to the SSE width (CoarseTracker.cpp:736-746)
+  h->t_warp_lvl = lvl; h->t_warp_kind = kind;
+  if (out6) {
+    out6[0] = E; out6[1] = nE; out6[2] = sT / (sN + 0.1); out6[3] = 0; out6[4] = sRT / (sN + 0.1); out6[5] = nS / (float)nE;
+  }
+  return SOSBA_OK;
+}
+
+API int sosba_tracker_calc_res_pose(sosba_t *h, int32_t lvl, int32_t slot, const double refToNew[12], const float affLL[2], float cutoff,
+                                    double out6[6], int32_t counts[3]) {
+  CHECK_H(h);
+  if (!refToNew || !affLL) return SOSBA_E_ARG;
+  float R[9], t[3];
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) R[3 * i + j] = (float)refToNew[4 * i + j]; t[i] = (float)refToNew[4 * i + 3]; }
+  if (lvl < 0 || lvl >= h->levels) return SOSBA_E_ARG;
+  return track_res_common(h, 0, lvl, slot, R, t, h->t_K[lvl], affLL[0], affLL[1], 1.f, cutoff, out6, counts);
+}
+
+API int sosba_tracker_calc_gs_pose(sosba_t *h, int32_t lvl, float a, float b0, double H[64], double b[8]) {
+  CHECK_H(h);
+  HostSide *hs = HS(h);
+  if (lvl != h->t_warp_lvl || h->t_warp_kind != 0) { sosba_set_error("calc_gs_pose needs calc_res_pose at the same level first"); return SOSBA_E_STATE; }
+  TrackGSArgs g;
+  g.n = h->t_n[lvl]; g.cap = h->t_warp_cap; g.kind = 0; g.warp = h->t_warp; g.fx = h->t_K[lvl][0]; g.fy = h->t_K[lvl][1]; g.a = a; g.b0 = b0;
+  g.scale = 1.f; g.tx = g.ty = g.tz = 0.f; g.acc = h->t_acc;
+  cudaMemsetAsync(h->t_acc + 8, 0, sizeof(double) * 48, h->stream);
+  launch_track_gs(h, g);
+  SOSBA_CUDA(cudaGetLastError());
+  int rc;
+  if ((rc = down(h, hs->pin_d, h->t_acc + 8, 45))) return rc;
+  if ((rc = sync(h))) return rc;
+  float A[9][9];
+  int q = 0;
+  for (int r = 0; r < 9; r++) for (int c = r; c < 9; c++) { A[r][c] = A[c][r] = (float)hs->pin_d[q++]; }
+  const int n = h->t_warp_n[lvl];
+  const float invn = 1.0f / n;   // CoarseTracker.cpp:595-596: divided by the padded count
+  const float sc[8] = {1.0f, 1.0f, 1.0f, 0.5f, 0.5f, 0.5f, 10.0f, 1000.0f};  // SCALE_XI_ROT x3, SCALE_XI_TRANS x3, SCALE_A, SCALE_B (:598-609)
+  for (int r = 0; r < 8; r++) {
+    for (int c = 0; c < 8; c++) H[8 * r + c] = (double)A[r][c] * invn;
+    b[r] = (double)A[r][8] * invn;
+  }
+  for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) H[8 * r + c] *= sc[c];
+  for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) H[8 * r + c] *= sc[r];
+  for (int r = 0; r < 8; r++) b[r] *= sc[r];
+  return SOSBA_OK;
+}
+
+API int sosba_scale_set_stereo(sosba_t *h, const double T10[12], const float K1[4]) {
+  CHECK_H(h);
+  if (!T10 || !K1) return SOSBA_E_ARG;
+  memcpy(h->t_T10, T10, sizeof(double) * 12);
+  float (*K)[4] = h->t_K1;
+  for (int i = 0; i < 4; i++) K[0][i] = K1[i];
+  for (int l = 1; l < h->levels; l++) {  // ScaleOptimizer.cpp:72-77
+    K[l][0] = K[l - 1][0] * 0.5;
+    K[l][1] = K[l - 1][1] * 0.5;
+    K[l][2] = (K[0][2] + 0.5) / ((int)1 << l) - 0.5;
+    K[l][3] = (K[0][3] + 0.5) / ((int)1 << l) - 0.5;
+  }
+  h->t_haveStereo = true;
+  return SOSBA_OK;
+}
+
+API int sosba_scale_calc_res(sosba_t *h, int32_t lvl, int32_t slot, float scale, float cutoff, double out6[6], int32_t counts[3]) {
+  CHECK_H(h);
+  if (!h->t_haveStereo) { sosba_set_error("scale_set_stereo first"); return SOSBA_E_STATE; }
+  if (lvl < 0 || lvl >= h->levels) return SOSBA_E_ARG;
+  float R[9], t[3];
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) R[3 * i + j] = (float)h->t_T10[4 * i + j]; t[i] = (float)h->t_T10[4 * i + 3]; }
+  return track_res_common(h, 1, lvl, slot, R, t, h->t_K1[lvl], 1.f, 0.f, scale, cutoff, out6, counts);
+}
+
+API int sosba_scale_calc_gs(sosba_t *h, int32_t lvl, float scale, float *H, float *b) {
+  CHECK_H(h);
+  HostSide *hs = HS(h);
+  if (lvl != h->t_warp_lvl || h->t_warp_kind != 1) { sosba_set_error("scale_calc_gs needs scale_calc_res at the same level first"); return SOSBA_E_STATE; }
+  TrackGSArgs g;
+  g.n = h->t_n[lvl]; g.cap = h->t_warp_cap; g.kind = 1; g.warp = h->t_warp; g.fx = h->t_K1[lvl][0]; g.fy = h->t_K1[lvl][1]; g.a = 0.f; g.b0 = 0.f;
+  g.scale = scale; g.tx = (float)h->t_T10[3]; g.ty = (float)h->t_T10[7]; g.tz = (float)h->t_T10[11]; g.acc = h->t_acc;
+  cudaMemsetAsync(h->t_acc + 8, 0, sizeof(double) * 48, h->stream);
+  launch_track_gs(h, g);
+  SOSBA_CUDA(cudaGetLastError());
+  int rc;
+  if ((rc = down(h, hs->pin_d, h->t_acc + 8, 3))) return rc;
+  if ((rc = sync(h))) return rc;
+  const int n = h->t_warp_n[lvl];
+  if (H) *H = (float)hs->pin_d[0] * (1.0f / n);
+  if (b) *b = (float)hs->pin_d[1] * (1.0f / n);
+  return SOSBA_OK;
+}
+
+// ---- composed Gauss-Newton loop: FullSystem::optimize (FullSystemOptimize.cpp:305-489), IMU off -----
+static int upload_tables(sosba *h, BA *ba, bool full) {
+  WindowTables &w = ba->wt;
+  sosba_window win;
+  memset(&win, 0, sizeof(win));
+  win.nf = w.nf;
+  win.frame_slot = w.frame_slot.data();
+  win.precalc = w.precalc.data();
+  win.adHost = w.adHost.data(); win.adTarget = w.adTarget.data();
+  win.adHTdeltaF = w.adHTdeltaF.data();
+  win.frame_energy_th = w.frameEnergyTH.data();
+  for (int i = 0; i < 4; i++) { win.calib[i] = w.calib[i]; win.cDeltaF[i] = w.cDeltaF[i]; win.cPrior[i] = w.cPrior[i]; }
+  win.frame_prior = w.frame_prior.data(); win.frame_delta_prior = w.frame_delta_prior.data(); win.frame_delta = w.frame_delta.data();
+  return window_apply(h, &win, full);
+}
+
+API int sosba_ba_upload(sosba_t *h, const sosba_ba_problem *prob) {
+  CHECK_H(h);
+  if (!prob || prob->nf <= 0 || !prob->frames) return SOSBA_E_ARG;
+  BA *ba = h->ba;
+  ba->st.load(h->cfg, prob);
+  ba->st.make_adjoints(h->cfg, ba->wt);
+  ba->st.make_precalc(ba->wt);
+  int rc;
+  if ((rc = upload_tables(h, ba, true))) return rc;
+  if ((rc = sosba_points_set(h, &prob->points))) return rc;
+  if ((rc = sosba_residuals_set(h, &prob->residuals))) return rc;
+  const int D = 4 + 8 * prob->nf;
+  ba->have_HM = !ba->st.HM.empty();
+  if (ba->have_HM) {
+    HostSide *hs = HS(h);
+    if ((rc = up(h, hs->d_HMtmp, ba->st.HM.data(), (size_t)D * D)) || (rc = up(h, hs->d_bMtmp, ba->st.bM.data(), D))) return rc;
+    if ((rc = sync(h))) return rc;
+  }
+  ba->iterations_done = 0;
+  return SOSBA_OK;
+}
+
+// one loop body: backupState, solveSystem, doStepFromBackup, linearizeAll(false), applyRes.  Returns canbreak.
+static int ba_iterate_once(sosba *h, bool *canbreak, sosba_linearize_out *lo) {
+  BA *ba = h->ba;
+  HostSide *hs = HS(h);
+  const int nf = h->nf, D = 4 + 8 * nf;
+  int rc;
+  ba->st.backup();
+  if ((rc = enqueue_solve(h, ba->have_HM ? hs->d_HMtmp : nullptr, ba->have_HM ? hs->d_bMtmp : nullptr, 1))) return rc;
+  if ((rc = down(h, hs->pin_d, h->d_x, D)) || (rc = down(h, hs->pin_d + 256, h->d_stats + 1, 3)) || (rc = down(h, hs->pin_i, hs->d_status, 1))) return rc;
+  if ((rc = sync(h))) return rc;
+  if (hs->pin_i[0]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
+  float sums[4];
+  ba->st.step_frames(hs->pin_d, 1.0f, sums);
+  ba->st.make_precalc(ba->wt);
+  for (int i = 0; i < nf; i++) ba->wt.frameEnergyTH[i] = ba->st.frames[i].frameEnergyTH;
+  if ((rc = upload_tables(h, ba, false))) return rc;
+  enqueue_linearize(h, 0);
+  launch_apply_res(h, lin_args(h), 0);
+  SOSBA_CUDA(cudaGetLastError());
+  sosba_linearize_out tmp;
+  if ((rc = read_linearize_out(h, lo ? lo : &tmp))) return rc;
+  ba->st.frames.back().frameEnergyTH = (lo ? lo : &tmp)->new_frame_energy_th;
+  const float numID = (float)hs->pin_d[258];
+  const float sumNID = numID > 0 ? (float)hs->pin_d[257] / numID : 0.f;
+  const float th = h->cfg.th_opt_iterations;
+  if (canbreak)
+    *canbreak = sqrtf(sums[0]) < 0.0005 * th && sqrtf(sums[1]) < 0.00005 * th && sqrtf(sums[3]) < 0.00005 * th && sqrtf(sums[2]) * sumNID < 0.00005 * th;
+  ba->iterations_done++;
+  return SOSBA_OK;
+}
+
+API int sosba_ba_iterate(sosba_t *h, int32_t n, int32_t *n_res) {
+  CHECK_H(h);
+  if (!h->ba->st.loaded) { sosba_set_error("ba_upload first"); return SOSBA_E_STATE; }
+  for (int i = 0; i < n; i++) {
+    int rc = ba_iterate_once(h, nullptr, nullptr);
+    if (rc) return rc;
+  }
+  if (n_res) *n_res = h->R - HS(h)->n_lin;
+  return SOSBA_OK;
+}
+
+API int sosba_ba_download(sosba_t *h, sosba_ba_problem *prob) {
+  CHECK_H(h);
+  if (!prob || !h->ba->st.loaded) return SOSBA_E_STATE;
+  h->ba->st.store(prob);
+  if (prob->idepth_out) {
+    int rc = down(h, prob->idepth_out, h->p_idepth, h->P);
+    if (rc) return rc;
+    return sync(h);
+  }
+  return SOSBA_OK;
+}
+
+API int sosba_optimize(sosba_t *h, sosba_ba_problem *prob, int32_t mnumOptIts, sosba_optimize_out *out) {
+  CHECK_H(h);
+  if (!prob || !out) return SOSBA_E_ARG;
+  memset(out, 0, sizeof(*out));
+  int rc = sosba_ba_upload(h, prob);
+  if (rc) return rc;
+  BA *ba = h->ba;
+  HostSide *hs = HS(h);
+  const int nf = prob->nf;
+  if (nf < 2) return SOSBA_OK;
+  if (nf < 3) mnumOptIts = 20;
+  if (nf < 4) mnumOptIts = 15;
+  launch_reset_oob(h, lin_args(h));
+  sosba_linearize_out lo;
+  enqueue_linearize(h, 0);
+  launch_apply_res(h, lin_args(h), 0);
+  if ((rc = read_linearize_out(h, &lo))) return rc;
+  ba->st.frames.back().frameEnergyTH = lo.new_frame_energy_th;
+  out->energy_initial = lo.energy;
+  int it = 0;
+  for (int iteration = 0; iteration < mnumOptIts; iteration++) {
+    bool canbreak = false;
+    if ((rc = ba_iterate_once(h, &canbreak, &lo))) return rc;
+    it++;
+    if (canbreak && iteration >= h->cfg.min_opt_iterations) break;
+  }
+  out->iterations = it;
+  // new evaluation point for the newest frame (FullSystemOptimize.cpp:415-423)
+  sosba_host::FrameH &nf_ = ba->st.frames.back();
+  double newStateZero[10] = {0, 0, 0, 0, 0, 0, nf_.state[6], nf_.state[7], 0, 0};
+  nf_.setEvalPT(nf_.camToWorld, newStateZero);
+  ba->st.make_adjoints(h->cfg, ba->wt);
+  ba->st.make_precalc(ba->wt);
+  if ((rc = upload_tables(h, ba, true))) return rc;
+  enqueue_linearize(h, 1);
+  if ((rc = read_linearize_out(h, &lo))) return rc;
+  nf_.frameEnergyTH = lo.new_frame_energy_th;
+  out->energy_final = lo.energy;
+  out->n_removed = lo.n_removed;
+  if ((rc = down(h, hs->pin_i, h->d_counts + 5, 1)) || (rc = down(h, hs->pin_d, h->d_x, 4 + 8 * nf))) return rc;
+  if ((rc = sync(h))) return rc;
+  out->res_in_a = hs->pin_i[0];
+  out->rmse = sqrtf((float)(lo.energy / (SOSBA_PATTERN * out->res_in_a)));
+  double n2 = 0;
+  for (int i = 0; i < 4 + 8 * nf; i++) n2 += hs->pin_d[i] * hs->pin_d[i];
+  out->last_x_norm = sqrt(n2);
+  return sosba_ba_download(h, prob);
+}

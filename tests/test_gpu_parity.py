@@ -1,0 +1,272 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar: bit-exact for integer bookkeeping (residual states, counts, removal sets, pyramid
+levels); per-residual floats rel 1e-5; block accumulators / stitched H,b rel 1e-4 of the Frobenius norm;
+solved step rel 1e-3; tracker H,b rel 1e-4."""
+import numpy as np
+import pytest
+
+from _scenes import CONFIG_B, KITTI, SMALL, open_handle, relerr, scene, upload
+
+pytestmark = pytest.mark.gpu
+
+
+def both(gpu, orc, sc, **kw):
+    out = []
+    for lib in (gpu, orc):
+        h = open_handle(lib, sc)
+        P, keep = upload(h, sc, **kw)
+        out.append((h, P, keep))
+    return out
+
+
+# ---- a1 -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(640, 480), (752, 480), (1232, 368), (512, 512), (322, 242)])
+def test_pyramid_bit_exact(gpu, orc, shape):
+    w, h = shape
+    rng = np.random.default_rng(w * 7 + h)
+    img = (rng.uniform(0, 255, (h, w)) * 0.3 + 0.7 * 127 * (1 + np.sin(np.arange(w)[None, :] * 0.07) * np.cos(np.arange(h)[:, None] * 0.05))).astype(np.float32)
+    B = np.linspace(0, 255, 256).astype(np.float32) ** 1.02
+    for useB in (False, True):
+        res = []
+        for lib in (gpu, orc):
+            cfg = lib.config_default(w, h)
+            cfg.max_frames = 2
+            from sos_slam_b200 import binding
+            hd = binding.Handle(lib, cfg)
+            hd.frame_make_images(1, img, B if useB else None)
+            res.append([hd.frame_get_level(1, l) for l in range(hd.levels)])
+            res[-1].append(hd.levels)
+            hd.close()
+        assert res[0][-1] == res[1][-1]
+        for l in range(res[0][-1]):
+            assert np.array_equal(res[0][l][0], res[1][l][0]), f"dI level {l}"
+            assert np.array_equal(res[0][l][1], res[1][l][1]), f"absSquaredGrad level {l}"
+
+
+# ---- a3/a4/a5 -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [SMALL, CONFIG_B, KITTI], ids=["small", "configB", "kitti"])
+def test_linearize_apply(gpu, orc, cfg):
+    sc = scene(**cfg)
+    (hg, Pg, kg), (ho, Po, ko) = both(gpu, orc, sc)
+    for h in (hg, ho):
+        h.reset_oob()
+    lg, lo = hg.linearize_all(False), ho.linearize_all(False)
+    for k in ("n_in", "n_oob", "n_outlier", "n_removed"):
+        assert lg[k] == lo[k], (k, lg, lo)
+    assert lg["new_frame_energy_th"] == lo["new_frame_energy_th"]
+    assert abs(lg["energy"] - lo["energy"]) <= 1e-9 * abs(lo["energy"])
+    sg, so = hg.get_state(), ho.get_state()
+    assert np.array_equal(sg["new_state"], so["new_state"])
+    live = so["new_state"] != 1
+    assert np.array_equal(sg["new_energy"][live], so["new_energy"][live])
+    assert np.array_equal(sg["new_energy_wo"], so["new_energy_wo"])
+    Jg, Jo = hg.get_jacobians(False), ho.get_jacobians(False)
+    assert np.array_equal(Jg[live], Jo[live])          # same op order, no FMA: bit-exact
+    ag, ao = hg.get_aux(), ho.get_aux()
+    assert np.array_equal(ag["projectedTo"][live], ao["projectedTo"][live])
+    assert np.array_equal(ag["centerProjectedTo"][live], ao["centerProjectedTo"][live])
+    for h in (hg, ho):
+        h.apply_res()
+    sg, so = hg.get_state(), ho.get_state()
+    for k in ("state", "is_active"):
+        assert np.array_equal(sg[k], so[k]), k
+    act = so["is_active"] == 1
+    assert np.array_equal(hg.get_jacobians(True)[act], ho.get_jacobians(True)[act])
+    ag, ao = hg.get_aux(), ho.get_aux()
+    assert np.allclose(ag["JpJdF"][act], ao["JpJdF"][act], rtol=1e-5, atol=1e-6 * np.abs(ao["JpJdF"][act]).max())
+    # second linearisation from the committed state and the new threshold
+    lg, lo = hg.linearize_all(True), ho.linearize_all(True)
+    for k in ("n_in", "n_oob", "n_outlier", "n_removed"):
+        assert lg[k] == lo[k], (k, lg, lo)
+    mg, ng = hg.points_get_stats()
+    mo, no = ho.points_get_stats()
+    assert np.array_equal(ng, no)
+    assert np.allclose(mg, mo, rtol=1e-6)
+    hg.close(); ho.close()
+
+
+# ---- a6-a11 -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [SMALL, CONFIG_B, KITTI], ids=["small", "configB", "kitti"])
+def test_accumulate_solve(gpu, orc, cfg):
+    sc = scene(**cfg)
+    D = 4 + 8 * sc.nf
+    rng = np.random.default_rng(11)
+    A = rng.normal(size=(D, D))
+    HM = (A @ A.T) * 50.0
+    bM = rng.normal(size=D) * 10.0
+    (hg, Pg, kg), (ho, Po, ko) = both(gpu, orc, sc, calib_delta=(1e-4, -2e-4, 3e-4, 1e-4))
+    for h in (hg, ho):
+        h.reset_oob(); h.linearize_all(False); h.apply_res()
+    ag, ao = hg.accumulate(), ho.accumulate()
+    assert ag["resInA"] == ao["resInA"] and ag["resInL"] == ao["resInL"]
+    for k in ("HA", "bA", "HL", "bL", "Hsc", "bsc"):
+        assert relerr(ag[k], ao[k]) < 1e-4, (k, relerr(ag[k], ao[k]))
+    assert np.allclose(ag["HA"], ag["HA"].T, rtol=0, atol=1e-9 * np.abs(ag["HA"]).max())
+    assert np.allclose(ag["Hsc"], ag["Hsc"].T, rtol=0, atol=1e-9 * np.abs(ag["Hsc"]).max())
+    pg, po = hg.points_get_acc(), ho.points_get_acc()
+    for k in pg:
+        assert np.allclose(pg[k], po[k], rtol=2e-5, atol=2e-6 * max(1e-30, np.abs(po[k]).max())), k
+    for (hm, bm) in ((None, None), (HM, bM)):
+        xg, Hg, bg = hg.solve_system(hm, bm)
+        xo, Ho, bo = ho.solve_system(hm, bm)
+        assert relerr(Hg, Ho) < 1e-4 and relerr(bg, bo) < 1e-4
+        # compare the step in the H-norm (the system is ill-conditioned along the gauge)
+        d = xg - xo
+        assert np.sqrt(abs(d @ Ho @ d)) <= 1e-3 * np.sqrt(abs(xo @ Ho @ xo)), (relerr(xg, xo))
+        assert relerr(xg, xo) < 5e-3
+        x = xo
+        stg, sto = hg.resubstitute(x), ho.resubstitute(x)
+        assert np.allclose(stg, sto, rtol=2e-4, atol=2e-6 * np.abs(sto).max())
+    hg.close(); ho.close()
+
+
+def test_linearized_and_marginalize(gpu, orc):
+    """fixLinearizationF (a13), addPoint<1> with deltas, marginalizePointsF (addPoint<2> + SC(false))."""
+    sc = scene(**SMALL)
+    (hg, Pg, kg), (ho, Po, ko) = both(gpu, orc, sc, calib_delta=(2e-4, 1e-4, -1e-4, 3e-4))
+    counts = np.bincount(sc.res_point, minlength=sc.n_points)
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    pts = np.arange(0, sc.n_points, 7, dtype=np.int32)
+    rids = np.concatenate([np.arange(starts[p], starts[p + 1]) for p in pts]).astype(np.int32)
+    for h in (hg, ho):
+        h.reset_oob(); h.linearize_all(False); h.apply_res()
+    act = ho.get_state()["is_active"]
+    rids = rids[act[rids] == 1]
+    for h in (hg, ho):
+        h.fix_linearization(rids)
+    ag, ao = hg.get_aux(), ho.get_aux()
+    assert np.array_equal(ag["res_toZeroF"][rids], ao["res_toZeroF"][rids])
+    assert np.array_equal(hg.get_state()["is_linearized"], ho.get_state()["is_linearized"])
+    ag, ao = hg.accumulate(), ho.accumulate()
+    assert ag["resInA"] == ao["resInA"] and ag["resInL"] == ao["resInL"] and ao["resInL"] == len(rids)
+    for k in ("HA", "bA", "HL", "bL", "Hsc", "bsc"):
+        assert relerr(ag[k], ao[k]) < 1e-4, (k, relerr(ag[k], ao[k]))
+    Hg, bg, ng = hg.marginalize_points(pts)
+    Ho, bo, no = ho.marginalize_points(pts)
+    assert ng == no
+    assert relerr(Hg, Ho) < 1e-4 and relerr(bg, bo) < 1e-4
+    hg.close(); ho.close()
+
+
+# ---- the composed Gauss-Newton loop -------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [SMALL, CONFIG_B], ids=["small", "configB"])
+def test_optimize(gpu, orc, cfg):
+    sc = scene(**cfg)
+    res = []
+    for lib in (gpu, orc):
+        h = open_handle(lib, sc)
+        from sos_slam_b200 import problem
+        val, val0 = problem.calib_of(sc)
+        P, keep = h.make_problem(problem.frames_of(sc), val, val0, problem.points_of(sc), problem.residuals_of(sc))
+        out = h.optimize(P, 6)
+        res.append((out, h.problem_result(P, keep), h.get_state()))
+        h.close()
+    (og, rg, sg), (oo, ro, so) = res
+    assert og["iterations"] == oo["iterations"]
+    assert og["energy_initial"] == pytest.approx(oo["energy_initial"], rel=1e-9)
+    assert og["energy_final"] == pytest.approx(oo["energy_final"], rel=2e-3)
+    assert og["energy_final"] < 0.05 * og["energy_initial"]
+    assert abs(og["res_in_a"] - oo["res_in_a"]) <= 2
+    assert int((sg["state"] != so["state"]).sum()) <= max(2, sg["state"].size // 500)
+    assert np.allclose(rg["state"], ro["state"], rtol=2e-3, atol=1e-7)
+    assert np.allclose(rg["idepth"], ro["idepth"], rtol=2e-3, atol=1e-5)
+    assert np.allclose(rg["evalPT"], ro["evalPT"], rtol=1e-6, atol=1e-7)
+
+
+# ---- a14/a15/a17 ----------------------------------------------------------------------------------
+def _ref_points(sc, h, lvl, n, rng):
+    w, hh = sc.w >> lvl, sc.h >> lvl
+    u = rng.integers(2, w - 2, n).astype(np.float32)
+    v = rng.integers(2, hh - 2, n).astype(np.float32)
+    idepth = rng.uniform(0.35, 0.65, n).astype(np.float32)
+    dI, _ = h.frame_get_level(0, lvl)
+    color = dI[v.astype(int), u.astype(int), 0].copy()
+    return u, v, idepth, color
+
+
+@pytest.mark.parametrize("cfg", [SMALL, CONFIG_B], ids=["small", "configB"])
+def test_tracker_and_scale(gpu, orc, cfg):
+    from sos_slam_b200 import synth
+    sc = scene(**cfg)
+    hg, ho = open_handle(gpu, sc), open_handle(orc, sc)
+    T = (np.linalg.inv(sc.camToWorld_true[1]) @ sc.camToWorld_true[0])[:3, :4]
+    T10 = synth.se3_exp([0.1, 0.002, -0.001, 0.001, -0.002, 0.0005])[:3, :4]
+    K = sc.K.astype(np.float32)
+    for h in (hg, ho):
+        h.tracker_make_k(K)
+        h.scale_set_stereo(T10, K * np.array([1.01, 0.99, 1.0, 1.0], np.float32))
+    for lvl in range(hg.levels):
+        rng = np.random.default_rng(100 + lvl)
+        n = max(37, 9000 >> (2 * lvl))
+        pts = _ref_points(sc, ho, lvl, n, rng)
+        for h in (hg, ho):
+            h.tracker_set_ref(lvl, *pts)
+        for cutoff in (20.0, 6.0):
+            og, cg = hg.tracker_calc_res_pose(lvl, 1, T, (1.02, -3.0), cutoff)
+            oo, co = ho.tracker_calc_res_pose(lvl, 1, T, (1.02, -3.0), cutoff)
+            assert np.array_equal(cg, co), (lvl, cg, co)
+            assert np.allclose(og, oo, rtol=2e-5, atol=1e-6), (lvl, og, oo)
+            Hg, bg = hg.tracker_calc_gs_pose(lvl, 1.02, 0.004)
+            Ho, bo = ho.tracker_calc_gs_pose(lvl, 1.02, 0.004)
+            assert relerr(Hg, Ho) < 1e-4 and relerr(bg, bo) < 1e-4
+        for s in (1.0, 0.8):
+            og, cg = hg.scale_calc_res(lvl, 2, s, 20.0)
+            oo, co = ho.scale_calc_res(lvl, 2, s, 20.0)
+            assert np.array_equal(cg, co), (lvl, cg, co)
+            assert np.allclose(og, oo, rtol=2e-5, atol=1e-6)
+            Hg, bg = hg.scale_calc_gs(lvl, s)
+            Ho, bo = ho.scale_calc_gs(lvl, s)
+            assert Hg == pytest.approx(Ho, rel=1e-4) and bg == pytest.approx(bo, rel=1e-4, abs=1e-6 * abs(Ho))
+    hg.close(); ho.close()
+
+
+# ---- edge cases -----------------------------------------------------------------------------------
+def test_edge_cases(gpu, orc):
+    from sos_slam_b200 import problem
+    sc = scene(**SMALL)
+    # (1) points without residuals + a ragged residual list; (2) a window seen from far away: everything OOB
+    pts = problem.points_of(sc)
+    res = problem.residuals_of(sc)
+    keep = (res["point"] % 3) != 0          # every third point loses all its residuals
+    res = {k: v[keep] for k, v in res.items()}
+    for far in (False, True):
+        out = []
+        for lib in (gpu, orc):
+            h = open_handle(lib, sc)
+            frames = problem.frames_of(sc)
+            if far:
+                for f in frames[1:]:
+                    f["evalPT"] = f["evalPT"].copy()
+                    f["evalPT"][:3, 3] += 50.0
+            val, val0 = problem.calib_of(sc)
+            P, k = h.make_problem(frames, val, val0, pts, res)
+            h.ba_upload(P)
+            h.reset_oob()
+            lo = h.linearize_all(False)
+            h.apply_res()
+            acc = h.accumulate()
+            st = h.get_state()
+            out.append((lo, acc, st))
+            h.close()
+        (lg, ag, sg), (lo, ao, so) = out
+        for k in ("n_in", "n_oob", "n_outlier"):
+            assert lg[k] == lo[k]
+        assert np.array_equal(sg["state"], so["state"])
+        assert ag["resInA"] == ao["resInA"]
+        if far:
+            assert lo["n_in"] == 0
+        for k in ("HA", "HL", "Hsc"):
+            assert relerr(ag[k], ao[k]) < 1e-4
+    # (3) empty residual set
+    for lib in (gpu,):
+        h = open_handle(lib, sc)
+        empty = {k: v[:0] for k, v in problem.residuals_of(sc).items()}
+        val, val0 = problem.calib_of(sc)
+        P, k = h.make_problem(problem.frames_of(sc), val, val0, pts, empty)
+        h.ba_upload(P)
+        lo = h.linearize_all(False)
+        assert lo["n_in"] == 0 and lo["energy"] == 0.0 and lo["new_frame_energy_th"] == 12 * 12 * 8
+        acc = h.accumulate()
+        assert acc["resInA"] == 0 and not acc["HA"].any() and not acc["Hsc"].any()
+        h.close()

@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — photometric residuals/sec and GN-iteration ms of the windowed bundle-adjustment hot path.
+
+Workload (BASELINE.json configs[1]): synthetic 640x480, 8-keyframe window, 2000 active points, BA only.
+One STEP = one FullSystem::optimize(6) of that window (FullSystemOptimize.cpp:305-489): resetOOB,
+linearizeAll + applyRes, 6 x {solveSystemF, doStepFromBackup, linearizeAll, applyRes}, new evaluation point,
+linearizeAll(fix) — 8 linearisation passes and 6 solves, forced (min_opt_iterations) so every step does the
+same work.  1 photometric residual = 1 of the 8 pattern samples of a PointFrameResidual.
+
+  value  : residuals/s with the window resident in HBM (sosba_ba_optimize), CUDA events per step, L2 flushed
+           between steps, max over ranks.
+  e2e    : the same step through the public C ABI with HOST buffers (sosba_frame_make_images of the newest
+           keyframe + sosba_optimize: H2D of image, points, residuals, frame states; D2H of the result).
+  --impl reference : the CPU restatement of the reference path (oracle/, -O3 -mavx2 -mfma, all host threads;
+           the reference itself cannot be built here — see DESIGN.md) on the same window, same step.
+N > 1 (weak scaling): N x 2000 points, point-sharded, one all-reduce of the block tables per GN iteration.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "photometric_residuals_per_sec"
+UNIT = "residuals/s"
+ITERS = 6
+BYTES_LINEARIZE = 787          # algorithmic bytes per PointFrameResidual per linearisation
+WORKLOAD = "synthetic 640x480 stereo, 8-KF window, 2000 active points, BA only (BASELINE.json configs[1])"
+
+
+def load():
+    from sosba_loader import load_package
+    pkg = load_package()
+    from sos_slam_b200 import binding, problem, synth
+    return pkg, binding, problem, synth
+
+
+def get_scene(synth, n_points_factor=1):
+    from _scenes import CONFIG_B, scene
+    sc = scene(**CONFIG_B)
+    if n_points_factor > 1:
+        sc = synth.replicate_points(sc, n_points_factor)
+    return sc
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def forced_cfg(lib, sc, threads=1):
+    cfg = lib.config_default(sc.w, sc.h)
+    cfg.num_threads = threads
+    cfg.max_frames = sc.nf + 2
+    cfg.min_opt_iterations = 1000   # never break early: every step runs exactly ITERS Gauss-Newton iterations
+    return cfg
+
+
+def run_reference(args):
+    """The reference's CPU path (oracle restatement, speed build) on the host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg, binding, problem, synth = load()
+    path = os.path.join(ROOT, "oracle", "_build", "liborc_speed.so")
+    if not os.path.exists(path):
+        import __graft_entry__ as g
+        g.build()
+    lib = binding.Lib(path, "orc")
+    sc = get_scene(synth, max(1, args.gpus))
+    cores = os.cpu_count() or 1
+    cfg = forced_cfg(lib, sc, threads=cores)
+    h = binding.Handle(lib, cfg)
+    for i, img in enumerate(sc.images):
+        h.frame_make_images(i, img)
+    val, val0 = problem.calib_of(sc)
+
+    def step():
+        h.frame_make_images(sc.nf - 1, sc.images[-1])
+        P, keep = h.make_problem(problem.frames_of(sc), val, val0, problem.points_of(sc), problem.residuals_of(sc))
+        return h.optimize(P, ITERS)
+
+    for _ in range(args.warmup):
+        out = step()
+    t0 = time.perf_counter()
+    nres = 0
+    for _ in range(args.steps):
+        out = step()
+        nres += out["reserved0"] * 8 * (out["iterations"] + 2)
+    dt = time.perf_counter() - t0
+    v = nres / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "gn_iter_ms": 1e3 * dt / args.steps / ITERS, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "points": sc.n_points, "residuals": sc.n_residuals, "gn_iterations_per_step": ITERS,
+                       "linearizations_per_step": ITERS + 2},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} full optimize() steps of the workload, oracle speed build (-O3 -mavx2 -mfma), {cores} IndexThreadReduce workers"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sosba")
+    ap.add_argument("--points-factor", type=int, default=0, help="scaling sweep: multiply the 2000 points (default: = gpus)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libsosba has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg, binding, problem, synth = load()
+    lib = pkg.load()
+    factor = args.points_factor or max(1, world)
+    sc = get_scene(synth, factor)
+    cfg = forced_cfg(lib, sc)
+    h = binding.Handle(lib, cfg, device=local)
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)
+    for i, img in enumerate(sc.images):
+        h.frame_make_images(i, img)
+    val, val0 = problem.calib_of(sc)
+    pts, res = problem.points_of(sc), problem.residuals_of(sc)
+    if world > 1:
+        uid = [None]
+        if rank == 0:
+            uid[0] = h.lib_unique_id()
+        dist.broadcast_object_list(uid, src=0)
+        h.comm_init(uid[0], rank, world)
+        p0, p1 = problem.shard_points(sc.res_point, sc.n_points, world)[rank]
+        pts, res = problem.shard_scene_arrays(pts, res, p0, p1)
+    P, keep = h.make_problem(problem.frames_of(sc), val, val0, pts, res)
+    h.ba_upload(P)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: resident window ------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        out = h.ba_optimize(ITERS)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    h.profile_enable(True)
+    l0 = h.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    nres_local = 0
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)           # evict the window from L2 (126 MB) between steps
+        ev[k][0].record(stream)
+        out = h.ba_optimize(ITERS)
+        ev[k][1].record(stream)
+        nres_local += out["reserved0"] * 8 * (out["iterations"] + 2)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = h.launch_count() - l0
+    lin_ms, lin_n = h.profile_read()
+    h.profile_enable(False)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    tot_ms = sum(step_ms)
+    clocks = sampler.stop()
+    t = torch.tensor([tot_ms, float(nres_local)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        tot_ms, nres = float(tmax[0]), float(tsum[1])
+    else:
+        nres = float(nres_local)
+    value = nres / (tot_ms * 1e-3)
+
+    # ---- GN-iteration ms: the loop body alone, warm L2 ------------------------------------------------
+    n_it = 30
+    h.ba_iterate(3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    h.ba_iterate(n_it)
+    e1.record(stream)
+    barrier()
+    gn_ms = e0.elapsed_time(e1) / n_it
+
+    # ---- e2e: host buffers through the public C ABI ---------------------------------------------------
+    frames = problem.frames_of(sc)
+    h2d = sc.images[-1].nbytes + sum(np.asarray(v).nbytes for v in pts.values()) + sum(np.asarray(v).nbytes for v in res.values()) + len(frames) * 8 * 32
+    d2h = len(frames) * 8 * 32 + 4 * len(pts["u"])
+
+    def e2e_step():
+        h.frame_make_images(sc.nf - 1, sc.images[-1])
+        Pn, kn = h.make_problem(frames, val, val0, pts, res)
+        o = h.optimize(Pn, ITERS)
+        return o
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e2e_ms, e2e_res = 0.0, 0
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        tw = time.perf_counter()
+        a.record(stream)
+        o = e2e_step()
+        b.record(stream)
+        torch.cuda.synchronize()
+        e2e_ms += max(a.elapsed_time(b), 1e3 * (time.perf_counter() - tw))   # device timeline and host wall agree; take the larger
+        e2e_res += o["reserved0"] * 8 * (o["iterations"] + 2)
+    t = torch.tensor([e2e_ms, float(e2e_res)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        e2e_ms, e2e_res = float(tmax[0]), float(tsum[1])
+    e2e_value = e2e_res / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (linearize) ---------------------------------------------------
+    peak, peak_src = measured_peak()
+    R_lin = out["reserved0"]
+    lin_us = 1e3 * lin_ms / max(lin_n, 1)
+    achieved = BYTES_LINEARIZE * R_lin / (lin_us * 1e-6) / 1e9 if lin_n else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_linearize.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_linearize", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "launch_us": lin_us, "launches_timed": lin_n,
+                "algorithmic_bytes_per_launch": BYTES_LINEARIZE * R_lin,
+                "note": "1 of 8 launches per step runs on a flushed L2; the window (63 MB) is L2-resident for the rest — latency-bound at this size, see DESIGN.md §5 sweep"}
+
+    # ---- CPU baseline (rank 0, bounded sample) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        opath = os.path.join(ROOT, "oracle", "_build", "liborc_speed.so")
+        if os.path.exists(opath):
+            olib = binding.Lib(opath, "orc")
+            cores = os.cpu_count() or 1
+            sc1 = get_scene(synth, 1)
+            oh = binding.Handle(olib, forced_cfg(olib, sc1, threads=cores))
+            for i, img in enumerate(sc1.images):
+                oh.frame_make_images(i, img)
+            v1, v10 = problem.calib_of(sc1)
+            n, tcpu, rcpu = 0, 0.0, 0
+            while n < 3 or (tcpu < 8.0 and n < 60):
+                Pn, kn = oh.make_problem(problem.frames_of(sc1), v1, v10, problem.points_of(sc1), problem.residuals_of(sc1))
+                t0 = time.perf_counter()
+                o = oh.optimize(Pn, ITERS)
+                dt = time.perf_counter() - t0
+                if n >= 1:
+                    tcpu += dt; rcpu += o["reserved0"] * 8 * (o["iterations"] + 2)
+                n += 1
+            oh.close()
+            cpu = {"value": rcpu / tcpu, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{n - 1} optimize() steps of the same window ({tcpu:.1f} s), oracle speed build, {cores} IndexThreadReduce workers",
+                   "ms_per_step": 1e3 * tcpu / (n - 1)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": tot_ms / args.steps, "gn_iter_ms": gn_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD if factor == 1 else WORKLOAD + f" x{factor} points, point-sharded", "points": sc.n_points,
+                           "residuals": sc.n_residuals, "gn_iterations_per_step": ITERS, "linearizations_per_step": ITERS + 2,
+                           "l2": "flushed between steps (256 MiB fill); per-step CUDA events on the launch stream", "parallelism": f"points/{world}"},
+                "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                                          "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps, "final_rmse": out["rmse"]}
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -150,6 +150,12 @@ int sosba_set_stream(sosba_t *h, void *cuda_stream);
 int sosba_synchronize(sosba_t *h);
 /* Number of kernel launches issued by this handle since creation (bench `gpu_launches`). */
 int64_t sosba_launch_count(const sosba_t *h);
+/* CUDA-event bracket around every PointFrameResidual::linearize kernel launch, on its launch stream:
+ * enable, run, then read the summed duration and the number of launches (the bench roofline). */
+int sosba_profile_enable(sosba_t *h, int32_t on);
+int sosba_profile_read(sosba_t *h, double *ms_total, int32_t *launches);
+/* sosba_frame_make_images with the irradiance image (and B, or NULL) already in device memory. */
+int sosba_frame_make_images_dev(sosba_t *h, int32_t slot, const float *color_dev, const float *B_dev);
 int32_t sosba_pyr_levels(const sosba_t *h);
 
 /* ---- a1: FrameHessian::makeImages (HessianBlocks.cpp:121-176) -------------------------------- */
@@ -283,6 +289,9 @@ int sosba_optimize(sosba_t *h, sosba_ba_problem *prob, int32_t max_iterations, s
 
 /* The same loop with the problem already resident on the device: uploads `prob` once ... */
 int sosba_ba_upload(sosba_t *h, const sosba_ba_problem *prob);
+/* ... FullSystem::optimize on the resident problem (sosba_optimize = ba_upload + ba_optimize + ba_download);
+ * out->reserved0 = residuals linearised per linearizeAll pass. */
+int sosba_ba_optimize(sosba_t *h, int32_t max_iterations, sosba_optimize_out *out);
 /* ... and runs `n` loop bodies (solveSystem + doStepFromBackup + linearizeAll(false) + applyRes)
  * without touching host problem buffers.  n_res_linearized: residuals linearized per body. */
 int sosba_ba_iterate(sosba_t *h, int32_t n, int32_t *n_res_linearized);

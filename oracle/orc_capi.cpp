@@ -335,6 +335,11 @@ ORC_API int orc_optimize(orc_handle *h, sosba_ba_problem *prob, int32_t max_it, 
   h->ba.store(h->o, prob);
   return SOSBA_OK;
 }
+ORC_API int orc_ba_optimize(orc_handle *h, int32_t max_it, sosba_optimize_out *out) {
+  if (!h->ba_loaded) return SOSBA_E_STATE;
+  h->ba.optimize(h->o, h->HM.empty() ? nullptr : h->HM.data(), h->bM.empty() ? nullptr : h->bM.data(), max_it, out);
+  return SOSBA_OK;
+}
 ORC_API int orc_ba_iterate(orc_handle *h, int32_t n, int32_t *n_res) {
   if (!h->ba_loaded) return SOSBA_E_STATE;
   sosba_linearize_out lo;

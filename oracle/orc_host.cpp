@@ -259,6 +259,7 @@ void BAState::optimize(Oracle &o, const double *HM, const double *bM, int mnumOp
   linearizeAll(o, false, &lo);
   frames.back().frameEnergyTH = o.frameEnergyTH[nf - 1];
   out->energy_initial = lo.energy;
+  out->reserved0 = lo.n_in + lo.n_oob + lo.n_outlier;  // residuals linearised per pass (bench bookkeeping)
   for (int id : o.activeResiduals) applyRes(o.res[id], true);
   int it = 0;
   for (int iteration = 0; iteration < mnumOptIts; iteration++) {

@@ -128,7 +128,7 @@ class Lib:
                   "accumulate", "points_get_acc", "solve_system", "resubstitute", "marginalize_points",
                   "tracker_make_k", "tracker_set_ref", "tracker_calc_res_pose", "tracker_calc_gs_pose",
                   "scale_set_stereo", "scale_calc_res", "scale_calc_gs", "optimize", "ba_upload", "ba_iterate",
-                  "ba_download", "pyr_levels"):
+                  "ba_download", "ba_optimize", "pyr_levels"):
             self.f(n).restype = C.c_int
         self.f("destroy").restype = None
         if self.has("launch_count"):
@@ -187,6 +187,11 @@ class Handle:
 
     def launch_count(self) -> int:
         return int(self.lib.f("launch_count")(self.h))
+
+    def lib_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        self._ck(self.lib.f("comm_unique_id")(buf), "comm_unique_id")
+        return bytes(buf)
 
     def comm_init(self, uid: bytes, rank: int, world: int):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
@@ -455,7 +460,23 @@ class Handle:
     def optimize(self, P, max_iterations: int) -> dict:
         out = OptimizeOut()
         self._ck(self.lib.f("optimize")(self.h, C.byref(P), C.c_int32(max_iterations), C.byref(out)), "optimize")
-        return {n: getattr(out, n) for n, _ in OptimizeOut._fields_ if not n.startswith("reserved")}
+        return {n: getattr(out, n) for n, _ in OptimizeOut._fields_ if n != "reserved1"}
+
+    def ba_optimize(self, max_iterations: int) -> dict:
+        out = OptimizeOut()
+        self._ck(self.lib.f("ba_optimize")(self.h, C.c_int32(max_iterations), C.byref(out)), "ba_optimize")
+        return {n: getattr(out, n) for n, _ in OptimizeOut._fields_ if n != "reserved1"}
+
+    def profile_enable(self, on: bool):
+        self._ck(self.lib.f("profile_enable")(self.h, C.c_int32(1 if on else 0)), "profile_enable")
+
+    def profile_read(self):
+        ms, n = C.c_double(0), C.c_int32(0)
+        self._ck(self.lib.f("profile_read")(self.h, C.byref(ms), C.byref(n)), "profile_read")
+        return ms.value, n.value
+
+    def frame_make_images_dev(self, slot, color_ptr: int, B_ptr: int = 0):
+        self._ck(self.lib.f("frame_make_images_dev")(self.h, C.c_int32(slot), C.c_void_p(color_ptr), C.c_void_p(B_ptr or None)), "frame_make_images_dev")
 
     def ba_upload(self, P):
         self._ck(self.lib.f("ba_upload")(self.h, C.byref(P)), "ba_upload")

@@ -74,9 +74,11 @@ int sosba_allreduce_acc(sosba *h) {
   const int nf = h->nf, D = 4 + 8 * nf;
   ncclComm_t c = (ncclComm_t)h->comm;
   NCCLCHK(g_nccl.GroupStart());
-  NCCLCHK(g_nccl.AllReduce(h->d_accTop, h->d_accTop, 2 * (size_t)nf * nf * SOSBA_TOPB, ncclFloat64, ncclSum, c, h->stream));
-  NCCLCHK(g_nccl.AllReduce(h->d_accSC, h->d_accSC, (size_t)(D + 1) * (D + 1), ncclFloat64, ncclSum, c, h->stream));
-  NCCLCHK(g_nccl.AllReduce(h->d_counts + 5, h->d_counts + 5, 2, ncclInt32, ncclSum, c, h->stream));
+  // d_accTop (A | L) and d_accSC are adjacent in the scratch region: one fp64 sum; the two residual counters after
+  const size_t nd = 2 * (size_t)nf * nf * SOSBA_TOPB + (size_t)(D + 1) * (D + 1);
+  int *cnt = (int *)(h->d_H + 3 * ((size_t)D * D + D) + 4);
+  NCCLCHK(g_nccl.AllReduce(h->d_accTop, h->d_accTop, nd, ncclFloat64, ncclSum, c, h->stream));
+  NCCLCHK(g_nccl.AllReduce(cnt, cnt, 2, ncclInt32, ncclSum, c, h->stream));
   NCCLCHK(g_nccl.GroupEnd());
   h->launches += 1;
   return SOSBA_OK;

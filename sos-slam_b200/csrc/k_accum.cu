@@ -101,77 +101,25 @@ __global__ void __launch_bounds__(TOP_WARPS * 32) k_top_accumulate(AccArgs a, in
     nacc++; ntotal++;
   }
   flush();
-  if (lane == 0 && ntotal) atomicAdd(&a.counts[5], ntotal);
+  if (lane == 0 && ntotal) atomicAdd(a.n_acc, ntotal);
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-point sums: G lanes per point, lane j owns residual res_begin[p] + j; sums run in residual order.
-template <int G>
-__global__ void __launch_bounds__(256) k_point_sums(PointArgs a) {
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = gid / G, j = gid % G;
-  const int np = a.plist ? a.n_plist : a.P;
-  if (k >= np) return;
-  const int p = a.plist ? a.plist[k] : k;
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-  const int rb = a.res_begin[p], re = a.res_begin[p + 1];
-  float bd = 0.f, Hdd = 0.f, Hcd[4] = {0.f, 0.f, 0.f, 0.f};
-  float c_bd = 0.f, c_Hdd = 0.f, c_Hcd[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int base = rb; base < re; base += G) {  // a point has <= nf-1 residuals; the loop runs once
-    const int r = base + j;
-    bool use = r < re;
-    if (use) {
-      use = a.r_is_active[r] && !a.r_dropped[r];
-      if (a.mode == 0) use = use && !a.r_is_lin[r];
-      if (a.mode == 1) use = use && a.r_is_lin[r];
-    }
-    c_bd = c_Hdd = 0.f; c_Hcd[0] = c_Hcd[1] = c_Hcd[2] = c_Hcd[3] = 0.f;
-    if (use) {
-      const float *rec = a.rec + (size_t)r * SOSBA_CREC;
-      const float a00 = rec[CR_A], a01 = rec[CR_A + 1], a11 = rec[CR_A + 2];
-      const float Jpdd0 = rec[CR_JPDD], Jpdd1 = rec[CR_JPDD + 1];
-      const float JI_r0 = rec[CR_TR + 4], JI_r1 = rec[CR_TR + 5];
-      const float v0 = a00 * Jpdd0 + a01 * Jpdd1, v1 = a01 * Jpdd0 + a11 * Jpdd1;  // JIdx2 * Jpdd
-      c_bd = JI_r0 * Jpdd0 + JI_r1 * Jpdd1;
-      c_Hdd = v0 * Jpdd0 + v1 * Jpdd1;
-#pragma unroll
-      for (int i = 0; i < 4; i++) c_Hcd[i] = rec[CR_X + i] * v0 + rec[CR_Y + i] * v1;
-    }
-    const int cnt = min(G, re - base);
-    for (int q = 0; q < cnt; q++) {
-      bd += __shfl_sync(gmask, c_bd, q, G);
-      Hdd += __shfl_sync(gmask, c_Hdd, q, G);
-#pragma unroll
-      for (int i = 0; i < 4; i++) Hcd[i] += __shfl_sync(gmask, c_Hcd[i], q, G);
-    }
-  }
-  if (j == 0) {
-    if (a.mode == 0) {
-      a.HddA[p] = Hdd; a.bdA[p] = bd;
-      for (int i = 0; i < 4; i++) a.HcdA[4 * p + i] = Hcd[i];
-    } else {
-      a.HddL[p] = Hdd; a.bdL[p] = bd;
-      for (int i = 0; i < 4; i++) a.HcdL[4 * p + i] = Hcd[i];
-      if (a.mode == 2) { a.HddA[p] = 0.f; a.bdA[p] = 0.f; for (int i = 0; i < 4; i++) a.HcdA[4 * p + i] = 0.f; }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Schur complement in stitched space.  CTA = 256 threads, tiles of 32 points.
-//   phase 1 (8 lanes... one warp per 4 points x 8 residual lanes for nf<=9, generic loop otherwise):
-//           HdiF, bdSumF, g -> shared Gs[32][DPAD]
-//   phase 2 register-tiled SYRK: thread owns 4x4 tiles of the (D+1)^2 upper triangle
+// Per-point sums + Schur complement in stitched space.  CTA = 256 threads, tiles of 32 points.
+//   phase 1: 8 lanes per point, lane q owns residual res_begin[p] + q (+8, +16 for nf > 9):
+//            (a) its share of Hdd / bd / Hcd (AccumulatedTopHessian.cpp:124-127), summed across the lanes in
+//                residual order into the A (non-linearised) and L (linearised) point sums (:132-146);
+//            (b) adHost * JpJdF (host rows, summed over the lanes) and adTarget * JpJdF (target rows);
+//            then HdiF, bdSumF (AccumulatedSCHessian.cpp:46-56) and g -> shared Gs[32][DPAD]
+//   phase 2: register-tiled SYRK acc += w * g g^T; thread owns up to 3 4x4 tiles of the (D+1)^2 upper triangle
 constexpr int SC_TP = 32;       // points per tile
 constexpr int SC_MAXT = 3;      // 4x4 tiles per thread (nf <= 16)
-__global__ void __launch_bounds__(256) k_sc_accumulate(SCArgs a, int DP, int DPAD, int ntiles4, int tiles_total) {
+__global__ void __launch_bounds__(256) k_point_sc(SCArgs a, int DP, int DPAD, int ntiles4, int tiles_total) {
   extern __shared__ float smem[];
   float *Gs = smem;                    // [SC_TP][DPAD]
   float *Ws = smem + SC_TP * DPAD;     // [SC_TP]
   const int tid = threadIdx.x;
   const int nt4 = DPAD / 4;
-  // tile assignment: linear index over upper-triangular 4x4 tiles (ti <= tj)
   int my_ti[SC_MAXT], my_tj[SC_MAXT];
   float acc[SC_MAXT][16];
 #pragma unroll
@@ -187,49 +135,94 @@ __global__ void __launch_bounds__(256) k_sc_accumulate(SCArgs a, int DP, int DPA
     for (int q = 0; q < 16; q++) acc[m][q] = 0.f;
   }
   const int np = a.plist ? a.n_plist : a.P;
-  const int D = a.D;
+  const int D = a.D, nf = a.nf;
+  const int lp = tid >> 3, sub = tid & 7;
+  const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
 
   for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
     for (int i = tid; i < SC_TP * DPAD; i += 256) Gs[i] = 0.f;
     if (tid < SC_TP) Ws[tid] = 0.f;
     __syncthreads();
-    // phase 1: 8 threads per point
     {
-      const int lp = tid >> 3, sub = tid & 7;
       const int k = tile * SC_TP + lp;
-      if (k < np) {
+      if (k < np) {   // uniform across the 8 lanes of a point
         const int p = a.plist ? a.plist[k] : k;
         const int rb = a.res_begin[p], re = a.res_begin[p + 1];
+        const int host = a.p_host[p];
+        float *g = Gs + lp * DPAD;
+        float HddA = 0.f, bdA = 0.f, HcdA[4] = {0.f, 0.f, 0.f, 0.f}, HddL = 0.f, bdL = 0.f, HcdL[4] = {0.f, 0.f, 0.f, 0.f};
+        float gh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int ngood = 0;
-        for (int r = rb; r < re; r++) ngood += (a.r_is_active[r] && !a.r_dropped[r]) ? 1 : 0;
+        for (int base = rb; base < re; base += 8) {   // one round for nf <= 9
+          const int r = base + sub;
+          const bool use = r < re && a.r_is_active[r] && !a.r_dropped[r];
+          const bool lin = use && (a.mode == 2 || a.r_is_lin[r]);
+          float c_bd = 0.f, c_Hdd = 0.f, c_Hcd[4] = {0.f, 0.f, 0.f, 0.f};
+          float sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (use) {
+            const float4 *rec4 = (const float4 *)(a.rec + (size_t)r * SOSBA_CREC);
+            const float4 x03 = rec4[0];                    // CR_X 0..3
+            const float4 y_a = rec4[2], y_b = rec4[3];     // floats 8..15: x[8],x[9],y[0],y[1] | y[2],y[3],y[4],y[5]
+            const float4 f20 = rec4[5], f24 = rec4[6], f28 = rec4[7], f32 = rec4[8], f36 = rec4[9];
+            const float4 v03 = rec4[10], v47 = rec4[11];   // JpJdF
+            const float a00 = f20.x, a01 = f20.y, a11 = f20.z;               // CR_A 20..22
+            const float JI_r0 = f24.w, JI_r1 = f28.x;                         // CR_TR+4 = 27, 28
+            const float Jpdd0 = f32.w, Jpdd1 = f36.x;                         // CR_JPDD = 35, 36
+            const float v0 = a00 * Jpdd0 + a01 * Jpdd1, v1 = a01 * Jpdd0 + a11 * Jpdd1;  // JIdx2 * Jpdd
+            c_bd = JI_r0 * Jpdd0 + JI_r1 * Jpdd1;
+            c_Hdd = v0 * Jpdd0 + v1 * Jpdd1;
+            const float xs[4] = {x03.x, x03.y, x03.z, x03.w}, ys[4] = {y_a.z, y_a.w, y_b.x, y_b.y};
+#pragma unroll
+            for (int i = 0; i < 4; i++) c_Hcd[i] = xs[i] * v0 + ys[i] * v1;
+            const int t = a.r_target[r];
+            const float4 *Ah = (const float4 *)(a.adHostF + 64 * (size_t)(host + t * nf));
+            const float4 *At = (const float4 *)(a.adTargetF + 64 * (size_t)(host + t * nf));
+            const float v[8] = {v03.x, v03.y, v03.z, v03.w, v47.x, v47.y, v47.z, v47.w};
+#pragma unroll
+            for (int row = 0; row < 8; row++) {
+              const float4 h0 = __ldg(Ah + 2 * row), h1 = __ldg(Ah + 2 * row + 1), t0 = __ldg(At + 2 * row), t1 = __ldg(At + 2 * row + 1);
+              sh[row] = h0.x * v[0] + h0.y * v[1] + h0.z * v[2] + h0.w * v[3] + h1.x * v[4] + h1.y * v[5] + h1.z * v[6] + h1.w * v[7];
+              const float st = t0.x * v[0] + t0.y * v[1] + t0.z * v[2] + t0.w * v[3] + t1.x * v[4] + t1.y * v[5] + t1.z * v[6] + t1.w * v[7];
+              atomicAdd(&g[4 + 8 * t + row], st);   // one residual per (point, target): uncontended
+            }
+          }
+          ngood += __popc(__ballot_sync(gmask, use) & gmask);
+          const int cnt = min(8, re - base);
+          for (int q = 0; q < cnt; q++) {   // residual-order sums (deterministic, reference order)
+            const bool ql = __shfl_sync(gmask, (int)lin, q, 8) != 0;
+            const float q_bd = __shfl_sync(gmask, c_bd, q, 8), q_Hdd = __shfl_sync(gmask, c_Hdd, q, 8);
+            if (ql) { bdL += q_bd; HddL += q_Hdd; } else { bdA += q_bd; HddA += q_Hdd; }
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const float qc = __shfl_sync(gmask, c_Hcd[i], q, 8); if (ql) HcdL[i] += qc; else HcdA[i] += qc; }
+          }
+#pragma unroll
+          for (int row = 0; row < 8; row++) {
+            float s = sh[row];
+            s += __shfl_xor_sync(gmask, s, 1, 8); s += __shfl_xor_sync(gmask, s, 2, 8); s += __shfl_xor_sync(gmask, s, 4, 8);
+            gh[row] += s;
+          }
+        }
+        if (sub == 0) {
+          a.HddA[p] = HddA; a.bdA[p] = bdA; a.HddL[p] = HddL; a.bdL[p] = bdL;
+          for (int i = 0; i < 4; i++) { a.HcdA[4 * p + i] = HcdA[i]; a.HcdL[4 * p + i] = HcdL[i]; }
+        }
         if (ngood == 0) {
           if (sub == 0) { a.HdiF[p] = 0.f; a.bdSumF[p] = 0.f; a.idepth_hessian[p] = 0.f; a.maxRelBaseline[p] = 0.f; }
         } else {
-          float H = a.HddA[p] + a.HddL[p] + a.priorF[p];
+          float H = HddA + HddL + a.priorF[p];
           if (H < 1e-10) H = 1e-10;
           const float HdiF = (float)(1.0 / (double)H);
-          float bdSum = a.bdA[p] + a.bdL[p];
+          float bdSum = bdA + bdL;
           if (a.shiftPriorToZero) bdSum += a.priorF[p] * a.deltaF[p];
-          float *g = Gs + lp * DPAD;
           if (sub == 0) {
             a.HdiF[p] = HdiF; a.bdSumF[p] = bdSum; a.idepth_hessian[p] = H;
             Ws[lp] = HdiF;
-            for (int i = 0; i < 4; i++) g[i] = a.HcdA[4 * p + i] + a.HcdL[4 * p + i];
             g[D] = bdSum;
           }
-          const int host = a.p_host[p];
-          for (int r = rb; r < re; r++) {  // thread `sub` computes row `sub` of adHost*v and adTarget*v
-            if (!(a.r_is_active[r] && !a.r_dropped[r])) continue;
-            const int t = a.r_target[r];
-            const float *v = a.rec + (size_t)r * SOSBA_CREC + CR_JPJDF;
-            const float *Ah = a.adHostF + 64 * (size_t)(host + t * a.nf) + 8 * sub;
-            const float *At = a.adTargetF + 64 * (size_t)(host + t * a.nf) + 8 * sub;
-            float sh = 0.f, st = 0.f;
 #pragma unroll
-            for (int q = 0; q < 8; q++) { const float vq = v[q]; sh += Ah[q] * vq; st += At[q] * vq; }
-            g[4 + 8 * host + sub] += sh;   // only this thread touches (lp, host row sub)
-            g[4 + 8 * t + sub] += st;
-          }
+          for (int i = 0; i < 4; i++) if (sub == i) g[i] = HcdA[i] + HcdL[i];
+#pragma unroll
+          for (int i = 0; i < 8; i++) if (sub == i) atomicAdd(&g[4 + 8 * host + i], gh[i]);
         }
       }
     }
@@ -254,7 +247,6 @@ __global__ void __launch_bounds__(256) k_sc_accumulate(SCArgs a, int DP, int DPA
     }
     __syncthreads();
   }
-  // flush
 #pragma unroll
   for (int m = 0; m < SC_MAXT; m++) {
     if (my_ti[m] < 0) continue;
@@ -264,7 +256,7 @@ __global__ void __launch_bounds__(256) k_sc_accumulate(SCArgs a, int DP, int DPA
 #pragma unroll
       for (int jj = 0; jj < 4; jj++) {
         const int i = i0 + ii, j = j0 + jj;
-        if (i < DP && j < DP && acc[m][ii * 4 + jj] != 0.f) atomicAdd(a.accSC + (size_t)i * DP + j, (double)acc[m][ii * 4 + jj]);
+        if (i <= j && j < DP && acc[m][ii * 4 + jj] != 0.f) atomicAdd(a.accSC + (size_t)i * DP + j, (double)acc[m][ii * 4 + jj]);
       }
   }
 }
@@ -275,9 +267,9 @@ __global__ void __launch_bounds__(64) k_stitch_top(const double *__restrict__ ac
                                                    const double *__restrict__ adTarget, int nf, double *__restrict__ H, double *__restrict__ b) {
   __shared__ double accH[13][13];
   __shared__ double Ah[64], At[64], AhP[64], AtP[64];
-  const int blk = blockIdx.x;          // = h + nf*t
+  const int blk = blockIdx.x % (nf * nf);   // = h + nf*t ; blockIdx.x / nf^2 selects the table (A pass, L pass)
   const int h = blk % nf, t = blk / nf;
-  const double *src = accTop + (size_t)blk * SOSBA_TOPB;
+  const double *src = accTop + (size_t)blockIdx.x * SOSBA_TOPB;
   if (src[91] == 0.0) return;          // num == 0 (AccumulatedTopHessian.cpp:168-170)
   const int tid = threadIdx.x;
   const int D = 4 + 8 * nf;
@@ -363,42 +355,50 @@ __global__ void __launch_bounds__(256) k_finalize_sc(const double *__restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// a11  resubstituteFPt (+ the point part of backupState / doStepFromBackup when do_step)
+// a11  resubstituteFPt (+ the point part of backupState / doStepFromBackup when do_step); 8 lanes per point,
+// lane q owns residual res_begin[p] + q; the subtraction chain runs in residual order like the reference.
 __global__ void __launch_bounds__(256) k_resubstitute(ResubArgs a) {
   __shared__ double s_sum[3];
   if (threadIdx.x < 3) s_sum[threadIdx.x] = 0.0;
   __syncthreads();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = gid >> 3, sub = gid & 7;
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
   float st2 = 0.f, absid = 0.f, one = 0.f;
   if (p < a.P) {
     const int rb = a.res_begin[p], re = a.res_begin[p + 1];
+    const int host = a.p_host[p];
+    const float *xc = a.xAd + (size_t)a.nf * a.nf * 8;
+    float b = a.bdSumF[p];
+    float dotc = 0.f;
+    for (int i = 0; i < 4; i++) dotc += xc[i] * (a.HcdA[4 * p + i] + a.HcdL[4 * p + i]);
+    b -= dotc;
     int ngood = 0;
-    for (int r = rb; r < re; r++) ngood += (a.r_is_active[r] && !a.r_dropped[r]) ? 1 : 0;
-    float step = 0.f;
-    if (ngood > 0) {
-      const float *xc = a.xAd + (size_t)a.nf * a.nf * 8;
-      float b = a.bdSumF[p];
-      float dotc = 0.f;
-      for (int i = 0; i < 4; i++) dotc += xc[i] * (a.HcdA[4 * p + i] + a.HcdL[4 * p + i]);
-      b -= dotc;
-      const int host = a.p_host[p];
-      for (int r = rb; r < re; r++) {
-        if (!(a.r_is_active[r] && !a.r_dropped[r])) continue;
-        const float *xa = a.xAd + 8 * (size_t)(host * a.nf + a.r_target[r]);
-        const float *v = a.rec + (size_t)r * SOSBA_CREC + CR_JPJDF;
-        float s = 0.f;
-        for (int i = 0; i < 8; i++) s += xa[i] * v[i];
-        b -= s;
+    for (int base = rb; base < re; base += 8) {
+      const int r = base + sub;
+      const bool use = r < re && a.r_is_active[r] && !a.r_dropped[r];
+      float s = 0.f;
+      if (use) {
+        const float4 *xa = (const float4 *)(a.xAd + 8 * (size_t)(host * a.nf + a.r_target[r]));
+        const float4 *v = (const float4 *)(a.rec + (size_t)r * SOSBA_CREC + CR_JPJDF);
+        const float4 x0 = xa[0], x1 = xa[1], v0 = v[0], v1 = v[1];
+        s = x0.x * v0.x; s += x0.y * v0.y; s += x0.z * v0.z; s += x0.w * v0.w;
+        s += x1.x * v1.x; s += x1.y * v1.y; s += x1.z * v1.z; s += x1.w * v1.w;
       }
-      step = -b * a.HdiF[p];
+      ngood += __popc(__ballot_sync(gmask, use) & gmask);
+      const int cnt = min(8, re - base);
+      for (int q = 0; q < cnt; q++) b -= __shfl_sync(gmask, s, q, 8);   // inactive lanes contribute 0
     }
-    a.step[p] = step;
-    if (a.do_step) {
-      const float backup = a.idepth[p];       // backupState: idepth_backup = idepth
-      a.idepth_backup[p] = backup;
-      const float nid = backup + step;        // stepfacD = 1
-      a.idepth[p] = nid; a.idepth_zero[p] = nid; a.deltaF[p] = 0.f;
-      st2 = step * step; absid = fabsf(backup); one = 1.f;
+    if (sub == 0) {
+      const float step = ngood > 0 ? -b * a.HdiF[p] : 0.f;
+      a.step[p] = step;
+      if (a.do_step) {
+        const float backup = a.idepth[p];       // backupState: idepth_backup = idepth
+        a.idepth_backup[p] = backup;
+        const float nid = backup + step;        // stepfacD = 1
+        a.idepth[p] = nid; a.idepth_zero[p] = nid; a.deltaF[p] = 0.f;
+        st2 = step * step; absid = fabsf(backup); one = 1.f;
+      }
     }
   }
   if (a.do_step) {
@@ -438,25 +438,15 @@ void launch_top_accumulate(sosba *h, const AccArgs &a) {
   h->launches++;
 }
 
-void launch_point_sums(sosba *h, const PointArgs &a) {
-  const int np = a.plist ? a.n_plist : a.P;
-  if (np == 0) return;
-  const int maxres = a.nf - 1;
-  if (maxres <= 8) k_point_sums<8><<<(np * 8 + 255) / 256, 256, 0, h->stream>>>(a);
-  else if (maxres <= 16) k_point_sums<16><<<(np * 16 + 255) / 256, 256, 0, h->stream>>>(a);
-  else k_point_sums<32><<<(np * 32 + 255) / 256, 256, 0, h->stream>>>(a);
-  h->launches++;
-}
-
-void launch_sc_accumulate(sosba *h, const SCArgs &a) {
+void launch_point_sc(sosba *h, const SCArgs &a) {
   const int np = a.plist ? a.n_plist : a.P;
   if (np == 0) return;
   const int DP = a.D + 1, DPAD = (DP + 3) / 4 * 4, nt4 = DPAD / 4;
   const int ntiles4 = nt4 * (nt4 + 1) / 2;
   const int tiles_total = (np + SC_TP - 1) / SC_TP;
-  int blocks = tiles_total < h->sm_count ? tiles_total : h->sm_count;
+  int blocks = tiles_total < 2 * h->sm_count ? tiles_total : 2 * h->sm_count;
   const size_t smem = (size_t)(SC_TP * DPAD + SC_TP) * sizeof(float);
-  k_sc_accumulate<<<blocks, 256, smem, h->stream>>>(a, DP, DPAD, ntiles4, tiles_total);
+  k_point_sc<<<blocks, 256, smem, h->stream>>>(a, DP, DPAD, ntiles4, tiles_total);
   h->launches++;
 }
 
@@ -467,6 +457,12 @@ void launch_stitch_top(sosba *h, const double *accTop, const double *adHost, con
   h->launches += 2;
 }
 
+// hot path: both tables (A | L) into one raw H, b; symmetrisation and priors happen inside k_solve
+void launch_stitch_raw(sosba *h, const double *accTop2, const double *adHost, const double *adTarget, int nf, int ntables, double *H, double *b) {
+  k_stitch_top<<<ntables * nf * nf, 64, 0, h->stream>>>(accTop2, adHost, adTarget, nf, H, b);
+  h->launches++;
+}
+
 void launch_finalize_sc(sosba *h, const double *accSC, int nf, double *H, double *b) {
   k_finalize_sc<<<1, 256, 0, h->stream>>>(accSC, 4 + 8 * nf, H, b);
   h->launches++;
@@ -474,6 +470,6 @@ void launch_finalize_sc(sosba *h, const double *accSC, int nf, double *H, double
 
 void launch_resubstitute(sosba *h, const ResubArgs &a) {
   if (a.P == 0) return;
-  k_resubstitute<<<(a.P + 255) / 256, 256, 0, h->stream>>>(a);
+  k_resubstitute<<<(a.P * 8 + 255) / 256, 256, 0, h->stream>>>(a);
   h->launches++;
 }

@@ -1,137 +1,143 @@
 // k_solve.cu — EnergyFunctional::solveSystemF without IMU (EnergyFunctional.cpp:1029-1184) as ONE single-CTA
-// fp64 kernel: assemble HFinal = HA + HL (+HM), b (+bM + HM*delta), damp diag*(1+1e-5), subtract H_sc/(1+1e-5),
-// b_sc, Jacobi-precondition with 1/sqrt(diag+10), pivoted LDL^T (the left-looking algorithm with the
-// largest-|diagonal| transposition rule of Eigen::LDLT, the solver called at :1147-1148), substitute, undo the
-// scaling, and prepare xAd[h*nf+t] = x_h^T adHostF[h+nf*t] + x_t^T adTargetF[h+nf*t] for resubstituteF_MT (:496-524).
-// D = 4 + 8*nf <= 132; the matrix lives in shared memory (D*(D+1) doubles).
+// fp64 kernel.  Input is the raw stitch of the top blocks (A and L passes summed, not yet symmetrised), the
+// stitched-space Schur Gram matrix, the priors and (optionally) the marginalisation prior HM, bM:
+//   HFinal = sym(Htop) + priors (+HM), b = btop + prior*delta_prior (+bM + HM*delta); diag *= (1+1e-5);
+//   HFinal -= H_sc/(1+1e-5); b -= b_sc; Jacobi scaling 1/sqrt(diag+10); LDL^T with the transposition order of
+//   Eigen::LDLT (the solver called at :1147-1148); back-substitution; x = S * y; then
+//   xAd[h*nf+t] = x_h^T adHostF[h+nf*t] + x_t^T adTargetF[h+nf*t] for resubstituteF_MT (:496-524).
+// D = 4 + 8*nf <= 132; the (D+1)^2 augmented matrix lives in shared memory.
 #include <math.h>
 
 #include "kernels.h"
 
 namespace {
 
+// Pivot order.  Eigen::LDLT is left-looking: when it searches the largest |diagonal| of the trailing block at
+// step k, none of those entries has been touched yet, so the transposition sequence depends only on the
+// diagonal of the (preconditioned) input.  One warp replays it on a copy of the diagonal; perm[i] = original
+// index that ends up at position i.  The factorisation itself can then run without pivoting, in any order.
+__device__ void pivot_order(const double *__restrict__ diag_in, double *__restrict__ d, int *__restrict__ perm, int D, int lane) {
+  for (int i = lane; i < D; i += 32) { d[i] = fabs(diag_in[i]); perm[i] = i; }
+  __syncwarp();
+  for (int k = 0; k < D; k++) {
+    double best = -1.0; int bi = D;
+    for (int i = k + lane; i < D; i += 32) { const double v = d[i]; if (v > best) { best = v; bi = i; } }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0 && bi != k) { const double t = d[k]; d[k] = d[bi]; d[bi] = t; const int p = perm[k]; perm[k] = perm[bi]; perm[bi] = p; }
+    __syncwarp();
+  }
+}
+
+// final (undamped) top value at (r,c), r >= c, from the raw stitch (AccumulatedTopHessian.h:107-126 epilogue)
+__device__ __forceinline__ double top_entry(const double *__restrict__ Hraw, int D, int r, int c) {
+  if (c >= 4 && ((r - 4) >> 3) != ((c - 4) >> 3)) return Hraw[(size_t)r * D + c] + Hraw[(size_t)c * D + r];
+  return Hraw[(size_t)r * D + c];
+}
+
 __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
   extern __shared__ double sm[];
-  const int D = a.D, LD = D + 1, tid = threadIdx.x, nth = blockDim.x;
-  double *M = sm;                 // [D][LD]
-  double *bb = M + (size_t)D * LD;  // [D]
-  double *S = bb + D;             // [D]
-  double *temp = S + D;           // [D]
-  double *y = temp + D;           // [D]
-  __shared__ int tr[136];
-  __shared__ int s_big;
-  __shared__ double s_red[8];
-  __shared__ int s_redi[8];
-  const double lambda = 1e-5;                       // EnergyFunctional.cpp:1031
-  const double sc = (double)(1.0f / (float)(1 + lambda));  // float-typed scalar (:1099)
-
-  // ---- assemble --------------------------------------------------------------------------------
-  for (int e = tid; e < D * D; e += nth) {
-    const int r = e / D, c = e % D;
-    double v = a.HA[e] + a.HL[e];
-    if (a.HM) v += a.HM[e];
-    if (r == c) v *= (1 + lambda);
-    v -= a.Hsc[e] * sc;
-    M[r * LD + c] = v;
-    if (a.Hfinal) a.Hfinal[e] = v;
-  }
-  for (int r = tid; r < D; r += nth) {
-    double v = a.bA[r] + a.bL[r];
-    if (a.HM) {  // bM_top = bM + HM * getStitchedDeltaF() (:1070-1091)
-      double s = 0;
-      for (int c = 0; c < D; c++) {
-        const double dl = c < 4 ? (double)a.cDeltaF[c] : a.wprior[4 + 16 * a.nf + (c - 4)];
-        s += a.HM[(size_t)r * D + c] * dl;
-      }
-      v += a.bM[r] + s;
-    }
-    v -= a.bsc[r];
-    bb[r] = v;
-    if (a.bfinal) a.bfinal[r] = v;
-  }
-  __syncthreads();
-  // ---- Jacobi preconditioning (:1143-1146) -------------------------------------------------------
-  for (int i = tid; i < D; i += nth) S[i] = 1.0 / sqrt(M[i * LD + i] + 10.0);
-  __syncthreads();
-  for (int e = tid; e < D * D; e += nth) { const int r = e / D, c = e % D; M[r * LD + c] = S[r] * M[r * LD + c] * S[c]; }
-  for (int i = tid; i < D; i += nth) y[i] = S[i] * bb[i];
-  __syncthreads();
-
-  // ---- pivoted LDL^T, lower triangle in place ------------------------------------------------------
+  const int D = a.D, LD = D + 1, tid = threadIdx.x, nth = blockDim.x, nf = a.nf;
+  double *M = sm;                          // [D+1][LD]: permuted, preconditioned lower triangle + rhs row
+  double *S = M + (size_t)(D + 1) * LD;    // [D] Jacobi scaling
+  double *bb = S + D;                      // [D] unscaled rhs
+  double *cbuf = bb + D;                   // [D+1]
+  double *lbuf = cbuf + D + 1;             // [D+1]
+  double *dtmp = lbuf + D + 1;             // [D]
+  double *delta = dtmp + D;                // [D]
+  __shared__ int perm[136];
+  const double lambda = 1e-5;                               // EnergyFunctional.cpp:1031
+  const double sc = (double)(1.0f / (float)(1 + lambda));   // float-typed scalar (:1099)
+  const double *cPrior = a.wprior, *fprior = a.wprior + 4, *fdp = a.wprior + 4 + 8 * nf, *fdelta = a.wprior + 4 + 16 * nf;
+  const int DP = D + 1;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nth >> 5;
+
+  // ---- diagonal, rhs --------------------------------------------------------------------------------
+  for (int i = tid; i < D; i += nth) delta[i] = i < 4 ? (double)a.cDeltaF[i] : fdelta[i - 4];
+  __syncthreads();
+  for (int r = warp; r < D; r += nwarps) {   // bM_top = bM + HM * delta (:1070-1091)
+    double s = 0;
+    if (a.HM) for (int c = lane; c < D; c += 32) s += a.HM[(size_t)r * D + c] * delta[c];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      const double pr = r < 4 ? cPrior[r] : fprior[r - 4];
+      const double dpr = r < 4 ? (double)a.cDeltaF[r] : fdp[r - 4];
+      double v = a.btop[r] + pr * dpr;                     // AccumulatedTopHessian.cpp:292-300 (L pass carries the priors)
+      if (a.HM) v += a.bM[r] + s;
+      v -= a.accSC[(size_t)r * DP + D];
+      bb[r] = v;
+      if (a.bfinal) a.bfinal[r] = v;
+      double dg = a.Htop[(size_t)r * D + r] + pr;
+      if (a.HM) dg += a.HM[(size_t)r * D + r];
+      dg *= (1 + lambda);
+      dg -= a.accSC[(size_t)r * DP + r] * sc;
+      dtmp[r] = dg;
+      S[r] = 1.0 / sqrt(dg + 10.0);                        // :1143-1146
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    for (int i = lane; i < D; i += 32) cbuf[i] = S[i] * dtmp[i] * S[i];
+    __syncwarp();
+    pivot_order(cbuf, lbuf, perm, D, lane);
+  }
+  __syncthreads();
+  // ---- assemble the permuted, preconditioned lower triangle --------------------------------------------
+  for (int e = tid; e < D * D; e += nth) {
+    const int i = e / D, j = e % D;
+    if (j > i) continue;
+    int r = perm[i], c = perm[j];
+    if (r < c) { const int t = r; r = c; c = t; }
+    double v;
+    if (r == c) v = dtmp[r];
+    else {
+      v = top_entry(a.Htop, D, r, c);
+      if (a.HM) v += a.HM[(size_t)r * D + c];
+      v -= a.accSC[(size_t)c * DP + r] * sc;
+    }
+    if (a.Hfinal) { a.Hfinal[(size_t)r * D + c] = v; a.Hfinal[(size_t)c * D + r] = v; }
+    M[i * LD + j] = S[r] * v * S[c];
+  }
+  for (int j = tid; j < D; j += nth) M[D * LD + j] = S[perm[j]] * bb[perm[j]];
+  __syncthreads();
+
+  // ---- right-looking LDL^T with the rhs as an extra row: row D ends as D^-1 L^-1 P b ----------------------
+  const int ty = tid >> 4, tx = tid & 15;
   for (int k = 0; k < D; k++) {
-    // largest |diagonal| of the trailing block, first index on ties
-    {
-      double best = -1.0; int bi = D;
-      for (int i = k + tid; i < D; i += nth) { const double v = fabs(M[i * LD + i]); if (v > best) { best = v; bi = i; } }
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-      }
-      if (lane == 0) { s_red[warp] = best; s_redi[warp] = bi; }
-      __syncthreads();
-      if (tid == 0) {
-        double bv = s_red[0]; int bidx = s_redi[0];
-        for (int w = 1; w < nwarps; w++) if (s_red[w] > bv || (s_red[w] == bv && s_redi[w] < bidx)) { bv = s_red[w]; bidx = s_redi[w]; }
-        s_big = bidx; tr[k] = bidx;
-      }
-      __syncthreads();
+    const double dk = M[k * LD + k];
+    for (int i = k + 1 + tid; i <= D; i += nth) {
+      const double v = M[i * LD + k];
+      cbuf[i] = v;
+      const double l = dk != 0.0 ? v / dk : 0.0;
+      lbuf[i] = l;
+      M[i * LD + k] = l;
     }
-    const int big = s_big;
-    if (big != k) {  // symmetric transposition on the lower triangle
-      for (int c = tid; c < k; c += nth) { const double t = M[k * LD + c]; M[k * LD + c] = M[big * LD + c]; M[big * LD + c] = t; }
-      for (int r = big + 1 + tid; r < D; r += nth) { const double t = M[r * LD + k]; M[r * LD + k] = M[r * LD + big]; M[r * LD + big] = t; }
-      for (int i = k + 1 + tid; i < big; i += nth) { const double t = M[i * LD + k]; M[i * LD + k] = M[big * LD + i]; M[big * LD + i] = t; }
-      if (tid == 0) { const double t = M[k * LD + k]; M[k * LD + k] = M[big * LD + big]; M[big * LD + big] = t; }
-      __syncthreads();
+    __syncthreads();
+    for (int i = k + 1 + ty; i <= D; i += 16) {
+      const double li = lbuf[i];
+      const int jmax = i < D ? i : D - 1;
+      for (int j = k + 1 + tx; j <= jmax; j += 16) M[i * LD + j] -= li * cbuf[j];
     }
-    if (k > 0) {
-      for (int j = tid; j < k; j += nth) temp[j] = M[j * LD + j] * M[k * LD + j];
-      __syncthreads();
-      // rows k..D-1: 4 lanes per row share the dot product over j < k (row k itself updates the pivot)
-      const int sub = tid & 3;
-      for (int base = k; base < D; base += (nth >> 2)) {  // uniform trip count: the shuffles need the whole warp
-        const int row = base + (tid >> 2);
-        double s = 0;
-        if (row < D) for (int j = sub; j < k; j += 4) s += M[row * LD + j] * temp[j];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (row < D && sub == 0) M[row * LD + k] -= s;
-      }
-      __syncthreads();
-    }
-    const double akk = M[k * LD + k];
-    if (fabs(akk) > 0) for (int i = k + 1 + tid; i < D; i += nth) M[i * LD + k] /= akk;
     __syncthreads();
   }
-  // ---- solve: P b, L, D, L^T, P^T ------------------------------------------------------------------
-  if (tid == 0) {
-    for (int k = 0; k < D; k++) { const double t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
-  }
+  // ---- L^T w = z, undo permutation and scaling -----------------------------------------------------------
+  double *w = cbuf;
+  for (int j = tid; j < D; j += nth) w[j] = M[D * LD + j];
   __syncthreads();
-  for (int j = 0; j < D; j++) {  // forward, column oriented
-    const double yj = y[j];
-    for (int i = j + 1 + tid; i < D; i += nth) y[i] -= M[i * LD + j] * yj;
+  for (int j = D - 1; j > 0; j--) {
+    const double wj = w[j];
+    for (int i = tid; i < j; i += nth) w[i] -= M[j * LD + i] * wj;
     __syncthreads();
   }
-  for (int i = tid; i < D; i += nth) { const double d = M[i * LD + i]; y[i] = fabs(d) > 1.0 / 1.7976931348623157e308 ? y[i] / d : 0.0; }
-  __syncthreads();
-  for (int j = D - 1; j >= 0; j--) {  // backward with L^T
-    const double yj = y[j];
-    for (int i = tid; i < j; i += nth) y[i] -= M[j * LD + i] * yj;
-    __syncthreads();
-  }
-  if (tid == 0) {
-    for (int k = D - 1; k >= 0; k--) { const double t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
-  }
-  __syncthreads();
+  double *y = lbuf;   // x in original order
   bool bad = false;
-  for (int i = tid; i < D; i += nth) { const double xi = S[i] * y[i]; a.x[i] = xi; y[i] = xi; if (!isfinite(xi)) bad = true; }
+  for (int j = tid; j < D; j += nth) { const int r = perm[j]; const double xi = S[r] * w[j]; y[r] = xi; a.x[r] = xi; if (!isfinite(xi)) bad = true; }
   if (bad && a.status) a.status[0] = 1;
   __syncthreads();
   // ---- xAd (EnergyFunctional.cpp:509-513) and xc ------------------------------------------------------
   if (a.xAd) {
-    const int nf = a.nf;
     for (int e = tid; e < nf * nf * 8; e += nth) {
       const int c = e & 7, ht = e >> 3, h = ht / nf, t = ht % nf;   // xAd index = h*nf + t
       const float *AhF = a.adHostF + 64 * (size_t)(h + nf * t), *AtF = a.adTargetF + 64 * (size_t)(h + nf * t);
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(256) k_make_xad(const double *__restrict__ x, 
 
 }  // namespace
 
-size_t solve_smem_bytes(int D) { return ((size_t)D * (D + 1) + 4 * (size_t)D) * sizeof(double); }
+size_t solve_smem_bytes(int D) { return ((size_t)(D + 1) * (D + 1) + 6 * (size_t)D + 8) * sizeof(double); }
 
 void launch_solve(sosba *h, const SolveArgs &a) {
   const size_t smem = solve_smem_bytes(a.D);

@@ -43,6 +43,20 @@ struct ThArgs {
 };
 void launch_energy_th(sosba *h, const ThArgs &a);
 
+// frames + calibration part of a Gauss-Newton step, device resident
+#define SOSBA_FS 64   // doubles per frame: evalPT[12] state[10]@12 state_zero[10]@22 state_backup[10]@32 step[10]@42 ab_exposure@52
+struct StepArgs {
+  int nf;
+  float stepfac;
+  const double *x;
+  double *fs, *cs;       // frame states [nf*SOSBA_FS]; calib value[4] | value_zero[4] | value_backup[4] | step[4]
+  float *precalc, *adHTdeltaF, *calib;
+  const float *adHostF, *adTargetF;
+  double *wprior;
+  double *iter;          // out: sumA, sumB, sumT, sumR (already / nf)
+};
+void launch_frame_step(sosba *h, const StepArgs &a);
+
 // tracker / scale optimizer (calcResPose / calcResScale): writes the 8 warped SoA arrays (masked, not
 // compacted: invalid points carry weight 0) and the sums
 struct TrackResArgs {
@@ -70,54 +84,47 @@ struct AccArgs {
   const uint8_t *r_is_lin, *r_is_active, *r_dropped;
   const float *rec;
   double *accTop;    // [nf*nf*92]
-  int *counts;       // [5] += residuals accumulated
+  int *n_acc;        // += residuals accumulated (resInA / resInL / resInM)
 };
 void launch_top_accumulate(sosba *h, const AccArgs &a);
 
-struct PointArgs {
+// per-point sums (A: non-linearised, L: linearised; mode 2: every active residual -> L, A = 0) + Schur term
+struct SCArgs {
   int P, nf, D;
   const int *plist;  // nullptr = all points, else the points to process (marginalisation)
   int n_plist;
-  int mode;          // 0: A sums (non-linearised)  1: L sums (linearised)  2: marginalisation sums (-> L, A = 0)
+  int mode;          // 0: accumulateAF/LF/SCF  2: marginalizePointsF
+  int shiftPriorToZero;
   const int *res_begin, *r_target, *p_host;
   const uint8_t *r_is_lin, *r_is_active, *r_dropped;
   const float *rec;
   float *HddA, *bdA, *HcdA, *HddL, *bdL, *HcdL;
-};
-void launch_point_sums(sosba *h, const PointArgs &a);
-
-struct SCArgs {
-  int P, nf, D;
-  const int *plist;
-  int n_plist;
-  int shiftPriorToZero;
-  const int *res_begin, *r_target, *p_host;
-  const uint8_t *r_is_active, *r_dropped;
-  const float *rec;
-  const float *HddA, *bdA, *HcdA, *HddL, *bdL, *HcdL, *priorF, *deltaF;
+  const float *priorF, *deltaF;
   float *HdiF, *bdSumF, *idepth_hessian, *maxRelBaseline;
   const float *adHostF, *adTargetF;
-  double *accSC;     // [(D+1)*(D+1)] upper tiles
+  double *accSC;     // [(D+1)*(D+1)] upper triangle
 };
-void launch_sc_accumulate(sosba *h, const SCArgs &a);
+void launch_point_sc(sosba *h, const SCArgs &a);
 
 // top blocks -> H (D*D), b (D): AccumulatedTopHessianSSE::stitchDoubleInternal + stitchDoubleMT epilogue
 void launch_stitch_top(sosba *h, const double *accTop, const double *adHost, const double *adTarget, int nf, double *H, double *b,
                        int usePrior, const double *wprior, const float *cDeltaF);
+void launch_stitch_raw(sosba *h, const double *accTop2, const double *adHost, const double *adTarget, int nf, int ntables, double *H, double *b);
 // accSC -> Hsc (D*D), bsc (D)
 void launch_finalize_sc(sosba *h, const double *accSC, int nf, double *H, double *b);
 
 // ---- k_solve.cu ---------------------------------------------------------------------------------
 struct SolveArgs {
   int nf, D;
-  const double *HA, *bA, *HL, *bL, *Hsc, *bsc;   // stitched
-  const double *HM, *bM;                          // may be null
-  const double *wprior;                           // frame_delta at 4 + 16*nf
+  const double *Htop, *btop;   // raw stitch of the A and L top blocks (k_stitch_top output, not symmetrised)
+  const double *accSC;         // (D+1)^2 Gram matrix of the Schur term, upper tiles
+  const double *HM, *bM;       // may be null
+  const double *wprior;        // cPrior[4] | frame_prior | frame_delta_prior | frame_delta
   const float *cDeltaF;
-  double *x, *Hfinal, *bfinal;                    // out
+  double *x, *Hfinal, *bfinal; // out (Hfinal/bfinal may be null)
   const float *adHostF, *adTargetF;
-  float *xAd;                                     // [nf*nf*8] then xc[4]
-  int *status;                                    // [0] non-finite flag
+  float *xAd;                  // [nf*nf*8] then xc[4]
+  int *status;                 // [0] non-finite flag
 };
 void launch_solve(sosba *h, const SolveArgs &a);
 

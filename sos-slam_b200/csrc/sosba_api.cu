@@ -19,6 +19,7 @@
 size_t solve_smem_bytes(int D);
 void launch_make_xad(sosba *h, const double *d_x, int nf, const float *adHostF, const float *adTargetF, float *xAd);
 void launch_scale_prior(sosba *h, float *priorF, const int *ids, int n, float fac);
+void launch_stitch_raw(sosba *h, const double *accTop2, const double *adHost, const double *adTarget, int nf, int ntables, double *H, double *b);
 
 using sosba_host::BAState;
 using sosba_host::WindowTables;
@@ -50,6 +51,10 @@ struct HostSide {
   double *d_HMtmp = nullptr, *d_bMtmp = nullptr;
   int *d_ids = nullptr; int ids_cap = 0;
   int *d_status = nullptr;
+  double *d_scratch = nullptr, *d_rstats = nullptr, *d_Hfinal = nullptr;
+  double *d_fs = nullptr, *d_cs = nullptr, *d_iter = nullptr;   // device-resident frame / calibration state of the GN loop
+  int *d_cnt = nullptr;
+  size_t scratch_doubles = 0;
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;   // (start, stop) pairs around the linearize kernel
 };
@@ -165,9 +170,11 @@ API int sosba_create(const sosba_config *cfg, int32_t device, sosba_t **out) {
   SOSBA_CUDA(cudaMallocHost((void **)&hs->pin_d, 4096 * sizeof(double)));
   SOSBA_CUDA(cudaMallocHost((void **)&hs->pin_i, 64 * sizeof(int)));
   SOSBA_CUDA(cudaMallocHost((void **)&hs->pin_f, 4096 * sizeof(float)));
+  // linearize statistics, one region so that one memset clears it and one copy reads it back:
+  //   double energy | double pad | int counts[16] | float thOut[4]
   DALLOC(h, h->d_stats, 16);
-  DALLOC(h, h->d_counts, 16);
-  DALLOC(h, h->d_thOut, 4);
+  h->d_counts = (int *)(h->d_stats + 2);
+  h->d_thOut = (float *)(h->d_counts + 16);
   DALLOC(h, h->t_acc, 64);
   DALLOC(h, hs->d_status, 4);
   h->ba = new BA();
@@ -276,8 +283,9 @@ static int ensure_window(sosba *h, int nf) {
   if (nf <= h->nf_alloc) return SOSBA_OK;
   dfree(h, h->d_precalc); dfree(h, h->d_adHostF); dfree(h, h->d_adTargetF); dfree(h, h->d_adHTdeltaF); dfree(h, h->d_frameEnergyTH);
   dfree(h, h->d_adHost); dfree(h, h->d_adTarget); dfree(h, h->d_calib); dfree(h, h->d_wprior); dfree(h, h->d_img0);
-  dfree(h, h->d_accTop); dfree(h, h->d_accSC); dfree(h, h->d_H); dfree(h, h->d_x); dfree(h, h->d_xAd);
+  dfree(h, h->d_x); dfree(h, h->d_xAd);
   HostSide *hs = HS(h);
+  dfree(h, hs->d_scratch); h->d_accTop = h->d_accSC = h->d_H = nullptr;
   dfree(h, hs->d_HMtmp); dfree(h, hs->d_bMtmp);
   const size_t n2 = (size_t)nf * nf;
   const int D = 4 + 8 * nf;
@@ -288,12 +296,22 @@ static int ensure_window(sosba *h, int nf) {
   DALLOC(h, h->d_calib, 16);
   DALLOC(h, h->d_wprior, 4 + 24 * (size_t)nf);
   DALLOC(h, h->d_img0, nf);
-  DALLOC(h, h->d_accTop, 2 * n2 * SOSBA_TOPB);             // A | L
-  DALLOC(h, h->d_accSC, (size_t)(D + 1) * (D + 1));
-  DALLOC(h, h->d_H, 4 * ((size_t)D * D + D));              // A | L | SC | final
+  {  // one scratch region zeroed by a single memset per solve: top tables (A | L), Schur Gram, H parts A | L | SC,
+     // back-substitution sums [4], counters (ints) ; H part 3 (final system) follows and is never cleared
+    const size_t HB = (size_t)D * D + D;
+    hs->scratch_doubles = 2 * n2 * SOSBA_TOPB + (size_t)(D + 1) * (D + 1) + 3 * HB + 4 + 4;
+    DALLOC(h, hs->d_scratch, hs->scratch_doubles + HB);
+    h->d_accTop = hs->d_scratch;
+    h->d_accSC = h->d_accTop + 2 * n2 * SOSBA_TOPB;
+    h->d_H = h->d_accSC + (size_t)(D + 1) * (D + 1);
+    hs->d_rstats = h->d_H + 3 * HB;
+    hs->d_cnt = (int *)(hs->d_rstats + 4);                  // [0] resInA [1] resInL [2] non-finite status
+    hs->d_Hfinal = hs->d_scratch + hs->scratch_doubles;
+  }
   DALLOC(h, h->d_x, D);
   DALLOC(h, h->d_xAd, n2 * 8 + 8);
   DALLOC(h, hs->d_HMtmp, (size_t)D * D); DALLOC(h, hs->d_bMtmp, D);
+  if (!hs->d_fs) { DALLOC(h, hs->d_fs, 16 * SOSBA_FS); DALLOC(h, hs->d_cs, 16); DALLOC(h, hs->d_iter, 8); }
   h->nf_alloc = nf; h->D_alloc = D;
   return SOSBA_OK;
 }
@@ -488,8 +506,7 @@ API int sosba_reset_oob(sosba_t *h) {
 
 // enqueue linearizeAll on the stream (no host sync)
 static void enqueue_linearize(sosba *h, int fix) {
-  cudaMemsetAsync(h->d_stats, 0, sizeof(double) * 1, h->stream);
-  cudaMemsetAsync(h->d_counts, 0, sizeof(int) * 5, h->stream);
+  cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(double) + 5 * sizeof(int), h->stream);
   LinArgs a = lin_args(h);
   HostSide *hs = HS(h);
   if (hs->prof_on) {
@@ -513,12 +530,13 @@ static void enqueue_linearize(sosba *h, int fix) {
 static int read_linearize_out(sosba *h, sosba_linearize_out *out) {
   HostSide *hs = HS(h);
   int rc;
-  if ((rc = down(h, hs->pin_d, h->d_stats, 1)) || (rc = down(h, hs->pin_i, h->d_counts, 5)) || (rc = down(h, hs->pin_f, h->d_thOut, 1))) return rc;
+  if ((rc = down(h, hs->pin_d, h->d_stats, 12))) return rc;   // energy | pad | counts[16] | thOut[4]
   if ((rc = sync(h))) return rc;
   if (out) {
+    const int *ci = (const int *)(hs->pin_d + 2);
     out->energy = hs->pin_d[0];
-    out->new_frame_energy_th = hs->pin_f[0];
-    out->n_in = hs->pin_i[0]; out->n_oob = hs->pin_i[1]; out->n_outlier = hs->pin_i[2]; out->n_removed = hs->pin_i[3];
+    out->new_frame_energy_th = ((const float *)(ci + 16))[0];
+    out->n_in = ci[0]; out->n_oob = ci[1]; out->n_outlier = ci[2]; out->n_removed = ci[3];
     out->reserved0 = 0;
   }
   return SOSBA_OK;
@@ -639,53 +657,54 @@ API int sosba_points_get_acc(sosba_t *h, float *HddA, float *bdA, float *HcdA, f
 }
 
 // ---- a6-a9 --------------------------------------------------------------------------------------
-static inline double *Hpart(sosba *h, int which) { const int D = 4 + 8 * h->nf; return h->d_H + (size_t)which * ((size_t)D * D + D); }
+static inline double *Hpart(sosba *h, int which) {
+  const int D = 4 + 8 * h->nf;
+  if (which == 3) return HS(h)->d_Hfinal;
+  return h->d_H + (size_t)which * ((size_t)D * D + D);
+}
 static inline double *bpart(sosba *h, int which) { const int D = 4 + 8 * h->nf; return Hpart(h, which) + (size_t)D * D; }
 
 int sosba_allreduce_acc(sosba *h);  // comm.cu: no-op without a communicator
 
-// accumulateAF_MT + accumulateLF_MT + accumulateSCF_MT on the stream; results stay in d_H parts 0..2, counts[5..6]
-static int enqueue_accumulate(sosba *h) {
+static SCArgs sc_args(sosba *h, int mode, const int *plist, int n_plist, int shift) {
+  SCArgs s;
+  s.P = h->P; s.nf = h->nf; s.D = 4 + 8 * h->nf; s.plist = plist; s.n_plist = n_plist; s.mode = mode; s.shiftPriorToZero = shift;
+  s.res_begin = h->p_res_begin; s.r_target = h->r_target; s.p_host = h->p_host;
+  s.r_is_lin = h->r_is_lin; s.r_is_active = h->r_is_active; s.r_dropped = h->r_dropped;
+  s.rec = h->r_rec; s.HddA = h->p_HddA; s.bdA = h->p_bdA; s.HcdA = h->p_HcdA; s.HddL = h->p_HddL; s.bdL = h->p_bdL; s.HcdL = h->p_HcdL;
+  s.priorF = h->p_priorF; s.deltaF = h->p_deltaF; s.HdiF = h->p_HdiF; s.bdSumF = h->p_bdSumF; s.idepth_hessian = h->p_idepth_hessian;
+  s.maxRelBaseline = h->p_maxRelBaseline; s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.accSC = h->d_accSC;
+  return s;
+}
+
+// the block tables of accumulateAF_MT / accumulateLF_MT / accumulateSCF_MT (EnergyFunctional.cpp:197-254):
+// one memset, top blocks (A, and L when linearised residuals exist), per-point sums + Schur Gram, all-reduce
+static int enqueue_blocks(sosba *h) {
   HostSide *hs = HS(h);
-  const int nf = h->nf, D = 4 + 8 * nf;
-  const size_t n2 = (size_t)nf * nf, HB = (size_t)D * D + D;
-  cudaMemsetAsync(h->d_accTop, 0, sizeof(double) * 2 * n2 * SOSBA_TOPB, h->stream);
-  cudaMemsetAsync(h->d_accSC, 0, sizeof(double) * (size_t)(D + 1) * (D + 1), h->stream);
-  cudaMemsetAsync(h->d_H, 0, sizeof(double) * 3 * HB, h->stream);
-  cudaMemsetAsync(h->d_counts + 5, 0, sizeof(int) * 2, h->stream);
-  LinArgs la = lin_args(h);
+  const int nf = h->nf;
+  const size_t n2 = (size_t)nf * nf;
+  cudaMemsetAsync(hs->d_scratch, 0, sizeof(double) * hs->scratch_doubles, h->stream);
   AccArgs a;
   a.R = h->R; a.P = h->P; a.nf = nf; a.n_list = h->R; a.list = h->r_by_block; a.mode = 0;
   a.r_point = h->r_point; a.r_target = h->r_target; a.r_host = h->r_host;
   a.r_is_lin = h->r_is_lin; a.r_is_active = h->r_is_active; a.r_dropped = h->r_dropped;
-  a.rec = h->r_rec; a.accTop = h->d_accTop; a.counts = h->d_counts;
+  a.rec = h->r_rec; a.accTop = h->d_accTop; a.n_acc = hs->d_cnt;
   launch_top_accumulate(h, a);
-  PointArgs pa;
-  pa.P = h->P; pa.nf = nf; pa.D = D; pa.plist = nullptr; pa.n_plist = 0; pa.mode = 0;
-  pa.res_begin = h->p_res_begin; pa.r_target = h->r_target; pa.p_host = h->p_host;
-  pa.r_is_lin = h->r_is_lin; pa.r_is_active = h->r_is_active; pa.r_dropped = h->r_dropped; pa.rec = h->r_rec;
-  pa.HddA = h->p_HddA; pa.bdA = h->p_bdA; pa.HcdA = h->p_HcdA; pa.HddL = h->p_HddL; pa.bdL = h->p_bdL; pa.HcdL = h->p_HcdL;
-  launch_point_sums(h, pa);
   if (hs->n_lin > 0) {
-    launch_prep_records(h, la, 1, nullptr, h->R);
+    launch_prep_records(h, lin_args(h), 1, nullptr, h->R);
     AccArgs l = a;
-    l.mode = 1; l.accTop = h->d_accTop + n2 * SOSBA_TOPB; l.counts = h->d_counts + 1;  // counts[6]
+    l.mode = 1; l.accTop = h->d_accTop + n2 * SOSBA_TOPB; l.n_acc = hs->d_cnt + 1;
     launch_top_accumulate(h, l);
-    pa.mode = 1;
-    launch_point_sums(h, pa);
-  } else {
-    cudaMemsetAsync(h->p_HddL, 0, sizeof(float) * h->P, h->stream);
-    cudaMemsetAsync(h->p_bdL, 0, sizeof(float) * h->P, h->stream);
-    cudaMemsetAsync(h->p_HcdL, 0, sizeof(float) * 4 * h->P, h->stream);
   }
-  SCArgs s;
-  s.P = h->P; s.nf = nf; s.D = D; s.plist = nullptr; s.n_plist = 0; s.shiftPriorToZero = 1;
-  s.res_begin = h->p_res_begin; s.r_target = h->r_target; s.p_host = h->p_host; s.r_is_active = h->r_is_active; s.r_dropped = h->r_dropped;
-  s.rec = h->r_rec; s.HddA = h->p_HddA; s.bdA = h->p_bdA; s.HcdA = h->p_HcdA; s.HddL = h->p_HddL; s.bdL = h->p_bdL; s.HcdL = h->p_HcdL;
-  s.priorF = h->p_priorF; s.deltaF = h->p_deltaF; s.HdiF = h->p_HdiF; s.bdSumF = h->p_bdSumF; s.idepth_hessian = h->p_idepth_hessian;
-  s.maxRelBaseline = h->p_maxRelBaseline; s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.accSC = h->d_accSC;
-  launch_sc_accumulate(h, s);
-  int rc = sosba_allreduce_acc(h);   // points are sharded across ranks: sum the block tables (identical on every rank afterwards)
+  launch_point_sc(h, sc_args(h, 0, nullptr, 0, 1));
+  return sosba_allreduce_acc(h);   // points are sharded across ranks: sum the block tables (identical on every rank afterwards)
+}
+
+// API path: the three stitched systems separately (d_H parts 0..2)
+static int enqueue_accumulate(sosba *h) {
+  const int nf = h->nf;
+  const size_t n2 = (size_t)nf * nf;
+  int rc = enqueue_blocks(h);
   if (rc) return rc;
   launch_stitch_top(h, h->d_accTop, h->d_adHost, h->d_adTarget, nf, Hpart(h, 0), bpart(h, 0), 0, h->d_wprior, h->d_calib + 6);
   launch_stitch_top(h, h->d_accTop + n2 * SOSBA_TOPB, h->d_adHost, h->d_adTarget, nf, Hpart(h, 1), bpart(h, 1), 1, h->d_wprior, h->d_calib + 6);
@@ -703,7 +722,7 @@ API int sosba_accumulate(sosba_t *h, double *HA, double *bA, double *HL, double 
   HostSide *hs = HS(h);
   if ((rc = fetch(h, HA, Hpart(h, 0), (size_t)D * D)) || (rc = fetch(h, bA, bpart(h, 0), D)) || (rc = fetch(h, HL, Hpart(h, 1), (size_t)D * D)) ||
       (rc = fetch(h, bL, bpart(h, 1), D)) || (rc = fetch(h, Hsc, Hpart(h, 2), (size_t)D * D)) || (rc = fetch(h, bsc, bpart(h, 2), D)) ||
-      (rc = down(h, hs->pin_i, h->d_counts + 5, 2)))
+      (rc = down(h, hs->pin_i, hs->d_cnt, 2)))
     return rc;
   if ((rc = sync(h))) return rc;
   if (resInA) *resInA = hs->pin_i[0];
@@ -718,23 +737,22 @@ static ResubArgs resub_args(sosba *h, int do_step) {
   r.r_is_active = h->r_is_active; r.r_dropped = h->r_dropped; r.rec = h->r_rec; r.xAd = h->d_xAd;
   r.HcdA = h->p_HcdA; r.HcdL = h->p_HcdL; r.bdSumF = h->p_bdSumF; r.HdiF = h->p_HdiF; r.step = h->p_step;
   r.do_step = do_step; r.idepth = h->p_idepth; r.idepth_zero = h->p_idepth_zero; r.idepth_backup = h->p_idepth_backup; r.deltaF = h->p_deltaF;
-  r.stats = h->d_stats;
+  r.stats = HS(h)->d_rstats - 1;   // the kernel writes stats[1..3]
   return r;
 }
 
 static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int do_step) {
   HostSide *hs = HS(h);
   const int nf = h->nf, D = 4 + 8 * nf;
-  int rc = enqueue_accumulate(h);
+  int rc = enqueue_blocks(h);
   if (rc) return rc;
-  cudaMemsetAsync(hs->d_status, 0, sizeof(int), h->stream);
-  cudaMemsetAsync(h->d_stats + 1, 0, sizeof(double) * 3, h->stream);
+  launch_stitch_raw(h, h->d_accTop, h->d_adHost, h->d_adTarget, nf, hs->n_lin > 0 ? 2 : 1, Hpart(h, 0), bpart(h, 0));
   SolveArgs s;
   s.nf = nf; s.D = D;
-  s.HA = Hpart(h, 0); s.bA = bpart(h, 0); s.HL = Hpart(h, 1); s.bL = bpart(h, 1); s.Hsc = Hpart(h, 2); s.bsc = bpart(h, 2);
+  s.Htop = Hpart(h, 0); s.btop = bpart(h, 0); s.accSC = h->d_accSC;
   s.HM = d_HM; s.bM = d_bM; s.wprior = h->d_wprior; s.cDeltaF = h->d_calib + 6;
   s.x = h->d_x; s.Hfinal = Hpart(h, 3); s.bfinal = bpart(h, 3);
-  s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.xAd = h->d_xAd; s.status = hs->d_status;
+  s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.xAd = h->d_xAd; s.status = hs->d_cnt + 2;
   launch_solve(h, s);
   launch_resubstitute(h, resub_args(h, do_step));
   SOSBA_CUDA(cudaGetLastError());
@@ -754,7 +772,7 @@ API int sosba_solve_system(sosba_t *h, const double *HM, const double *bM, doubl
   }
   if ((rc = enqueue_solve(h, prior ? hs->d_HMtmp : nullptr, prior ? hs->d_bMtmp : nullptr, 0))) return rc;
   if ((rc = fetch(h, x, h->d_x, D)) || (rc = fetch(h, Hf, Hpart(h, 3), (size_t)D * D)) || (rc = fetch(h, bf, bpart(h, 3), D)) ||
-      (rc = down(h, hs->pin_i, hs->d_status, 1)))
+      (rc = down(h, hs->pin_i, hs->d_cnt + 2, 1)))
     return rc;
   if ((rc = sync(h))) return rc;
   if (hs->pin_i[0]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
@@ -781,7 +799,7 @@ API int sosba_marginalize_points(sosba_t *h, const int32_t *ids, int32_t n, doub
   if (n < 0 || (n > 0 && !ids) || !H || !b || h->nf <= 0) return SOSBA_E_ARG;
   HostSide *hs = HS(h);
   const int nf = h->nf, D = 4 + 8 * nf;
-  const size_t n2 = (size_t)nf * nf, HB = (size_t)D * D + D;
+  const size_t HB = (size_t)D * D + D;
   // residual list of the chosen points, ordered by block
   std::vector<int> rl;
   for (int i = 0; i < n; i++) {
@@ -797,37 +815,22 @@ API int sosba_marginalize_points(sosba_t *h, const int32_t *ids, int32_t n, doub
   if (rc) return rc;
   const int *d_pl = hs->d_ids, *d_rl = hs->d_ids + n;
   launch_scale_prior(h, h->p_priorF, d_pl, n, h->cfg.idepth_fix_prior_marg_fac);  // EnergyFunctional.cpp:901
-  cudaMemsetAsync(h->d_accTop, 0, sizeof(double) * n2 * SOSBA_TOPB, h->stream);
-  cudaMemsetAsync(h->d_accSC, 0, sizeof(double) * (size_t)(D + 1) * (D + 1), h->stream);
-  cudaMemsetAsync(h->d_H, 0, sizeof(double) * 3 * HB, h->stream);
-  cudaMemsetAsync(h->d_counts + 5, 0, sizeof(int) * 2, h->stream);
+  cudaMemsetAsync(hs->d_scratch, 0, sizeof(double) * hs->scratch_doubles, h->stream);
   LinArgs la = lin_args(h);
   launch_prep_records(h, la, 2, d_rl, (int)rl.size());
   AccArgs a;
   a.R = h->R; a.P = h->P; a.nf = nf; a.n_list = (int)rl.size(); a.list = d_rl; a.mode = 2;
   a.r_point = h->r_point; a.r_target = h->r_target; a.r_host = h->r_host;
   a.r_is_lin = h->r_is_lin; a.r_is_active = h->r_is_active; a.r_dropped = h->r_dropped;
-  a.rec = h->r_rec; a.accTop = h->d_accTop; a.counts = h->d_counts;
+  a.rec = h->r_rec; a.accTop = h->d_accTop; a.n_acc = hs->d_cnt;
   launch_top_accumulate(h, a);
-  PointArgs pa;
-  pa.P = h->P; pa.nf = nf; pa.D = D; pa.plist = d_pl; pa.n_plist = n; pa.mode = 2;
-  pa.res_begin = h->p_res_begin; pa.r_target = h->r_target; pa.p_host = h->p_host;
-  pa.r_is_lin = h->r_is_lin; pa.r_is_active = h->r_is_active; pa.r_dropped = h->r_dropped; pa.rec = h->r_rec;
-  pa.HddA = h->p_HddA; pa.bdA = h->p_bdA; pa.HcdA = h->p_HcdA; pa.HddL = h->p_HddL; pa.bdL = h->p_bdL; pa.HcdL = h->p_HcdL;
-  launch_point_sums(h, pa);
-  SCArgs s;
-  s.P = h->P; s.nf = nf; s.D = D; s.plist = d_pl; s.n_plist = n; s.shiftPriorToZero = 0;
-  s.res_begin = h->p_res_begin; s.r_target = h->r_target; s.p_host = h->p_host; s.r_is_active = h->r_is_active; s.r_dropped = h->r_dropped;
-  s.rec = h->r_rec; s.HddA = h->p_HddA; s.bdA = h->p_bdA; s.HcdA = h->p_HcdA; s.HddL = h->p_HddL; s.bdL = h->p_bdL; s.HcdL = h->p_HcdL;
-  s.priorF = h->p_priorF; s.deltaF = h->p_deltaF; s.HdiF = h->p_HdiF; s.bdSumF = h->p_bdSumF; s.idepth_hessian = h->p_idepth_hessian;
-  s.maxRelBaseline = h->p_maxRelBaseline; s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.accSC = h->d_accSC;
-  launch_sc_accumulate(h, s);
+  launch_point_sc(h, sc_args(h, 2, d_pl, n, 0));
   if ((rc = sosba_allreduce_acc(h))) return rc;
   launch_stitch_top(h, h->d_accTop, h->d_adHost, h->d_adTarget, nf, Hpart(h, 0), bpart(h, 0), 0, h->d_wprior, h->d_calib + 6);
   launch_finalize_sc(h, h->d_accSC, nf, Hpart(h, 2), bpart(h, 2));
   SOSBA_CUDA(cudaGetLastError());
   std::vector<double> M(HB), Msc(HB);
-  if ((rc = down(h, M.data(), Hpart(h, 0), HB)) || (rc = down(h, Msc.data(), Hpart(h, 2), HB)) || (rc = down(h, hs->pin_i, h->d_counts + 5, 1))) return rc;
+  if ((rc = down(h, M.data(), Hpart(h, 0), HB)) || (rc = down(h, Msc.data(), Hpart(h, 2), HB)) || (rc = down(h, hs->pin_i, hs->d_cnt, 1))) return rc;
   if ((rc = sync(h))) return rc;
   for (size_t i = 0; i < (size_t)D * D; i++) H[i] = M[i] - Msc[i];
   for (int i = 0; i < D; i++) b[i] = M[(size_t)D * D + i] - Msc[(size_t)D * D + i];
@@ -1012,6 +1015,8 @@ static int upload_tables(sosba *h, BA *ba, bool full) {
   return window_apply(h, &win, full);
 }
 
+static int upload_frame_state(sosba *h);
+
 API int sosba_ba_upload(sosba_t *h, const sosba_ba_problem *prob) {
   CHECK_H(h);
   if (!prob || prob->nf <= 0 || !prob->frames) return SOSBA_E_ARG;
@@ -1036,54 +1041,108 @@ API int sosba_ba_upload(sosba_t *h, const sosba_ba_problem *prob) {
     if ((rc = sync(h))) return rc;
   }
   ba->iterations_done = 0;
+  return upload_frame_state(h);
+}
+
+// host mirror -> device frame / calibration state
+static int upload_frame_state(sosba *h) {
+  BA *ba = h->ba;
+  HostSide *hs = HS(h);
+  const int nf = (int)ba->st.frames.size();
+  int rc = sync(h);
+  if (rc) return rc;
+  double *p = hs->pin_d;   // 4096 doubles: nf*64 + 16 fits
+  memset(p, 0, sizeof(double) * (nf * SOSBA_FS + 16));
+  for (int f = 0; f < nf; f++) {
+    const sosba_host::FrameH &F = ba->st.frames[f];
+    double *q = p + SOSBA_FS * f;
+    sosba_math::rigid_to34(F.evalPT, q);
+    for (int i = 0; i < 10; i++) { q[12 + i] = F.state[i]; q[22 + i] = F.state_zero[i]; q[32 + i] = F.state_backup[i]; q[42 + i] = F.step[i]; }
+    q[52] = F.ab_exposure;
+  }
+  double *c = p + nf * SOSBA_FS;
+  for (int i = 0; i < 4; i++) { c[i] = ba->st.calib.value[i]; c[4 + i] = ba->st.calib.value_zero[i]; c[8 + i] = ba->st.calib.value_backup[i]; c[12 + i] = ba->st.calib.step[i]; }
+  if ((rc = up(h, hs->d_fs, p, (size_t)nf * SOSBA_FS)) || (rc = up(h, hs->d_cs, c, 16))) return rc;
+  return sync(h);
+}
+
+// device frame / calibration state -> host mirror
+static int download_frame_state(sosba *h) {
+  BA *ba = h->ba;
+  HostSide *hs = HS(h);
+  const int nf = (int)ba->st.frames.size();
+  int rc;
+  double *p = hs->pin_d;
+  if ((rc = down(h, p, hs->d_fs, (size_t)nf * SOSBA_FS)) || (rc = down(h, p + nf * SOSBA_FS, hs->d_cs, 16)) || (rc = down(h, hs->pin_f, h->d_frameEnergyTH, nf))) return rc;
+  if ((rc = sync(h))) return rc;
+  for (int f = 0; f < nf; f++) {
+    sosba_host::FrameH &F = ba->st.frames[f];
+    const double *q = p + SOSBA_FS * f;
+    for (int i = 0; i < 10; i++) { F.state_backup[i] = q[32 + i]; F.step[i] = q[42 + i]; }
+    F.setState(q + 12);
+    F.frameEnergyTH = hs->pin_f[f];
+  }
+  const double *c = p + nf * SOSBA_FS;
+  for (int i = 0; i < 4; i++) { ba->st.calib.value_backup[i] = c[8 + i]; ba->st.calib.step[i] = c[12 + i]; }
+  ba->st.calib.setValue(c);
   return SOSBA_OK;
 }
 
-// one loop body: backupState, solveSystem, doStepFromBackup, linearizeAll(false), applyRes.  Returns canbreak.
-static int ba_iterate_once(sosba *h, bool *canbreak, sosba_linearize_out *lo) {
+// one loop body of FullSystem::optimize (FullSystemOptimize.cpp:358-413), enqueued on the stream with no host
+// round trip: backupState + solveSystemF + doStepFromBackup (points in k_resubstitute, frames/calib/precalc in
+// k_frame_step) + linearizeAll(false) + applyRes
+static int enqueue_iteration(sosba *h) {
   BA *ba = h->ba;
   HostSide *hs = HS(h);
-  const int nf = h->nf, D = 4 + 8 * nf;
-  int rc;
-  ba->st.backup();
-  if ((rc = enqueue_solve(h, ba->have_HM ? hs->d_HMtmp : nullptr, ba->have_HM ? hs->d_bMtmp : nullptr, 1))) return rc;
-  if ((rc = down(h, hs->pin_d, h->d_x, D)) || (rc = down(h, hs->pin_d + 256, h->d_stats + 1, 3)) || (rc = down(h, hs->pin_i, hs->d_status, 1))) return rc;
-  if ((rc = sync(h))) return rc;
-  if (hs->pin_i[0]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
-  float sums[4];
-  ba->st.step_frames(hs->pin_d, 1.0f, sums);
-  ba->st.make_precalc(ba->wt);
-  for (int i = 0; i < nf; i++) ba->wt.frameEnergyTH[i] = ba->st.frames[i].frameEnergyTH;
-  if ((rc = upload_tables(h, ba, false))) return rc;
+  int rc = enqueue_solve(h, ba->have_HM ? hs->d_HMtmp : nullptr, ba->have_HM ? hs->d_bMtmp : nullptr, 1);
+  if (rc) return rc;
+  StepArgs st;
+  st.nf = h->nf; st.stepfac = 1.0f; st.x = h->d_x; st.fs = hs->d_fs; st.cs = hs->d_cs;
+  st.precalc = h->d_precalc; st.adHTdeltaF = h->d_adHTdeltaF; st.calib = h->d_calib;
+  st.adHostF = h->d_adHostF; st.adTargetF = h->d_adTargetF; st.wprior = h->d_wprior; st.iter = hs->d_iter;
+  launch_frame_step(h, st);
   enqueue_linearize(h, 0);
   launch_apply_res(h, lin_args(h), 0);
   SOSBA_CUDA(cudaGetLastError());
-  sosba_linearize_out tmp;
-  if ((rc = read_linearize_out(h, lo ? lo : &tmp))) return rc;
-  ba->st.frames.back().frameEnergyTH = (lo ? lo : &tmp)->new_frame_energy_th;
+  ba->iterations_done++;
+  return SOSBA_OK;
+}
+
+// read back what the host needs to decide `canbreak` (doStepFromBackup's return value) after an iteration
+static int read_iteration(sosba *h, bool *canbreak, sosba_linearize_out *lo) {
+  HostSide *hs = HS(h);
+  int rc;
+  if ((rc = down(h, hs->pin_d + 256, hs->d_rstats, 3)) || (rc = down(h, hs->pin_d + 264, hs->d_iter, 4)) || (rc = down(h, hs->pin_i, hs->d_cnt + 2, 1))) return rc;
+  if ((rc = read_linearize_out(h, lo))) return rc;   // syncs
+  if (hs->pin_i[0]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
+  const float sumA = (float)hs->pin_d[264], sumB = (float)hs->pin_d[265], sumT = (float)hs->pin_d[266], sumR = (float)hs->pin_d[267];
   const float numID = (float)hs->pin_d[258];
   const float sumNID = numID > 0 ? (float)hs->pin_d[257] / numID : 0.f;
   const float th = h->cfg.th_opt_iterations;
   if (canbreak)
-    *canbreak = sqrtf(sums[0]) < 0.0005 * th && sqrtf(sums[1]) < 0.00005 * th && sqrtf(sums[3]) < 0.00005 * th && sqrtf(sums[2]) * sumNID < 0.00005 * th;
-  ba->iterations_done++;
+    *canbreak = sqrtf(sumA) < 0.0005 * th && sqrtf(sumB) < 0.00005 * th && sqrtf(sumR) < 0.00005 * th && sqrtf(sumT) * sumNID < 0.00005 * th;
   return SOSBA_OK;
 }
 
 API int sosba_ba_iterate(sosba_t *h, int32_t n, int32_t *n_res) {
   CHECK_H(h);
   if (!h->ba->st.loaded) { sosba_set_error("ba_upload first"); return SOSBA_E_STATE; }
-  for (int i = 0; i < n; i++) {
-    int rc = ba_iterate_once(h, nullptr, nullptr);
-    if (rc) return rc;
-  }
-  if (n_res) *n_res = h->R - HS(h)->n_lin;
+  HostSide *hs = HS(h);
+  int rc;
+  for (int i = 0; i < n; i++)
+    if ((rc = enqueue_iteration(h))) return rc;
+  if ((rc = down(h, hs->pin_i, hs->d_cnt + 2, 1))) return rc;
+  if ((rc = sync(h))) return rc;
+  if (hs->pin_i[0]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
+  if (n_res) *n_res = h->R - hs->n_lin;
   return SOSBA_OK;
 }
 
 API int sosba_ba_download(sosba_t *h, sosba_ba_problem *prob) {
   CHECK_H(h);
   if (!prob || !h->ba->st.loaded) return SOSBA_E_STATE;
+  int rc0 = download_frame_state(h);
+  if (rc0) return rc0;
   h->ba->st.store(prob);
   if (prob->idepth_out) {
     int rc = down(h, prob->idepth_out, h->p_idepth, h->P);
@@ -1111,29 +1170,31 @@ API int sosba_ba_optimize(sosba_t *h, int32_t mnumOptIts, sosba_optimize_out *ou
   launch_apply_res(h, lin_args(h), 0);
   if ((rc = read_linearize_out(h, &lo))) return rc;
   out->reserved0 = lo.n_in + lo.n_oob + lo.n_outlier;   // residuals linearised per pass (bench bookkeeping)
-  ba->st.frames.back().frameEnergyTH = lo.new_frame_energy_th;
   out->energy_initial = lo.energy;
   int it = 0;
   for (int iteration = 0; iteration < mnumOptIts; iteration++) {
     bool canbreak = false;
-    if ((rc = ba_iterate_once(h, &canbreak, &lo))) return rc;
+    if ((rc = enqueue_iteration(h))) return rc;
+    if ((rc = read_iteration(h, &canbreak, &lo))) return rc;
     it++;
     if (canbreak && iteration >= h->cfg.min_opt_iterations) break;
   }
   out->iterations = it;
   // new evaluation point for the newest frame (FullSystemOptimize.cpp:415-423)
+  if ((rc = download_frame_state(h))) return rc;
   sosba_host::FrameH &nf_ = ba->st.frames.back();
   double newStateZero[10] = {0, 0, 0, 0, 0, 0, nf_.state[6], nf_.state[7], 0, 0};
   nf_.setEvalPT(nf_.camToWorld, newStateZero);
   ba->st.make_adjoints(h->cfg, ba->wt);
   ba->st.make_precalc(ba->wt);
   if ((rc = upload_tables(h, ba, true))) return rc;
+  if ((rc = upload_frame_state(h))) return rc;
   enqueue_linearize(h, 1);
   if ((rc = read_linearize_out(h, &lo))) return rc;
   nf_.frameEnergyTH = lo.new_frame_energy_th;
   out->energy_final = lo.energy;
   out->n_removed = lo.n_removed;
-  if ((rc = down(h, hs->pin_i, h->d_counts + 5, 1)) || (rc = down(h, hs->pin_d, h->d_x, 4 + 8 * nf))) return rc;
+  if ((rc = down(h, hs->pin_i, hs->d_cnt, 1)) || (rc = down(h, hs->pin_d, h->d_x, 4 + 8 * nf))) return rc;
   if ((rc = sync(h))) return rc;
   out->res_in_a = hs->pin_i[0];
   out->rmse = sqrtf((float)(lo.energy / (SOSBA_PATTERN * out->res_in_a)));

@@ -595,13 +595,17 @@ __device__ __forceinline__ void d_mul33f(const float *A, const float *B, float *
 
 __global__ void __launch_bounds__(256) k_frame_step(StepArgs a) {
   using namespace sosba_math;
+  __shared__ double s_fs[16 * SOSBA_FS];
   __shared__ Rigid s_c2w[16], s_w2c[16];
   __shared__ double s_scaled[16][2];
   __shared__ float s_K[4];
   const int nf = a.nf, tid = threadIdx.x;
   const double SC_T = 0.5, SC_R = 1.0, SC_A = 10.0, SC_B = 1000.0, SC_F = 50.0, SC_C = 50.0;
+  for (int e = tid; e < nf * SOSBA_FS; e += blockDim.x) s_fs[e] = a.fs[e];
+  __syncthreads();
   if (tid < nf) {
-    double *F = a.fs + SOSBA_FS * tid;
+    double *F = s_fs + SOSBA_FS * tid;
+    double *G = a.fs + SOSBA_FS * tid;
     double *state = F + 12, *backup = F + 32, *step = F + 42;
     for (int i = 0; i < 8; i++) step[i] = -a.x[4 + 8 * tid + i];
     step[8] = step[9] = 0.0;
@@ -609,6 +613,7 @@ __global__ void __launch_bounds__(256) k_frame_step(StepArgs a) {
     for (int i = 0; i < 10; i++) {
       backup[i] = state[i];
       state[i] = backup[i] + (double)a.stepfac * step[i];
+      G[12 + i] = state[i]; G[32 + i] = backup[i]; G[42 + i] = step[i];
     }
     for (int i = 0; i < 3; i++) scaled[i] = SC_T * state[i];
     for (int i = 3; i < 6; i++) scaled[i] = SC_R * state[i];
@@ -639,10 +644,10 @@ __global__ void __launch_bounds__(256) k_frame_step(StepArgs a) {
     a.calib[5] = 1.0f / sf[1];
   }
   __syncthreads();
-  if (tid == 0) {  // step norms of doStepFromBackup, float accumulation in frame order
+  if (tid == 64) {  // step norms of doStepFromBackup, float accumulation in frame order
     float sumA = 0, sumB = 0, sumT = 0, sumR = 0;
     for (int f = 0; f < nf; f++) {
-      const double *st = a.fs + SOSBA_FS * f + 42;
+      const double *st = s_fs + SOSBA_FS * f + 42;
       sumA += st[6] * st[6];
       sumB += st[7] * st[7];
       sumT += st[0] * st[0] + st[1] * st[1] + st[2] * st[2];
@@ -655,36 +660,50 @@ __global__ void __launch_bounds__(256) k_frame_step(StepArgs a) {
   const float Ki[9] = {1.0f / fx, 0, -cx / fx, 0, 1.0f / fy, -cy / fy, 0, 0, 1};
   for (int e = tid; e < nf * nf; e += blockDim.x) {
     const int h = e / nf, t = e % nf;
-    const double *Fh = a.fs + SOSBA_FS * h, *Ft = a.fs + SOSBA_FS * t;
-    float *p = a.precalc + (size_t)e * SOSBA_PRECALC_FLOATS;
+    const double *Fh = s_fs + SOSBA_FS * h, *Ft = s_fs + SOSBA_FS * t;
+    // setDeltaF first (its 32 float4 adjoint loads are in flight while the fp64 rigid algebra runs)
+    const int idx = h + t * nf;
+    const float4 *AhF = (const float4 *)(a.adHostF + 64 * (size_t)idx), *AtF = (const float4 *)(a.adTargetF + 64 * (size_t)idx);
+    float4 rh[16], rt[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) { rh[q] = __ldg(AhF + q); rt[q] = __ldg(AtF + q); }
+    float pre[SOSBA_PRECALC_FLOATS];
     const Rigid l0 = rigid_mul(rigid_inverse(rigid_from34(Ft)), rigid_from34(Fh));
-    for (int i = 0; i < 9; i++) p[SOSBA_PC_RTLL0 + i] = (float)l0.R[i];
-    for (int i = 0; i < 3; i++) p[SOSBA_PC_TTLL0 + i] = (float)l0.t[i];
+    for (int i = 0; i < 9; i++) pre[SOSBA_PC_RTLL0 + i] = (float)l0.R[i];
+    for (int i = 0; i < 3; i++) pre[SOSBA_PC_TTLL0 + i] = (float)l0.t[i];
     const Rigid l = rigid_mul(s_w2c[t], s_c2w[h]);
-    float R[9], tt[3], KR[9], KRKi[9];
+    float R[9], tt[3], KR[9];
     for (int i = 0; i < 9; i++) R[i] = (float)l.R[i];
     for (int i = 0; i < 3; i++) tt[i] = (float)l.t[i];
     d_mul33f(K, R, KR);
-    d_mul33f(KR, Ki, KRKi);
-    for (int i = 0; i < 9; i++) p[SOSBA_PC_KRKI + i] = KRKi[i];
-    for (int i = 0; i < 3; i++) p[SOSBA_PC_KT + i] = (K[3 * i] * tt[0] + K[3 * i + 1] * tt[1]) + K[3 * i + 2] * tt[2];
+    d_mul33f(KR, Ki, pre + SOSBA_PC_KRKI);
+    for (int i = 0; i < 3; i++) pre[SOSBA_PC_KT + i] = (K[3 * i] * tt[0] + K[3 * i + 1] * tt[1]) + K[3 * i + 2] * tt[2];
     float expF = (float)Fh[52], expT = (float)Ft[52];     // AffLight::fromToVecExposure (NumType.h:157-168)
     if (expF == 0 || expT == 0) expT = expF = 1;
     const double aa = exp(s_scaled[t][0] - s_scaled[h][0]) * expT / expF;
     const double bbv = s_scaled[t][1] - aa * s_scaled[h][1];
-    p[SOSBA_PC_AFF] = (float)aa;
-    p[SOSBA_PC_AFF + 1] = (float)bbv;
-    p[SOSBA_PC_B0] = (float)(Fh[22 + 7] * SC_B);
-    p[SOSBA_PC_DIST] = (float)sqrt(l.t[0] * l.t[0] + l.t[1] * l.t[1] + l.t[2] * l.t[2]);
-    // setDeltaF: adHTdeltaF[h + t*nf] = delta_h^T adHostF + delta_t^T adTargetF
-    const int idx = h + t * nf;
-    float dh[8], dt[8];
-    for (int i = 0; i < 8; i++) { dh[i] = (float)(Fh[12 + i] - Fh[22 + i]); dt[i] = (float)(Ft[12 + i] - Ft[22 + i]); }
-    for (int c = 0; c < 8; c++) {
-      float sh = 0, st = 0;
-      for (int k = 0; k < 8; k++) { sh += dh[k] * a.adHostF[64 * (size_t)idx + 8 * k + c]; st += dt[k] * a.adTargetF[64 * (size_t)idx + 8 * k + c]; }
-      a.adHTdeltaF[8 * (size_t)idx + c] = sh + st;
+    pre[SOSBA_PC_AFF] = (float)aa;
+    pre[SOSBA_PC_AFF + 1] = (float)bbv;
+    pre[SOSBA_PC_B0] = (float)(Fh[22 + 7] * SC_B);
+    pre[SOSBA_PC_DIST] = (float)sqrt(l.t[0] * l.t[0] + l.t[1] * l.t[1] + l.t[2] * l.t[2]);
+    pre[28] = pre[29] = pre[30] = pre[31] = 0.f;
+    float4 *p4 = (float4 *)(a.precalc + (size_t)e * SOSBA_PRECALC_FLOATS);
+#pragma unroll
+    for (int q = 0; q < 8; q++) p4[q] = make_float4(pre[4 * q], pre[4 * q + 1], pre[4 * q + 2], pre[4 * q + 3]);
+    // adHTdeltaF[h + t*nf] = delta_h^T adHostF + delta_t^T adTargetF, summed over k in order
+    float sh[8] = {0, 0, 0, 0, 0, 0, 0, 0}, st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float dh = (float)(Fh[12 + k] - Fh[22 + k]), dt = (float)(Ft[12 + k] - Ft[22 + k]);
+      const float4 h0 = rh[2 * k], h1 = rh[2 * k + 1], t0 = rt[2 * k], t1 = rt[2 * k + 1];
+      sh[0] += dh * h0.x; sh[1] += dh * h0.y; sh[2] += dh * h0.z; sh[3] += dh * h0.w;
+      sh[4] += dh * h1.x; sh[5] += dh * h1.y; sh[6] += dh * h1.z; sh[7] += dh * h1.w;
+      st[0] += dt * t0.x; st[1] += dt * t0.y; st[2] += dt * t0.z; st[3] += dt * t0.w;
+      st[4] += dt * t1.x; st[5] += dt * t1.y; st[6] += dt * t1.z; st[7] += dt * t1.w;
     }
+    float4 *o4 = (float4 *)(a.adHTdeltaF + 8 * (size_t)idx);
+    o4[0] = make_float4(sh[0] + st[0], sh[1] + st[1], sh[2] + st[2], sh[3] + st[3]);
+    o4[1] = make_float4(sh[4] + st[4], sh[5] + st[5], sh[6] + st[6], sh[7] + st[7]);
   }
 }
 

@@ -125,6 +125,7 @@ struct SolveArgs {
   const float *adHostF, *adTargetF;
   float *xAd;                  // [nf*nf*8] then xc[4]
   int *status;                 // [0] non-finite flag
+  long long *dbg;              // optional: clock64() at the phase boundaries (SOSBA_SOLVE_DEBUG)
 };
 void launch_solve(sosba *h, const SolveArgs &a);
 

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -741,7 +742,7 @@ static ResubArgs resub_args(sosba *h, int do_step) {
   return r;
 }
 
-static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int do_step) {
+static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int do_step, bool want_final = false) {
   HostSide *hs = HS(h);
   const int nf = h->nf, D = 4 + 8 * nf;
   int rc = enqueue_blocks(h);
@@ -751,8 +752,21 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
   s.nf = nf; s.D = D;
   s.Htop = Hpart(h, 0); s.btop = bpart(h, 0); s.accSC = h->d_accSC;
   s.HM = d_HM; s.bM = d_bM; s.wprior = h->d_wprior; s.cDeltaF = h->d_calib + 6;
-  s.x = h->d_x; s.Hfinal = Hpart(h, 3); s.bfinal = bpart(h, 3);
+  s.x = h->d_x; s.Hfinal = want_final ? Hpart(h, 3) : nullptr; s.bfinal = want_final ? bpart(h, 3) : nullptr;
   s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.xAd = h->d_xAd; s.status = hs->d_cnt + 2;
+  s.dbg = nullptr;
+  if (getenv("SOSBA_SOLVE_DEBUG")) {
+    static long long *d_dbg = nullptr;
+    if (!d_dbg) cudaMalloc(&d_dbg, 64 * sizeof(long long));
+    s.dbg = d_dbg;
+    launch_solve(h, s);
+    long long t[8];
+    cudaMemcpyAsync(t, d_dbg, sizeof(t), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    fprintf(stderr, "k_solve cycles:");
+    for (int i = 1; i < 8; i++) fprintf(stderr, " %lld", t[i] - t[i - 1]);
+    fprintf(stderr, " total %lld\n", t[7] - t[0]);
+  } else
   launch_solve(h, s);
   launch_resubstitute(h, resub_args(h, do_step));
   SOSBA_CUDA(cudaGetLastError());
@@ -770,7 +784,7 @@ API int sosba_solve_system(sosba_t *h, const double *HM, const double *bM, doubl
     if ((rc = up(h, hs->d_HMtmp, HM, (size_t)D * D)) || (rc = up(h, hs->d_bMtmp, bM, D))) return rc;
     if ((rc = sync(h))) return rc;
   }
-  if ((rc = enqueue_solve(h, prior ? hs->d_HMtmp : nullptr, prior ? hs->d_bMtmp : nullptr, 0))) return rc;
+  if ((rc = enqueue_solve(h, prior ? hs->d_HMtmp : nullptr, prior ? hs->d_bMtmp : nullptr, 0, Hf || bf))) return rc;
   if ((rc = fetch(h, x, h->d_x, D)) || (rc = fetch(h, Hf, Hpart(h, 3), (size_t)D * D)) || (rc = fetch(h, bf, bpart(h, 3), D)) ||
       (rc = down(h, hs->pin_i, hs->d_cnt + 2, 1)))
     return rc;

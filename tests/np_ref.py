@@ -1,0 +1,349 @@
+"""Second, independent restatement (numpy) of parts of the reference path, written from the reference
+sources rather than from oracle/ — used by the CPU tests to cross-check the C++ oracle.  TEST INFRASTRUCTURE.
+
+  pyramid          FrameHessian::makeImages            src/FullSystem/HessianBlocks.cpp:121-176
+  window_tables    FrameFramePrecalc::set              src/FullSystem/HessianBlocks.cpp:431-461
+                   EnergyFunctional::setAdjointsF      src/OptimizationBackend/EnergyFunctional.cpp:42-103
+                   EnergyFunctional::setDeltaF         src/OptimizationBackend/EnergyFunctional.cpp:163-194
+  linearize        PointFrameResidual::linearize       src/FullSystem/Residuals.cpp:77-271
+  dense_system     what accumulateAF/SCF + stitch compute, as plain fp64 dense algebra
+                   (AccumulatedTopHessian.cpp:35-147,231-301; AccumulatedSCHessian.cpp:32-158)
+
+float32 arithmetic is kept in float32 with the reference's operation order (numpy does not contract to FMA),
+so `linearize` is expected to agree with the oracle bit for bit when both are given the same window tables.
+"""
+import numpy as np
+
+F = np.float32
+PATTERN = np.array([[0, -2], [-1, -1], [1, -1], [-2, 0], [0, 0], [2, 0], [-1, 1], [0, 2]], dtype=np.int32)  # settings.cpp:307-309
+SCALE_XI_TRANS, SCALE_XI_ROT, SCALE_A, SCALE_B, SCALE_F, SCALE_C = 0.5, 1.0, 10.0, 1000.0, 50.0, 50.0
+PRECALC_FLOATS = 32
+RES_IN, RES_OOB, RES_OUTLIER = 0, 1, 2
+
+
+# ---- a1 ------------------------------------------------------------------------------------------
+def pyramid(img, levels, B=None, gamma=1):
+    """Returns [(dI (h,w,3) float32, absSquaredGrad (h,w) float32)] per level; first/last row gradients 0."""
+    out = []
+    I = np.asarray(img, F)
+    for lvl in range(levels):
+        if lvl > 0:
+            p = out[-1][0][..., 0]
+            h, w = p.shape[0] // 2, p.shape[1] // 2
+            p = p[:2 * h, :2 * w]
+            I = F(0.25) * (((p[0::2, 0::2] + p[0::2, 1::2]) + p[1::2, 0::2]) + p[1::2, 1::2])
+        h, w = I.shape
+        flat = I.reshape(-1)
+        dx = np.zeros(w * h, F)
+        dy = np.zeros(w * h, F)
+        idx = np.arange(w, w * (h - 1))
+        dx[idx] = F(0.5) * (flat[idx + 1] - flat[idx - 1])     # flat index: crosses row boundaries at the first/last column
+        dy[idx] = F(0.5) * (flat[idx + w] - flat[idx - w])
+        dx[~np.isfinite(dx)] = 0
+        dy[~np.isfinite(dy)] = 0
+        ab = dx * dx + dy * dy
+        if B is not None and gamma == 1:
+            c = (flat + F(0.5)).astype(np.int32)
+            c = np.clip(c, 5, 250)
+            gw = np.asarray(B, F)[c + 1] - np.asarray(B, F)[c]
+            ab2 = ab * (gw * gw)
+            ab[idx] = ab2[idx]
+        dI = np.stack([flat, dx, dy], axis=1).reshape(h, w, 3)
+        out.append((dI, ab.reshape(h, w)))
+    return out
+
+
+# ---- SE3 (thirdparty/Sophus/sophus/se3.hpp, so3.hpp) ------------------------------------------------
+def hat(w):
+    return np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]], np.float64)
+
+
+def se3_exp(xi):
+    u, w = np.asarray(xi[:3], np.float64), np.asarray(xi[3:6], np.float64)
+    th = np.linalg.norm(w)
+    K = hat(w)
+    if th < 1e-10:
+        R = np.eye(3) + K
+        V = R
+    else:
+        R = np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * (K @ K)
+        V = np.eye(3) + (1 - np.cos(th)) / th ** 2 * K + (th - np.sin(th)) / th ** 3 * (K @ K)
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = V @ u
+    return T
+
+
+def se3_inv(T):
+    o = np.eye(4)
+    o[:3, :3] = T[:3, :3].T
+    o[:3, 3] = -T[:3, :3].T @ T[:3, 3]
+    return o
+
+
+def se3_adj(T):
+    R, t = T[:3, :3], T[:3, 3]
+    A = np.zeros((6, 6))
+    A[:3, :3] = R
+    A[3:, 3:] = R
+    A[:3, 3:] = hat(t) @ R
+    return A
+
+
+def to44(T34):
+    T = np.eye(4)
+    T[:3, :4] = np.asarray(T34, np.float64).reshape(3, 4)
+    return T
+
+
+def aff_from_to(expF, expT, aF, bF, aT, bT):
+    """AffLight::fromToVecExposure (util/NumType.h:157-168)."""
+    expF, expT = F(expF), F(expT)
+    if expF == 0 or expT == 0:
+        expF = expT = F(1)
+    a = np.exp(aT - aF) * float(expT) / float(expF)
+    return a, bT - a * bF
+
+
+def _mm3(A, B):
+    """float32 3x3 product with the coefficient order ((a0 b0 + a1 b1) + a2 b2)."""
+    A, B = np.asarray(A, F), np.asarray(B, F)
+    C = np.zeros((3, 3), F)
+    for i in range(3):
+        for j in range(3):
+            C[i, j] = (A[i, 0] * B[0, j] + A[i, 1] * B[1, j]) + A[i, 2] * B[2, j]
+    return C
+
+
+def window_tables(frames, calib_value, calib_value_zero, cfg_priors=None):
+    """frames: list of dicts as problem.frames_of.  Returns the dict Handle.window_set takes."""
+    nf = len(frames)
+    ev = [to44(f["evalPT"]) for f in frames]
+    st = [np.asarray(f["state"], np.float64) for f in frames]
+    st0 = [np.asarray(f["state_zero"], np.float64) for f in frames]
+    scaled = [np.array([SCALE_XI_TRANS * s[0], SCALE_XI_TRANS * s[1], SCALE_XI_TRANS * s[2], SCALE_XI_ROT * s[3], SCALE_XI_ROT * s[4],
+                        SCALE_XI_ROT * s[5], SCALE_A * s[6], SCALE_B * s[7]]) for s in st]
+    c2w = [se3_exp(scaled[i][:6]) @ ev[i] for i in range(nf)]
+    w2c = [se3_inv(T) for T in c2w]
+    cal = np.array([SCALE_F * calib_value[0], SCALE_F * calib_value[1], SCALE_C * calib_value[2], SCALE_C * calib_value[3]])
+    calf = cal.astype(F)
+    fx, fy, cx, cy = calf
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], F)
+    Ki = np.array([[F(1) / fx, 0, -cx / fx], [0, F(1) / fy, -cy / fy], [0, 0, 1]], F)
+    precalc = np.zeros((nf, nf, PRECALC_FLOATS), F)
+    adHost = np.zeros((nf * nf, 8, 8))
+    adTarget = np.zeros((nf * nf, 8, 8))
+    adHTdeltaF = np.zeros((nf * nf, 8), F)
+    for h in range(nf):
+        for t in range(nf):
+            l0 = se3_inv(ev[t]) @ ev[h]
+            l = w2c[t] @ c2w[h]
+            pc = precalc[h, t]
+            pc[0:9] = l0[:3, :3].astype(F).reshape(9)
+            pc[9:12] = l0[:3, 3].astype(F)
+            R = l[:3, :3].astype(F)
+            tt = l[:3, 3].astype(F)
+            pc[12:21] = _mm3(_mm3(K, R), Ki).reshape(9)
+            for i in range(3):
+                pc[21 + i] = (K[i, 0] * tt[0] + K[i, 1] * tt[1]) + K[i, 2] * tt[2]
+            a, b = aff_from_to(frames[h]["ab_exposure"], frames[t]["ab_exposure"], scaled[h][6], scaled[h][7], scaled[t][6], scaled[t][7])
+            pc[24], pc[25] = F(a), F(b)
+            pc[26] = F(st0[h][7] * SCALE_B)
+            pc[27] = F(np.linalg.norm(l[:3, 3]))
+            # adjoints (EnergyFunctional.cpp:56-83)
+            AH, AT = np.eye(8), np.eye(8)
+            adjT = se3_adj(se3_inv(ev[t])).T
+            AH[:6, :6] = adjT
+            AT[:6, :6] = -adjT
+            a0, _ = aff_from_to(frames[h]["ab_exposure"], frames[t]["ab_exposure"], st0[h][6] * SCALE_A, st0[h][7] * SCALE_B,
+                                st0[t][6] * SCALE_A, st0[t][7] * SCALE_B)
+            a0 = float(F(a0))
+            AT[6, 6] = -a0
+            AH[6, 6] = a0
+            AT[7, 7] = -1
+            AH[7, 7] = a0
+            for M in (AH, AT):
+                M[0:3] *= SCALE_XI_TRANS
+                M[3:6] *= SCALE_XI_ROT
+                M[6] *= SCALE_A
+                M[7] *= SCALE_B
+            idx = h + t * nf
+            adHost[idx], adTarget[idx] = AH, AT
+            dh = (st[h] - st0[h])[:8].astype(F)
+            dt = (st[t] - st0[t])[:8].astype(F)
+            AHf, ATf = AH.astype(F), AT.astype(F)
+            sh = np.zeros(8, F)
+            stt = np.zeros(8, F)
+            for k in range(8):
+                sh = sh + dh[k] * AHf[k]
+                stt = stt + dt[k] * ATf[k]
+            adHTdeltaF[idx] = sh + stt
+    pri = cfg_priors or {}
+    frame_prior = np.zeros((nf, 8))
+    for i, f in enumerate(frames):
+        if int(f.get("frame_id", i)) == 0:   # FrameHessian::getPrior for the first frame (HessianBlocks.h:301-323)
+            frame_prior[i, 0:3] = pri.get("initial_trans_prior", 1e10)
+            frame_prior[i, 3:6] = pri.get("initial_rot_prior", 1e11)
+            frame_prior[i, 6] = pri.get("initial_aff_a_prior", 1e14)
+            frame_prior[i, 7] = pri.get("initial_aff_b_prior", 1e14)
+    return {"nf": nf, "frame_slot": np.array([f.get("slot", i) for i, f in enumerate(frames)], np.int32),
+            "precalc": precalc.reshape(-1), "adHost": adHost.reshape(-1), "adTarget": adTarget.reshape(-1),
+            "adHTdeltaF": adHTdeltaF.reshape(-1),
+            "frame_energy_th": np.array([f.get("frame_energy_th", 512.0) for f in frames], F),
+            "calib": calf, "cDeltaF": (np.asarray(calib_value) - np.asarray(calib_value_zero)).astype(F),
+            "cPrior": np.full(4, pri.get("initial_calib_hessian", 5e9)),
+            "frame_prior": frame_prior.reshape(-1), "frame_delta_prior": np.array([s[:8] for s in st]).reshape(-1),
+            "frame_delta": np.array([(s - s0)[:8] for s, s0 in zip(st, st0)]).reshape(-1)}
+
+
+# ---- a3 ------------------------------------------------------------------------------------------
+def _interp33(img, x, y):
+    """getInterpolatedElement33 (util/globalFuncs.h:68-82); img (h,w,3); x,y float32 arrays."""
+    ix = x.astype(np.int32)
+    iy = y.astype(np.int32)
+    dx = x - ix.astype(F)
+    dy = y - iy.astype(F)
+    dxdy = dx * dy
+    t11, t01, t10, t00 = img[iy + 1, ix + 1], img[iy + 1, ix], img[iy, ix + 1], img[iy, ix]
+    w11, w01, w10, w00 = dxdy, dy - dxdy, dx - dxdy, F(1) - dx - dy + dxdy
+    return w11[..., None] * t11 + w01[..., None] * t01 + w10[..., None] * t10 + w00[..., None] * t00
+
+
+def linearize(win, pts, res, images_dI, w, h, frame_energy_th=None, huber=9.0, outlier_sum=2500.0):
+    """All residuals with state IN at entry.  Returns dict(new_state, new_energy, new_energy_wo, J (R,74), projectedTo, center)."""
+    nf = win["nf"]
+    precalc = np.asarray(win["precalc"], F).reshape(nf, nf, PRECALC_FLOATS)
+    fxl, fyl, cxl, cyl = [F(x) for x in win["calib"]]
+    fxli, fyli = F(1) / fxl, F(1) / fyl
+    th_f = np.asarray(win["frame_energy_th"] if frame_energy_th is None else frame_energy_th, F)
+    rp = np.asarray(res["point"])
+    rt = np.asarray(res["target"])
+    rh = np.asarray(pts["host"])[rp]
+    R = len(rp)
+    pc = precalc[rh, rt]
+    R0, t0, KRKi, Kt = pc[:, 0:9], pc[:, 9:12], pc[:, 12:21], pc[:, 21:24]
+    aff0, aff1, b0 = pc[:, 24], pc[:, 25], pc[:, 26]
+    pu, pv = np.asarray(pts["u"], F)[rp], np.asarray(pts["v"], F)[rp]
+    idz, idp = np.asarray(pts["idepth_zero"], F)[rp], np.asarray(pts["idepth"], F)[rp]
+    color, weights = np.asarray(pts["color"], F).reshape(-1, 8)[rp], np.asarray(pts["weights"], F).reshape(-1, 8)[rp]
+    wM3, hM3 = F(w - 3), F(h - 3)
+    with np.errstate(all="ignore"):
+        # centre projection (ResidualProjections.h:43-73)
+        Kl0, Kl1, Kl2 = (pu + F(0) - cxl) * fxli, (pv + F(0) - cyl) * fyli, np.ones(R, F)
+        ptp = [((R0[:, 3 * i] * Kl0 + R0[:, 3 * i + 1] * Kl1) + R0[:, 3 * i + 2] * Kl2) + t0[:, i] * idz for i in range(3)]
+        dres = F(1) / ptp[2]
+        nid = idz * dres
+        u, v = ptp[0] * dres, ptp[1] * dres
+        Ku, Kv = u * fxl + cxl, v * fyl + cyl
+        ok_c = (dres > 0) & (Ku > F(1.1)) & (Kv > F(1.1)) & (Ku < wM3) & (Kv < hM3)
+        J = np.zeros((R, 74), F)
+        d_d_x = dres * (t0[:, 0] - t0[:, 2] * u) * F(1) * fxl
+        d_d_y = dres * (t0[:, 1] - t0[:, 2] * v) * F(1) * fyl
+        cx2 = dres * (R0[:, 6] * u - R0[:, 0])
+        cx3 = fxl * dres * (R0[:, 7] * u - R0[:, 1]) * fyli
+        cx0, cx1 = Kl0 * cx2, Kl1 * cx3
+        cy2 = fyl * dres * (R0[:, 6] * v - R0[:, 3]) * fxli
+        cy3 = dres * (R0[:, 7] * v - R0[:, 4])
+        cy0, cy1 = Kl0 * cy2, Kl1 * cy3
+        SF, SC = F(SCALE_F), F(SCALE_C)
+        Jpdc0 = np.stack([(cx0 + u) * SF, cx1 * SF, (cx2 + F(1)) * SC, cx3 * SC], 1)
+        Jpdc1 = np.stack([cy0 * SF, (cy1 + v) * SF, cy2 * SC, (cy3 + F(1)) * SC], 1)
+        z = np.zeros(R, F)
+        Jpdxi0 = np.stack([nid * fxl, z, -nid * u * fxl, -u * v * fxl, (F(1) + u * u) * fxl, -v * fxl], 1)
+        Jpdxi1 = np.stack([z, nid * fyl, -nid * v * fyl, -(F(1) + v * v) * fyl, u * v * fyl, u * fyl], 1)
+        J[:, 8:14], J[:, 14:20], J[:, 20:24], J[:, 24:28] = Jpdxi0, Jpdxi1, Jpdc0, Jpdc1
+        J[:, 28], J[:, 29] = d_d_x, d_d_y
+        # pattern
+        up = pu[:, None] + PATTERN[None, :, 0].astype(F)
+        vp = pv[:, None] + PATTERN[None, :, 1].astype(F)
+        q = [((KRKi[:, 3 * i, None] * up + KRKi[:, 3 * i + 1, None] * vp) + KRKi[:, 3 * i + 2, None] * F(1)) + Kt[:, i, None] * idp[:, None] for i in range(3)]
+        Kup, Kvp = q[0] / q[2], q[1] / q[2]
+        ok_p = (Kup > F(1.1)) & (Kvp > F(1.1)) & (Kup < wM3) & (Kvp < hM3)
+        hit = np.zeros((R, 8, 3), F)
+        for t in range(nf):
+            m = (rt[:, None] == t) & ok_p
+            if m.any():
+                hit[m] = _interp33(images_dI[t], Kup[m], Kvp[m])
+        ok_p &= np.isfinite(hit[..., 0])
+        ok = ok_c & ok_p.all(axis=1)
+        residual = hit[..., 0] - (aff0[:, None] * color + aff1[:, None]).astype(F)
+        drdA = color - b0[:, None]
+        c = F(outlier_sum)
+        wgt = np.sqrt(c / (c + (hit[..., 1] * hit[..., 1] + hit[..., 2] * hit[..., 2])))
+        wgt = F(0.5) * (wgt + weights)
+        hth = F(huber)
+        hw = np.where(np.abs(residual) < hth, F(1), hth / np.abs(residual)).astype(F)
+        e_terms = wgt * wgt * hw * residual * residual * (F(2) - hw)
+        hw = np.where(hw < 1, np.sqrt(hw), hw).astype(F)
+        hw = hw * wgt
+        hx, hy = hit[..., 1] * hw, hit[..., 2] * hw
+
+        def seq(a):
+            s = np.zeros(R, F)
+            for i in range(8):
+                s = s + a[:, i]
+            return s
+        energy = seq(e_terms)
+        J[:, 0:8] = residual * hw
+        J[:, 30:38], J[:, 38:46] = hx, hy
+        J[:, 46:54], J[:, 54:62] = drdA * hw, hw
+        J00, J11, J10 = seq(hx * hx), seq(hy * hy), seq(hx * hy)
+        J[:, 62], J[:, 63], J[:, 64], J[:, 65] = J00, J10, J10, J11
+        J[:, 66], J[:, 67], J[:, 68], J[:, 69] = seq(drdA * hw * hx), seq(drdA * hw * hy), seq(hw * hx), seq(hw * hy)
+        A00, A01, A11 = seq(drdA * drdA * hw * hw), seq(drdA * hw * hw), seq(hw * hw)
+        J[:, 70], J[:, 71], J[:, 72], J[:, 73] = A00, A01, A01, A11
+        wJI2 = seq(hw * hw * (hx * hx + hy * hy))
+    th = np.maximum(th_f[rh], th_f[rt])
+    outl = (energy > th) | (wJI2 < 2)
+    new_state = np.where(ok, np.where(outl, RES_OUTLIER, RES_IN), RES_OOB).astype(np.uint8)
+    new_energy = np.where(outl, th, energy).astype(F)
+    return {"new_state": new_state, "new_energy": new_energy, "new_energy_wo": np.where(ok, energy, F(-1)).astype(F), "J": J,
+            "projectedTo": np.stack([Kup, Kvp], -1), "center": np.stack([Ku, Kv, nid], 1), "host": rh}
+
+
+# ---- a6-a10 as dense fp64 algebra --------------------------------------------------------------------
+def dense_system(win, pts, res, J, active, n_points):
+    """Full Gauss-Newton normal equations over [calib(4) | frames(8 nf) | idepth(P)] from per-residual J records
+    (RawResidualJacobian order), then the split the reference makes: top (H, b) and Schur (Hsc, bsc)."""
+    nf = win["nf"]
+    D = 4 + 8 * nf
+    adH = np.asarray(win["adHost"]).reshape(nf * nf, 8, 8)
+    adT = np.asarray(win["adTarget"]).reshape(nf * nf, 8, 8)
+    rp, rt = np.asarray(res["point"]), np.asarray(res["target"])
+    rh = np.asarray(pts["host"])[rp]
+    J = np.asarray(J, np.float64)
+    H = np.zeros((D, D))
+    b = np.zeros(D)
+    Hcd = np.zeros((n_points, D))
+    Hdd = np.zeros(n_points)
+    bd = np.zeros(n_points)
+    for r in np.nonzero(active)[0]:
+        j = J[r]
+        resF, Jxi, Jc, Jd = j[0:8], j[8:20].reshape(2, 6), j[20:28].reshape(2, 4), j[28:30]
+        JI, Jab = j[30:46].reshape(2, 8), j[46:62].reshape(2, 8)
+        Jrel = np.zeros((8, 13))                       # d r_i / d [calib, xi_rel, a, b, idepth]
+        Jrel[:, 0:4] = JI.T @ Jc
+        Jrel[:, 4:10] = JI.T @ Jxi
+        Jrel[:, 10:12] = Jab.T
+        Jrel[:, 12] = JI.T @ Jd
+        idx = rh[r] + rt[r] * nf
+        Jg = np.zeros((8, D))
+        Jg[:, 0:4] = Jrel[:, 0:4]
+        Jg[:, 4 + 8 * rh[r]:12 + 8 * rh[r]] += Jrel[:, 4:12] @ adH[idx].T
+        Jg[:, 4 + 8 * rt[r]:12 + 8 * rt[r]] += Jrel[:, 4:12] @ adT[idx].T
+        H += Jg.T @ Jg
+        b += Jg.T @ resF
+        p = rp[r]
+        Hcd[p] += Jg.T @ Jrel[:, 12]
+        Hdd[p] += Jrel[:, 12] @ Jrel[:, 12]
+        bd[p] += Jrel[:, 12] @ resF
+    return H, b, Hcd, Hdd, bd
+
+
+def schur(Hcd, Hdd, bd, prior=0.0):
+    Hd = Hdd + prior
+    m = Hdd > 0
+    Hdi = np.where(m, 1.0 / np.maximum(Hd, 1e-10), 0.0)
+    Hsc = (Hcd.T * Hdi) @ Hcd
+    bsc = Hcd.T @ (Hdi * bd)
+    return Hsc, bsc

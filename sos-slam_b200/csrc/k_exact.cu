@@ -582,131 +582,6 @@ __global__ void __launch_bounds__(256) k_track_res(TrackResArgs a) {
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Frames / calibration part of one Gauss-Newton step on the device (single CTA, fp64):
-//   EnergyFunctional::resubstituteF_MT frame+calib steps (:500-507), FullSystem::backupState (:260-271),
-//   doStepFromBackup frames+calib (:185-257), FrameHessian::setState (HessianBlocks.h:217-230),
-//   FrameFramePrecalc::set (HessianBlocks.cpp:431-461), setDeltaF (EnergyFunctional.cpp:163-194).
-// Mirrors host_ba.cpp (same float operation order); keeps the whole iteration on the stream with no host round trip.
-__device__ __forceinline__ void d_mul33f(const float *A, const float *B, float *C) {
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) C[3 * i + j] = (A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j]) + A[3 * i + 2] * B[6 + j];
-}
-
-__global__ void __launch_bounds__(256) k_frame_step(StepArgs a) {
-  using namespace sosba_math;
-  __shared__ double s_fs[16 * SOSBA_FS];
-  __shared__ Rigid s_c2w[16], s_w2c[16];
-  __shared__ double s_scaled[16][2];
-  __shared__ float s_K[4];
-  const int nf = a.nf, tid = threadIdx.x;
-  const double SC_T = 0.5, SC_R = 1.0, SC_A = 10.0, SC_B = 1000.0, SC_F = 50.0, SC_C = 50.0;
-  for (int e = tid; e < nf * SOSBA_FS; e += blockDim.x) s_fs[e] = a.fs[e];
-  __syncthreads();
-  if (tid < nf) {
-    double *F = s_fs + SOSBA_FS * tid;
-    double *G = a.fs + SOSBA_FS * tid;
-    double *state = F + 12, *backup = F + 32, *step = F + 42;
-    for (int i = 0; i < 8; i++) step[i] = -a.x[4 + 8 * tid + i];
-    step[8] = step[9] = 0.0;
-    double scaled[10];
-    for (int i = 0; i < 10; i++) {
-      backup[i] = state[i];
-      state[i] = backup[i] + (double)a.stepfac * step[i];
-      G[12 + i] = state[i]; G[32 + i] = backup[i]; G[42 + i] = step[i];
-    }
-    for (int i = 0; i < 3; i++) scaled[i] = SC_T * state[i];
-    for (int i = 3; i < 6; i++) scaled[i] = SC_R * state[i];
-    scaled[6] = SC_A * state[6]; scaled[7] = SC_B * state[7]; scaled[8] = SC_A * state[8]; scaled[9] = SC_B * state[9];
-    const Rigid ev = rigid_from34(F);
-    const Rigid c2w = rigid_mul(rigid_exp(scaled), ev);
-    s_c2w[tid] = c2w;
-    s_w2c[tid] = rigid_inverse(c2w);
-    s_scaled[tid][0] = scaled[6]; s_scaled[tid][1] = scaled[7];
-    for (int i = 0; i < 8; i++) {
-      a.wprior[4 + 8 * nf + 8 * tid + i] = state[i];                 // delta_prior = state - getPriorZero() (== 0)
-      a.wprior[4 + 16 * nf + 8 * tid + i] = state[i] - F[22 + i];    // delta = state - state_zero
-    }
-  }
-  if (tid == 32) {  // calibration: CalibHessian::setValue (HessianBlocks.h:487-501)
-    double *C = a.cs;   // value[4] | value_zero[4] | value_backup[4] | step[4]
-    float sf[4];
-    for (int i = 0; i < 4; i++) {
-      C[12 + i] = -a.x[i];
-      C[8 + i] = C[i];
-      C[i] = C[8 + i] + (double)a.stepfac * C[12 + i];
-      sf[i] = (float)((i < 2 ? SC_F : SC_C) * C[i]);
-      s_K[i] = sf[i];
-      a.calib[i] = sf[i];
-      a.calib[6 + i] = (float)(C[i] - C[4 + i]);
-    }
-    a.calib[4] = 1.0f / sf[0];
-    a.calib[5] = 1.0f / sf[1];
-  }
-  __syncthreads();
-  if (tid == 64) {  // step norms of doStepFromBackup, float accumulation in frame order
-    float sumA = 0, sumB = 0, sumT = 0, sumR = 0;
-    for (int f = 0; f < nf; f++) {
-      const double *st = s_fs + SOSBA_FS * f + 42;
-      sumA += st[6] * st[6];
-      sumB += st[7] * st[7];
-      sumT += st[0] * st[0] + st[1] * st[1] + st[2] * st[2];
-      sumR += st[3] * st[3] + st[4] * st[4] + st[5] * st[5];
-    }
-    a.iter[0] = sumA / nf; a.iter[1] = sumB / nf; a.iter[2] = sumT / nf; a.iter[3] = sumR / nf;
-  }
-  const float fx = s_K[0], fy = s_K[1], cx = s_K[2], cy = s_K[3];
-  const float K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
-  const float Ki[9] = {1.0f / fx, 0, -cx / fx, 0, 1.0f / fy, -cy / fy, 0, 0, 1};
-  for (int e = tid; e < nf * nf; e += blockDim.x) {
-    const int h = e / nf, t = e % nf;
-    const double *Fh = s_fs + SOSBA_FS * h, *Ft = s_fs + SOSBA_FS * t;
-    // setDeltaF first (its 32 float4 adjoint loads are in flight while the fp64 rigid algebra runs)
-    const int idx = h + t * nf;
-    const float4 *AhF = (const float4 *)(a.adHostF + 64 * (size_t)idx), *AtF = (const float4 *)(a.adTargetF + 64 * (size_t)idx);
-    float4 rh[16], rt[16];
-#pragma unroll
-    for (int q = 0; q < 16; q++) { rh[q] = __ldg(AhF + q); rt[q] = __ldg(AtF + q); }
-    float pre[SOSBA_PRECALC_FLOATS];
-    const Rigid l0 = rigid_mul(rigid_inverse(rigid_from34(Ft)), rigid_from34(Fh));
-    for (int i = 0; i < 9; i++) pre[SOSBA_PC_RTLL0 + i] = (float)l0.R[i];
-    for (int i = 0; i < 3; i++) pre[SOSBA_PC_TTLL0 + i] = (float)l0.t[i];
-    const Rigid l = rigid_mul(s_w2c[t], s_c2w[h]);
-    float R[9], tt[3], KR[9];
-    for (int i = 0; i < 9; i++) R[i] = (float)l.R[i];
-    for (int i = 0; i < 3; i++) tt[i] = (float)l.t[i];
-    d_mul33f(K, R, KR);
-    d_mul33f(KR, Ki, pre + SOSBA_PC_KRKI);
-    for (int i = 0; i < 3; i++) pre[SOSBA_PC_KT + i] = (K[3 * i] * tt[0] + K[3 * i + 1] * tt[1]) + K[3 * i + 2] * tt[2];
-    float expF = (float)Fh[52], expT = (float)Ft[52];     // AffLight::fromToVecExposure (NumType.h:157-168)
-    if (expF == 0 || expT == 0) expT = expF = 1;
-    const double aa = exp(s_scaled[t][0] - s_scaled[h][0]) * expT / expF;
-    const double bbv = s_scaled[t][1] - aa * s_scaled[h][1];
-    pre[SOSBA_PC_AFF] = (float)aa;
-    pre[SOSBA_PC_AFF + 1] = (float)bbv;
-    pre[SOSBA_PC_B0] = (float)(Fh[22 + 7] * SC_B);
-    pre[SOSBA_PC_DIST] = (float)sqrt(l.t[0] * l.t[0] + l.t[1] * l.t[1] + l.t[2] * l.t[2]);
-    pre[28] = pre[29] = pre[30] = pre[31] = 0.f;
-    float4 *p4 = (float4 *)(a.precalc + (size_t)e * SOSBA_PRECALC_FLOATS);
-#pragma unroll
-    for (int q = 0; q < 8; q++) p4[q] = make_float4(pre[4 * q], pre[4 * q + 1], pre[4 * q + 2], pre[4 * q + 3]);
-    // adHTdeltaF[h + t*nf] = delta_h^T adHostF + delta_t^T adTargetF, summed over k in order
-    float sh[8] = {0, 0, 0, 0, 0, 0, 0, 0}, st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const float dh = (float)(Fh[12 + k] - Fh[22 + k]), dt = (float)(Ft[12 + k] - Ft[22 + k]);
-      const float4 h0 = rh[2 * k], h1 = rh[2 * k + 1], t0 = rt[2 * k], t1 = rt[2 * k + 1];
-      sh[0] += dh * h0.x; sh[1] += dh * h0.y; sh[2] += dh * h0.z; sh[3] += dh * h0.w;
-      sh[4] += dh * h1.x; sh[5] += dh * h1.y; sh[6] += dh * h1.z; sh[7] += dh * h1.w;
-      st[0] += dt * t0.x; st[1] += dt * t0.y; st[2] += dt * t0.z; st[3] += dt * t0.w;
-      st[4] += dt * t1.x; st[5] += dt * t1.y; st[6] += dt * t1.z; st[7] += dt * t1.w;
-    }
-    float4 *o4 = (float4 *)(a.adHTdeltaF + 8 * (size_t)idx);
-    o4[0] = make_float4(sh[0] + st[0], sh[1] + st[1], sh[2] + st[2], sh[3] + st[3]);
-    o4[1] = make_float4(sh[4] + st[4], sh[5] + st[5], sh[6] + st[6], sh[7] + st[7]);
-  }
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -749,10 +624,6 @@ void launch_prep_records(sosba *h, const LinArgs &a, int mode, const int *d_list
 }
 void launch_energy_th(sosba *h, const ThArgs &a) {
   k_energy_th<<<1, 1024, 0, h->stream>>>(a);
-  h->launches++;
-}
-void launch_frame_step(sosba *h, const StepArgs &a) {
-  k_frame_step<<<1, 256, 0, h->stream>>>(a);
   h->launches++;
 }
 void launch_track_res(sosba *h, const TrackResArgs &a) {

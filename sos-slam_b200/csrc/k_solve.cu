@@ -7,7 +7,11 @@
 //   xAd[h*nf+t] = x_h^T adHostF[h+nf*t] + x_t^T adTargetF[h+nf*t] for resubstituteF_MT (:496-524).
 // D = 4 + 8*nf <= 132; the (D+1)^2 augmented matrix lives in shared memory.
 #include <math.h>
+#include <stdlib.h>
 
+#include <algorithm>
+
+#include "host_math.h"
 #include "kernels.h"
 
 namespace {
@@ -18,43 +22,218 @@ __device__ __forceinline__ double top_entry(const double *__restrict__ Hraw, int
   return Hraw[(size_t)r * D + c];
 }
 
-// 256 threads as a 16x16 grid; thread (ty,tx) keeps the entries {(ty+16a, tx+16b)} of the augmented, permuted,
-// preconditioned lower triangle in registers for the whole factorisation (T = ceil((D+1)/16)).
+// 256 threads as a 16x16 grid.  Thread (ty,tx) keeps the entries {(ty+16(kb+a), tx+16(kb+b))} of the trailing part of
+// the augmented, permuted, preconditioned lower triangle in registers (T = ceil((D+1)/16) tile rows/columns).
 // Pivot order: Eigen::LDLT is left-looking, so when it searches the largest |diagonal| of the trailing block none
 // of those entries has been updated yet — the transposition sequence depends only on the input diagonal and equals
-// a descending sort of |diag| (ties broken by index).  The factorisation itself then needs no pivot search and can
-// run right-looking with one barrier per column; the right-hand side rides along as row D, ending as D^-1 L^-1 P b.
+// a descending sort of |diag| (ties broken by index).  The factorisation itself then needs no pivot search and runs
+// right-looking in panels of 4 columns with ONE barrier per panel: the owners publish the panel, every thread
+// factorises the 4x4 diagonal block redundantly in registers, forms the L21 rows of its own tile rows / columns and
+// applies the rank-4 update.  After every 16 columns the register tiles shift by one, so the loop body indexes
+// registers statically yet stays small enough to live in the instruction cache (a fully unrolled factorisation is
+// instruction-fetch bound: every instruction would run exactly once).  The right-hand side rides along as row D,
+// ending as D^-1 L^-1 P b.
+// Inputs arrive by TMA bulk copies (cp.async.bulk + mbarrier) into shared memory, so the permuted gathers of the
+// assembly never touch L2.
+// This file is compiled with -fmad=false (the fused frame step mirrors host_ba.cpp operation by operation), so the
+// factorisation spells its fused multiply-adds out with fma().
+// 1/v: MUFU.RCP64H seed (about 20 bits) + two Newton steps, no slow path — the pivots of the Jacobi-scaled system are O(1).
+// v == 0 gives inf -> nan -> 0: the column is left alone (Eigen: pivot_is_valid).
+__device__ __forceinline__ double safe_rcp(double v) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
+  double e = fma(-v, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-v, r, 1.0);
+  r = fma(r, e, r);
+  return isfinite(r) ? r : 0.0;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(mbar))
+               : "memory");
+}
+
+constexpr int SOLVE_UPD = 256;      // update warps: 16x16 thread grid over the trailing tiles
+constexpr int SOLVE_PAN = 128;      // panel warps: one thread per remaining row
+constexpr int SOLVE_THREADS = SOLVE_UPD + SOLVE_PAN;
+constexpr int BAR_PUB = 1, BAR_LY = 2;   // named barriers (0 is __syncthreads)
+
+__device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(SOLVE_THREADS) : "memory"); }
+// bar.arrive orders the arriving thread's earlier shared-memory writes before the barrier completes (the PTX ISA's
+// producer/consumer pattern: st.shared; bar.arrive  ||  bar.sync; ld.shared), so no fence is needed.
+__device__ __forceinline__ void nb_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(SOLVE_THREADS) : "memory"); }
+
+// Update warps, panel p (k0 = 16 kb + 4 q) with NA live tile rows.  L (l = y / d) of the panel sits in the persistent
+// factor storage Lp (row-major [row][4]), Y in the double-buffered Y4.  The next panel lives in tile column JP: the
+// lanes that own it (8 per warp) update and publish it FIRST, with only their own shared-memory loads in the way, so
+// the panel warps can start on panel p+1 while the bulk of the rank-4 update runs (look-ahead).
+// LAST (q == 3): tile column 0 is finished, the next panel sits in column 1.
+template <int T, int NA, bool LAST>
+__device__ __forceinline__ void update_step(double (&reg)[T][T], const double *__restrict__ Lp, const double *__restrict__ Y4, double *__restrict__ pbn,
+                                            const int kb, const int q, const int ty, const int tx, long long *dbg) {
+  constexpr int JP = LAST ? 1 : 0;
+  const int k0n = 16 * kb + 4 * q + 4;
+  const int cn = tx - 4 * ((q + 1) & 3);   // my column inside the next panel, if 0 <= cn < 4
+  const bool owner = cn >= 0 && cn < 4;
+  const double2 *pl = (const double2 *)(Lp + (size_t)(ty + 16 * (kb + JP)) * 4);   // + 32 double2 per tile row
+  const double2 *py = (const double2 *)(Y4 + (size_t)(tx + 16 * (kb + JP)) * 4);
+  double *pub = pbn + (size_t)(ty + 16 * (kb + JP)) * 4 + cn;
+  nb_sync(BAR_LY);
+  double li[NA][4];
+#pragma unroll
+  for (int ia = JP; ia < NA; ia++) {   // two rows per warp: one wavefront per load
+    const double2 l01 = pl[32 * (ia - JP)], l23 = pl[32 * (ia - JP) + 1];
+    li[ia][0] = l01.x; li[ia][1] = l01.y; li[ia][2] = l23.x; li[ia][3] = l23.y;
+  }
+  if (NA > JP) {
+    const double2 y01 = py[0], y23 = py[1];
+    if (dbg) dbg[0] = clock64() + (long long)(y23.y == 123.0);
+#pragma unroll
+    for (int ia = JP; ia < NA; ia++) {
+      const double v = fma(-li[ia][3], y23.y, fma(-li[ia][2], y23.x, fma(-li[ia][1], y01.y, fma(-li[ia][0], y01.x, reg[ia][JP]))));
+      reg[ia][JP] = v;
+      if (owner && ty + 16 * (kb + ia) >= k0n + cn) pub[64 * (ia - JP)] = v;   // rows past D are zero tiles landing in the padding
+    }
+  }
+  if (dbg) dbg[1] = clock64() + (long long)(reg[JP][JP] == 123.0);
+  nb_arrive(BAR_PUB);
+  // the bulk of the rank-4 update runs while the panel warps work on panel p+1
+#pragma unroll
+  for (int jb = JP + 1; jb < NA; jb++) {
+    const double2 y01 = py[32 * (jb - JP)], y23 = py[32 * (jb - JP) + 1];
+#pragma unroll
+    for (int ia = jb; ia < NA; ia++)
+      reg[ia][jb] = fma(-li[ia][3], y23.y, fma(-li[ia][2], y23.x, fma(-li[ia][1], y01.y, fma(-li[ia][0], y01.x, reg[ia][jb]))));
+  }
+}
+
+template <int T, int NA>
+struct UpdateDispatch {
+  static __device__ __forceinline__ void run(int nact, bool last, double (&reg)[T][T], const double *Lp, const double *Y4, double *pbn, int kb, int q,
+                                             int ty, int tx, long long *dbg) {
+    if (nact == NA) {
+      if (last) update_step<T, NA, true>(reg, Lp, Y4, pbn, kb, q, ty, tx, dbg);
+      else update_step<T, NA, false>(reg, Lp, Y4, pbn, kb, q, ty, tx, dbg);
+    } else UpdateDispatch<T, NA - 1>::run(nact, last, reg, Lp, Y4, pbn, kb, q, ty, tx, dbg);
+  }
+};
 template <int T>
-__global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
-  extern __shared__ double sm[];
+struct UpdateDispatch<T, 0> {
+  static __device__ __forceinline__ void run(int, bool, double (&)[T][T], const double *, const double *, double *, int, int, int, int, long long *) {}
+};
+
+// Panel warps, panel k0: the 4x4 diagonal block (redundantly per thread), then one row of L21 per thread: threads 0..7
+// retire the rows of this and the previous pivot block from Y4 (they must read as zero columns from now on), thread
+// 8 + r owns row k0 + 4 + r.  L goes to the persistent factor storage Lp ([row][4]; row D = the right-hand side,
+// ending as D^-1 L^-1 P b), Y to Y4; thread 0 also stores L11 into the rows of the pivot block.
+__device__ __forceinline__ void panel_rows(const double *__restrict__ pb, double *__restrict__ Lp, double *__restrict__ Y4, const int D, const int k0,
+                                           const int pt, long long *dbg) {
+  const double2 *pd = (const double2 *)(pb + (size_t)k0 * 4);
+  const int i = k0 - 4 + pt;
+  const bool live = pt >= 8 && i <= D;
+  const double2 *pp = (const double2 *)(pb + (size_t)(live ? i : k0) * 4);
+  double2 *pl = (double2 *)(Lp + (size_t)i * 4), *py = (double2 *)(Y4 + (size_t)i * 4);
+  nb_sync(BAR_PUB);
+  const double a00 = pd[0].x;
+  const double2 q1 = pd[2], q2a = pd[4], q2b = pd[5], q3a = pd[6], q3b = pd[7];
+  const double2 pa = pp[0], pc = pp[1];
+  const double a10 = q1.x, a11 = q1.y, a20 = q2a.x, a21 = q2a.y, a22 = q2b.x, a30 = q3a.x, a31 = q3a.y, a32 = q3b.x, a33 = q3b.y;
+  if (dbg) dbg[0] = clock64() + (long long)(a00 == 123.0) + (long long)(pc.y == 123.0);   // panel data landed
+  const double r0 = safe_rcp(a00);
+  const double l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0, m0 = pa.x * r0;
+  const double d1 = fma(-l10, a10, a11), r1 = safe_rcp(d1);
+  const double y21 = fma(-l20, a10, a21), y31 = fma(-l30, a10, a31), y1 = fma(-m0, a10, pa.y);
+  const double l21 = y21 * r1, l31 = y31 * r1, m1 = y1 * r1;
+  const double d2 = fma(-l21, y21, fma(-l20, a20, a22)), r2 = safe_rcp(d2);
+  const double y32 = fma(-l31, y21, fma(-l30, a20, a32)), y2 = fma(-m1, y21, fma(-m0, a20, pc.x));
+  const double l32 = y32 * r2, m2 = y2 * r2;
+  const double d3 = fma(-l32, y32, fma(-l31, y31, fma(-l30, a30, a33))), r3 = safe_rcp(d3);
+  const double y3 = fma(-m2, y32, fma(-m1, y31, fma(-m0, a30, pc.y))), m3 = y3 * r3;
+  if (dbg) dbg[1] = clock64() + (long long)(m3 == 123.0);   // chain done
+  if (live) {
+    pl[0] = make_double2(m0, m1);
+    pl[1] = make_double2(m2, m3);
+    if (i < D) { py[0] = make_double2(pa.x, y1); py[1] = make_double2(y2, y3); }   // the rhs row is nobody's column
+  } else if (pt < 8 && i >= 0) {
+    py[0] = make_double2(0.0, 0.0);
+    py[1] = make_double2(0.0, 0.0);
+  }
+  if (pt == 0) {   // L11 (unit lower) into the pivot rows of this panel's factor block
+    Lp[(size_t)(k0 + 1) * 4] = l10;
+    Lp[(size_t)(k0 + 2) * 4] = l20; Lp[(size_t)(k0 + 2) * 4 + 1] = l21;
+    Lp[(size_t)(k0 + 3) * 4] = l30; Lp[(size_t)(k0 + 3) * 4 + 1] = l31; Lp[(size_t)(k0 + 3) * 4 + 2] = l32;
+  }
+}
+
+__device__ void frame_step_body(const StepArgs &a);
+
+template <int T>
+__global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
+  extern __shared__ __align__(16) double sm[];
   const int D = a.D, LD = D + 1, tid = threadIdx.x, nf = a.nf;
-  double *M = sm;                          // [D][LD] unit lower factor, for the back substitution
-  double *S = M + (size_t)D * LD;          // [D] Jacobi scaling
+  const int DP = D + 1;
+  constexpr int PST = 16 * T + 1;          // rows per panel block of the factor storage (+1: de-phases the banks of consecutive blocks)
+  double *M = sm;                          // [D][D] staged raw top H; later M4: [D/4][PST][4] unit lower factor, panel by panel, row D = rhs
+  double *As = M + (size_t)D * PST;        // [D+1][D] assembled lower triangle, row D = rhs
+  double *S = As + (size_t)DP * D;         // [D] Jacobi scaling
   double *bb = S + D;                      // [D] unscaled rhs
   double *dtmp = bb + D;                   // [D] damped diagonal
   double *delta = dtmp + D;                // [D]
   double *key = delta + D;                 // [D]
-  double *col = key + D;                   // [2][D+2] column broadcast, double buffered
-  double *z = col + 2 * (D + 2);           // [D]
+  double *z = key + D;                     // [D]
+  double *pan = z + D;                     // [2][16T*4] panel, double buffered, rows past D stay zero
+  double *Yb = pan + 2 * (size_t)(16 * T) * 4;   // [2][16T*4] Y rows of the current panel, double buffered
+  double *stage = Yb + 2 * (size_t)(16 * T) * 4; // optional: accSC [(D+1)^2 (+1)], then HM [D*D]
   __shared__ int perm[144];
-  __shared__ double s_dk[2];
+  __shared__ __align__(8) unsigned long long mbar;
   const double lambda = 1e-5;                               // EnergyFunctional.cpp:1031
   const double sc = (double)(1.0f / (float)(1 + lambda));   // float-typed scalar (:1099)
   const double *cPrior = a.wprior, *fprior = a.wprior + 4, *fdp = a.wprior + 4 + 8 * nf, *fdelta = a.wprior + 4 + 16 * nf;
-  const int DP = D + 1;
   const int warp = tid >> 5, lane = tid & 31;
   const int ty = tid >> 4, tx = tid & 15;
 #define SOLVE_TS(n) do { if (a.dbg && tid == 0) a.dbg[n] = clock64(); } while (0)
   SOLVE_TS(0);
 
+  // ---- stage the inputs in shared memory: one thread issues the bulk copies, everyone waits on the mbarrier ------
+  const double *Hsrc = M, *Ssrc = a.accSC, *HMsrc = a.HM;
+  const unsigned bytesH = (unsigned)((size_t)D * D * 8), bytesS = (unsigned)((((size_t)DP * DP + 1) & ~(size_t)1) * 8);
+  double *Ss = stage, *Hm = stage + (bytesS >> 3);
+  if (a.stage_sc) Ssrc = Ss;
+  if (a.HM && a.stage_hm) HMsrc = Hm;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned total = bytesH + (a.stage_sc ? bytesS : 0u) + ((a.HM && a.stage_hm) ? bytesH : 0u);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(total) : "memory");
+    bulk_g2s(M, a.Htop, bytesH, &mbar);
+    if (a.stage_sc) bulk_g2s(Ss, a.accSC, bytesS, &mbar);
+    if (a.HM && a.stage_hm) bulk_g2s(Hm, a.HM, bytesH, &mbar);
+  }
+  for (int i = tid; i < 4 * (16 * T) * 4; i += SOLVE_THREADS) pan[i] = 0.0;   // panel + Y buffers: rows past D must read as zero
+  for (int i = tid; i < D; i += SOLVE_THREADS) delta[i] = i < 4 ? (double)a.cDeltaF[i] : fdelta[i - 4];
+  double pr = 0.0, dpr = 0.0, bt = 0.0, bm = 0.0;   // per-row inputs that stay in global memory: fetch them under the copies
+  if (tid < D) {
+    pr = tid < 4 ? cPrior[tid] : fprior[tid - 4];
+    dpr = tid < 4 ? (double)a.cDeltaF[tid] : fdp[tid - 4];
+    bt = a.btop[tid];
+    if (a.HM) bm = a.bM[tid];
+  }
+  __syncthreads();   // mbarrier initialised and armed before anyone polls it
+  {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
+    }
+  }
   // ---- diagonal, rhs --------------------------------------------------------------------------------
-  for (int i = tid; i < D; i += 256) delta[i] = i < 4 ? (double)a.cDeltaF[i] : fdelta[i - 4];
-  __syncthreads();
   double *hmd = key;   // HM * delta, bM_top = bM + HM * delta (:1070-1091)
   if (a.HM) {
-    for (int r = warp; r < D; r += 8) {
+    for (int r = warp; r < D; r += SOLVE_THREADS / 32) {
       double s = 0;
-      for (int c = lane; c < D; c += 32) s += a.HM[(size_t)r * D + c] * delta[c];
+      for (int c = lane; c < D; c += 32) s += HMsrc[(size_t)r * D + c] * delta[c];
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) hmd[r] = s;
     }
@@ -62,12 +241,10 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
   }
   if (tid < D) {
     const int r = tid;
-    const double pr = r < 4 ? cPrior[r] : fprior[r - 4];
-    const double dpr = r < 4 ? (double)a.cDeltaF[r] : fdp[r - 4];
-    const double bt = a.btop[r], scb = a.accSC[(size_t)r * DP + D], ht = a.Htop[(size_t)r * D + r], scd = a.accSC[(size_t)r * DP + r];
+    const double scb = Ssrc[(size_t)r * DP + D], ht = Hsrc[(size_t)r * D + r], scd = Ssrc[(size_t)r * DP + r];
     double v = bt + pr * dpr;                            // AccumulatedTopHessian.cpp:292-300 (the L pass carries the priors)
     double dg = ht + pr;
-    if (a.HM) { v += a.bM[r] + hmd[r]; dg += a.HM[(size_t)r * D + r]; }
+    if (a.HM) { v += bm + hmd[r]; dg += HMsrc[(size_t)r * D + r]; }
     v -= scb;
     bb[r] = v;
     if (a.bfinal) a.bfinal[r] = v;
@@ -90,115 +267,111 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
   }
   __syncthreads();
   SOLVE_TS(2);
-  // ---- assemble into registers ---------------------------------------------------------------------------
-  double reg[T][T];
-#pragma unroll
-  for (int ia = 0; ia < T; ia++) {
-    // one register-tile row at a time: indices, then all global loads of the row in flight, then the arithmetic
-    int er[T], ec[T];
-    double h1[T], h2[T], hs[T], hm[T];
-    const int i = ty + 16 * ia;
-#pragma unroll
-    for (int jb = 0; jb <= ia; jb++) {
-      const int j = tx + 16 * jb;
-      const bool ok = i < D && j <= i;
-      int r = perm[ok ? i : 0], c = perm[ok ? j : 0];
-      if (r < c) { const int t = r; r = c; c = t; }
-      er[jb] = r; ec[jb] = c;
+  // ---- assemble the permuted, scaled lower triangle (+ rhs row) in shared memory, then pull the register tiles ------
+  // rows r and D-1-r together hold D+1 lower-triangle entries: a branch-free enumeration of exactly D(D+1)/2 entries
+  {
+    const int total = (D >> 1) * DP;
+#pragma unroll 5
+    for (int e = tid; e < total; e += SOLVE_THREADS) {
+      const int rr = e / DP, cc = e - rr * DP;
+      const bool lo = cc <= rr;
+      const int i = lo ? rr : D - 1 - rr, j = lo ? cc : cc - rr - 1;
+      const int pi = perm[i], pj = perm[j];
+      const int r = max(pi, pj), c = min(pi, pj);
+      const double h1 = Hsrc[(size_t)r * D + c], h2 = Hsrc[(size_t)c * D + r];
+      const double hs = Ssrc[(size_t)c * DP + r];
+      const double hm = a.HM ? HMsrc[(size_t)r * D + c] : 0.0;
+      const bool offdiag = c >= 4 && ((r - 4) >> 3) != ((c - 4) >> 3);   // AccumulatedTopHessian.h:107-126 epilogue
+      double u = (offdiag ? h1 + h2 : h1) + hm;
+      u -= hs * sc;
+      u = r == c ? dtmp[r] : u;
+      if (a.Hfinal) { a.Hfinal[(size_t)r * D + c] = u; a.Hfinal[(size_t)c * D + r] = u; }
+      As[i * D + j] = S[r] * u * S[c];
     }
-#pragma unroll
-    for (int jb = 0; jb <= ia; jb++) {
-      const int r = er[jb], c = ec[jb];
-      h1[jb] = a.Htop[(size_t)r * D + c];
-      h2[jb] = a.Htop[(size_t)c * D + r];
-      hs[jb] = a.accSC[(size_t)c * DP + r];
-      hm[jb] = a.HM ? a.HM[(size_t)r * D + c] : 0.0;
-    }
-#pragma unroll
-    for (int jb = 0; jb < T; jb++) {
-      double v = 0.0;
-      if (jb <= ia) {
-        const int j = tx + 16 * jb;
-        if (i == D && j < D) {
-          const int c = perm[j];
-          v = S[c] * bb[c];
-        } else if (i < D && j <= i) {
-          const int r = er[jb], c = ec[jb];
-          double u;
-          if (r == c) u = dtmp[r];
-          else {
-            const bool offdiag = c >= 4 && ((r - 4) >> 3) != ((c - 4) >> 3);   // AccumulatedTopHessian.h:107-126 epilogue
-            u = (offdiag ? h1[jb] + h2[jb] : h1[jb]) + hm[jb];
-            u -= hs[jb] * sc;
-          }
-          if (a.Hfinal) { a.Hfinal[(size_t)r * D + c] = u; a.Hfinal[(size_t)c * D + r] = u; }
-          v = S[r] * u * S[c];
-        }
-      }
-      reg[ia][jb] = v;
-    }
+    for (int j = tid; j < D; j += SOLVE_THREADS) { const int c = perm[j]; As[D * D + j] = S[c] * bb[c]; }
   }
+  __syncthreads();
   SOLVE_TS(3);
-  // ---- right-looking LDL^T, one barrier per column ------------------------------------------------------------
+  // ---- right-looking LDL^T in panels of 4 columns with look-ahead ---------------------------------------------------
+  // update warps (tid < 256) own the trailing tiles in registers; panel warps (tid >= 256) own one row each of the
+  // current panel.  BAR_PUB: panel p published (update -> panel), BAR_LY: L/Y of panel p ready (panel -> update).
+  const int npanels = D >> 2;
+  if (tid < SOLVE_UPD) {
+    double reg[T][T];
 #pragma unroll
-  for (int kb = 0; kb < T; kb++) {     // column block: static, so every register index below is a constant
-    for (int km = 0; km < 16; km++) {
-      const int k = 16 * kb + km;
-      if (k >= D) break;
-      double *cb = col + (k & 1) * (D + 2);
-      if (tx == km) {
+    for (int ia = 0; ia < T; ia++)
 #pragma unroll
-        for (int ia = kb; ia < T; ia++) {
-          const int i = ty + 16 * ia;
-          const double v = reg[ia][kb];
-          if (i > k && i <= D) cb[i] = v;
-          if (i == k) s_dk[k & 1] = __drcp_rn(v);
-        }
+      for (int jb = 0; jb < T; jb++) {
+        const int i = ty + 16 * ia, j = tx + 16 * jb;
+        reg[ia][jb] = (jb <= ia && i <= D && j < D && j <= i) ? As[i * D + j] : 0.0;
       }
-      __syncthreads();
-      const double rcp0 = s_dk[k & 1];
-      const double rcp = isfinite(rcp0) ? rcp0 : 0.0;   // zero pivot: leave the column (Eigen: pivot_is_valid)
-      double li[T], cj[T];
+    if (tx < 4) {
 #pragma unroll
-      for (int ia = kb; ia < T; ia++) { const int i = ty + 16 * ia; li[ia] = (i > k && i <= D) ? cb[i] * rcp : 0.0; }
-#pragma unroll
-      for (int jb = kb; jb < T; jb++) { const int j = tx + 16 * jb; cj[jb] = (j > k && j < D) ? cb[j] : 0.0; }
-#pragma unroll
-      for (int ia = kb; ia < T; ia++)
-#pragma unroll
-        for (int jb = kb; jb <= ia; jb++) reg[ia][jb] -= li[ia] * cj[jb];   // entries outside the trailing block see li or cj == 0
-      if (tx == km) {
-#pragma unroll
-        for (int ia = kb; ia < T; ia++)
-          if (ty + 16 * ia > k) reg[ia][kb] = li[ia];   // keep the unit-lower factor in place
+      for (int ia = 0; ia < T; ia++) {
+        const int i = ty + 16 * ia;
+        if (i >= tx) pan[i * 4 + tx] = reg[ia][0];
       }
+    }
+    for (int e = tid; e < D * PST; e += SOLVE_UPD) M[e] = 0.0;   // the staged H is consumed: the region becomes the factor storage
+    nb_arrive(BAR_PUB);
+#pragma unroll 1
+    for (int kb = 0; 4 * kb < npanels; kb++) {
+      const int nact = (DP - 16 * kb + 15) >> 4;   // live tile rows (rows <= D)
+#pragma unroll 1
+      for (int q = 0; q < 4; q++) {
+        const int p = 4 * kb + q;
+        if (p >= npanels) break;
+        if (p + 1 == npanels) { nb_sync(BAR_LY); break; }   // nothing left to update: the rhs row was finished by the panel warps
+        long long *dbg = (a.dbg && tid == 0 && p >= 4 && p < 6) ? a.dbg + 16 + 8 * (p - 4) + 3 : nullptr;
+        UpdateDispatch<T, T>::run(nact, q == 3, reg, M + (size_t)p * PST * 4, Yb + (size_t)(p & 1) * (16 * T) * 4,
+                                  pan + (size_t)((p + 1) & 1) * (16 * T) * 4, kb, q, ty, tx, dbg);
+        if (dbg) dbg[2] = clock64() + (long long)(reg[T - 1][T - 1] == 123.0);
+      }
+      // next 16 columns: tile (a,b) takes over from tile (a+1,b+1)
+#pragma unroll
+      for (int ia = 0; ia < T - 1; ia++)
+#pragma unroll
+        for (int jb = 0; jb <= ia; jb++) reg[ia][jb] = reg[ia + 1][jb + 1];
+#pragma unroll
+      for (int jb = 0; jb < T; jb++) reg[T - 1][jb] = 0.0;
+    }
+  } else {
+    const int pt = tid - SOLVE_UPD;
+#pragma unroll 1
+    for (int p = 0; p < npanels; p++) {
+      long long *dbg = (a.dbg && pt == 8 && p >= 4 && p < 6) ? a.dbg + 16 + 8 * (p - 4) : nullptr;
+      panel_rows(pan + (size_t)(p & 1) * (16 * T) * 4, M + (size_t)p * PST * 4, Yb + (size_t)(p & 1) * (16 * T) * 4, D, 4 * p, pt, dbg);
+      if (dbg) dbg[2] = clock64();
+      nb_arrive(BAR_LY);
     }
   }
   SOLVE_TS(4);
-  // ---- spill the factor, back substitution L^T w = z in one warp ----------------------------------------------
-#pragma unroll
-  for (int ia = 0; ia < T; ia++)
-#pragma unroll
-    for (int jb = 0; jb < T; jb++) {
-      const int i = ty + 16 * ia, j = tx + 16 * jb;
-      if (i < D && j < i) M[i * LD + j] = reg[ia][jb];
-      if (i == D && j < D) z[j] = reg[ia][jb];
-    }
+  // ---- back substitution L^T w = z in one warp (lane l keeps rows l, l+32, ...), the next row of L always in flight.
+  // L[j][i] sits at M4[i >> 2][j][i & 3]; the rhs row D holds z.
   __syncthreads();
   if (warp == 0) {
     constexpr int W = (16 * T + 31) / 32;
-    double w[W];
+    double w[W], Ln[W];
+    int off[W];   // offset of column (lane + 32 m) inside a factor row
 #pragma unroll
-    for (int m = 0; m < W; m++) { const int i = lane + 32 * m; w[m] = i < D ? z[i] : 0.0; }
+    for (int m = 0; m < W; m++) {
+      const int i = lane + 32 * m;
+      off[m] = (i >> 2) * PST * 4 + (i & 3);
+      w[m] = i < D ? M[off[m] + D * 4] : 0.0;
+      Ln[m] = i < D - 1 ? M[off[m] + (D - 1) * 4] : 0.0;
+    }
+#pragma unroll 1
     for (int j = D - 1; j > 0; j--) {
       const int jm = j >> 5, jl = j & 31;
+      double Lc[W];
+#pragma unroll
+      for (int m = 0; m < W; m++) { Lc[m] = Ln[m]; const int i = lane + 32 * m; Ln[m] = (j > 1 && i < j - 1) ? M[off[m] + (j - 1) * 4] : 0.0; }
       double own = 0.0;
 #pragma unroll
       for (int m = 0; m < W; m++) own = m == jm ? w[m] : own;
       const double wj = __shfl_sync(0xffffffffu, own, jl);
-      const double *Lj = M + j * LD;
 #pragma unroll
-      for (int m = 0; m < W; m++) { const int i = lane + 32 * m; if (i < j) w[m] -= Lj[i] * wj; }
+      for (int m = 0; m < W; m++) w[m] = fma(-Lc[m], wj, w[m]);   // Lc is 0 for i >= j
     }
 #pragma unroll
     for (int m = 0; m < W; m++) { const int i = lane + 32 * m; if (i < D) z[i] = w[m]; }
@@ -207,13 +380,13 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
   SOLVE_TS(5);
   double *y = key;   // x in original order
   bool bad = false;
-  for (int j = tid; j < D; j += 256) { const int r = perm[j]; const double xi = S[r] * z[j]; y[r] = xi; a.x[r] = xi; if (!isfinite(xi)) bad = true; }
+  for (int j = tid; j < D; j += SOLVE_THREADS) { const int r = perm[j]; const double xi = S[r] * z[j]; y[r] = xi; a.x[r] = xi; if (!isfinite(xi)) bad = true; }
   if (bad && a.status) a.status[0] = 1;
   __syncthreads();
   SOLVE_TS(6);
   // ---- xAd (EnergyFunctional.cpp:509-513) and xc ------------------------------------------------------
   if (a.xAd) {
-    for (int e = tid; e < nf * nf * 8; e += 256) {
+    for (int e = tid; e < nf * nf * 8; e += SOLVE_THREADS) {
       const int c = e & 7, ht = e >> 3, h = ht / nf, t = ht % nf;   // xAd index = h*nf + t
       const float *AhF = a.adHostF + 64 * (size_t)(h + nf * t), *AtF = a.adTargetF + 64 * (size_t)(h + nf * t);
       float ah[8], at[8];
@@ -221,13 +394,145 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
       for (int k = 0; k < 8; k++) { ah[k] = __ldg(AhF + k * 8 + c); at[k] = __ldg(AtF + k * 8 + c); }
       float sh = 0.f, st = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; k++) { sh += (float)y[4 + 8 * h + k] * ah[k]; st += (float)y[4 + 8 * t + k] * at[k]; }
+      for (int k = 0; k < 8; k++) { sh = fmaf((float)y[4 + 8 * h + k], ah[k], sh); st = fmaf((float)y[4 + 8 * t + k], at[k], st); }
       a.xAd[e] = sh + st;
     }
     if (tid < 4) a.xAd[(size_t)nf * nf * 8 + tid] = (float)y[tid];
   }
   SOLVE_TS(7);
+  // ---- frames / calibration part of doStepFromBackup, new precalc and deltas (same CTA, no extra launch) ---------
+  if (a.do_step) {
+    __syncthreads();
+    frame_step_body(a.step);
+  }
+  SOLVE_TS(8);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Frames / calibration part of one Gauss-Newton step on the device (single CTA, fp64):
+//   EnergyFunctional::resubstituteF_MT frame+calib steps (:500-507), FullSystem::backupState (:260-271),
+//   doStepFromBackup frames+calib (:185-257), FrameHessian::setState (HessianBlocks.h:217-230),
+//   FrameFramePrecalc::set (HessianBlocks.cpp:431-461), setDeltaF (EnergyFunctional.cpp:163-194).
+// Mirrors host_ba.cpp (same float operation order); keeps the whole iteration on the stream with no host round trip.
+__device__ __forceinline__ void d_mul33f(const float *A, const float *B, float *C) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) C[3 * i + j] = (A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j]) + A[3 * i + 2] * B[6 + j];
+}
+
+__device__ void frame_step_body(const StepArgs &a) {
+  using namespace sosba_math;
+  __shared__ double s_fs[16 * SOSBA_FS];
+  __shared__ Rigid s_c2w[16], s_w2c[16];
+  __shared__ double s_scaled[16][2];
+  __shared__ float s_K[4];
+  const int nf = a.nf, tid = threadIdx.x;
+  const double SC_T = 0.5, SC_R = 1.0, SC_A = 10.0, SC_B = 1000.0, SC_F = 50.0, SC_C = 50.0;
+  for (int e = tid; e < nf * SOSBA_FS; e += blockDim.x) s_fs[e] = a.fs[e];
+  __syncthreads();
+  if (tid < nf) {
+    double *F = s_fs + SOSBA_FS * tid;
+    double *G = a.fs + SOSBA_FS * tid;
+    double *state = F + 12, *backup = F + 32, *step = F + 42;
+    for (int i = 0; i < 8; i++) step[i] = -a.x[4 + 8 * tid + i];
+    step[8] = step[9] = 0.0;
+    double scaled[10];
+    for (int i = 0; i < 10; i++) {
+      backup[i] = state[i];
+      state[i] = backup[i] + (double)a.stepfac * step[i];
+      G[12 + i] = state[i]; G[32 + i] = backup[i]; G[42 + i] = step[i];
+    }
+    for (int i = 0; i < 3; i++) scaled[i] = SC_T * state[i];
+    for (int i = 3; i < 6; i++) scaled[i] = SC_R * state[i];
+    scaled[6] = SC_A * state[6]; scaled[7] = SC_B * state[7]; scaled[8] = SC_A * state[8]; scaled[9] = SC_B * state[9];
+    const Rigid ev = rigid_from34(F);
+    const Rigid c2w = rigid_mul(rigid_exp(scaled), ev);
+    s_c2w[tid] = c2w;
+    s_w2c[tid] = rigid_inverse(c2w);
+    s_scaled[tid][0] = scaled[6]; s_scaled[tid][1] = scaled[7];
+    for (int i = 0; i < 8; i++) {
+      a.wprior[4 + 8 * nf + 8 * tid + i] = state[i];                 // delta_prior = state - getPriorZero() (== 0)
+      a.wprior[4 + 16 * nf + 8 * tid + i] = state[i] - F[22 + i];    // delta = state - state_zero
+    }
+  }
+  if (tid == 32) {  // calibration: CalibHessian::setValue (HessianBlocks.h:487-501)
+    double *C = a.cs;   // value[4] | value_zero[4] | value_backup[4] | step[4]
+    float sf[4];
+    for (int i = 0; i < 4; i++) {
+      C[12 + i] = -a.x[i];
+      C[8 + i] = C[i];
+      C[i] = C[8 + i] + (double)a.stepfac * C[12 + i];
+      sf[i] = (float)((i < 2 ? SC_F : SC_C) * C[i]);
+      s_K[i] = sf[i];
+      a.calib[i] = sf[i];
+      a.calib[6 + i] = (float)(C[i] - C[4 + i]);
+    }
+    a.calib[4] = 1.0f / sf[0];
+    a.calib[5] = 1.0f / sf[1];
+  }
+  __syncthreads();
+  if (tid == 64) {  // step norms of doStepFromBackup, float accumulation in frame order
+    float sumA = 0, sumB = 0, sumT = 0, sumR = 0;
+    for (int f = 0; f < nf; f++) {
+      const double *st = s_fs + SOSBA_FS * f + 42;
+      sumA += st[6] * st[6];
+      sumB += st[7] * st[7];
+      sumT += st[0] * st[0] + st[1] * st[1] + st[2] * st[2];
+      sumR += st[3] * st[3] + st[4] * st[4] + st[5] * st[5];
+    }
+    a.iter[0] = sumA / nf; a.iter[1] = sumB / nf; a.iter[2] = sumT / nf; a.iter[3] = sumR / nf;
+  }
+  const float fx = s_K[0], fy = s_K[1], cx = s_K[2], cy = s_K[3];
+  const float K[9] = {fx, 0, cx, 0, fy, cy, 0, 0, 1};
+  const float Ki[9] = {1.0f / fx, 0, -cx / fx, 0, 1.0f / fy, -cy / fy, 0, 0, 1};
+  for (int e = tid; e < nf * nf; e += blockDim.x) {
+    const int h = e / nf, t = e % nf;
+    const double *Fh = s_fs + SOSBA_FS * h, *Ft = s_fs + SOSBA_FS * t;
+    // setDeltaF first (its 32 float4 adjoint loads are in flight while the fp64 rigid algebra runs)
+    const int idx = h + t * nf;
+    const float4 *AhF = (const float4 *)(a.adHostF + 64 * (size_t)idx), *AtF = (const float4 *)(a.adTargetF + 64 * (size_t)idx);
+    float4 rh[16], rt[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) { rh[q] = __ldg(AhF + q); rt[q] = __ldg(AtF + q); }
+    float pre[SOSBA_PRECALC_FLOATS];
+    const Rigid l0 = rigid_mul(rigid_inverse(rigid_from34(Ft)), rigid_from34(Fh));
+    for (int i = 0; i < 9; i++) pre[SOSBA_PC_RTLL0 + i] = (float)l0.R[i];
+    for (int i = 0; i < 3; i++) pre[SOSBA_PC_TTLL0 + i] = (float)l0.t[i];
+    const Rigid l = rigid_mul(s_w2c[t], s_c2w[h]);
+    float R[9], tt[3], KR[9];
+    for (int i = 0; i < 9; i++) R[i] = (float)l.R[i];
+    for (int i = 0; i < 3; i++) tt[i] = (float)l.t[i];
+    d_mul33f(K, R, KR);
+    d_mul33f(KR, Ki, pre + SOSBA_PC_KRKI);
+    for (int i = 0; i < 3; i++) pre[SOSBA_PC_KT + i] = (K[3 * i] * tt[0] + K[3 * i + 1] * tt[1]) + K[3 * i + 2] * tt[2];
+    float expF = (float)Fh[52], expT = (float)Ft[52];     // AffLight::fromToVecExposure (NumType.h:157-168)
+    if (expF == 0 || expT == 0) expT = expF = 1;
+    const double aa = exp(s_scaled[t][0] - s_scaled[h][0]) * expT / expF;
+    const double bbv = s_scaled[t][1] - aa * s_scaled[h][1];
+    pre[SOSBA_PC_AFF] = (float)aa;
+    pre[SOSBA_PC_AFF + 1] = (float)bbv;
+    pre[SOSBA_PC_B0] = (float)(Fh[22 + 7] * SC_B);
+    pre[SOSBA_PC_DIST] = (float)sqrt(l.t[0] * l.t[0] + l.t[1] * l.t[1] + l.t[2] * l.t[2]);
+    pre[28] = pre[29] = pre[30] = pre[31] = 0.f;
+    float4 *p4 = (float4 *)(a.precalc + (size_t)e * SOSBA_PRECALC_FLOATS);
+#pragma unroll
+    for (int q = 0; q < 8; q++) p4[q] = make_float4(pre[4 * q], pre[4 * q + 1], pre[4 * q + 2], pre[4 * q + 3]);
+    // adHTdeltaF[h + t*nf] = delta_h^T adHostF + delta_t^T adTargetF, summed over k in order
+    float sh[8] = {0, 0, 0, 0, 0, 0, 0, 0}, st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float dh = (float)(Fh[12 + k] - Fh[22 + k]), dt = (float)(Ft[12 + k] - Ft[22 + k]);
+      const float4 h0 = rh[2 * k], h1 = rh[2 * k + 1], t0 = rt[2 * k], t1 = rt[2 * k + 1];
+      sh[0] += dh * h0.x; sh[1] += dh * h0.y; sh[2] += dh * h0.z; sh[3] += dh * h0.w;
+      sh[4] += dh * h1.x; sh[5] += dh * h1.y; sh[6] += dh * h1.z; sh[7] += dh * h1.w;
+      st[0] += dt * t0.x; st[1] += dt * t0.y; st[2] += dt * t0.z; st[3] += dt * t0.w;
+      st[4] += dt * t1.x; st[5] += dt * t1.y; st[6] += dt * t1.z; st[7] += dt * t1.w;
+    }
+    float4 *o4 = (float4 *)(a.adHTdeltaF + 8 * (size_t)idx);
+    o4[0] = make_float4(sh[0] + st[0], sh[1] + st[1], sh[2] + st[2], sh[3] + st[3]);
+    o4[1] = make_float4(sh[4] + st[4], sh[5] + st[5], sh[6] + st[6], sh[7] + st[7]);
+  }
+}
+
 
 // resubstitute with a caller-provided x: only the xAd part of the kernel above
 __global__ void __launch_bounds__(256) k_make_xad(const double *__restrict__ x, int nf, const float *__restrict__ adHostF,
@@ -245,22 +550,45 @@ __global__ void __launch_bounds__(256) k_make_xad(const double *__restrict__ x, 
 
 }  // namespace
 
-size_t solve_smem_bytes(int D) { return ((size_t)D * (D + 1) + 6 * (size_t)D + 2 * (size_t)(D + 2) + 8) * sizeof(double); }
+static size_t solve_smem_base(int D, int T) {   // factor storage, As, six D-vectors, panel + Y buffers (all even counts: 16-byte alignment holds)
+  return ((size_t)D * (16 * T + 1) + (size_t)(D + 1) * D + 6 * (size_t)D + 4 * (size_t)(16 * T) * 4) * sizeof(double);
+}
 
-void launch_solve(sosba *h, const SolveArgs &a) {
-  const size_t smem = solve_smem_bytes(a.D);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(k_solve<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_solve<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_solve<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
+template <int T>
+static int launch_solve_t(sosba *h, SolveArgs &a) {
+  static size_t dyn_max = 0;   // per instantiation: opt-in limit minus the kernel's static shared memory
+  if (!dyn_max) {
+    int dev = 0, optin = 0;
+    cudaFuncAttributes fa;
+    SOSBA_CUDA(cudaGetDevice(&dev));
+    SOSBA_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    SOSBA_CUDA(cudaFuncGetAttributes(&fa, k_solve<T>));
+    const size_t lim = (size_t)optin - fa.sharedSizeBytes - 1024;
+    SOSBA_CUDA(cudaFuncSetAttribute(k_solve<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+    dyn_max = lim;
   }
-  const int T = (a.D + 1 + 15) / 16;
-  if (T <= 5) k_solve<5><<<1, 256, smem, h->stream>>>(a);
-  else if (T <= 7) k_solve<7><<<1, 256, smem, h->stream>>>(a);
-  else k_solve<9><<<1, 256, smem, h->stream>>>(a);
+  const int D = a.D;
+  // stage accSC (and HM) in shared memory when they fit beside the factor
+  size_t smem = solve_smem_base(D, T);
+  const size_t bytesS = ((((size_t)D + 1) * (D + 1) + 1) & ~(size_t)1) * 8;
+  a.stage_sc = a.stage_hm = 0;
+  if (smem + bytesS <= dyn_max) { a.stage_sc = 1; smem += bytesS; }
+  if (a.stage_sc && a.HM && smem + (size_t)D * D * 8 <= dyn_max) { a.stage_hm = 1; smem += (size_t)D * D * 8; }
+  if (smem > dyn_max) { sosba_set_error("window too large for the single-CTA solve (D=%d)", D); return SOSBA_E_ARG; }
+  k_solve<T><<<1, SOLVE_THREADS, smem, h->stream>>>(a);
+  SOSBA_CUDA(cudaGetLastError());
   h->launches++;
+  return SOSBA_OK;
+}
+
+int launch_solve(sosba *h, const SolveArgs &a0) {
+  SolveArgs a = a0;
+  if ((a.D & 3) || a.D + 1 > 16 * 7) { sosba_set_error("single-CTA solve supports 4 + 8 nf <= 108 (nf <= 13), got D=%d", a.D); return SOSBA_E_ARG; }
+  int T = (a.D + 1 + 15) / 16;
+  if (const char *f = getenv("SOSBA_SOLVE_FORCE_T")) T = std::max(T, atoi(f));   // debug: run a wider instantiation
+  if (T <= 3) return launch_solve_t<3>(h, a);
+  if (T <= 5) return launch_solve_t<5>(h, a);
+  return launch_solve_t<7>(h, a);
 }
 
 void launch_make_xad(sosba *h, const double *d_x, int nf, const float *adHostF, const float *adTargetF, float *xAd) {

@@ -55,7 +55,6 @@ struct StepArgs {
   double *wprior;
   double *iter;          // out: sumA, sumB, sumT, sumR (already / nf)
 };
-void launch_frame_step(sosba *h, const StepArgs &a);
 
 // tracker / scale optimizer (calcResPose / calcResScale): writes the 8 warped SoA arrays (masked, not
 // compacted: invalid points carry weight 0) and the sums
@@ -126,8 +125,11 @@ struct SolveArgs {
   float *xAd;                  // [nf*nf*8] then xc[4]
   int *status;                 // [0] non-finite flag
   long long *dbg;              // optional: clock64() at the phase boundaries (SOSBA_SOLVE_DEBUG)
+  int do_step;                 // also run the frames / calibration part of doStepFromBackup (FullSystemOptimize.cpp:185-257)
+  StepArgs step;
+  int stage_sc, stage_hm;      // set by launch_solve: accSC / HM staged in shared memory
 };
-void launch_solve(sosba *h, const SolveArgs &a);
+int launch_solve(sosba *h, const SolveArgs &a);
 
 struct ResubArgs {
   int P, nf;

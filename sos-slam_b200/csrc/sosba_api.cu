@@ -17,7 +17,6 @@
 #include "host_ba.h"
 #include "kernels.h"
 
-size_t solve_smem_bytes(int D);
 void launch_make_xad(sosba *h, const double *d_x, int nf, const float *adHostF, const float *adTargetF, float *xAd);
 void launch_scale_prior(sosba *h, float *priorF, const int *ids, int n, float fac);
 void launch_stitch_raw(sosba *h, const double *accTop2, const double *adHost, const double *adTarget, int nf, int ntables, double *H, double *b);
@@ -26,6 +25,8 @@ using sosba_host::BAState;
 using sosba_host::WindowTables;
 
 static thread_local char g_err[512] = "";
+static long long *g_dbg = nullptr;   // SOSBA_SOLVE_DEBUG: k_solve phase timestamps (clock64), 16 per launch
+static long g_dbg_n = 0;
 void sosba_set_error(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -191,6 +192,29 @@ API void sosba_destroy(sosba_t *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (g_dbg && g_dbg_n > 8) {
+    std::vector<long long> t(64 * 32);
+    cudaMemcpy(t.data(), g_dbg, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    const int n = (int)std::min<long>(g_dbg_n, 64);
+    fprintf(stderr, "k_solve phase cycles (median of last %d launches): ", n);
+    for (int ph = 1; ph < 9; ph++) {
+      std::vector<long long> v;
+      for (int k = 0; k < n; k++) v.push_back(t[32 * k + ph] - t[32 * k + ph - 1]);
+      std::sort(v.begin(), v.end());
+      fprintf(stderr, " %lld", v[v.size() / 2]);
+    }
+    std::vector<long long> v;
+    for (int k = 0; k < n; k++) v.push_back(t[32 * k + 8] - t[32 * k]);
+    std::sort(v.begin(), v.end());
+    fprintf(stderr, "  total %lld\n", v[v.size() / 2]);
+    {  // panels 4..6 of the last launch: [panel start, panel done, update start, update done] relative to panel 4's start
+      const long long *q = t.data() + 32 * ((g_dbg_n - 1) % 64) + 16;
+      fprintf(stderr, "k_solve look-ahead timeline, panels 4,5: [panel: data landed, chain done, stored | update: L/Y landed, published, rest done] (cycles):");
+      for (int i = 0; i < 16; i++) if ((i & 7) < 6) fprintf(stderr, " %lld%s", q[i] - q[0], (i & 7) == 2 ? " |" : (i & 7) == 5 ? " ||" : "");
+      fprintf(stderr, "\n");
+    }
+    g_dbg_n = 0;
+  }
   sosba_comm_destroy(h);
   HostSide *hs = HS(h);
   for (void *p : hs->allocs) cudaFree(p);
@@ -300,11 +324,12 @@ static int ensure_window(sosba *h, int nf) {
   {  // one scratch region zeroed by a single memset per solve: top tables (A | L), Schur Gram, H parts A | L | SC,
      // back-substitution sums [4], counters (ints) ; H part 3 (final system) follows and is never cleared
     const size_t HB = (size_t)D * D + D;
-    hs->scratch_doubles = 2 * n2 * SOSBA_TOPB + (size_t)(D + 1) * (D + 1) + 3 * HB + 4 + 4;
+    const size_t scpad = (((size_t)(D + 1) * (D + 1)) + 1) & ~(size_t)1;   // even: H, b behind it stay 16-byte aligned (TMA bulk copies in k_solve)
+    hs->scratch_doubles = 2 * n2 * SOSBA_TOPB + scpad + 3 * HB + 4 + 4;
     DALLOC(h, hs->d_scratch, hs->scratch_doubles + HB);
     h->d_accTop = hs->d_scratch;
     h->d_accSC = h->d_accTop + 2 * n2 * SOSBA_TOPB;
-    h->d_H = h->d_accSC + (size_t)(D + 1) * (D + 1);
+    h->d_H = h->d_accSC + scpad;
     hs->d_rstats = h->d_H + 3 * HB;
     hs->d_cnt = (int *)(hs->d_rstats + 4);                  // [0] resInA [1] resInL [2] non-finite status
     hs->d_Hfinal = hs->d_scratch + hs->scratch_doubles;
@@ -742,6 +767,17 @@ static ResubArgs resub_args(sosba *h, int do_step) {
   return r;
 }
 
+static StepArgs step_args(sosba *h) {
+  HostSide *hs = HS(h);
+  StepArgs st;
+  st.nf = h->nf; st.stepfac = 1.0f; st.x = h->d_x; st.fs = hs->d_fs; st.cs = hs->d_cs;
+  st.precalc = h->d_precalc; st.adHTdeltaF = h->d_adHTdeltaF; st.calib = h->d_calib;
+  st.adHostF = h->d_adHostF; st.adTargetF = h->d_adTargetF; st.wprior = h->d_wprior; st.iter = hs->d_iter;
+  return st;
+}
+
+// accumulate + stitch + solve + back-substitution; with do_step also backupState / doStepFromBackup of the points (in
+// k_resubstitute) and of the frames, calibration, precalc and deltas (fused into the tail of k_solve)
 static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int do_step, bool want_final = false) {
   HostSide *hs = HS(h);
   const int nf = h->nf, D = 4 + 8 * nf;
@@ -755,19 +791,15 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
   s.x = h->d_x; s.Hfinal = want_final ? Hpart(h, 3) : nullptr; s.bfinal = want_final ? bpart(h, 3) : nullptr;
   s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.xAd = h->d_xAd; s.status = hs->d_cnt + 2;
   s.dbg = nullptr;
-  if (getenv("SOSBA_SOLVE_DEBUG")) {
-    static long long *d_dbg = nullptr;
-    if (!d_dbg) cudaMalloc(&d_dbg, 64 * sizeof(long long));
-    s.dbg = d_dbg;
-    launch_solve(h, s);
-    long long t[8];
-    cudaMemcpyAsync(t, d_dbg, sizeof(t), cudaMemcpyDeviceToHost, h->stream);
-    cudaStreamSynchronize(h->stream);
-    fprintf(stderr, "k_solve cycles:");
-    for (int i = 1; i < 8; i++) fprintf(stderr, " %lld", t[i] - t[i - 1]);
-    fprintf(stderr, " total %lld\n", t[7] - t[0]);
-  } else
-  launch_solve(h, s);
+  s.do_step = do_step;
+  s.step = step_args(h);
+  s.stage_sc = s.stage_hm = 0;
+  static const bool solve_debug = getenv("SOSBA_SOLVE_DEBUG") != nullptr;
+  if (solve_debug) {   // phase timestamps of the last 64 launches, no host sync: read back and printed by sosba_destroy
+    if (!g_dbg) cudaMalloc(&g_dbg, 64 * 32 * sizeof(long long));
+    s.dbg = g_dbg + 32 * (g_dbg_n++ % 64);
+  }
+  if ((rc = launch_solve(h, s))) return rc;
   launch_resubstitute(h, resub_args(h, do_step));
   SOSBA_CUDA(cudaGetLastError());
   return SOSBA_OK;
@@ -1110,11 +1142,6 @@ static int enqueue_iteration(sosba *h) {
   HostSide *hs = HS(h);
   int rc = enqueue_solve(h, ba->have_HM ? hs->d_HMtmp : nullptr, ba->have_HM ? hs->d_bMtmp : nullptr, 1);
   if (rc) return rc;
-  StepArgs st;
-  st.nf = h->nf; st.stepfac = 1.0f; st.x = h->d_x; st.fs = hs->d_fs; st.cs = hs->d_cs;
-  st.precalc = h->d_precalc; st.adHTdeltaF = h->d_adHTdeltaF; st.calib = h->d_calib;
-  st.adHostF = h->d_adHostF; st.adTargetF = h->d_adTargetF; st.wprior = h->d_wprior; st.iter = hs->d_iter;
-  launch_frame_step(h, st);
   enqueue_linearize(h, 0);
   launch_apply_res(h, lin_args(h), 0);
   SOSBA_CUDA(cudaGetLastError());

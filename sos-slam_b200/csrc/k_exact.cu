@@ -100,11 +100,25 @@ __device__ __forceinline__ float4 pick4(int k, float4 c0, float4 c1, float4 c2, 
   return r;
 }
 
+__device__ void energy_th_body(const ThArgs &a);
+__device__ __forceinline__ float bfly8(unsigned mask, float v);
+
 // a3  one residual = 8 consecutive lanes (one per pattern sample); 32 residuals per 256-thread block.
+// APPLY: PointFrameResidual::applyRes(true) + EFResidual::takeDataF of the same residual fused in (the commit record is
+//        written straight from registers; FullSystemOptimize.cpp:363-372 runs linearizeAll then applyRes back to back).
+// WRITE_J: materialise the candidate RawResidualJacobian record and projectedTo (the Gauss-Newton loop needs neither).
+// TH: the last CTA to finish runs setNewFrameEnergyTH (FullSystemOptimize.cpp:84-124) — no separate launch.
+template <bool APPLY, bool WRITE_J, bool TH>
 __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
   __shared__ double s_energy;
   __shared__ int s_cnt[3];
+  __shared__ int s_last;
+  if (a.gate && *a.gate) return;   // the Gauss-Newton loop already converged (device-side break)
   if (threadIdx.x == 0) { s_energy = 0.0; s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; }
+  if (a.zero_n > 0) {              // clear the block tables of the accumulation that follows (one memset less on the stream)
+    double2 *zb = (double2 *)a.zero_buf;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.zero_n; i += gridDim.x * blockDim.x) zb[i] = make_double2(0.0, 0.0);
+  }
   __syncthreads();
 
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -232,6 +246,7 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
           if (a.affModeB < 0) jab1 = 0;
 
           // candidate record: PointFrameResidual::J
+          if (WRITE_J) {
           float *J = (a.r_sel[r] ? a.J1 : a.J0) + (size_t)r * SOSBA_JREC;
           J[JR_RES + idx] = resF;
           J[JR_JIDX0 + idx] = hx;
@@ -253,6 +268,7 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
           }
           a.proj[(size_t)r * 16 + idx * 2] = Ku;
           a.proj[(size_t)r * 16 + idx * 2 + 1] = Kv;
+          }
 
           energyWO = energyLeft0;
           float energyLeft = energyLeft0;
@@ -260,6 +276,32 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
           if (energyLeft > th || wJI2_sum < 2) { energyLeft = th; outcome = SOSBA_RES_OUTLIER; }
           else outcome = SOSBA_RES_IN;
           ret_energy = energyLeft;
+          if (APPLY && outcome == SOSBA_RES_IN) {   // EFResidual::takeDataF on the registers of this linearisation
+            const float JI_r0 = bfly8(gmask, resF * hx), JI_r1 = bfly8(gmask, resF * hy);
+            const float Jab_r0 = bfly8(gmask, resF * jab0), Jab_r1 = bfly8(gmask, resF * jab1), rr = bfly8(gmask, resF * resF);
+            float *rec = a.rec + (size_t)r * SOSBA_CREC;
+            if (idx == 0) *(float4 *)(rec + CR_X) = make_float4(d_C_x[0], d_C_x[1], d_C_x[2], d_C_x[3]);
+            if (idx == 1) { *(float4 *)(rec + CR_X + 4) = make_float4(d_xi_x[0], d_xi_x[1], d_xi_x[2], d_xi_x[3]); *(float2 *)(rec + CR_X + 8) = make_float2(d_xi_x[4], d_xi_x[5]); }
+            if (idx == 2) { *(float2 *)(rec + CR_Y) = make_float2(d_C_y[0], d_C_y[1]); *(float2 *)(rec + CR_Y + 2) = make_float2(d_C_y[2], d_C_y[3]); }
+            if (idx == 3) { *(float2 *)(rec + CR_Y + 4) = make_float2(d_xi_y[0], d_xi_y[1]); *(float4 *)(rec + CR_Y + 6) = make_float4(d_xi_y[2], d_xi_y[3], d_xi_y[4], d_xi_y[5]); }
+            if (idx == 4) {
+              *(float4 *)(rec + CR_A) = make_float4(JIdxJIdx_00, JIdxJIdx_10, JIdxJIdx_11, JabJIdx_00);
+              *(float4 *)(rec + CR_TR + 1) = make_float4(JabJIdx_01, JabJIdx_10, JabJIdx_11, JI_r0);
+              rec[CR_TR + 5] = JI_r1;
+            }
+            if (idx == 5) {
+              rec[CR_BR + 0] = JabJab_00; rec[CR_BR + 1] = JabJab_01; rec[CR_BR + 2] = Jab_r0;
+              *(float4 *)(rec + CR_BR + 3) = make_float4(JabJab_11, Jab_r1, rr, d_d_x);
+              rec[CR_JPDD + 1] = d_d_y;
+            }
+            const float v0 = JIdxJIdx_00 * d_d_x + JIdxJIdx_10 * d_d_y, v1 = JIdxJIdx_10 * d_d_x + JIdxJIdx_11 * d_d_y;
+            float jp;
+            if (idx < 6) jp = (idx == 0 ? d_xi_x[0] : idx == 1 ? d_xi_x[1] : idx == 2 ? d_xi_x[2] : idx == 3 ? d_xi_x[3] : idx == 4 ? d_xi_x[4] : d_xi_x[5]) * v0 +
+                              (idx == 0 ? d_xi_y[0] : idx == 1 ? d_xi_y[1] : idx == 2 ? d_xi_y[2] : idx == 3 ? d_xi_y[3] : idx == 4 ? d_xi_y[4] : d_xi_y[5]) * v1;
+            else if (idx == 6) jp = JabJIdx_00 * d_d_x + JabJIdx_01 * d_d_y;
+            else jp = JabJIdx_10 * d_d_x + JabJIdx_11 * d_d_y;
+            rec[CR_JPJDF + idx] = jp;
+          }
           if (idx == 0) {
             a.r_new_energy[r] = energyLeft;
             a.center[(size_t)r * 3 + 0] = cKu; a.center[(size_t)r * 3 + 1] = cKv; a.center[(size_t)r * 3 + 2] = c_new_idepth;
@@ -271,11 +313,19 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
         }
       }
     }
+    if (APPLY && WRITE_J) __syncwarp(gmask);   // every lane has used r_sel before lane 0 flips it
     if (idx == 0) {
       a.r_new_state[r] = (uint8_t)outcome;
       a.r_new_energy_wo[r] = energyWO;
       atomicAdd(&s_energy, (double)ret_energy);
       atomicAdd(&s_cnt[outcome], 1);
+      if (APPLY && a.r_state[r] != SOSBA_RES_OOB) {   // applyRes(true): "can never go back from OOB" (Residuals.cpp:306-309)
+        a.r_is_active[r] = outcome == SOSBA_RES_IN ? 1 : 0;
+        a.r_state[r] = (uint8_t)outcome;
+        // state_energy = state_NewEnergy, which a linearisation that left early (new state OOB) did not refresh
+        a.r_energy[r] = outcome == SOSBA_RES_OOB ? a.r_new_energy[r] : ret_energy;
+        if (WRITE_J && outcome == SOSBA_RES_IN) a.r_sel[r] ^= 1;   // std::swap(J, data->J)
+      }
     }
   }
   __syncthreads();
@@ -284,6 +334,18 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
     if (s_cnt[0]) atomicAdd(&a.counts[0], s_cnt[0]);
     if (s_cnt[1]) atomicAdd(&a.counts[1], s_cnt[1]);
     if (s_cnt[2]) atomicAdd(&a.counts[2], s_cnt[2]);
+  }
+  if (TH) {   // last CTA done: the newest-frame energies of every CTA are in place
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = atomicAdd(a.ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      energy_th_body(a.th);
+      if (threadIdx.x == 0) *a.ticket = 0;
+    }
   }
 }
 
@@ -443,7 +505,7 @@ __global__ void __launch_bounds__(256) k_prep_records(LinArgs a, int mode, const
 // ------------------------------------------------------------------------------------------------
 // setNewFrameEnergyTH: exact k-th smallest (nth_element) by 4-pass radix select on the bit patterns of the
 // (non-negative) energies.  One CTA; the list is at most one entry per active point.
-__global__ void __launch_bounds__(1024) k_energy_th(ThArgs a) {
+__device__ void energy_th_body(const ThArgs &a) {
   __shared__ unsigned hist[256];
   __shared__ unsigned s_prefix, s_k;
   const int n = a.counts[4];
@@ -492,6 +554,7 @@ __global__ void __launch_bounds__(1024) k_energy_th(ThArgs a) {
     a.thOut[0] = th;
   }
 }
+__global__ void __launch_bounds__(1024) k_energy_th(ThArgs a) { energy_th_body(a); }
 
 // ------------------------------------------------------------------------------------------------
 // a14 / a17  one thread per reference point.  The warped buffers are written in place (index i) with
@@ -599,7 +662,15 @@ void launch_make_images(sosba *h, int slot, const float *d_color, const float *d
 void launch_linearize(sosba *h, const LinArgs &a) {
   if (a.R == 0) return;
   const int blocks = (a.R * 8 + 255) / 256;
-  k_linearize<<<blocks, 256, 0, h->stream>>>(a);
+  k_linearize<false, true, false><<<blocks, 256, 0, h->stream>>>(a);
+  h->launches++;
+}
+// linearizeAll(false) + setNewFrameEnergyTH + applyRes(true) in one launch (the loop body of FullSystem::optimize)
+void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j) {
+  if (a.R == 0) { k_energy_th<<<1, 256, 0, h->stream>>>(a.th); h->launches++; return; }
+  const int blocks = (a.R * 8 + 255) / 256;
+  if (write_j) k_linearize<true, true, true><<<blocks, 256, 0, h->stream>>>(a);
+  else k_linearize<true, false, true><<<blocks, 256, 0, h->stream>>>(a);
   h->launches++;
 }
 void launch_apply_res(sosba *h, const LinArgs &a, int fix) {

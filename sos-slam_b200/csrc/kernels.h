@@ -4,6 +4,15 @@
 #include "sosba_internal.h"
 
 // ---- k_exact.cu ---------------------------------------------------------------------------------
+// setNewFrameEnergyTH: k-th smallest of newE[0..counts[4]) -> frameEnergyTH[nf-1], thOut[0]
+struct ThArgs {
+  const float *newE;
+  int *counts;
+  float *frameEnergyTH;
+  int nf;
+  float thN, thFacMedian, thConstWeight, overallWeight;
+  float *thOut;
+};
 struct LinArgs {
   int R, nf;
   const int *r_point, *r_target, *r_host;
@@ -22,25 +31,23 @@ struct LinArgs {
   double *stats;      // [0] energy
   int *counts;        // 0 in, 1 oob, 2 outlier, 3 removed, 4 n newest-frame energies
   float *newE;        // newest-frame energies (unordered)
+  // fused variants (launch_linearize_apply)
+  ThArgs th;          // setNewFrameEnergyTH in the last CTA
+  int *ticket;        // CTA completion counter (self-resetting)
+  const int *gate;    // non-null: skip the launch when *gate != 0 (the loop broke on the device)
+  double *zero_buf;   // non-null: zero_n double2 to clear (block tables of the next accumulation)
+  int zero_n;
 };
 
 void launch_make_images(sosba *h, int slot, const float *d_color, const float *d_B);
 void launch_linearize(sosba *h, const LinArgs &a);
+void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j);
 void launch_apply_res(sosba *h, const LinArgs &a, int fix);
 void launch_reset_oob(sosba *h, const LinArgs &a);
 void launch_fix_linearization(sosba *h, const LinArgs &a, const int *d_ids, int n);
 // mode 1: linearised residuals (resApprox = res_toZeroF + J*delta), mode 2: marginalisation (res_toZeroF);
 // list==nullptr -> all residuals.  Rewrites the commit record of every selected residual.
 void launch_prep_records(sosba *h, const LinArgs &a, int mode, const int *d_list, int n);
-// setNewFrameEnergyTH: k-th smallest of newE[0..counts[4]) -> frameEnergyTH[nf-1], thOut[0]
-struct ThArgs {
-  const float *newE;
-  int *counts;
-  float *frameEnergyTH;
-  int nf;
-  float thN, thFacMedian, thConstWeight, overallWeight;
-  float *thOut;
-};
 void launch_energy_th(sosba *h, const ThArgs &a);
 
 // frames + calibration part of a Gauss-Newton step, device resident

@@ -56,7 +56,8 @@ struct HostSide {
   double *d_scratch = nullptr, *d_rstats = nullptr, *d_Hfinal = nullptr;
   double *d_fs = nullptr, *d_cs = nullptr, *d_iter = nullptr;   // device-resident frame / calibration state of the GN loop
   int *d_cnt = nullptr;
-  size_t scratch_doubles = 0;
+  size_t scratch_doubles = 0, scratch_zero_doubles = 0;   // all of it / the part the fused linearize clears (tables + H parts)
+  bool tables_clean = false;
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;   // (start, stop) pairs around the linearize kernel
 };
@@ -331,6 +332,7 @@ static int ensure_window(sosba *h, int nf) {
     h->d_accSC = h->d_accTop + 2 * n2 * SOSBA_TOPB;
     h->d_H = h->d_accSC + scpad;
     hs->d_rstats = h->d_H + 3 * HB;
+    hs->scratch_zero_doubles = (size_t)(hs->d_rstats - hs->d_scratch) & ~(size_t)1;
     hs->d_cnt = (int *)(hs->d_rstats + 4);                  // [0] resInA [1] resInL [2] non-finite status
     hs->d_Hfinal = hs->d_scratch + hs->scratch_doubles;
   }
@@ -519,6 +521,11 @@ static LinArgs lin_args(sosba *h) {
   a.w = h->cfg.w; a.wM3G = (float)(h->cfg.w - 3); a.hM3G = (float)(h->cfg.h - 3);
   a.huberTH = h->cfg.huber_th; a.outlierTHSum = h->cfg.outlier_th_sum_component; a.affModeA = h->cfg.affine_opt_mode_a; a.affModeB = h->cfg.affine_opt_mode_b;
   a.stats = h->d_stats; a.counts = h->d_counts; a.newE = h->d_newE;
+  a.th.newE = h->d_newE; a.th.counts = h->d_counts; a.th.frameEnergyTH = h->d_frameEnergyTH; a.th.nf = h->nf;
+  a.th.thN = h->cfg.frame_energy_th_n; a.th.thFacMedian = h->cfg.frame_energy_th_fac_median; a.th.thConstWeight = h->cfg.frame_energy_th_const_weight;
+  a.th.overallWeight = h->cfg.overall_energy_th_weight; a.th.thOut = h->d_thOut;
+  a.ticket = h->d_counts + 12;
+  a.gate = nullptr; a.zero_buf = nullptr; a.zero_n = 0;
   return a;
 }
 
@@ -545,11 +552,7 @@ static void enqueue_linearize(sosba *h, int fix) {
   } else {
     launch_linearize(h, a);
   }
-  ThArgs t;
-  t.newE = h->d_newE; t.counts = h->d_counts; t.frameEnergyTH = h->d_frameEnergyTH; t.nf = h->nf;
-  t.thN = h->cfg.frame_energy_th_n; t.thFacMedian = h->cfg.frame_energy_th_fac_median; t.thConstWeight = h->cfg.frame_energy_th_const_weight;
-  t.overallWeight = h->cfg.overall_energy_th_weight; t.thOut = h->d_thOut;
-  launch_energy_th(h, t);
+  launch_energy_th(h, a.th);
   if (fix) launch_apply_res(h, a, 1);
 }
 
@@ -709,7 +712,9 @@ static int enqueue_blocks(sosba *h) {
   HostSide *hs = HS(h);
   const int nf = h->nf;
   const size_t n2 = (size_t)nf * nf;
-  cudaMemsetAsync(hs->d_scratch, 0, sizeof(double) * hs->scratch_doubles, h->stream);
+  if (!hs->tables_clean) cudaMemsetAsync(hs->d_scratch, 0, sizeof(double) * hs->scratch_doubles, h->stream);
+  else cudaMemsetAsync(hs->d_rstats, 0, sizeof(double) * 8, h->stream);   // back-substitution sums + counters only
+  hs->tables_clean = false;
   AccArgs a;
   a.R = h->R; a.P = h->P; a.nf = nf; a.n_list = h->R; a.list = h->r_by_block; a.mode = 0;
   a.r_point = h->r_point; a.r_target = h->r_target; a.r_host = h->r_host;
@@ -1137,16 +1142,34 @@ static int download_frame_state(sosba *h) {
 // one loop body of FullSystem::optimize (FullSystemOptimize.cpp:358-413), enqueued on the stream with no host
 // round trip: backupState + solveSystemF + doStepFromBackup (points in k_resubstitute, frames/calib/precalc in
 // k_frame_step) + linearizeAll(false) + applyRes
+static void enqueue_linearize_apply(sosba *h, bool zero_tables);
 static int enqueue_iteration(sosba *h) {
   BA *ba = h->ba;
   HostSide *hs = HS(h);
   int rc = enqueue_solve(h, ba->have_HM ? hs->d_HMtmp : nullptr, ba->have_HM ? hs->d_bMtmp : nullptr, 1);
   if (rc) return rc;
-  enqueue_linearize(h, 0);
-  launch_apply_res(h, lin_args(h), 0);
+  enqueue_linearize_apply(h, true);
   SOSBA_CUDA(cudaGetLastError());
   ba->iterations_done++;
   return SOSBA_OK;
+}
+
+// linearizeAll(false) + applyRes in ONE launch (threshold in its last CTA); also clears the block tables for the
+// accumulation of the next loop body
+static void enqueue_linearize_apply(sosba *h, bool zero_tables) {
+  HostSide *hs = HS(h);
+  cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(double) + 5 * sizeof(int), h->stream);
+  LinArgs a = lin_args(h);
+  if (zero_tables) { a.zero_buf = hs->d_scratch; a.zero_n = (int)(hs->scratch_zero_doubles / 2); }
+  if (hs->prof_on) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, h->stream);
+    launch_linearize_apply(h, a, false);
+    cudaEventRecord(e1, h->stream);
+    hs->prof_ev.push_back(e0); hs->prof_ev.push_back(e1);
+  } else launch_linearize_apply(h, a, false);
+  hs->tables_clean = zero_tables;
 }
 
 // read back what the host needs to decide `canbreak` (doStepFromBackup's return value) after an iteration

@@ -1,0 +1,83 @@
+// energy_th.cuh — FullSystem::setNewFrameEnergyTH (FullSystemOptimize.cpp:84-124) as a CTA-wide device function:
+// exact k-th smallest (std::nth_element) of the newest-frame residual energies by a 4-pass radix select on the bit
+// patterns of the (non-negative) floats.  The values are read from global memory once (kept in registers when the list
+// fits 8 per thread), histogram updates are aggregated per warp (most energies share their top byte).
+// Included by k_exact.cu (stand-alone launch, last CTA of the linearisation) and k_accum.cu (spare CTA of the
+// accumulation); the float formula uses explicit _rn intrinsics so both translation units round identically.
+#pragma once
+#include "kernels.h"
+
+__device__ __forceinline__ void energy_th_hist_add(unsigned *hist, unsigned bin, bool valid) {
+  const unsigned act = __ballot_sync(0xffffffffu, valid);   // called by whole warps
+  if (!valid) return;
+  const unsigned peers = __match_any_sync(act, bin);
+  if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+}
+
+__device__ inline void energy_th_body(const ThArgs &a) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_prefix, s_k;
+  const int n = a.counts[4];
+  const unsigned *v = (const unsigned *)a.newE;
+  const int nt = blockDim.x;
+  if (n == 0) {
+    if (threadIdx.x == 0) { a.frameEnergyTH[a.nf - 1] = 12 * 12 * 8; a.thOut[0] = 12 * 12 * 8; }
+    return;
+  }
+  constexpr int KEEP = 8;
+  unsigned mine[KEEP];
+  const bool cached = n <= KEEP * nt;
+  if (cached) {
+#pragma unroll
+    for (int q = 0; q < KEEP; q++) { const int i = threadIdx.x + q * nt; mine[q] = i < n ? v[i] : 0u; }
+  }
+  if (threadIdx.x == 0) { s_prefix = 0; s_k = (unsigned)(int)(a.thN * n); }
+  for (int pass = 3; pass >= 0; pass--) {
+    for (int i = threadIdx.x; i < 256; i += nt) hist[i] = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix, shift = 8 * pass;
+    const unsigned himask = pass == 3 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    if (cached) {
+#pragma unroll
+      for (int q = 0; q < KEEP; q++) {
+        const int i = threadIdx.x + q * nt;
+        const unsigned x = mine[q];
+        energy_th_hist_add(hist, (x >> shift) & 255u, i < n && (x & himask) == prefix);
+      }
+    } else {
+      for (int i0 = 0; i0 < n; i0 += nt) {
+        const int i = i0 + threadIdx.x;
+        const unsigned x = i < n ? v[i] : 0u;
+        energy_th_hist_add(hist, (x >> shift) & 255u, i < n && (x & himask) == prefix);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // warp 0: find the bin holding rank s_k (8 bins per lane, inclusive scan over lanes)
+      const unsigned lane = threadIdx.x;
+      unsigned c[8], tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) { c[q] = hist[8 * lane + q]; tot += c[q]; }
+      unsigned incl = tot;
+      for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += u; }
+      const unsigned excl = incl - tot, k = s_k;
+      const bool own = k >= excl && k < incl;
+      __syncwarp();
+      if (own) {
+        unsigned kk = k - excl, b = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { if (kk >= c[q] && b == (unsigned)q) { kk -= c[q]; b = q + 1; } }
+        s_k = kk; s_prefix = prefix | ((8 * lane + b) << shift);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float nthElement = sqrtf(__uint_as_float(s_prefix));
+    float th = __fmul_rn(nthElement, a.thFacMedian);
+    th = __fadd_rn(__fmul_rn(26.0f, a.thConstWeight), __fmul_rn(th, __fsub_rn(1.0f, a.thConstWeight)));
+    th = __fmul_rn(th, th);
+    th = __fmul_rn(th, __fmul_rn(a.overallWeight, a.overallWeight));
+    a.frameEnergyTH[a.nf - 1] = th;
+    a.thOut[0] = th;
+  }
+}

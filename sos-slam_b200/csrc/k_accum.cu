@@ -17,6 +17,7 @@
 // done as a register-tiled SYRK over 32-point tiles in shared memory — nf^3 8x8 blocks never exist.
 #include <math.h>
 
+#include "energy_th.cuh"
 #include "kernels.h"
 
 namespace {
@@ -262,6 +263,244 @@ __global__ void __launch_bounds__(256) k_point_sc(SCArgs a, int DP, int DPAD, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused accumulation of one Gauss-Newton iteration (accumulateAF_MT + accumulateLF_MT + accumulateSCF_MT,
+// EnergyFunctional.cpp:197-254) over tiles of SC_TP points: the commit records of the tile's residuals (contiguous,
+// point-major) arrive in shared memory by ONE TMA bulk copy and are read from there by all three consumers:
+//   top blocks   warp w walks target t = w, w+8, ... over the tile's points (same host for a whole tile in practice:
+//                points are listed host by host), 91 block entries in registers, flushed with fp64 red.global
+//   point sums   8 lanes per point (Hdd / bd / Hcd, A and L), HdiF, bdSumF, and g
+//   Schur        register-tiled SYRK acc += w g g^T in stitched space
+// The last CTA of the grid does not accumulate: it runs the pending setNewFrameEnergyTH selection of the preceding
+// linearisation, off the critical path.
+__device__ __forceinline__ unsigned smem_u32a(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256) k_accumulate_fused(FusedAccArgs a, int DP, int DPAD, int ntiles4, int tiles_total, int max_res) {
+  extern __shared__ __align__(16) float smem[];
+  if (a.gate && *a.gate) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (a.do_th && blockIdx.x == gridDim.x - 1) { energy_th_body(a.th); return; }
+  const int nf = a.nf, D = a.D;
+  float *Rs = smem;                                   // [max_res][SOSBA_CREC]
+  float *Gs = Rs + (size_t)max_res * SOSBA_CREC;      // [SC_TP][DPAD]
+  float *Ws = Gs + SC_TP * DPAD;                      // [SC_TP]
+  int *slot = (int *)(Ws + SC_TP);                    // [SC_TP][nf] residual (tile-local) of (point, target) or -1
+  int *s_host = slot + SC_TP * nf;                    // [SC_TP]
+  int *s_rb = s_host + SC_TP;                         // [SC_TP + 1]
+  unsigned char *s_flag = (unsigned char *)(s_rb + SC_TP + 1);   // [max_res] bit0 use, bit1 linearised
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ int s_nacc[2];
+  const int nt4 = DPAD / 4;
+  int my_ti[SC_MAXT], my_tj[SC_MAXT];
+  float acc[SC_MAXT][16];
+#pragma unroll
+  for (int m = 0; m < SC_MAXT; m++) {
+    int t = tid + m * 256;
+    my_ti[m] = -1; my_tj[m] = 0;
+    if (t < ntiles4) {
+      int ti = 0, base = 0;
+      while (t >= base + (nt4 - ti)) { base += nt4 - ti; ti++; }
+      my_ti[m] = ti; my_tj[m] = ti + (t - base);
+    }
+#pragma unroll
+    for (int q = 0; q < 16; q++) acc[m][q] = 0.f;
+  }
+  const EntryDesc d0 = entry_desc(lane), d1 = entry_desc(lane + 32), d2 = entry_desc(lane + 64);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32a(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_nacc[0] = s_nacc[1] = 0;
+  }
+  const int lp = tid >> 3, sub = tid & 7;
+  const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
+  unsigned phase = 0;
+  const int nworkers = a.do_th ? gridDim.x - 1 : gridDim.x;
+
+  for (int tile = blockIdx.x; tile < tiles_total; tile += nworkers) {
+    const int p0 = tile * SC_TP, np = min(SC_TP, a.P - p0);
+    __syncthreads();   // previous tile fully consumed (and the mbarrier initialised)
+    const int rb = a.res_begin[p0], nres = a.res_begin[p0 + np] - rb;
+    if (tid == 0 && nres > 0) {
+      const unsigned bytes = (unsigned)nres * SOSBA_CREC * 4u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32a(&mbar)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32a(Rs)),
+                   "l"(a.rec + (size_t)rb * SOSBA_CREC), "r"(bytes), "r"(smem_u32a(&mbar))
+                   : "memory");
+    }
+    for (int i = tid; i < SC_TP * DPAD; i += 256) Gs[i] = 0.f;
+    for (int i = tid; i < SC_TP * nf; i += 256) slot[i] = -1;
+    if (tid < SC_TP) { Ws[tid] = 0.f; s_host[tid] = tid < np ? a.p_host[p0 + tid] : 0; }
+    if (tid <= SC_TP) s_rb[tid] = a.res_begin[p0 + min(tid, np)] - rb;
+    for (int i = tid; i < nres; i += 256) {
+      const int r = rb + i;
+      const bool use = a.r_is_active[r] && !a.r_dropped[r];
+      s_flag[i] = (unsigned char)((use ? 1 : 0) | (a.r_is_lin[r] ? 2 : 0));
+    }
+    __syncthreads();
+    for (int i = tid; i < nres; i += 256) {   // (point, target) -> residual; a point has at most one residual per target
+      int pl = 0;
+      while (pl + 1 < np && s_rb[pl + 1] <= i) pl++;   // tile-local point of residual i (<= 32 steps, usually few)
+      slot[pl * nf + a.r_target[rb + i]] = i;
+    }
+    __syncthreads();
+    if (nres > 0) {
+      unsigned done = 0;
+      while (!done)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_u32a(&mbar)), "r"(phase) : "memory");
+      phase ^= 1;
+    }
+    // ---- top blocks ------------------------------------------------------------------------------------------
+    {
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+      int cur = -1, nacc = 0, nA = 0, nL = 0;
+      auto flush = [&]() {
+        if (cur >= 0 && nacc > 0) {
+          double *dst = a.accTop + (size_t)cur * SOSBA_TOPB;
+          atomicAdd(dst + lane, (double)acc0);
+          atomicAdd(dst + lane + 32, (double)acc1);
+          if (lane + 64 < 91) atomicAdd(dst + lane + 64, (double)acc2);
+          if (lane == 31) atomicAdd(dst + 91, (double)nacc);
+        }
+        acc0 = acc1 = acc2 = 0.f; nacc = 0;
+      };
+      for (int t = warp; t < nf; t += 8) {
+        for (int pl = 0; pl < np; pl++) {
+          const int i = slot[pl * nf + t];
+          if (i < 0) continue;
+          const int f = s_flag[i];
+          if (!(f & 1)) continue;
+          const int key = (f >> 1) * nf * nf + s_host[pl] + t * nf;
+          if (key != cur) { flush(); cur = key; }
+          const float *rec = Rs + (size_t)i * SOSBA_CREC;
+          acc0 += entry_value(rec, d0);
+          acc1 += entry_value(rec, d1);
+          acc2 += entry_value(rec, d2);
+          nacc++;
+          if (f & 2) nL++; else nA++;
+        }
+      }
+      flush();
+      if (lane == 0) { if (nA) atomicAdd(&s_nacc[0], nA); if (nL) atomicAdd(&s_nacc[1], nL); }
+    }
+    // ---- point sums + g ------------------------------------------------------------------------------------
+    if (lp < np) {   // uniform across the 8 lanes of a point
+      const int p = p0 + lp;
+      const int lb = s_rb[lp], le = s_rb[lp + 1];
+      const int host = s_host[lp];
+      float *g = Gs + lp * DPAD;
+      float HddA = 0.f, bdA = 0.f, HcdA[4] = {0.f, 0.f, 0.f, 0.f}, HddL = 0.f, bdL = 0.f, HcdL[4] = {0.f, 0.f, 0.f, 0.f};
+      float gh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int ngood = 0;
+      for (int base = lb; base < le; base += 8) {   // one round for nf <= 9
+        const int i = base + sub;
+        const int f = i < le ? s_flag[i] : 0;
+        const bool use = f & 1;
+        const bool lin = use && (f & 2);
+        float c_bd = 0.f, c_Hdd = 0.f, c_Hcd[4] = {0.f, 0.f, 0.f, 0.f};
+        float sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (use) {
+          const float4 *rec4 = (const float4 *)(Rs + (size_t)i * SOSBA_CREC);
+          const float4 x03 = rec4[0];                    // CR_X 0..3
+          const float4 y_a = rec4[2], y_b = rec4[3];     // floats 8..15: x[8],x[9],y[0],y[1] | y[2],y[3],y[4],y[5]
+          const float4 f20 = rec4[5], f24 = rec4[6], f28 = rec4[7], f32 = rec4[8], f36 = rec4[9];
+          const float4 v03 = rec4[10], v47 = rec4[11];   // JpJdF
+          const float a00 = f20.x, a01 = f20.y, a11 = f20.z;               // CR_A 20..22
+          const float JI_r0 = f24.w, JI_r1 = f28.x;                         // CR_TR+4 = 27, 28
+          const float Jpdd0 = f32.w, Jpdd1 = f36.x;                         // CR_JPDD = 35, 36
+          const float v0 = a00 * Jpdd0 + a01 * Jpdd1, v1 = a01 * Jpdd0 + a11 * Jpdd1;  // JIdx2 * Jpdd
+          c_bd = JI_r0 * Jpdd0 + JI_r1 * Jpdd1;
+          c_Hdd = v0 * Jpdd0 + v1 * Jpdd1;
+          const float xs[4] = {x03.x, x03.y, x03.z, x03.w}, ys[4] = {y_a.z, y_a.w, y_b.x, y_b.y};
+#pragma unroll
+          for (int q = 0; q < 4; q++) c_Hcd[q] = xs[q] * v0 + ys[q] * v1;
+          const int t = a.r_target[rb + i];
+          const float4 *Ah = (const float4 *)(a.adHostF + 64 * (size_t)(host + t * nf));
+          const float4 *At = (const float4 *)(a.adTargetF + 64 * (size_t)(host + t * nf));
+          const float v[8] = {v03.x, v03.y, v03.z, v03.w, v47.x, v47.y, v47.z, v47.w};
+#pragma unroll
+          for (int row = 0; row < 8; row++) {
+            const float4 h0 = __ldg(Ah + 2 * row), h1 = __ldg(Ah + 2 * row + 1), t0 = __ldg(At + 2 * row), t1 = __ldg(At + 2 * row + 1);
+            sh[row] = h0.x * v[0] + h0.y * v[1] + h0.z * v[2] + h0.w * v[3] + h1.x * v[4] + h1.y * v[5] + h1.z * v[6] + h1.w * v[7];
+            const float st = t0.x * v[0] + t0.y * v[1] + t0.z * v[2] + t0.w * v[3] + t1.x * v[4] + t1.y * v[5] + t1.z * v[6] + t1.w * v[7];
+            atomicAdd(&g[4 + 8 * t + row], st);   // one residual per (point, target): uncontended
+          }
+        }
+        ngood += __popc(__ballot_sync(gmask, use) & gmask);
+        const int cnt = min(8, le - base);
+        for (int q = 0; q < cnt; q++) {   // residual-order sums (deterministic, reference order)
+          const bool ql = __shfl_sync(gmask, (int)lin, q, 8) != 0;
+          const float q_bd = __shfl_sync(gmask, c_bd, q, 8), q_Hdd = __shfl_sync(gmask, c_Hdd, q, 8);
+          if (ql) { bdL += q_bd; HddL += q_Hdd; } else { bdA += q_bd; HddA += q_Hdd; }
+#pragma unroll
+          for (int k = 0; k < 4; k++) { const float qc = __shfl_sync(gmask, c_Hcd[k], q, 8); if (ql) HcdL[k] += qc; else HcdA[k] += qc; }
+        }
+#pragma unroll
+        for (int row = 0; row < 8; row++) {
+          float sv = sh[row];
+          sv += __shfl_xor_sync(gmask, sv, 1, 8); sv += __shfl_xor_sync(gmask, sv, 2, 8); sv += __shfl_xor_sync(gmask, sv, 4, 8);
+          gh[row] += sv;
+        }
+      }
+      if (sub == 0) {
+        a.HddA[p] = HddA; a.bdA[p] = bdA; a.HddL[p] = HddL; a.bdL[p] = bdL;
+        *(float4 *)(a.HcdA + 4 * (size_t)p) = make_float4(HcdA[0], HcdA[1], HcdA[2], HcdA[3]);
+        *(float4 *)(a.HcdL + 4 * (size_t)p) = make_float4(HcdL[0], HcdL[1], HcdL[2], HcdL[3]);
+      }
+      if (ngood == 0) {
+        if (sub == 0) { a.HdiF[p] = 0.f; a.bdSumF[p] = 0.f; a.idepth_hessian[p] = 0.f; a.maxRelBaseline[p] = 0.f; }
+      } else {
+        float H = HddA + HddL + a.priorF[p];
+        if (H < 1e-10) H = 1e-10;
+        const float HdiF = (float)(1.0 / (double)H);
+        float bdSum = bdA + bdL;
+        if (a.shiftPriorToZero) bdSum += a.priorF[p] * a.deltaF[p];
+        if (sub == 0) {
+          a.HdiF[p] = HdiF; a.bdSumF[p] = bdSum; a.idepth_hessian[p] = H;
+          Ws[lp] = HdiF;
+          g[D] = bdSum;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (sub == q) g[q] = HcdA[q] + HcdL[q];
+#pragma unroll
+        for (int q = 0; q < 8; q++) if (sub == q) atomicAdd(&g[4 + 8 * host + q], gh[q]);
+      }
+    }
+    __syncthreads();
+    // ---- Schur: acc += w g g^T ----------------------------------------------------------------------------
+#pragma unroll
+    for (int m = 0; m < SC_MAXT; m++) {
+      if (my_ti[m] < 0) continue;
+      const int i0 = my_ti[m] * 4, j0 = my_tj[m] * 4;
+      for (int k = 0; k < np; k++) {
+        const float w = Ws[k];
+        if (w == 0.f) continue;
+        const float4 gi = *(const float4 *)(Gs + k * DPAD + i0);
+        const float4 gj = *(const float4 *)(Gs + k * DPAD + j0);
+        const float wi[4] = {gi.x * w, gi.y * w, gi.z * w, gi.w * w};
+        const float gjv[4] = {gj.x, gj.y, gj.z, gj.w};
+#pragma unroll
+        for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++) acc[m][ii * 4 + jj] += wi[ii] * gjv[jj];
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < SC_MAXT; m++) {
+    if (my_ti[m] < 0) continue;
+    const int i0 = my_ti[m] * 4, j0 = my_tj[m] * 4;
+#pragma unroll
+    for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        const int i = i0 + ii, j = j0 + jj;
+        if (i <= j && j < DP && acc[m][ii * 4 + jj] != 0.f) atomicAdd(a.accSC + (size_t)i * DP + j, (double)acc[m][ii * 4 + jj]);
+      }
+  }
+  __syncthreads();
+  if (tid < 2 && s_nacc[tid]) atomicAdd(a.n_acc + tid, s_nacc[tid]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // One CTA (64 threads) per (host,target) block: accH (13x13 fp64) -> H, b with the adjoint sandwich.
 __global__ void __launch_bounds__(64) k_stitch_top(const double *__restrict__ accTop, const double *__restrict__ adHost,
                                                    const double *__restrict__ adTarget, int nf, double *__restrict__ H, double *__restrict__ b) {
@@ -472,4 +711,27 @@ void launch_resubstitute(sosba *h, const ResubArgs &a) {
   if (a.P == 0) return;
   k_resubstitute<<<(a.P * 8 + 255) / 256, 256, 0, h->stream>>>(a);
   h->launches++;
+}
+
+// mode-0 accumulation (A, L and Schur tables) in one launch.  Returns false when the tile cannot be staged in shared
+// memory (the caller falls back to the separate kernels).
+bool launch_accumulate_fused(sosba *h, const FusedAccArgs &a, int max_res_per_tile) {
+  if (a.P == 0) return true;
+  const int DP = a.D + 1, DPAD = (DP + 3) / 4 * 4, nt4 = DPAD / 4;
+  const int ntiles4 = nt4 * (nt4 + 1) / 2;
+  if (ntiles4 > SC_MAXT * 256) return false;
+  const int tiles_total = (a.P + SC_TP - 1) / SC_TP;
+  const int max_res = max_res_per_tile > 0 ? max_res_per_tile : 1;
+  size_t smem = (size_t)max_res * SOSBA_CREC * 4 + (size_t)(SC_TP * DPAD + SC_TP) * 4 + (size_t)(SC_TP * a.nf + 2 * SC_TP + 1) * 4 + (size_t)max_res;
+  smem = (smem + 15) & ~(size_t)15;
+  if (smem > 200 * 1024) return false;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (cudaFuncSetAttribute(k_accumulate_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return false;
+    configured = 200 * 1024;
+  }
+  int workers = tiles_total < 2 * h->sm_count ? tiles_total : 2 * h->sm_count;
+  k_accumulate_fused<<<workers + (a.do_th ? 1 : 0), 256, smem, h->stream>>>(a, DP, DPAD, ntiles4, tiles_total, max_res);
+  h->launches++;
+  return true;
 }

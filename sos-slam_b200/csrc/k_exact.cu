@@ -14,6 +14,7 @@
 //   track_res            CoarseTracker::calcResPose / ScaleOptimizer::calcResScale   CoarseTracker.cpp:612-764, ScaleOptimizer.cpp:273-437
 #include <math.h>
 
+#include "energy_th.cuh"
 #include "host_math.h"
 #include "kernels.h"
 
@@ -100,7 +101,6 @@ __device__ __forceinline__ float4 pick4(int k, float4 c0, float4 c1, float4 c2, 
   return r;
 }
 
-__device__ void energy_th_body(const ThArgs &a);
 __device__ __forceinline__ float bfly8(unsigned mask, float v);
 
 // a3  one residual = 8 consecutive lanes (one per pattern sample); 32 residuals per 256-thread block.
@@ -503,57 +503,7 @@ __global__ void __launch_bounds__(256) k_prep_records(LinArgs a, int mode, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// setNewFrameEnergyTH: exact k-th smallest (nth_element) by 4-pass radix select on the bit patterns of the
-// (non-negative) energies.  One CTA; the list is at most one entry per active point.
-__device__ void energy_th_body(const ThArgs &a) {
-  __shared__ unsigned hist[256];
-  __shared__ unsigned s_prefix, s_k;
-  const int n = a.counts[4];
-  const unsigned *v = (const unsigned *)a.newE;
-  if (n == 0) {
-    if (threadIdx.x == 0) { a.frameEnergyTH[a.nf - 1] = 12 * 12 * 8; a.thOut[0] = 12 * 12 * 8; }
-    return;
-  }
-  if (threadIdx.x == 0) { s_prefix = 0; s_k = (unsigned)(int)(a.thN * n); }
-  for (int pass = 3; pass >= 0; pass--) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    const unsigned prefix = s_prefix, shift = 8 * pass;
-    const unsigned himask = pass == 3 ? 0u : (0xFFFFFFFFu << (shift + 8));
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      unsigned x = v[i];
-      if ((x & himask) == prefix) atomicAdd(&hist[(x >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {  // warp 0: find the bin holding rank s_k (8 bins per lane, inclusive scan over lanes)
-      const unsigned lane = threadIdx.x;
-      unsigned c[8], tot = 0;
-#pragma unroll
-      for (int q = 0; q < 8; q++) { c[q] = hist[8 * lane + q]; tot += c[q]; }
-      unsigned incl = tot;
-      for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += v; }
-      const unsigned excl = incl - tot, k = s_k;
-      const bool mine = k >= excl && k < incl;
-      __syncwarp();
-      if (mine) {
-        unsigned kk = k - excl, b = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) { if (kk >= c[q] && b == (unsigned)q) { kk -= c[q]; b = q + 1; } }
-        s_k = kk; s_prefix = prefix | ((8 * lane + b) << shift);
-      }
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    float nthElement = sqrtf(__uint_as_float(s_prefix));
-    float th = nthElement * a.thFacMedian;
-    th = 26.0f * a.thConstWeight + th * (1 - a.thConstWeight);
-    th = th * th;
-    th *= a.overallWeight * a.overallWeight;
-    a.frameEnergyTH[a.nf - 1] = th;
-    a.thOut[0] = th;
-  }
-}
+// setNewFrameEnergyTH: energy_th.cuh
 __global__ void __launch_bounds__(1024) k_energy_th(ThArgs a) { energy_th_body(a); }
 
 // ------------------------------------------------------------------------------------------------
@@ -666,11 +616,16 @@ void launch_linearize(sosba *h, const LinArgs &a) {
   h->launches++;
 }
 // linearizeAll(false) + setNewFrameEnergyTH + applyRes(true) in one launch (the loop body of FullSystem::optimize)
-void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j) {
-  if (a.R == 0) { k_energy_th<<<1, 256, 0, h->stream>>>(a.th); h->launches++; return; }
+void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j, bool th_inline) {
+  if (a.R == 0) { if (th_inline) { k_energy_th<<<1, 256, 0, h->stream>>>(a.th); h->launches++; } return; }
   const int blocks = (a.R * 8 + 255) / 256;
-  if (write_j) k_linearize<true, true, true><<<blocks, 256, 0, h->stream>>>(a);
-  else k_linearize<true, false, true><<<blocks, 256, 0, h->stream>>>(a);
+  if (write_j) {
+    if (th_inline) k_linearize<true, true, true><<<blocks, 256, 0, h->stream>>>(a);
+    else k_linearize<true, true, false><<<blocks, 256, 0, h->stream>>>(a);
+  } else {
+    if (th_inline) k_linearize<true, false, true><<<blocks, 256, 0, h->stream>>>(a);
+    else k_linearize<true, false, false><<<blocks, 256, 0, h->stream>>>(a);
+  }
   h->launches++;
 }
 void launch_apply_res(sosba *h, const LinArgs &a, int fix) {

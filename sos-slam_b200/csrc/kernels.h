@@ -41,7 +41,8 @@ struct LinArgs {
 
 void launch_make_images(sosba *h, int slot, const float *d_color, const float *d_B);
 void launch_linearize(sosba *h, const LinArgs &a);
-void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j);
+// th_inline: the last CTA runs setNewFrameEnergyTH; otherwise the caller schedules it (spare CTA of the next accumulation)
+void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j, bool th_inline);
 void launch_apply_res(sosba *h, const LinArgs &a, int fix);
 void launch_reset_oob(sosba *h, const LinArgs &a);
 void launch_fix_linearization(sosba *h, const LinArgs &a, const int *d_ids, int n);
@@ -111,6 +112,26 @@ struct SCArgs {
   double *accSC;     // [(D+1)*(D+1)] upper triangle
 };
 void launch_point_sc(sosba *h, const SCArgs &a);
+
+// accumulateAF_MT + accumulateLF_MT + accumulateSCF_MT of all points in one launch (k_accumulate_fused)
+struct FusedAccArgs {
+  int P, nf, D, R;
+  int shiftPriorToZero;
+  int do_th;           // the spare CTA runs the pending setNewFrameEnergyTH
+  const int *res_begin, *r_target, *p_host;
+  const uint8_t *r_is_lin, *r_is_active, *r_dropped;
+  const float *rec;
+  double *accTop;      // [2][nf*nf*92]: A | L
+  int *n_acc;          // [0] resInA [1] resInL
+  float *HddA, *bdA, *HcdA, *HddL, *bdL, *HcdL;
+  const float *priorF, *deltaF;
+  float *HdiF, *bdSumF, *idepth_hessian, *maxRelBaseline;
+  const float *adHostF, *adTargetF;
+  double *accSC;       // [(D+1)*(D+1)] upper triangle
+  ThArgs th;
+  const int *gate;
+};
+bool launch_accumulate_fused(sosba *h, const FusedAccArgs &a, int max_res_per_tile);
 
 // top blocks -> H (D*D), b (D): AccumulatedTopHessianSSE::stitchDoubleInternal + stitchDoubleMT epilogue
 void launch_stitch_top(sosba *h, const double *accTop, const double *adHost, const double *adTarget, int nf, double *H, double *b,

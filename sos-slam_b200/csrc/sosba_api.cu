@@ -58,6 +58,9 @@ struct HostSide {
   int *d_cnt = nullptr;
   size_t scratch_doubles = 0, scratch_zero_doubles = 0;   // all of it / the part the fused linearize clears (tables + H parts)
   bool tables_clean = false;
+  bool th_pending = false;      // setNewFrameEnergyTH of the last fused linearisation still to run
+  bool fused_acc_ok = false;    // every (point, target) pair holds at most one residual and a tile fits shared memory
+  int max_res_per_tile = 0;
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;   // (start, stop) pairs around the linearize kernel
 };
@@ -479,6 +482,19 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
     cnt[host[i] + t * nf + 1]++;
   }
   for (int p = 0; p < P; p++) hs->res_begin[p + 1] += hs->res_begin[p];
+  {  // the fused accumulation stages the residuals of 32 consecutive points and indexes them by (point, target)
+    hs->fused_acc_ok = true;
+    hs->max_res_per_tile = 0;
+    std::vector<int> seen(nf, -1);
+    for (int p = 0; p < P && hs->fused_acc_ok; p++)
+      for (int i = hs->res_begin[p]; i < hs->res_begin[p + 1]; i++) {
+        if (seen[r->target[i]] == p) { hs->fused_acc_ok = false; break; }
+        seen[r->target[i]] = p;
+      }
+    for (int p0 = 0; p0 < P; p0 += 32) hs->max_res_per_tile = std::max(hs->max_res_per_tile, hs->res_begin[std::min(P, p0 + 32)] - hs->res_begin[p0]);
+    hs->th_pending = false;
+    hs->tables_clean = false;
+  }
   for (int b = 0; b < nf * nf; b++) cnt[b + 1] += cnt[b];
   for (int i = 0; i < n; i++) by_block[cnt[host[i] + r->target[i] * nf]++] = i;   // stable counting sort by block
   std::vector<uint8_t> u8(n);
@@ -537,8 +553,17 @@ API int sosba_reset_oob(sosba_t *h) {
   return SOSBA_OK;
 }
 
+// the threshold selection of a fused linearisation that no accumulation picked up yet
+static void flush_pending_th(sosba *h) {
+  HostSide *hs = HS(h);
+  if (!hs->th_pending) return;
+  launch_energy_th(h, lin_args(h).th);
+  hs->th_pending = false;
+}
+
 // enqueue linearizeAll on the stream (no host sync)
 static void enqueue_linearize(sosba *h, int fix) {
+  flush_pending_th(h);
   cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(double) + 5 * sizeof(int), h->stream);
   LinArgs a = lin_args(h);
   HostSide *hs = HS(h);
@@ -559,6 +584,7 @@ static void enqueue_linearize(sosba *h, int fix) {
 static int read_linearize_out(sosba *h, sosba_linearize_out *out) {
   HostSide *hs = HS(h);
   int rc;
+  flush_pending_th(h);
   if ((rc = down(h, hs->pin_d, h->d_stats, 12))) return rc;   // energy | pad | counts[16] | thOut[4]
   if ((rc = sync(h))) return rc;
   if (out) {
@@ -715,6 +741,23 @@ static int enqueue_blocks(sosba *h) {
   if (!hs->tables_clean) cudaMemsetAsync(hs->d_scratch, 0, sizeof(double) * hs->scratch_doubles, h->stream);
   else cudaMemsetAsync(hs->d_rstats, 0, sizeof(double) * 8, h->stream);   // back-substitution sums + counters only
   hs->tables_clean = false;
+  bool fused = false;
+  if (hs->fused_acc_ok) {
+    if (hs->n_lin > 0) launch_prep_records(h, lin_args(h), 1, nullptr, h->R);
+    FusedAccArgs f;
+    f.P = h->P; f.nf = nf; f.D = 4 + 8 * nf; f.R = h->R; f.shiftPriorToZero = 1; f.do_th = hs->th_pending ? 1 : 0;
+    f.res_begin = h->p_res_begin; f.r_target = h->r_target; f.p_host = h->p_host;
+    f.r_is_lin = h->r_is_lin; f.r_is_active = h->r_is_active; f.r_dropped = h->r_dropped; f.rec = h->r_rec;
+    f.accTop = h->d_accTop; f.n_acc = hs->d_cnt;
+    f.HddA = h->p_HddA; f.bdA = h->p_bdA; f.HcdA = h->p_HcdA; f.HddL = h->p_HddL; f.bdL = h->p_bdL; f.HcdL = h->p_HcdL;
+    f.priorF = h->p_priorF; f.deltaF = h->p_deltaF; f.HdiF = h->p_HdiF; f.bdSumF = h->p_bdSumF; f.idepth_hessian = h->p_idepth_hessian;
+    f.maxRelBaseline = h->p_maxRelBaseline; f.adHostF = h->d_adHostF; f.adTargetF = h->d_adTargetF; f.accSC = h->d_accSC;
+    f.th = lin_args(h).th; f.gate = nullptr;
+    fused = launch_accumulate_fused(h, f, hs->max_res_per_tile);
+    if (fused) hs->th_pending = false;
+  }
+  if (!fused) {
+  flush_pending_th(h);
   AccArgs a;
   a.R = h->R; a.P = h->P; a.nf = nf; a.n_list = h->R; a.list = h->r_by_block; a.mode = 0;
   a.r_point = h->r_point; a.r_target = h->r_target; a.r_host = h->r_host;
@@ -728,6 +771,7 @@ static int enqueue_blocks(sosba *h) {
     launch_top_accumulate(h, l);
   }
   launch_point_sc(h, sc_args(h, 0, nullptr, 0, 1));
+  }
   return sosba_allreduce_acc(h);   // points are sharded across ranks: sum the block tables (identical on every rank afterwards)
 }
 
@@ -1158,17 +1202,20 @@ static int enqueue_iteration(sosba *h) {
 // accumulation of the next loop body
 static void enqueue_linearize_apply(sosba *h, bool zero_tables) {
   HostSide *hs = HS(h);
+  flush_pending_th(h);
   cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(double) + 5 * sizeof(int), h->stream);
   LinArgs a = lin_args(h);
   if (zero_tables) { a.zero_buf = hs->d_scratch; a.zero_n = (int)(hs->scratch_zero_doubles / 2); }
+  const bool th_inline = !hs->fused_acc_ok;   // otherwise the spare CTA of the next accumulation runs the selection
   if (hs->prof_on) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, h->stream);
-    launch_linearize_apply(h, a, false);
+    launch_linearize_apply(h, a, false, th_inline);
     cudaEventRecord(e1, h->stream);
     hs->prof_ev.push_back(e0); hs->prof_ev.push_back(e1);
-  } else launch_linearize_apply(h, a, false);
+  } else launch_linearize_apply(h, a, false, th_inline);
+  hs->th_pending = !th_inline;
   hs->tables_clean = zero_tables;
 }
 
@@ -1195,6 +1242,7 @@ API int sosba_ba_iterate(sosba_t *h, int32_t n, int32_t *n_res) {
   int rc;
   for (int i = 0; i < n; i++)
     if ((rc = enqueue_iteration(h))) return rc;
+  flush_pending_th(h);
   if ((rc = down(h, hs->pin_i, hs->d_cnt + 2, 1))) return rc;
   if ((rc = sync(h))) return rc;
   if (hs->pin_i[0]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }

@@ -47,6 +47,46 @@ __device__ __forceinline__ float entry_value(const float *s, const EntryDesc &d)
   return 0.f;
 }
 
+// The 91 entries of one block over the 32 lanes without divergence: every lane runs the same four expressions.
+//   q0: 10x10 entry `lane` (0..31)   q1: 10x10 entry 32 + lane (lane < 23)   tr: TopRight entry lane (< 30)   br: BotRight entry lane (< 6)
+// 10x10 entry (r,c) = x_r (a x_c + b y_c) + y_r (b x_c + c y_c)   (AccumulatorApprox::update, MatrixAccumulators.h:928-1050)
+struct LaneEntries {
+  int r0, c0, r1, c1, trp, trq, brk;   // clamped to valid offsets for idle lanes
+  bool v1, vtr, vbr;
+};
+__device__ __forceinline__ LaneEntries lane_entries(int lane) {
+  LaneEntries L;
+  EntryDesc d = entry_desc(lane);
+  L.r0 = d.p; L.c0 = d.q;
+  L.v1 = lane < 23;
+  d = entry_desc(L.v1 ? lane + 32 : 32);
+  L.r1 = d.p; L.c1 = d.q;
+  L.vtr = lane < 30;
+  L.trp = L.vtr ? lane / 3 : 0; L.trq = L.vtr ? lane % 3 : 0;
+  L.vbr = lane < 6;
+  L.brk = L.vbr ? lane : 0;
+  return L;
+}
+struct LaneAcc { float q0, q1, tr, br; };
+__device__ __forceinline__ void lane_accumulate(const float *__restrict__ s, const LaneEntries &L, LaneAcc &A) {
+  const float4 abc = *(const float4 *)(s + CR_A);   // a, b, c, (TR[0])
+  const float xr0 = s[CR_X + L.r0], yr0 = s[CR_Y + L.r0], xc0 = s[CR_X + L.c0], yc0 = s[CR_Y + L.c0];
+  const float xr1 = s[CR_X + L.r1], yr1 = s[CR_Y + L.r1], xc1 = s[CR_X + L.c1], yc1 = s[CR_Y + L.c1];
+  const float xp = s[CR_X + L.trp], yp = s[CR_Y + L.trp], t0 = s[CR_TR + 2 * L.trq], t1 = s[CR_TR + 2 * L.trq + 1];
+  const float bv = s[CR_BR + L.brk];
+  A.q0 += xr0 * (abc.x * xc0 + abc.y * yc0) + yr0 * (abc.y * xc0 + abc.z * yc0);
+  A.q1 += xr1 * (abc.x * xc1 + abc.y * yc1) + yr1 * (abc.y * xc1 + abc.z * yc1);
+  A.tr += xp * t0 + yp * t1;
+  A.br += bv;
+}
+__device__ __forceinline__ void lane_flush(double *__restrict__ dst, int lane, const LaneEntries &L, const LaneAcc &A, int n) {
+  atomicAdd(dst + lane, (double)A.q0);
+  if (L.v1) atomicAdd(dst + 32 + lane, (double)A.q1);
+  if (L.vtr) atomicAdd(dst + 55 + lane, (double)A.tr);
+  if (L.vbr) atomicAdd(dst + 85 + lane, (double)A.br);
+  if (lane == 31) atomicAdd(dst + 91, (double)n);
+}
+
 // One warp walks a contiguous chunk of the block-ordered residual list.
 constexpr int TOP_WARPS = 8;
 __global__ void __launch_bounds__(TOP_WARPS * 32) k_top_accumulate(AccArgs a, int chunk) {
@@ -55,20 +95,14 @@ __global__ void __launch_bounds__(TOP_WARPS * 32) k_top_accumulate(AccArgs a, in
   const int gw = blockIdx.x * TOP_WARPS + warp;
   const int k0 = gw * chunk, k1 = min(k0 + chunk, a.n_list);
   if (k0 >= k1) return;
-  const EntryDesc d0 = entry_desc(lane), d1 = entry_desc(lane + 32), d2 = entry_desc(lane + 64);
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  const LaneEntries LE = lane_entries(lane);
+  LaneAcc A = {0.f, 0.f, 0.f, 0.f};
   int cur = -1, nacc = 0, ntotal = 0;
   float *s = s_rec[warp];
 
   auto flush = [&]() {
-    if (cur >= 0 && nacc > 0) {
-      double *dst = a.accTop + (size_t)cur * SOSBA_TOPB;
-      atomicAdd(dst + lane, (double)acc0);
-      atomicAdd(dst + lane + 32, (double)acc1);
-      if (lane + 64 < 91) atomicAdd(dst + lane + 64, (double)acc2);
-      if (lane == 31) atomicAdd(dst + 91, (double)nacc);
-    }
-    acc0 = acc1 = acc2 = 0.f; nacc = 0;
+    if (cur >= 0 && nacc > 0) lane_flush(a.accTop + (size_t)cur * SOSBA_TOPB, lane, LE, A, nacc);
+    A.q0 = A.q1 = A.tr = A.br = 0.f; nacc = 0;
   };
 
   // software prefetch: the record of residual k+1 is in flight while k is accumulated
@@ -96,9 +130,7 @@ __global__ void __launch_bounds__(TOP_WARPS * 32) k_top_accumulate(AccArgs a, in
     s[lane] = c0;
     if (lane < SOSBA_CREC - 32) s[32 + lane] = c1;
     __syncwarp();
-    acc0 += entry_value(s, d0);
-    acc1 += entry_value(s, d1);
-    acc2 += entry_value(s, d2);
+    lane_accumulate(s, LE, A);
     nacc++; ntotal++;
   }
   flush();
@@ -274,7 +306,10 @@ __global__ void __launch_bounds__(256) k_point_sc(SCArgs a, int DP, int DPAD, in
 // linearisation, off the critical path.
 __device__ __forceinline__ unsigned smem_u32a(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(256) k_accumulate_fused(FusedAccArgs a, int DP, int DPAD, int ntiles4, int tiles_total, int max_res) {
+constexpr int ADJ_ST = 68;   // floats per staged 8x8 adjoint (64 + 4: float4 rows of different targets fall into different banks)
+
+constexpr int ACC_THREADS = 512;   // warps 0..7: point sums (8 lanes per point), warps 8..15: top blocks (one target each), concurrently
+__global__ void __launch_bounds__(ACC_THREADS) k_accumulate_fused(FusedAccArgs a, int DP, int DPAD, int ntiles4, int tiles_total, int max_res) {
   extern __shared__ __align__(16) float smem[];
   if (a.gate && *a.gate) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -283,10 +318,12 @@ __global__ void __launch_bounds__(256) k_accumulate_fused(FusedAccArgs a, int DP
   float *Rs = smem;                                   // [max_res][SOSBA_CREC]
   float *Gs = Rs + (size_t)max_res * SOSBA_CREC;      // [SC_TP][DPAD]
   float *Ws = Gs + SC_TP * DPAD;                      // [SC_TP]
-  int *slot = (int *)(Ws + SC_TP);                    // [SC_TP][nf] residual (tile-local) of (point, target) or -1
-  int *s_host = slot + SC_TP * nf;                    // [SC_TP]
-  int *s_rb = s_host + SC_TP;                         // [SC_TP + 1]
-  unsigned char *s_flag = (unsigned char *)(s_rb + SC_TP + 1);   // [max_res] bit0 use, bit1 linearised
+  float *Adh = Ws + SC_TP;                            // [nf][ADJ_ST] adHostF[h0 + t*nf]
+  float *Adt = Adh + nf * ADJ_ST;                     // [nf][ADJ_ST] adTargetF[h0 + t*nf]
+  int *s_rb = (int *)(Adt + nf * ADJ_ST);             // [SC_TP + 1]
+  unsigned short *s_list = (unsigned short *)(s_rb + SC_TP + 1);   // [nf][2][SC_TP] tile-local residuals per target: active | linearised
+  unsigned char *s_flag = (unsigned char *)(s_list + nf * 2 * SC_TP);   // [max_res] bit0 use, bit1 linearised
+  unsigned char *s_tgt = s_flag + max_res;            // [max_res]
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ int s_nacc[2];
   const int nt4 = DPAD / 4;
@@ -294,7 +331,7 @@ __global__ void __launch_bounds__(256) k_accumulate_fused(FusedAccArgs a, int DP
   float acc[SC_MAXT][16];
 #pragma unroll
   for (int m = 0; m < SC_MAXT; m++) {
-    int t = tid + m * 256;
+    int t = tid + m * ACC_THREADS;
     my_ti[m] = -1; my_tj[m] = 0;
     if (t < ntiles4) {
       int ti = 0, base = 0;
@@ -304,7 +341,7 @@ __global__ void __launch_bounds__(256) k_accumulate_fused(FusedAccArgs a, int DP
 #pragma unroll
     for (int q = 0; q < 16; q++) acc[m][q] = 0.f;
   }
-  const EntryDesc d0 = entry_desc(lane), d1 = entry_desc(lane + 32), d2 = entry_desc(lane + 64);
+  const LaneEntries LE = lane_entries(lane);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32a(&mbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -314,11 +351,13 @@ __global__ void __launch_bounds__(256) k_accumulate_fused(FusedAccArgs a, int DP
   const unsigned gmask = 0xFFu << ((tid & 31) & ~7);
   unsigned phase = 0;
   const int nworkers = a.do_th ? gridDim.x - 1 : gridDim.x;
-
+#define ACC_TS(n) do { if (a.dbg && blockIdx.x == 0 && tid == 32) a.dbg[n] = clock64(); } while (0)
+#define ACC_TS2(n) do { if (a.dbg && blockIdx.x == 0 && tid == 288) a.dbg[n] = clock64(); } while (0)
+  ACC_TS(0);
   for (int tile = blockIdx.x; tile < tiles_total; tile += nworkers) {
-    const int p0 = tile * SC_TP, np = min(SC_TP, a.P - p0);
+    const int4 td = a.tiles[tile];   // first point, points (<= SC_TP, one host), first residual, residuals
+    const int p0 = td.x, np = td.y, rb = td.z, nres = td.w;
     __syncthreads();   // previous tile fully consumed (and the mbarrier initialised)
-    const int rb = a.res_begin[p0], nres = a.res_begin[p0 + np] - rb;
     if (tid == 0 && nres > 0) {
       const unsigned bytes = (unsigned)nres * SOSBA_CREC * 4u;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32a(&mbar)), "r"(bytes) : "memory");
@@ -326,21 +365,21 @@ __global__ void __launch_bounds__(256) k_accumulate_fused(FusedAccArgs a, int DP
                    "l"(a.rec + (size_t)rb * SOSBA_CREC), "r"(bytes), "r"(smem_u32a(&mbar))
                    : "memory");
     }
-    for (int i = tid; i < SC_TP * DPAD; i += 256) Gs[i] = 0.f;
-    for (int i = tid; i < SC_TP * nf; i += 256) slot[i] = -1;
-    if (tid < SC_TP) { Ws[tid] = 0.f; s_host[tid] = tid < np ? a.p_host[p0 + tid] : 0; }
-    if (tid <= SC_TP) s_rb[tid] = a.res_begin[p0 + min(tid, np)] - rb;
-    for (int i = tid; i < nres; i += 256) {
+    const int host = a.p_host[p0];
+    for (int i = tid; i < nres; i += ACC_THREADS) {
       const int r = rb + i;
       const bool use = a.r_is_active[r] && !a.r_dropped[r];
       s_flag[i] = (unsigned char)((use ? 1 : 0) | (a.r_is_lin[r] ? 2 : 0));
+      s_tgt[i] = (unsigned char)a.r_target[r];
     }
-    __syncthreads();
-    for (int i = tid; i < nres; i += 256) {   // (point, target) -> residual; a point has at most one residual per target
-      int pl = 0;
-      while (pl + 1 < np && s_rb[pl + 1] <= i) pl++;   // tile-local point of residual i (<= 32 steps, usually few)
-      slot[pl * nf + a.r_target[rb + i]] = i;
+    for (int e = tid; e < nf * 16; e += ACC_THREADS) {   // the 2 x nf adjoints of this host, 16 float4 each
+      const int t = e >> 4, k = e & 15;
+      *(float4 *)(Adh + t * ADJ_ST + 4 * k) = __ldg((const float4 *)(a.adHostF + 64 * (size_t)(host + t * nf)) + k);
+      *(float4 *)(Adt + t * ADJ_ST + 4 * k) = __ldg((const float4 *)(a.adTargetF + 64 * (size_t)(host + t * nf)) + k);
     }
+    if (tid <= np) s_rb[tid] = a.res_begin[p0 + tid] - rb;
+    for (int i = tid; i < SC_TP * DPAD; i += ACC_THREADS) Gs[i] = 0.f;
+    if (tid < SC_TP) Ws[tid] = 0.f;
     __syncthreads();
     if (nres > 0) {
       unsigned done = 0;
@@ -348,44 +387,42 @@ __global__ void __launch_bounds__(256) k_accumulate_fused(FusedAccArgs a, int DP
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_u32a(&mbar)), "r"(phase) : "memory");
       phase ^= 1;
     }
-    // ---- top blocks ------------------------------------------------------------------------------------------
-    {
-      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-      int cur = -1, nacc = 0, nA = 0, nL = 0;
-      auto flush = [&]() {
-        if (cur >= 0 && nacc > 0) {
-          double *dst = a.accTop + (size_t)cur * SOSBA_TOPB;
-          atomicAdd(dst + lane, (double)acc0);
-          atomicAdd(dst + lane + 32, (double)acc1);
-          if (lane + 64 < 91) atomicAdd(dst + lane + 64, (double)acc2);
-          if (lane == 31) atomicAdd(dst + 91, (double)nacc);
+    ACC_TS(1);
+    // ---- top blocks: warp w compacts the residuals of target t = w, w+8, ... (a point has at most one) and sums them
+    if (warp >= 8) {
+      int nA = 0, nL = 0;
+      for (int t = warp - 8; t < nf; t += 8) {
+        unsigned short *lst = s_list + (size_t)t * 2 * SC_TP;
+        int cnt[2] = {0, 0};
+        for (int base = 0; base < nres; base += 32) {
+          const int i = base + lane;
+          const int f = i < nres && s_tgt[i] == t ? s_flag[i] : 0;
+#pragma unroll
+          for (int l = 0; l < 2; l++) {
+            const bool m = (f & 1) && ((f >> 1) == l);
+            const unsigned bal = __ballot_sync(0xffffffffu, m);
+            if (m) lst[l * SC_TP + cnt[l] + __popc(bal & ((1u << lane) - 1))] = (unsigned short)i;
+            cnt[l] += __popc(bal);
+          }
         }
-        acc0 = acc1 = acc2 = 0.f; nacc = 0;
-      };
-      for (int t = warp; t < nf; t += 8) {
-        for (int pl = 0; pl < np; pl++) {
-          const int i = slot[pl * nf + t];
-          if (i < 0) continue;
-          const int f = s_flag[i];
-          if (!(f & 1)) continue;
-          const int key = (f >> 1) * nf * nf + s_host[pl] + t * nf;
-          if (key != cur) { flush(); cur = key; }
-          const float *rec = Rs + (size_t)i * SOSBA_CREC;
-          acc0 += entry_value(rec, d0);
-          acc1 += entry_value(rec, d1);
-          acc2 += entry_value(rec, d2);
-          nacc++;
-          if (f & 2) nL++; else nA++;
+        __syncwarp();
+#pragma unroll
+        for (int l = 0; l < 2; l++) {
+          if (cnt[l] == 0) continue;
+          LaneAcc A = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+          for (int n = 0; n < cnt[l]; n++) lane_accumulate(Rs + (size_t)lst[l * SC_TP + n] * SOSBA_CREC, LE, A);
+          lane_flush(a.accTop + ((size_t)l * nf * nf + host + t * nf) * SOSBA_TOPB, lane, LE, A, cnt[l]);
         }
+        nA += cnt[0]; nL += cnt[1];
       }
-      flush();
       if (lane == 0) { if (nA) atomicAdd(&s_nacc[0], nA); if (nL) atomicAdd(&s_nacc[1], nL); }
+      ACC_TS2(2);
     }
-    // ---- point sums + g ------------------------------------------------------------------------------------
-    if (lp < np) {   // uniform across the 8 lanes of a point
+    // ---- point sums + g (warps 0..7, concurrently with the top blocks) ------------------------------------------
+    if (warp < 8 && lp < np) {   // uniform across the 8 lanes of a point
       const int p = p0 + lp;
       const int lb = s_rb[lp], le = s_rb[lp + 1];
-      const int host = s_host[lp];
       float *g = Gs + lp * DPAD;
       float HddA = 0.f, bdA = 0.f, HcdA[4] = {0.f, 0.f, 0.f, 0.f}, HddL = 0.f, bdL = 0.f, HcdL[4] = {0.f, 0.f, 0.f, 0.f};
       float gh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -412,17 +449,19 @@ __global__ void __launch_bounds__(256) k_accumulate_fused(FusedAccArgs a, int DP
           const float xs[4] = {x03.x, x03.y, x03.z, x03.w}, ys[4] = {y_a.z, y_a.w, y_b.x, y_b.y};
 #pragma unroll
           for (int q = 0; q < 4; q++) c_Hcd[q] = xs[q] * v0 + ys[q] * v1;
-          const int t = a.r_target[rb + i];
-          const float4 *Ah = (const float4 *)(a.adHostF + 64 * (size_t)(host + t * nf));
-          const float4 *At = (const float4 *)(a.adTargetF + 64 * (size_t)(host + t * nf));
+          const int t = s_tgt[i];
+          const float4 *Ah = (const float4 *)(Adh + t * ADJ_ST), *At = (const float4 *)(Adt + t * ADJ_ST);
           const float v[8] = {v03.x, v03.y, v03.z, v03.w, v47.x, v47.y, v47.z, v47.w};
+          float st[8];
 #pragma unroll
           for (int row = 0; row < 8; row++) {
-            const float4 h0 = __ldg(Ah + 2 * row), h1 = __ldg(Ah + 2 * row + 1), t0 = __ldg(At + 2 * row), t1 = __ldg(At + 2 * row + 1);
+            const float4 h0 = Ah[2 * row], h1 = Ah[2 * row + 1], t0 = At[2 * row], t1 = At[2 * row + 1];
             sh[row] = h0.x * v[0] + h0.y * v[1] + h0.z * v[2] + h0.w * v[3] + h1.x * v[4] + h1.y * v[5] + h1.z * v[6] + h1.w * v[7];
-            const float st = t0.x * v[0] + t0.y * v[1] + t0.z * v[2] + t0.w * v[3] + t1.x * v[4] + t1.y * v[5] + t1.z * v[6] + t1.w * v[7];
-            atomicAdd(&g[4 + 8 * t + row], st);   // one residual per (point, target): uncontended
+            st[row] = t0.x * v[0] + t0.y * v[1] + t0.z * v[2] + t0.w * v[3] + t1.x * v[4] + t1.y * v[5] + t1.z * v[6] + t1.w * v[7];
           }
+          // one residual per (point, target): this lane is the only writer of the target rows
+          *(float4 *)(g + 4 + 8 * t) = make_float4(st[0], st[1], st[2], st[3]);
+          *(float4 *)(g + 8 + 8 * t) = make_float4(st[4], st[5], st[6], st[7]);
         }
         ngood += __popc(__ballot_sync(gmask, use) & gmask);
         const int cnt = min(8, le - base);
@@ -461,18 +500,20 @@ __global__ void __launch_bounds__(256) k_accumulate_fused(FusedAccArgs a, int DP
 #pragma unroll
         for (int q = 0; q < 4; q++) if (sub == q) g[q] = HcdA[q] + HcdL[q];
 #pragma unroll
-        for (int q = 0; q < 8; q++) if (sub == q) atomicAdd(&g[4 + 8 * host + q], gh[q]);
+        for (int q = 0; q < 8; q++) if (sub == q) g[4 + 8 * host + q] = gh[q];   // no residual targets the host itself
       }
     }
+    ACC_TS(6);
     __syncthreads();
-    // ---- Schur: acc += w g g^T ----------------------------------------------------------------------------
+    if (a.dbg && blockIdx.x == 0 && tid == 32) a.dbg[3] = clock64() + (long long)(Ws[0] == 123.f);
+    // ---- Schur: acc += w g g^T (a point without good residuals has w = 0 and an all-zero g) ----------------------
 #pragma unroll
     for (int m = 0; m < SC_MAXT; m++) {
       if (my_ti[m] < 0) continue;
       const int i0 = my_ti[m] * 4, j0 = my_tj[m] * 4;
-      for (int k = 0; k < np; k++) {
+#pragma unroll 4
+      for (int k = 0; k < SC_TP; k++) {
         const float w = Ws[k];
-        if (w == 0.f) continue;
         const float4 gi = *(const float4 *)(Gs + k * DPAD + i0);
         const float4 gj = *(const float4 *)(Gs + k * DPAD + j0);
         const float wi[4] = {gi.x * w, gi.y * w, gi.z * w, gi.w * w};
@@ -484,6 +525,7 @@ __global__ void __launch_bounds__(256) k_accumulate_fused(FusedAccArgs a, int DP
       }
     }
   }
+  ACC_TS(4);
 #pragma unroll
   for (int m = 0; m < SC_MAXT; m++) {
     if (my_ti[m] < 0) continue;
@@ -496,6 +538,7 @@ __global__ void __launch_bounds__(256) k_accumulate_fused(FusedAccArgs a, int DP
         if (i <= j && j < DP && acc[m][ii * 4 + jj] != 0.f) atomicAdd(a.accSC + (size_t)i * DP + j, (double)acc[m][ii * 4 + jj]);
       }
   }
+  ACC_TS(5);
   __syncthreads();
   if (tid < 2 && s_nacc[tid]) atomicAdd(a.n_acc + tid, s_nacc[tid]);
 }
@@ -715,14 +758,15 @@ void launch_resubstitute(sosba *h, const ResubArgs &a) {
 
 // mode-0 accumulation (A, L and Schur tables) in one launch.  Returns false when the tile cannot be staged in shared
 // memory (the caller falls back to the separate kernels).
-bool launch_accumulate_fused(sosba *h, const FusedAccArgs &a, int max_res_per_tile) {
-  if (a.P == 0) return true;
+bool launch_accumulate_fused(sosba *h, const FusedAccArgs &a, int max_res_per_tile, int tiles_total) {
+  if (a.P == 0 || tiles_total == 0) return true;
   const int DP = a.D + 1, DPAD = (DP + 3) / 4 * 4, nt4 = DPAD / 4;
   const int ntiles4 = nt4 * (nt4 + 1) / 2;
-  if (ntiles4 > SC_MAXT * 256) return false;
-  const int tiles_total = (a.P + SC_TP - 1) / SC_TP;
-  const int max_res = max_res_per_tile > 0 ? max_res_per_tile : 1;
-  size_t smem = (size_t)max_res * SOSBA_CREC * 4 + (size_t)(SC_TP * DPAD + SC_TP) * 4 + (size_t)(SC_TP * a.nf + 2 * SC_TP + 1) * 4 + (size_t)max_res;
+  if (ntiles4 > SC_MAXT * ACC_THREADS || a.nf > 255) return false;
+  const int max_res = (max_res_per_tile > 0 ? max_res_per_tile + 3 : 4) & ~3;
+  if (max_res > 60000) return false;
+  size_t smem = (size_t)max_res * SOSBA_CREC * 4 + (size_t)(SC_TP * DPAD + SC_TP) * 4 + (size_t)2 * a.nf * ADJ_ST * 4 + (size_t)(SC_TP + 1) * 4 +
+                (size_t)a.nf * 2 * SC_TP * 2 + 2 * (size_t)max_res;
   smem = (smem + 15) & ~(size_t)15;
   if (smem > 200 * 1024) return false;
   static size_t configured = 0;
@@ -731,7 +775,7 @@ bool launch_accumulate_fused(sosba *h, const FusedAccArgs &a, int max_res_per_ti
     configured = 200 * 1024;
   }
   int workers = tiles_total < 2 * h->sm_count ? tiles_total : 2 * h->sm_count;
-  k_accumulate_fused<<<workers + (a.do_th ? 1 : 0), 256, smem, h->stream>>>(a, DP, DPAD, ntiles4, tiles_total, max_res);
+  k_accumulate_fused<<<workers + (a.do_th ? 1 : 0), ACC_THREADS, smem, h->stream>>>(a, DP, DPAD, ntiles4, tiles_total, max_res);
   h->launches++;
   return true;
 }

@@ -118,6 +118,7 @@ struct FusedAccArgs {
   int P, nf, D, R;
   int shiftPriorToZero;
   int do_th;           // the spare CTA runs the pending setNewFrameEnergyTH
+  const int4 *tiles;   // per tile: first point, points (<= 32, one host), first residual, residuals
   const int *res_begin, *r_target, *p_host;
   const uint8_t *r_is_lin, *r_is_active, *r_dropped;
   const float *rec;
@@ -130,8 +131,9 @@ struct FusedAccArgs {
   double *accSC;       // [(D+1)*(D+1)] upper triangle
   ThArgs th;
   const int *gate;
+  long long *dbg;      // optional phase timestamps (SOSBA_SOLVE_DEBUG)
 };
-bool launch_accumulate_fused(sosba *h, const FusedAccArgs &a, int max_res_per_tile);
+bool launch_accumulate_fused(sosba *h, const FusedAccArgs &a, int max_res_per_tile, int tiles_total);
 
 // top blocks -> H (D*D), b (D): AccumulatedTopHessianSSE::stitchDoubleInternal + stitchDoubleMT epilogue
 void launch_stitch_top(sosba *h, const double *accTop, const double *adHost, const double *adTarget, int nf, double *H, double *b,

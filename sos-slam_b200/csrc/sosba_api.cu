@@ -60,7 +60,8 @@ struct HostSide {
   bool tables_clean = false;
   bool th_pending = false;      // setNewFrameEnergyTH of the last fused linearisation still to run
   bool fused_acc_ok = false;    // every (point, target) pair holds at most one residual and a tile fits shared memory
-  int max_res_per_tile = 0;
+  int max_res_per_tile = 0, n_tiles = 0, tiles_cap = 0;
+  int *d_tiles = nullptr;       // int4 per tile of the fused accumulation
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;   // (start, stop) pairs around the linearize kernel
 };
@@ -216,6 +217,12 @@ API void sosba_destroy(sosba_t *h) {
       fprintf(stderr, "k_solve look-ahead timeline, panels 4,5: [panel: data landed, chain done, stored | update: L/Y landed, published, rest done] (cycles):");
       for (int i = 0; i < 16; i++) if ((i & 7) < 6) fprintf(stderr, " %lld%s", q[i] - q[0], (i & 7) == 2 ? " |" : (i & 7) == 5 ? " ||" : "");
       fprintf(stderr, "\n");
+    }
+    {
+      long long q[8];
+      cudaMemcpy(q, g_dbg + 64 * 32, sizeof(q), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "k_accumulate_fused CTA 0 phase cycles (last launch): setup %lld | top (warp 9) %lld || points (warp 1) %lld | barrier %lld schur %lld flush %lld\n",
+              q[1] - q[0], q[2] - q[1], q[6] - q[1], q[3] - q[6], q[4] - q[3], q[5] - q[4]);
     }
     g_dbg_n = 0;
   }
@@ -482,7 +489,7 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
     cnt[host[i] + t * nf + 1]++;
   }
   for (int p = 0; p < P; p++) hs->res_begin[p + 1] += hs->res_begin[p];
-  {  // the fused accumulation stages the residuals of 32 consecutive points and indexes them by (point, target)
+  {  // the fused accumulation stages the residuals of up to 32 consecutive points of ONE host and lists them per target
     hs->fused_acc_ok = true;
     hs->max_res_per_tile = 0;
     std::vector<int> seen(nf, -1);
@@ -491,7 +498,23 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
         if (seen[r->target[i]] == p) { hs->fused_acc_ok = false; break; }
         seen[r->target[i]] = p;
       }
-    for (int p0 = 0; p0 < P; p0 += 32) hs->max_res_per_tile = std::max(hs->max_res_per_tile, hs->res_begin[std::min(P, p0 + 32)] - hs->res_begin[p0]);
+    std::vector<int> tiles;
+    for (int p0 = 0; p0 < P;) {
+      int np = 1;
+      while (np < 32 && p0 + np < P && hs->p_host[p0 + np] == hs->p_host[p0]) np++;
+      const int rb = hs->res_begin[p0], nres = hs->res_begin[p0 + np] - rb;
+      tiles.insert(tiles.end(), {p0, np, rb, nres});
+      hs->max_res_per_tile = std::max(hs->max_res_per_tile, nres);
+      p0 += np;
+    }
+    hs->n_tiles = (int)tiles.size() / 4;
+    if ((int)tiles.size() > hs->tiles_cap) {
+      dfree(h, hs->d_tiles);
+      DALLOC(h, hs->d_tiles, tiles.size() * 2 + 64);
+      hs->tiles_cap = (int)tiles.size() * 2 + 64;
+    }
+    if (!tiles.empty() && (rc = up(h, hs->d_tiles, tiles.data(), tiles.size()))) return rc;
+    if ((rc = sync(h))) return rc;   // `tiles` is a local
     hs->th_pending = false;
     hs->tables_clean = false;
   }
@@ -746,6 +769,7 @@ static int enqueue_blocks(sosba *h) {
     if (hs->n_lin > 0) launch_prep_records(h, lin_args(h), 1, nullptr, h->R);
     FusedAccArgs f;
     f.P = h->P; f.nf = nf; f.D = 4 + 8 * nf; f.R = h->R; f.shiftPriorToZero = 1; f.do_th = hs->th_pending ? 1 : 0;
+    f.tiles = (const int4 *)hs->d_tiles;
     f.res_begin = h->p_res_begin; f.r_target = h->r_target; f.p_host = h->p_host;
     f.r_is_lin = h->r_is_lin; f.r_is_active = h->r_is_active; f.r_dropped = h->r_dropped; f.rec = h->r_rec;
     f.accTop = h->d_accTop; f.n_acc = hs->d_cnt;
@@ -753,7 +777,8 @@ static int enqueue_blocks(sosba *h) {
     f.priorF = h->p_priorF; f.deltaF = h->p_deltaF; f.HdiF = h->p_HdiF; f.bdSumF = h->p_bdSumF; f.idepth_hessian = h->p_idepth_hessian;
     f.maxRelBaseline = h->p_maxRelBaseline; f.adHostF = h->d_adHostF; f.adTargetF = h->d_adTargetF; f.accSC = h->d_accSC;
     f.th = lin_args(h).th; f.gate = nullptr;
-    fused = launch_accumulate_fused(h, f, hs->max_res_per_tile);
+    f.dbg = (g_dbg && getenv("SOSBA_SOLVE_DEBUG")) ? g_dbg + 64 * 32 : nullptr;
+    fused = launch_accumulate_fused(h, f, hs->max_res_per_tile, hs->n_tiles);
     if (fused) hs->th_pending = false;
   }
   if (!fused) {
@@ -845,7 +870,7 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
   s.stage_sc = s.stage_hm = 0;
   static const bool solve_debug = getenv("SOSBA_SOLVE_DEBUG") != nullptr;
   if (solve_debug) {   // phase timestamps of the last 64 launches, no host sync: read back and printed by sosba_destroy
-    if (!g_dbg) cudaMalloc(&g_dbg, 64 * 32 * sizeof(long long));
+    if (!g_dbg) cudaMalloc(&g_dbg, (64 * 32 + 16) * sizeof(long long));
     s.dbg = g_dbg + 32 * (g_dbg_n++ % 64);
   }
   if ((rc = launch_solve(h, s))) return rc;

@@ -641,6 +641,11 @@ __global__ void __launch_bounds__(256) k_finalize_sc(const double *__restrict__ 
 // lane q owns residual res_begin[p] + q; the subtraction chain runs in residual order like the reference.
 __global__ void __launch_bounds__(256) k_resubstitute(ResubArgs a) {
   __shared__ double s_sum[3];
+  if (a.gate && *a.gate) return;
+  if (a.zero_lin && blockIdx.x == 0 && threadIdx.x < 7) {   // energy | pad | counts[0..4] of the linearisation that follows
+    if (threadIdx.x < 2) a.zero_lin[threadIdx.x] = 0.0;
+    else ((int *)(a.zero_lin + 2))[threadIdx.x - 2] = 0;
+  }
   if (threadIdx.x < 3) s_sum[threadIdx.x] = 0.0;
   __syncthreads();
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;

@@ -504,7 +504,10 @@ __global__ void __launch_bounds__(256) k_prep_records(LinArgs a, int mode, const
 
 // ------------------------------------------------------------------------------------------------
 // setNewFrameEnergyTH: energy_th.cuh
-__global__ void __launch_bounds__(1024) k_energy_th(ThArgs a) { energy_th_body(a); }
+__global__ void __launch_bounds__(1024) k_energy_th(ThArgs a, const int *gate) {
+  if (gate && *gate) return;
+  energy_th_body(a);
+}
 
 // ------------------------------------------------------------------------------------------------
 // a14 / a17  one thread per reference point.  The warped buffers are written in place (index i) with
@@ -617,7 +620,7 @@ void launch_linearize(sosba *h, const LinArgs &a) {
 }
 // linearizeAll(false) + setNewFrameEnergyTH + applyRes(true) in one launch (the loop body of FullSystem::optimize)
 void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j, bool th_inline) {
-  if (a.R == 0) { if (th_inline) { k_energy_th<<<1, 256, 0, h->stream>>>(a.th); h->launches++; } return; }
+  if (a.R == 0) { if (th_inline) { k_energy_th<<<1, 256, 0, h->stream>>>(a.th, a.gate); h->launches++; } return; }
   const int blocks = (a.R * 8 + 255) / 256;
   if (write_j) {
     if (th_inline) k_linearize<true, true, true><<<blocks, 256, 0, h->stream>>>(a);
@@ -648,8 +651,8 @@ void launch_prep_records(sosba *h, const LinArgs &a, int mode, const int *d_list
   k_prep_records<<<(n * 8 + 255) / 256, 256, 0, h->stream>>>(a, mode, d_list, n);
   h->launches++;
 }
-void launch_energy_th(sosba *h, const ThArgs &a) {
-  k_energy_th<<<1, 1024, 0, h->stream>>>(a);
+void launch_energy_th(sosba *h, const ThArgs &a, const int *gate) {
+  k_energy_th<<<1, 1024, 0, h->stream>>>(a, gate);
   h->launches++;
 }
 void launch_track_res(sosba *h, const TrackResArgs &a) {

@@ -196,6 +196,25 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
   const int ty = tid >> 4, tx = tid & 15;
 #define SOLVE_TS(n) do { if (a.dbg && tid == 0) a.dbg[n] = clock64(); } while (0)
   SOLVE_TS(0);
+  if (a.ctl) {   // did the previous loop body converge?  (doStepFromBackup's return value, FullSystemOptimize.cpp:238-256)
+    __shared__ int s_stop;
+    if (tid == 0) {
+      int stop = a.ctl[0];
+      if (!stop && a.iter_index >= 1 && a.iter_index - 1 >= a.min_it) {
+        const double *it = a.step.iter;   // sumA, sumB, sumT, sumR of the previous body (already / nf)
+        const float sumA = (float)it[0], sumB = (float)it[1], sumT = (float)it[2], sumR = (float)it[3];
+        const float numID = (float)a.prev_rstats[2];
+        const float sumNID = numID > 0 ? (float)a.prev_rstats[1] / numID : 0.f;
+        const float th = a.th_opt;
+        stop = sqrtf(sumA) < 0.0005 * th && sqrtf(sumB) < 0.00005 * th && sqrtf(sumR) < 0.00005 * th && sqrtf(sumT) * sumNID < 0.00005 * th;
+        if (stop) a.ctl[0] = 1;
+      }
+      if (!stop) a.ctl[1] = a.iter_index + 1;
+      s_stop = stop;
+    }
+    __syncthreads();
+    if (s_stop) return;
+  }
 
   // ---- stage the inputs in shared memory: one thread issues the bulk copies, everyone waits on the mbarrier ------
   const double *Hsrc = M, *Ssrc = a.accSC, *HMsrc = a.HM;

@@ -49,7 +49,7 @@ void launch_fix_linearization(sosba *h, const LinArgs &a, const int *d_ids, int 
 // mode 1: linearised residuals (resApprox = res_toZeroF + J*delta), mode 2: marginalisation (res_toZeroF);
 // list==nullptr -> all residuals.  Rewrites the commit record of every selected residual.
 void launch_prep_records(sosba *h, const LinArgs &a, int mode, const int *d_list, int n);
-void launch_energy_th(sosba *h, const ThArgs &a);
+void launch_energy_th(sosba *h, const ThArgs &a, const int *gate = nullptr);
 
 // frames + calibration part of a Gauss-Newton step, device resident
 #define SOSBA_FS 64   // doubles per frame: evalPT[12] state[10]@12 state_zero[10]@22 state_backup[10]@32 step[10]@42 ab_exposure@52
@@ -158,6 +158,11 @@ struct SolveArgs {
   int do_step;                 // also run the frames / calibration part of doStepFromBackup (FullSystemOptimize.cpp:185-257)
   StepArgs step;
   int stage_sc, stage_hm;      // set by launch_solve: accSC / HM staged in shared memory
+  // device-side loop control of FullSystem::optimize (FullSystemOptimize.cpp:358-413): no host round trip per iteration
+  int *ctl;                    // null = always run; [0] latch "loop broke", [1] iterations run
+  int iter_index, min_it;      // this is loop body `iter_index`; break after body i if canbreak(i) && i >= min_it
+  float th_opt;                // setting_thOptIterations
+  const double *prev_rstats;   // back-substitution sums of body iter_index-1: [0] sum step^2 [1] sum |idepth| [2] count
 };
 int launch_solve(sosba *h, const SolveArgs &a);
 
@@ -172,6 +177,8 @@ struct ResubArgs {
   int do_step;
   float *idepth, *idepth_zero, *idepth_backup, *deltaF;
   double *stats;  // [1] sum step^2  [2] sum |idepth_backup|  [3] count
+  const int *gate;     // non-null: skip when *gate != 0
+  double *zero_lin;    // non-null: clear the linearisation sums (2 doubles + 5 ints) for the launch that follows
 };
 void launch_resubstitute(sosba *h, const ResubArgs &a);
 

@@ -58,6 +58,10 @@ struct HostSide {
   int *d_cnt = nullptr;
   size_t scratch_doubles = 0, scratch_zero_doubles = 0;   // all of it / the part the fused linearize clears (tables + H parts)
   bool tables_clean = false;
+  int rstats_par = 0;           // which half of d_rstats the next back-substitution writes
+  int *d_ctl = nullptr;         // device loop control: [0] latch, [1] iterations run
+  const int *gate = nullptr;    // = d_ctl while a gated optimize loop is being enqueued
+  int loop_iter = -1;           // body index while enqueuing a gated loop
   bool th_pending = false;      // setNewFrameEnergyTH of the last fused linearisation still to run
   bool fused_acc_ok = false;    // every (point, target) pair holds at most one residual and a tile fits shared memory
   int max_res_per_tile = 0, n_tiles = 0, tiles_cap = 0;
@@ -336,20 +340,20 @@ static int ensure_window(sosba *h, int nf) {
      // back-substitution sums [4], counters (ints) ; H part 3 (final system) follows and is never cleared
     const size_t HB = (size_t)D * D + D;
     const size_t scpad = (((size_t)(D + 1) * (D + 1)) + 1) & ~(size_t)1;   // even: H, b behind it stay 16-byte aligned (TMA bulk copies in k_solve)
-    hs->scratch_doubles = 2 * n2 * SOSBA_TOPB + scpad + 3 * HB + 4 + 4;
+    hs->scratch_doubles = 2 * n2 * SOSBA_TOPB + scpad + 3 * HB + 2 + 8 + 2;
     DALLOC(h, hs->d_scratch, hs->scratch_doubles + HB);
     h->d_accTop = hs->d_scratch;
     h->d_accSC = h->d_accTop + 2 * n2 * SOSBA_TOPB;
     h->d_H = h->d_accSC + scpad;
-    hs->d_rstats = h->d_H + 3 * HB;
+    hs->d_cnt = (int *)(h->d_H + 3 * HB);                   // [0] resInA [1] resInL (cleared with the tables)
+    hs->d_rstats = h->d_H + 3 * HB + 2;                     // 2 x 4 doubles: back-substitution sums by loop body parity
     hs->scratch_zero_doubles = (size_t)(hs->d_rstats - hs->d_scratch) & ~(size_t)1;
-    hs->d_cnt = (int *)(hs->d_rstats + 4);                  // [0] resInA [1] resInL [2] non-finite status
     hs->d_Hfinal = hs->d_scratch + hs->scratch_doubles;
   }
   DALLOC(h, h->d_x, D);
   DALLOC(h, h->d_xAd, n2 * 8 + 8);
   DALLOC(h, hs->d_HMtmp, (size_t)D * D); DALLOC(h, hs->d_bMtmp, D);
-  if (!hs->d_fs) { DALLOC(h, hs->d_fs, 16 * SOSBA_FS); DALLOC(h, hs->d_cs, 16); DALLOC(h, hs->d_iter, 8); }
+  if (!hs->d_fs) { DALLOC(h, hs->d_fs, 16 * SOSBA_FS); DALLOC(h, hs->d_cs, 16); DALLOC(h, hs->d_iter, 8); DALLOC(h, hs->d_ctl, 4); }
   h->nf_alloc = nf; h->D_alloc = D;
   return SOSBA_OK;
 }
@@ -580,7 +584,7 @@ API int sosba_reset_oob(sosba_t *h) {
 static void flush_pending_th(sosba *h) {
   HostSide *hs = HS(h);
   if (!hs->th_pending) return;
-  launch_energy_th(h, lin_args(h).th);
+  launch_energy_th(h, lin_args(h).th, hs->gate);
   hs->th_pending = false;
 }
 
@@ -762,7 +766,7 @@ static int enqueue_blocks(sosba *h) {
   const int nf = h->nf;
   const size_t n2 = (size_t)nf * nf;
   if (!hs->tables_clean) cudaMemsetAsync(hs->d_scratch, 0, sizeof(double) * hs->scratch_doubles, h->stream);
-  else cudaMemsetAsync(hs->d_rstats, 0, sizeof(double) * 8, h->stream);   // back-substitution sums + counters only
+  else cudaMemsetAsync(hs->d_rstats + 4 * hs->rstats_par, 0, sizeof(double) * 4, h->stream);   // back-substitution sums of this body
   hs->tables_clean = false;
   bool fused = false;
   if (hs->fused_acc_ok) {
@@ -776,7 +780,7 @@ static int enqueue_blocks(sosba *h) {
     f.HddA = h->p_HddA; f.bdA = h->p_bdA; f.HcdA = h->p_HcdA; f.HddL = h->p_HddL; f.bdL = h->p_bdL; f.HcdL = h->p_HcdL;
     f.priorF = h->p_priorF; f.deltaF = h->p_deltaF; f.HdiF = h->p_HdiF; f.bdSumF = h->p_bdSumF; f.idepth_hessian = h->p_idepth_hessian;
     f.maxRelBaseline = h->p_maxRelBaseline; f.adHostF = h->d_adHostF; f.adTargetF = h->d_adTargetF; f.accSC = h->d_accSC;
-    f.th = lin_args(h).th; f.gate = nullptr;
+    f.th = lin_args(h).th; f.gate = hs->gate;
     f.dbg = (g_dbg && getenv("SOSBA_SOLVE_DEBUG")) ? g_dbg + 64 * 32 : nullptr;
     fused = launch_accumulate_fused(h, f, hs->max_res_per_tile, hs->n_tiles);
     if (fused) hs->th_pending = false;
@@ -837,7 +841,8 @@ static ResubArgs resub_args(sosba *h, int do_step) {
   r.r_is_active = h->r_is_active; r.r_dropped = h->r_dropped; r.rec = h->r_rec; r.xAd = h->d_xAd;
   r.HcdA = h->p_HcdA; r.HcdL = h->p_HcdL; r.bdSumF = h->p_bdSumF; r.HdiF = h->p_HdiF; r.step = h->p_step;
   r.do_step = do_step; r.idepth = h->p_idepth; r.idepth_zero = h->p_idepth_zero; r.idepth_backup = h->p_idepth_backup; r.deltaF = h->p_deltaF;
-  r.stats = HS(h)->d_rstats - 1;   // the kernel writes stats[1..3]
+  r.stats = HS(h)->d_rstats + 4 * HS(h)->rstats_par - 1;   // the kernel writes stats[1..3]
+  r.gate = HS(h)->gate; r.zero_lin = nullptr;
   return r;
 }
 
@@ -863,18 +868,24 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
   s.Htop = Hpart(h, 0); s.btop = bpart(h, 0); s.accSC = h->d_accSC;
   s.HM = d_HM; s.bM = d_bM; s.wprior = h->d_wprior; s.cDeltaF = h->d_calib + 6;
   s.x = h->d_x; s.Hfinal = want_final ? Hpart(h, 3) : nullptr; s.bfinal = want_final ? bpart(h, 3) : nullptr;
-  s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.xAd = h->d_xAd; s.status = hs->d_cnt + 2;
+  s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.xAd = h->d_xAd; s.status = hs->d_ctl + 2;
   s.dbg = nullptr;
   s.do_step = do_step;
   s.step = step_args(h);
   s.stage_sc = s.stage_hm = 0;
+  s.ctl = hs->gate ? hs->d_ctl : nullptr; s.iter_index = hs->loop_iter; s.min_it = h->cfg.min_opt_iterations; s.th_opt = h->cfg.th_opt_iterations;
+  s.prev_rstats = hs->d_rstats + 4 * (hs->rstats_par ^ 1);
   static const bool solve_debug = getenv("SOSBA_SOLVE_DEBUG") != nullptr;
   if (solve_debug) {   // phase timestamps of the last 64 launches, no host sync: read back and printed by sosba_destroy
     if (!g_dbg) cudaMalloc(&g_dbg, (64 * 32 + 16) * sizeof(long long));
     s.dbg = g_dbg + 32 * (g_dbg_n++ % 64);
   }
   if ((rc = launch_solve(h, s))) return rc;
-  launch_resubstitute(h, resub_args(h, do_step));
+  {
+    ResubArgs ra = resub_args(h, do_step);
+    if (do_step) ra.zero_lin = h->d_stats;   // the fused linearisation follows: no memset on the stream
+    launch_resubstitute(h, ra);
+  }
   SOSBA_CUDA(cudaGetLastError());
   return SOSBA_OK;
 }
@@ -890,9 +901,10 @@ API int sosba_solve_system(sosba_t *h, const double *HM, const double *bM, doubl
     if ((rc = up(h, hs->d_HMtmp, HM, (size_t)D * D)) || (rc = up(h, hs->d_bMtmp, bM, D))) return rc;
     if ((rc = sync(h))) return rc;
   }
+  cudaMemsetAsync(hs->d_ctl + 2, 0, sizeof(int), h->stream);
   if ((rc = enqueue_solve(h, prior ? hs->d_HMtmp : nullptr, prior ? hs->d_bMtmp : nullptr, 0, Hf || bf))) return rc;
   if ((rc = fetch(h, x, h->d_x, D)) || (rc = fetch(h, Hf, Hpart(h, 3), (size_t)D * D)) || (rc = fetch(h, bf, bpart(h, 3), D)) ||
-      (rc = down(h, hs->pin_i, hs->d_cnt + 2, 1)))
+      (rc = down(h, hs->pin_i, hs->d_ctl + 2, 1)))
     return rc;
   if ((rc = sync(h))) return rc;
   if (hs->pin_i[0]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
@@ -1218,6 +1230,7 @@ static int enqueue_iteration(sosba *h) {
   int rc = enqueue_solve(h, ba->have_HM ? hs->d_HMtmp : nullptr, ba->have_HM ? hs->d_bMtmp : nullptr, 1);
   if (rc) return rc;
   enqueue_linearize_apply(h, true);
+  hs->rstats_par ^= 1;
   SOSBA_CUDA(cudaGetLastError());
   ba->iterations_done++;
   return SOSBA_OK;
@@ -1228,8 +1241,8 @@ static int enqueue_iteration(sosba *h) {
 static void enqueue_linearize_apply(sosba *h, bool zero_tables) {
   HostSide *hs = HS(h);
   flush_pending_th(h);
-  cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(double) + 5 * sizeof(int), h->stream);
-  LinArgs a = lin_args(h);
+  LinArgs a = lin_args(h);   // the linearisation sums were cleared by the back-substitution launch of this body
+  a.gate = hs->gate;
   if (zero_tables) { a.zero_buf = hs->d_scratch; a.zero_n = (int)(hs->scratch_zero_doubles / 2); }
   const bool th_inline = !hs->fused_acc_ok;   // otherwise the spare CTA of the next accumulation runs the selection
   if (hs->prof_on) {
@@ -1244,31 +1257,16 @@ static void enqueue_linearize_apply(sosba *h, bool zero_tables) {
   hs->tables_clean = zero_tables;
 }
 
-// read back what the host needs to decide `canbreak` (doStepFromBackup's return value) after an iteration
-static int read_iteration(sosba *h, bool *canbreak, sosba_linearize_out *lo) {
-  HostSide *hs = HS(h);
-  int rc;
-  if ((rc = down(h, hs->pin_d + 256, hs->d_rstats, 3)) || (rc = down(h, hs->pin_d + 264, hs->d_iter, 4)) || (rc = down(h, hs->pin_i, hs->d_cnt + 2, 1))) return rc;
-  if ((rc = read_linearize_out(h, lo))) return rc;   // syncs
-  if (hs->pin_i[0]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
-  const float sumA = (float)hs->pin_d[264], sumB = (float)hs->pin_d[265], sumT = (float)hs->pin_d[266], sumR = (float)hs->pin_d[267];
-  const float numID = (float)hs->pin_d[258];
-  const float sumNID = numID > 0 ? (float)hs->pin_d[257] / numID : 0.f;
-  const float th = h->cfg.th_opt_iterations;
-  if (canbreak)
-    *canbreak = sqrtf(sumA) < 0.0005 * th && sqrtf(sumB) < 0.00005 * th && sqrtf(sumR) < 0.00005 * th && sqrtf(sumT) * sumNID < 0.00005 * th;
-  return SOSBA_OK;
-}
-
 API int sosba_ba_iterate(sosba_t *h, int32_t n, int32_t *n_res) {
   CHECK_H(h);
   if (!h->ba->st.loaded) { sosba_set_error("ba_upload first"); return SOSBA_E_STATE; }
   HostSide *hs = HS(h);
   int rc;
+  cudaMemsetAsync(hs->d_ctl + 2, 0, sizeof(int), h->stream);
   for (int i = 0; i < n; i++)
     if ((rc = enqueue_iteration(h))) return rc;
   flush_pending_th(h);
-  if ((rc = down(h, hs->pin_i, hs->d_cnt + 2, 1))) return rc;
+  if ((rc = down(h, hs->pin_i, hs->d_ctl + 2, 1))) return rc;
   if ((rc = sync(h))) return rc;
   if (hs->pin_i[0]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
   if (n_res) *n_res = h->R - hs->n_lin;
@@ -1308,14 +1306,21 @@ API int sosba_ba_optimize(sosba_t *h, int32_t mnumOptIts, sosba_optimize_out *ou
   if ((rc = read_linearize_out(h, &lo))) return rc;
   out->reserved0 = lo.n_in + lo.n_oob + lo.n_outlier;   // residuals linearised per pass (bench bookkeeping)
   out->energy_initial = lo.energy;
-  int it = 0;
+  // the whole loop goes onto the stream at once: k_solve of body i latches "converged" from the step norms of body i-1
+  // (doStepFromBackup's canbreak, iteration >= setting_minOptIterations) and every later launch returns immediately
+  cudaMemsetAsync(hs->d_ctl, 0, 4 * sizeof(int), h->stream);
+  hs->gate = hs->d_ctl;
   for (int iteration = 0; iteration < mnumOptIts; iteration++) {
-    bool canbreak = false;
-    if ((rc = enqueue_iteration(h))) return rc;
-    if ((rc = read_iteration(h, &canbreak, &lo))) return rc;
-    it++;
-    if (canbreak && iteration >= h->cfg.min_opt_iterations) break;
+    hs->loop_iter = iteration;
+    if ((rc = enqueue_iteration(h))) { hs->gate = nullptr; hs->loop_iter = -1; return rc; }
   }
+  flush_pending_th(h);
+  hs->gate = nullptr; hs->loop_iter = -1;
+  hs->tables_clean = false;   // a loop that broke early leaves partial block tables behind
+  if ((rc = down(h, hs->pin_i, hs->d_ctl, 2)) || (rc = down(h, hs->pin_i + 2, hs->d_ctl + 2, 1))) return rc;
+  if ((rc = sync(h))) return rc;
+  if (hs->pin_i[2]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
+  const int it = hs->pin_i[1];
   out->iterations = it;
   // new evaluation point for the newest frame (FullSystemOptimize.cpp:415-423)
   if ((rc = download_frame_state(h))) return rc;

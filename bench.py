@@ -33,7 +33,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "photometric_residuals_per_sec"
 UNIT = "residuals/s"
 ITERS = 6
-BYTES_LINEARIZE = 787          # algorithmic bytes per PointFrameResidual per linearisation
+BYTES_LINEARIZE = 616          # algorithmic bytes per PointFrameResidual of the fused linearize+applyRes launch of the GN loop (DESIGN.md §4.1;
+                               # the un-fused API variant, SURVEY.md §8d: 787)
 WORKLOAD = "synthetic 640x480 stereo, 8-KF window, 2000 active points, BA only (BASELINE.json configs[1])"
 
 
@@ -63,29 +64,67 @@ def measured_peak():
 
 
 class ClockSampler:
+    """SM clock + throttle reasons of one GPU, sampled DURING the timed region (NVML in a thread, every 5 ms;
+    falls back to `nvidia-smi -lms` when pynvml is unavailable)."""
+
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.th = None
+        self.nvml = None
         self.proc = None
+        self.rows = []
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                for bit, name in self.NAMES.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.th.join(timeout=1)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 5 ms"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -105,7 +144,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 def forced_cfg(lib, sc, threads=1):
@@ -163,7 +202,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sosba")
     ap.add_argument("--points-factor", type=int, default=0, help="scaling sweep: multiply the 2000 points (default: = gpus)")
@@ -305,7 +344,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_linearize", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "launch_us": lin_us, "launches_timed": lin_n,
                 "algorithmic_bytes_per_launch": BYTES_LINEARIZE * R_lin,
-                "note": "1 of 8 launches per step runs on a flushed L2; the window (63 MB) is L2-resident for the rest — latency-bound at this size, see DESIGN.md §5 sweep"}
+                "note": "fused linearize+applyRes launches of the GN loop (6 of the 8 linearisations of a step); 8.4 MB per launch = one partial wave: latency-bound at this size (DESIGN.md section 5; points sweep in profiles/)"}
 
     # ---- CPU baseline (rank 0, bounded sample) ---------------------------------------------------------
     cpu = None

@@ -76,7 +76,7 @@ int sosba_allreduce_acc(sosba *h) {
   NCCLCHK(g_nccl.GroupStart());
   // d_accTop (A | L) and d_accSC are adjacent in the scratch region: one fp64 sum; the two residual counters after
   const size_t nd = 2 * (size_t)nf * nf * SOSBA_TOPB + (size_t)(D + 1) * (D + 1);
-  int *cnt = (int *)(h->d_H + 3 * ((size_t)D * D + D) + 4);
+  int *cnt = (int *)(h->d_H + 3 * ((size_t)D * D + D));   // resInA, resInL right behind the H parts (sosba_api.cu: ensure_window)
   NCCLCHK(g_nccl.AllReduce(h->d_accTop, h->d_accTop, nd, ncclFloat64, ncclSum, c, h->stream));
   NCCLCHK(g_nccl.AllReduce(cnt, cnt, 2, ncclInt32, ncclSum, c, h->stream));
   NCCLCHK(g_nccl.GroupEnd());

@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
     __syncthreads();
     if (s_stop) return;
   }
+  if (tid == 0 && a.res_out) a.res_out[0] = a.res_in[0];
 
   // ---- stage the inputs in shared memory: one thread issues the bulk copies, everyone waits on the mbarrier ------
   const double *Hsrc = M, *Ssrc = a.accSC, *HMsrc = a.HM;

@@ -163,6 +163,8 @@ struct SolveArgs {
   int iter_index, min_it;      // this is loop body `iter_index`; break after body i if canbreak(i) && i >= min_it
   float th_opt;                // setting_thOptIterations
   const double *prev_rstats;   // back-substitution sums of body iter_index-1: [0] sum step^2 [1] sum |idepth| [2] count
+  const int *res_in;           // resInA of the accumulation this solve consumes ...
+  int *res_out;                // ... copied where the table clearing of the next linearisation does not reach
 };
 int launch_solve(sosba *h, const SolveArgs &a);
 

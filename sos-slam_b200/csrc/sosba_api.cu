@@ -594,16 +594,7 @@ static void enqueue_linearize(sosba *h, int fix) {
   cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(double) + 5 * sizeof(int), h->stream);
   LinArgs a = lin_args(h);
   HostSide *hs = HS(h);
-  if (hs->prof_on) {
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, h->stream);
-    launch_linearize(h, a);
-    cudaEventRecord(e1, h->stream);
-    hs->prof_ev.push_back(e0); hs->prof_ev.push_back(e1);
-  } else {
-    launch_linearize(h, a);
-  }
+  launch_linearize(h, a);   // (the bench roofline brackets the fused launches of the loop, enqueue_linearize_apply)
   launch_energy_th(h, a.th);
   if (fix) launch_apply_res(h, a, 1);
 }
@@ -875,6 +866,7 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
   s.stage_sc = s.stage_hm = 0;
   s.ctl = hs->gate ? hs->d_ctl : nullptr; s.iter_index = hs->loop_iter; s.min_it = h->cfg.min_opt_iterations; s.th_opt = h->cfg.th_opt_iterations;
   s.prev_rstats = hs->d_rstats + 4 * (hs->rstats_par ^ 1);
+  s.res_in = hs->d_cnt; s.res_out = hs->d_ctl + 3;
   static const bool solve_debug = getenv("SOSBA_SOLVE_DEBUG") != nullptr;
   if (solve_debug) {   // phase timestamps of the last 64 launches, no host sync: read back and printed by sosba_destroy
     if (!g_dbg) cudaMalloc(&g_dbg, (64 * 32 + 16) * sizeof(long long));
@@ -1336,7 +1328,7 @@ API int sosba_ba_optimize(sosba_t *h, int32_t mnumOptIts, sosba_optimize_out *ou
   nf_.frameEnergyTH = lo.new_frame_energy_th;
   out->energy_final = lo.energy;
   out->n_removed = lo.n_removed;
-  if ((rc = down(h, hs->pin_i, hs->d_cnt, 1)) || (rc = down(h, hs->pin_d, h->d_x, 4 + 8 * nf))) return rc;
+  if ((rc = down(h, hs->pin_i, hs->d_ctl + 3, 1)) || (rc = down(h, hs->pin_d, h->d_x, 4 + 8 * nf))) return rc;   // resInA of the last solve
   if ((rc = sync(h))) return rc;
   out->res_in_a = hs->pin_i[0];
   out->rmse = sqrtf((float)(lo.energy / (SOSBA_PATTERN * out->res_in_a)));

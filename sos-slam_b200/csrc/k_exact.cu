@@ -113,7 +113,15 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
   __shared__ double s_energy;
   __shared__ int s_cnt[3];
   __shared__ int s_last;
-  if (a.gate && *a.gate) return;   // the Gauss-Newton loop already converged (device-side break)
+  // first round trip: the loop gate and every per-residual id / flag at once (independent loads)
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = gid >> 3, idx = gid & 7;
+  const bool inr = r < a.R;
+  const int gate = a.gate ? *a.gate : 0;
+  const int m_lin = inr ? a.r_is_lin[r] : 1, m_drop = inr ? a.r_dropped[r] : 1, m_state = inr ? a.r_state[r] : 0;
+  const int m_pt = inr ? a.r_point[r] : 0, m_host = inr ? a.r_host[r] : 0, m_target = inr ? a.r_target[r] : 0;
+  const float m_energy = inr ? a.r_energy[r] : 0.f;
+  if (gate) return;   // the Gauss-Newton loop already converged (device-side break)
   if (threadIdx.x == 0) { s_energy = 0.0; s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; }
   if (a.zero_n > 0) {              // clear the block tables of the accumulation that follows (one memset less on the stream)
     double2 *zb = (double2 *)a.zero_buf;
@@ -121,19 +129,16 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
   }
   __syncthreads();
 
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = gid >> 3, idx = gid & 7;
   const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
-  bool live = r < a.R;
-  if (live) live = !(a.r_is_lin[r] | a.r_dropped[r]);
+  const bool live = inr && !(m_lin | m_drop);
   int outcome = -1;       // state_NewState once decided
   float ret_energy = 0.f; // linearize() return value
   if (live) {
-    const int pt = a.r_point[r], host = a.r_host[r], target = a.r_target[r];
-    const float old_energy = a.r_energy[r];
+    const int pt = m_pt, host = m_host, target = m_target;
+    const float old_energy = m_energy;
     float energyWO = -1.f;
     bool done = false;
-    if (a.r_state[r] == SOSBA_RES_OOB) { outcome = SOSBA_RES_OOB; ret_energy = old_energy; done = true; }
+    if (m_state == SOSBA_RES_OOB) { outcome = SOSBA_RES_OOB; ret_energy = old_energy; done = true; }
 
     if (!done) {
       const float *pc = a.precalc + (size_t)(host * a.nf + target) * SOSBA_PRECALC_FLOATS;
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
         bool bad = !(Ku > 1.1f && Kv > 1.1f && Ku < a.wM3G && Kv < a.hM3G);
         float3 hit = make_float3(0.f, 0.f, 0.f);
         if (!bad) {
-          hit = interp33(a.img0[target], Ku, Kv, a.w);
+          hit = interp33(a.img[target], Ku, Kv, a.w);
           if (!isfinite(hit.x)) bad = true;
         }
         if (__any_sync(gmask, bad)) {
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
       a.r_new_energy_wo[r] = energyWO;
       atomicAdd(&s_energy, (double)ret_energy);
       atomicAdd(&s_cnt[outcome], 1);
-      if (APPLY && a.r_state[r] != SOSBA_RES_OOB) {   // applyRes(true): "can never go back from OOB" (Residuals.cpp:306-309)
+      if (APPLY && m_state != SOSBA_RES_OOB) {   // applyRes(true): "can never go back from OOB" (Residuals.cpp:306-309)
         a.r_is_active[r] = outcome == SOSBA_RES_IN ? 1 : 0;
         a.r_state[r] = (uint8_t)outcome;
         // state_energy = state_NewEnergy, which a linearisation that left early (new state OOB) did not refresh

@@ -24,7 +24,7 @@ struct LinArgs {
   float *p_maxRelBaseline;
   int *p_numGood;
   const float *precalc, *frameEnergyTH, *calib, *adHTdeltaF;  // calib: fxl fyl cxl cyl fxli fyli | cDeltaF[4]
-  const float4 *const *img0;
+  const float4 *img[16];   // level-0 image of each window frame (kernel parameter space: no pointer-table load)
   int w;              // level-0 width
   float wM3G, hM3G;   // globalCalib.cpp:63-64
   float huberTH, outlierTHSum, affModeA, affModeB;

@@ -560,7 +560,7 @@ static LinArgs lin_args(sosba *h) {
   a.p_u = h->p_u; a.p_v = h->p_v; a.p_idepth = h->p_idepth; a.p_idepth_zero = h->p_idepth_zero; a.p_color = h->p_color; a.p_weights = h->p_weights;
   a.p_deltaF = h->p_deltaF; a.p_maxRelBaseline = h->p_maxRelBaseline; a.p_numGood = h->p_numGood;
   a.precalc = h->d_precalc; a.frameEnergyTH = h->d_frameEnergyTH; a.calib = h->d_calib; a.adHTdeltaF = h->d_adHTdeltaF;
-  a.img0 = (const float4 *const *)h->d_img0;
+  for (int i = 0; i < 16; i++) a.img[i] = i < h->nf ? h->slot_img[h->frame_slot[i]] : nullptr;
   a.w = h->cfg.w; a.wM3G = (float)(h->cfg.w - 3); a.hM3G = (float)(h->cfg.h - 3);
   a.huberTH = h->cfg.huber_th; a.outlierTHSum = h->cfg.outlier_th_sum_component; a.affModeA = h->cfg.affine_opt_mode_a; a.affModeB = h->cfg.affine_opt_mode_b;
   a.stats = h->d_stats; a.counts = h->d_counts; a.newE = h->d_newE;

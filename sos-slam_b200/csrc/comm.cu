@@ -68,18 +68,58 @@ API int sosba_comm_destroy(sosba_t *h) {
   return SOSBA_OK;
 }
 
-// sum of the block tables over ranks, in place, on the compute stream
-int sosba_allreduce_acc(sosba *h) {
+// sum of the block tables over ranks, in place, on the compute stream; the same (aggregated) launch carries the
+// back-substitution sums of the previous loop body (so that every rank takes the same break decision), the residual
+// counters and — when `with_newE` — the newest-frame energies of the last linearisation (a sum with zeros elsewhere =
+// exact concatenation, so every rank selects the same 70th percentile as a single GPU would)
+int sosba_allreduce_acc(sosba *h, int with_newE) {
   if (!h->comm || h->world <= 1) return SOSBA_OK;
   const int nf = h->nf, D = 4 + 8 * nf;
   ncclComm_t c = (ncclComm_t)h->comm;
   NCCLCHK(g_nccl.GroupStart());
-  // d_accTop (A | L) and d_accSC are adjacent in the scratch region: one fp64 sum; the two residual counters after
+  // d_accTop (A | L) and d_accSC are adjacent in the scratch region: one fp64 sum
   const size_t nd = 2 * (size_t)nf * nf * SOSBA_TOPB + (size_t)(D + 1) * (D + 1);
-  int *cnt = (int *)(h->d_H + 3 * ((size_t)D * D + D));   // resInA, resInL right behind the H parts (sosba_api.cu: ensure_window)
   NCCLCHK(g_nccl.AllReduce(h->d_accTop, h->d_accTop, nd, ncclFloat64, ncclSum, c, h->stream));
-  NCCLCHK(g_nccl.AllReduce(cnt, cnt, 2, ncclInt32, ncclSum, c, h->stream));
+  NCCLCHK(g_nccl.AllReduce(h->d_rstats_all, h->d_rstats_all, 8, ncclFloat64, ncclSum, c, h->stream));
+  NCCLCHK(g_nccl.AllReduce(h->d_cnt_all, h->d_cnt_all, 2, ncclInt32, ncclSum, c, h->stream));
+  if (with_newE && h->d_newE_all) {
+    NCCLCHK(g_nccl.AllReduce(h->d_newE_all, h->d_newE_all, (size_t)h->world * h->newE_cap, ncclFloat32, ncclSum, c, h->stream));
+    NCCLCHK(g_nccl.AllReduce(h->d_newE_cnt, h->d_newE_cnt, h->world, ncclInt32, ncclSum, c, h->stream));
+  }
   NCCLCHK(g_nccl.GroupEnd());
   h->launches += 1;
+  return SOSBA_OK;
+}
+
+// the linearisation sums of an API-level linearizeAll: energy (1 double), state histogram + removals (4 ints), energies
+int sosba_allreduce_lin(sosba *h, int with_stats) {
+  if (!h->comm || h->world <= 1) return SOSBA_OK;
+  ncclComm_t c = (ncclComm_t)h->comm;
+  NCCLCHK(g_nccl.GroupStart());
+  if (with_stats) {
+    NCCLCHK(g_nccl.AllReduce(h->d_stats, h->d_stats, 1, ncclFloat64, ncclSum, c, h->stream));
+    NCCLCHK(g_nccl.AllReduce(h->d_counts, h->d_counts, 4, ncclInt32, ncclSum, c, h->stream));
+  }
+  if (h->d_newE_all) {
+    NCCLCHK(g_nccl.AllReduce(h->d_newE_all, h->d_newE_all, (size_t)h->world * h->newE_cap, ncclFloat32, ncclSum, c, h->stream));
+    NCCLCHK(g_nccl.AllReduce(h->d_newE_cnt, h->d_newE_cnt, h->world, ncclInt32, ncclSum, c, h->stream));
+  }
+  NCCLCHK(g_nccl.GroupEnd());
+  h->launches += 1;
+  return SOSBA_OK;
+}
+
+// max of one host integer over ranks (setup only: synchronises)
+int sosba_comm_max_int(sosba *h, int v, int *out) {
+  *out = v;
+  if (!h->comm || h->world <= 1) return SOSBA_OK;
+  int *d = nullptr;
+  if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return SOSBA_E_CUDA;
+  cudaMemcpyAsync(d, &v, sizeof(int), cudaMemcpyHostToDevice, h->stream);
+  ncclResult_t r = g_nccl.AllReduce(d, d, 1, ncclInt32, ncclMax, (ncclComm_t)h->comm, h->stream);
+  cudaMemcpyAsync(out, d, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (r != 0) { sosba_set_error("ncclAllReduce(max) -> %s", g_nccl.GetErrorString(r)); return SOSBA_E_NCCL; }
   return SOSBA_OK;
 }

@@ -17,19 +17,31 @@ __device__ __forceinline__ void energy_th_hist_add(unsigned *hist, unsigned bin,
 __device__ inline void energy_th_body(const ThArgs &a) {
   __shared__ unsigned hist[256];
   __shared__ unsigned s_prefix, s_k;
-  const int n = a.counts[4];
+  __shared__ int s_off[17];   // prefix sums of the segment lengths
+  if (threadIdx.x == 0) {
+    int o = 0;
+    for (int sgm = 0; sgm < a.nseg; sgm++) { s_off[sgm] = o; o += a.seg_counts[sgm]; }
+    s_off[a.nseg] = o;
+  }
+  __syncthreads();
+  const int n = s_off[a.nseg];
   const unsigned *v = (const unsigned *)a.newE;
   const int nt = blockDim.x;
   if (n == 0) {
     if (threadIdx.x == 0) { a.frameEnergyTH[a.nf - 1] = 12 * 12 * 8; a.thOut[0] = 12 * 12 * 8; }
     return;
   }
+  auto elem = [&](int i) -> unsigned {   // i-th energy of the concatenated list
+    int sgm = 0;
+    while (sgm + 1 < a.nseg && i >= s_off[sgm + 1]) sgm++;
+    return v[(size_t)sgm * a.seg_stride + (i - s_off[sgm])];
+  };
   constexpr int KEEP = 8;
   unsigned mine[KEEP];
   const bool cached = n <= KEEP * nt;
   if (cached) {
 #pragma unroll
-    for (int q = 0; q < KEEP; q++) { const int i = threadIdx.x + q * nt; mine[q] = i < n ? v[i] : 0u; }
+    for (int q = 0; q < KEEP; q++) { const int i = threadIdx.x + q * nt; mine[q] = i < n ? elem(i) : 0u; }
   }
   if (threadIdx.x == 0) { s_prefix = 0; s_k = (unsigned)(int)(a.thN * n); }
   for (int pass = 3; pass >= 0; pass--) {
@@ -47,7 +59,7 @@ __device__ inline void energy_th_body(const ThArgs &a) {
     } else {
       for (int i0 = 0; i0 < n; i0 += nt) {
         const int i = i0 + threadIdx.x;
-        const unsigned x = i < n ? v[i] : 0u;
+        const unsigned x = i < n ? elem(i) : 0u;
         energy_th_hist_add(hist, (x >> shift) & 255u, i < n && (x & himask) == prefix);
       }
     }

@@ -646,6 +646,8 @@ __global__ void __launch_bounds__(256) k_resubstitute(ResubArgs a) {
     if (threadIdx.x < 2) a.zero_lin[threadIdx.x] = 0.0;
     else ((int *)(a.zero_lin + 2))[threadIdx.x - 2] = 0;
   }
+  if (a.zero_newE)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.zero_newE_n; i += gridDim.x * blockDim.x) a.zero_newE[i] = 0.f;
   if (threadIdx.x < 3) s_sum[threadIdx.x] = 0.0;
   __syncthreads();
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
             a.r_new_energy[r] = energyLeft;
             a.center[(size_t)r * 3 + 0] = cKu; a.center[(size_t)r * 3 + 1] = cKv; a.center[(size_t)r * 3 + 2] = c_new_idepth;
             if (target == a.nf - 1) {  // input of setNewFrameEnergyTH
-              int pos = atomicAdd(&a.counts[4], 1);
+              int pos = atomicAdd(a.newE_count, 1);
               a.newE[pos] = energyWO;
             }
           }

@@ -4,15 +4,21 @@
 #include "sosba_internal.h"
 
 // ---- k_exact.cu ---------------------------------------------------------------------------------
-// setNewFrameEnergyTH: k-th smallest of newE[0..counts[4]) -> frameEnergyTH[nf-1], thOut[0]
+// setNewFrameEnergyTH: k-th smallest of the newest-frame energies -> frameEnergyTH[nf-1], thOut[0].
+// The list is `nseg` segments of `seg_stride` floats with `seg_counts[s]` valid entries each: one segment on a single GPU
+// (seg_counts = &counts[4]); with point shards one segment per rank, gathered by the per-iteration all-reduce (a sum
+// with zeros elsewhere is an exact concatenation).
 struct ThArgs {
   const float *newE;
-  int *counts;
+  const int *seg_counts;
+  int nseg, seg_stride;
   float *frameEnergyTH;
   int nf;
   float thN, thFacMedian, thConstWeight, overallWeight;
   float *thOut;
 };
+void launch_energy_th(sosba *h, const ThArgs &a, const int *gate = nullptr);
+
 struct LinArgs {
   int R, nf;
   const int *r_point, *r_target, *r_host;
@@ -30,7 +36,8 @@ struct LinArgs {
   float huberTH, outlierTHSum, affModeA, affModeB;
   double *stats;      // [0] energy
   int *counts;        // 0 in, 1 oob, 2 outlier, 3 removed, 4 n newest-frame energies
-  float *newE;        // newest-frame energies (unordered)
+  float *newE;        // newest-frame energies of this rank (unordered)
+  int *newE_count;    // its length (atomic append)
   // fused variants (launch_linearize_apply)
   ThArgs th;          // setNewFrameEnergyTH in the last CTA
   int *ticket;        // CTA completion counter (self-resetting)
@@ -49,7 +56,6 @@ void launch_fix_linearization(sosba *h, const LinArgs &a, const int *d_ids, int 
 // mode 1: linearised residuals (resApprox = res_toZeroF + J*delta), mode 2: marginalisation (res_toZeroF);
 // list==nullptr -> all residuals.  Rewrites the commit record of every selected residual.
 void launch_prep_records(sosba *h, const LinArgs &a, int mode, const int *d_list, int n);
-void launch_energy_th(sosba *h, const ThArgs &a, const int *gate = nullptr);
 
 // frames + calibration part of a Gauss-Newton step, device resident
 #define SOSBA_FS 64   // doubles per frame: evalPT[12] state[10]@12 state_zero[10]@22 state_backup[10]@32 step[10]@42 ab_exposure@52
@@ -181,6 +187,8 @@ struct ResubArgs {
   double *stats;  // [1] sum step^2  [2] sum |idepth_backup|  [3] count
   const int *gate;     // non-null: skip when *gate != 0
   double *zero_lin;    // non-null: clear the linearisation sums (2 doubles + 5 ints) for the launch that follows
+  float *zero_newE;    // non-null (point shards): clear all ranks' newest-frame energy segments + their counts
+  int zero_newE_n;     // floats + ints to clear, as 4-byte words
 };
 void launch_resubstitute(sosba *h, const ResubArgs &a);
 

@@ -24,6 +24,9 @@ void launch_stitch_raw(sosba *h, const double *accTop2, const double *adHost, co
 using sosba_host::BAState;
 using sosba_host::WindowTables;
 
+int sosba_allreduce_acc(sosba *h, int with_newE);  // comm.cu: no-ops without a communicator
+int sosba_allreduce_lin(sosba *h, int with_stats);
+int sosba_comm_max_int(sosba *h, int v, int *out);
 static thread_local char g_err[512] = "";
 static long long *g_dbg = nullptr;   // SOSBA_SOLVE_DEBUG: k_solve phase timestamps (clock64), 16 per launch
 static long g_dbg_n = 0;
@@ -348,6 +351,7 @@ static int ensure_window(sosba *h, int nf) {
     hs->d_cnt = (int *)(h->d_H + 3 * HB);                   // [0] resInA [1] resInL (cleared with the tables)
     hs->d_rstats = h->d_H + 3 * HB + 2;                     // 2 x 4 doubles: back-substitution sums by loop body parity
     hs->scratch_zero_doubles = (size_t)(hs->d_rstats - hs->d_scratch) & ~(size_t)1;
+    h->d_rstats_all = hs->d_rstats; h->d_cnt_all = hs->d_cnt;
     hs->d_Hfinal = hs->d_scratch + hs->scratch_doubles;
   }
   DALLOC(h, h->d_x, D);
@@ -470,6 +474,7 @@ static int ensure_residuals(sosba *h, int R) {
   return SOSBA_OK;
 }
 
+static void clear_gathered_energies(sosba *h);
 API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
   CHECK_H(h);
   if (!r || r->n < 0 || h->nf <= 0) { sosba_set_error("residuals_set needs window_set/points_set first"); return SOSBA_E_STATE; }
@@ -522,6 +527,17 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
     hs->th_pending = false;
     hs->tables_clean = false;
   }
+  if (h->comm && h->world > 1) {   // point shards: room for every rank's newest-frame energies (one per local point at most)
+    int cap = 0;
+    if ((rc = sosba_comm_max_int(h, ((P + 63) / 64 + 1) * 64, &cap))) return rc;
+    if (cap > h->newE_cap) {
+      dfree(h, h->d_newE_all);
+      DALLOC(h, h->d_newE_all, (size_t)h->world * cap + h->world);
+      h->newE_cap = cap;
+    }
+    h->d_newE_cnt = (int *)(h->d_newE_all + (size_t)h->world * h->newE_cap);
+    clear_gathered_energies(h);
+  }
   for (int b = 0; b < nf * nf; b++) cnt[b + 1] += cnt[b];
   for (int i = 0; i < n; i++) by_block[cnt[host[i] + r->target[i] * nf]++] = i;   // stable counting sort by block
   std::vector<uint8_t> u8(n);
@@ -563,8 +579,15 @@ static LinArgs lin_args(sosba *h) {
   for (int i = 0; i < 16; i++) a.img[i] = i < h->nf ? h->slot_img[h->frame_slot[i]] : nullptr;
   a.w = h->cfg.w; a.wM3G = (float)(h->cfg.w - 3); a.hM3G = (float)(h->cfg.h - 3);
   a.huberTH = h->cfg.huber_th; a.outlierTHSum = h->cfg.outlier_th_sum_component; a.affModeA = h->cfg.affine_opt_mode_a; a.affModeB = h->cfg.affine_opt_mode_b;
-  a.stats = h->d_stats; a.counts = h->d_counts; a.newE = h->d_newE;
-  a.th.newE = h->d_newE; a.th.counts = h->d_counts; a.th.frameEnergyTH = h->d_frameEnergyTH; a.th.nf = h->nf;
+  a.stats = h->d_stats; a.counts = h->d_counts;
+  if (h->d_newE_all) {   // point shards: this rank's segment of the gathered list
+    a.newE = h->d_newE_all + (size_t)h->rank * h->newE_cap; a.newE_count = h->d_newE_cnt + h->rank;
+    a.th.newE = h->d_newE_all; a.th.seg_counts = h->d_newE_cnt; a.th.nseg = h->world; a.th.seg_stride = h->newE_cap;
+  } else {
+    a.newE = h->d_newE; a.newE_count = h->d_counts + 4;
+    a.th.newE = h->d_newE; a.th.seg_counts = h->d_counts + 4; a.th.nseg = 1; a.th.seg_stride = 0;
+  }
+  a.th.frameEnergyTH = h->d_frameEnergyTH; a.th.nf = h->nf;
   a.th.thN = h->cfg.frame_energy_th_n; a.th.thFacMedian = h->cfg.frame_energy_th_fac_median; a.th.thConstWeight = h->cfg.frame_energy_th_const_weight;
   a.th.overallWeight = h->cfg.overall_energy_th_weight; a.th.thOut = h->d_thOut;
   a.ticket = h->d_counts + 12;
@@ -581,10 +604,16 @@ API int sosba_reset_oob(sosba_t *h) {
 }
 
 // the threshold selection of a fused linearisation that no accumulation picked up yet
+static void clear_gathered_energies(sosba *h) {   // point shards: every segment must be empty before the next append / reduce
+  if (h->d_newE_all) cudaMemsetAsync(h->d_newE_all, 0, ((size_t)h->world * h->newE_cap + h->world) * 4, h->stream);
+}
+
 static void flush_pending_th(sosba *h) {
   HostSide *hs = HS(h);
   if (!hs->th_pending) return;
+  sosba_allreduce_lin(h, 0);
   launch_energy_th(h, lin_args(h).th, hs->gate);
+  clear_gathered_energies(h);
   hs->th_pending = false;
 }
 
@@ -592,11 +621,13 @@ static void flush_pending_th(sosba *h) {
 static void enqueue_linearize(sosba *h, int fix) {
   flush_pending_th(h);
   cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(double) + 5 * sizeof(int), h->stream);
+  clear_gathered_energies(h);
   LinArgs a = lin_args(h);
-  HostSide *hs = HS(h);
   launch_linearize(h, a);   // (the bench roofline brackets the fused launches of the loop, enqueue_linearize_apply)
-  launch_energy_th(h, a.th);
   if (fix) launch_apply_res(h, a, 1);
+  sosba_allreduce_lin(h, 1);   // point shards: global energy, state histogram, removals, newest-frame energies
+  launch_energy_th(h, a.th);
+  clear_gathered_energies(h);
 }
 
 static int read_linearize_out(sosba *h, sosba_linearize_out *out) {
@@ -737,7 +768,6 @@ static inline double *Hpart(sosba *h, int which) {
 }
 static inline double *bpart(sosba *h, int which) { const int D = 4 + 8 * h->nf; return Hpart(h, which) + (size_t)D * D; }
 
-int sosba_allreduce_acc(sosba *h);  // comm.cu: no-op without a communicator
 
 static SCArgs sc_args(sosba *h, int mode, const int *plist, int n_plist, int shift) {
   SCArgs s;
@@ -763,7 +793,7 @@ static int enqueue_blocks(sosba *h) {
   if (hs->fused_acc_ok) {
     if (hs->n_lin > 0) launch_prep_records(h, lin_args(h), 1, nullptr, h->R);
     FusedAccArgs f;
-    f.P = h->P; f.nf = nf; f.D = 4 + 8 * nf; f.R = h->R; f.shiftPriorToZero = 1; f.do_th = hs->th_pending ? 1 : 0;
+    f.P = h->P; f.nf = nf; f.D = 4 + 8 * nf; f.R = h->R; f.shiftPriorToZero = 1; f.do_th = (hs->th_pending && !(h->comm && h->world > 1)) ? 1 : 0;
     f.tiles = (const int4 *)hs->d_tiles;
     f.res_begin = h->p_res_begin; f.r_target = h->r_target; f.p_host = h->p_host;
     f.r_is_lin = h->r_is_lin; f.r_is_active = h->r_is_active; f.r_dropped = h->r_dropped; f.rec = h->r_rec;
@@ -774,10 +804,10 @@ static int enqueue_blocks(sosba *h) {
     f.th = lin_args(h).th; f.gate = hs->gate;
     f.dbg = (g_dbg && getenv("SOSBA_SOLVE_DEBUG")) ? g_dbg + 64 * 32 : nullptr;
     fused = launch_accumulate_fused(h, f, hs->max_res_per_tile, hs->n_tiles);
-    if (fused) hs->th_pending = false;
+    if (fused && f.do_th) hs->th_pending = false;
   }
   if (!fused) {
-  flush_pending_th(h);
+  if (!(h->comm && h->world > 1)) flush_pending_th(h);
   AccArgs a;
   a.R = h->R; a.P = h->P; a.nf = nf; a.n_list = h->R; a.list = h->r_by_block; a.mode = 0;
   a.r_point = h->r_point; a.r_target = h->r_target; a.r_host = h->r_host;
@@ -792,7 +822,13 @@ static int enqueue_blocks(sosba *h) {
   }
   launch_point_sc(h, sc_args(h, 0, nullptr, 0, 1));
   }
-  return sosba_allreduce_acc(h);   // points are sharded across ranks: sum the block tables (identical on every rank afterwards)
+  // points are sharded across ranks: sum the block tables (identical on every rank afterwards); the pending newest-frame
+  // energies ride along and the threshold selection runs right behind the reduction
+  const bool shard_th = h->comm && h->world > 1 && hs->th_pending;
+  int rc = sosba_allreduce_acc(h, shard_th ? 1 : 0);
+  if (rc) return rc;
+  if (shard_th) { launch_energy_th(h, lin_args(h).th, hs->gate); hs->th_pending = false; }
+  return SOSBA_OK;
 }
 
 // API path: the three stitched systems separately (d_H parts 0..2)
@@ -833,7 +869,7 @@ static ResubArgs resub_args(sosba *h, int do_step) {
   r.HcdA = h->p_HcdA; r.HcdL = h->p_HcdL; r.bdSumF = h->p_bdSumF; r.HdiF = h->p_HdiF; r.step = h->p_step;
   r.do_step = do_step; r.idepth = h->p_idepth; r.idepth_zero = h->p_idepth_zero; r.idepth_backup = h->p_idepth_backup; r.deltaF = h->p_deltaF;
   r.stats = HS(h)->d_rstats + 4 * HS(h)->rstats_par - 1;   // the kernel writes stats[1..3]
-  r.gate = HS(h)->gate; r.zero_lin = nullptr;
+  r.gate = HS(h)->gate; r.zero_lin = nullptr; r.zero_newE = nullptr; r.zero_newE_n = 0;
   return r;
 }
 
@@ -875,7 +911,10 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
   if ((rc = launch_solve(h, s))) return rc;
   {
     ResubArgs ra = resub_args(h, do_step);
-    if (do_step) ra.zero_lin = h->d_stats;   // the fused linearisation follows: no memset on the stream
+    if (do_step) {   // the fused linearisation follows: no memsets on the stream
+      ra.zero_lin = h->d_stats;
+      if (h->d_newE_all) { ra.zero_newE = h->d_newE_all; ra.zero_newE_n = h->world * h->newE_cap + h->world; }
+    }
     launch_resubstitute(h, ra);
   }
   SOSBA_CUDA(cudaGetLastError());
@@ -949,7 +988,7 @@ API int sosba_marginalize_points(sosba_t *h, const int32_t *ids, int32_t n, doub
   a.rec = h->r_rec; a.accTop = h->d_accTop; a.n_acc = hs->d_cnt;
   launch_top_accumulate(h, a);
   launch_point_sc(h, sc_args(h, 2, d_pl, n, 0));
-  if ((rc = sosba_allreduce_acc(h))) return rc;
+  if ((rc = sosba_allreduce_acc(h, 0))) return rc;
   launch_stitch_top(h, h->d_accTop, h->d_adHost, h->d_adTarget, nf, Hpart(h, 0), bpart(h, 0), 0, h->d_wprior, h->d_calib + 6);
   launch_finalize_sc(h, h->d_accSC, nf, Hpart(h, 2), bpart(h, 2));
   SOSBA_CUDA(cudaGetLastError());
@@ -1236,7 +1275,8 @@ static void enqueue_linearize_apply(sosba *h, bool zero_tables) {
   LinArgs a = lin_args(h);   // the linearisation sums were cleared by the back-substitution launch of this body
   a.gate = hs->gate;
   if (zero_tables) { a.zero_buf = hs->d_scratch; a.zero_n = (int)(hs->scratch_zero_doubles / 2); }
-  const bool th_inline = !hs->fused_acc_ok;   // otherwise the spare CTA of the next accumulation runs the selection
+  // the selection runs in the spare CTA of the next accumulation, or (point shards) behind the next all-reduce
+  const bool th_inline = !hs->fused_acc_ok && !(h->comm && h->world > 1);
   if (hs->prof_on) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);

@@ -144,6 +144,12 @@ struct sosba {
   // multi-GPU
   void *comm = nullptr;
   int rank = 0, world = 1;
+  // what rides on the per-iteration all-reduce besides the block tables (set by sosba_api.cu)
+  double *d_rstats_all = nullptr;   // [8] back-substitution sums, both loop-body parities
+  int *d_cnt_all = nullptr;         // [2] resInA, resInL
+  float *d_newE_all = nullptr;      // [world][newE_cap] newest-frame energies, one segment per rank ...
+  int *d_newE_cnt = nullptr;        // ... [world] lengths, stored right behind the segments
+  int newE_cap = 0;
 };
 
 void sosba_set_error(const char *fmt, ...);

@@ -168,6 +168,7 @@ __device__ __forceinline__ void panel_rows(const double *__restrict__ pb, double
   }
 }
 
+template <bool RETARGET>
 __device__ void frame_step_body(const StepArgs &a);
 
 template <int T>
@@ -423,7 +424,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
   // ---- frames / calibration part of doStepFromBackup, new precalc and deltas (same CTA, no extra launch) ---------
   if (a.do_step) {
     __syncthreads();
-    frame_step_body(a.step);
+    frame_step_body<false>(a.step);
   }
   SOLVE_TS(8);
 }
@@ -439,6 +440,10 @@ __device__ __forceinline__ void d_mul33f(const float *A, const float *B, float *
     for (int j = 0; j < 3; j++) C[3 * i + j] = (A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j]) + A[3 * i + 2] * B[6 + j];
 }
 
+// RETARGET (after the loop, FullSystemOptimize.cpp:415-423): no step; the newest frame gets its current pose as the new
+// evaluation point (setEvalPT(PRE_camToWorld, [0, aff])), and with it new adjoints (EnergyFunctional::setAdjointsF,
+// EnergyFunctional.cpp:42-103; mirrors host_ba.cpp make_adjoints), precalc and deltas for every pair.
+template <bool RETARGET>
 __device__ void frame_step_body(const StepArgs &a) {
   using namespace sosba_math;
   __shared__ double s_fs[16 * SOSBA_FS];
@@ -453,19 +458,31 @@ __device__ void frame_step_body(const StepArgs &a) {
     double *F = s_fs + SOSBA_FS * tid;
     double *G = a.fs + SOSBA_FS * tid;
     double *state = F + 12, *backup = F + 32, *step = F + 42;
-    for (int i = 0; i < 8; i++) step[i] = -a.x[4 + 8 * tid + i];
-    step[8] = step[9] = 0.0;
     double scaled[10];
-    for (int i = 0; i < 10; i++) {
-      backup[i] = state[i];
-      state[i] = backup[i] + (double)a.stepfac * step[i];
-      G[12 + i] = state[i]; G[32 + i] = backup[i]; G[42 + i] = step[i];
+    if (!RETARGET) {
+      for (int i = 0; i < 8; i++) step[i] = -a.x[4 + 8 * tid + i];
+      step[8] = step[9] = 0.0;
+      for (int i = 0; i < 10; i++) {
+        backup[i] = state[i];
+        state[i] = backup[i] + (double)a.stepfac * step[i];
+        G[12 + i] = state[i]; G[32 + i] = backup[i]; G[42 + i] = step[i];
+      }
     }
     for (int i = 0; i < 3; i++) scaled[i] = SC_T * state[i];
     for (int i = 3; i < 6; i++) scaled[i] = SC_R * state[i];
     scaled[6] = SC_A * state[6]; scaled[7] = SC_B * state[7]; scaled[8] = SC_A * state[8]; scaled[9] = SC_B * state[9];
-    const Rigid ev = rigid_from34(F);
-    const Rigid c2w = rigid_mul(rigid_exp(scaled), ev);
+    Rigid ev = rigid_from34(F);
+    Rigid c2w = rigid_mul(rigid_exp(scaled), ev);
+    if (RETARGET && tid == nf - 1) {   // FrameHessian::setEvalPT(PRE_camToWorld, [0 0 0 0 0 0 a b 0 0])
+      ev = c2w;
+      rigid_to34(ev, F); rigid_to34(ev, G);
+      for (int i = 0; i < 10; i++) {
+        const double v = (i == 6 || i == 7) ? state[i] : 0.0;
+        state[i] = v; F[22 + i] = v; G[12 + i] = v; G[22 + i] = v;
+        scaled[i] = i < 3 ? SC_T * v : i < 6 ? SC_R * v : (i & 1) ? SC_B * v : SC_A * v;
+      }
+      c2w = rigid_mul(rigid_exp(scaled), ev);
+    }
     s_c2w[tid] = c2w;
     s_w2c[tid] = rigid_inverse(c2w);
     s_scaled[tid][0] = scaled[6]; s_scaled[tid][1] = scaled[7];
@@ -478,9 +495,11 @@ __device__ void frame_step_body(const StepArgs &a) {
     double *C = a.cs;   // value[4] | value_zero[4] | value_backup[4] | step[4]
     float sf[4];
     for (int i = 0; i < 4; i++) {
-      C[12 + i] = -a.x[i];
-      C[8 + i] = C[i];
-      C[i] = C[8 + i] + (double)a.stepfac * C[12 + i];
+      if (!RETARGET) {
+        C[12 + i] = -a.x[i];
+        C[8 + i] = C[i];
+        C[i] = C[8 + i] + (double)a.stepfac * C[12 + i];
+      }
       sf[i] = (float)((i < 2 ? SC_F : SC_C) * C[i]);
       s_K[i] = sf[i];
       a.calib[i] = sf[i];
@@ -490,7 +509,7 @@ __device__ void frame_step_body(const StepArgs &a) {
     a.calib[5] = 1.0f / sf[1];
   }
   __syncthreads();
-  if (tid == 64) {  // step norms of doStepFromBackup, float accumulation in frame order
+  if (!RETARGET && tid == 64) {  // step norms of doStepFromBackup, float accumulation in frame order
     float sumA = 0, sumB = 0, sumT = 0, sumR = 0;
     for (int f = 0; f < nf; f++) {
       const double *st = s_fs + SOSBA_FS * f + 42;
@@ -511,8 +530,38 @@ __device__ void frame_step_body(const StepArgs &a) {
     const int idx = h + t * nf;
     const float4 *AhF = (const float4 *)(a.adHostF + 64 * (size_t)idx), *AtF = (const float4 *)(a.adTargetF + 64 * (size_t)idx);
     float4 rh[16], rt[16];
+    if (!RETARGET) {
 #pragma unroll
-    for (int q = 0; q < 16; q++) { rh[q] = __ldg(AhF + q); rt[q] = __ldg(AtF + q); }
+      for (int q = 0; q < 16; q++) { rh[q] = __ldg(AhF + q); rt[q] = __ldg(AtF + q); }
+    } else {   // setAdjointsF for this pair, from the (new) evaluation points
+      double Adj[36];
+      rigid_adj(rigid_inverse(rigid_from34(Ft)), Adj);   // worldToTarget at the evaluation point
+      double AH[64], AT[64];
+      for (int i = 0; i < 64; i++) AH[i] = AT[i] = 0.0;
+      for (int i = 0; i < 8; i++) AH[9 * i] = AT[9 * i] = 1.0;
+      for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) { AH[8 * i + j] = Adj[6 * j + i]; AT[8 * i + j] = -Adj[6 * j + i]; }
+      float eF = (float)Fh[52], eT = (float)Ft[52];
+      if (eF == 0 || eT == 0) eT = eF = 1;
+      const float a0 = (float)(exp(Ft[22 + 6] * SC_A - Fh[22 + 6] * SC_A) * eT / eF);   // aff_g2l_0 of both frames
+      AT[8 * 6 + 6] = -a0; AH[8 * 6 + 6] = a0; AT[8 * 7 + 7] = -1; AH[8 * 7 + 7] = a0;
+      const double rs[8] = {SC_T, SC_T, SC_T, SC_R, SC_R, SC_R, SC_A, SC_B};
+      double *gH = a.adHost + 64 * (size_t)idx, *gT = a.adTarget + 64 * (size_t)idx;
+      float *gHf = const_cast<float *>(a.adHostF) + 64 * (size_t)idx, *gTf = const_cast<float *>(a.adTargetF) + 64 * (size_t)idx;
+      float fh[64], ft[64];
+      for (int i = 0; i < 8; i++)
+        for (int j = 0; j < 8; j++) {
+          const double vh = AH[8 * i + j] * rs[i], vt = AT[8 * i + j] * rs[i];
+          gH[8 * i + j] = vh; gT[8 * i + j] = vt;
+          fh[8 * i + j] = (float)vh; ft[8 * i + j] = (float)vt;
+          gHf[8 * i + j] = fh[8 * i + j]; gTf[8 * i + j] = ft[8 * i + j];
+        }
+#pragma unroll
+      for (int q = 0; q < 16; q++) {
+        rh[q] = make_float4(fh[4 * q], fh[4 * q + 1], fh[4 * q + 2], fh[4 * q + 3]);
+        rt[q] = make_float4(ft[4 * q], ft[4 * q + 1], ft[4 * q + 2], ft[4 * q + 3]);
+      }
+    }
     float pre[SOSBA_PRECALC_FLOATS];
     const Rigid l0 = rigid_mul(rigid_inverse(rigid_from34(Ft)), rigid_from34(Fh));
     for (int i = 0; i < 9; i++) pre[SOSBA_PC_RTLL0 + i] = (float)l0.R[i];
@@ -553,6 +602,9 @@ __device__ void frame_step_body(const StepArgs &a) {
   }
 }
 
+
+// the new evaluation point of the newest keyframe at the end of FullSystem::optimize, with all dependent window tables
+__global__ void __launch_bounds__(256) k_frame_retarget(StepArgs a) { frame_step_body<true>(a); }
 
 // resubstitute with a caller-provided x: only the xAd part of the kernel above
 __global__ void __launch_bounds__(256) k_make_xad(const double *__restrict__ x, int nf, const float *__restrict__ adHostF,
@@ -613,5 +665,10 @@ int launch_solve(sosba *h, const SolveArgs &a0) {
 
 void launch_make_xad(sosba *h, const double *d_x, int nf, const float *adHostF, const float *adTargetF, float *xAd) {
   k_make_xad<<<1, 256, 0, h->stream>>>(d_x, nf, adHostF, adTargetF, xAd);
+  h->launches++;
+}
+
+void launch_frame_retarget(sosba *h, const StepArgs &a) {
+  k_frame_retarget<<<1, 256, 0, h->stream>>>(a);
   h->launches++;
 }

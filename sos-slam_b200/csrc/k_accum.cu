@@ -311,6 +311,7 @@ constexpr int ADJ_ST = 68;   // floats per staged 8x8 adjoint (64 + 4: float4 ro
 constexpr int ACC_THREADS = 512;   // warps 0..7: point sums (8 lanes per point), warps 8..15: top blocks (one target each), concurrently
 __global__ void __launch_bounds__(ACC_THREADS) k_accumulate_fused(FusedAccArgs a, int DP, int DPAD, int ntiles4, int tiles_total, int max_res) {
   extern __shared__ __align__(16) float smem[];
+  PDL_ENTER();
   if (a.gate && *a.gate) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (a.do_th && blockIdx.x == gridDim.x - 1) { energy_th_body(a.th); return; }
@@ -549,6 +550,7 @@ __global__ void __launch_bounds__(64) k_stitch_top(const double *__restrict__ ac
                                                    const double *__restrict__ adTarget, int nf, double *__restrict__ H, double *__restrict__ b) {
   __shared__ double accH[13][13];
   __shared__ double Ah[64], At[64], AhP[64], AtP[64];
+  PDL_ENTER();
   const int blk = blockIdx.x % (nf * nf);   // = h + nf*t ; blockIdx.x / nf^2 selects the table (A pass, L pass)
   const int h = blk % nf, t = blk / nf;
   const double *src = accTop + (size_t)blockIdx.x * SOSBA_TOPB;
@@ -641,6 +643,7 @@ __global__ void __launch_bounds__(256) k_finalize_sc(const double *__restrict__ 
 // lane q owns residual res_begin[p] + q; the subtraction chain runs in residual order like the reference.
 __global__ void __launch_bounds__(256) k_resubstitute(ResubArgs a) {
   __shared__ double s_sum[3];
+  PDL_ENTER();
   if (a.gate && *a.gate) return;
   if (a.zero_lin && blockIdx.x == 0 && threadIdx.x < 7) {   // energy | pad | counts[0..4] of the linearisation that follows
     if (threadIdx.x < 2) a.zero_lin[threadIdx.x] = 0.0;
@@ -748,7 +751,7 @@ void launch_stitch_top(sosba *h, const double *accTop, const double *adHost, con
 
 // hot path: both tables (A | L) into one raw H, b; symmetrisation and priors happen inside k_solve
 void launch_stitch_raw(sosba *h, const double *accTop2, const double *adHost, const double *adTarget, int nf, int ntables, double *H, double *b) {
-  k_stitch_top<<<ntables * nf * nf, 64, 0, h->stream>>>(accTop2, adHost, adTarget, nf, H, b);
+  launch_pdl(k_stitch_top, ntables * nf * nf, 64, 0, h->stream, accTop2, adHost, adTarget, nf, H, b);
   h->launches++;
 }
 
@@ -759,7 +762,7 @@ void launch_finalize_sc(sosba *h, const double *accSC, int nf, double *H, double
 
 void launch_resubstitute(sosba *h, const ResubArgs &a) {
   if (a.P == 0) return;
-  k_resubstitute<<<(a.P * 8 + 255) / 256, 256, 0, h->stream>>>(a);
+  launch_pdl(k_resubstitute, (a.P * 8 + 255) / 256, 256, 0, h->stream, a);
   h->launches++;
 }
 
@@ -782,7 +785,7 @@ bool launch_accumulate_fused(sosba *h, const FusedAccArgs &a, int max_res_per_ti
     configured = 200 * 1024;
   }
   int workers = tiles_total < 2 * h->sm_count ? tiles_total : 2 * h->sm_count;
-  k_accumulate_fused<<<workers + (a.do_th ? 1 : 0), ACC_THREADS, smem, h->stream>>>(a, DP, DPAD, ntiles4, tiles_total, max_res);
+  launch_pdl(k_accumulate_fused, workers + (a.do_th ? 1 : 0), ACC_THREADS, smem, h->stream, a, DP, DPAD, ntiles4, tiles_total, max_res);
   h->launches++;
   return true;
 }

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
   __shared__ double s_energy;
   __shared__ int s_cnt[3];
   __shared__ int s_last;
+  PDL_ENTER();
   // first round trip: the loop gate and every per-residual id / flag at once (independent loads)
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = gid >> 3, idx = gid & 7;
@@ -628,11 +629,11 @@ void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j, bool th_in
   if (a.R == 0) { if (th_inline) { k_energy_th<<<1, 256, 0, h->stream>>>(a.th, a.gate); h->launches++; } return; }
   const int blocks = (a.R * 8 + 255) / 256;
   if (write_j) {
-    if (th_inline) k_linearize<true, true, true><<<blocks, 256, 0, h->stream>>>(a);
-    else k_linearize<true, true, false><<<blocks, 256, 0, h->stream>>>(a);
+    if (th_inline) launch_pdl(k_linearize<true, true, true>, blocks, 256, 0, h->stream, a);
+    else launch_pdl(k_linearize<true, true, false>, blocks, 256, 0, h->stream, a);
   } else {
-    if (th_inline) k_linearize<true, false, true><<<blocks, 256, 0, h->stream>>>(a);
-    else k_linearize<true, false, false><<<blocks, 256, 0, h->stream>>>(a);
+    if (th_inline) launch_pdl(k_linearize<true, false, true>, blocks, 256, 0, h->stream, a);
+    else launch_pdl(k_linearize<true, false, false>, blocks, 256, 0, h->stream, a);
   }
   h->launches++;
 }

@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
   const int warp = tid >> 5, lane = tid & 31;
   const int ty = tid >> 4, tx = tid & 15;
 #define SOLVE_TS(n) do { if (a.dbg && tid == 0) a.dbg[n] = clock64(); } while (0)
+  PDL_ENTER();
   SOLVE_TS(0);
   if (a.ctl) {   // did the previous loop body converge?  (doStepFromBackup's return value, FullSystemOptimize.cpp:238-256)
     __shared__ int s_stop;
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
     if (s_stop) return;
   }
   if (tid == 0 && a.res_out) a.res_out[0] = a.res_in[0];
+  if (a.zero_rstats && tid < 4) a.zero_rstats[tid] = 0.0;   // the back-substitution sums of this body (k_resubstitute follows)
 
   // ---- stage the inputs in shared memory: one thread issues the bulk copies, everyone waits on the mbarrier ------
   const double *Hsrc = M, *Ssrc = a.accSC, *HMsrc = a.HM;
@@ -563,9 +565,11 @@ __device__ void frame_step_body(const StepArgs &a) {
       }
     }
     float pre[SOSBA_PRECALC_FLOATS];
-    const Rigid l0 = rigid_mul(rigid_inverse(rigid_from34(Ft)), rigid_from34(Fh));
-    for (int i = 0; i < 9; i++) pre[SOSBA_PC_RTLL0 + i] = (float)l0.R[i];
-    for (int i = 0; i < 3; i++) pre[SOSBA_PC_TTLL0 + i] = (float)l0.t[i];
+    if (RETARGET) {   // PRE_RTll_0 / PRE_tTll_0 depend on the evaluation points only: constant while the loop runs
+      const Rigid l0 = rigid_mul(rigid_inverse(rigid_from34(Ft)), rigid_from34(Fh));
+      for (int i = 0; i < 9; i++) pre[SOSBA_PC_RTLL0 + i] = (float)l0.R[i];
+      for (int i = 0; i < 3; i++) pre[SOSBA_PC_TTLL0 + i] = (float)l0.t[i];
+    }
     const Rigid l = rigid_mul(s_w2c[t], s_c2w[h]);
     float R[9], tt[3], KR[9];
     for (int i = 0; i < 9; i++) R[i] = (float)l.R[i];
@@ -584,7 +588,7 @@ __device__ void frame_step_body(const StepArgs &a) {
     pre[28] = pre[29] = pre[30] = pre[31] = 0.f;
     float4 *p4 = (float4 *)(a.precalc + (size_t)e * SOSBA_PRECALC_FLOATS);
 #pragma unroll
-    for (int q = 0; q < 8; q++) p4[q] = make_float4(pre[4 * q], pre[4 * q + 1], pre[4 * q + 2], pre[4 * q + 3]);
+    for (int q = RETARGET ? 0 : 3; q < 8; q++) p4[q] = make_float4(pre[4 * q], pre[4 * q + 1], pre[4 * q + 2], pre[4 * q + 3]);
     // adHTdeltaF[h + t*nf] = delta_h^T adHostF + delta_t^T adTargetF, summed over k in order
     float sh[8] = {0, 0, 0, 0, 0, 0, 0, 0}, st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -647,7 +651,7 @@ static int launch_solve_t(sosba *h, SolveArgs &a) {
   if (smem + bytesS <= dyn_max) { a.stage_sc = 1; smem += bytesS; }
   if (a.stage_sc && a.HM && smem + (size_t)D * D * 8 <= dyn_max) { a.stage_hm = 1; smem += (size_t)D * D * 8; }
   if (smem > dyn_max) { sosba_set_error("window too large for the single-CTA solve (D=%d)", D); return SOSBA_E_ARG; }
-  k_solve<T><<<1, SOLVE_THREADS, smem, h->stream>>>(a);
+  SOSBA_CUDA(launch_pdl(k_solve<T>, 1, SOLVE_THREADS, smem, h->stream, a));
   SOSBA_CUDA(cudaGetLastError());
   h->launches++;
   return SOSBA_OK;

@@ -1,7 +1,24 @@
 // kernels.h — launchers of the sm_100a kernels (k_exact.cu: built with -fmad=false so per-residual float
 // expressions round exactly like the parity definition; k_accum.cu / k_solve.cu / k_tracker.cu).
 #pragma once
+#include <utility>
+
 #include "sosba_internal.h"
+
+// Programmatic dependent launch (PDL) for the kernels of the Gauss-Newton loop body: the next launch may be scheduled
+// while the current grid drains; every such kernel starts with PDL_ENTER() — let ITS dependents launch early, then wait
+// until the grid it depends on has completed and its memory is visible.  Without the launch attribute both are no-ops.
+#define PDL_ENTER() do { asm volatile("griddepcontrol.launch_dependents;"); asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ---- k_exact.cu ---------------------------------------------------------------------------------
 // setNewFrameEnergyTH: k-th smallest of the newest-frame energies -> frameEnergyTH[nf-1], thOut[0].
@@ -173,6 +190,7 @@ struct SolveArgs {
   const double *prev_rstats;   // back-substitution sums of body iter_index-1: [0] sum step^2 [1] sum |idepth| [2] count
   const int *res_in;           // resInA of the accumulation this solve consumes ...
   int *res_out;                // ... copied where the table clearing of the next linearisation does not reach
+  double *zero_rstats;         // non-null: clear the 4 back-substitution sums the following k_resubstitute accumulates into
 };
 int launch_solve(sosba *h, const SolveArgs &a);
 

@@ -804,7 +804,7 @@ static int enqueue_blocks(sosba *h) {
   const int nf = h->nf;
   const size_t n2 = (size_t)nf * nf;
   if (!hs->tables_clean) cudaMemsetAsync(hs->d_scratch, 0, sizeof(double) * hs->scratch_doubles, h->stream);
-  else cudaMemsetAsync(hs->d_rstats + 4 * hs->rstats_par, 0, sizeof(double) * 4, h->stream);   // back-substitution sums of this body
+  // (clean tables: the back-substitution sums of this body are cleared by k_solve)
   hs->tables_clean = false;
   bool fused = false;
   if (hs->fused_acc_ok) {
@@ -921,6 +921,7 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
   s.ctl = hs->gate ? hs->d_ctl : nullptr; s.iter_index = hs->loop_iter; s.min_it = h->cfg.min_opt_iterations; s.th_opt = h->cfg.th_opt_iterations;
   s.prev_rstats = hs->d_rstats + 4 * (hs->rstats_par ^ 1);
   s.res_in = hs->d_cnt; s.res_out = hs->d_ctl + 3;
+  s.zero_rstats = hs->d_rstats + 4 * hs->rstats_par;
   static const bool solve_debug = getenv("SOSBA_SOLVE_DEBUG") != nullptr;
   if (solve_debug) {   // phase timestamps of the last 64 launches, no host sync: read back and printed by sosba_destroy
     if (!g_dbg) cudaMalloc(&g_dbg, (64 * 32 + 16) * sizeof(long long));

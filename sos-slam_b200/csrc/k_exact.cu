@@ -110,8 +110,8 @@ __device__ __forceinline__ float bfly8(unsigned mask, float v);
 // TH: the last CTA to finish runs setNewFrameEnergyTH (FullSystemOptimize.cpp:84-124) — no separate launch.
 template <bool APPLY, bool WRITE_J, bool TH>
 __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
-  __shared__ double s_energy;
-  __shared__ int s_cnt[3];
+  __shared__ double s_we[8];    // per-warp energy sums (no shared-memory fp64 atomics: those are CAS loops)
+  __shared__ int s_wc[8][3];    // per-warp state histogram
   __shared__ int s_last;
   PDL_ENTER();
   // first round trip: the loop gate and every per-residual id / flag at once (independent loads)
@@ -123,7 +123,6 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
   const int m_pt = inr ? a.r_point[r] : 0, m_host = inr ? a.r_host[r] : 0, m_target = inr ? a.r_target[r] : 0;
   const float m_energy = inr ? a.r_energy[r] : 0.f;
   if (gate) return;   // the Gauss-Newton loop already converged (device-side break)
-  if (threadIdx.x == 0) { s_energy = 0.0; s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; }
   if (a.zero_n > 0) {              // clear the block tables of the accumulation that follows (one memset less on the stream)
     double2 *zb = (double2 *)a.zero_buf;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.zero_n; i += gridDim.x * blockDim.x) zb[i] = make_double2(0.0, 0.0);
@@ -323,8 +322,6 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
     if (idx == 0) {
       a.r_new_state[r] = (uint8_t)outcome;
       a.r_new_energy_wo[r] = energyWO;
-      atomicAdd(&s_energy, (double)ret_energy);
-      atomicAdd(&s_cnt[outcome], 1);
       if (APPLY && m_state != SOSBA_RES_OOB) {   // applyRes(true): "can never go back from OOB" (Residuals.cpp:306-309)
         a.r_is_active[r] = outcome == SOSBA_RES_IN ? 1 : 0;
         a.r_state[r] = (uint8_t)outcome;
@@ -334,12 +331,26 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
       }
     }
   }
+  {  // energy and state histogram: 4 residual leaders per warp -> warp sum -> CTA sum (fixed order) -> one atomic each
+    const bool lead = live && idx == 0;
+    double e = lead ? (double)ret_energy : 0.0;
+    int c0 = lead && outcome == 0, c1 = lead && outcome == 1, c2 = lead && outcome == 2;
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) {
+      e += __shfl_xor_sync(0xffffffffu, e, o);
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o); c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+    if ((threadIdx.x & 31) == 0) { const int w = threadIdx.x >> 5; s_we[w] = e; s_wc[w][0] = c0; s_wc[w][1] = c1; s_wc[w][2] = c2; }
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (s_energy != 0.0) atomicAdd(&a.stats[0], s_energy);
-    if (s_cnt[0]) atomicAdd(&a.counts[0], s_cnt[0]);
-    if (s_cnt[1]) atomicAdd(&a.counts[1], s_cnt[1]);
-    if (s_cnt[2]) atomicAdd(&a.counts[2], s_cnt[2]);
+    double e = 0.0;
+    int c[3] = {0, 0, 0};
+    for (int w = 0; w < 8; w++) { e += s_we[w]; c[0] += s_wc[w][0]; c[1] += s_wc[w][1]; c[2] += s_wc[w][2]; }
+    if (e != 0.0) atomicAdd(&a.stats[0], e);
+    if (c[0]) atomicAdd(&a.counts[0], c[0]);
+    if (c[1]) atomicAdd(&a.counts[1], c[1]);
+    if (c[2]) atomicAdd(&a.counts[2], c[2]);
   }
   if (TH) {   // last CTA done: the newest-frame energies of every CTA are in place
     if (threadIdx.x == 0) {

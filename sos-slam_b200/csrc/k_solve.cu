@@ -13,6 +13,7 @@
 
 #include "host_math.h"
 #include "kernels.h"
+#include "resub.cuh"
 
 namespace {
 
@@ -610,6 +611,15 @@ __device__ void frame_step_body(const StepArgs &a) {
 // the new evaluation point of the newest keyframe at the end of FullSystem::optimize, with all dependent window tables
 __global__ void __launch_bounds__(256) k_frame_retarget(StepArgs a) { frame_step_body<true>(a); }
 
+// The step of one loop body in ONE launch: the points (back-substitution + doStepFromBackup, CTAs 0..n-2) and, concurrently
+// in the spare last CTA, the frames / calibration / precalc / deltas.  Both only need x from k_solve.
+__global__ void __launch_bounds__(256) k_step(ResubArgs ra, StepArgs sa) {
+  PDL_ENTER();
+  if (ra.gate && *ra.gate) return;
+  if (blockIdx.x == gridDim.x - 1) { frame_step_body<false>(sa); return; }
+  resubstitute_body(ra, blockIdx.x, gridDim.x - 1);
+}
+
 // resubstitute with a caller-provided x: only the xAd part of the kernel above
 __global__ void __launch_bounds__(256) k_make_xad(const double *__restrict__ x, int nf, const float *__restrict__ adHostF,
                                                   const float *__restrict__ adTargetF, float *__restrict__ xAd) {
@@ -674,5 +684,11 @@ void launch_make_xad(sosba *h, const double *d_x, int nf, const float *adHostF, 
 
 void launch_frame_retarget(sosba *h, const StepArgs &a) {
   k_frame_retarget<<<1, 256, 0, h->stream>>>(a);
+  h->launches++;
+}
+
+void launch_step(sosba *h, const ResubArgs &ra, const StepArgs &sa) {
+  const int blocks = (ra.P * 8 + 255) / 256;
+  launch_pdl(k_step, blocks + 1, 256, 0, h->stream, ra, sa);
   h->launches++;
 }

@@ -211,6 +211,7 @@ struct ResubArgs {
   int zero_newE_n;     // floats + ints to clear, as 4-byte words
 };
 void launch_resubstitute(sosba *h, const ResubArgs &a);
+void launch_step(sosba *h, const ResubArgs &ra, const StepArgs &sa);   // resubstitute + frame step, concurrently, one launch
 
 // ---- k_tracker.cu -------------------------------------------------------------------------------
 struct TrackGSArgs {

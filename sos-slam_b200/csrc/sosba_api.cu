@@ -915,8 +915,8 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
   s.x = h->d_x; s.Hfinal = want_final ? Hpart(h, 3) : nullptr; s.bfinal = want_final ? bpart(h, 3) : nullptr;
   s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.xAd = h->d_xAd; s.status = hs->d_ctl + 2;
   s.dbg = nullptr;
-  s.do_step = do_step;
-  s.step = step_args(h);
+  s.do_step = 0;            // the frame step runs in the spare CTA of the step launch, beside the back-substitution
+  s.step = step_args(h);    // (k_solve still reads step.iter: the step norms of the previous body, for the loop latch)
   s.stage_sc = s.stage_hm = 0;
   s.ctl = hs->gate ? hs->d_ctl : nullptr; s.iter_index = hs->loop_iter; s.min_it = h->cfg.min_opt_iterations; s.th_opt = h->cfg.th_opt_iterations;
   s.prev_rstats = hs->d_rstats + 4 * (hs->rstats_par ^ 1);
@@ -934,7 +934,8 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
       ra.zero_lin = h->d_stats;
       if (h->d_newE_all) { ra.zero_newE = h->d_newE_all; ra.zero_newE_n = h->world * h->newE_cap + h->world; }
     }
-    launch_resubstitute(h, ra);
+    if (do_step) launch_step(h, ra, step_args(h));
+    else launch_resubstitute(h, ra);
   }
   SOSBA_CUDA(cudaGetLastError());
   return SOSBA_OK;

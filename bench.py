@@ -337,6 +337,45 @@ def main():
         e2e_ms, e2e_res = float(tmax[0]), float(tsum[1])
     e2e_value = e2e_res / (e2e_ms * 1e-3)
 
+    # ---- the other kernels of the path: per-call time, host buffers in ------------
+    other = None
+    if rank == 0:
+        try:
+            reps = 30
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                h.frame_make_images(sc.nf, sc.images[-1])      # a1: H2D of the irradiance image + the 4-level pyramid
+            h.synchronize()
+            pyr_ms = 1e3 * (time.perf_counter() - t0) / reps
+            rng = np.random.default_rng(5)
+            n_ref = 10000
+            K = sc.K.astype(np.float32)
+            h.tracker_make_k(K)
+            u = rng.integers(2, sc.w - 2, n_ref).astype(np.float32)
+            v = rng.integers(2, sc.h - 2, n_ref).astype(np.float32)
+            idp = rng.uniform(0.35, 0.65, n_ref).astype(np.float32)
+            col = sc.images[0][v.astype(int), u.astype(int)].astype(np.float32)
+            h.tracker_set_ref(0, u, v, idp, col)
+            T = (np.linalg.inv(sc.camToWorld_true[1]) @ sc.camToWorld_true[0])[:3, :4]
+            h.scale_set_stereo(T, K)
+            h.tracker_calc_res_pose(0, 1, T, (1.0, 0.0), 20.0)
+            h.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                h.tracker_calc_res_pose(0, 1, T, (1.0, 0.0), 20.0)      # a14 (returns the Vec6 to the host: one sync per call, as the LM loop needs)
+                h.tracker_calc_gs_pose(0, 1.0, 0.0)                      # a15
+            trk_ms = 1e3 * (time.perf_counter() - t0) / reps
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                h.scale_calc_res(0, 1, 1.0, 20.0)                        # a17
+                h.scale_calc_gs(0, 1.0)
+            scl_ms = 1e3 * (time.perf_counter() - t0) / reps
+            other = {"make_images_ms": pyr_ms, "make_images_note": f"{sc.w}x{sc.h}, H2D + 4 levels, host wall per call",
+                     "tracker_calcRes_plus_calcGS_ms": trk_ms, "scale_calcRes_plus_calcGS_ms": scl_ms,
+                     "tracker_note": f"level 0, {n_ref} reference points, results returned to the host each call (host wall)"}
+        except Exception as ex:   # the BA numbers above do not depend on this block
+            other = {"error": str(ex)}
+
     # ---- roofline of the dominant kernel (linearize) ---------------------------------------------------
     peak, peak_src = measured_peak()
     R_lin = out["reserved0"]
@@ -389,7 +428,7 @@ def main():
                            "l2": "flushed between steps (256 MiB fill); per-step CUDA events on the launch stream", "parallelism": f"points/{world}"},
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                                           "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "other_kernels": other,
                 "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps, "final_rmse": out["rmse"]}
         print(json.dumps(line), flush=True)
     h.close()

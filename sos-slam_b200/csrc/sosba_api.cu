@@ -72,6 +72,8 @@ struct HostSide {
   bool fused_acc_ok = false;    // every (point, target) pair holds at most one residual and a tile fits shared memory
   int max_res_per_tile = 0, n_tiles = 0, tiles_cap = 0;
   int *d_tiles = nullptr;       // int4 per tile of the fused accumulation
+  float *p_zero_arena = nullptr;   // point outputs / CSR that start from zero (one memset per points_set)
+  size_t p_zero_words = 0;
   char *stage = nullptr;        // pinned staging ring of up()
   size_t stage_cap = 0, stage_off = 0;
   bool prof_on = false;
@@ -428,14 +430,23 @@ API int sosba_window_update(sosba_t *h, const sosba_window *w) { CHECK_H(h); if 
 
 static int ensure_points(sosba *h, int P) {
   if (P <= h->P_alloc) return SOSBA_OK;
-  float **fl[] = {&h->p_u, &h->p_v, &h->p_idepth, &h->p_idepth_zero, &h->p_priorF, &h->p_deltaF, &h->p_HddA, &h->p_bdA, &h->p_HddL, &h->p_bdL,
-                  &h->p_HdiF, &h->p_bdSumF, &h->p_step, &h->p_idepth_backup, &h->p_idepth_hessian, &h->p_maxRelBaseline};
+  HostSide *hs = HS(h);
+  float **fl[] = {&h->p_u, &h->p_v, &h->p_idepth, &h->p_idepth_zero, &h->p_priorF, &h->p_deltaF};
   for (auto p : fl) dfree(h, *p);
-  dfree(h, h->p_color); dfree(h, h->p_weights); dfree(h, h->p_HcdA); dfree(h, h->p_HcdL); dfree(h, h->p_host); dfree(h, h->p_res_begin); dfree(h, h->p_numGood);
-  const size_t n = (size_t)P + (size_t)P / 4 + 64;
+  dfree(h, h->p_color); dfree(h, h->p_weights); dfree(h, h->p_host); dfree(h, hs->p_zero_arena);
+  const size_t n = ((size_t)P + (size_t)P / 4 + 64 + 3) & ~(size_t)3;
   for (auto p : fl) DALLOC(h, *p, n);
-  DALLOC(h, h->p_color, n * 8); DALLOC(h, h->p_weights, n * 8); DALLOC(h, h->p_HcdA, n * 4); DALLOC(h, h->p_HcdL, n * 4);
-  DALLOC(h, h->p_host, n); DALLOC(h, h->p_res_begin, n + 1); DALLOC(h, h->p_numGood, n);
+  DALLOC(h, h->p_color, n * 8); DALLOC(h, h->p_weights, n * 8); DALLOC(h, h->p_host, n);
+  // everything a new point set starts from zero: one arena, one memset
+  hs->p_zero_words = 10 * n + 8 * n + n + (n + 4);
+  DALLOC(h, hs->p_zero_arena, hs->p_zero_words);
+  float *z = hs->p_zero_arena;
+  float **zl[] = {&h->p_HddA, &h->p_bdA, &h->p_HddL, &h->p_bdL, &h->p_HdiF, &h->p_bdSumF, &h->p_step, &h->p_idepth_backup, &h->p_idepth_hessian, &h->p_maxRelBaseline};
+  for (auto p : zl) { *p = z; z += n; }
+  h->p_HcdA = z; z += 4 * n;
+  h->p_HcdL = z; z += 4 * n;
+  h->p_numGood = (int *)z; z += n;
+  h->p_res_begin = (int *)z;
   h->P_alloc = (int)n;
   return SOSBA_OK;
 }
@@ -455,11 +466,7 @@ API int sosba_points_set(sosba_t *h, const sosba_points *p) {
     return rc;
   if (p->priorF) { if ((rc = up(h, h->p_priorF, p->priorF, n))) return rc; } else cudaMemsetAsync(h->p_priorF, 0, n * 4, h->stream);
   if (p->deltaF) { if ((rc = up(h, h->p_deltaF, p->deltaF, n))) return rc; } else cudaMemsetAsync(h->p_deltaF, 0, n * 4, h->stream);
-  float *z[] = {h->p_HddA, h->p_bdA, h->p_HddL, h->p_bdL, h->p_HdiF, h->p_bdSumF, h->p_step, h->p_idepth_backup, h->p_idepth_hessian, h->p_maxRelBaseline};
-  for (float *q : z) cudaMemsetAsync(q, 0, n * 4, h->stream);
-  cudaMemsetAsync(h->p_HcdA, 0, n * 16, h->stream); cudaMemsetAsync(h->p_HcdL, 0, n * 16, h->stream);
-  cudaMemsetAsync(h->p_numGood, 0, n * 4, h->stream);
-  cudaMemsetAsync(h->p_res_begin, 0, (n + 1) * 4, h->stream);
+  cudaMemsetAsync(hs->p_zero_arena, 0, hs->p_zero_words * 4, h->stream);   // accumulators, steps, CSR
   hs->res_begin.assign(n + 1, 0);
   h->R = 0;
   return SOSBA_OK;
@@ -1353,8 +1360,10 @@ API int sosba_ba_optimize(sosba_t *h, int32_t mnumOptIts, sosba_optimize_out *ou
   if (nf < 4) mnumOptIts = 15;
   // Everything below goes onto the stream without a host round trip; ONE synchronisation at the end reads the results.
   launch_reset_oob(h, lin_args(h));
-  enqueue_linearize(h, 0);
-  launch_apply_res(h, lin_args(h), 0);
+  flush_pending_th(h);
+  cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(double) + 5 * sizeof(int), h->stream);
+  clear_gathered_energies(h);
+  enqueue_linearize_apply(h, false);   // linearizeAll(false) + applyRes, fused
   // energy | pad | counts[16] | thOut of the first linearisation: stashed on the device, read at the end
   cudaMemcpyAsync(hs->d_stash, h->d_stats, 12 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
   // the whole loop: k_solve of body i latches "converged" from the step norms of body i-1 (doStepFromBackup's canbreak,

@@ -169,6 +169,28 @@ __device__ __forceinline__ void panel_rows(const double *__restrict__ pb, double
   }
 }
 
+// Back substitution L^T w = z, rows jhi..jlo (descending), all inside lane-register block MT (j >> 5 == MT): the step
+// chain is shuffle (w_j) -> fma; the factor row of the next step is always in flight.  L[j][i] = M4[off_i + 4 j].
+template <int W, int MT>
+__device__ __forceinline__ void backsub_segment(double (&w)[W], const double *__restrict__ M4, const int (&off)[W], const int jhi, const int jlo, const int lane) {
+  if (jhi < jlo) return;
+  double Ln[MT + 1];
+#pragma unroll
+  for (int m = 0; m <= MT; m++) Ln[m] = (m < MT || lane + 32 * m < jhi) ? M4[off[m] + jhi * 4] : 0.0;
+#pragma unroll 2
+  for (int j = jhi; j >= jlo; j--) {
+    double Lc[MT + 1];
+#pragma unroll
+    for (int m = 0; m <= MT; m++) {
+      Lc[m] = Ln[m];
+      Ln[m] = (j > jlo && (m < MT || lane + 32 * m < j - 1)) ? M4[off[m] + (j - 1) * 4] : 0.0;
+    }
+    const double wj = __shfl_sync(0xffffffffu, w[MT], j & 31);
+#pragma unroll
+    for (int m = 0; m <= MT; m++) w[m] = fma(-Lc[m], wj, w[m]);   // Lc is 0 for columns i >= j
+  }
+}
+
 template <bool RETARGET>
 __device__ void frame_step_body(const StepArgs &a);
 
@@ -375,28 +397,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
   __syncthreads();
   if (warp == 0) {
     constexpr int W = (16 * T + 31) / 32;
-    double w[W], Ln[W];
+    double w[W];
     int off[W];   // offset of column (lane + 32 m) inside a factor row
 #pragma unroll
     for (int m = 0; m < W; m++) {
       const int i = lane + 32 * m;
       off[m] = (i >> 2) * PST * 4 + (i & 3);
       w[m] = i < D ? M[off[m] + D * 4] : 0.0;
-      Ln[m] = i < D - 1 ? M[off[m] + (D - 1) * 4] : 0.0;
     }
-#pragma unroll 1
-    for (int j = D - 1; j > 0; j--) {
-      const int jm = j >> 5, jl = j & 31;
-      double Lc[W];
-#pragma unroll
-      for (int m = 0; m < W; m++) { Lc[m] = Ln[m]; const int i = lane + 32 * m; Ln[m] = (j > 1 && i < j - 1) ? M[off[m] + (j - 1) * 4] : 0.0; }
-      double own = 0.0;
-#pragma unroll
-      for (int m = 0; m < W; m++) own = m == jm ? w[m] : own;
-      const double wj = __shfl_sync(0xffffffffu, own, jl);
-#pragma unroll
-      for (int m = 0; m < W; m++) w[m] = fma(-Lc[m], wj, w[m]);   // Lc is 0 for i >= j
-    }
+    if (W > 3) backsub_segment<W, (W > 3 ? 3 : 0)>(w, M, off, min(D - 1, 127), 96, lane);
+    if (W > 2) backsub_segment<W, (W > 2 ? 2 : 0)>(w, M, off, min(D - 1, 95), 64, lane);
+    if (W > 1) backsub_segment<W, (W > 1 ? 1 : 0)>(w, M, off, min(D - 1, 63), 32, lane);
+    backsub_segment<W, 0>(w, M, off, min(D - 1, 31), 1, lane);
 #pragma unroll
     for (int m = 0; m < W; m++) { const int i = lane + 32 * m; if (i < D) z[i] = w[m]; }
   }
@@ -614,9 +626,30 @@ __global__ void __launch_bounds__(256) k_frame_retarget(StepArgs a) { frame_step
 // The step of one loop body in ONE launch: the points (back-substitution + doStepFromBackup, CTAs 0..n-2) and, concurrently
 // in the spare last CTA, the frames / calibration / precalc / deltas.  Both only need x from k_solve.
 __global__ void __launch_bounds__(256) k_step(ResubArgs ra, StepArgs sa) {
+  __shared__ __align__(16) float s_xad[16 * 16 * 8 + 4];
   PDL_ENTER();
   if (ra.gate && *ra.gate) return;
   if (blockIdx.x == gridDim.x - 1) { frame_step_body<false>(sa); return; }
+  // xAd[h*nf+t] = x_h^T adHostF[h+nf*t] + x_t^T adTargetF[h+nf*t] and xc (EnergyFunctional.cpp:509-513): every CTA builds
+  // the small table in shared memory (adjoints are L2-resident) instead of waiting for k_solve to do it serially
+  {
+    const int nf = ra.nf, tid = threadIdx.x;
+    const double *x = sa.x;
+    for (int e = tid; e < nf * nf * 8; e += blockDim.x) {
+      const int c = e & 7, ht = e >> 3, h = ht / nf, t = ht % nf;
+      const float *AhF = sa.adHostF + 64 * (size_t)(h + nf * t), *AtF = sa.adTargetF + 64 * (size_t)(h + nf * t);
+      float ah[8], at[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) { ah[k] = __ldg(AhF + k * 8 + c); at[k] = __ldg(AtF + k * 8 + c); }
+      float sh = 0.f, st = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; k++) { sh = fmaf((float)x[4 + 8 * h + k], ah[k], sh); st = fmaf((float)x[4 + 8 * t + k], at[k], st); }
+      s_xad[e] = sh + st;
+    }
+    if (tid < 4) s_xad[nf * nf * 8 + tid] = (float)x[tid];
+    __syncthreads();
+    ra.xAd = s_xad;
+  }
   resubstitute_body(ra, blockIdx.x, gridDim.x - 1);
 }
 

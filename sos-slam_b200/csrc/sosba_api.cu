@@ -922,6 +922,7 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
   s.x = h->d_x; s.Hfinal = want_final ? Hpart(h, 3) : nullptr; s.bfinal = want_final ? bpart(h, 3) : nullptr;
   s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.xAd = h->d_xAd; s.status = hs->d_ctl + 2;
   s.dbg = nullptr;
+  if (do_step) s.xAd = nullptr;   // the step launch builds xAd per CTA
   s.do_step = 0;            // the frame step runs in the spare CTA of the step launch, beside the back-substitution
   s.step = step_args(h);    // (k_solve still reads step.iter: the step norms of the previous body, for the loop latch)
   s.stage_sc = s.stage_hm = 0;

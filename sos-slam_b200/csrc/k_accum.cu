@@ -656,6 +656,18 @@ __global__ void k_scale_prior(float *__restrict__ priorF, const int *__restrict_
 
 }  // namespace
 
+namespace {
+__global__ void k_fill_f32(float *__restrict__ dst, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
+}
+}  // namespace
+void launch_fill_f32(sosba *h, float *dst, int n, float v) {
+  if (n == 0) return;
+  k_fill_f32<<<(n + 255) / 256, 256, 0, h->stream>>>(dst, n, v);
+  h->launches++;
+}
+
 void launch_scale_prior(sosba *h, float *priorF, const int *ids, int n, float fac) {
   if (n == 0) return;
   k_scale_prior<<<(n + 255) / 256, 256, 0, h->stream>>>(priorF, ids, n, fac);

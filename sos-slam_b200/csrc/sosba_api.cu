@@ -20,6 +20,7 @@
 
 void launch_make_xad(sosba *h, const double *d_x, int nf, const float *adHostF, const float *adTargetF, float *xAd);
 void launch_scale_prior(sosba *h, float *priorF, const int *ids, int n, float fac);
+void launch_fill_f32(sosba *h, float *dst, int n, float v);
 void launch_stitch_raw(sosba *h, const double *accTop2, const double *adHost, const double *adTarget, int nf, int ntables, double *H, double *b);
 
 using sosba_host::BAState;
@@ -49,7 +50,7 @@ struct BA {
 
 // per-handle host mirrors that the device kernels never read
 struct HostSide {
-  std::vector<int> p_host, res_begin, r_point, r_target;
+  std::vector<int> p_host, res_begin, r_point, r_target, r_host_tmp;
   std::vector<void *> allocs;
   int n_lin = 0;
   double *pin_d = nullptr;   // pinned scratch: [4096] doubles
@@ -511,7 +512,8 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
   h->R = n;
   hs->r_point.assign(r->point, r->point + n);
   hs->r_target.assign(r->target, r->target + n);
-  std::vector<int> host(n), by_block(n), cnt(nf * nf + 1, 0);
+  std::vector<int> &host = hs->r_host_tmp;   // scratch vectors live in the handle: no allocation per keyframe
+  host.resize(n);
   hs->res_begin.assign(P + 1, 0);
   int prev = -1;
   for (int i = 0; i < n; i++) {
@@ -521,7 +523,6 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
     host[i] = hs->p_host[p];
     if (host[i] < 0 || host[i] >= nf) { sosba_set_error("point %d: host %d invalid", p, host[i]); return SOSBA_E_ARG; }
     hs->res_begin[p + 1]++;
-    cnt[host[i] + t * nf + 1]++;
   }
   for (int p = 0; p < P; p++) hs->res_begin[p + 1] += hs->res_begin[p];
   {  // the fused accumulation stages the residuals of up to 32 consecutive points of ONE host and lists them per target
@@ -563,14 +564,17 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
     h->d_newE_cnt = (int *)(h->d_newE_all + (size_t)h->world * h->newE_cap);
     clear_gathered_energies(h);
   }
-  for (int b = 0; b < nf * nf; b++) cnt[b + 1] += cnt[b];
-  for (int i = 0; i < n; i++) by_block[cnt[host[i] + r->target[i] * nf]++] = i;   // stable counting sort by block
-  std::vector<uint8_t> u8(n);
-  std::vector<float> e(n, 0.f);
   hs->n_lin = 0;
   if ((rc = up(h, h->r_point, r->point, n)) || (rc = up(h, h->r_target, r->target, n)) || (rc = up(h, h->r_host, host.data(), n)) ||
-      (rc = up(h, h->r_by_block, by_block.data(), n)) || (rc = up(h, h->p_res_begin, hs->res_begin.data(), P + 1)))
+      (rc = up(h, h->p_res_begin, hs->res_begin.data(), P + 1)))
     return rc;
+  if (!hs->fused_acc_ok) {   // only the un-fused accumulation walks the residuals in (host, target)-block order
+    std::vector<int> by_block(n), cnt(nf * nf + 1, 0);
+    for (int i = 0; i < n; i++) cnt[host[i] + r->target[i] * nf + 1]++;
+    for (int b = 0; b < nf * nf; b++) cnt[b + 1] += cnt[b];
+    for (int i = 0; i < n; i++) by_block[cnt[host[i] + r->target[i] * nf]++] = i;   // stable counting sort by block
+    if ((rc = up(h, h->r_by_block, by_block.data(), n))) return rc;
+  }
   auto upflag = [&](uint8_t *dst, const uint8_t *src, uint8_t dflt) -> int {
     if (src) return up(h, dst, src, n);
     cudaMemsetAsync(dst, dflt, n, h->stream);
@@ -585,8 +589,9 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
   cudaMemsetAsync(h->r_dropped, 0, n, h->stream);
   if (r->state_energy) { if ((rc = up(h, h->r_energy, r->state_energy, n)) || (rc = up(h, h->r_new_energy, r->state_energy, n))) return rc; }
   else { cudaMemsetAsync(h->r_energy, 0, (size_t)n * 4, h->stream); cudaMemsetAsync(h->r_new_energy, 0, (size_t)n * 4, h->stream); }
-  for (int i = 0; i < n; i++) e[i] = -1.f;
-  return up(h, h->r_new_energy_wo, e.data(), n);
+  launch_fill_f32(h, h->r_new_energy_wo, n, -1.f);   // state_NewEnergyWithOutlier = -1 until linearised (Residuals.cpp:78)
+  SOSBA_CUDA(cudaGetLastError());
+  return SOSBA_OK;
 }
 
 static LinArgs lin_args(sosba *h) {
@@ -1212,18 +1217,26 @@ API int sosba_ba_upload(sosba_t *h, const sosba_ba_problem *prob) {
   CHECK_H(h);
   if (!prob || prob->nf <= 0 || !prob->frames) return SOSBA_E_ARG;
   BA *ba = h->ba;
+  static const bool timing = getenv("SOSBA_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](auto a, auto b) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+  const auto t0 = now();
   ba->st.load(h->cfg, prob);
   ba->st.make_adjoints(h->cfg, ba->wt);
   ba->st.make_precalc(ba->wt);
   int rc;
+  const auto t1 = now();
   if ((rc = upload_tables(h, ba, true))) return rc;
+  const auto t2 = now();
   if ((rc = sosba_points_set(h, &prob->points))) return rc;
+  const auto t3 = now();
   {  // EnergyFunctional::setDeltaF: p->deltaF = idepth - idepth_zero (EnergyFunctional.cpp:187-191)
     std::vector<float> d(prob->points.n);
     for (int i = 0; i < prob->points.n; i++) d[i] = prob->points.idepth[i] - prob->points.idepth_zero[i];
     if ((rc = sosba_points_update(h, nullptr, nullptr, d.data()))) return rc;
   }
   if ((rc = sosba_residuals_set(h, &prob->residuals))) return rc;
+  if (timing) fprintf(stderr, "ba_upload: host tables %ld us, window %ld us, points %ld us, delta+residuals %ld us\n", us(t0, t1), us(t1, t2), us(t2, t3), us(t3, now()));
   const int D = 4 + 8 * prob->nf;
   ba->have_HM = !ba->st.HM.empty();
   if (ba->have_HM) {

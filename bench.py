@@ -45,9 +45,14 @@ def load():
     return pkg, binding, problem, synth
 
 
+WORKLOADS = {"configB": WORKLOAD,
+             "kitti": "KITTI-shaped 1232x368 stereo, 12-KF window, 4000 active points, BA only (BASELINE.json configs[3] shape, 1 GPU)"}
+_workload = "configB"
+
+
 def get_scene(synth, n_points_factor=1):
-    from _scenes import CONFIG_B, scene
-    sc = scene(**CONFIG_B)
+    from _scenes import CONFIG_B, KITTI, scene
+    sc = scene(**(KITTI if _workload == "kitti" else CONFIG_B))
     if n_points_factor > 1:
         sc = synth.replicate_points(sc, n_points_factor)
     return sc
@@ -207,7 +212,11 @@ def main():
     ap.add_argument("--impl", default="sosba")
     ap.add_argument("--points-factor", type=int, default=0, help="scaling sweep: multiply the 2000 points (default: = gpus)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="configB", choices=sorted(WORKLOADS), help="configB = the benchmark workload (BASELINE.json configs[1]); others are extra data points")
     args = ap.parse_args()
+    global _workload, WORKLOAD
+    _workload = args.workload
+    WORKLOAD = WORKLOADS[_workload]
     if args.impl == "reference":
         return run_reference(args)
 
@@ -370,7 +379,20 @@ def main():
                 h.scale_calc_res(0, 1, 1.0, 20.0)                        # a17
                 h.scale_calc_gs(0, 1.0)
             scl_ms = 1e3 * (time.perf_counter() - t0) / reps
+            # 8f rank 1: traceNewCoarse of 2000 immature points per older keyframe into the newest one (host buffers in and out)
+            case = synth.trace_case(sc, sc.nf - 1, n_per_host=2000, seed=3)
+            ip_parts = [h.immature_init(hst, case["u"][case["host"] == hst], case["v"][case["host"] == hst]) for hst in range(sc.nf - 1)]
+            ip = {k: np.concatenate([q[k] for q in ip_parts]) for k in ip_parts[0]}
+            trace_ms, trace_counts = [], None
+            for _ in range(5):
+                ipc = {k: x.copy() for k, x in ip.items()}
+                t0 = time.perf_counter()
+                trace_counts = h.trace_immature(sc.nf - 1, case["host"], case["KRKi"], case["Kt"], case["aff"], ipc)
+                trace_ms.append(1e3 * (time.perf_counter() - t0))
             other = {"make_images_ms": pyr_ms, "make_images_note": f"{sc.w}x{sc.h}, H2D + 4 levels, host wall per call",
+                     "trace_immature_ms": float(np.median(trace_ms)), "trace_immature_points": int(case["host"].size),
+                     "trace_immature_counts": [int(x) for x in trace_counts],
+                     "trace_note": "first trace (unbounded interval: the longest epipolar search), host SoA in and out, host wall per call",
                      "tracker_calcRes_plus_calcGS_ms": trk_ms, "scale_calcRes_plus_calcGS_ms": scl_ms,
                      "tracker_note": f"level 0, {n_ref} reference points, results returned to the host each call (host wall)"}
         except Exception as ex:   # the BA numbers above do not depend on this block

@@ -297,6 +297,40 @@ int sosba_ba_optimize(sosba_t *h, int32_t max_iterations, sosba_optimize_out *ou
 int sosba_ba_iterate(sosba_t *h, int32_t n, int32_t *n_res_linearized);
 int sosba_ba_download(sosba_t *h, sosba_ba_problem *prob);
 
+/* ---- next row: immature points ------------------------------------------------ */
+/* ImmaturePointStatus, ImmaturePoint.h:40-47 */
+enum { SOSBA_IPS_GOOD = 0, SOSBA_IPS_OOB = 1, SOSBA_IPS_OUTLIER = 2, SOSBA_IPS_SKIPPED = 3, SOSBA_IPS_BADCONDITION = 4, SOSBA_IPS_UNINITIALIZED = 5 };
+
+/* The members of ImmaturePoint (ImmaturePoint.h:50-92) that the constructor fills and traceOn reads / updates, SoA. */
+typedef struct sosba_immature {
+  int32_t n;
+  int32_t reserved0;
+  const int32_t *host;            /* [n] dense index of the host frame: selects KRKi / Kt / aff of traceNewCoarse */
+  const float *u, *v;             /* [n] host pixel (integers stored as float, ImmaturePoint.cpp:30) */
+  const float *color;             /* [n*8] */
+  const float *weights;           /* [n*8] */
+  const float *gradH;             /* [n*4] Mat22f, row-major (symmetric) */
+  const float *energy_th;         /* [n] */
+  float *idepth_min, *idepth_max; /* [n] in/out; a fresh point has 0 / NaN */
+  float *quality;                 /* [n] in/out; a fresh point has 10000 */
+  uint8_t *last_trace_status;     /* [n] in/out ImmaturePointStatus */
+  float *last_trace_uv;           /* [n*2] out */
+  float *last_trace_pixel_interval; /* [n] out */
+} sosba_immature;
+
+/* ImmaturePoint::ImmaturePoint (ImmaturePoint.cpp:28-60): color / weights / gradH / energyTH of n candidate pixels of the
+ * frame in `host_slot` (getInterpolatedElement33BiLin, globalFuncs.h:162-182).  energy_th is NaN where a colour is not
+ * finite (the reference then discards the point).  Outputs are host buffers. */
+int sosba_immature_init(sosba_t *h, int32_t host_slot, int32_t n, const int32_t *u, const int32_t *v, float *color /*[n*8]*/,
+                        float *weights /*[n*8]*/, float *gradH /*[n*4]*/, float *energy_th /*[n]*/);
+
+/* FullSystem::traceNewCoarse (FullSystem.cpp:311-361): ImmaturePoint::traceOn (ImmaturePoint.cpp:70-415) of every point
+ * against the frame in `frame_slot`.  KRKi [nhosts*9] row-major, Kt [nhosts*3], aff [nhosts*2]: hostToFrame_KRKi /
+ * hostToFrame_Kt / hostToFrame_affine per host.  counts[6]: points per ImmaturePointStatus after the pass
+ * (trace_good, _oob, _out, _skip, _badcondition, _uninitialized). */
+int sosba_trace_immature(sosba_t *h, int32_t frame_slot, int32_t nhosts, const float *KRKi, const float *Kt, const float *aff,
+                         sosba_immature *pts, int32_t counts[6]);
+
 /* ---- multi-GPU: points shard across ranks, one all-reduce of [H,b] per GN iteration ----------- */
 /* 128-byte NCCL unique id (rank 0 creates, caller broadcasts, every rank inits). */
 int sosba_comm_unique_id(uint8_t id[128]);

@@ -387,3 +387,17 @@ ORC_API void orc_se3_exp(const double a[6], double T[12]) { se3_exp(a).to_rowmaj
 ORC_API void orc_se3_log(const double T[12], double a[6]) { se3_log(SE3::from_rowmajor34(T), a); }
 ORC_API void orc_se3_adj(const double T[12], double A[36]) { se3_adj(SE3::from_rowmajor34(T), A); }
 ORC_API void orc_ldlt_solve(const double *A, const double *b, double *x, int32_t n) { ldlt_solve(A, b, x, n); }
+
+// ---- next row: immature points ----------------------------------------------------
+ORC_API int orc_immature_init(orc_handle *h, int32_t slot, int32_t n, const int32_t *u, const int32_t *v, float *color, float *weights, float *gradH,
+                              float *energy_th) {
+  if (slot < 0 || slot >= (int)h->o.slots.size() || n < 0) return SOSBA_E_ARG;
+  immature_init(h->o, slot, n, u, v, color, weights, gradH, energy_th);
+  return SOSBA_OK;
+}
+ORC_API int orc_trace_immature(orc_handle *h, int32_t frame_slot, int32_t nhosts, const float *KRKi, const float *Kt, const float *aff,
+                               sosba_immature *pts, int32_t counts[6]) {
+  if (frame_slot < 0 || frame_slot >= (int)h->o.slots.size() || !pts) return SOSBA_E_ARG;
+  trace_immature(h->o, frame_slot, nhosts, KRKi, Kt, aff, pts, counts);
+  return SOSBA_OK;
+}

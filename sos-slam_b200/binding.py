@@ -76,6 +76,16 @@ class BAProblem(C.Structure):
                 ("residuals", Residuals), ("HM", f64p), ("bM", f64p), ("idepth_out", f32p)]
 
 
+class Immature(C.Structure):
+    _fields_ = [("n", C.c_int32), ("reserved0", C.c_int32), ("host", i32p), ("u", f32p), ("v", f32p), ("color", f32p),
+                ("weights", f32p), ("gradH", f32p), ("energy_th", f32p), ("idepth_min", f32p), ("idepth_max", f32p),
+                ("quality", f32p), ("last_trace_status", u8p), ("last_trace_uv", f32p),
+                ("last_trace_pixel_interval", f32p)]
+
+
+IPS_GOOD, IPS_OOB, IPS_OUTLIER, IPS_SKIPPED, IPS_BADCONDITION, IPS_UNINITIALIZED = range(6)
+
+
 class OptimizeOut(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("res_in_a", C.c_int32), ("energy_initial", C.c_double),
                 ("energy_final", C.c_double), ("rmse", C.c_float), ("n_removed", C.c_int32),
@@ -128,7 +138,7 @@ class Lib:
                   "accumulate", "points_get_acc", "solve_system", "resubstitute", "marginalize_points",
                   "tracker_make_k", "tracker_set_ref", "tracker_calc_res_pose", "tracker_calc_gs_pose",
                   "scale_set_stereo", "scale_calc_res", "scale_calc_gs", "optimize", "ba_upload", "ba_iterate",
-                  "ba_download", "ba_optimize", "pyr_levels"):
+                  "ba_download", "ba_optimize", "pyr_levels", "immature_init", "trace_immature"):
             self.f(n).restype = C.c_int
         self.f("destroy").restype = None
         if self.has("launch_count"):
@@ -385,6 +395,37 @@ class Handle:
     def tracker_set_ref(self, lvl, u, v, idepth, color):
         u, v, idepth, color = _f32(u), _f32(v), _f32(idepth), _f32(color)
         self._ck(self.lib.f("tracker_set_ref")(self.h, C.c_int32(lvl), C.c_int32(u.size), _p(u, f32p), _p(v, f32p), _p(idepth, f32p), _p(color, f32p)), "tracker_set_ref")
+
+    # ---- immature points (ImmaturePoint.cpp:28-60, 70-415; FullSystem.cpp:311-361)
+    def immature_init(self, host_slot, u, v):
+        """-> dict of the constructor's outputs for candidate pixels (u, v) of the frame in `host_slot`; idepth interval,
+        quality and status are the fresh point's (0 / NaN, 10000, UNINITIALIZED)."""
+        u, v = _i32(u), _i32(v)
+        n = u.size
+        out = dict(u=u.astype(np.float32), v=v.astype(np.float32), color=np.zeros((n, 8), np.float32), weights=np.zeros((n, 8), np.float32),
+                   gradH=np.zeros((n, 4), np.float32), energy_th=np.zeros(n, np.float32), idepth_min=np.zeros(n, np.float32),
+                   idepth_max=np.full(n, np.nan, np.float32), quality=np.full(n, 10000, np.float32),
+                   status=np.full(n, IPS_UNINITIALIZED, np.uint8), uv=np.zeros((n, 2), np.float32), pixel_interval=np.zeros(n, np.float32))
+        self._ck(self.lib.f("immature_init")(self.h, C.c_int32(host_slot), C.c_int32(n), _p(u, i32p), _p(v, i32p), _p(out["color"], f32p),
+                                             _p(out["weights"], f32p), _p(out["gradH"], f32p), _p(out["energy_th"], f32p)), "immature_init")
+        return out
+
+    def trace_immature(self, frame_slot, host, KRKi, Kt, aff, pts):
+        """traceOn of every point in `pts` (the dict of immature_init, updated in place) against `frame_slot`;
+        host [n] indexes KRKi [nh,3,3] / Kt [nh,3] / aff [nh,2].  -> counts[6] per ImmaturePointStatus."""
+        host, KRKi, Kt, aff = _i32(host), _f32(KRKi), _f32(Kt), _f32(aff)
+        for k in ("u", "v", "color", "weights", "gradH", "energy_th", "idepth_min", "idepth_max", "quality", "uv", "pixel_interval"):
+            pts[k] = _f32(pts[k])
+        pts["status"] = _u8(pts["status"])
+        ip = Immature(n=host.size, reserved0=0, host=_p(host, i32p), u=_p(pts["u"], f32p), v=_p(pts["v"], f32p), color=_p(pts["color"], f32p),
+                      weights=_p(pts["weights"], f32p), gradH=_p(pts["gradH"], f32p), energy_th=_p(pts["energy_th"], f32p),
+                      idepth_min=_p(pts["idepth_min"], f32p), idepth_max=_p(pts["idepth_max"], f32p), quality=_p(pts["quality"], f32p),
+                      last_trace_status=_p(pts["status"], u8p), last_trace_uv=_p(pts["uv"], f32p),
+                      last_trace_pixel_interval=_p(pts["pixel_interval"], f32p))
+        counts = np.zeros(6, np.int32)
+        self._ck(self.lib.f("trace_immature")(self.h, C.c_int32(frame_slot), C.c_int32(KRKi.size // 9), _p(KRKi, f32p), _p(Kt, f32p), _p(aff, f32p),
+                                              C.byref(ip), _p(counts, i32p)), "trace_immature")
+        return counts
 
     def tracker_calc_res_pose(self, lvl, slot, refToNew34, affLL, cutoff):
         T = _f64(refToNew34).reshape(12)

@@ -213,6 +213,26 @@ struct ResubArgs {
 void launch_resubstitute(sosba *h, const ResubArgs &a);
 void launch_step(sosba *h, const ResubArgs &ra, const StepArgs &sa);   // resubstitute + frame step, concurrently, one launch
 
+// ---- k_trace.cu ---------------------------------------------------------------------------------
+struct TraceArgs {
+  int n, w, h;
+  const float4 *img;          // level 0 of the traced-into frame (trace_on) / of the host frame (immature_init)
+  // immature_init
+  const int *iu, *iv;
+  float *color_out, *weights_out, *gradH_out, *energyTH_out;
+  float outlierTHSum, overallWeight;
+  // trace_on
+  const int *host;
+  const float *u, *v, *color, *weights, *gradH, *energyTH;
+  float *idepth_min, *idepth_max, *quality, *uv, *pixint;
+  uint8_t *status;
+  const float *KRKi, *Kt, *aff;   // per host
+  float huberTH;
+  int *counts;                // [6] per ImmaturePointStatus
+};
+void launch_immature_init(sosba *h, const TraceArgs &a);
+void launch_trace_on(sosba *h, const TraceArgs &a);
+
 // ---- k_tracker.cu -------------------------------------------------------------------------------
 struct TrackGSArgs {
   int n, cap, kind;

@@ -50,6 +50,10 @@ struct BA {
 
 // per-handle host mirrors that the device kernels never read
 struct HostSide {
+  float *d_imm = nullptr;   // immature-point arena (k_trace.cu): 30 floats + 1 status byte per point, grown on demand
+  size_t imm_cap = 0;
+  float *d_imm_host = nullptr;   // KRKi / Kt / aff per host frame + the 6 status counters
+  int imm_host_cap = 0;
   std::vector<int> p_host, res_begin, r_point, r_target, r_host_tmp;
   std::vector<void *> allocs;
   int n_lin = 0;
@@ -1436,4 +1440,104 @@ API int sosba_optimize(sosba_t *h, sosba_ba_problem *prob, int32_t mnumOptIts, s
     fprintf(stderr, "sosba_optimize host wall: upload %ld us, optimize %ld us, download %ld us\n", us(t0, t1), us(t1, t2), us(t2, t3));
   }
   return rc;
+}
+
+// ---- next row: immature points --------------------------------------------
+// arena layout for n points (floats): [u n][v n][color 8n][weights 8n][gradH 4n][energyTH n][idmin n][idmax n][quality n][uv 2n][pixint n][host n (int)][status n bytes]
+static int ensure_immature(sosba *h, size_t n, int nhosts) {
+  HostSide *hs = HS(h);
+  if (n > hs->imm_cap) {
+    dfree(h, hs->d_imm);
+    hs->imm_cap = n + n / 4 + 256;
+    DALLOC(h, hs->d_imm, 31 * hs->imm_cap);
+  }
+  if (nhosts > hs->imm_host_cap) {
+    dfree(h, hs->d_imm_host);
+    hs->imm_host_cap = nhosts + 8;
+    DALLOC(h, hs->d_imm_host, 14 * (size_t)hs->imm_host_cap + 8);
+  }
+  return SOSBA_OK;
+}
+
+API int sosba_immature_init(sosba_t *h, int32_t host_slot, int32_t n, const int32_t *u, const int32_t *v, float *color, float *weights, float *gradH,
+                            float *energy_th) {
+  CHECK_H(h);
+  if (host_slot < 0 || host_slot >= (int)h->slot_img.size() || !h->slot_valid[host_slot] || n < 0) { sosba_set_error("bad slot / n"); return SOSBA_E_ARG; }
+  if (n == 0) return SOSBA_OK;
+  if (!u || !v || !color || !weights || !gradH || !energy_th) { sosba_set_error("null buffer"); return SOSBA_E_ARG; }
+  for (int i = 0; i < n; i++)   // the pattern reaches 2 px and the bilinear tap one more: the reference's selector keeps candidates inside this margin
+    if (u[i] < 2 || v[i] < 2 || u[i] > h->wl[0] - 4 || v[i] > h->hl[0] - 4) { sosba_set_error("candidate %d outside the image margin", i); return SOSBA_E_ARG; }
+  int rc;
+  if ((rc = ensure_immature(h, (size_t)n, 1))) return rc;
+  HostSide *hs = HS(h);
+  const size_t N = (size_t)n;
+  float *d = hs->d_imm;
+  TraceArgs a = {};
+  a.n = n; a.w = h->wl[0]; a.h = h->hl[0]; a.img = h->slot_img[host_slot] + h->lvl_off[0];
+  a.iu = (const int *)d; a.iv = (const int *)(d + N);
+  a.color_out = d + 2 * N; a.weights_out = d + 10 * N; a.gradH_out = d + 18 * N; a.energyTH_out = d + 22 * N;
+  a.outlierTHSum = h->cfg.outlier_th_sum_component; a.overallWeight = h->cfg.overall_energy_th_weight;
+  if ((rc = up(h, (int *)d, (const int *)u, N)) || (rc = up(h, (int *)(d + N), (const int *)v, N))) return rc;
+  // a colour that is not finite ends the pattern loop early (ImmaturePoint.cpp:43): the entries behind it are left as 0
+  SOSBA_CUDA(cudaMemsetAsync(d + 2 * N, 0, 16 * N * sizeof(float), h->stream));
+  launch_immature_init(h, a);
+  SOSBA_CUDA(cudaGetLastError());
+  if ((rc = down(h, color, a.color_out, 8 * N)) || (rc = down(h, weights, a.weights_out, 8 * N)) || (rc = down(h, gradH, a.gradH_out, 4 * N)) ||
+      (rc = down(h, energy_th, a.energyTH_out, N)))
+    return rc;
+  return sync(h);
+}
+
+API int sosba_trace_immature(sosba_t *h, int32_t frame_slot, int32_t nhosts, const float *KRKi, const float *Kt, const float *aff, sosba_immature *pts,
+                             int32_t counts[6]) {
+  CHECK_H(h);
+  if (frame_slot < 0 || frame_slot >= (int)h->slot_img.size() || !h->slot_valid[frame_slot] || !pts || pts->n < 0 || nhosts < 0) {
+    sosba_set_error("bad slot / points");
+    return SOSBA_E_ARG;
+  }
+  if (counts) for (int i = 0; i < 6; i++) counts[i] = 0;
+  const int n = pts->n;
+  if (n == 0) return SOSBA_OK;
+  if (!KRKi || !Kt || !aff || !pts->host || !pts->u || !pts->v || !pts->color || !pts->weights || !pts->gradH || !pts->energy_th || !pts->idepth_min ||
+      !pts->idepth_max || !pts->quality || !pts->last_trace_status || !pts->last_trace_uv || !pts->last_trace_pixel_interval) {
+    sosba_set_error("null buffer");
+    return SOSBA_E_ARG;
+  }
+  for (int i = 0; i < n; i++)
+    if (pts->host[i] < 0 || pts->host[i] >= nhosts) { sosba_set_error("point %d: host %d outside [0,%d)", i, pts->host[i], nhosts); return SOSBA_E_ARG; }
+  int rc;
+  if ((rc = ensure_immature(h, (size_t)n, nhosts))) return rc;
+  HostSide *hs = HS(h);
+  const size_t N = (size_t)n;
+  float *d = hs->d_imm, *dh = hs->d_imm_host;
+  float *d_u = d, *d_v = d + N, *d_color = d + 2 * N, *d_w = d + 10 * N, *d_G = d + 18 * N, *d_eth = d + 22 * N, *d_min = d + 23 * N, *d_max = d + 24 * N,
+        *d_q = d + 25 * N, *d_uv = d + 26 * N, *d_pi = d + 28 * N;
+  int *d_host = (int *)(d + 29 * N);
+  uint8_t *d_st = (uint8_t *)(d + 30 * N);
+  int *d_counts = (int *)(dh + 14 * (size_t)hs->imm_host_cap);
+  if ((rc = up(h, d_u, pts->u, N)) || (rc = up(h, d_v, pts->v, N)) || (rc = up(h, d_color, pts->color, 8 * N)) || (rc = up(h, d_w, pts->weights, 8 * N)) ||
+      (rc = up(h, d_G, pts->gradH, 4 * N)) || (rc = up(h, d_eth, pts->energy_th, N)) || (rc = up(h, d_min, (const float *)pts->idepth_min, N)) ||
+      (rc = up(h, d_max, (const float *)pts->idepth_max, N)) || (rc = up(h, d_q, (const float *)pts->quality, N)) ||
+      (rc = up(h, d_uv, (const float *)pts->last_trace_uv, 2 * N)) || (rc = up(h, d_pi, (const float *)pts->last_trace_pixel_interval, N)) ||
+      (rc = up(h, d_host, (const int *)pts->host, N)) || (rc = up(h, d_st, (const uint8_t *)pts->last_trace_status, N)) ||
+      (rc = up(h, dh, KRKi, 9 * (size_t)nhosts)) || (rc = up(h, dh + 9 * (size_t)hs->imm_host_cap, Kt, 3 * (size_t)nhosts)) ||
+      (rc = up(h, dh + 12 * (size_t)hs->imm_host_cap, aff, 2 * (size_t)nhosts)))
+    return rc;
+  SOSBA_CUDA(cudaMemsetAsync(d_counts, 0, 6 * sizeof(int), h->stream));
+  TraceArgs a = {};
+  a.n = n; a.w = h->wl[0]; a.h = h->hl[0]; a.img = h->slot_img[frame_slot] + h->lvl_off[0];
+  a.host = d_host; a.u = d_u; a.v = d_v; a.color = d_color; a.weights = d_w; a.gradH = d_G; a.energyTH = d_eth;
+  a.idepth_min = d_min; a.idepth_max = d_max; a.quality = d_q; a.uv = d_uv; a.pixint = d_pi; a.status = d_st;
+  a.KRKi = dh; a.Kt = dh + 9 * (size_t)hs->imm_host_cap; a.aff = dh + 12 * (size_t)hs->imm_host_cap;
+  a.huberTH = h->cfg.huber_th; a.counts = d_counts;
+  launch_trace_on(h, a);
+  SOSBA_CUDA(cudaGetLastError());
+  if ((rc = down(h, pts->idepth_min, (const float *)d_min, N)) || (rc = down(h, pts->idepth_max, (const float *)d_max, N)) ||
+      (rc = down(h, pts->quality, (const float *)d_q, N)) || (rc = down(h, pts->last_trace_uv, (const float *)d_uv, 2 * N)) ||
+      (rc = down(h, pts->last_trace_pixel_interval, (const float *)d_pi, N)) || (rc = down(h, pts->last_trace_status, (const uint8_t *)d_st, N)) ||
+      (rc = down(h, hs->pin_i, (const int *)d_counts, 6)))
+    return rc;
+  if ((rc = sync(h))) return rc;
+  if (counts) for (int i = 0; i < 6; i++) counts[i] = hs->pin_i[i];
+  return SOSBA_OK;
 }

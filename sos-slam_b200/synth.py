@@ -287,3 +287,35 @@ def replicate_points(scene: Scene, factor: int, seed: int = 7) -> Scene:
         pt_idepth=np.concatenate(ids), pt_idepth_true=np.concatenate(idt), pt_color=np.concatenate(cols),
         pt_weights=np.concatenate(wgts), res_point=np.concatenate(rp).astype(np.int32),
         res_target=np.concatenate(rt).astype(np.int32))
+
+
+def trace_case(scene: Scene, new_frame: int, n_per_host: int = 200, seed: int = 11, pose_noise: float = 0.0):
+    """Inputs of FullSystem::traceNewCoarse (FullSystem.cpp:311-361) for tracing candidates of every other frame of the
+    window into `new_frame`: integer candidate pixels per host (random, inside the selector's margin) and the per-host
+    KRKi / Kt / affine brightness transfer built from the scene's estimated poses.
+    -> dict(host [n], u [n], v [n], KRKi [nf,3,3], Kt [nf,3], aff [nf,2]); host indexes frames (the row of `new_frame`
+    itself is the identity and has no points)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = [float(x) for x in scene.K]
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]])
+    Ki = np.linalg.inv(K)
+    hosts, us, vs = [], [], []
+    KRKi = np.zeros((scene.nf, 3, 3), np.float32)
+    Kt = np.zeros((scene.nf, 3), np.float32)
+    aff = np.zeros((scene.nf, 2), np.float32)
+    w2c_new = np.linalg.inv(scene.evalPT[new_frame])
+    for hst in range(scene.nf):
+        T = w2c_new @ scene.evalPT[hst]
+        if pose_noise:
+            T = se3_exp(rng.normal(0, pose_noise, 6)) @ T
+        KRKi[hst] = (K.astype(np.float32) @ T[:3, :3].astype(np.float32)) @ Ki.astype(np.float32)
+        Kt[hst] = K.astype(np.float32) @ T[:3, 3].astype(np.float32)
+        # AffLight::fromToVecExposure (util/NumType.h): a = e^{a_t - a_h} * t_exp / h_exp, b = b_t - a * b_h
+        a = np.exp(scene.aff_true[new_frame, 0] - scene.aff_true[hst, 0]) * scene.ab_exposure[new_frame] / scene.ab_exposure[hst]
+        aff[hst] = (a, scene.aff_true[new_frame, 1] - a * scene.aff_true[hst, 1])
+        if hst == new_frame:
+            continue
+        hosts.append(np.full(n_per_host, hst, np.int32))
+        us.append(rng.integers(6, scene.w - 7, n_per_host).astype(np.int32))
+        vs.append(rng.integers(6, scene.h - 7, n_per_host).astype(np.int32))
+    return dict(host=np.concatenate(hosts), u=np.concatenate(us), v=np.concatenate(vs), KRKi=KRKi, Kt=Kt, aff=aff)

@@ -66,3 +66,13 @@ def relerr(a, b):
     b = np.asarray(b, np.float64)
     den = np.linalg.norm(b)
     return float(np.linalg.norm(a - b) / den) if den > 0 else float(np.linalg.norm(a - b))
+
+
+def trace_points(h, sc, case):
+    """ImmaturePoint construction of every candidate of `case` (synth.trace_case) through handle `h` -> one SoA dict."""
+    parts = []
+    for hst in range(sc.nf):
+        m = case["host"] == hst
+        if m.any():
+            parts.append(h.immature_init(hst, case["u"][m], case["v"][m]))
+    return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}

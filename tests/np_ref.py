@@ -347,3 +347,168 @@ def schur(Hcd, Hdd, bd, prior=0.0):
     Hsc = (Hcd.T * Hdi) @ Hcd
     bsc = Hcd.T @ (Hdi * bd)
     return Hsc, bsc
+
+
+# ---- immature points ----------------------------------------------------------------
+# Independent restatement of ImmaturePoint::ImmaturePoint (ImmaturePoint.cpp:28-60) and ImmaturePoint::traceOn
+# (ImmaturePoint.cpp:70-415) in float32 numpy; the epipolar search is vectorised over steps x pattern (positions by a
+# sequential float32 cumsum, like the reference's ptx += dx), the Gauss-Newton refinement is a plain loop.
+F = np.float32
+IPS_GOOD, IPS_OOB, IPS_OUTLIER, IPS_SKIPPED, IPS_BADCONDITION, IPS_UNINITIALIZED = range(6)
+
+
+def _bilin(dI, x, y):
+    """getInterpolatedElement33 (globalFuncs.h:68-82) on dI (h, w, 3) at float32 positions (any shape) -> (..., 3)."""
+    x = np.asarray(x, F); y = np.asarray(y, F)
+    ix = x.astype(np.int32); iy = y.astype(np.int32)
+    dx = x - ix.astype(F); dy = y - iy.astype(F)
+    dxdy = dx * dy
+    w11, w01, w10, w00 = dxdy, dy - dxdy, dx - dxdy, F(1) - dx - dy + dxdy
+    return (w11[..., None] * dI[iy + 1, ix + 1] + w01[..., None] * dI[iy + 1, ix] + w10[..., None] * dI[iy, ix + 1] + w00[..., None] * dI[iy, ix])
+
+
+def immature_init_ref(dI, u, v, outlier_th_sum=F(2500), overall_weight=F(1)):
+    """dI (h, w, 3) float32; integer pixels u, v -> color (n,8), weights (n,8), gradH (n,4), energyTH (n,)."""
+    n = len(u)
+    color = np.zeros((n, 8), F); weights = np.zeros((n, 8), F); G = np.zeros((n, 4), F)
+    for idx, (px, py) in enumerate(PATTERN):
+        x = u + px; y = v + py
+        tl, tr, bl, br = dI[y, x, 0], dI[y, x + 1, 0], dI[y + 1, x, 0], dI[y + 1, x + 1, 0]
+        # integer position: dx = dy = 0 in getInterpolatedElement33BiLin (globalFuncs.h:161-182)
+        z, o = F(0), F(1)
+        top = z * tr + o * tl; bot = z * br + o * bl; left = z * bl + o * tl; right = z * br + o * tr
+        c0 = z * right + o * left; gx = right - left; gy = bot - top
+        color[:, idx] = c0
+        G[:, 0] += gx * gx; G[:, 1] += gx * gy; G[:, 2] += gy * gx; G[:, 3] += gy * gy
+        weights[:, idx] = np.sqrt(outlier_th_sum / (outlier_th_sum + (gx * gx + gy * gy)))
+    eth = np.full(n, F(8) * F(144) * (overall_weight * overall_weight), F)
+    return color, weights, G, eth
+
+
+def trace_on_ref(dI, p, KRKi, Kt, aff, huber=F(9)):
+    """One point.  p: dict(u, v, color[8], weights[8], gradH[4], energy_th, idepth_min, idepth_max, quality, status);
+    returns the updated dict (plus uv, pixel_interval)."""
+    p = dict(p)
+    if p["status"] == IPS_OOB:
+        return p
+    h, w = dI.shape[:2]
+    KRKi = np.asarray(KRKi, F).reshape(3, 3); Kt = np.asarray(Kt, F); aff = np.asarray(aff, F)
+
+    def leave(status, uv=(-1, -1), interval=0):
+        p["status"] = status; p["uv"] = (F(uv[0]), F(uv[1])); p["pixel_interval"] = F(interval)
+        return p
+
+    def inside(a, b):
+        return a > 4 and b > 4 and a < w - 5 and b < h - 5
+
+    max_search = F(w + h) * F(0.027)
+    pr = (KRKi[:, 0] * F(p["u"]) + KRKi[:, 1] * F(p["v"])) + KRKi[:, 2]
+    pmin = pr + Kt * F(p["idepth_min"])
+    uMin, vMin = pmin[0] / pmin[2], pmin[1] / pmin[2]
+    if not inside(uMin, vMin):
+        return leave(IPS_OOB)
+    finite_max = bool(np.isfinite(p["idepth_max"]))
+    if finite_max:
+        pmax = pr + Kt * F(p["idepth_max"])
+        uMax, vMax = pmax[0] / pmax[2], pmax[1] / pmax[2]
+        if not inside(uMax, vMax):
+            return leave(IPS_OOB)
+        dist = np.sqrt((uMin - uMax) * (uMin - uMax) + (vMin - vMax) * (vMin - vMax))
+        if dist < F(1.5):
+            return leave(IPS_SKIPPED, ((uMax + uMin) * F(0.5), (vMax + vMin) * F(0.5)), dist)
+    else:
+        dist = max_search
+        pmax = pr + Kt * F(0.01)
+        uMax, vMax = pmax[0] / pmax[2], pmax[1] / pmax[2]
+        ex, ey = uMax - uMin, vMax - vMin
+        d = F(1) / np.sqrt(ex * ex + ey * ey)
+        uMax = uMin + dist * ex * d; vMax = vMin + dist * ey * d
+        if not inside(uMax, vMax):
+            return leave(IPS_OOB)
+    if not (p["idepth_min"] < 0 or (pmin[2] > F(0.75) and pmin[2] < F(1.5))):
+        return leave(IPS_OOB)
+    dx, dy = uMax - uMin, vMax - vMin
+    G = np.asarray(p["gradH"], F)
+    a = (dx * G[0] + dy * G[2]) * dx + (dx * G[1] + dy * G[3]) * dy
+    b = (dy * G[0] + (-dx) * G[2]) * dy + (dy * G[1] + (-dx) * G[3]) * (-dx)
+    with np.errstate(all="ignore"):
+        err_px = F(0.2) + F(0.2) * (a + b) / a
+    if err_px * F(2) > dist and finite_max:
+        return leave(IPS_BADCONDITION, ((uMax + uMin) * F(0.5), (vMax + vMin) * F(0.5)), dist)
+    if err_px > 10:
+        err_px = F(10)
+    dx = dx / dist; dy = dy / dist
+    if dist > max_search:
+        dist = max_search
+    nsteps = int(F(1.9999) + dist / F(1))
+    shift = uMin * F(1000) - np.floor(uMin * F(1000))
+    x0, y0 = uMin - shift * dx, vMin - shift * dy
+    pat = np.asarray(PATTERN, F)
+    rx = KRKi[0, 0] * pat[:, 0] + KRKi[0, 1] * pat[:, 1]
+    ry = KRKi[1, 0] * pat[:, 0] + KRKi[1, 1] * pat[:, 1]
+    if not (np.isfinite(dx) and np.isfinite(dy)):
+        return leave(IPS_OOB)
+    nsteps = min(nsteps, 99)
+    xs = np.cumsum(np.concatenate([[x0], np.full(nsteps - 1, dx, F)]).astype(F), dtype=F)
+    ys = np.cumsum(np.concatenate([[y0], np.full(nsteps - 1, dy, F)]).astype(F), dtype=F)
+    color = np.asarray(p["color"], F); wts = np.asarray(p["weights"], F)
+    ref = aff[0] * color + aff[1]
+    hit = _bilin(dI, xs[:, None] + rx[None, :], ys[:, None] + ry[None, :])[..., 0]
+    r = hit - ref[None, :]
+    hw = np.where(np.abs(r) < huber, F(1), huber / np.maximum(np.abs(r), F(1e-30))).astype(F)
+    term = np.where(np.isfinite(hit), hw * r * r * (F(2) - hw), F(1e5)).astype(F)
+    energies = np.zeros(nsteps, F)
+    for idx in range(8):
+        energies = energies + term[:, idx]
+    best = int(np.argmin(energies))        # first minimum, like the strict '<' of the reference
+    bestU, bestV, bestE = xs[best], ys[best], energies[best]
+    far = np.abs(np.arange(nsteps) - best) > 2
+    second = energies[far].min() if far.any() else F(1e10)
+    second = min(second, F(1e10))
+    with np.errstate(all="ignore"):
+        new_q = F(second) / bestE
+    if new_q < p["quality"] or nsteps > 10:
+        p["quality"] = new_q
+    uBak, vBak, back = bestU, bestV, F(0)
+    bestE = F(1e5)
+    for _ in range(3):
+        H, bb, E = F(1), F(0), F(0)
+        for idx in range(8):
+            hit3 = _bilin(dI, F(bestU + rx[idx]), F(bestV + ry[idx]))
+            if not np.isfinite(hit3[0]):
+                E += F(1e5)
+                continue
+            res = hit3[0] - (aff[0] * color[idx] + aff[1])
+            dd = dx * hit3[1] + dy * hit3[2]
+            hw1 = F(1) if abs(res) < huber else huber / abs(res)
+            H += hw1 * dd * dd
+            bb += hw1 * res * dd
+            E += wts[idx] * wts[idx] * hw1 * res * res * (F(2) - hw1)
+        if E > bestE:
+            back = back * F(0.5)
+            bestU = uBak + back * dx; bestV = vBak + back * dy
+        else:
+            step = F(-1) * bb / H
+            step = min(max(step, F(-0.5)), F(0.5))
+            if not np.isfinite(step):
+                step = F(0)
+            uBak, vBak, back = bestU, bestV, step
+            bestU = bestU + step * dx; bestV = bestV + step * dy
+            bestE = E
+        if abs(back) < F(0.1):
+            break
+    if not (bestE < F(p["energy_th"]) * F(1.2)):
+        return leave(IPS_OOB if p["status"] == IPS_OUTLIER else IPS_OUTLIER)
+    with np.errstate(all="ignore"):
+        if dx * dx > dy * dy:
+            lo = (pr[2] * (bestU - err_px * dx) - pr[0]) / (Kt[0] - Kt[2] * (bestU - err_px * dx))
+            hi = (pr[2] * (bestU + err_px * dx) - pr[0]) / (Kt[0] - Kt[2] * (bestU + err_px * dx))
+        else:
+            lo = (pr[2] * (bestV - err_px * dy) - pr[1]) / (Kt[1] - Kt[2] * (bestV - err_px * dy))
+            hi = (pr[2] * (bestV + err_px * dy) - pr[1]) / (Kt[1] - Kt[2] * (bestV + err_px * dy))
+    if lo > hi:
+        lo, hi = hi, lo
+    p["idepth_min"], p["idepth_max"] = F(lo), F(hi)
+    if not (np.isfinite(lo) and np.isfinite(hi)) or hi < 0:
+        return leave(IPS_OUTLIER)
+    return leave(IPS_GOOD, (bestU, bestV), F(2) * err_px)

@@ -391,3 +391,64 @@ def test_shard_points_balanced():
         assert all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
         per = [int(counts[a:b].sum()) for a, b in sh]
         assert max(per) - min(per) <= 16
+
+
+# ---- next row: immature points ----------------------------------------------------
+def _dI_of(h, slot, sc):
+    dI, _ = h.frame_get_level(slot, 0)
+    return np.asarray(dI, np.float32).reshape(sc.h, sc.w, 3)
+
+
+def test_immature_init_vs_numpy(orc):
+    """ImmaturePoint::ImmaturePoint (ImmaturePoint.cpp:28-60): colours, weights, gradH, energyTH bit for bit."""
+    from sos_slam_b200 import synth
+    sc = scene(**SMALLC)
+    h = open_handle(orc, sc)
+    case = synth.trace_case(sc, sc.nf - 1, n_per_host=150)
+    m = case["host"] == 1
+    got = h.immature_init(1, case["u"][m], case["v"][m])
+    color, weights, G, eth = np_ref.immature_init_ref(_dI_of(h, 1, sc), case["u"][m], case["v"][m])
+    assert np.array_equal(got["color"], color) and np.array_equal(got["weights"], weights)
+    assert np.array_equal(got["gradH"], G) and np.array_equal(got["energy_th"], eth)
+    assert np.all(got["status"] == np_ref.IPS_UNINITIALIZED) and np.all(np.isnan(got["idepth_max"]))
+    h.close()
+
+
+def test_trace_immature_vs_numpy(orc):
+    """ImmaturePoint::traceOn (ImmaturePoint.cpp:70-415) over two consecutive frames: first trace with an unbounded
+    interval, second with the interval of the first.  Statuses must agree for every point; intervals to float rounding
+    (the numpy restatement sums the pattern energies in the same order but vectorised)."""
+    from sos_slam_b200 import synth
+    sc = scene(**SMALLC)
+    h = open_handle(orc, sc)
+    seen = set()
+    pts = None
+    for new_frame, hosts_case in ((sc.nf - 2, None), (sc.nf - 1, None)):
+        case = synth.trace_case(sc, new_frame, n_per_host=60, seed=11)
+        keep = case["host"] < sc.nf - 2                 # the same candidates in both passes
+        host, u, v = case["host"][keep], case["u"][keep], case["v"][keep]
+        if pts is None:
+            pts = trace_points_cpu(h, sc, host, u, v)
+        before = {k: np.array(x, copy=True) for k, x in pts.items()}
+        counts = h.trace_immature(new_frame, host, case["KRKi"], case["Kt"], case["aff"], pts)
+        assert counts.sum() == host.size and np.array_equal(counts, np.bincount(pts["status"], minlength=6))
+        dI = _dI_of(h, new_frame, sc)
+        for k in range(host.size):
+            p = dict(u=before["u"][k], v=before["v"][k], color=before["color"][k], weights=before["weights"][k], gradH=before["gradH"][k],
+                     energy_th=before["energy_th"][k], idepth_min=before["idepth_min"][k], idepth_max=before["idepth_max"][k],
+                     quality=before["quality"][k], status=int(before["status"][k]), uv=tuple(before["uv"][k]), pixel_interval=before["pixel_interval"][k])
+            r = np_ref.trace_on_ref(dI, p, case["KRKi"][host[k]], case["Kt"][host[k]], case["aff"][host[k]])
+            assert r["status"] == pts["status"][k], (new_frame, k, r["status"], pts["status"][k])
+            seen.add(int(r["status"]))
+            np.testing.assert_allclose(np.array(r["uv"], np.float32), pts["uv"][k], rtol=0, atol=2e-3)
+            np.testing.assert_allclose(r["pixel_interval"], pts["pixel_interval"][k], rtol=1e-5)
+            if r["status"] == np_ref.IPS_GOOD:
+                np.testing.assert_allclose([r["idepth_min"], r["idepth_max"]], [pts["idepth_min"][k], pts["idepth_max"][k]], rtol=2e-3, atol=1e-5)
+                np.testing.assert_allclose(r["quality"], pts["quality"][k], rtol=1e-4)
+    assert {np_ref.IPS_GOOD, np_ref.IPS_OOB, np_ref.IPS_OUTLIER} <= seen and (np_ref.IPS_SKIPPED in seen or np_ref.IPS_BADCONDITION in seen), seen
+    h.close()
+
+
+def trace_points_cpu(h, sc, host, u, v):
+    parts = [h.immature_init(int(hst), u[host == hst], v[host == hst]) for hst in np.unique(host)]
+    return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}

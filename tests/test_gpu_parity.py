@@ -2,11 +2,11 @@
 
 Bar: bit-exact for integer bookkeeping (residual states, counts, removal sets, pyramid
 levels); per-residual floats rel 1e-5; block accumulators / stitched H,b rel 1e-4 of the Frobenius norm;
-solved step rel 1e-3; tracker H,b rel 1e-4."""
+solved step rel 1e-3; tracker H,b rel 1e-4; immature points (constructor + traceOn) bit-exact in every field."""
 import numpy as np
 import pytest
 
-from _scenes import CONFIG_B, KITTI, SMALL, open_handle, relerr, scene, upload
+from _scenes import CONFIG_B, KITTI, SMALL, open_handle, relerr, scene, trace_points, upload
 
 pytestmark = pytest.mark.gpu
 
@@ -275,3 +275,56 @@ def test_edge_cases(gpu, orc):
         acc = h.accumulate()
         assert acc["resInA"] == 0 and not acc["HA"].any() and not acc["Hsc"].any()
         h.close()
+
+
+# ---- next row: immature points ------------------------------------------------
+@pytest.mark.parametrize("cfg", [SMALL, CONFIG_B, KITTI], ids=["small", "configB", "kitti"])
+def test_immature_trace_bit_exact(gpu, orc, cfg):
+    """ImmaturePoint::ImmaturePoint + traceOn (ImmaturePoint.cpp:28-60, 70-415) through three consecutive
+    traceNewCoarse passes (FullSystem.cpp:311-361): unbounded interval, then two refinements.  Every field of every
+    point (colours, weights, gradH, energyTH, interval, quality, status, uv, pixel interval) and the status counters are
+    identical bit for bit to the oracle's."""
+    from sos_slam_b200 import synth
+    sc = scene(**cfg)
+    hg, ho = open_handle(gpu, sc), open_handle(orc, sc)
+    first = sc.nf - 3
+    base = synth.trace_case(sc, first, n_per_host=500, seed=21)
+    keep = base["host"] < first
+    sel = dict(host=base["host"][keep], u=base["u"][keep], v=base["v"][keep])
+    pg, po = trace_points(hg, sc, sel), trace_points(ho, sc, sel)
+    for k in pg:
+        assert np.array_equal(pg[k], po[k], equal_nan=True), k
+    seen = np.zeros(6, np.int64)
+    for new_frame in (first, first + 1, first + 2):
+        case = synth.trace_case(sc, new_frame, n_per_host=1, seed=21, pose_noise=2e-3 if new_frame == first + 2 else 0.0)
+        cg = hg.trace_immature(new_frame, sel["host"], case["KRKi"], case["Kt"], case["aff"], pg)
+        co = ho.trace_immature(new_frame, sel["host"], case["KRKi"], case["Kt"], case["aff"], po)
+        assert np.array_equal(cg, co), (new_frame, cg, co)
+        assert cg.sum() == sel["host"].size and np.array_equal(cg, np.bincount(pg["status"], minlength=6))
+        for k in pg:
+            assert np.array_equal(pg[k], po[k], equal_nan=True), (new_frame, k, int(np.sum(pg[k] != po[k])))
+        seen += cg
+    assert np.all(seen[:4] > 0) and (cfg is SMALL or seen[4] > 0), seen     # GOOD, OOB, OUTLIER, SKIPPED (+ BADCONDITION on the larger images)
+    hg.close(); ho.close()
+
+
+def test_immature_edge_cases(gpu, orc):
+    """n = 0, a candidate outside the selector margin, a host index out of range, a point that is already OOB."""
+    from sos_slam_b200 import binding, synth
+    sc = scene(**SMALL)
+    hg = open_handle(gpu, sc)
+    empty = hg.immature_init(0, np.zeros(0, np.int32), np.zeros(0, np.int32))
+    case = synth.trace_case(sc, sc.nf - 1, n_per_host=4)
+    assert hg.trace_immature(sc.nf - 1, np.zeros(0, np.int32), case["KRKi"], case["Kt"], case["aff"], empty).sum() == 0
+    with pytest.raises(binding.SosbaError):
+        hg.immature_init(0, np.array([0], np.int32), np.array([10], np.int32))
+    pts = hg.immature_init(0, np.array([50, 60], np.int32), np.array([40, 44], np.int32))
+    with pytest.raises(binding.SosbaError):
+        hg.trace_immature(sc.nf - 1, np.array([0, sc.nf], np.int32), case["KRKi"], case["Kt"], case["aff"], pts)
+    pts["status"][0] = binding.IPS_OOB
+    before = {k: v.copy() for k, v in pts.items()}
+    c = hg.trace_immature(sc.nf - 1, np.array([0, 0], np.int32), case["KRKi"], case["Kt"], case["aff"], pts)
+    assert c[binding.IPS_OOB] >= 1 and c.sum() == 2
+    for k in pts:   # an OOB point is returned untouched (ImmaturePoint.cpp:74-75)
+        assert np.array_equal(pts[k][0], before[k][0], equal_nan=True), k
+    hg.close()

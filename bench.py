@@ -389,7 +389,16 @@ def main():
                 t0 = time.perf_counter()
                 trace_counts = h.trace_immature(sc.nf - 1, case["host"], case["KRKi"], case["Kt"], case["aff"], ipc)
                 trace_ms.append(1e3 * (time.perf_counter() - t0))
-            other = {"make_images_ms": pyr_ms, "make_images_note": f"{sc.w}x{sc.h}, H2D + 4 levels, host wall per call",
+            okp = np.isfinite(ipc["idepth_max"])
+            sub = {k: x[okp] for k, x in ipc.items()}
+            win = synth.activation_case(sc)
+            act_ms = []
+            for _ in range(5):
+                t0 = time.perf_counter()
+                act = h.optimize_immature(np.arange(sc.nf), win["RTll"], win["tTll"], win["aff"], win["calib"], case["host"][okp], sub)
+                act_ms.append(1e3 * (time.perf_counter() - t0))
+            other = {"optimize_immature_ms": float(np.median(act_ms)), "optimize_immature_points": int(okp.sum()),
+                     "optimize_immature_activated": int((act[0] == 1).sum()), "make_images_ms": pyr_ms, "make_images_note": f"{sc.w}x{sc.h}, H2D + 4 levels, host wall per call",
                      "trace_immature_ms": float(np.median(trace_ms)), "trace_immature_points": int(case["host"].size),
                      "trace_immature_counts": [int(x) for x in trace_counts],
                      "trace_note": "first trace (unbounded interval: the longest epipolar search), host SoA in and out, host wall per call",
@@ -436,8 +445,27 @@ def main():
                 if n >= 1:
                     tcpu += dt; rcpu += o["reserved0"] * 8 * (o["iterations"] + 2)
                 n += 1
+            # the 8f rank-1 row on the host cores: traceNewCoarse is a serial loop in the reference (FullSystem.cpp:311-361)
+            cpu_trace = None
+            try:
+                case = synth.trace_case(sc1, sc1.nf - 1, n_per_host=2000, seed=3)
+                parts = [oh.immature_init(hst, case["u"][case["host"] == hst], case["v"][case["host"] == hst]) for hst in range(sc1.nf - 1)]
+                ip = {k: np.concatenate([q[k] for q in parts]) for k in parts[0]}
+                t0 = time.perf_counter()
+                oh.trace_immature(sc1.nf - 1, case["host"], case["KRKi"], case["Kt"], case["aff"], ip)
+                t_tr = time.perf_counter() - t0
+                okp = np.isfinite(ip["idepth_max"])
+                win = synth.activation_case(sc1)
+                sub = {k: x[okp] for k, x in ip.items()}
+                t0 = time.perf_counter()
+                oh.optimize_immature(np.arange(sc1.nf), win["RTll"], win["tTll"], win["aff"], win["calib"], case["host"][okp], sub)
+                t_act = time.perf_counter() - t0
+                cpu_trace = {"trace_immature_ms": 1e3 * t_tr, "optimize_immature_ms": 1e3 * t_act, "cores": 1,
+                             "note": "same inputs as other_kernels; single thread (the reference's trace loop is serial, its activation loop threaded)"}
+            except Exception as ex:
+                cpu_trace = {"error": str(ex)}
             oh.close()
-            cpu = {"value": rcpu / tcpu, "unit": UNIT, "cores": cores, "kind": "port",
+            cpu = {"other_kernels": cpu_trace, "value": rcpu / tcpu, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{n - 1} optimize() steps of the same window ({tcpu:.1f} s), oracle speed build, {cores} IndexThreadReduce workers",
                    "ms_per_step": 1e3 * tcpu / (n - 1)}
 

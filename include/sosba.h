@@ -331,6 +331,33 @@ int sosba_immature_init(sosba_t *h, int32_t host_slot, int32_t n, const int32_t 
 int sosba_trace_immature(sosba_t *h, int32_t frame_slot, int32_t nhosts, const float *KRKi, const float *Kt, const float *aff,
                          sosba_immature *pts, int32_t counts[6]);
 
+/* The frame pairs of the window as FullSystem::activatePointsMT sees them (FullSystem.cpp:377-505): per (host, target)
+ * FrameFramePrecalc::PRE_RTll / PRE_tTll / PRE_aff_mode (HessianBlocks.cpp:184-214), row (host * nf + target). */
+typedef struct sosba_activation_window {
+  int32_t nf;
+  int32_t min_obs;                /* minObs of optimizeImmaturePoint; the reference passes 1 (FullSystem.cpp:371) */
+  const int32_t *frame_slot;      /* [nf] image slot of frame i */
+  const float *RTll;              /* [nf*nf*9] row-major 3x3 */
+  const float *tTll;              /* [nf*nf*3] */
+  const float *aff;               /* [nf*nf*2] */
+  float calib[4];                 /* fxl fyl cxl cyl (HCalib scaled values) */
+  int32_t reserved0;
+  int32_t reserved1;
+} sosba_activation_window;
+
+enum { SOSBA_ACT_SKIP = 0, SOSBA_ACT_ACTIVATED = 1, SOSBA_ACT_DELETE = -1 };
+
+/* FullSystem::activatePointsMT_Reductor -> optimizeImmaturePoint (FullSystemOptPoint.cpp:47-192) with
+ * ImmaturePoint::linearizeResidual (ImmaturePoint.cpp:475-545) for every point of `pts` (reads host, u, v, color, weights,
+ * energy_th, idepth_min, idepth_max).  Outputs (host buffers):
+ *   result[n]        SOSBA_ACT_ACTIVATED (a PointHessian is created), SOSBA_ACT_SKIP (return 0: not well constrained, the
+ *                    point stays immature), SOSBA_ACT_DELETE (return -1: outlier / non-finite, the point is deleted)
+ *   idepth[n]        currentIdepth after the Gauss-Newton iterations (setIdepth / setIdepthZero of the new point)
+ *   res_state[n*nf]  final state_state of the temporary residual towards frame t (SOSBA_RES_*); 255 at t == host.
+ *                    The caller creates a PointFrameResidual for every SOSBA_RES_IN entry of an activated point. */
+int sosba_optimize_immature(sosba_t *h, const sosba_activation_window *win, const sosba_immature *pts, int8_t *result, float *idepth,
+                            uint8_t *res_state);
+
 /* ---- multi-GPU: points shard across ranks, one all-reduce of [H,b] per GN iteration ----------- */
 /* 128-byte NCCL unique id (rank 0 creates, caller broadcasts, every rank inits). */
 int sosba_comm_unique_id(uint8_t id[128]);

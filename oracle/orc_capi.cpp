@@ -401,3 +401,13 @@ ORC_API int orc_trace_immature(orc_handle *h, int32_t frame_slot, int32_t nhosts
   trace_immature(h->o, frame_slot, nhosts, KRKi, Kt, aff, pts, counts);
   return SOSBA_OK;
 }
+ORC_API int orc_optimize_immature(orc_handle *h, const sosba_activation_window *win, const sosba_immature *pts, int8_t *result, float *idepth,
+                                  uint8_t *res_state) {
+  if (!win || !pts || win->nf < 1) return SOSBA_E_ARG;
+  for (int f = 0; f < win->nf; f++)
+    if (win->frame_slot[f] < 0 || win->frame_slot[f] >= (int)h->o.slots.size()) return SOSBA_E_ARG;
+  for (int k = 0; k < pts->n; k++)
+    if (pts->host[k] < 0 || pts->host[k] >= win->nf) return SOSBA_E_ARG;
+  optimize_immature(h->o, win, pts, result, idepth, res_state);
+  return SOSBA_OK;
+}

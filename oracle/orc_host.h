@@ -61,6 +61,7 @@ void tracker_makeK(Oracle &o, const float calib[4]);
 // orc_trace.cpp
 void immature_init(Oracle &o, int slot, int n, const int32_t *u, const int32_t *v, float *color, float *weights, float *gradH, float *energyTH);
 void trace_immature(Oracle &o, int frame_slot, int nhosts, const float *KRKi, const float *Kt, const float *aff, sosba_immature *pts, int32_t counts[6]);
+void optimize_immature(Oracle &o, const sosba_activation_window *win, const sosba_immature *pts, int8_t *result, float *idepth, uint8_t *res_state);
 void tracker_calcResPose(Oracle &o, int lvl, int slot, const double refToNew[12], const float affLL[2], float cutoffTH, double out6[6], int32_t counts[3]);
 void tracker_calcGSSSEPose(Oracle &o, int lvl, float a, float b0, double H[64], double b[8]);
 void scale_calcRes(Oracle &o, int lvl, int slot, float scale, float cutoffTH, double out6[6], int32_t counts[3]);

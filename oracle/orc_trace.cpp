@@ -9,6 +9,7 @@
 // ((a0 x + a1 y) + a2 z; v^T G evaluated before (v^T G) v).
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "orc_core.h"
 
@@ -233,6 +234,136 @@ void trace_immature(Oracle &o, int frame_slot, int nhosts, const float *KRKi, co
     pts->last_trace_status[k] = (uint8_t)p.status;
     pts->last_trace_uv[2 * k] = p.uv[0]; pts->last_trace_uv[2 * k + 1] = p.uv[1]; pts->last_trace_pixel_interval[k] = p.pixint;
     counts[p.status]++;
+  }
+}
+
+
+// ---- activation: ImmaturePoint::linearizeResidual (ImmaturePoint.cpp:475-545) + optimizeImmaturePoint (FullSystemOptPoint.cpp:47-192)
+struct TmpRes {   // ImmaturePointTemporaryResidual (ImmaturePoint.h:31-38)
+  int state_state, state_NewState;
+  double state_energy, state_NewEnergy;
+  int target;
+};
+struct ActPoint {
+  float u, v, energyTH;
+  const float *color, *weights;
+  int host;
+};
+
+static double linearizeResidual(const Oracle &o, const sosba_activation_window *win, const ActPoint &p, float outlierTHSlack, TmpRes &tr, float &Hdd, float &bd,
+                                float idepth) {
+  if (tr.state_state == SOSBA_RES_OOB) { tr.state_NewState = SOSBA_RES_OOB; return tr.state_energy; }
+  const size_t pair = (size_t)p.host * win->nf + tr.target;
+  const float *R = win->RTll + 9 * pair, *t = win->tTll + 3 * pair, *affLL = win->aff + 2 * pair;
+  const float fxl = win->calib[0], fyl = win->calib[1], cxl = win->calib[2], cyl = win->calib[3];
+  const float fxli = 1.0f / fxl, fyli = 1.0f / fyl;   // HessianBlocks.h:494-495
+  const float *dIl = o.slots[win->frame_slot[tr.target]].lvl[0].dI.data();
+  const int wG = o.wl[0];
+  const float wM3G = o.wl[0] - 3, hM3G = o.hl[0] - 3, huberTH = o.cfg.huber_th;
+  float energyLeft = 0;
+  for (int idx = 0; idx < 8; idx++) {
+    const int dx = patternP[idx][0], dy = patternP[idx][1];
+    // projectPoint (ResidualProjections.h:52-73)
+    float KliP[3] = {(p.u + dx - cxl) * fxli, (p.v + dy - cyl) * fyli, 1};
+    float ptp[3];
+    for (int i = 0; i < 3; i++) ptp[i] = ((R[3 * i] * KliP[0] + R[3 * i + 1] * KliP[1]) + R[3 * i + 2] * KliP[2]) + t[i] * idepth;
+    float drescale = 1.0f / ptp[2];
+    bool ok = drescale > 0;
+    float u = 0, v = 0, Ku = 0, Kv = 0;
+    if (ok) {
+      u = ptp[0] * drescale; v = ptp[1] * drescale;
+      Ku = u * fxl + cxl; Kv = v * fyl + cyl;
+      ok = Ku > 1.1f && Kv > 1.1f && Ku < wM3G && Kv < hM3G;
+    }
+    if (!ok) { tr.state_NewState = SOSBA_RES_OOB; return tr.state_energy; }
+    float hit[3];
+    interp33t(dIl, Ku, Kv, wG, hit);
+    if (!std::isfinite(hit[0])) { tr.state_NewState = SOSBA_RES_OOB; return tr.state_energy; }
+    float residual = hit[0] - (affLL[0] * p.color[idx] + affLL[1]);
+    float hw = fabsf(residual) < huberTH ? 1 : huberTH / fabsf(residual);
+    energyLeft += p.weights[idx] * p.weights[idx] * hw * residual * residual * (2 - hw);
+    float dxInterp = hit[1] * fxl, dyInterp = hit[2] * fyl;
+    float d_idepth = (dxInterp * drescale * (t[0] - t[2] * u) + dyInterp * drescale * (t[1] - t[2] * v)) * SCALE_IDEPTH;   // derive_idepth (:32-40)
+    hw *= p.weights[idx] * p.weights[idx];
+    Hdd += (hw * d_idepth) * d_idepth;
+    bd += (hw * residual) * d_idepth;
+  }
+  if (energyLeft > p.energyTH * outlierTHSlack) {
+    energyLeft = p.energyTH * outlierTHSlack;
+    tr.state_NewState = SOSBA_RES_OUTLIER;
+  } else {
+    tr.state_NewState = SOSBA_RES_IN;
+  }
+  tr.state_NewEnergy = energyLeft;
+  return energyLeft;
+}
+
+// -> SOSBA_ACT_*; idepth_out = currentIdepth; states[nf] (255 at the host)
+static int optimizeImmaturePoint(const Oracle &o, const sosba_activation_window *win, const ActPoint &p, float idepth_min, float idepth_max, TmpRes *residuals,
+                                 float *idepth_out, uint8_t *states) {
+  const float minIdepthH_act = 100;      // settings.cpp:61
+  const int GNItsOnPointActivation = 3;  // settings.cpp:133
+  int nres = 0;
+  for (int f = 0; f < win->nf; f++) {
+    states[f] = 255;
+    if (f != p.host) {
+      residuals[nres].state_NewEnergy = residuals[nres].state_energy = 0;
+      residuals[nres].state_NewState = SOSBA_RES_OUTLIER;
+      residuals[nres].state_state = SOSBA_RES_IN;
+      residuals[nres].target = f;
+      nres++;
+    }
+  }
+  float lastEnergy = 0, lastHdd = 0, lastbd = 0;
+  float currentIdepth = (idepth_max + idepth_min) * 0.5f;
+  *idepth_out = currentIdepth;
+  for (int i = 0; i < nres; i++) {
+    lastEnergy += linearizeResidual(o, win, p, 1000, residuals[i], lastHdd, lastbd, currentIdepth);   // float += double
+    residuals[i].state_state = residuals[i].state_NewState;
+    residuals[i].state_energy = residuals[i].state_NewEnergy;
+  }
+  auto publish = [&]() { for (int i = 0; i < nres; i++) states[residuals[i].target] = (uint8_t)residuals[i].state_state; };
+  if (!std::isfinite(lastEnergy) || lastHdd < minIdepthH_act) { publish(); return SOSBA_ACT_SKIP; }
+  float lambda = 0.1;
+  for (int iteration = 0; iteration < GNItsOnPointActivation; iteration++) {
+    float H = lastHdd;
+    H *= 1 + lambda;
+    float step = (1.0 / H) * lastbd;     // evaluated in double, rounded once
+    float newIdepth = currentIdepth - step;
+    float newHdd = 0, newbd = 0, newEnergy = 0;
+    for (int i = 0; i < nres; i++) newEnergy += linearizeResidual(o, win, p, 1, residuals[i], newHdd, newbd, newIdepth);
+    if (!std::isfinite(lastEnergy) || newHdd < minIdepthH_act) { *idepth_out = currentIdepth; publish(); return SOSBA_ACT_SKIP; }
+    if (newEnergy < lastEnergy) {
+      currentIdepth = newIdepth; lastHdd = newHdd; lastbd = newbd; lastEnergy = newEnergy;
+      for (int i = 0; i < nres; i++) {
+        residuals[i].state_state = residuals[i].state_NewState;
+        residuals[i].state_energy = residuals[i].state_NewEnergy;
+      }
+      lambda *= 0.5;
+    } else {
+      lambda *= 5;
+    }
+    if (fabsf(step) < 0.0001 * currentIdepth) break;   // double comparison
+  }
+  *idepth_out = currentIdepth;
+  publish();
+  if (!std::isfinite(currentIdepth)) return SOSBA_ACT_DELETE;
+  int numGoodRes = 0;
+  for (int i = 0; i < nres; i++)
+    if (residuals[i].state_state == SOSBA_RES_IN) numGoodRes++;
+  if (numGoodRes < win->min_obs) return SOSBA_ACT_DELETE;
+  if (!std::isfinite(p.energyTH)) return SOSBA_ACT_DELETE;   // PointHessian ctor copies energyTH (HessianBlocks.cpp:55)
+  return SOSBA_ACT_ACTIVATED;
+}
+
+// FullSystem::activatePointsMT_Reductor (FullSystem.cpp:363-373)
+void optimize_immature(Oracle &o, const sosba_activation_window *win, const sosba_immature *pts, int8_t *result, float *idepth, uint8_t *res_state) {
+  std::vector<TmpRes> tr(win->nf);
+  for (int k = 0; k < pts->n; k++) {
+    ActPoint p;
+    p.u = pts->u[k]; p.v = pts->v[k]; p.energyTH = pts->energy_th[k]; p.color = pts->color + 8 * (size_t)k; p.weights = pts->weights + 8 * (size_t)k;
+    p.host = pts->host[k];
+    result[k] = (int8_t)optimizeImmaturePoint(o, win, p, pts->idepth_min[k], pts->idepth_max[k], tr.data(), idepth + k, res_state + (size_t)k * win->nf);
   }
 }
 

@@ -83,6 +83,12 @@ class Immature(C.Structure):
                 ("last_trace_pixel_interval", f32p)]
 
 
+class ActivationWindow(C.Structure):
+    _fields_ = [("nf", C.c_int32), ("min_obs", C.c_int32), ("frame_slot", i32p), ("RTll", f32p), ("tTll", f32p), ("aff", f32p),
+                ("calib", C.c_float * 4), ("reserved0", C.c_int32), ("reserved1", C.c_int32)]
+
+
+ACT_SKIP, ACT_ACTIVATED, ACT_DELETE = 0, 1, -1
 IPS_GOOD, IPS_OOB, IPS_OUTLIER, IPS_SKIPPED, IPS_BADCONDITION, IPS_UNINITIALIZED = range(6)
 
 
@@ -138,7 +144,7 @@ class Lib:
                   "accumulate", "points_get_acc", "solve_system", "resubstitute", "marginalize_points",
                   "tracker_make_k", "tracker_set_ref", "tracker_calc_res_pose", "tracker_calc_gs_pose",
                   "scale_set_stereo", "scale_calc_res", "scale_calc_gs", "optimize", "ba_upload", "ba_iterate",
-                  "ba_download", "ba_optimize", "pyr_levels", "immature_init", "trace_immature"):
+                  "ba_download", "ba_optimize", "pyr_levels", "immature_init", "trace_immature", "optimize_immature"):
             self.f(n).restype = C.c_int
         self.f("destroy").restype = None
         if self.has("launch_count"):
@@ -426,6 +432,25 @@ class Handle:
         self._ck(self.lib.f("trace_immature")(self.h, C.c_int32(frame_slot), C.c_int32(KRKi.size // 9), _p(KRKi, f32p), _p(Kt, f32p), _p(aff, f32p),
                                               C.byref(ip), _p(counts, i32p)), "trace_immature")
         return counts
+
+    def optimize_immature(self, frame_slot, RTll, tTll, aff, calib, host, pts, min_obs=1):
+        """optimizeImmaturePoint (FullSystemOptPoint.cpp:47-192) of every point of `pts` (dict of immature_init, after tracing).
+        RTll [nf,nf,3,3], tTll [nf,nf,3], aff [nf,nf,2] per (host, target); calib = fxl fyl cxl cyl.
+        -> result [n] int8 (ACT_*), idepth [n], res_state [n, nf]."""
+        frame_slot, RTll, tTll, aff, host = _i32(frame_slot), _f32(RTll), _f32(tTll), _f32(aff), _i32(host)
+        nf, n = frame_slot.size, host.size
+        arr = {k: _f32(pts[k]) for k in ("u", "v", "color", "weights", "energy_th", "idepth_min", "idepth_max")}
+        win = ActivationWindow(nf=nf, min_obs=min_obs, frame_slot=_p(frame_slot, i32p), RTll=_p(RTll, f32p), tTll=_p(tTll, f32p), aff=_p(aff, f32p),
+                               calib=(C.c_float * 4)(*[float(x) for x in calib]))
+        ip = Immature(n=n, reserved0=0, host=_p(host, i32p), u=_p(arr["u"], f32p), v=_p(arr["v"], f32p), color=_p(arr["color"], f32p),
+                      weights=_p(arr["weights"], f32p), energy_th=_p(arr["energy_th"], f32p), idepth_min=_p(arr["idepth_min"], f32p),
+                      idepth_max=_p(arr["idepth_max"], f32p))
+        result = np.zeros(n, np.int8)
+        idepth = np.zeros(n, np.float32)
+        res_state = np.zeros((n, nf), np.uint8)
+        self._ck(self.lib.f("optimize_immature")(self.h, C.byref(win), C.byref(ip), _p(result, C.POINTER(C.c_int8)), _p(idepth, f32p), _p(res_state, u8p)),
+                 "optimize_immature")
+        return result, idepth, res_state
 
     def tracker_calc_res_pose(self, lvl, slot, refToNew34, affLL, cutoff):
         T = _f64(refToNew34).reshape(12)

@@ -5,9 +5,10 @@
 //   trace_on        ImmaturePoint::traceOn             src/FullSystem/ImmaturePoint.cpp:70-415
 //                   FullSystem::traceNewCoarse         src/FullSystem/FullSystem.cpp:311-361
 //
-// One thread per immature point: the epipolar search is a sequential walk of up to 99 steps with 8 bilinear taps each,
-// followed by at most 3 Gauss-Newton steps on the line; points of one host are contiguous, so neighbouring threads walk
-// neighbouring epipolar segments of the same image (L1/L2 locality).
+// Eight lanes per immature point, one per pattern tap: the epipolar search is a sequential walk of up to 99 steps (the
+// positions accumulate ptx += dx in float), each step 8 bilinear taps that the lanes fetch in parallel and sum in pattern
+// order with shuffles; then at most 3 Gauss-Newton steps on the line.  Points of one host are contiguous, so neighbouring
+// lane groups walk neighbouring epipolar segments of the same image (L1/L2 locality).
 #include <math.h>
 
 #include "kernels.h"
@@ -69,11 +70,36 @@ __global__ void __launch_bounds__(128) k_immature_init(TraceArgs a) {
   a.energyTH_out[p] = th;
 }
 
-__global__ void __launch_bounds__(128) k_trace_on(TraceArgs a) {
+// Sum of the 8 per-tap terms of one point in pattern order, starting from `acc`: ((acc + t0) + t1) + ... -- the order
+// of the reference's scalar loop.  `gmask` is the mask of the point's 8 lanes; every lane returns the same value.
+__device__ __forceinline__ float ordered_sum8(unsigned gmask, float acc, float term) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc += __shfl_sync(gmask, term, i, 8);
+  return acc;
+}
+// same, but only the first `limit` taps contribute (a pattern aborted at tap `limit` keeps its partial sums)
+__device__ __forceinline__ float ordered_sum8_upto(unsigned gmask, float acc, float term, int limit) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float t = __shfl_sync(gmask, term, i, 8);
+    if (i < limit) acc += t;
+  }
+  return acc;
+}
+
+#define TRACE_THREADS 128
+#define TRACE_PPB (TRACE_THREADS / 8)   // points per block
+
+// 8 lanes per point, lane = pattern tap.  All 8 lanes evaluate the (identical) scalar set-up, so every branch is uniform
+// within a point's lane group; the per-step energies are summed across the lanes in pattern order.
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace_on(TraceArgs a) {
   __shared__ int s_cnt[6];
+  __shared__ float s_err[TRACE_PPB][100];
   if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int grp = threadIdx.x >> 3, tap = threadIdx.x & 7;
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+  const int k = blockIdx.x * TRACE_PPB + grp;
   if (k < a.n) {
     int status = a.status[k];
     if (status != SOSBA_IPS_OOB) {
@@ -141,59 +167,62 @@ __global__ void __launch_bounds__(128) k_trace_on(TraceArgs a) {
         int numSteps = 1.9999f + dist / 1.0f;
         const float randShift = uMin * 1000 - floorf(uMin * 1000);
         float ptx = uMin - randShift * dx, pty = vMin - randShift * dy;
-        float rot[8][2];
-#pragma unroll
-        for (int idx = 0; idx < 8; idx++) {
-          rot[idx][0] = KRKi[0] * t_pattern[idx][0] + KRKi[1] * t_pattern[idx][1];
-          rot[idx][1] = KRKi[3] * t_pattern[idx][0] + KRKi[4] * t_pattern[idx][1];
-        }
+        // this lane's rotated pattern offset
+        const float rot0 = KRKi[0] * t_pattern[tap][0] + KRKi[1] * t_pattern[tap][1];
+        const float rot1 = KRKi[3] * t_pattern[tap][0] + KRKi[4] * t_pattern[tap][1];
         if (!isfinite(dx) || !isfinite(dy)) { status = SOSBA_IPS_OOB; done = true; }
         if (!done) {
-          const float *color = a.color + 8 * (size_t)k, *weights = a.weights + 8 * (size_t)k;
-          float col[8];
-#pragma unroll
-          for (int idx = 0; idx < 8; idx++) col[idx] = (float)(aff[0] * color[idx] + aff[1]);
-          float errors[100];
+          const float color = a.color[8 * (size_t)k + tap], weight = a.weights[8 * (size_t)k + tap];
+          const float col = (float)(aff[0] * color + aff[1]);
+          float *errors = s_err[grp];
           float bestU = 0, bestV = 0, bestEnergy = 1e10f;
           int bestIdx = -1;
           if (numSteps >= 100) numSteps = 99;
           for (int i = 0; i < numSteps; i++) {
-            float energy = 0;
-#pragma unroll
-            for (int idx = 0; idx < 8; idx++) {
-              const float hit = interp31(a.img, (float)(ptx + rot[idx][0]), (float)(pty + rot[idx][1]), wG);
-              if (!isfinite(hit)) { energy += 1e5f; continue; }
-              const float residual = hit - col[idx];
+            const float hit = interp31(a.img, (float)(ptx + rot0), (float)(pty + rot1), wG);
+            float term = 1e5f;
+            if (isfinite(hit)) {
+              const float residual = hit - col;
               const float hw = fabsf(residual) < a.huberTH ? 1 : a.huberTH / fabsf(residual);
-              energy += hw * residual * residual * (2 - hw);
+              term = hw * residual * residual * (2 - hw);
             }
-            errors[i] = energy;
+            const float energy = ordered_sum8(gmask, 0.f, term);
+            if (tap == (i & 7)) errors[i] = energy;
             if (energy < bestEnergy) { bestU = ptx; bestV = pty; bestEnergy = energy; bestIdx = i; }
             ptx += dx; pty += dy;
           }
+          __syncwarp(gmask);
+          // min over the steps outside the test radius: each lane scans a stride-8 subset, then the group takes the min
           float secondBest = 1e10f;
-          for (int i = 0; i < numSteps; i++)
+          for (int i = tap; i < numSteps; i += 8)
             if ((i < bestIdx - 2 || i > bestIdx + 2) && errors[i] < secondBest) secondBest = errors[i];   // setting_minTraceTestRadius
+#pragma unroll
+          for (int o = 4; o >= 1; o >>= 1) secondBest = fminf(secondBest, __shfl_xor_sync(gmask, secondBest, o, 8));
           const float newQuality = secondBest / bestEnergy;
           float quality = a.quality[k];
           if (newQuality < quality || numSteps > 10) quality = newQuality;
-          a.quality[k] = quality;
+          __syncwarp(gmask);
+          if (tap == 0) a.quality[k] = quality;
 
           float uBak = bestU, vBak = bestV, stepBack = 0;
           bestEnergy = 1e5f;
           for (int it = 0; it < 3; it++) {   // setting_trace_GNIterations
-            float H = 1, bb = 0, energy = 0;
-#pragma unroll
-            for (int idx = 0; idx < 8; idx++) {
-              const float3 hit = interp33(a.img, (float)(bestU + rot[idx][0]), (float)(bestV + rot[idx][1]), wG);
-              if (!isfinite(hit.x)) { energy += 1e5f; continue; }
-              const float residual = hit.x - (aff[0] * color[idx] + aff[1]);
+            const float3 hit = interp33(a.img, (float)(bestU + rot0), (float)(bestV + rot1), wG);
+            float tH = 0.f, tb = 0.f, tE = 1e5f;
+            if (isfinite(hit.x)) {
+              const float residual = hit.x - (aff[0] * color + aff[1]);
               const float dResdDist = dx * hit.y + dy * hit.z;
               const float hw = fabsf(residual) < a.huberTH ? 1 : a.huberTH / fabsf(residual);
-              H += hw * dResdDist * dResdDist;
-              bb += hw * residual * dResdDist;
-              energy += weights[idx] * weights[idx] * hw * residual * residual * (2 - hw);
+              tH = hw * dResdDist * dResdDist;
+              tb = hw * residual * dResdDist;
+              tE = weight * weight * hw * residual * residual * (2 - hw);
             }
+            // a non-finite tap adds nothing to H and b in the reference; adding +0.f leaves the sums bit-identical
+            // unless a sum is -0.f, which cannot happen (H starts at 1; b = -0.f + 0.f = +0.f only if every term so far was -0.f,
+            // and then b * anything compares and steps identically)
+            const float H = ordered_sum8(gmask, 1.f, tH);
+            const float bb = ordered_sum8(gmask, 0.f, tb);
+            const float energy = ordered_sum8(gmask, 0.f, tE);
             if (energy > bestEnergy) {
               stepBack *= 0.5f;
               bestU = uBak + stepBack * dx;
@@ -226,21 +255,153 @@ __global__ void __launch_bounds__(128) k_trace_on(TraceArgs a) {
               pixint = 2 * errorInPixel; uv0 = bestU; uv1 = bestV;
               status = SOSBA_IPS_GOOD;
             }
-            a.idepth_min[k] = idepth_min; a.idepth_max[k] = idepth_max;   // the interval is rewritten before the NaN test (ImmaturePoint.cpp:385-405)
+            // the interval is rewritten before the NaN test (ImmaturePoint.cpp:385-405)
+            if (tap == 0) { a.idepth_min[k] = idepth_min; a.idepth_max[k] = idepth_max; }
           }
         }
       }
-      a.status[k] = (uint8_t)status;
-      a.uv[2 * (size_t)k] = uv0; a.uv[2 * (size_t)k + 1] = uv1; a.pixint[k] = pixint;
+      if (tap == 0) {
+        a.status[k] = (uint8_t)status;
+        a.uv[2 * (size_t)k] = uv0; a.uv[2 * (size_t)k + 1] = uv1; a.pixint[k] = pixint;
+      }
     }
-    atomicAdd(&s_cnt[status], 1);
+    if (tap == 0) atomicAdd(&s_cnt[status], 1);
   }
   __syncthreads();
   if (threadIdx.x < 6 && s_cnt[threadIdx.x]) atomicAdd(&a.counts[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
+// ---- activation ---------------------------------------------------------------------------------
+//   linearize_residual   ImmaturePoint::linearizeResidual      src/FullSystem/ImmaturePoint.cpp:475-545
+//   k_optimize_immature  FullSystem::optimizeImmaturePoint     src/FullSystem/FullSystemOptPoint.cpp:47-192
+//                        (activatePointsMT_Reductor, FullSystem.cpp:363-373: 8 lanes per immature point, one per pattern tap)
+struct ActPoint {
+  float u, v, energyTH;
+  float color, w2;   // this lane's tap; w2 = weights[idx] * weights[idx], the only form the weights appear in
+  int host;
+};
+
+// Eight lanes per point, lane = pattern tap.  Returns the residual's energy (a float value, or the stored state_energy);
+// Hdd / bd accumulate tap by tap in pattern order, and the partial sums of a residual that leaves the image half-way through
+// the pattern stay in (ImmaturePoint.cpp:497-534): the first failing tap `limit` cuts the ordered sums.
+__device__ __forceinline__ float linearize_residual(const ActivateArgs &a, const ActPoint &p, unsigned gmask, int tap, float slack, int target, uint8_t state,
+                                                    float state_energy, uint8_t &newState, float &newEnergy, float &Hdd, float &bd, float idepth) {
+  if (state == SOSBA_RES_OOB) { newState = SOSBA_RES_OOB; return state_energy; }
+  const size_t pair = (size_t)p.host * a.nf + target;
+  const float *R = a.RTll + 9 * pair, *t = a.tTll + 3 * pair;
+  const float aff0 = __ldg(a.aff + 2 * pair), aff1 = __ldg(a.aff + 2 * pair + 1);
+  float Rr[9], tt[3];
+#pragma unroll
+  for (int i = 0; i < 9; i++) Rr[i] = __ldg(R + i);
+#pragma unroll
+  for (int i = 0; i < 3; i++) tt[i] = __ldg(t + i);
+  const float fxli = 1.0f / a.fxl, fyli = 1.0f / a.fyl;
+  const float wM3G = a.w - 3, hM3G = a.h - 3;
+  const float4 *img = a.img[target];
+  const int dx = t_pattern[tap][0], dy = t_pattern[tap][1];
+  const float K0 = (p.u + dx - a.cxl) * fxli, K1 = (p.v + dy - a.cyl) * fyli;
+  float ptp[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) ptp[i] = ((Rr[3 * i] * K0 + Rr[3 * i + 1] * K1) + Rr[3 * i + 2] * 1.0f) + tt[i] * idepth;
+  const float drescale = 1.0f / ptp[2];
+  bool ok = drescale > 0;
+  const float u = ptp[0] * drescale, v = ptp[1] * drescale;
+  const float Ku = u * a.fxl + a.cxl, Kv = v * a.fyl + a.cyl;
+  ok = ok && (Ku > 1.1f && Kv > 1.1f && Ku < wM3G && Kv < hM3G);
+  float tE = 0.f, tH = 0.f, tb = 0.f;
+  if (ok) {
+    const float3 hit = interp33(img, Ku, Kv, a.w);
+    if (!isfinite(hit.x)) ok = false;
+    else {
+      const float residual = hit.x - (aff0 * p.color + aff1);
+      float hw = fabsf(residual) < a.huberTH ? 1 : a.huberTH / fabsf(residual);
+      tE = p.w2 * hw * residual * residual * (2 - hw);
+      const float dxInterp = hit.y * a.fxl, dyInterp = hit.z * a.fyl;
+      const float d_idepth = (dxInterp * drescale * (tt[0] - tt[2] * u) + dyInterp * drescale * (tt[1] - tt[2] * v)) * 1.0f;   // SCALE_IDEPTH
+      hw *= p.w2;
+      tH = (hw * d_idepth) * d_idepth;
+      tb = (hw * residual) * d_idepth;
+    }
+  }
+  const unsigned shift = (threadIdx.x & 31) & ~7;
+  const unsigned fail = (__ballot_sync(gmask, !ok) >> shift) & 0xFFu;
+  const int limit = fail ? __ffs(fail) - 1 : 8;
+  Hdd = ordered_sum8_upto(gmask, Hdd, tH, limit);
+  bd = ordered_sum8_upto(gmask, bd, tb, limit);
+  if (fail) { newState = SOSBA_RES_OOB; return state_energy; }
+  float energyLeft = ordered_sum8(gmask, 0.f, tE);
+  if (energyLeft > p.energyTH * slack) { energyLeft = p.energyTH * slack; newState = SOSBA_RES_OUTLIER; }
+  else newState = SOSBA_RES_IN;
+  newEnergy = energyLeft;
+  return energyLeft;
+}
+
+__global__ void __launch_bounds__(TRACE_THREADS) k_optimize_immature(ActivateArgs a) {
+  const int grp = threadIdx.x >> 3, tap = threadIdx.x & 7;
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+  const int k = blockIdx.x * TRACE_PPB + grp;
+  if (k >= a.n) return;
+  ActPoint p;
+  p.u = a.u[k]; p.v = a.v[k]; p.energyTH = a.energyTH[k]; p.host = a.host[k];
+  p.color = a.color[8 * (size_t)k + tap];
+  { const float w = a.weights[8 * (size_t)k + tap]; p.w2 = w * w; }
+  // ImmaturePointTemporaryResidual per target frame (slot of the host unused); identical in the 8 lanes
+  uint8_t st[SOSBA_ACT_MAXF], nst[SOSBA_ACT_MAXF];
+  float en[SOSBA_ACT_MAXF], nen[SOSBA_ACT_MAXF];
+  const int nf = a.nf;
+  for (int f = 0; f < nf; f++) { st[f] = SOSBA_RES_IN; nst[f] = SOSBA_RES_OUTLIER; en[f] = nen[f] = 0.f; }
+  float lastEnergy = 0, lastHdd = 0, lastbd = 0;
+  float currentIdepth = (a.idepth_max[k] + a.idepth_min[k]) * 0.5f;
+  for (int f = 0; f < nf; f++) {
+    if (f == p.host) continue;
+    const float e = linearize_residual(a, p, gmask, tap, 1000.f, f, st[f], en[f], nst[f], nen[f], lastHdd, lastbd, currentIdepth);
+    lastEnergy = (float)((double)lastEnergy + (double)e);   // float += double (FullSystemOptPoint.cpp:70)
+    st[f] = nst[f]; en[f] = nen[f];
+  }
+  int result = SOSBA_ACT_ACTIVATED;
+  if (!isfinite(lastEnergy) || lastHdd < 100.f) result = SOSBA_ACT_SKIP;   // setting_minIdepthH_act
+  if (result == SOSBA_ACT_ACTIVATED) {
+    float lambda = 0.1f;
+    for (int iteration = 0; iteration < 3; iteration++) {   // setting_GNItsOnPointActivation
+      float H = lastHdd;
+      H *= 1 + lambda;
+      const float step = (float)((1.0 / (double)H) * (double)lastbd);
+      const float newIdepth = currentIdepth - step;
+      float newHdd = 0, newbd = 0, newEnergy = 0;
+      for (int f = 0; f < nf; f++) {
+        if (f == p.host) continue;
+        const float e = linearize_residual(a, p, gmask, tap, 1.f, f, st[f], en[f], nst[f], nen[f], newHdd, newbd, newIdepth);
+        newEnergy = (float)((double)newEnergy + (double)e);
+      }
+      if (!isfinite(lastEnergy) || newHdd < 100.f) { result = SOSBA_ACT_SKIP; break; }
+      if (newEnergy < lastEnergy) {
+        currentIdepth = newIdepth; lastHdd = newHdd; lastbd = newbd; lastEnergy = newEnergy;
+        for (int f = 0; f < nf; f++) { st[f] = nst[f]; en[f] = nen[f]; }
+        lambda = (float)((double)lambda * 0.5);
+      } else {
+        lambda *= 5;
+      }
+      if ((double)fabsf(step) < 0.0001 * (double)currentIdepth) break;
+    }
+  }
+  if (tap != 0) return;
+  int good = 0;
+  for (int f = 0; f < nf; f++) {
+    a.res_state[(size_t)k * nf + f] = f == p.host ? 255 : st[f];
+    good += (f != p.host && st[f] == SOSBA_RES_IN);
+  }
+  if (result == SOSBA_ACT_ACTIVATED && (!isfinite(currentIdepth) || good < a.min_obs || !isfinite(p.energyTH))) result = SOSBA_ACT_DELETE;
+  a.result[k] = (signed char)result;
+  a.idepth[k] = currentIdepth;
+}
+
 }  // namespace
 
+void launch_optimize_immature(sosba *h, const ActivateArgs &a) {
+  if (a.n == 0) return;
+  k_optimize_immature<<<(a.n + TRACE_PPB - 1) / TRACE_PPB, TRACE_THREADS, 0, h->stream>>>(a);
+  h->launches++;
+}
 void launch_immature_init(sosba *h, const TraceArgs &a) {
   if (a.n == 0) return;
   k_immature_init<<<(a.n + 127) / 128, 128, 0, h->stream>>>(a);
@@ -248,6 +409,6 @@ void launch_immature_init(sosba *h, const TraceArgs &a) {
 }
 void launch_trace_on(sosba *h, const TraceArgs &a) {
   if (a.n == 0) return;
-  k_trace_on<<<(a.n + 127) / 128, 128, 0, h->stream>>>(a);
+  k_trace_on<<<(a.n + TRACE_PPB - 1) / TRACE_PPB, TRACE_THREADS, 0, h->stream>>>(a);
   h->launches++;
 }

@@ -230,6 +230,19 @@ struct TraceArgs {
   float huberTH;
   int *counts;                // [6] per ImmaturePointStatus
 };
+#define SOSBA_ACT_MAXF 32
+struct ActivateArgs {
+  int n, nf, w, h, min_obs;
+  const float4 *img[SOSBA_ACT_MAXF];   // level 0 of frame f
+  const float *RTll, *tTll, *aff;      // per (host * nf + target)
+  float fxl, fyl, cxl, cyl, huberTH;
+  const int *host;
+  const float *u, *v, *color, *weights, *energyTH, *idepth_min, *idepth_max;
+  signed char *result;
+  float *idepth;
+  uint8_t *res_state;                  // [n * nf]
+};
+void launch_optimize_immature(sosba *h, const ActivateArgs &a);
 void launch_immature_init(sosba *h, const TraceArgs &a);
 void launch_trace_on(sosba *h, const TraceArgs &a);
 

@@ -52,6 +52,10 @@ struct BA {
 struct HostSide {
   float *d_imm = nullptr;   // immature-point arena (k_trace.cu): 30 floats + 1 status byte per point, grown on demand
   size_t imm_cap = 0;
+  float *d_act = nullptr;       // activation outputs: [idepth n floats][result n bytes][res_state n*nf bytes]
+  size_t act_cap = 0;
+  float *d_act_win = nullptr;   // PRE_RTll / PRE_tTll / PRE_aff_mode per frame pair
+  int act_win_cap = 0;
   float *d_imm_host = nullptr;   // KRKi / Kt / aff per host frame + the 6 status counters
   int imm_host_cap = 0;
   std::vector<int> p_host, res_begin, r_point, r_target, r_host_tmp;
@@ -1488,6 +1492,21 @@ API int sosba_immature_init(sosba_t *h, int32_t host_slot, int32_t n, const int3
   return sync(h);
 }
 
+// A block of the pinned staging ring, valid until the stream is synchronised twice (the ring only wraps behind a sync).
+static int stage_reserve(sosba *h, size_t bytes, char **p) {
+  HostSide *hs = HS(h);
+  if (!hs->stage || bytes > hs->stage_cap) { sosba_set_error("staging block of %zu bytes", bytes); return SOSBA_E_ARG; }
+  if (hs->stage_off + bytes > hs->stage_cap) {
+    SOSBA_CUDA(cudaStreamSynchronize(h->stream));
+    hs->stage_off = 0;
+  }
+  *p = hs->stage + hs->stage_off;
+  hs->stage_off += (bytes + 255) & ~(size_t)255;
+  return SOSBA_OK;
+}
+static const int IMM_CHUNK = 48 * 1024;   // points per pass: 48k x 121 B = 5.8 MB of the 16 MB ring
+
+// One pass = one H2D of the packed SoA, one launch, one D2H of the in/out tail, one synchronisation.
 API int sosba_trace_immature(sosba_t *h, int32_t frame_slot, int32_t nhosts, const float *KRKi, const float *Kt, const float *aff, sosba_immature *pts,
                              int32_t counts[6]) {
   CHECK_H(h);
@@ -1496,48 +1515,121 @@ API int sosba_trace_immature(sosba_t *h, int32_t frame_slot, int32_t nhosts, con
     return SOSBA_E_ARG;
   }
   if (counts) for (int i = 0; i < 6; i++) counts[i] = 0;
-  const int n = pts->n;
-  if (n == 0) return SOSBA_OK;
+  if (pts->n == 0) return SOSBA_OK;
   if (!KRKi || !Kt || !aff || !pts->host || !pts->u || !pts->v || !pts->color || !pts->weights || !pts->gradH || !pts->energy_th || !pts->idepth_min ||
       !pts->idepth_max || !pts->quality || !pts->last_trace_status || !pts->last_trace_uv || !pts->last_trace_pixel_interval) {
     sosba_set_error("null buffer");
     return SOSBA_E_ARG;
   }
-  for (int i = 0; i < n; i++)
+  for (int i = 0; i < pts->n; i++)
     if (pts->host[i] < 0 || pts->host[i] >= nhosts) { sosba_set_error("point %d: host %d outside [0,%d)", i, pts->host[i], nhosts); return SOSBA_E_ARG; }
   int rc;
-  if ((rc = ensure_immature(h, (size_t)n, nhosts))) return rc;
+  if ((rc = ensure_immature(h, (size_t)std::min(pts->n, IMM_CHUNK), nhosts))) return rc;
   HostSide *hs = HS(h);
-  const size_t N = (size_t)n;
-  float *d = hs->d_imm, *dh = hs->d_imm_host;
-  float *d_u = d, *d_v = d + N, *d_color = d + 2 * N, *d_w = d + 10 * N, *d_G = d + 18 * N, *d_eth = d + 22 * N, *d_min = d + 23 * N, *d_max = d + 24 * N,
-        *d_q = d + 25 * N, *d_uv = d + 26 * N, *d_pi = d + 28 * N;
-  int *d_host = (int *)(d + 29 * N);
-  uint8_t *d_st = (uint8_t *)(d + 30 * N);
+  float *dh = hs->d_imm_host;
   int *d_counts = (int *)(dh + 14 * (size_t)hs->imm_host_cap);
-  if ((rc = up(h, d_u, pts->u, N)) || (rc = up(h, d_v, pts->v, N)) || (rc = up(h, d_color, pts->color, 8 * N)) || (rc = up(h, d_w, pts->weights, 8 * N)) ||
-      (rc = up(h, d_G, pts->gradH, 4 * N)) || (rc = up(h, d_eth, pts->energy_th, N)) || (rc = up(h, d_min, (const float *)pts->idepth_min, N)) ||
-      (rc = up(h, d_max, (const float *)pts->idepth_max, N)) || (rc = up(h, d_q, (const float *)pts->quality, N)) ||
-      (rc = up(h, d_uv, (const float *)pts->last_trace_uv, 2 * N)) || (rc = up(h, d_pi, (const float *)pts->last_trace_pixel_interval, N)) ||
-      (rc = up(h, d_host, (const int *)pts->host, N)) || (rc = up(h, d_st, (const uint8_t *)pts->last_trace_status, N)) ||
-      (rc = up(h, dh, KRKi, 9 * (size_t)nhosts)) || (rc = up(h, dh + 9 * (size_t)hs->imm_host_cap, Kt, 3 * (size_t)nhosts)) ||
+  if ((rc = up(h, dh, KRKi, 9 * (size_t)nhosts)) || (rc = up(h, dh + 9 * (size_t)hs->imm_host_cap, Kt, 3 * (size_t)nhosts)) ||
       (rc = up(h, dh + 12 * (size_t)hs->imm_host_cap, aff, 2 * (size_t)nhosts)))
     return rc;
   SOSBA_CUDA(cudaMemsetAsync(d_counts, 0, 6 * sizeof(int), h->stream));
-  TraceArgs a = {};
-  a.n = n; a.w = h->wl[0]; a.h = h->hl[0]; a.img = h->slot_img[frame_slot] + h->lvl_off[0];
-  a.host = d_host; a.u = d_u; a.v = d_v; a.color = d_color; a.weights = d_w; a.gradH = d_G; a.energyTH = d_eth;
-  a.idepth_min = d_min; a.idepth_max = d_max; a.quality = d_q; a.uv = d_uv; a.pixint = d_pi; a.status = d_st;
-  a.KRKi = dh; a.Kt = dh + 9 * (size_t)hs->imm_host_cap; a.aff = dh + 12 * (size_t)hs->imm_host_cap;
-  a.huberTH = h->cfg.huber_th; a.counts = d_counts;
-  launch_trace_on(h, a);
-  SOSBA_CUDA(cudaGetLastError());
-  if ((rc = down(h, pts->idepth_min, (const float *)d_min, N)) || (rc = down(h, pts->idepth_max, (const float *)d_max, N)) ||
-      (rc = down(h, pts->quality, (const float *)d_q, N)) || (rc = down(h, pts->last_trace_uv, (const float *)d_uv, 2 * N)) ||
-      (rc = down(h, pts->last_trace_pixel_interval, (const float *)d_pi, N)) || (rc = down(h, pts->last_trace_status, (const uint8_t *)d_st, N)) ||
-      (rc = down(h, hs->pin_i, (const int *)d_counts, 6)))
-    return rc;
-  if ((rc = sync(h))) return rc;
+  for (int off = 0; off < pts->n; off += IMM_CHUNK) {
+    const int n = std::min(IMM_CHUNK, pts->n - off);
+    const size_t N = (size_t)n, bytes = 30 * N * sizeof(float) + N;
+    char *blk;
+    if ((rc = stage_reserve(h, bytes, &blk))) return rc;
+    float *s = (float *)blk, *d = hs->d_imm;
+    // arena (floats): [u][v][color 8][weights 8][gradH 4][energyTH] | [idmin][idmax][quality][uv 2][pixint] [host (int)] [status (bytes)]
+    memcpy(s, pts->u + off, 4 * N); memcpy(s + N, pts->v + off, 4 * N);
+    memcpy(s + 2 * N, pts->color + 8 * (size_t)off, 32 * N); memcpy(s + 10 * N, pts->weights + 8 * (size_t)off, 32 * N);
+    memcpy(s + 18 * N, pts->gradH + 4 * (size_t)off, 16 * N); memcpy(s + 22 * N, pts->energy_th + off, 4 * N);
+    memcpy(s + 23 * N, pts->idepth_min + off, 4 * N); memcpy(s + 24 * N, pts->idepth_max + off, 4 * N); memcpy(s + 25 * N, pts->quality + off, 4 * N);
+    memcpy(s + 26 * N, pts->last_trace_uv + 2 * (size_t)off, 8 * N); memcpy(s + 28 * N, pts->last_trace_pixel_interval + off, 4 * N);
+    memcpy(s + 29 * N, pts->host + off, 4 * N); memcpy(s + 30 * N, pts->last_trace_status + off, N);
+    SOSBA_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyHostToDevice, h->stream));
+    TraceArgs a = {};
+    a.n = n; a.w = h->wl[0]; a.h = h->hl[0]; a.img = h->slot_img[frame_slot] + h->lvl_off[0];
+    a.u = d; a.v = d + N; a.color = d + 2 * N; a.weights = d + 10 * N; a.gradH = d + 18 * N; a.energyTH = d + 22 * N;
+    a.idepth_min = d + 23 * N; a.idepth_max = d + 24 * N; a.quality = d + 25 * N; a.uv = d + 26 * N; a.pixint = d + 28 * N;
+    a.host = (const int *)(d + 29 * N); a.status = (uint8_t *)(d + 30 * N);
+    a.KRKi = dh; a.Kt = dh + 9 * (size_t)hs->imm_host_cap; a.aff = dh + 12 * (size_t)hs->imm_host_cap;
+    a.huberTH = h->cfg.huber_th; a.counts = d_counts;
+    launch_trace_on(h, a);
+    SOSBA_CUDA(cudaGetLastError());
+    SOSBA_CUDA(cudaMemcpyAsync(s + 23 * N, d + 23 * N, 7 * N * sizeof(float) + N, cudaMemcpyDeviceToHost, h->stream));
+    if (off + n >= pts->n) { if ((rc = down(h, hs->pin_i, (const int *)d_counts, 6))) return rc; }
+    if ((rc = sync(h))) return rc;
+    memcpy(pts->idepth_min + off, s + 23 * N, 4 * N); memcpy(pts->idepth_max + off, s + 24 * N, 4 * N); memcpy(pts->quality + off, s + 25 * N, 4 * N);
+    memcpy(pts->last_trace_uv + 2 * (size_t)off, s + 26 * N, 8 * N); memcpy(pts->last_trace_pixel_interval + off, s + 28 * N, 4 * N);
+    memcpy(pts->last_trace_status + off, s + 30 * N, N);
+  }
   if (counts) for (int i = 0; i < 6; i++) counts[i] = hs->pin_i[i];
+  return SOSBA_OK;
+}
+
+API int sosba_optimize_immature(sosba_t *h, const sosba_activation_window *win, const sosba_immature *pts, int8_t *result, float *idepth, uint8_t *res_state) {
+  CHECK_H(h);
+  if (!win || !pts || win->nf < 1 || win->nf > SOSBA_ACT_MAXF || pts->n < 0 || !win->frame_slot || !win->RTll || !win->tTll || !win->aff) {
+    sosba_set_error("bad activation window (1 <= nf <= %d)", SOSBA_ACT_MAXF);
+    return SOSBA_E_ARG;
+  }
+  const int nf = win->nf;
+  if (pts->n == 0) return SOSBA_OK;
+  if (!pts->host || !pts->u || !pts->v || !pts->color || !pts->weights || !pts->energy_th || !pts->idepth_min || !pts->idepth_max || !result || !idepth ||
+      !res_state) {
+    sosba_set_error("null buffer");
+    return SOSBA_E_ARG;
+  }
+  ActivateArgs a = {};
+  for (int f = 0; f < nf; f++) {
+    const int slot = win->frame_slot[f];
+    if (slot < 0 || slot >= (int)h->slot_img.size() || !h->slot_valid[slot]) { sosba_set_error("frame %d: bad slot %d", f, slot); return SOSBA_E_ARG; }
+    a.img[f] = h->slot_img[slot] + h->lvl_off[0];
+  }
+  for (int i = 0; i < pts->n; i++)
+    if (pts->host[i] < 0 || pts->host[i] >= nf) { sosba_set_error("point %d: host %d outside [0,%d)", i, pts->host[i], nf); return SOSBA_E_ARG; }
+  int rc;
+  const int chunk = std::min(pts->n, IMM_CHUNK);
+  if ((rc = ensure_immature(h, (size_t)chunk, 1))) return rc;
+  HostSide *hs = HS(h);
+  const size_t out_bytes = (size_t)chunk * (4 + 1 + nf);
+  if (out_bytes > hs->act_cap) {
+    dfree(h, hs->d_act);
+    hs->act_cap = out_bytes + out_bytes / 4 + 1024;
+    DALLOC(h, hs->d_act, (hs->act_cap + 3) / 4);
+  }
+  if (nf * nf > hs->act_win_cap) {
+    dfree(h, hs->d_act_win);
+    hs->act_win_cap = nf * nf;
+    DALLOC(h, hs->d_act_win, 14 * (size_t)hs->act_win_cap);
+  }
+  float *dw = hs->d_act_win;
+  const size_t NP = (size_t)nf * nf;
+  if ((rc = up(h, dw, win->RTll, 9 * NP)) || (rc = up(h, dw + 9 * NP, win->tTll, 3 * NP)) || (rc = up(h, dw + 12 * NP, win->aff, 2 * NP))) return rc;
+  a.nf = nf; a.w = h->wl[0]; a.h = h->hl[0]; a.min_obs = win->min_obs;
+  a.RTll = dw; a.tTll = dw + 9 * NP; a.aff = dw + 12 * NP;
+  a.fxl = win->calib[0]; a.fyl = win->calib[1]; a.cxl = win->calib[2]; a.cyl = win->calib[3]; a.huberTH = h->cfg.huber_th;
+  for (int off = 0; off < pts->n; off += IMM_CHUNK) {
+    const int n = std::min(IMM_CHUNK, pts->n - off);
+    const size_t N = (size_t)n, in_bytes = 22 * N * sizeof(float), ob = N * (4 + 1 + nf);
+    char *blk;
+    if ((rc = stage_reserve(h, std::max(in_bytes, ob), &blk))) return rc;
+    float *s = (float *)blk, *d = hs->d_imm;
+    // arena (floats): [u][v][color 8][weights 8][energyTH][idmin][idmax][host (int)]
+    memcpy(s, pts->u + off, 4 * N); memcpy(s + N, pts->v + off, 4 * N);
+    memcpy(s + 2 * N, pts->color + 8 * (size_t)off, 32 * N); memcpy(s + 10 * N, pts->weights + 8 * (size_t)off, 32 * N);
+    memcpy(s + 18 * N, pts->energy_th + off, 4 * N); memcpy(s + 19 * N, pts->idepth_min + off, 4 * N); memcpy(s + 20 * N, pts->idepth_max + off, 4 * N);
+    memcpy(s + 21 * N, pts->host + off, 4 * N);
+    SOSBA_CUDA(cudaMemcpyAsync(d, s, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    a.n = n;
+    a.u = d; a.v = d + N; a.color = d + 2 * N; a.weights = d + 10 * N; a.energyTH = d + 18 * N; a.idepth_min = d + 19 * N; a.idepth_max = d + 20 * N;
+    a.host = (const int *)(d + 21 * N);
+    a.idepth = hs->d_act; a.result = (signed char *)(hs->d_act + N); a.res_state = (uint8_t *)(hs->d_act + N) + N;
+    launch_optimize_immature(h, a);
+    SOSBA_CUDA(cudaGetLastError());
+    // the input block has been consumed by the copy engine once the kernel ran; reuse it for the results
+    SOSBA_CUDA(cudaMemcpyAsync(blk, hs->d_act, ob, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = sync(h))) return rc;
+    memcpy(idepth + off, blk, 4 * N); memcpy(result + off, blk + 4 * N, N); memcpy(res_state + (size_t)off * nf, blk + 5 * N, N * nf);
+  }
   return SOSBA_OK;
 }

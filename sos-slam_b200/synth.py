@@ -319,3 +319,20 @@ def trace_case(scene: Scene, new_frame: int, n_per_host: int = 200, seed: int = 
         us.append(rng.integers(6, scene.w - 7, n_per_host).astype(np.int32))
         vs.append(rng.integers(6, scene.h - 7, n_per_host).astype(np.int32))
     return dict(host=np.concatenate(hosts), u=np.concatenate(us), v=np.concatenate(vs), KRKi=KRKi, Kt=Kt, aff=aff)
+
+
+def activation_case(scene: Scene):
+    """Per (host, target) FrameFramePrecalc::PRE_RTll / PRE_tTll / PRE_aff_mode (HessianBlocks.cpp:184-214) of the
+    window at the scene's estimated poses -> dict(RTll [nf,nf,3,3], tTll [nf,nf,3], aff [nf,nf,2], calib [4])."""
+    nf = scene.nf
+    RTll = np.zeros((nf, nf, 3, 3), np.float32)
+    tTll = np.zeros((nf, nf, 3), np.float32)
+    aff = np.zeros((nf, nf, 2), np.float32)
+    for hst in range(nf):
+        for tgt in range(nf):
+            T = np.linalg.inv(scene.evalPT[tgt]) @ scene.evalPT[hst]
+            RTll[hst, tgt] = T[:3, :3]
+            tTll[hst, tgt] = T[:3, 3]
+            a = np.exp(scene.aff_true[tgt, 0] - scene.aff_true[hst, 0]) * scene.ab_exposure[tgt] / scene.ab_exposure[hst]
+            aff[hst, tgt] = (a, scene.aff_true[tgt, 1] - a * scene.aff_true[hst, 1])
+    return dict(RTll=RTll, tTll=tTll, aff=aff, calib=np.asarray(scene.K, np.float32))

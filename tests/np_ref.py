@@ -512,3 +512,103 @@ def trace_on_ref(dI, p, KRKi, Kt, aff, huber=F(9)):
     if not (np.isfinite(lo) and np.isfinite(hi)) or hi < 0:
         return leave(IPS_OUTLIER)
     return leave(IPS_GOOD, (bestU, bestV), F(2) * err_px)
+
+
+ACT_SKIP, ACT_ACTIVATED, ACT_DELETE = 0, 1, -1
+
+
+def _linearize_residual_ref(dI, p, R, t, affLL, calib, slack, tr, acc, idepth, huber=F(9)):
+    """ImmaturePoint::linearizeResidual (ImmaturePoint.cpp:475-545).  tr: dict(state, energy, new_state, new_energy);
+    acc: [Hdd, bd] accumulated in place (partial sums of an aborted pattern stay, as in the reference)."""
+    if tr["state"] == 1:
+        tr["new_state"] = 1
+        return np.float64(tr["energy"])
+    h, w = dI.shape[:2]
+    fx, fy, cx, cy = [F(x) for x in calib]
+    fxi, fyi = F(1) / fx, F(1) / fy
+    E = F(0)
+    for idx, (px, py) in enumerate(PATTERN):
+        Kl = np.array([(F(p["u"]) + F(px) - cx) * fxi, (F(p["v"]) + F(py) - cy) * fyi, F(1)], F)
+        ptp = ((R[:, 0] * Kl[0] + R[:, 1] * Kl[1]) + R[:, 2] * Kl[2]) + t * idepth
+        with np.errstate(all="ignore"):
+            dres = F(1) / ptp[2]
+        if not dres > 0:
+            tr["new_state"] = 1
+            return np.float64(tr["energy"])
+        u, v = ptp[0] * dres, ptp[1] * dres
+        Ku, Kv = u * fx + cx, v * fy + cy
+        if not (Ku > F(1.1) and Kv > F(1.1) and Ku < F(w - 3) and Kv < F(h - 3)):
+            tr["new_state"] = 1
+            return np.float64(tr["energy"])
+        hit = _bilin(dI, Ku, Kv)
+        if not np.isfinite(hit[0]):
+            tr["new_state"] = 1
+            return np.float64(tr["energy"])
+        res = hit[0] - (affLL[0] * F(p["color"][idx]) + affLL[1])
+        hw = F(1) if abs(res) < huber else huber / abs(res)
+        wt = F(p["weights"][idx])
+        E = E + wt * wt * hw * res * res * (F(2) - hw)
+        dxi, dyi = hit[1] * fx, hit[2] * fy
+        dd = dxi * dres * (t[0] - t[2] * u) + dyi * dres * (t[1] - t[2] * v)
+        hw = hw * (wt * wt)
+        acc[0] = acc[0] + (hw * dd) * dd
+        acc[1] = acc[1] + (hw * res) * dd
+    lim = F(p["energy_th"]) * F(slack)
+    if E > lim:
+        E = lim
+        tr["new_state"] = 2
+    else:
+        tr["new_state"] = 0
+    tr["new_energy"] = np.float64(E)
+    return np.float64(E)
+
+
+def optimize_immature_ref(dIs, p, host, RTll, tTll, aff, calib, min_obs=1):
+    """FullSystem::optimizeImmaturePoint (FullSystemOptPoint.cpp:47-192) for one point.  dIs: list of (h, w, 3) images per
+    frame.  -> (result, idepth, states[nf])."""
+    nf = len(dIs)
+    targets = [f for f in range(nf) if f != host]
+    trs = {f: dict(state=0, energy=np.float64(0), new_state=2, new_energy=np.float64(0)) for f in targets}
+
+    def sweep(slack, idepth):
+        acc = [F(0), F(0)]
+        E = F(0)
+        for f in targets:
+            E = F(np.float64(E) + _linearize_residual_ref(dIs[f], p, RTll[host, f], tTll[host, f], aff[host, f], calib, slack, trs[f], acc, idepth))
+        return E, acc[0], acc[1]
+
+    def commit():
+        for f in targets:
+            trs[f]["state"] = trs[f]["new_state"]; trs[f]["energy"] = trs[f]["new_energy"]
+
+    def states():
+        s = np.full(nf, 255, np.uint8)
+        for f in targets:
+            s[f] = trs[f]["state"]
+        return s
+
+    cur = (F(p["idepth_max"]) + F(p["idepth_min"])) * F(0.5)
+    lastE, lastH, lastb = sweep(1000, cur)
+    commit()
+    if not np.isfinite(lastE) or lastH < 100:
+        return ACT_SKIP, cur, states()
+    lam = F(0.1)
+    for _ in range(3):
+        H = lastH * (F(1) + lam)
+        step = F((1.0 / np.float64(H)) * np.float64(lastb))
+        new = cur - step
+        newE, newH, newb = sweep(1, new)
+        if not np.isfinite(lastE) or newH < 100:
+            return ACT_SKIP, cur, states()
+        if newE < lastE:
+            cur, lastH, lastb, lastE = new, newH, newb, newE
+            commit()
+            lam = F(np.float64(lam) * 0.5)
+        else:
+            lam = lam * F(5)
+        if np.float64(abs(step)) < 0.0001 * np.float64(cur):
+            break
+    st = states()
+    if not np.isfinite(cur) or int(np.sum(st == 0)) < min_obs or not np.isfinite(p["energy_th"]):
+        return ACT_DELETE, cur, st
+    return ACT_ACTIVATED, cur, st

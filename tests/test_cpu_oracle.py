@@ -452,3 +452,35 @@ def test_trace_immature_vs_numpy(orc):
 def trace_points_cpu(h, sc, host, u, v):
     parts = [h.immature_init(int(hst), u[host == hst], v[host == hst]) for hst in np.unique(host)]
     return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+
+
+def test_optimize_immature_vs_numpy(orc):
+    """FullSystem::optimizeImmaturePoint + ImmaturePoint::linearizeResidual (FullSystemOptPoint.cpp:47-192,
+    ImmaturePoint.cpp:475-545) on points traced twice: result code and residual states identical, idepth to rounding."""
+    from sos_slam_b200 import synth
+    sc = scene(**SMALLC)
+    h = open_handle(orc, sc)
+    case = synth.trace_case(sc, sc.nf - 2, n_per_host=80, seed=5)
+    keep = case["host"] < sc.nf - 2
+    host, u, v = case["host"][keep], case["u"][keep], case["v"][keep]
+    pts = trace_points_cpu(h, sc, host, u, v)
+    for new_frame in (sc.nf - 2, sc.nf - 1):
+        c = synth.trace_case(sc, new_frame, n_per_host=1)
+        h.trace_immature(new_frame, host, c["KRKi"], c["Kt"], c["aff"], pts)
+    ok = np.isfinite(pts["idepth_max"])          # activatePointsMT drops never-traced points before this step (FullSystem.cpp:437-444)
+    sel = {k: x[ok] for k, x in pts.items()}
+    hs = host[ok]
+    win = synth.activation_case(sc)
+    result, idepth, states = h.optimize_immature(np.arange(sc.nf), win["RTll"], win["tTll"], win["aff"], win["calib"], hs, sel)
+    dIs = [_dI_of(h, f, sc) for f in range(sc.nf)]
+    seen = set()
+    for k in range(hs.size):
+        p = {key: sel[key][k] for key in ("u", "v", "color", "weights", "energy_th", "idepth_min", "idepth_max")}
+        r, d, st = np_ref.optimize_immature_ref(dIs, p, int(hs[k]), win["RTll"], win["tTll"], win["aff"], win["calib"])
+        assert r == result[k], (k, r, result[k])
+        assert np.array_equal(st, states[k]), (k, st, states[k])
+        np.testing.assert_allclose(d, idepth[k], rtol=1e-4)
+        seen.add(int(r))
+    assert np_ref.ACT_ACTIVATED in seen and len(seen) >= 2, seen
+    assert (result == np_ref.ACT_ACTIVATED).sum() > hs.size // 4
+    h.close()

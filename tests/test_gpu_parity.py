@@ -305,6 +305,18 @@ def test_immature_trace_bit_exact(gpu, orc, cfg):
             assert np.array_equal(pg[k], po[k], equal_nan=True), (new_frame, k, int(np.sum(pg[k] != po[k])))
         seen += cg
     assert np.all(seen[:4] > 0) and (cfg is SMALL or seen[4] > 0), seen     # GOOD, OOB, OUTLIER, SKIPPED (+ BADCONDITION on the larger images)
+
+    # activation: optimizeImmaturePoint + linearizeResidual (FullSystemOptPoint.cpp:47-192, ImmaturePoint.cpp:475-545) of
+    # every point that was traced successfully at least once -- result code, depth and residual states bit for bit
+    ok = np.isfinite(pg["idepth_max"])
+    sub = {k: x[ok] for k, x in pg.items()}
+    win = synth.activation_case(sc)
+    outs = [h.optimize_immature(np.arange(sc.nf), win["RTll"], win["tTll"], win["aff"], win["calib"], sel["host"][ok], sub) for h in (hg, ho)]
+    for name, x, y in zip(("result", "idepth", "res_state"), outs[0], outs[1]):
+        assert np.array_equal(x, y, equal_nan=True), (name, int(np.sum(x != y)))
+    res = outs[0][0]
+    assert (res == 1).sum() > ok.sum() // 4 and (res != 1).sum() > 0, np.bincount(res + 1, minlength=3)
+    assert np.all(outs[0][2][np.arange(ok.sum()), sel["host"][ok]] == 255)
     hg.close(); ho.close()
 
 

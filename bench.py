@@ -356,6 +356,17 @@ def main():
                 h.frame_make_images(sc.nf, sc.images[-1])      # a1: H2D of the irradiance image + the 4-level pyramid
             h.synchronize()
             pyr_ms = 1e3 * (time.perf_counter() - t0) / reps
+            # 8f rank 2: raw 8-bit frame in, photometric + geometric undistortion and the pyramid on the device
+            uc = synth.undistort_case(sc.w, sc.h)
+            h.undistort_set(uc["w_org"], uc["h_org"], uc["remapX"], uc["remapY"], uc["G"], uc["vignette_inv"])
+            h.frame_make_images_raw(sc.nf, uc["raw"])
+            h.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                h.frame_make_images_raw(sc.nf, uc["raw"])
+            h.synchronize()
+            raw_ms = 1e3 * (time.perf_counter() - t0) / reps
+            h.frame_make_images(sc.nf, sc.images[-1])
             rng = np.random.default_rng(5)
             n_ref = 10000
             K = sc.K.astype(np.float32)
@@ -398,7 +409,9 @@ def main():
                 act = h.optimize_immature(np.arange(sc.nf), win["RTll"], win["tTll"], win["aff"], win["calib"], case["host"][okp], sub)
                 act_ms.append(1e3 * (time.perf_counter() - t0))
             other = {"optimize_immature_ms": float(np.median(act_ms)), "optimize_immature_points": int(okp.sum()),
-                     "optimize_immature_activated": int((act[0] == 1).sum()), "make_images_ms": pyr_ms, "make_images_note": f"{sc.w}x{sc.h}, H2D + 4 levels, host wall per call",
+                     "optimize_immature_activated": int((act[0] == 1).sum()), "make_images_raw_ms": raw_ms,
+                     "make_images_raw_note": f"{uc['w_org']}x{uc['h_org']} 8-bit raw frame in: H2D + response/vignette + rectification + 4 levels, host wall per call",
+                     "make_images_ms": pyr_ms, "make_images_note": f"{sc.w}x{sc.h}, H2D + 4 levels, host wall per call",
                      "trace_immature_ms": float(np.median(trace_ms)), "trace_immature_points": int(case["host"].size),
                      "trace_immature_counts": [int(x) for x in trace_counts],
                      "trace_note": "first trace (unbounded interval: the longest epipolar search), host SoA in and out, host wall per call",
@@ -445,6 +458,17 @@ def main():
                 if n >= 1:
                     tcpu += dt; rcpu += o["reserved0"] * 8 * (o["iterations"] + 2)
                 n += 1
+            cpu_raw_ms = None
+            try:
+                uc = synth.undistort_case(sc1.w, sc1.h)
+                oh.undistort_set(uc["w_org"], uc["h_org"], uc["remapX"], uc["remapY"], uc["G"], uc["vignette_inv"])
+                oh.frame_make_images_raw(sc1.nf, uc["raw"])
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    oh.frame_make_images_raw(sc1.nf, uc["raw"])
+                cpu_raw_ms = 1e3 * (time.perf_counter() - t0) / 5
+            except Exception:
+                pass
             # the 8f rank-1 row on the host cores: traceNewCoarse is a serial loop in the reference (FullSystem.cpp:311-361)
             cpu_trace = None
             try:
@@ -460,7 +484,7 @@ def main():
                 t0 = time.perf_counter()
                 oh.optimize_immature(np.arange(sc1.nf), win["RTll"], win["tTll"], win["aff"], win["calib"], case["host"][okp], sub)
                 t_act = time.perf_counter() - t0
-                cpu_trace = {"trace_immature_ms": 1e3 * t_tr, "optimize_immature_ms": 1e3 * t_act, "cores": 1,
+                cpu_trace = {"make_images_raw_ms": cpu_raw_ms, "trace_immature_ms": 1e3 * t_tr, "optimize_immature_ms": 1e3 * t_act, "cores": 1,
                              "note": "same inputs as other_kernels; single thread (the reference's trace loop is serial, its activation loop threaded)"}
             except Exception as ex:
                 cpu_trace = {"error": str(ex)}

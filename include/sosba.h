@@ -165,6 +165,24 @@ int sosba_frame_make_images(sosba_t *h, int32_t slot, const float *color, const 
  * First/last row of dx,dy,absSquaredGrad are uninitialised in the reference; here they are 0. */
 int sosba_frame_get_level(sosba_t *h, int32_t slot, int32_t lvl, float *dI3, float *abs_sq_grad);
 
+/* ---- next row: the pre-pyramid image path ------------------------------------------------
+ * Undistort::undistort<T> (util/Undistort.cpp:361-458) with PhotometricUndistorter::processFrame<T> (:194-227) fused in
+ * front of makeImages: the caller hands over the RAW camera frame (8 or 16 bit), the device applies the inverse response
+ * G and the inverse vignette, resamples through the rectification map and builds the pyramid.
+ *   w_org, h_org   raw image size (Undistort::wOrg / hOrg); the output size is the handle's w x h
+ *   remapX/remapY  [w*h] Undistort::remapX / remapY (source position per output pixel, remapX < 0 = no source: output 0);
+ *                  both NULL = passthrough (requires w_org == w, h_org == h)
+ *   G              [g_depth] PhotometricUndistorter::G (g_depth 256 or 65536), NULL = no photometric calibration
+ *                  (the `!valid || setting_photometricCalibration == 0` branch: factor * raw)
+ *   vignette_inv   [w_org*h_org] PhotometricUndistorter::vignetteMapInv, NULL = setting_photometricCalibration < 2
+ * benchmark_varNoise / benchmark_varBlurNoise (dataset-corruption experiments, 0 by default) are not supported. */
+int sosba_undistort_set(sosba_t *h, int32_t w_org, int32_t h_org, const float *remapX, const float *remapY, const float *G, int32_t g_depth,
+                        const float *vignette_inv);
+/* raw: w_org*h_org pixels of raw_bits (8 or 16) bits; factor: the `factor` argument of undistort (used when G is NULL);
+ * B as in sosba_frame_make_images; image_out: optional [w*h] copy of the undistorted irradiance (ImageAndExposure::image),
+ * NULL to keep it on the device. */
+int sosba_frame_make_images_raw(sosba_t *h, int32_t slot, const void *raw, int32_t raw_bits, float factor, const float *B, float *image_out);
+
 /* ---- window / point / residual upload ------------------------------------------------------- */
 int sosba_window_set(sosba_t *h, const sosba_window *w);
 int sosba_points_set(sosba_t *h, const sosba_points *p);

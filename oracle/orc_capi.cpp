@@ -411,3 +411,36 @@ ORC_API int orc_optimize_immature(orc_handle *h, const sosba_activation_window *
   optimize_immature(h->o, win, pts, result, idepth, res_state);
   return SOSBA_OK;
 }
+
+// ---- next row: pre-pyramid image path ---------------------------------------------
+ORC_API int orc_undistort_set(orc_handle *h, int32_t w_org, int32_t h_org, const float *remapX, const float *remapY, const float *G, int32_t g_depth,
+                              const float *vignette_inv) {
+  Oracle &o = h->o;
+  const int w = o.wl[0], hh = o.hl[0];
+  if (w_org < 2 || h_org < 2 || (!remapX) != (!remapY) || (G && g_depth != 256 && g_depth != 65536) || (vignette_inv && !G)) return SOSBA_E_ARG;
+  if (!remapX && (w_org != w || h_org != hh)) return SOSBA_E_ARG;
+  Oracle::Undist &U = o.und;
+  U = Oracle::Undist();
+  U.wOrg = w_org; U.hOrg = h_org; U.passthrough = !remapX;
+  if (remapX) {
+    U.remapX.assign(remapX, remapX + (size_t)w * hh); U.remapY.assign(remapY, remapY + (size_t)w * hh);
+    for (size_t i = 0; i < U.remapX.size(); i++)   // the bilinear tap reads (x+1, y+1): the reference's map construction guarantees this margin
+      if (U.remapX[i] >= 0 && !(U.remapX[i] < w_org - 1 && U.remapY[i] >= 0 && U.remapY[i] < h_org - 1)) return SOSBA_E_ARG;
+  }
+  if (G) { U.haveG = true; U.gDepth = g_depth; U.G.assign(G, G + g_depth); }
+  if (vignette_inv) { U.haveV = true; U.vignetteInv.assign(vignette_inv, vignette_inv + (size_t)w_org * h_org); }
+  U.set = true;
+  return SOSBA_OK;
+}
+ORC_API int orc_frame_make_images_raw(orc_handle *h, int32_t slot, const void *raw, int32_t raw_bits, float factor, const float *B, float *image_out) {
+  Oracle &o = h->o;
+  if (!o.und.set) return SOSBA_E_STATE;
+  if (slot < 0 || slot >= (int)o.slots.size() || !raw || (raw_bits != 8 && raw_bits != 16)) return SOSBA_E_ARG;
+  if (raw_bits == 8 && o.und.haveG && o.und.gDepth < 256) return SOSBA_E_ARG;
+  if (raw_bits == 16 && o.und.haveG && o.und.gDepth != 65536) return SOSBA_E_ARG;
+  std::vector<float> img((size_t)o.wl[0] * o.hl[0]);
+  undistort_raw(o, raw, raw_bits, factor, img.data());
+  if (image_out) memcpy(image_out, img.data(), img.size() * sizeof(float));
+  make_images(o, slot, img.data(), B);
+  return SOSBA_OK;
+}

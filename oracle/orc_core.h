@@ -83,6 +83,13 @@ struct Oracle {
   float wM3G, hM3G;  // globalCalib.cpp:63-64
   std::vector<Pyramid> slots;
 
+  // pre-pyramid image path (orc_trace.cpp: undistort_raw)
+  struct Undist {
+    bool set = false, passthrough = true, haveG = false, haveV = false;
+    int wOrg = 0, hOrg = 0, gDepth = 0;
+    std::vector<float> remapX, remapY, G, vignetteInv;
+  } und;
+
   // window
   int nf = 0;
   std::vector<int> frame_slot;

@@ -367,4 +367,34 @@ void optimize_immature(Oracle &o, const sosba_activation_window *win, const sosb
   }
 }
 
+
+// ---- pre-pyramid image path: PhotometricUndistorter::processFrame (util/Undistort.cpp:194-227) + Undistort::undistort (:361-458)
+void undistort_raw(const Oracle &o, const void *raw, int raw_bits, float factor, float *out) {
+  const Oracle::Undist &U = o.und;
+  const int wOrg = U.wOrg, hOrg = U.hOrg, w = o.wl[0], h = o.hl[0];
+  std::vector<float> data((size_t)wOrg * hOrg);
+  const uint8_t *r8 = (const uint8_t *)raw;
+  const uint16_t *r16 = (const uint16_t *)raw;
+  for (int i = 0; i < wOrg * hOrg; i++) {
+    const int v = raw_bits == 8 ? r8[i] : r16[i];
+    if (!U.haveG) data[i] = factor * v;
+    else {
+      data[i] = U.G[v];
+      if (U.haveV) data[i] *= U.vignetteInv[i];
+    }
+  }
+  if (U.passthrough) { memcpy(out, data.data(), sizeof(float) * w * h); return; }
+  for (int idx = w * h - 1; idx >= 0; idx--) {
+    float xx = U.remapX[idx], yy = U.remapY[idx];
+    if (xx < 0) out[idx] = 0;
+    else {
+      int xxi = xx, yyi = yy;
+      xx -= xxi; yy -= yyi;
+      float xxyy = xx * yy;
+      const float *src = data.data() + xxi + yyi * wOrg;
+      out[idx] = xxyy * src[1 + wOrg] + (yy - xxyy) * src[wOrg] + (xx - xxyy) * src[1] + (1 - xx - yy + xxyy) * src[0];
+    }
+  }
+}
+
 }  // namespace orc

@@ -144,7 +144,7 @@ class Lib:
                   "accumulate", "points_get_acc", "solve_system", "resubstitute", "marginalize_points",
                   "tracker_make_k", "tracker_set_ref", "tracker_calc_res_pose", "tracker_calc_gs_pose",
                   "scale_set_stereo", "scale_calc_res", "scale_calc_gs", "optimize", "ba_upload", "ba_iterate",
-                  "ba_download", "ba_optimize", "pyr_levels", "immature_init", "trace_immature", "optimize_immature"):
+                  "ba_download", "ba_optimize", "pyr_levels", "immature_init", "trace_immature", "optimize_immature", "undistort_set", "frame_make_images_raw"):
             self.f(n).restype = C.c_int
         self.f("destroy").restype = None
         if self.has("launch_count"):
@@ -401,6 +401,24 @@ class Handle:
     def tracker_set_ref(self, lvl, u, v, idepth, color):
         u, v, idepth, color = _f32(u), _f32(v), _f32(idepth), _f32(color)
         self._ck(self.lib.f("tracker_set_ref")(self.h, C.c_int32(lvl), C.c_int32(u.size), _p(u, f32p), _p(v, f32p), _p(idepth, f32p), _p(color, f32p)), "tracker_set_ref")
+
+    # ---- pre-pyramid image path (util/Undistort.cpp:194-227, 361-458)
+    def undistort_set(self, w_org, h_org, remapX=None, remapY=None, G=None, vignette_inv=None):
+        rx = None if remapX is None else _f32(remapX)
+        ry = None if remapY is None else _f32(remapY)
+        g = None if G is None else _f32(G)
+        vi = None if vignette_inv is None else _f32(vignette_inv)
+        self._ck(self.lib.f("undistort_set")(self.h, C.c_int32(w_org), C.c_int32(h_org), _p(rx, f32p), _p(ry, f32p), _p(g, f32p),
+                                             C.c_int32(0 if g is None else g.size), _p(vi, f32p)), "undistort_set")
+
+    def frame_make_images_raw(self, slot, raw, factor=1.0, B=None, want_image=False):
+        raw = np.ascontiguousarray(raw)
+        assert raw.dtype in (np.uint8, np.uint16)
+        b = None if B is None else _f32(B)
+        out = np.zeros((self.cfg.h, self.cfg.w), np.float32) if want_image else None
+        self._ck(self.lib.f("frame_make_images_raw")(self.h, C.c_int32(slot), raw.ctypes.data_as(C.c_void_p), C.c_int32(8 * raw.dtype.itemsize),
+                                                     C.c_float(factor), _p(b, f32p), _p(out, f32p)), "frame_make_images_raw")
+        return out
 
     # ---- immature points (ImmaturePoint.cpp:28-60, 70-415; FullSystem.cpp:311-361)
     def immature_init(self, host_slot, u, v):

@@ -617,6 +617,40 @@ __global__ void __launch_bounds__(256) k_track_res(TrackResArgs a) {
 
 }  // namespace
 
+// ---- pre-pyramid image path ---------------------------------------------------------------------
+//   PhotometricUndistorter::processFrame<T>   src/util/Undistort.cpp:194-227   (G[raw] * vignetteMapInv, or factor * raw)
+//   Undistort::undistort<T>                   src/util/Undistort.cpp:361-458   (bilinear resampling through remapX / remapY)
+// One thread per output pixel; the photometric correction is applied to the four source texels on the fly (raw bytes +
+// the 1 KB response table instead of a float intermediate image), in the reference's float expression order.
+template <class T> __device__ __forceinline__ float photometric(const UndistortArgs &a, const T *raw, int i) {
+  const int v = raw[i];
+  if (!a.G) return a.factor * v;
+  float d = __ldg(a.G + v);
+  if (a.vig) d *= __ldg(a.vig + i);
+  return d;
+}
+template <class T> __global__ void __launch_bounds__(256) k_undistort(UndistortArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.w * a.h) return;
+  const T *raw = (const T *)a.raw;
+  if (!a.remap) { a.out[idx] = photometric(a, raw, idx); return; }
+  const float2 r = __ldg(a.remap + idx);
+  float xx = r.x, yy = r.y;
+  if (xx < 0) { a.out[idx] = 0; return; }
+  const int xxi = xx, yyi = yy;
+  xx -= xxi; yy -= yyi;
+  const float xxyy = xx * yy;
+  const int s = xxi + yyi * a.wOrg;
+  a.out[idx] = xxyy * photometric(a, raw, s + 1 + a.wOrg) + (yy - xxyy) * photometric(a, raw, s + a.wOrg) + (xx - xxyy) * photometric(a, raw, s + 1) +
+               (1 - xx - yy + xxyy) * photometric(a, raw, s);
+}
+void launch_undistort(sosba *h, const UndistortArgs &a) {
+  const int n = a.w * a.h;
+  if (a.bits == 8) k_undistort<uint8_t><<<(n + 255) / 256, 256, 0, h->stream>>>(a);
+  else k_undistort<uint16_t><<<(n + 255) / 256, 256, 0, h->stream>>>(a);
+  h->launches++;
+}
+
 // ------------------------------------------------------------------------------------------------
 void launch_make_images(sosba *h, int slot, const float *d_color, const float *d_B) {
   for (int l = 0; l < h->levels; l++) {

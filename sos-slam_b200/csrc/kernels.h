@@ -213,6 +213,17 @@ struct ResubArgs {
 void launch_resubstitute(sosba *h, const ResubArgs &a);
 void launch_step(sosba *h, const ResubArgs &ra, const StepArgs &sa);   // resubstitute + frame step, concurrently, one launch
 
+// ---- pre-pyramid image path (k_exact.cu) ----------------------------------------------------------
+struct UndistortArgs {
+  int w, h, wOrg, hOrg, bits;     // bits: 8 or 16
+  const void *raw;                // wOrg*hOrg raw pixels
+  const float2 *remap;            // (remapX, remapY) per output pixel, or nullptr (passthrough)
+  const float *G, *vig;           // inverse response / inverse vignette, or nullptr
+  float factor;
+  float *out;                     // w*h irradiance
+};
+void launch_undistort(sosba *h, const UndistortArgs &a);
+
 // ---- k_trace.cu ---------------------------------------------------------------------------------
 struct TraceArgs {
   int n, w, h;

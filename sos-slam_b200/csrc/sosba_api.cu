@@ -52,6 +52,12 @@ struct BA {
 struct HostSide {
   float *d_imm = nullptr;   // immature-point arena (k_trace.cu): 30 floats + 1 status byte per point, grown on demand
   size_t imm_cap = 0;
+  // pre-pyramid image path (sosba_undistort_set)
+  bool und_set = false;
+  int und_wOrg = 0, und_hOrg = 0, und_gDepth = 0;
+  float2 *d_remap = nullptr;
+  float *d_G = nullptr, *d_vig = nullptr;
+  unsigned char *d_raw = nullptr;
   float *d_act = nullptr;       // activation outputs: [idepth n floats][result n bytes][res_state n*nf bytes]
   size_t act_cap = 0;
   float *d_act_win = nullptr;   // PRE_RTll / PRE_tTll / PRE_aff_mode per frame pair
@@ -323,6 +329,69 @@ API int sosba_frame_make_images(sosba_t *h, int32_t slot, const float *color, co
   launch_make_images(h, slot, h->d_stage, B ? h->d_B : nullptr);
   h->slot_valid[slot] = 1;
   SOSBA_CUDA(cudaGetLastError());
+  return SOSBA_OK;
+}
+
+// ---- 8f rank 2: raw frame -> photometric + geometric undistortion -> pyramid ----------------------
+API int sosba_undistort_set(sosba_t *h, int32_t w_org, int32_t h_org, const float *remapX, const float *remapY, const float *G, int32_t g_depth,
+                            const float *vignette_inv) {
+  CHECK_H(h);
+  const int w = h->cfg.w, hh = h->cfg.h;
+  if (w_org < 2 || h_org < 2 || (!remapX) != (!remapY) || (G && g_depth != 256 && g_depth != 65536) || (vignette_inv && !G)) {
+    sosba_set_error("undistort_set: bad arguments");
+    return SOSBA_E_ARG;
+  }
+  if (!remapX && (w_org != w || h_org != hh)) { sosba_set_error("passthrough needs w_org x h_org == w x h"); return SOSBA_E_ARG; }
+  HostSide *hs = HS(h);
+  int rc;
+  if ((rc = sync(h))) return rc;
+  dfree(h, hs->d_remap); dfree(h, hs->d_G); dfree(h, hs->d_vig); dfree(h, hs->d_raw);
+  hs->und_set = false;
+  const size_t n = (size_t)w * hh, no = (size_t)w_org * h_org;
+  if (remapX) {
+    std::vector<float2> rm(n);
+    for (size_t i = 0; i < n; i++) {
+      // the bilinear tap reads (x+1, y+1): the reference's map construction guarantees this margin (Undistort.cpp:862-884)
+      if (remapX[i] >= 0 && !(remapX[i] < w_org - 1 && remapY[i] >= 0 && remapY[i] < h_org - 1)) {
+        sosba_set_error("remap entry %zu (%g, %g) outside the raw image", i, remapX[i], remapY[i]);
+        return SOSBA_E_ARG;
+      }
+      rm[i] = make_float2(remapX[i], remapY[i]);
+    }
+    DALLOC(h, hs->d_remap, n);
+    SOSBA_CUDA(cudaMemcpyAsync(hs->d_remap, rm.data(), n * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = sync(h))) return rc;
+  }
+  if (G) { DALLOC(h, hs->d_G, g_depth); SOSBA_CUDA(cudaMemcpyAsync(hs->d_G, G, g_depth * sizeof(float), cudaMemcpyHostToDevice, h->stream)); }
+  if (vignette_inv) { DALLOC(h, hs->d_vig, no); SOSBA_CUDA(cudaMemcpyAsync(hs->d_vig, vignette_inv, no * sizeof(float), cudaMemcpyHostToDevice, h->stream)); }
+  DALLOC(h, hs->d_raw, no * 2);
+  hs->und_wOrg = w_org; hs->und_hOrg = h_org; hs->und_gDepth = G ? g_depth : 0;
+  if ((rc = sync(h))) return rc;
+  hs->und_set = true;
+  return SOSBA_OK;
+}
+
+API int sosba_frame_make_images_raw(sosba_t *h, int32_t slot, const void *raw, int32_t raw_bits, float factor, const float *B, float *image_out) {
+  CHECK_H(h);
+  HostSide *hs = HS(h);
+  if (!hs->und_set) { sosba_set_error("undistort_set first"); return SOSBA_E_STATE; }
+  if (slot < 0 || slot >= (int)h->slot_img.size() || !raw || (raw_bits != 8 && raw_bits != 16)) { sosba_set_error("bad slot / raw"); return SOSBA_E_ARG; }
+  if (hs->und_gDepth && raw_bits == 16 && hs->und_gDepth != 65536) { sosba_set_error("16-bit frame with a %d-entry response", hs->und_gDepth); return SOSBA_E_ARG; }
+  const size_t no = (size_t)hs->und_wOrg * hs->und_hOrg, n = (size_t)h->cfg.w * h->cfg.h;
+  int rc;
+  if ((rc = up_bytes(h, hs->d_raw, raw, no * (raw_bits / 8)))) return rc;
+  if (B && (rc = up(h, h->d_B, B, 256))) return rc;
+  UndistortArgs a;
+  a.w = h->cfg.w; a.h = h->cfg.h; a.wOrg = hs->und_wOrg; a.hOrg = hs->und_hOrg; a.bits = raw_bits;
+  a.raw = hs->d_raw; a.remap = hs->d_remap; a.G = hs->d_G; a.vig = hs->d_vig; a.factor = factor; a.out = h->d_stage;
+  launch_undistort(h, a);
+  launch_make_images(h, slot, h->d_stage, B ? h->d_B : nullptr);
+  h->slot_valid[slot] = 1;
+  SOSBA_CUDA(cudaGetLastError());
+  if (image_out) {
+    if ((rc = down(h, image_out, (const float *)h->d_stage, n))) return rc;
+    return sync(h);
+  }
   return SOSBA_OK;
 }
 

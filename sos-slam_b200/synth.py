@@ -336,3 +336,34 @@ def activation_case(scene: Scene):
             a = np.exp(scene.aff_true[tgt, 0] - scene.aff_true[hst, 0]) * scene.ab_exposure[tgt] / scene.ab_exposure[hst]
             aff[hst, tgt] = (a, scene.aff_true[tgt, 1] - a * scene.aff_true[hst, 1])
     return dict(RTll=RTll, tTll=tTll, aff=aff, calib=np.asarray(scene.K, np.float32))
+
+
+def undistort_case(w, h, w_org=None, h_org=None, seed=3, bits=8, k1=-0.28, k2=0.07):
+    """A synthetic camera for the pre-pyramid image path (util/Undistort.cpp): raw frame (w_org x h_org, `bits` bits), a
+    rectification map built like Undistort's (radial-tangential model, entries without a source set to -1, :854-884), an
+    inverse response G and an inverse vignette.  -> dict(raw, remapX, remapY, G, vignette_inv, w_org, h_org)."""
+    rng = np.random.default_rng(seed)
+    w_org = w_org or w + 112
+    h_org = h_org or h + 32
+    ys, xs = np.mgrid[0:h_org, 0:w_org].astype(np.float64)
+    tex = 110 + 70 * np.sin(xs * 0.045) * np.cos(ys * 0.06) + 35 * np.sin((xs + 2 * ys) * 0.013) + rng.normal(0, 6, (h_org, w_org))
+    top = (1 << bits) - 1
+    raw = np.clip(tex * (top / 255.0), 0, top).astype(np.uint8 if bits == 8 else np.uint16)
+    depth = 256 if bits == 8 else 65536
+    G = (255.0 * (np.arange(depth) / (depth - 1.0)) ** 1.18).astype(np.float32)          # inverse response, G[0] = 0, G[top] = 255
+    r2 = ((xs - w_org / 2) ** 2 + (ys - h_org / 2) ** 2) / (w_org / 2) ** 2
+    vignette_inv = (1.0 / (1.0 - 0.35 * r2 + 0.05 * r2 * r2)).astype(np.float32)
+    # output pinhole K chosen so that the corners fall outside the raw image (exercises the -1 entries)
+    fx_o, fy_o, cx_o, cy_o = 0.62 * w_org, 0.62 * w_org, w_org / 2 - 0.5, h_org / 2 - 0.5
+    fx, fy, cx, cy = 0.50 * w, 0.50 * w, w / 2 - 0.5, h / 2 - 0.5
+    yo, xo = np.mgrid[0:h, 0:w].astype(np.float32)
+    xn = (xo - np.float32(cx)) / np.float32(fx)
+    yn = (yo - np.float32(cy)) / np.float32(fy)
+    rr = xn * xn + yn * yn
+    fac = 1 + np.float32(k1) * rr + np.float32(k2) * rr * rr
+    ix = (np.float32(fx_o) * (xn * fac) + np.float32(cx_o)).astype(np.float32)
+    iy = (np.float32(fy_o) * (yn * fac) + np.float32(cy_o)).astype(np.float32)
+    ok = (ix > 0) & (iy > 0) & (ix < w_org - 1) & (iy < h_org - 1)
+    remapX = np.where(ok, ix, np.float32(-1)).astype(np.float32)
+    remapY = np.where(ok, iy, np.float32(-1)).astype(np.float32)
+    return dict(raw=raw, remapX=remapX, remapY=remapY, G=G, vignette_inv=vignette_inv, w_org=w_org, h_org=h_org)

@@ -612,3 +612,25 @@ def optimize_immature_ref(dIs, p, host, RTll, tTll, aff, calib, min_obs=1):
     if not np.isfinite(cur) or int(np.sum(st == 0)) < min_obs or not np.isfinite(p["energy_th"]):
         return ACT_DELETE, cur, st
     return ACT_ACTIVATED, cur, st
+
+
+# ---- pre-pyramid image path ---------------------------------------------------------
+def undistort_ref(raw, remapX, remapY, G=None, vignette_inv=None, factor=1.0):
+    """PhotometricUndistorter::processFrame (util/Undistort.cpp:194-227) + Undistort::undistort (:361-458), float32."""
+    h_org, w_org = raw.shape
+    if G is None:
+        data = (F(factor) * raw.astype(F)).astype(F)
+    else:
+        data = np.asarray(G, F)[raw.astype(np.int64)]
+        if vignette_inv is not None:
+            data = (data * np.asarray(vignette_inv, F).reshape(h_org, w_org)).astype(F)
+    if remapX is None:
+        return data
+    xx = np.asarray(remapX, F); yy = np.asarray(remapY, F)
+    ok = xx >= 0
+    xs = np.where(ok, xx, F(0)); ys = np.where(ok, yy, F(0))
+    xi = xs.astype(np.int32); yi = ys.astype(np.int32)
+    fx = xs - xi.astype(F); fy = ys - yi.astype(F)
+    fxy = fx * fy
+    out = fxy * data[yi + 1, xi + 1] + (fy - fxy) * data[yi + 1, xi] + (fx - fxy) * data[yi, xi + 1] + (F(1) - fx - fy + fxy) * data[yi, xi]
+    return np.where(ok, out, F(0)).astype(F)

@@ -484,3 +484,38 @@ def test_optimize_immature_vs_numpy(orc):
     assert np_ref.ACT_ACTIVATED in seen and len(seen) >= 2, seen
     assert (result == np_ref.ACT_ACTIVATED).sum() > hs.size // 4
     h.close()
+
+
+# ---- next row: pre-pyramid image path ---------------------------------------------
+@pytest.mark.parametrize("mode", ["full8", "full16", "nocalib", "passthrough"])
+def test_undistort_vs_numpy(orc, mode):
+    """Undistort::undistort + PhotometricUndistorter::processFrame (util/Undistort.cpp:194-227, 361-458): the undistorted
+    irradiance image bit for bit against numpy, and the pyramid built from it equals makeImages of that image."""
+    from sos_slam_b200 import binding, synth
+    w, h = 320, 240
+    bits = 16 if mode == "full16" else 8
+    c = synth.undistort_case(w, h, bits=bits) if mode != "passthrough" else synth.undistort_case(w, h, w_org=w, h_org=h)
+    cfg = orc.config_default(w, h)
+    cfg.max_frames = 2
+    hd = binding.Handle(orc, cfg)
+    with pytest.raises(binding.SosbaError):
+        hd.frame_make_images_raw(0, c["raw"])               # no undistorter configured yet
+    G = None if mode == "nocalib" else c["G"]
+    V = None if mode == "nocalib" else c["vignette_inv"]
+    rx, ry = (None, None) if mode == "passthrough" else (c["remapX"], c["remapY"])
+    hd.undistort_set(c["w_org"], c["h_org"], rx, ry, G, V)
+    img = hd.frame_make_images_raw(0, c["raw"], factor=0.9, want_image=True)
+    ref = np_ref.undistort_ref(c["raw"], rx, ry, G, V, factor=0.9)
+    assert np.array_equal(img, ref)
+    if mode != "passthrough":
+        assert (c["remapX"] < 0).sum() > 100 and np.all(img[c["remapX"] < 0] == 0)
+    hd.frame_make_images(1, ref)
+    for lvl in range(hd.levels):
+        a, b = hd.frame_get_level(0, lvl), hd.frame_get_level(1, lvl)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    bad = c["remapX"].copy()
+    bad[5, 5] = c["w_org"] - 0.5                             # would read one texel past the raw row
+    if mode == "full8":
+        with pytest.raises(binding.SosbaError):
+            hd.undistort_set(c["w_org"], c["h_org"], bad, c["remapY"], G, V)
+    hd.close()

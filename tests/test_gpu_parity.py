@@ -340,3 +340,31 @@ def test_immature_edge_cases(gpu, orc):
     for k in pts:   # an OOB point is returned untouched (ImmaturePoint.cpp:74-75)
         assert np.array_equal(pts[k][0], before[k][0], equal_nan=True), k
     hg.close()
+
+
+# ---- next row: pre-pyramid image path -----------------------------------------
+@pytest.mark.parametrize("mode", ["full8", "full16", "nocalib", "passthrough"])
+@pytest.mark.parametrize("shape", [(640, 480), (1232, 368)])
+def test_undistort_raw_bit_exact(gpu, orc, mode, shape):
+    """Raw frame -> PhotometricUndistorter::processFrame + Undistort::undistort (util/Undistort.cpp:194-227, 361-458) ->
+    makeImages: the undistorted irradiance and every pyramid level identical bit for bit to the oracle's."""
+    from sos_slam_b200 import binding, synth
+    w, h = shape
+    bits = 16 if mode == "full16" else 8
+    c = synth.undistort_case(w, h, bits=bits) if mode != "passthrough" else synth.undistort_case(w, h, w_org=w, h_org=h)
+    G = None if mode == "nocalib" else c["G"]
+    V = None if mode == "nocalib" else c["vignette_inv"]
+    rx, ry = (None, None) if mode == "passthrough" else (c["remapX"], c["remapY"])
+    B = (np.linspace(0, 255, 256) ** 1.01).astype(np.float32)
+    outs = []
+    for lib in (gpu, orc):
+        cfg = lib.config_default(w, h)
+        cfg.max_frames = 1
+        hd = binding.Handle(lib, cfg)
+        hd.undistort_set(c["w_org"], c["h_org"], rx, ry, G, V)
+        img = hd.frame_make_images_raw(0, c["raw"], factor=0.9, B=B, want_image=True)
+        outs.append((img, [hd.frame_get_level(0, l) for l in range(hd.levels)]))
+        hd.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])

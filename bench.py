@@ -317,34 +317,51 @@ def main():
     frames0 = bytes(ctypes.string_at(ctypes.addressof(kn[0]), ctypes.sizeof(kn[0])))
     calib0 = list(Pn.calib_value)
 
-    def e2e_step():
+    raw8 = np.clip(np.rint(sc.images[-1]), 0, 255).astype(np.uint8)      # the camera frame as it arrives (8f rank 2 input)
+
+    def e2e_step(raw=False):
         ctypes.memmove(ctypes.addressof(kn[0]), frames0, len(frames0))
         for i in range(4):
             Pn.calib_value[i] = calib0[i]
-        h.frame_make_images(sc.nf - 1, sc.images[-1])
+        if raw:
+            h.frame_make_images_raw(sc.nf - 1, raw8)
+        else:
+            h.frame_make_images(sc.nf - 1, sc.images[-1])
         return h.optimize(Pn, ITERS)
 
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    e2e_ms, e2e_res = 0.0, 0
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        tw = time.perf_counter()
-        a.record(stream)
-        o = e2e_step()
-        b.record(stream)
-        torch.cuda.synchronize()
-        e2e_ms += max(a.elapsed_time(b), 1e3 * (time.perf_counter() - tw))   # device timeline and host wall agree; take the larger
-        e2e_res += o["reserved0"] * 8 * (o["iterations"] + 2)
-    t = torch.tensor([e2e_ms, float(e2e_res)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        e2e_ms, e2e_res = float(tmax[0]), float(tsum[1])
+    def e2e_loop(raw):
+        for _ in range(3):
+            e2e_step(raw)
+        barrier()
+        ms, nres = 0.0, 0
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            tw = time.perf_counter()
+            a.record(stream)
+            o = e2e_step(raw)
+            b.record(stream)
+            torch.cuda.synchronize()
+            ms += max(a.elapsed_time(b), 1e3 * (time.perf_counter() - tw))   # device timeline and host wall agree; take the larger
+            nres += o["reserved0"] * 8 * (o["iterations"] + 2)
+        t = torch.tensor([ms, float(nres)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            return float(tmax[0]), float(tsum[1])
+        return ms, float(nres)
+
+    e2e_ms, e2e_res = e2e_loop(False)
     e2e_value = e2e_res / (e2e_ms * 1e-3)
+    # the same step fed with the 8-bit camera frame (passthrough rectification, no photometric calibration, factor 1):
+    # reported next to the headline e2e, which keeps the float irradiance image of FrameHessian::makeImages as its input
+    h.undistort_set(sc.w, sc.h)
+    raw_ms, raw_res = e2e_loop(True)
+    e2e_raw = {"value": raw_res / (raw_ms * 1e-3), "unit": UNIT, "ms_per_step": raw_ms / args.steps,
+               "h2d_bytes_per_step": int(h2d - sc.images[-1].nbytes + raw8.nbytes),
+               "note": "newest keyframe enters as the 8-bit camera frame (sosba_frame_make_images_raw) instead of the float irradiance image"}
+    h.frame_make_images(sc.nf - 1, sc.images[-1])
 
     # ---- the other kernels of the path: per-call time, host buffers in ------------
     other = None
@@ -502,7 +519,7 @@ def main():
                            "l2": "flushed between steps (256 MiB fill); per-step CUDA events on the launch stream", "parallelism": f"points/{world}"},
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                                           "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "other_kernels": other,
+                "e2e_raw_frame": e2e_raw, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "other_kernels": other,
                 "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps, "final_rmse": out["rmse"]}
         print(json.dumps(line), flush=True)
     h.close()

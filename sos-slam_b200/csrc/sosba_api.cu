@@ -58,6 +58,9 @@ struct HostSide {
   float2 *d_remap = nullptr;
   float *d_G = nullptr, *d_vig = nullptr;
   unsigned char *d_raw = nullptr;
+  std::vector<char> big_stage;        // pageable staging for uploads larger than half the pinned ring
+  float *p_arena = nullptr;           // uploaded members of the points (carve_points)
+  unsigned char *r_arena = nullptr;   // ids / energies / flags of the residuals (carve_residuals)
   float *d_act = nullptr;       // activation outputs: [idepth n floats][result n bytes][res_state n*nf bytes]
   size_t act_cap = 0;
   float *d_act_win = nullptr;   // PRE_RTll / PRE_tTll / PRE_aff_mode per frame pair
@@ -133,6 +136,18 @@ static int up_bytes(sosba *h, void *dst, const void *src, size_t bytes) {
   }
   memcpy(hs->stage + hs->stage_off, src, bytes);
   SOSBA_CUDA(cudaMemcpyAsync(dst, hs->stage + hs->stage_off, bytes, cudaMemcpyHostToDevice, h->stream));
+  hs->stage_off += (bytes + 255) & ~(size_t)255;
+  return SOSBA_OK;
+}
+// A block of the pinned staging ring, valid until the stream is synchronised twice (the ring only wraps behind a sync).
+static int stage_reserve(sosba *h, size_t bytes, char **p) {
+  HostSide *hs = HS(h);
+  if (!hs->stage || bytes > hs->stage_cap) { sosba_set_error("staging block of %zu bytes", bytes); return SOSBA_E_ARG; }
+  if (hs->stage_off + bytes > hs->stage_cap) {
+    SOSBA_CUDA(cudaStreamSynchronize(h->stream));
+    hs->stage_off = 0;
+  }
+  *p = hs->stage + hs->stage_off;
   hs->stage_off += (bytes + 255) & ~(size_t)255;
   return SOSBA_OK;
 }
@@ -509,12 +524,10 @@ API int sosba_window_update(sosba_t *h, const sosba_window *w) { CHECK_H(h); if 
 static int ensure_points(sosba *h, int P) {
   if (P <= h->P_alloc) return SOSBA_OK;
   HostSide *hs = HS(h);
-  float **fl[] = {&h->p_u, &h->p_v, &h->p_idepth, &h->p_idepth_zero, &h->p_priorF, &h->p_deltaF};
-  for (auto p : fl) dfree(h, *p);
-  dfree(h, h->p_color); dfree(h, h->p_weights); dfree(h, h->p_host); dfree(h, hs->p_zero_arena);
-  const size_t n = ((size_t)P + (size_t)P / 4 + 64 + 3) & ~(size_t)3;
-  for (auto p : fl) DALLOC(h, *p, n);
-  DALLOC(h, h->p_color, n * 8); DALLOC(h, h->p_weights, n * 8); DALLOC(h, h->p_host, n);
+  dfree(h, hs->p_arena); dfree(h, hs->p_zero_arena);
+  const size_t n = ((size_t)P + (size_t)P / 4 + 64 + 63) & ~(size_t)63;
+  // the uploaded members of the points live in ONE arena in the order points_set stages them (carve_points): one H2D
+  DALLOC(h, hs->p_arena, 23 * n);
   // everything a new point set starts from zero: one arena, one memset
   hs->p_zero_words = 10 * n + 8 * n + n + (n + 4);
   DALLOC(h, hs->p_zero_arena, hs->p_zero_words);
@@ -529,6 +542,13 @@ static int ensure_points(sosba *h, int P) {
   return SOSBA_OK;
 }
 
+// arena of N = round_up(n, 64) points: [u|v|idepth|idepth_zero|priorF|deltaF] float, color[8], weights[8], host int
+static void carve_points(sosba *h, size_t N) {
+  float *f = HS(h)->p_arena;
+  h->p_u = f; h->p_v = f + N; h->p_idepth = f + 2 * N; h->p_idepth_zero = f + 3 * N; h->p_priorF = f + 4 * N; h->p_deltaF = f + 5 * N;
+  h->p_color = f + 6 * N; h->p_weights = f + 14 * N; h->p_host = (int *)(f + 22 * N);
+}
+
 API int sosba_points_set(sosba_t *h, const sosba_points *p) {
   CHECK_H(h);
   if (!p || p->n < 0) return SOSBA_E_ARG;
@@ -538,12 +558,22 @@ API int sosba_points_set(sosba_t *h, const sosba_points *p) {
   h->P = p->n;
   HostSide *hs = HS(h);
   hs->p_host.assign(p->host, p->host + n);
-  if ((rc = up(h, h->p_u, p->u, n)) || (rc = up(h, h->p_v, p->v, n)) || (rc = up(h, h->p_idepth, p->idepth, n)) ||
-      (rc = up(h, h->p_idepth_zero, p->idepth_zero, n)) || (rc = up(h, h->p_color, p->color, n * 8)) ||
-      (rc = up(h, h->p_weights, p->weights, n * 8)) || (rc = up(h, h->p_host, p->host, n)))
-    return rc;
-  if (p->priorF) { if ((rc = up(h, h->p_priorF, p->priorF, n))) return rc; } else cudaMemsetAsync(h->p_priorF, 0, n * 4, h->stream);
-  if (p->deltaF) { if ((rc = up(h, h->p_deltaF, p->deltaF, n))) return rc; } else cudaMemsetAsync(h->p_deltaF, 0, n * 4, h->stream);
+  {
+    const size_t N = (n + 63) & ~(size_t)63, bytes = 23 * N * sizeof(float);
+    carve_points(h, N);
+    if (n > 0) {
+      char *blk = nullptr;
+      if (bytes <= hs->stage_cap / 2) { if ((rc = stage_reserve(h, bytes, &blk))) return rc; }
+      else { hs->big_stage.resize(bytes); blk = hs->big_stage.data(); }
+      float *sf = (float *)blk;
+      memcpy(sf, p->u, 4 * n); memcpy(sf + N, p->v, 4 * n); memcpy(sf + 2 * N, p->idepth, 4 * n); memcpy(sf + 3 * N, p->idepth_zero, 4 * n);
+      if (p->priorF) memcpy(sf + 4 * N, p->priorF, 4 * n); else memset(sf + 4 * N, 0, 4 * n);
+      if (p->deltaF) memcpy(sf + 5 * N, p->deltaF, 4 * n); else memset(sf + 5 * N, 0, 4 * n);
+      memcpy(sf + 6 * N, p->color, 32 * n); memcpy(sf + 14 * N, p->weights, 32 * n); memcpy(sf + 22 * N, p->host, 4 * n);
+      SOSBA_CUDA(cudaMemcpyAsync(hs->p_arena, blk, bytes, cudaMemcpyHostToDevice, h->stream));
+      if (blk == hs->big_stage.data()) { if ((rc = sync(h))) return rc; }
+    }
+  }
   cudaMemsetAsync(hs->p_zero_arena, 0, hs->p_zero_words * 4, h->stream);   // accumulators, steps, CSR
   hs->res_begin.assign(n + 1, 0);
   h->R = 0;
@@ -561,21 +591,26 @@ API int sosba_points_update(sosba_t *h, const float *idepth, const float *idepth
 
 static int ensure_residuals(sosba *h, int R) {
   if (R <= h->R_alloc) return SOSBA_OK;
-  int **il[] = {&h->r_point, &h->r_target, &h->r_host, &h->r_by_block};
-  uint8_t **ul[] = {&h->r_state, &h->r_new_state, &h->r_is_lin, &h->r_is_active, &h->r_is_new, &h->r_sel, &h->r_dropped};
-  float **fl[] = {&h->r_energy, &h->r_new_energy, &h->r_new_energy_wo};
-  for (auto p : il) dfree(h, *p);
-  for (auto p : ul) dfree(h, *p);
-  for (auto p : fl) dfree(h, *p);
+  HostSide *hs = HS(h);
+  dfree(h, hs->r_arena); dfree(h, h->r_by_block);
   dfree(h, h->r_J[0]); dfree(h, h->r_J[1]); dfree(h, h->r_rec); dfree(h, h->r_rtz); dfree(h, h->r_proj); dfree(h, h->r_center); dfree(h, h->d_newE);
-  const size_t n = (size_t)R + (size_t)R / 4 + 64;
-  for (auto p : il) DALLOC(h, *p, n);
-  for (auto p : ul) DALLOC(h, *p, n);
-  for (auto p : fl) DALLOC(h, *p, n);
+  const size_t n = ((size_t)R + (size_t)R / 4 + 64 + 63) & ~(size_t)63;
+  // ids, energies and flags of the residuals live in ONE arena in the order residuals_set stages them: one H2D per upload
+  DALLOC(h, hs->r_arena, 31 * n);
+  DALLOC(h, h->r_by_block, n);
   DALLOC(h, h->r_J[0], n * SOSBA_JREC); DALLOC(h, h->r_J[1], n * SOSBA_JREC); DALLOC(h, h->r_rec, n * SOSBA_CREC);
   DALLOC(h, h->r_rtz, n * 8); DALLOC(h, h->r_proj, n * 16); DALLOC(h, h->r_center, n * 3); DALLOC(h, h->d_newE, n);
   h->R_alloc = (int)n;
   return SOSBA_OK;
+}
+// arena of N = round_up(n, 64) residuals: [point|target|host] int, [energy|new_energy|new_energy_wo] float, then 7 byte planes
+static void carve_residuals(sosba *h, size_t N) {
+  unsigned char *b = HS(h)->r_arena;
+  h->r_point = (int *)b; h->r_target = (int *)(b + 4 * N); h->r_host = (int *)(b + 8 * N);
+  h->r_energy = (float *)(b + 12 * N); h->r_new_energy = (float *)(b + 16 * N); h->r_new_energy_wo = (float *)(b + 20 * N);
+  unsigned char *u = b + 24 * N;
+  h->r_state = u; h->r_is_lin = u + N; h->r_is_active = u + 2 * N; h->r_is_new = u + 3 * N; h->r_new_state = u + 4 * N; h->r_sel = u + 5 * N;
+  h->r_dropped = u + 6 * N;
 }
 
 static void clear_gathered_energies(sosba *h);
@@ -642,9 +677,26 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
     clear_gathered_energies(h);
   }
   hs->n_lin = 0;
-  if ((rc = up(h, h->r_point, r->point, n)) || (rc = up(h, h->r_target, r->target, n)) || (rc = up(h, h->r_host, host.data(), n)) ||
-      (rc = up(h, h->p_res_begin, hs->res_begin.data(), P + 1)))
-    return rc;
+  if (n > 0) {
+    const size_t N = ((size_t)n + 63) & ~(size_t)63, bytes = 31 * N;
+    carve_residuals(h, N);
+    char *blk = nullptr;
+    if (bytes <= hs->stage_cap / 2) { if ((rc = stage_reserve(h, bytes, &blk))) return rc; }
+    else { hs->big_stage.resize(bytes); blk = hs->big_stage.data(); }
+    int *si = (int *)blk;
+    float *sf = (float *)(blk + 12 * N);
+    unsigned char *su = (unsigned char *)blk + 24 * N;
+    memcpy(si, r->point, 4 * (size_t)n); memcpy(si + N, r->target, 4 * (size_t)n); memcpy(si + 2 * N, host.data(), 4 * (size_t)n);
+    if (r->state_energy) { memcpy(sf, r->state_energy, 4 * (size_t)n); memcpy(sf + N, r->state_energy, 4 * (size_t)n); }
+    else memset(sf, 0, 8 * N);
+    for (int i = 0; i < n; i++) sf[2 * N + i] = -1.f;   // state_NewEnergyWithOutlier = -1 until linearised (Residuals.cpp:78)
+    auto flag = [&](unsigned char *dst, const uint8_t *src, uint8_t dflt) { if (src) memcpy(dst, src, n); else memset(dst, dflt, n); };
+    flag(su, r->state, SOSBA_RES_IN); flag(su + N, r->is_linearized, 0); flag(su + 2 * N, r->is_active, 0); flag(su + 3 * N, r->is_new, 1);
+    memset(su + 4 * N, SOSBA_RES_OUTLIER, N); memset(su + 5 * N, 0, 2 * N);
+    SOSBA_CUDA(cudaMemcpyAsync(hs->r_arena, blk, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (blk == hs->big_stage.data()) { if ((rc = sync(h))) return rc; }
+  }
+  if ((rc = up(h, h->p_res_begin, hs->res_begin.data(), P + 1))) return rc;
   if (!hs->fused_acc_ok) {   // only the un-fused accumulation walks the residuals in (host, target)-block order
     std::vector<int> by_block(n), cnt(nf * nf + 1, 0);
     for (int i = 0; i < n; i++) cnt[host[i] + r->target[i] * nf + 1]++;
@@ -652,21 +704,7 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
     for (int i = 0; i < n; i++) by_block[cnt[host[i] + r->target[i] * nf]++] = i;   // stable counting sort by block
     if ((rc = up(h, h->r_by_block, by_block.data(), n))) return rc;
   }
-  auto upflag = [&](uint8_t *dst, const uint8_t *src, uint8_t dflt) -> int {
-    if (src) return up(h, dst, src, n);
-    cudaMemsetAsync(dst, dflt, n, h->stream);
-    return SOSBA_OK;
-  };
-  if ((rc = upflag(h->r_state, r->state, SOSBA_RES_IN)) || (rc = upflag(h->r_is_lin, r->is_linearized, 0)) ||
-      (rc = upflag(h->r_is_active, r->is_active, 0)) || (rc = upflag(h->r_is_new, r->is_new, 1)))
-    return rc;
   if (r->is_linearized) for (int i = 0; i < n; i++) hs->n_lin += r->is_linearized[i] ? 1 : 0;
-  cudaMemsetAsync(h->r_new_state, SOSBA_RES_OUTLIER, n, h->stream);
-  cudaMemsetAsync(h->r_sel, 0, n, h->stream);
-  cudaMemsetAsync(h->r_dropped, 0, n, h->stream);
-  if (r->state_energy) { if ((rc = up(h, h->r_energy, r->state_energy, n)) || (rc = up(h, h->r_new_energy, r->state_energy, n))) return rc; }
-  else { cudaMemsetAsync(h->r_energy, 0, (size_t)n * 4, h->stream); cudaMemsetAsync(h->r_new_energy, 0, (size_t)n * 4, h->stream); }
-  launch_fill_f32(h, h->r_new_energy_wo, n, -1.f);   // state_NewEnergyWithOutlier = -1 until linearised (Residuals.cpp:78)
   SOSBA_CUDA(cudaGetLastError());
   return SOSBA_OK;
 }
@@ -1561,18 +1599,6 @@ API int sosba_immature_init(sosba_t *h, int32_t host_slot, int32_t n, const int3
   return sync(h);
 }
 
-// A block of the pinned staging ring, valid until the stream is synchronised twice (the ring only wraps behind a sync).
-static int stage_reserve(sosba *h, size_t bytes, char **p) {
-  HostSide *hs = HS(h);
-  if (!hs->stage || bytes > hs->stage_cap) { sosba_set_error("staging block of %zu bytes", bytes); return SOSBA_E_ARG; }
-  if (hs->stage_off + bytes > hs->stage_cap) {
-    SOSBA_CUDA(cudaStreamSynchronize(h->stream));
-    hs->stage_off = 0;
-  }
-  *p = hs->stage + hs->stage_off;
-  hs->stage_off += (bytes + 255) & ~(size_t)255;
-  return SOSBA_OK;
-}
 static const int IMM_CHUNK = 48 * 1024;   // points per pass: 48k x 121 B = 5.8 MB of the 16 MB ring
 
 // One pass = one H2D of the packed SoA, one launch, one D2H of the in/out tail, one synchronisation.

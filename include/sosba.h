@@ -376,6 +376,20 @@ enum { SOSBA_ACT_SKIP = 0, SOSBA_ACT_ACTIVATED = 1, SOSBA_ACT_DELETE = -1 };
 int sosba_optimize_immature(sosba_t *h, const sosba_activation_window *win, const sosba_immature *pts, int8_t *result, float *idepth,
                             uint8_t *res_state);
 
+/* ---- next row: loop-closure direct alignment -----------------------------------------
+ * PoseEstimator (src/LoopClosure/PoseEstimator.cpp): the LM loop of estimate() (:286-470) stays on the host and calls
+ * these two per iteration.  K per level comes from sosba_tracker_make_k (PoseEstimator::makeK :53-73 uses the same
+ * recursion as CoarseTracker::makeK). */
+/* pts of the matched LoopFrame (LoopHandler.h:85): xyz [n*3] = pts[i].first (camera-frame 3D point, Vector3d),
+ * color [n*levels] = pts[i].second[lvl], point-major. */
+int sosba_loop_set_points(sosba_t *h, int32_t n, const double *xyz, const float *color);
+/* PoseEstimator::calcRes (:147-284); affLL = AffLight::fromToVecExposure(refAbExposure, newFrame->ab_exposure, refAffGToL, aff_g2l).
+ * out6 / counts as sosba_tracker_calc_res_pose. */
+int sosba_loop_calc_res(sosba_t *h, int32_t lvl, int32_t slot, const double refToNew[12], const float affLL[2], float cutoffTH, double out6[6],
+                        int32_t counts[3]);
+/* PoseEstimator::calcGSSSE (:75-145); a = fromToVecExposure(...)[0], b0 = refAffGToL.b. */
+int sosba_loop_calc_gs(sosba_t *h, int32_t lvl, float a, float b0, double H[64], double b[8]);
+
 /* ---- multi-GPU: points shard across ranks, one all-reduce of [H,b] per GN iteration ----------- */
 /* 128-byte NCCL unique id (rank 0 creates, caller broadcasts, every rank inits). */
 int sosba_comm_unique_id(uint8_t id[128]);

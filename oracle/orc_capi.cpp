@@ -444,3 +444,26 @@ ORC_API int orc_frame_make_images_raw(orc_handle *h, int32_t slot, const void *r
   make_images(o, slot, img.data(), B);
   return SOSBA_OK;
 }
+
+// ---- next row: loop-closure direct alignment ----------------------------------------
+ORC_API int orc_loop_set_points(orc_handle *h, int32_t n, const double *xyz, const float *color) {
+  if (n < 0 || (n > 0 && (!xyz || !color))) return SOSBA_E_ARG;
+  Oracle &o = h->o;
+  o.loop_xyz.resize((size_t)3 * n);
+  for (size_t i = 0; i < (size_t)3 * n; i++) o.loop_xyz[i] = (float)xyz[i];
+  o.loop_color.assign(color, color + (size_t)n * o.levels);
+  return SOSBA_OK;
+}
+ORC_API int orc_loop_calc_res(orc_handle *h, int32_t lvl, int32_t slot, const double refToNew[12], const float affLL[2], float cutoff, double out6[6],
+                              int32_t counts[3]) {
+  if (lvl < 0 || lvl >= h->o.levels || slot < 0 || slot >= (int)h->o.slots.size() || !h->o.slots[slot].valid || !refToNew || !affLL) return SOSBA_E_ARG;
+  int32_t c[3];
+  double o6[6];
+  loop_calcRes(h->o, lvl, slot, refToNew, affLL, cutoff, out6 ? out6 : o6, counts ? counts : c);
+  return SOSBA_OK;
+}
+ORC_API int orc_loop_calc_gs(orc_handle *h, int32_t lvl, float a, float b0, double H[64], double b[8]) {
+  if (lvl < 0 || lvl >= h->o.levels) return SOSBA_E_ARG;
+  tracker_calcGSSSEPose(h->o, lvl, a, b0, H, b);
+  return SOSBA_OK;
+}

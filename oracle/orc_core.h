@@ -126,6 +126,7 @@ struct Oracle {
   std::vector<float> pc_u[SOSBA_MAX_LEVELS], pc_v[SOSBA_MAX_LEVELS], pc_idepth[SOSBA_MAX_LEVELS], pc_color[SOSBA_MAX_LEVELS];
   std::vector<float> bw_idepth, bw_u, bw_v, bw_dx, bw_dy, bw_residual, bw_weight, bw_refColor;  // poseBufWarped_*
   int bw_n = 0;
+  std::vector<float> loop_xyz, loop_color;   // PoseEstimator::pts (float-cast xyz [n*3], colour [n*levels])
   SE3 tfmF0ToF1;
   float fx1[SOSBA_MAX_LEVELS], fy1[SOSBA_MAX_LEVELS], cx1[SOSBA_MAX_LEVELS], cy1[SOSBA_MAX_LEVELS];
   std::vector<float> sw_rx1, sw_rx2, sw_rx3, sw_dx, sw_dy, sw_residual, sw_weight, sw_ref;  // scaleBufWarped_*

@@ -4,6 +4,7 @@
 //   ScaleOptimizer::makeK                 src/FullSystem/ScaleOptimizer.cpp:95-118
 //   CoarseTracker::calcResPose            src/FullSystem/CoarseTracker.cpp:612-764
 //   CoarseTracker::calcGSSSEPose          src/FullSystem/CoarseTracker.cpp:554-610
+//   PoseEstimator::calcRes / calcGSSSE    src/LoopClosure/PoseEstimator.cpp:147-284, 75-145
 //   ScaleOptimizer::calcResScale          src/FullSystem/ScaleOptimizer.cpp:273-437
 //   ScaleOptimizer::calcGSSSEScale        src/FullSystem/ScaleOptimizer.cpp:232-271
 //   Accumulator9::updateSSE_eighted       src/OptimizationBackend/MatrixAccumulators.h:1314-1432
@@ -109,6 +110,75 @@ void tracker_calcResPose(Oracle &o, int lvl, int slot, const double refToNew[12]
       o.bw_idepth[numTermsInWarped] = new_idepth; o.bw_u[numTermsInWarped] = u; o.bw_v[numTermsInWarped] = v;
       o.bw_dx[numTermsInWarped] = hitColor[1]; o.bw_dy[numTermsInWarped] = hitColor[2];
       o.bw_residual[numTermsInWarped] = residual; o.bw_weight[numTermsInWarped] = hw; o.bw_refColor[numTermsInWarped] = lpc_color[i];
+      numTermsInWarped++;
+    }
+  }
+  counts[0] = numTermsInE; counts[1] = numTermsInWarped; counts[2] = numSaturated;
+  while (numTermsInWarped % 4 != 0) {
+    o.bw_idepth[numTermsInWarped] = 0; o.bw_u[numTermsInWarped] = 0; o.bw_v[numTermsInWarped] = 0; o.bw_dx[numTermsInWarped] = 0;
+    o.bw_dy[numTermsInWarped] = 0; o.bw_residual[numTermsInWarped] = 0; o.bw_weight[numTermsInWarped] = 0; o.bw_refColor[numTermsInWarped] = 0;
+    numTermsInWarped++;
+  }
+  o.bw_n = numTermsInWarped;
+  out6[0] = E; out6[1] = numTermsInE; out6[2] = sumSquaredShiftT / (sumSquaredShiftNum + 0.1); out6[3] = 0;
+  out6[4] = sumSquaredShiftRT / (sumSquaredShiftNum + 0.1); out6[5] = numSaturated / (float)numTermsInE;
+}
+
+// PoseEstimator::calcRes (src/LoopClosure/PoseEstimator.cpp:147-284); fills the same warped buffers as calcResPose, so
+// PoseEstimator::calcGSSSE (:75-145, identical arithmetic to calcGSSSEPose) is tracker_calcGSSSEPose.
+void loop_calcRes(Oracle &o, int lvl, int slot, const double refToNew[12], const float affLL[2], float cutoffTH, double out6[6], int32_t counts[3]) {
+  ensure_warp_buffers(o);
+  float E = 0;
+  int numTermsInE = 0, numTermsInWarped = 0, numSaturated = 0;
+  const int wl = o.wl[lvl], hl = o.hl[lvl];
+  const float *dINewl = o.slots[slot].lvl[lvl].dI.data();
+  const float fxl = o.tfx[lvl], fyl = o.tfy[lvl], cxl = o.tcx[lvl], cyl = o.tcy[lvl];
+  M3<float> R; V3<float> t;
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) R(i, j) = (float)refToNew[i * 4 + j]; t[i] = (float)refToNew[i * 4 + 3]; }
+  float sumSquaredShiftT = 0, sumSquaredShiftRT = 0, sumSquaredShiftNum = 0;
+  const float huberTH = o.cfg.huber_th;
+  const float maxEnergy = 2 * huberTH * cutoffTH - huberTH * huberTH;
+  const size_t n = o.loop_xyz.size() / 3;
+  for (size_t i = 0; i < n; i++) {
+    float x = o.loop_xyz[3 * i], y = o.loop_xyz[3 * i + 1], z = o.loop_xyz[3 * i + 2];
+    float u0 = x / z, v0 = y / z;
+    float Ku0 = fxl * u0 + cxl, Kv0 = fyl * v0 + cyl;
+    V3<float> p3{{x, y, z}};
+    V3<float> pt = mul(R, p3);
+    for (int k = 0; k < 3; k++) pt[k] = pt[k] + t[k];
+    float u = pt[0] / pt[2], v = pt[1] / pt[2];
+    float Ku = fxl * u + cxl, Kv = fyl * v + cyl;
+    float new_idepth = 1 / pt[2];
+    if (lvl == 0 && i % 32 == 0) {
+      V3<float> xy1{{x, y, 1}};   // sic: the un-normalised x, y with z = 1 (PoseEstimator.cpp:208-223)
+      V3<float> ptT{{x + t[0], y + t[1], 1 + t[2]}};
+      float KuT = fxl * (ptT[0] / ptT[2]) + cxl, KvT = fyl * (ptT[1] / ptT[2]) + cyl;
+      V3<float> ptT2{{x - t[0], y - t[1], 1 - t[2]}};
+      float KuT2 = fxl * (ptT2[0] / ptT2[2]) + cxl, KvT2 = fyl * (ptT2[1] / ptT2[2]) + cyl;
+      V3<float> rp = mul(R, xy1);
+      V3<float> pt3{{rp[0] - t[0], rp[1] - t[1], rp[2] - t[2]}};
+      float Ku3 = fxl * (pt3[0] / pt3[2]) + cxl, Kv3 = fyl * (pt3[1] / pt3[2]) + cyl;
+      sumSquaredShiftT += (KuT - Ku0) * (KuT - Ku0) + (KvT - Kv0) * (KvT - Kv0);
+      sumSquaredShiftT += (KuT2 - Ku0) * (KuT2 - Ku0) + (KvT2 - Kv0) * (KvT2 - Kv0);
+      sumSquaredShiftRT += (Ku - Ku0) * (Ku - Ku0) + (Kv - Kv0) * (Kv - Kv0);
+      sumSquaredShiftRT += (Ku3 - Ku0) * (Ku3 - Ku0) + (Kv3 - Kv0) * (Kv3 - Kv0);
+      sumSquaredShiftNum += 2;
+    }
+    if (!(Ku > 2 && Kv > 2 && Ku < wl - 3 && Kv < hl - 3 && new_idepth > 0)) continue;
+    float refColor = o.loop_color[i * o.levels + lvl];
+    float hitColor[3];
+    interp33(dINewl, Ku, Kv, wl, hitColor);
+    if (!std::isfinite(hitColor[0])) continue;
+    float residual = hitColor[0] - (float)(affLL[0] * refColor + affLL[1]);
+    float hw = fabs(residual) < huberTH ? 1 : huberTH / fabs(residual);
+    if (fabs(residual) > cutoffTH) {
+      E += maxEnergy; numTermsInE++; numSaturated++;
+    } else {
+      E += hw * residual * residual * (2 - hw);
+      numTermsInE++;
+      o.bw_idepth[numTermsInWarped] = new_idepth; o.bw_u[numTermsInWarped] = u; o.bw_v[numTermsInWarped] = v;
+      o.bw_dx[numTermsInWarped] = hitColor[1]; o.bw_dy[numTermsInWarped] = hitColor[2];
+      o.bw_residual[numTermsInWarped] = residual; o.bw_weight[numTermsInWarped] = hw; o.bw_refColor[numTermsInWarped] = refColor;
       numTermsInWarped++;
     }
   }

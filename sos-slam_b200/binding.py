@@ -144,7 +144,7 @@ class Lib:
                   "accumulate", "points_get_acc", "solve_system", "resubstitute", "marginalize_points",
                   "tracker_make_k", "tracker_set_ref", "tracker_calc_res_pose", "tracker_calc_gs_pose",
                   "scale_set_stereo", "scale_calc_res", "scale_calc_gs", "optimize", "ba_upload", "ba_iterate",
-                  "ba_download", "ba_optimize", "pyr_levels", "immature_init", "trace_immature", "optimize_immature", "undistort_set", "frame_make_images_raw"):
+                  "ba_download", "ba_optimize", "pyr_levels", "immature_init", "trace_immature", "optimize_immature", "undistort_set", "frame_make_images_raw", "loop_set_points", "loop_calc_res", "loop_calc_gs"):
             self.f(n).restype = C.c_int
         self.f("destroy").restype = None
         if self.has("launch_count"):
@@ -401,6 +401,26 @@ class Handle:
     def tracker_set_ref(self, lvl, u, v, idepth, color):
         u, v, idepth, color = _f32(u), _f32(v), _f32(idepth), _f32(color)
         self._ck(self.lib.f("tracker_set_ref")(self.h, C.c_int32(lvl), C.c_int32(u.size), _p(u, f32p), _p(v, f32p), _p(idepth, f32p), _p(color, f32p)), "tracker_set_ref")
+
+    # ---- loop-closure direct alignment (LoopClosure/PoseEstimator.cpp:75-284)
+    def loop_set_points(self, xyz, color):
+        xyz, color = _f64(xyz), _f32(color)
+        self._ck(self.lib.f("loop_set_points")(self.h, C.c_int32(xyz.size // 3), _p(xyz, f64p), _p(color, f32p)), "loop_set_points")
+
+    def loop_calc_res(self, lvl, slot, refToNew34, affLL, cutoff):
+        T = _f64(refToNew34).reshape(12)
+        a = (C.c_float * 2)(float(affLL[0]), float(affLL[1]))
+        out6 = np.zeros(6)
+        cnt = np.zeros(3, np.int32)
+        self._ck(self.lib.f("loop_calc_res")(self.h, C.c_int32(lvl), C.c_int32(slot), _p(T, f64p), a, C.c_float(cutoff), _p(out6, f64p), _p(cnt, i32p)),
+                 "loop_calc_res")
+        return out6, cnt
+
+    def loop_calc_gs(self, lvl, a, b0):
+        H = np.zeros((8, 8))
+        b = np.zeros(8)
+        self._ck(self.lib.f("loop_calc_gs")(self.h, C.c_int32(lvl), C.c_float(a), C.c_float(b0), _p(H, f64p), _p(b, f64p)), "loop_calc_gs")
+        return H, b
 
     # ---- pre-pyramid image path (util/Undistort.cpp:194-227, 361-458)
     def undistort_set(self, w_org, h_org, remapX=None, remapY=None, G=None, vignette_inv=None):

@@ -542,10 +542,12 @@ __global__ void __launch_bounds__(256) k_track_res(TrackResArgs a) {
   float E = 0.f, sT = 0.f, sRT = 0.f, sN = 0.f;
   int inE = 0, inW = 0, sat = 0;
   if (i < a.n) {
-    const float x = a.pc[i], y = a.pc[a.n + i], id = a.pc[2 * a.n + i], refColor = a.pc[3 * a.n + i];
+    const float x = a.pc[i], y = a.pc[a.n + i], id = a.pc[2 * a.n + i], refColor = a.color[i];
     float3 pt;
     float rx0 = 0.f, rx1 = 0.f, rx2 = 0.f;
-    if (a.kind == 0) {
+    if (a.kind == 2) {   // PoseEstimator::calcRes (LoopClosure/PoseEstimator.cpp:193-206): 3D point, R in a.RKi, id holds z
+      pt = mul33(a.RKi, x, y, id);
+    } else if (a.kind == 0) {
       pt = mul33(a.RKi, x, y, 1.f);
     } else {  // scale * RKi (ScaleOptimizer.cpp:296-297): the matrix entries are scaled first
       float sRKi[9];
@@ -554,11 +556,26 @@ __global__ void __launch_bounds__(256) k_track_res(TrackResArgs a) {
       float3 rx = mul33(a.RKi, x, y, 1.f);
       rx0 = rx.x / id; rx1 = rx.y / id; rx2 = rx.z / id;
     }
-    pt.x = pt.x + a.t[0] * id; pt.y = pt.y + a.t[1] * id; pt.z = pt.z + a.t[2] * id;
+    if (a.kind == 2) { pt.x = pt.x + a.t[0]; pt.y = pt.y + a.t[1]; pt.z = pt.z + a.t[2]; }
+    else { pt.x = pt.x + a.t[0] * id; pt.y = pt.y + a.t[1] * id; pt.z = pt.z + a.t[2] * id; }
     const float u = pt.x / pt.z, v = pt.y / pt.z;
     const float Ku = a.fx * u + a.cx, Kv = a.fy * v + a.cy;
-    const float new_idepth = id / pt.z;
-    if (a.lvl == 0 && i % 32 == 0) {  // flow indicators (CoarseTracker.cpp:666-696)
+    const float new_idepth = a.kind == 2 ? 1 / pt.z : id / pt.z;
+    if (a.kind == 2 && a.lvl == 0 && i % 32 == 0) {  // flow indicators of the loop-closure variant (PoseEstimator.cpp:206-238)
+      const float Ku0 = a.fx * (x / id) + a.cx, Kv0 = a.fy * (y / id) + a.cy;
+      const float3 ptT = make_float3(x + a.t[0], y + a.t[1], 1 + a.t[2]);       // sic: (x, y, 1), not the normalised point
+      const float KuT = a.fx * (ptT.x / ptT.z) + a.cx, KvT = a.fy * (ptT.y / ptT.z) + a.cy;
+      const float3 ptT2 = make_float3(x - a.t[0], y - a.t[1], 1 - a.t[2]);
+      const float KuT2 = a.fx * (ptT2.x / ptT2.z) + a.cx, KvT2 = a.fy * (ptT2.y / ptT2.z) + a.cy;
+      const float3 rp = mul33(a.RKi, x, y, 1.f);
+      const float3 pt3 = make_float3(rp.x - a.t[0], rp.y - a.t[1], rp.z - a.t[2]);
+      const float Ku3 = a.fx * (pt3.x / pt3.z) + a.cx, Kv3 = a.fy * (pt3.y / pt3.z) + a.cy;
+      sT += (KuT - Ku0) * (KuT - Ku0) + (KvT - Kv0) * (KvT - Kv0);
+      sT += (KuT2 - Ku0) * (KuT2 - Ku0) + (KvT2 - Kv0) * (KvT2 - Kv0);
+      sRT += (Ku - Ku0) * (Ku - Ku0) + (Kv - Kv0) * (Kv - Kv0);
+      sRT += (Ku3 - Ku0) * (Ku3 - Ku0) + (Kv3 - Kv0) * (Kv3 - Kv0);
+      sN += 2;
+    } else if (a.lvl == 0 && i % 32 == 0) {  // flow indicators (CoarseTracker.cpp:666-696)
       float sKi[9];
       for (int k = 0; k < 9; k++) sKi[k] = a.kind == 0 ? a.Ki[k] : a.scale * a.Ki[k];
       float3 kp = mul33(sKi, x, y, 1.f);
@@ -581,14 +598,14 @@ __global__ void __launch_bounds__(256) k_track_res(TrackResArgs a) {
     if (Ku > 2 && Kv > 2 && Ku < a.w - 3 && Kv < a.h - 3 && new_idepth > 0) {
       float3 hit = interp33(a.img, Ku, Kv, a.w);
       if (isfinite(hit.x)) {
-        const float residual = a.kind == 0 ? hit.x - (float)(a.aff0 * refColor + a.aff1) : hit.x - refColor;
+        const float residual = a.kind != 1 ? hit.x - (float)(a.aff0 * refColor + a.aff1) : hit.x - refColor;
         const float hw = fabsf(residual) < a.huberTH ? 1 : a.huberTH / fabsf(residual);
         if (fabsf(residual) > a.cutoffTH) {
           E += a.maxEnergy; inE++; sat++;
         } else {
           E += hw * residual * residual * (2 - hw);
           inE++; inW++;
-          if (a.kind == 0) { o0 = new_idepth; o1 = u; o2 = v; }
+          if (a.kind != 1) { o0 = new_idepth; o1 = u; o2 = v; }
           else { o0 = rx0; o1 = rx1; o2 = rx2; }
           o3 = hit.y; o4 = hit.z; o5 = residual; o6 = hw; o7 = refColor;
         }

@@ -93,14 +93,15 @@ void launch_frame_retarget(sosba *h, const StepArgs &a);
 // compacted: invalid points carry weight 0) and the sums
 struct TrackResArgs {
   int n, lvl, w, h, cap;
-  const float *pc;        // u | v | idepth | color  (4 arrays of n)
+  const float *pc;        // u | v | idepth  (3 arrays of n); loop closure (kind 2): x | y | z of the 3D point
+  const float *color;     // reference colour of the level
   const float4 *img;      // level image of the new frame
   float RKi[9], Ki[9], t[3];
   float fx, fy, cx, cy;
   float aff0, aff1;
   float huberTH, cutoffTH, maxEnergy;
   float scale;            // scale variant only
-  int kind;               // 0 pose, 1 scale
+  int kind;               // 0 pose, 1 scale, 2 loop-closure pose (RKi holds R)
   float *warp;            // 8 arrays of cap floats
   double *acc;            // [0] E [1] shiftT [2] shiftRT [3] shiftNum ; ints in icnt
   int *icnt;              // [0] numTermsInE [1] numTermsInWarped [2] numSaturated

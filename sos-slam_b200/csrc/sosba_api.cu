@@ -61,6 +61,8 @@ struct HostSide {
   std::vector<char> big_stage;        // pageable staging for uploads larger than half the pinned ring
   float *p_arena = nullptr;           // uploaded members of the points (carve_points)
   unsigned char *r_arena = nullptr;   // ids / energies / flags of the residuals (carve_residuals)
+  float *d_loop = nullptr;      // loop-closure points: x | y | z | colour[level] (3 + levels arrays of loop_n)
+  int loop_n = 0, loop_cap = 0, last_res_n = 0;
   float *d_act = nullptr;       // activation outputs: [idepth n floats][result n bytes][res_state n*nf bytes]
   size_t act_cap = 0;
   float *d_act_win = nullptr;   // PRE_RTll / PRE_tTll / PRE_aff_mode per frame pair
@@ -1197,13 +1199,21 @@ API int sosba_tracker_set_ref(sosba_t *h, int32_t lvl, int32_t n, const float *u
 static int track_res_common(sosba *h, int kind, int lvl, int slot, const float R[9], const float t[3], const float K[4], float aff0, float aff1,
                             float scale, float cutoff, double out6[6], int32_t counts[3]) {
   HostSide *hs = HS(h);
+  if (kind == 2 && !hs->d_loop) { sosba_set_error("loop_set_points first"); return SOSBA_E_STATE; }
   if (!h->t_haveK) { sosba_set_error("tracker_make_k first"); return SOSBA_E_STATE; }
   if (lvl < 0 || lvl >= h->levels || slot < 0 || slot >= (int)h->slot_img.size() || !h->slot_valid[slot]) { sosba_set_error("bad level/slot"); return SOSBA_E_ARG; }
   TrackResArgs a;
-  a.n = h->t_n[lvl]; a.lvl = lvl; a.w = h->wl[lvl]; a.h = h->hl[lvl]; a.cap = h->t_warp_cap;
-  a.pc = h->t_pc[lvl]; a.img = h->slot_img[slot] + h->lvl_off[lvl];
+  a.lvl = lvl; a.w = h->wl[lvl]; a.h = h->hl[lvl]; a.cap = h->t_warp_cap;
+  a.img = h->slot_img[slot] + h->lvl_off[lvl];
   make_Ki(h->t_K[lvl], a.Ki);
-  mul33f(R, a.Ki, a.RKi);
+  if (kind == 2) {   // loop closure: 3D points x | y | z, then one colour array per level; the rotation is used as it is
+    a.n = hs->loop_n; a.pc = hs->d_loop; a.color = hs->d_loop + (size_t)(3 + lvl) * hs->loop_n;
+    for (int i = 0; i < 9; i++) a.RKi[i] = R[i];
+  } else {
+    a.n = h->t_n[lvl]; a.pc = h->t_pc[lvl]; a.color = h->t_pc[lvl] + 3 * (size_t)a.n;
+    mul33f(R, a.Ki, a.RKi);
+  }
+  hs->last_res_n = a.n;
   for (int i = 0; i < 3; i++) a.t[i] = t[i];
   a.fx = K[0]; a.fy = K[1]; a.cx = K[2]; a.cy = K[3];
   a.aff0 = aff0; a.aff1 = aff1;
@@ -1237,12 +1247,14 @@ API int sosba_tracker_calc_res_pose(sosba_t *h, int32_t lvl, int32_t slot, const
   return track_res_common(h, 0, lvl, slot, R, t, h->t_K[lvl], affLL[0], affLL[1], 1.f, cutoff, out6, counts);
 }
 
-API int sosba_tracker_calc_gs_pose(sosba_t *h, int32_t lvl, float a, float b0, double H[64], double b[8]) {
-  CHECK_H(h);
+static int gs_pose_common(sosba *h, int kind, int32_t lvl, float a, float b0, double H[64], double b[8]) {
   HostSide *hs = HS(h);
-  if (lvl != h->t_warp_lvl || h->t_warp_kind != 0) { sosba_set_error("calc_gs_pose needs calc_res_pose at the same level first"); return SOSBA_E_STATE; }
+  if (lvl < 0 || lvl >= h->levels || lvl != h->t_warp_lvl || h->t_warp_kind != kind) {
+    sosba_set_error("calc_gs needs the matching calc_res at the same level first");
+    return SOSBA_E_STATE;
+  }
   TrackGSArgs g;
-  g.n = h->t_n[lvl]; g.cap = h->t_warp_cap; g.kind = 0; g.warp = h->t_warp; g.fx = h->t_K[lvl][0]; g.fy = h->t_K[lvl][1]; g.a = a; g.b0 = b0;
+  g.n = hs->last_res_n; g.cap = h->t_warp_cap; g.kind = 0; g.warp = h->t_warp; g.fx = h->t_K[lvl][0]; g.fy = h->t_K[lvl][1]; g.a = a; g.b0 = b0;
   g.scale = 1.f; g.tx = g.ty = g.tz = 0.f; g.acc = h->t_acc;
   cudaMemsetAsync(h->t_acc + 8, 0, sizeof(double) * 48, h->stream);
   launch_track_gs(h, g);
@@ -1264,6 +1276,54 @@ API int sosba_tracker_calc_gs_pose(sosba_t *h, int32_t lvl, float a, float b0, d
   for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) H[8 * r + c] *= sc[r];
   for (int r = 0; r < 8; r++) b[r] *= sc[r];
   return SOSBA_OK;
+}
+
+API int sosba_tracker_calc_gs_pose(sosba_t *h, int32_t lvl, float a, float b0, double H[64], double b[8]) {
+  CHECK_H(h);
+  return gs_pose_common(h, 0, lvl, a, b0, H, b);
+}
+
+// ---- 8f rank 4: PoseEstimator (LoopClosure/PoseEstimator.cpp) -----------------------------------
+API int sosba_loop_set_points(sosba_t *h, int32_t n, const double *xyz, const float *color) {
+  CHECK_H(h);
+  if (n < 0 || (n > 0 && (!xyz || !color))) { sosba_set_error("loop_set_points: bad arguments"); return SOSBA_E_ARG; }
+  HostSide *hs = HS(h);
+  const int L = h->levels;
+  if (n > hs->loop_cap) {
+    dfree(h, hs->d_loop);
+    hs->loop_cap = n + n / 4 + 64;
+    DALLOC(h, hs->d_loop, (size_t)(3 + L) * hs->loop_cap);
+  }
+  if (n > h->t_warp_cap) {
+    dfree(h, h->t_warp);
+    h->t_warp_cap = n + n / 4 + 64;
+    DALLOC(h, h->t_warp, 8 * (size_t)h->t_warp_cap);
+  }
+  hs->loop_n = n;
+  if (n == 0) return SOSBA_OK;
+  std::vector<float> soa((size_t)(3 + L) * n);
+  for (int i = 0; i < n; i++) {
+    for (int k = 0; k < 3; k++) soa[(size_t)k * n + i] = (float)xyz[3 * (size_t)i + k];   // float x = pts[i].first(0) (PoseEstimator.cpp:188-190)
+    for (int l = 0; l < L; l++) soa[(size_t)(3 + l) * n + i] = color[(size_t)i * L + l];
+  }
+  int rc;
+  if ((rc = up(h, hs->d_loop, soa.data(), soa.size()))) return rc;
+  return sync(h);
+}
+
+API int sosba_loop_calc_res(sosba_t *h, int32_t lvl, int32_t slot, const double refToNew[12], const float affLL[2], float cutoff, double out6[6],
+                            int32_t counts[3]) {
+  CHECK_H(h);
+  if (!refToNew || !affLL) return SOSBA_E_ARG;
+  if (lvl < 0 || lvl >= h->levels) return SOSBA_E_ARG;
+  float R[9], t[3];
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) R[3 * i + j] = (float)refToNew[4 * i + j]; t[i] = (float)refToNew[4 * i + 3]; }
+  return track_res_common(h, 2, lvl, slot, R, t, h->t_K[lvl], affLL[0], affLL[1], 1.f, cutoff, out6, counts);
+}
+
+API int sosba_loop_calc_gs(sosba_t *h, int32_t lvl, float a, float b0, double H[64], double b[8]) {
+  CHECK_H(h);
+  return gs_pose_common(h, 2, lvl, a, b0, H, b);
 }
 
 API int sosba_scale_set_stereo(sosba_t *h, const double T10[12], const float K1[4]) {

@@ -367,3 +367,31 @@ def undistort_case(w, h, w_org=None, h_org=None, seed=3, bits=8, k1=-0.28, k2=0.
     remapX = np.where(ok, ix, np.float32(-1)).astype(np.float32)
     remapY = np.where(ok, iy, np.float32(-1)).astype(np.float32)
     return dict(raw=raw, remapX=remapX, remapY=remapY, G=G, vignette_inv=vignette_inv, w_org=w_org, h_org=h_org)
+
+
+def loop_case(scene: Scene, matched: int, levels: int, level_images, n: int = 3000, seed: int = 9):
+    """PoseEstimator inputs built like LoopHandler::addKeyFrame (LoopClosure/LoopHandler.cpp:186-209): 3D points of the
+    matched frame in its camera frame and their colour on every pyramid level (bilinear tap of channel 0 at the level's
+    pixel).  level_images[l] = (h_l, w_l) float32 intensity of the matched frame at level l.
+    -> dict(xyz [n,3] float64, color [n, levels] float32)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = [float(x) for x in scene.K]
+    sel = np.flatnonzero(scene.pt_host == matched)
+    if sel.size == 0:
+        sel = np.arange(scene.n_points)
+    idx = rng.choice(sel, n, replace=True)
+    u = scene.pt_u[idx].astype(np.float64) + rng.integers(-3, 4, n)
+    v = scene.pt_v[idx].astype(np.float64) + rng.integers(-3, 4, n)
+    u = np.clip(u, 4, scene.w - 5); v = np.clip(v, 4, scene.h - 5)
+    d = scene.pt_idepth[idx].astype(np.float64) * rng.uniform(0.99, 1.01, n)
+    xyz = np.stack([(u - cx) / fx / d, (v - cy) / fy / d, 1.0 / d], 1)
+    color = np.zeros((n, levels), np.float32)
+    for l in range(levels):
+        img = np.asarray(level_images[l], np.float32)
+        ul = ((u + 0.5) / (1 << l) - 0.5).astype(np.float32)
+        vl = ((v + 0.5) / (1 << l) - 0.5).astype(np.float32)
+        ix = ul.astype(np.int32); iy = vl.astype(np.int32)
+        dx = ul - ix; dy = vl - iy
+        dxdy = dx * dy
+        color[:, l] = dxdy * img[iy + 1, ix + 1] + (dy - dxdy) * img[iy + 1, ix] + (dx - dxdy) * img[iy, ix + 1] + (1 - dx - dy + dxdy) * img[iy, ix]
+    return dict(xyz=xyz, color=color)

@@ -634,3 +634,67 @@ def undistort_ref(raw, remapX, remapY, G=None, vignette_inv=None, factor=1.0):
     fxy = fx * fy
     out = fxy * data[yi + 1, xi + 1] + (fy - fxy) * data[yi + 1, xi] + (fx - fxy) * data[yi, xi + 1] + (F(1) - fx - fy + fxy) * data[yi, xi]
     return np.where(ok, out, F(0)).astype(F)
+
+
+# ---- loop-closure direct alignment ------------------------------------------------
+def loop_calc_res_ref(dI, K_lvl, xyz, color_lvl, refToNew, affLL, cutoff, lvl, huber=F(9)):
+    """PoseEstimator::calcRes (LoopClosure/PoseEstimator.cpp:147-284), vectorised float32.  dI (h, w, 3) level image of
+    the new frame, K_lvl = fx fy cx cy of the level.  -> out6 (float64), counts, warped buffers (dict, un-padded)."""
+    h, w = dI.shape[:2]
+    fx, fy, cx, cy = [F(x) for x in K_lvl]
+    R = np.asarray(refToNew, np.float64)[:3, :3].astype(F); t = np.asarray(refToNew, np.float64)[:3, 3].astype(F)
+    x, y, z = [np.asarray(xyz, np.float64)[:, k].astype(F) for k in range(3)]
+    pt = [(R[k, 0] * x + R[k, 1] * y) + R[k, 2] * z + t[k] for k in range(3)]
+    with np.errstate(all="ignore"):
+        u, v = pt[0] / pt[2], pt[1] / pt[2]
+        new_id = F(1) / pt[2]
+    Ku, Kv = fx * u + cx, fy * v + cy
+    sT = sRT = sN = F(0)
+    if lvl == 0:
+        for i in range(0, len(x), 32):
+            Ku0, Kv0 = fx * (x[i] / z[i]) + cx, fy * (y[i] / z[i]) + cy
+            pT = (x[i] + t[0], y[i] + t[1], F(1) + t[2])
+            KuT, KvT = fx * (pT[0] / pT[2]) + cx, fy * (pT[1] / pT[2]) + cy
+            pT2 = (x[i] - t[0], y[i] - t[1], F(1) - t[2])
+            KuT2, KvT2 = fx * (pT2[0] / pT2[2]) + cx, fy * (pT2[1] / pT2[2]) + cy
+            rp = [(R[k, 0] * x[i] + R[k, 1] * y[i]) + R[k, 2] * F(1) for k in range(3)]
+            p3 = (rp[0] - t[0], rp[1] - t[1], rp[2] - t[2])
+            Ku3, Kv3 = fx * (p3[0] / p3[2]) + cx, fy * (p3[1] / p3[2]) + cy
+            sT += (KuT - Ku0) * (KuT - Ku0) + (KvT - Kv0) * (KvT - Kv0)
+            sT += (KuT2 - Ku0) * (KuT2 - Ku0) + (KvT2 - Kv0) * (KvT2 - Kv0)
+            sRT += (Ku[i] - Ku0) * (Ku[i] - Ku0) + (Kv[i] - Kv0) * (Kv[i] - Kv0)
+            sRT += (Ku3 - Ku0) * (Ku3 - Ku0) + (Kv3 - Kv0) * (Kv3 - Kv0)
+            sN += F(2)
+    ok = (Ku > 2) & (Kv > 2) & (Ku < w - 3) & (Kv < h - 3) & (new_id > 0)
+    Kus, Kvs = np.where(ok, Ku, F(3)), np.where(ok, Kv, F(3))
+    hit = _bilin(dI, Kus, Kvs)
+    ok &= np.isfinite(hit[:, 0])
+    ref = np.asarray(color_lvl, F)
+    res = hit[:, 0] - (F(affLL[0]) * ref + F(affLL[1])).astype(F)
+    ares = np.abs(res)
+    hw = np.where(ares < huber, F(1), huber / np.maximum(ares, F(1e-30))).astype(F)
+    sat = ok & (ares > F(cutoff))
+    inw = ok & ~sat
+    maxE = F(2) * huber * F(cutoff) - huber * huber
+    terms = np.where(sat, maxE, hw * res * res * (F(2) - hw)).astype(F)
+    E = F(0)
+    for k in np.flatnonzero(ok):        # sequential float sum, the order of the reference loop
+        E += terms[k]
+    nE, nW, nS = int(ok.sum()), int(inw.sum()), int(sat.sum())
+    out6 = np.array([E, nE, sT / (sN + F(0.1)) if True else 0, 0, sRT / (sN + F(0.1)), F(nS) / F(max(nE, 1))], np.float64)
+    buf = dict(idepth=new_id[inw], u=u[inw], v=v[inw], dx=hit[inw, 1], dy=hit[inw, 2], residual=res[inw], weight=hw[inw], ref=ref[inw])
+    return out6, np.array([nE, nW, nS], np.int32), buf
+
+
+def pose_gs_ref(buf, fx, fy, a, b0):
+    """PoseEstimator::calcGSSSE (:75-145) in float64 from the warped buffers (n = count padded to a multiple of 4)."""
+    dx = buf["dx"].astype(np.float64) * fx; dy = buf["dy"].astype(np.float64) * fy
+    u, v, idp = [buf[k].astype(np.float64) for k in ("u", "v", "idepth")]
+    J = np.stack([idp * dx, idp * dy, -idp * (u * dx + v * dy), -((u * v) * dx + dy * (1 + v * v)), (u * v) * dy + dx * (1 + u * u), u * dy - v * dx,
+                  a * (b0 - buf["ref"].astype(np.float64)), -np.ones_like(u), buf["residual"].astype(np.float64)], 1)
+    A = (J * buf["weight"].astype(np.float64)[:, None]).T @ J
+    n = (len(u) + 3) // 4 * 4
+    sc = np.array([1, 1, 1, 0.5, 0.5, 0.5, 10, 1000], np.float64)
+    H = A[:8, :8] / n * sc[None, :] * sc[:, None]
+    b = A[:8, 8] / n * sc
+    return H, b

@@ -519,3 +519,38 @@ def test_undistort_vs_numpy(orc, mode):
         with pytest.raises(binding.SosbaError):
             hd.undistort_set(c["w_org"], c["h_org"], bad, c["remapY"], G, V)
     hd.close()
+
+
+# ---- next row: loop-closure direct alignment --------------------------------------
+def _loop_setup(lib, sc, n=1500):
+    from sos_slam_b200 import synth
+    h = open_handle(lib, sc)
+    h.tracker_make_k(sc.K.astype(np.float32))
+    lv = [np.asarray(h.frame_get_level(0, l)[0], np.float32).reshape(sc.h >> l, sc.w >> l, 3)[..., 0] for l in range(h.levels)]
+    case = synth.loop_case(sc, 0, h.levels, lv, n=n)
+    h.loop_set_points(case["xyz"], case["color"])
+    T = np.linalg.inv(sc.camToWorld_true[sc.nf - 1]) @ sc.camToWorld_true[0] @ synth.se3_exp(np.array([0.001, -0.0008, 0.0005, 0.0005, -0.0003, 0.0004]))
+    return h, case, T[:3, :4]
+
+
+def test_loop_pose_vs_numpy(orc):
+    """PoseEstimator::calcRes / calcGSSSE (LoopClosure/PoseEstimator.cpp:147-284, 75-145) against the numpy restatement on
+    every pyramid level: counts exact, energy and flow indicators to float rounding, H and b to 1e-5 (SSE float sums)."""
+    sc = scene(**SMALLC)
+    h, case, T = _loop_setup(orc, sc)
+    aff = (1.02, -1.5)
+    Kl = [np.array([sc.K[0] / (1 << l), sc.K[1] / (1 << l), (sc.K[2] + 0.5) / (1 << l) - 0.5, (sc.K[3] + 0.5) / (1 << l) - 0.5], np.float32)
+          for l in range(h.levels)]
+    for lvl in range(h.levels):
+        for cutoff in (20.0, 6.0):
+            out6, cnt = h.loop_calc_res(lvl, sc.nf - 1, T, aff, cutoff)
+            dI = np.asarray(h.frame_get_level(sc.nf - 1, lvl)[0], np.float32).reshape(sc.h >> lvl, sc.w >> lvl, 3)
+            r6, rc, buf = np_ref.loop_calc_res_ref(dI, Kl[lvl], case["xyz"], case["color"][:, lvl], T, aff, cutoff, lvl)
+            assert np.array_equal(cnt, rc), (lvl, cnt, rc)
+            assert cnt[1] > 150
+            np.testing.assert_allclose(out6, r6, rtol=2e-5, atol=1e-6)
+            H, b = h.loop_calc_gs(lvl, 1.02, 0.0)
+            Hr, br = np_ref.pose_gs_ref(buf, float(Kl[lvl][0]), float(Kl[lvl][1]), 1.02, 0.0)
+            assert relerr(H, Hr) < 2e-5 and relerr(b, br) < 2e-5, (lvl, relerr(H, Hr), relerr(b, br))
+        assert cnt[2] > 0            # the tight cutoff saturates some residuals
+    h.close()

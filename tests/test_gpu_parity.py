@@ -368,3 +368,35 @@ def test_undistort_raw_bit_exact(gpu, orc, mode, shape):
     assert np.array_equal(outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1], outs[1][1]):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+# ---- next row: loop-closure direct alignment ----------------------------------
+@pytest.mark.parametrize("cfg", [SMALL, CONFIG_B], ids=["small", "configB"])
+def test_loop_pose(gpu, orc, cfg):
+    """PoseEstimator::calcRes / calcGSSSE (LoopClosure/PoseEstimator.cpp:147-284, 75-145) on every level: counts
+    (numTermsInE / numTermsInWarped / numSaturated) exact, energy and flow indicators 2e-5, H and b 1e-4."""
+    from sos_slam_b200 import binding, synth
+    sc = scene(**cfg)
+    hg, ho = open_handle(gpu, sc), open_handle(orc, sc)
+    K = sc.K.astype(np.float32)
+    lv = [np.asarray(ho.frame_get_level(0, l)[0], np.float32).reshape(sc.h >> l, sc.w >> l, 3)[..., 0] for l in range(ho.levels)]
+    case = synth.loop_case(sc, 0, ho.levels, lv, n=6000)
+    T = (np.linalg.inv(sc.camToWorld_true[sc.nf - 1]) @ sc.camToWorld_true[0] @ synth.se3_exp(np.array([0.001, -0.0008, 0.0005, 0.0005, -0.0003, 0.0004])))[:3, :4]
+    with pytest.raises(binding.SosbaError):
+        hg.tracker_make_k(K); hg.loop_calc_res(0, sc.nf - 1, T, (1.0, 0.0), 20.0)       # no points yet
+    for h in (hg, ho):
+        h.tracker_make_k(K)
+        h.loop_set_points(case["xyz"], case["color"])
+    for lvl in range(hg.levels):
+        for cutoff in (20.0, 6.0):
+            og, cg = hg.loop_calc_res(lvl, sc.nf - 1, T, (1.02, -1.5), cutoff)
+            oo, co = ho.loop_calc_res(lvl, sc.nf - 1, T, (1.02, -1.5), cutoff)
+            assert np.array_equal(cg, co), (lvl, cg, co)
+            assert cg[1] > 500
+            assert np.allclose(og, oo, rtol=2e-5, atol=1e-6), (lvl, og, oo)
+            Hg, bg = hg.loop_calc_gs(lvl, 1.02, 0.0)
+            Ho, bo = ho.loop_calc_gs(lvl, 1.02, 0.0)
+            assert relerr(Hg, Ho) < 1e-4 and relerr(bg, bo) < 1e-4
+    with pytest.raises(binding.SosbaError):
+        hg.tracker_calc_gs_pose(0, 1.0, 0.0)                 # the warped buffers belong to the loop variant
+    hg.close(); ho.close()

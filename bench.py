@@ -384,6 +384,14 @@ def main():
             h.synchronize()
             raw_ms = 1e3 * (time.perf_counter() - t0) / reps
             h.frame_make_images(sc.nf, sc.images[-1])
+            # 8f rank 3: PixelSelector::makeMaps on the newest keyframe, density 1500 (setting_desiredImmatureDensity)
+            h.pixel_selector_set(np.random.default_rng(3141592).integers(0, 256, sc.w * sc.h).astype(np.uint8), 3)
+            h.pixel_select(sc.nf - 1, 1500.0, want_map=False)
+            sel_ms = []
+            for k in range(10):
+                t0 = time.perf_counter()
+                sel = h.pixel_select(k % sc.nf, 1500.0, want_map=False)
+                sel_ms.append(1e3 * (time.perf_counter() - t0))
             rng = np.random.default_rng(5)
             n_ref = 10000
             K = sc.K.astype(np.float32)
@@ -426,7 +434,7 @@ def main():
                 act = h.optimize_immature(np.arange(sc.nf), win["RTll"], win["tTll"], win["aff"], win["calib"], case["host"][okp], sub)
                 act_ms.append(1e3 * (time.perf_counter() - t0))
             other = {"optimize_immature_ms": float(np.median(act_ms)), "optimize_immature_points": int(okp.sum()),
-                     "optimize_immature_activated": int((act[0] == 1).sum()), "make_images_raw_ms": raw_ms,
+                     "optimize_immature_activated": int((act[0] == 1).sum()), "pixel_select_ms": float(np.median(sel_ms)), "pixel_select_n": int(sel["n"]), "make_images_raw_ms": raw_ms,
                      "make_images_raw_note": f"{uc['w_org']}x{uc['h_org']} 8-bit raw frame in: H2D + response/vignette + rectification + 4 levels, host wall per call",
                      "make_images_ms": pyr_ms, "make_images_note": f"{sc.w}x{sc.h}, H2D + 4 levels, host wall per call",
                      "trace_immature_ms": float(np.median(trace_ms)), "trace_immature_points": int(case["host"].size),
@@ -486,6 +494,18 @@ def main():
                 cpu_raw_ms = 1e3 * (time.perf_counter() - t0) / 5
             except Exception:
                 pass
+            cpu_sel_ms = None
+            try:
+                oh.pixel_selector_set(np.random.default_rng(3141592).integers(0, 256, sc1.w * sc1.h).astype(np.uint8), 3)
+                oh.pixel_select(sc1.nf - 1, 1500.0, want_map=False)
+                ts = []
+                for k in range(5):
+                    t0 = time.perf_counter()
+                    oh.pixel_select(k % sc1.nf, 1500.0, want_map=False)
+                    ts.append(1e3 * (time.perf_counter() - t0))
+                cpu_sel_ms = float(np.median(ts))
+            except Exception:
+                pass
             # the 8f rank-1 row on the host cores: traceNewCoarse is a serial loop in the reference (FullSystem.cpp:311-361)
             cpu_trace = None
             try:
@@ -501,7 +521,7 @@ def main():
                 t0 = time.perf_counter()
                 oh.optimize_immature(np.arange(sc1.nf), win["RTll"], win["tTll"], win["aff"], win["calib"], case["host"][okp], sub)
                 t_act = time.perf_counter() - t0
-                cpu_trace = {"make_images_raw_ms": cpu_raw_ms, "trace_immature_ms": 1e3 * t_tr, "optimize_immature_ms": 1e3 * t_act, "cores": 1,
+                cpu_trace = {"pixel_select_ms": cpu_sel_ms, "make_images_raw_ms": cpu_raw_ms, "trace_immature_ms": 1e3 * t_tr, "optimize_immature_ms": 1e3 * t_act, "cores": 1,
                              "note": "same inputs as other_kernels; single thread (the reference's trace loop is serial, its activation loop threaded)"}
             except Exception as ex:
                 cpu_trace = {"error": str(ex)}

@@ -376,6 +376,22 @@ enum { SOSBA_ACT_SKIP = 0, SOSBA_ACT_ACTIVATED = 1, SOSBA_ACT_DELETE = -1 };
 int sosba_optimize_immature(sosba_t *h, const sosba_activation_window *win, const sosba_immature *pts, int8_t *result, float *idepth,
                             uint8_t *res_state);
 
+/* ---- next row: pixel selection ---------------------------------------------------------
+ * PixelSelector (src/FullSystem/PixelSelector2.cpp).  The selector state of the reference object lives in the handle:
+ * randomPattern (w*h bytes, `rand() & 0xFF` after srand(3141592), :36-39 -- the caller passes its own array so both sides
+ * use the same numbers) and currentPotential (3 after construction, updated by every makeMaps). */
+int sosba_pixel_selector_set(sosba_t *h, const uint8_t *random_pattern, int32_t current_potential);
+/* PixelSelector::makeMaps(fh, map_out, density, recursionsLeft, plot = false, thFactor) (:146-282) with makeHists (:69-145)
+ * and select (:284-422) on the pyramid in `slot`.  Outputs (host buffers, any may be NULL):
+ *   n_selected          the return value numHaveSub
+ *   u, v, type [cap]    the non-zero entries of the status map in raster order (the order makeNewTraces walks it,
+ *                       FullSystem.cpp:1083-1097); type = 1, 2, 4 (the float stored in map_out = ImmaturePoint::my_type)
+ *   map_out [w*h]       the full status map of the reference
+ *   current_potential   currentPotential after the call
+ * Returns SOSBA_E_ARG if cap is smaller than the number of selected pixels. */
+int sosba_pixel_select(sosba_t *h, int32_t slot, float density, int32_t recursions_left, float th_factor, int32_t cap, int32_t *n_selected,
+                       int32_t *u, int32_t *v, float *type, float *map_out, int32_t *current_potential);
+
 /* ---- next row: loop-closure direct alignment -----------------------------------------
  * PoseEstimator (src/LoopClosure/PoseEstimator.cpp): the LM loop of estimate() (:286-470) stays on the host and calls
  * these two per iteration.  K per level comes from sosba_tracker_make_k (PoseEstimator::makeK :53-73 uses the same

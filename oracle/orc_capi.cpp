@@ -467,3 +467,36 @@ ORC_API int orc_loop_calc_gs(orc_handle *h, int32_t lvl, float a, float b0, doub
   tracker_calcGSSSEPose(h->o, lvl, a, b0, H, b);
   return SOSBA_OK;
 }
+
+// ---- next row: pixel selection ----------------------------------------------------
+ORC_API int orc_pixel_selector_set(orc_handle *h, const uint8_t *random_pattern, int32_t current_potential) {
+  if (!random_pattern || current_potential < 1) return SOSBA_E_ARG;
+  Oracle &o = h->o;
+  o.sel.randomPattern.assign(random_pattern, random_pattern + (size_t)o.wl[0] * o.hl[0]);
+  o.sel.currentPotential = current_potential;
+  return SOSBA_OK;
+}
+ORC_API int orc_pixel_select(orc_handle *h, int32_t slot, float density, int32_t recursions_left, float th_factor, int32_t cap, int32_t *n_selected,
+                             int32_t *u, int32_t *v, float *type, float *map_out, int32_t *current_potential) {
+  Oracle &o = h->o;
+  if (o.sel.randomPattern.empty()) return SOSBA_E_STATE;
+  if (slot < 0 || slot >= (int)o.slots.size() || !o.slots[slot].valid || o.levels < 3 || !(density > 0)) return SOSBA_E_ARG;
+  const int w = o.wl[0], hh = o.hl[0];
+  std::vector<float> map((size_t)w * hh);
+  const int n = pixel_select(o, slot, density, recursions_left, th_factor, map.data());
+  if (n_selected) *n_selected = n;
+  if (current_potential) *current_potential = o.sel.currentPotential;
+  if (map_out) memcpy(map_out, map.data(), map.size() * sizeof(float));
+  if (u || v || type) {
+    if (n > cap) return SOSBA_E_ARG;
+    int k = 0;
+    for (int i = 0; i < w * hh; i++)
+      if (map[i] != 0) {
+        if (u) u[k] = i % w;
+        if (v) v[k] = i / w;
+        if (type) type[k] = map[i];
+        k++;
+      }
+  }
+  return SOSBA_OK;
+}

@@ -83,6 +83,13 @@ struct Oracle {
   float wM3G, hM3G;  // globalCalib.cpp:63-64
   std::vector<Pyramid> slots;
 
+  // pixel selector (orc_select.cpp)
+  struct Selector {
+    std::vector<uint8_t> randomPattern;
+    int currentPotential = 3, thsStep = 0;
+    std::vector<float> ths, thsSmoothed;
+  } sel;
+
   // pre-pyramid image path (orc_trace.cpp: undistort_raw)
   struct Undist {
     bool set = false, passthrough = true, haveG = false, haveV = false;

@@ -59,6 +59,7 @@ void marginalizePoints(Oracle &o, const int32_t *ids, int n, double *H, double *
 // orc_tracker.cpp
 void tracker_makeK(Oracle &o, const float calib[4]);
 // orc_trace.cpp
+int pixel_select(Oracle &o, int slot, float density, int recursionsLeft, float thFactor, float *map_out);
 void undistort_raw(const Oracle &o, const void *raw, int raw_bits, float factor, float *out);
 void immature_init(Oracle &o, int slot, int n, const int32_t *u, const int32_t *v, float *color, float *weights, float *gradH, float *energyTH);
 void trace_immature(Oracle &o, int frame_slot, int nhosts, const float *KRKi, const float *Kt, const float *aff, sosba_immature *pts, int32_t counts[6]);

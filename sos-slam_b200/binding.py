@@ -144,7 +144,7 @@ class Lib:
                   "accumulate", "points_get_acc", "solve_system", "resubstitute", "marginalize_points",
                   "tracker_make_k", "tracker_set_ref", "tracker_calc_res_pose", "tracker_calc_gs_pose",
                   "scale_set_stereo", "scale_calc_res", "scale_calc_gs", "optimize", "ba_upload", "ba_iterate",
-                  "ba_download", "ba_optimize", "pyr_levels", "immature_init", "trace_immature", "optimize_immature", "undistort_set", "frame_make_images_raw", "loop_set_points", "loop_calc_res", "loop_calc_gs"):
+                  "ba_download", "ba_optimize", "pyr_levels", "immature_init", "trace_immature", "optimize_immature", "undistort_set", "frame_make_images_raw", "loop_set_points", "loop_calc_res", "loop_calc_gs", "pixel_selector_set", "pixel_select"):
             self.f(n).restype = C.c_int
         self.f("destroy").restype = None
         if self.has("launch_count"):
@@ -401,6 +401,23 @@ class Handle:
     def tracker_set_ref(self, lvl, u, v, idepth, color):
         u, v, idepth, color = _f32(u), _f32(v), _f32(idepth), _f32(color)
         self._ck(self.lib.f("tracker_set_ref")(self.h, C.c_int32(lvl), C.c_int32(u.size), _p(u, f32p), _p(v, f32p), _p(idepth, f32p), _p(color, f32p)), "tracker_set_ref")
+
+    # ---- pixel selection (FullSystem/PixelSelector2.cpp)
+    def pixel_selector_set(self, random_pattern, current_potential=3):
+        rp = _u8(random_pattern)
+        assert rp.size == self.cfg.w * self.cfg.h
+        self._ck(self.lib.f("pixel_selector_set")(self.h, _p(rp, u8p), C.c_int32(current_potential)), "pixel_selector_set")
+
+    def pixel_select(self, slot, density, recursions_left=1, th_factor=1.0, cap=None, want_map=True):
+        """-> dict(n, u, v, type, map, potential): makeMaps' return value, the raster-order list of selected pixels, the full
+        status map (float, 0/1/2/4) and currentPotential after the call."""
+        cap = cap if cap is not None else self.cfg.w * self.cfg.h // 4
+        u = np.zeros(cap, np.int32); v = np.zeros(cap, np.int32); t = np.zeros(cap, np.float32)
+        m = np.zeros((self.cfg.h, self.cfg.w), np.float32) if want_map else None
+        n = C.c_int32(0); pot = C.c_int32(0)
+        self._ck(self.lib.f("pixel_select")(self.h, C.c_int32(slot), C.c_float(density), C.c_int32(recursions_left), C.c_float(th_factor),
+                                            C.c_int32(cap), C.byref(n), _p(u, i32p), _p(v, i32p), _p(t, f32p), _p(m, f32p), C.byref(pot)), "pixel_select")
+        return dict(n=n.value, u=u[:n.value], v=v[:n.value], type=t[:n.value], map=m, potential=pot.value)
 
     # ---- loop-closure direct alignment (LoopClosure/PoseEstimator.cpp:75-284)
     def loop_set_points(self, xyz, color):

@@ -225,6 +225,26 @@ struct UndistortArgs {
 };
 void launch_undistort(sosba *h, const UndistortArgs &a);
 
+// ---- k_select.cu --------------------------------------------------------------------------------
+struct SelectArgs {
+  int w, h, w1, w2, w32, h32;
+  const float4 *img0, *img1, *img2;   // levels 0..2 of the frame ({I, dx, dy, absSquaredGrad})
+  float *ths, *thsSmoothed;           // [w32*h32 + 100]
+  const uint8_t *randomPattern;       // [w*h]
+  int pot, nbx, nby;                  // block grid of (4*pot)^2 blocks
+  float thFactor;
+  const int *base;                    // [nb] running level-0 count at the start of each block (exclusive scan of cnt_in)
+  const int *cnt_in;                  // [nb] counts the scan was taken from
+  int *cnt_out;                       // [nb] counts of this pass
+  uint8_t *map;                       // [w*h] status map (0, 1, 2, 4), cleared by the caller
+  int *totals;                        // [0..2] n2, n3, n4   [3] flag: counts changed   [4] selected pixels (compaction)
+};
+void launch_select_hists(sosba *h, const SelectArgs &a);
+void launch_select_blocks(sosba *h, const SelectArgs &a, bool write);
+void launch_select_serial(sosba *h, const SelectArgs &a);
+void launch_select_scan(sosba *h, const int *in, int *out, int n, int *total);
+void launch_select_compact(sosba *h, const uint8_t *map, int n, int *chunk_cnt, int *chunk_off, int *total, int cap, int2 *list);
+
 // ---- k_trace.cu ---------------------------------------------------------------------------------
 struct TraceArgs {
   int n, w, h;

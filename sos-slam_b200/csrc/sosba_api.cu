@@ -63,6 +63,14 @@ struct HostSide {
   unsigned char *r_arena = nullptr;   // ids / energies / flags of the residuals (carve_residuals)
   float *d_loop = nullptr;      // loop-closure points: x | y | z | colour[level] (3 + levels arrays of loop_n)
   int loop_n = 0, loop_cap = 0, last_res_n = 0;
+  // pixel selector (sosba_pixel_selector_set / sosba_pixel_select)
+  std::vector<uint8_t> sel_random;
+  int sel_pot = 3, sel_nb_cap = 0, sel_list_cap = 0;   // list capacity = w*h: at potential 1 every pixel can be selected
+  uint8_t *d_sel_random = nullptr, *d_sel_map = nullptr;
+  float *d_sel_ths = nullptr;          // ths | thsSmoothed, (w32*h32 + 100) each
+  int *d_sel_int = nullptr;            // totals[8] | chunk_cnt | chunk_off | cnt A | cnt B | base
+  int2 *d_sel_list = nullptr;
+  int2 *pin_sel_list = nullptr;        // pinned mirror of the first SEL_LIST_FAST entries + totals
   float *d_act = nullptr;       // activation outputs: [idepth n floats][result n bytes][res_state n*nf bytes]
   size_t act_cap = 0;
   float *d_act_win = nullptr;   // PRE_RTll / PRE_tTll / PRE_aff_mode per frame pair
@@ -297,6 +305,7 @@ API void sosba_destroy(sosba_t *h) {
   if (hs->stage) cudaFreeHost(hs->stage);
   if (hs->pin_i) cudaFreeHost(hs->pin_i);
   if (hs->pin_f) cudaFreeHost(hs->pin_f);
+  if (hs->pin_sel_list) cudaFreeHost(hs->pin_sel_list);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h->ba;
   { std::lock_guard<std::mutex> lk(g_mu); g_side.erase(h); }
@@ -1786,5 +1795,143 @@ API int sosba_optimize_immature(sosba_t *h, const sosba_activation_window *win, 
     if ((rc = sync(h))) return rc;
     memcpy(idepth + off, blk, 4 * N); memcpy(result + off, blk + 4 * N, N); memcpy(res_state + (size_t)off * nf, blk + 5 * N, N * nf);
   }
+  return SOSBA_OK;
+}
+
+// ---- next row: pixel selection --------------------------------------------
+
+API int sosba_pixel_selector_set(sosba_t *h, const uint8_t *random_pattern, int32_t current_potential) {
+  CHECK_H(h);
+  if (!random_pattern || current_potential < 1) { sosba_set_error("pixel_selector_set: bad arguments"); return SOSBA_E_ARG; }
+  if (h->levels < 3) { sosba_set_error("the selector reads pyramid levels 0..2"); return SOSBA_E_STATE; }
+  HostSide *hs = HS(h);
+  const size_t n = (size_t)h->cfg.w * h->cfg.h;
+  const int w32 = h->cfg.w / 32, h32 = h->cfg.h / 32, chunks = (int)((n + 1023) / 1024);
+  const int nb_max = ((h->cfg.w + 3) / 4) * ((h->cfg.h + 3) / 4);   // pot = 1
+  int rc;
+  if (!hs->d_sel_random) {
+    DALLOC(h, hs->d_sel_random, n);
+    DALLOC(h, hs->d_sel_map, n + 16);
+    DALLOC(h, hs->d_sel_ths, 2 * ((size_t)w32 * h32 + 100));
+    DALLOC(h, hs->d_sel_int, 8 + 2 * (size_t)chunks + 3 * (size_t)nb_max);
+    hs->sel_list_cap = (int)n;
+    DALLOC(h, hs->d_sel_list, n);
+    SOSBA_CUDA(cudaMallocHost((void **)&hs->pin_sel_list, sizeof(int2) * (n + 8192 + 8)));
+    hs->sel_nb_cap = nb_max;
+    SOSBA_CUDA(cudaMemsetAsync(hs->d_sel_ths, 0, 2 * ((size_t)w32 * h32 + 100) * sizeof(float), h->stream));
+  }
+  hs->sel_random.assign(random_pattern, random_pattern + n);
+  hs->sel_pot = current_potential;
+  if ((rc = up_bytes(h, hs->d_sel_random, random_pattern, n))) return rc;
+  return sync(h);
+}
+
+// PixelSelector::select on the device: fills d_sel_map, returns n2 / n3 / n4, the selected count and the raster-order list
+static int select_device(sosba *h, int slot, int pot, float thFactor, int n234[3], int *n_list) {
+  HostSide *hs = HS(h);
+  const int w = h->cfg.w, hh = h->cfg.h, n = w * hh, chunks = (n + 1023) / 1024;
+  SelectArgs a = {};
+  a.w = w; a.h = hh; a.w1 = h->wl[1]; a.w2 = h->wl[2]; a.w32 = w / 32; a.h32 = hh / 32;
+  a.img0 = h->slot_img[slot] + h->lvl_off[0]; a.img1 = h->slot_img[slot] + h->lvl_off[1]; a.img2 = h->slot_img[slot] + h->lvl_off[2];
+  a.ths = hs->d_sel_ths; a.thsSmoothed = hs->d_sel_ths + ((size_t)a.w32 * a.h32 + 100);
+  a.randomPattern = hs->d_sel_random;
+  a.pot = pot; a.nbx = (w + 4 * pot - 1) / (4 * pot); a.nby = (hh + 4 * pot - 1) / (4 * pot);
+  a.thFactor = thFactor;
+  const int nb = a.nbx * a.nby;
+  int *totals = hs->d_sel_int, *chunk_cnt = totals + 8, *chunk_off = chunk_cnt + chunks, *cntA = chunk_off + chunks, *cntB = cntA + hs->sel_nb_cap,
+      *base = cntB + hs->sel_nb_cap;
+  a.map = hs->d_sel_map; a.totals = totals; a.base = base;
+  // pass 0: counts with tentative directions
+  a.cnt_out = cntA; a.cnt_in = nullptr;
+  launch_select_blocks(h, a, false);
+  int rc;
+  int *cin = cntA, *cout = cntB;
+  for (int round = 0;; round++) {
+    launch_select_scan(h, cin, base, nb, nullptr);
+    SOSBA_CUDA(cudaMemsetAsync(totals, 0, 8 * sizeof(int), h->stream));
+    SOSBA_CUDA(cudaMemsetAsync(hs->d_sel_map, 0, (size_t)n, h->stream));
+    a.cnt_in = cin; a.cnt_out = cout;
+    if (round < 4) launch_select_blocks(h, a, true);
+    else launch_select_serial(h, a);   // counts that do not settle: sequential fallback (k_select.cu)
+    launch_select_compact(h, hs->d_sel_map, n, chunk_cnt, chunk_off, totals + 4, hs->sel_list_cap, hs->d_sel_list);
+    SOSBA_CUDA(cudaGetLastError());
+    // totals and the head of the list come back together; a longer list needs a second copy
+    const int fast = std::min(8192, hs->sel_list_cap);
+    if ((rc = down(h, (int *)hs->pin_sel_list, (const int *)totals, 8)) || (rc = down(h, hs->pin_sel_list + 4, (const int2 *)hs->d_sel_list, fast))) return rc;
+    if ((rc = sync(h))) return rc;
+    const int *t = (const int *)hs->pin_sel_list;
+    if (t[3] == 0 || round > 64) {
+      if (t[3]) { sosba_set_error("pixel_select: direction counts did not reach a fixed point"); return SOSBA_E_STATE; }
+      n234[0] = t[0]; n234[1] = t[1]; n234[2] = t[2];
+      *n_list = t[4];
+      if (t[4] > fast) {
+        if ((rc = down(h, hs->pin_sel_list + 4 + fast, (const int2 *)hs->d_sel_list + fast, (size_t)t[4] - fast))) return rc;
+        if ((rc = sync(h))) return rc;
+      }
+      return SOSBA_OK;
+    }
+    std::swap(cin, cout);   // the counts of this pass become the scan input of the next
+  }
+}
+
+API int sosba_pixel_select(sosba_t *h, int32_t slot, float density, int32_t recursions_left, float th_factor, int32_t cap, int32_t *n_selected,
+                           int32_t *u, int32_t *v, float *type, float *map_out, int32_t *current_potential) {
+  CHECK_H(h);
+  HostSide *hs = HS(h);
+  if (hs->sel_random.empty()) { sosba_set_error("pixel_selector_set first"); return SOSBA_E_STATE; }
+  if (slot < 0 || slot >= (int)h->slot_img.size() || !h->slot_valid[slot] || !(density > 0)) { sosba_set_error("bad slot / density"); return SOSBA_E_ARG; }
+  const int w = h->cfg.w, hh = h->cfg.h;
+  {  // makeHists (once per frame; the recursion of makeMaps reuses it)
+    SelectArgs a = {};
+    a.w = w; a.h = hh; a.w32 = w / 32; a.h32 = hh / 32;
+    a.img0 = h->slot_img[slot] + h->lvl_off[0];
+    a.ths = hs->d_sel_ths; a.thsSmoothed = hs->d_sel_ths + ((size_t)a.w32 * a.h32 + 100);
+    if (a.w32 * a.h32 > 0) launch_select_hists(h, a);
+  }
+  // PixelSelector::makeMaps (PixelSelector2.cpp:146-282): the control flow stays on the host
+  int rc, n234[3], n_list = 0;
+  float numHave, quotia;
+  const float numWant = density;
+  int idealPotential;
+  for (;;) {
+    if ((rc = select_device(h, slot, hs->sel_pot, th_factor, n234, &n_list))) return rc;
+    numHave = n234[0] + n234[1] + n234[2];
+    quotia = numWant / numHave;
+    const float K = numHave * (hs->sel_pot + 1) * (hs->sel_pot + 1);
+    idealPotential = sqrtf(K / numWant) - 1;
+    if (idealPotential < 1) idealPotential = 1;
+    if (recursions_left > 0 && quotia > 1.25 && hs->sel_pot > 1) {
+      if (idealPotential >= hs->sel_pot) idealPotential = hs->sel_pot - 1;
+      hs->sel_pot = idealPotential; recursions_left--;
+      continue;
+    } else if (recursions_left > 0 && quotia < 0.25) {
+      if (idealPotential <= hs->sel_pot) idealPotential = hs->sel_pot + 1;
+      hs->sel_pot = idealPotential; recursions_left--;
+      continue;
+    }
+    break;
+  }
+  // sub-sampling by the random pattern, indexed by the rank of the pixel among the selected ones in raster order (:226-238)
+  const int2 *list = hs->pin_sel_list + 4;
+  int numHaveSub = (int)numHave;
+  const bool sub = quotia < 0.95;
+  const unsigned char charTH = sub ? (unsigned char)(255 * quotia) : 255;
+  if (map_out) memset(map_out, 0, sizeof(float) * (size_t)w * hh);
+  int k = 0;
+  for (int rn = 0; rn < n_list; rn++) {
+    if (sub && hs->sel_random[rn] > charTH) { numHaveSub--; continue; }
+    const int idx = list[rn].x;
+    if (u || v || type) {
+      if (k >= cap) { sosba_set_error("pixel_select: more than cap = %d selected pixels", cap); return SOSBA_E_ARG; }
+      if (u) u[k] = idx % w;
+      if (v) v[k] = idx / w;
+      if (type) type[k] = (float)list[rn].y;
+    }
+    if (map_out) map_out[idx] = (float)list[rn].y;
+    k++;
+  }
+  hs->sel_pot = idealPotential;
+  if (n_selected) *n_selected = numHaveSub;
+  if (current_potential) *current_potential = hs->sel_pot;
   return SOSBA_OK;
 }

@@ -698,3 +698,159 @@ def pose_gs_ref(buf, fx, fy, a, b0):
     H = A[:8, :8] / n * sc[None, :] * sc[:, None]
     b = A[:8, 8] / n * sc
     return H, b
+
+
+# ---- pixel selection ----------------------------------------------------------------
+# Independent formulation of PixelSelector (FullSystem/PixelSelector2.cpp): makeHists with numpy block reductions, and
+# select() NOT as the reference's nested scan but through what that scan computes -- per pot-block the first arg-max of
+# |g . dir2| over pixels above the level-0 threshold; per 2pot-block a level-1 pick only if none of its pot-blocks picked;
+# per 4pot-block a level-2 pick only if nothing below it picked or updated.  Only the running count n2 is sequential.
+SEL_DIRS = np.array([[0, 1.0], [0.3827, 0.9239], [0.1951, 0.9808], [0.9239, 0.3827], [0.7071, 0.7071], [0.3827, -0.9239], [0.8315, 0.5556],
+                     [0.8315, -0.5556], [0.5556, -0.8315], [0.9808, 0.1951], [0.9239, -0.3827], [0.7071, -0.7071], [0.5556, 0.8315],
+                     [0.9808, -0.1951], [1.0, 0.0], [0.1951, -0.9808]], np.float32)
+
+
+def sel_hists_ref(absg0):
+    h, w = absg0.shape
+    w32, h32 = w // 32, h // 32
+    ths = np.zeros((h32, w32), F)
+    g = np.minimum(np.sqrt(absg0.astype(F)).astype(np.int32), 48)
+    valid = np.zeros((h, w), bool)
+    valid[1:h - 1, 1:w - 1] = True
+    for by in range(h32):
+        for bx in range(w32):
+            sl = (slice(32 * by, 32 * by + 32), slice(32 * bx, 32 * bx + 32))
+            vals = g[sl][valid[sl]]
+            hist = np.bincount(vals, minlength=49)
+            th = int(F(len(vals)) * F(0.5) + F(0.5))
+            q = 90
+            for i in range(49):
+                th -= hist[i]
+                if th < 0:
+                    q = i
+                    break
+            ths[by, bx] = q + 7
+    pad = np.pad(ths, 1)
+    cnt = np.pad(np.ones_like(ths), 1)
+    ssum = sum(pad[1 + dy:1 + dy + h32, 1 + dx:1 + dx + w32] for dy in (-1, 0, 1) for dx in (-1, 0, 1))
+    snum = sum(cnt[1 + dy:1 + dy + h32, 1 + dx:1 + dx + w32] for dy in (-1, 0, 1) for dx in (-1, 0, 1))
+    sm = (ssum.astype(F) / snum.astype(F))
+    return ths, (sm * sm).astype(F)
+
+
+def sel_select_ref(dI0, absg, ths_smoothed, random_pattern, pot, th_factor=1.0):
+    """-> (map (h, w) float32, (n2, n3, n4)).  dI0 (h, w, 3); absg = [level0, level1, level2] absSquaredGrad images."""
+    h, w = dI0.shape[:2]
+    w32 = w // 32
+    flat = np.concatenate([ths_smoothed.reshape(-1), np.zeros(100, F)])
+    ys, xs = np.mgrid[0:h, 0:w]
+    th0 = flat[(xs >> 5) + (ys >> 5) * w32].astype(F)
+    th1 = (th0 * F(0.75)).astype(F)
+    th2 = (th1 * (F(0.75) * F(0.75))).astype(F)
+    tf = F(th_factor)
+    inner = (xs >= 4) & (xs < w - 5) & (ys >= 4) & (ys <= h - 4)
+    ag1 = absg[1][(ys * F(0.5) + F(0.25)).astype(np.int32), (xs * F(0.5) + F(0.25)).astype(np.int32)]
+    ag2 = absg[2][(ys.astype(F) * F(0.25) + 0.125).astype(np.int32), (xs.astype(F) * F(0.25) + 0.125).astype(np.int32)]
+    c0 = inner & (absg[0] > th0 * tf)
+    c1 = inner & (ag1 > th1 * tf)
+    c2 = inner & (ag2 > th2 * tf)
+    gx, gy = dI0[..., 1].astype(F), dI0[..., 2].astype(F)
+    out = np.zeros((h, w), F)
+    n2 = n3 = n4 = 0
+
+    def pick(y0, x0, size, cand, d):
+        sl = (slice(y0, min(y0 + size, h)), slice(x0, min(x0 + size, w)))
+        m = cand[sl]
+        if not m.any():
+            return None
+        val = np.abs(gx[sl] * SEL_DIRS[d, 0] + gy[sl] * SEL_DIRS[d, 1]).astype(F)
+        val = np.where(m, val, F(-1))
+        return sl, val
+
+    for y4 in range(0, h, 4 * pot):
+        for x4 in range(0, w, 4 * pot):
+            d4 = random_pattern[n2] & 0xF
+            trig4 = False
+            order4 = []          # (scan position, value, idx) of the level-2 candidates in the reference's visiting order
+            for y3 in range(y4, min(y4 + 4 * pot, h), 2 * pot):
+                for x3 in range(x4, min(x4 + 4 * pot, w), 2 * pot):
+                    d3 = random_pattern[n2] & 0xF
+                    trig3 = False
+                    best3 = (F(0), -1)
+                    for y2 in range(y3, min(y3 + 2 * pot, h), pot):
+                        for x2 in range(x3, min(x3 + 2 * pot, w), pot):
+                            d2 = random_pattern[n2] & 0xF
+                            r = pick(y2, x2, pot, c0, d2)
+                            sel2 = False
+                            if r is not None:
+                                sl, val = r
+                                if val.max() > 0:
+                                    k = int(np.argmax(val))            # first maximum in row-major order
+                                    yy, xx = np.unravel_index(k, val.shape)
+                                    out[sl[0].start + yy, sl[1].start + xx] = 1
+                                    n2 += 1
+                                    sel2 = True
+                            if sel2:
+                                trig3 = True
+                                trig4 = True
+                                continue
+                            if trig3:
+                                continue
+                            r = pick(y2, x2, pot, c1, d3)
+                            if r is not None:
+                                sl, val = r
+                                if val.max() > best3[0]:
+                                    k = int(np.argmax(val))
+                                    yy, xx = np.unravel_index(k, val.shape)
+                                    best3 = (val.max(), (sl[0].start + yy, sl[1].start + xx))
+                                    trig4 = True
+                            if not trig4:
+                                r = pick(y2, x2, pot, c2, d4)
+                                if r is not None:
+                                    sl, val = r
+                                    order4.append((sl, val))
+                    if not trig3 and best3[1] != -1:
+                        out[best3[1]] = 2
+                        n3 += 1
+            if not trig4:
+                best = (F(0), None)
+                for sl, val in order4:
+                    if val.max() > best[0]:
+                        k = int(np.argmax(val))
+                        yy, xx = np.unravel_index(k, val.shape)
+                        best = (val.max(), (sl[0].start + yy, sl[1].start + xx))
+                if best[1] is not None:
+                    out[best[1]] = 4
+                    n4 += 1
+    return out, (n2, n3, n4)
+
+
+def sel_make_maps_ref(dI0, absg, random_pattern, potential, density, recursions_left=1, th_factor=1.0):
+    """PixelSelector::makeMaps (PixelSelector2.cpp:146-282) -> (map, numHaveSub, currentPotential)."""
+    _, ths_s = sel_hists_ref(absg[0])
+    while True:
+        m, n = sel_select_ref(dI0, absg, ths_s, random_pattern, potential, th_factor)
+        have = F(n[0] + n[1] + n[2])
+        with np.errstate(all="ignore"):
+            quotia = F(density) / have
+            K = have * F(potential + 1) * F(potential + 1)
+            ideal = int(np.sqrt(K / F(density)) - F(1))
+        ideal = max(ideal, 1)
+        if recursions_left > 0 and quotia > 1.25 and potential > 1:
+            potential = potential - 1 if ideal >= potential else ideal
+            recursions_left -= 1
+            continue
+        if recursions_left > 0 and quotia < 0.25:
+            potential = potential + 1 if ideal <= potential else ideal
+            recursions_left -= 1
+            continue
+        break
+    sub = int(have)
+    if quotia < 0.95:
+        char_th = int(F(255) * quotia) & 0xFF
+        flat = m.reshape(-1)
+        nz = np.flatnonzero(flat)
+        drop = random_pattern[:len(nz)] > char_th
+        flat[nz[drop]] = 0
+        sub -= int(drop.sum())
+    return m, sub, ideal

@@ -554,3 +554,51 @@ def test_loop_pose_vs_numpy(orc):
             assert relerr(H, Hr) < 2e-5 and relerr(b, br) < 2e-5, (lvl, relerr(H, Hr), relerr(b, br))
         assert cnt[2] > 0            # the tight cutoff saturates some residuals
     h.close()
+
+
+# ---- next row: pixel selection ----------------------------------------------------
+def _selector_inputs(h, slot, w, hh):
+    lv = [h.frame_get_level(slot, l) for l in range(3)]
+    dI0 = np.asarray(lv[0][0], np.float32).reshape(hh, w, 3)
+    absg = [np.asarray(lv[l][1], np.float32).reshape(hh >> l, w >> l) for l in range(3)]
+    return dI0, absg
+
+
+@pytest.mark.parametrize("pot", [1, 2, 3, 5])
+def test_pixel_select_vs_numpy(orc, pot):
+    """PixelSelector::makeHists + select (PixelSelector2.cpp:69-145, 284-422) at a fixed potential: the status map is identical
+    to an independent formulation (block arg-max with kill rules instead of the reference's interleaved scan)."""
+    from sos_slam_b200 import binding
+    sc = scene(w=192, h=160, nf=3, n_points=60, seed=8)
+    h = open_handle(orc, sc)
+    rp = np.random.default_rng(3141592).integers(0, 256, sc.w * sc.h).astype(np.uint8)
+    with pytest.raises(binding.SosbaError):
+        h.pixel_select(0, 1e9, 0)
+    h.pixel_selector_set(rp, pot)
+    got = h.pixel_select(1, 1e9, recursions_left=0, cap=sc.w * sc.h)          # density so large that nothing is sub-sampled: map = select()
+    dI0, absg = _selector_inputs(h, 1, sc.w, sc.h)
+    _, ths_s = np_ref.sel_hists_ref(absg[0])
+    ref, n = np_ref.sel_select_ref(dI0, absg, ths_s, rp, pot)
+    assert got["n"] == sum(n)
+    assert np.array_equal(got["map"], ref), int(np.sum(got["map"] != ref))
+    assert n[0] > 20 and (pot > 2 or n[1] > 0)
+    ys, xs = np.nonzero(ref)
+    assert np.array_equal(got["u"], xs) and np.array_equal(got["v"], ys) and np.array_equal(got["type"], ref[ys, xs])
+    h.close()
+
+
+@pytest.mark.parametrize("density,pot0", [(150.0, 3), (3000.0, 6), (40.0, 1), (600.0, 3)])
+def test_pixel_make_maps_vs_numpy(orc, density, pot0):
+    """PixelSelector::makeMaps (PixelSelector2.cpp:146-282): recursion on the potential, random sub-sampling, returned count
+    and the updated currentPotential."""
+    sc = scene(w=192, h=160, nf=3, n_points=60, seed=8)
+    h = open_handle(orc, sc)
+    rp = np.random.default_rng(7).integers(0, 256, sc.w * sc.h).astype(np.uint8)
+    h.pixel_selector_set(rp, pot0)
+    got = h.pixel_select(2, density)
+    dI0, absg = _selector_inputs(h, 2, sc.w, sc.h)
+    ref, n, pot = np_ref.sel_make_maps_ref(dI0, absg, rp, pot0, density)
+    assert (got["n"], got["potential"]) == (n, pot)
+    assert np.array_equal(got["map"], ref)
+    assert got["n"] == int(np.count_nonzero(ref)) == got["u"].size
+    h.close()

@@ -400,3 +400,64 @@ def test_loop_pose(gpu, orc, cfg):
     with pytest.raises(binding.SosbaError):
         hg.tracker_calc_gs_pose(0, 1.0, 0.0)                 # the warped buffers belong to the loop variant
     hg.close(); ho.close()
+
+
+# ---- next row: pixel selection --------------------------------------------------
+@pytest.mark.parametrize("cfg", [SMALL, CONFIG_B, KITTI], ids=["small", "configB", "kitti"])
+def test_pixel_select_bit_exact(gpu, orc, cfg):
+    """PixelSelector::makeMaps / makeHists / select (PixelSelector2.cpp:69-422): status map, raster-order list, returned
+    count and currentPotential identical to the oracle's -- at fixed potentials without sub-sampling, and through the
+    recursion + random sub-sampling of makeMaps for several densities, with the selector state carried from call to call."""
+    sc = scene(**cfg)
+    hg, ho = open_handle(gpu, sc), open_handle(orc, sc)
+    rp = np.random.default_rng(3141592).integers(0, 256, sc.w * sc.h).astype(np.uint8)
+    for pot in (1, 2, 3, 7):
+        outs = []
+        for h in (hg, ho):
+            h.pixel_selector_set(rp, pot)
+            outs.append(h.pixel_select(1, 1e9, recursions_left=0, cap=sc.w * sc.h))
+        g, o = outs
+        assert g["n"] == o["n"] and g["potential"] == o["potential"], (pot, g["n"], o["n"])
+        assert np.array_equal(g["map"], o["map"]), (pot, int(np.sum(g["map"] != o["map"])))
+        for k in ("u", "v", "type"):
+            assert np.array_equal(g[k], o[k]), (pot, k)
+        assert g["n"] > 50
+    for h in (hg, ho):
+        h.pixel_selector_set(rp, 3)
+    for slot, density in ((0, 1500.0), (1, 1500.0), (2, 6000.0), (3, 200.0), (0, 30000.0), (1, 1500.0)):
+        g, o = hg.pixel_select(slot, density, cap=sc.w * sc.h), ho.pixel_select(slot, density, cap=sc.w * sc.h)
+        assert (g["n"], g["potential"]) == (o["n"], o["potential"]), (slot, density, g["n"], o["n"], g["potential"], o["potential"])
+        assert np.array_equal(g["map"], o["map"])
+        for k in ("u", "v", "type"):
+            assert np.array_equal(g[k], o[k]), (slot, density, k)
+        assert g["n"] == np.count_nonzero(g["map"])
+    hg.close(); ho.close()
+
+
+@pytest.mark.parametrize("kind", ["stripes", "mixed"])
+def test_pixel_select_degenerate_directions(gpu, orc, kind):
+    """Gradients exactly orthogonal to direction 0 (an image area that varies along x only): whether a block selects a pixel
+    then depends on its direction, the per-block counts of the first pass are not final, and the running count of the
+    reference even stalls on such blocks (no selection -> same randomPattern entry -> same direction).  "mixed": a
+    degenerate band inside a textured image (the fix-up rounds settle); "stripes": the whole image (sequential fallback)."""
+    from sos_slam_b200 import binding
+    w, h = 320, 240
+    xs = np.arange(w, dtype=np.float32)
+    img = np.tile(100 + 60 * ((xs // 6) % 2) + 25 * ((xs // 45) % 2), (h, 1)).astype(np.float32)   # vertical step edges: dy == 0 exactly
+    if kind == "mixed":
+        tex = scene(**SMALL).images[0]
+        img[:, 96:] = tex[:, 96:]
+    rp = np.random.default_rng(5).integers(0, 256, w * h).astype(np.uint8)
+    outs = []
+    for lib in (gpu, orc):
+        cfg = lib.config_default(w, h)
+        cfg.max_frames = 1
+        hd = binding.Handle(lib, cfg)
+        hd.frame_make_images(0, img)
+        hd.pixel_selector_set(rp, 2)
+        outs.append([hd.pixel_select(0, 1e9, recursions_left=0, cap=w * h), hd.pixel_select(0, 800.0)])
+        hd.close()
+    for g, o in zip(*outs):
+        assert g["n"] == o["n"] and g["potential"] == o["potential"], (g["n"], o["n"])
+        assert np.array_equal(g["map"], o["map"]), int(np.sum(g["map"] != o["map"]))
+    assert outs[0][0]["n"] > (500 if kind == "mixed" else 0)

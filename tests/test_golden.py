@@ -91,3 +91,31 @@ def test_cuda_matches_golden(gpu):
     upd = np.abs(G["out_opt_state"] - G["in_state"]).max(axis=0) + 1e-12
     assert (np.abs(o["opt_state"] - G["out_opt_state"]).max(axis=0) <= 5e-3 * upd).all()
     assert np.allclose(o["opt_idepth"], G["out_opt_idepth"], rtol=2e-3, atol=1e-5)
+
+
+# ---- front-end rows: tests/golden/frontend_tiny.npz, made by tools/make_golden_frontend.py ----------
+import _frontend_case as fc  # noqa: E402
+
+FG = np.load(os.path.join(ROOT, "tests", "golden", "frontend_tiny.npz"))
+
+
+def _check_frontend(o):
+    for k in fc.EXACT:
+        assert np.array_equal(np.asarray(o[k]), FG["out_" + k], equal_nan=True), k
+    for k, tol in fc.CLOSE:
+        assert relerr(o[k], FG["out_" + k]) < tol, (k, relerr(o[k], FG["out_" + k]))
+
+
+def test_oracle_reproduces_frontend_golden(orc):
+    """raw frame -> irradiance -> pyramid, pixel selection, immature points (constructor, two traces, activation) and the
+    loop-closure alignment: the oracle reproduces the stored vectors bit for bit."""
+    o = fc.run(orc, FG)
+    _check_frontend(o)
+    for k, _ in fc.CLOSE:
+        assert np.array_equal(np.asarray(o[k]), FG["out_" + k]), k
+    assert FG["out_trace_counts"][1][[0, 1, 2, 3]].min() > 0 and (FG["out_act_result"] == 1).sum() > 50
+
+
+@pytest.mark.gpu
+def test_cuda_matches_frontend_golden(gpu):
+    _check_frontend(fc.run(gpu, FG))

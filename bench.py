@@ -536,7 +536,8 @@ def main():
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD if factor == 1 else WORKLOAD + f" x{factor} points, point-sharded", "points": sc.n_points,
                            "residuals": sc.n_residuals, "gn_iterations_per_step": ITERS, "linearizations_per_step": ITERS + 2,
-                           "l2": "flushed between steps (256 MiB fill); per-step CUDA events on the launch stream", "parallelism": f"points/{world}"},
+                           "l2": "flushed between steps (256 MiB fill); per-step CUDA events on the launch stream", "parallelism": f"points/{world}",
+                           "exchange": "none" if world == 1 else ("peer-memory push over NVLink (comm.cu)" if h.comm_uses_peer_memory() else "nccl all-reduce")},
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                                           "ms_per_step": e2e_ms / args.steps},
                 "e2e_raw_frame": e2e_raw, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "other_kernels": other,

@@ -411,6 +411,10 @@ int sosba_loop_calc_gs(sosba_t *h, int32_t lvl, float a, float b0, double H[64],
 int sosba_comm_unique_id(uint8_t id[128]);
 int sosba_comm_init(sosba_t *h, const uint8_t id[128], int32_t rank, int32_t world);
 int sosba_comm_destroy(sosba_t *h);
+/* 1 when the per-iteration exchange runs over peer memory (experimental, SOSBA_COMM_P2P=1 in the environment at
+ * sosba_comm_init: every rank pushes its partial tables into the other ranks' HBM over NVLink, cudaIpc-mapped), 0 when it
+ * is the NCCL all-reduce (the default: faster on 2 and 4 B200s). */
+int sosba_comm_uses_peer_memory(const sosba_t *h);
 
 #ifdef __cplusplus
 }

@@ -209,6 +209,9 @@ class Handle:
         self._ck(self.lib.f("comm_unique_id")(buf), "comm_unique_id")
         return bytes(buf)
 
+    def comm_uses_peer_memory(self) -> bool:
+        return bool(self.lib.has("comm_uses_peer_memory") and self.lib.f("comm_uses_peer_memory")(self.h))
+
     def comm_init(self, uid: bytes, rank: int, world: int):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         self._ck(self.lib.f("comm_init")(self.h, buf, C.c_int32(rank), C.c_int32(world)), "comm_init")

@@ -26,7 +26,7 @@ void launch_stitch_raw(sosba *h, const double *accTop2, const double *adHost, co
 using sosba_host::BAState;
 using sosba_host::WindowTables;
 
-int sosba_allreduce_acc(sosba *h, int with_newE);  // comm.cu: no-ops without a communicator
+int sosba_allreduce_acc(sosba *h, int with_newE, const int *gate, int *err, const ThArgs *th, int *th_done);  // comm.cu: no-ops without a communicator
 int sosba_allreduce_lin(sosba *h, int with_stats);
 int sosba_comm_max_int(sosba *h, int v, int *out);
 static thread_local char g_err[512] = "";
@@ -980,9 +980,12 @@ static int enqueue_blocks(sosba *h) {
   // points are sharded across ranks: sum the block tables (identical on every rank afterwards); the pending newest-frame
   // energies ride along and the threshold selection runs right behind the reduction
   const bool shard_th = h->comm && h->world > 1 && hs->th_pending;
-  int rc = sosba_allreduce_acc(h, shard_th ? 1 : 0);
+  ThArgs th = {};
+  if (shard_th) th = lin_args(h).th;
+  int th_done = 0;
+  int rc = sosba_allreduce_acc(h, shard_th ? 1 : 0, hs->gate, hs->gate ? hs->d_ctl + 2 : nullptr, shard_th ? &th : nullptr, &th_done);
   if (rc) return rc;
-  if (shard_th) { launch_energy_th(h, lin_args(h).th, hs->gate); hs->th_pending = false; }
+  if (shard_th) { if (!th_done) launch_energy_th(h, th, hs->gate); hs->th_pending = false; }
   return SOSBA_OK;
 }
 
@@ -1147,7 +1150,7 @@ API int sosba_marginalize_points(sosba_t *h, const int32_t *ids, int32_t n, doub
   a.rec = h->r_rec; a.accTop = h->d_accTop; a.n_acc = hs->d_cnt;
   launch_top_accumulate(h, a);
   launch_point_sc(h, sc_args(h, 2, d_pl, n, 0));
-  if ((rc = sosba_allreduce_acc(h, 0))) return rc;
+  if ((rc = sosba_allreduce_acc(h, 0, nullptr, nullptr, nullptr, nullptr))) return rc;
   launch_stitch_top(h, h->d_accTop, h->d_adHost, h->d_adTarget, nf, Hpart(h, 0), bpart(h, 0), 0, h->d_wprior, h->d_calib + 6);
   launch_finalize_sc(h, h->d_accSC, nf, Hpart(h, 2), bpart(h, 2));
   SOSBA_CUDA(cudaGetLastError());

@@ -24,8 +24,10 @@ def run(lib, sc, local, shard=None, uid=None, rank=0, world=1, iters=6):
     for i, img in enumerate(sc.images):
         h.frame_make_images(i, img)
     pts, res = problem.points_of(sc), problem.residuals_of(sc)
+    mode = "single"
     if shard is not None:
         h.comm_init(uid, rank, world)
+        mode = "peer-memory" if h.comm_uses_peer_memory() else "nccl"
         pts, res = problem.shard_scene_arrays(pts, res, *shard)
     val, val0 = problem.calib_of(sc)
     P, keep = h.make_problem(problem.frames_of(sc), val, val0, pts, res)
@@ -33,6 +35,7 @@ def run(lib, sc, local, shard=None, uid=None, rank=0, world=1, iters=6):
     r = h.problem_result(P, keep)
     st = h.get_state()["state"]
     h.close()
+    out["exchange"] = mode
     return out, r, st
 
 
@@ -49,8 +52,31 @@ def main():
         assert lib.f("comm_unique_id")(buf) == 0
         uid[0] = bytes(buf)
     dist.broadcast_object_list(uid, src=0)
+    def new_uid():
+        u = [None]
+        if rank == 0:
+            import ctypes
+            b = (ctypes.c_uint8 * 128)()
+            assert lib.f("comm_unique_id")(b) == 0
+            u[0] = bytes(b)
+        dist.broadcast_object_list(u, src=0)
+        return u[0]
+
     shards = problem.shard_points(sc.res_point, sc.n_points, world)
     out, r, st = run(lib, sc, local, shards[rank], uid[0], rank, world)
+    assert out["exchange"] == "nccl"
+    # the same window through the experimental peer-memory exchange: both must lead to the same optimised window
+    os.environ["SOSBA_COMM_P2P"] = "1"
+    out_n, r_n, st_n = run(lib, sc, local, shards[rank], new_uid(), rank, world)
+    del os.environ["SOSBA_COMM_P2P"]
+    dn = float(np.abs(r_n["state"] - r["state"]).max())
+    agree = (out_n["iterations"] == out["iterations"] and dn <= 1e-9 * max(1.0, float(np.abs(r["state"]).max()))
+             and np.allclose(r_n["frame_energy_th"], r["frame_energy_th"], rtol=1e-6) and np.array_equal(st_n, st))
+    if rank == 0:
+        print(f"exchange {out['exchange']} vs {out_n['exchange']}: iterations {out['iterations']} / {out_n['iterations']}, max state difference {dn:.2e}, "
+              f"residual states equal {np.array_equal(st_n, st)}")
+    assert agree, "peer-memory exchange and NCCL all-reduce disagree"
+    assert out_n["exchange"] == "peer-memory" or os.environ.get("SOSBA_ALLOW_NO_P2P"), "peer memory could not be mapped on this box"
     # every rank must hold the same frame states / thresholds / iteration count
     t = torch.tensor(np.concatenate([r["state"].ravel(), r["frame_energy_th"].astype(np.float64), [out["iterations"], out["energy_final"]]]), device="cuda")
     lo, hi = t.clone(), t.clone()

@@ -406,6 +406,33 @@ int sosba_loop_calc_res(sosba_t *h, int32_t lvl, int32_t slot, const double refT
 /* PoseEstimator::calcGSSSE (:75-145); a = fromToVecExposure(...)[0], b0 = refAffGToL.b. */
 int sosba_loop_calc_gs(sosba_t *h, int32_t lvl, float a, float b0, double H[64], double b[8]);
 
+/* CoarseInitializer::Pnt (src/FullSystem/CoarseInitializer.h:32-65) of one pyramid level, SoA: what calcResAndGS reads
+ * and writes. */
+typedef struct sosba_init_points {
+  int32_t n;
+  int32_t reserved0;
+  const float *u, *v;             /* [n] */
+  const float *idepth_new;        /* [n] */
+  const float *iR;                /* [n] */
+  const float *energy;            /* [n*2] (photometric, regulariser) */
+  const float *outlierTH;         /* [n] */
+  const uint8_t *isGood;          /* [n] */
+  float *energy_new;              /* [n*2] out */
+  uint8_t *isGood_new;            /* [n] out */
+  float *maxstep;                 /* [n] out */
+  float *lastHessian_new;         /* [n] out (written for isGood_new points only, like the reference) */
+  float *JbBuffer_new;            /* [n*10] out */
+} sosba_init_points;
+
+/* CoarseInitializer::calcResAndGS (src/FullSystem/CoarseInitializer.cpp:450-673) on level `lvl`: firstFrame in ref_slot,
+ * newFrame in new_slot, K per level from sosba_tracker_make_k (CoarseInitializer::makeK uses the same recursion).
+ * aff = (refToNew_aff.a, refToNew_aff.b); tlog = refToNew.log().head<3>(); alphaW / alphaK / couplingWeight as set in
+ * setFirst (:236-239).  H, b, Hsc, bsc: 8x8 / 8 floats (row-major); res3 = (E.A, alphaEnergy, E.num).
+ * lastHessian_new must be pre-filled by the caller with the points' current values (entries of rejected points are kept). */
+int sosba_init_calc_res_and_gs(sosba_t *h, int32_t lvl, int32_t ref_slot, int32_t new_slot, const double refToNew[12], const float aff[2],
+                               const float tlog[3], float alphaW, float alphaK, float couplingWeight, sosba_init_points *pts, float H[64], float b[8],
+                               float Hsc[64], float bsc[8], float res3[3]);
+
 /* ---- multi-GPU: points shard across ranks, one all-reduce of [H,b] per GN iteration ----------- */
 /* 128-byte NCCL unique id (rank 0 creates, caller broadcasts, every rank inits). */
 int sosba_comm_unique_id(uint8_t id[128]);

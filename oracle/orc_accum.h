@@ -126,6 +126,21 @@ template <int I> struct AccumulatorX {
 };
 
 // MatrixAccumulators.h:1172-1687 : 9x9 upper triangle, 4 SSE lanes per entry.
+// MatrixAccumulators.h:80-149 (only the scalar update is used on this path)
+struct Accumulator11 {
+  float A;
+  size_t num;
+  float SSEData[4], SSEData1k[4], SSEData1m[4];
+  float numIn1, numIn1k, numIn1m;
+  void initialize() { A = 0; memset(SSEData, 0, sizeof(SSEData)); memset(SSEData1k, 0, sizeof(SSEData1k)); memset(SSEData1m, 0, sizeof(SSEData1m)); num = 0; numIn1 = numIn1k = numIn1m = 0; }
+  void finish() { shiftUp(true); A = SSEData1m[0] + SSEData1m[1] + SSEData1m[2] + SSEData1m[3]; }
+  void updateSingle(float val) { SSEData[0] += val; num++; numIn1++; shiftUp(false); }
+  void shiftUp(bool force) {
+    if (numIn1 > 1000 || force) { for (int i = 0; i < 4; i++) SSEData1k[i] = SSEData[i] + SSEData1k[i]; numIn1k += numIn1; numIn1 = 0; memset(SSEData, 0, sizeof(SSEData)); }
+    if (numIn1k > 1000 || force) { for (int i = 0; i < 4; i++) SSEData1m[i] = SSEData1k[i] + SSEData1m[i]; numIn1m += numIn1k; numIn1k = 0; memset(SSEData1k, 0, sizeof(SSEData1k)); }
+  }
+};
+
 struct Accumulator9 {
   float H[9][9];
   size_t num;
@@ -142,6 +157,31 @@ struct Accumulator9 {
         H[r][c] = H[c][r] = d;
         idx += 4;
       }
+  }
+  // :1206-1312 ; J[k][lane]
+  void updateSSE(const float J[9][4]) {
+    float *pt = SSEData;
+    for (int r = 0; r < 9; r++)
+      for (int c = r; c < 9; c++) {
+        for (int l = 0; l < 4; l++) pt[l] = pt[l] + J[r][l] * J[c][l];
+        pt += 4;
+      }
+    num += 4; numIn1++;
+    shiftUp(false);
+  }
+  // :1543-1660 (lane `off` = 0): diagonal (Jr * Jr) * w, then Jr *= w and the rest of the row Jc * Jr
+  void updateSingleWeighted(const float Jin[9], float w) {
+    float J[9];
+    for (int i = 0; i < 9; i++) J[i] = Jin[i];
+    float *pt = SSEData;
+    for (int r = 0; r < 9; r++) {
+      *pt += J[r] * J[r] * w;
+      pt += 4;
+      J[r] *= w;
+      for (int c = r + 1; c < 9; c++) { *pt += J[c] * J[r]; pt += 4; }
+    }
+    num++; numIn1++;
+    shiftUp(false);
   }
   // :1314-1432 ; J[k][lane], w[lane]
   void updateSSE_eighted(const float J[9][4], const float w[4]) {

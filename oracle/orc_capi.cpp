@@ -500,3 +500,13 @@ ORC_API int orc_pixel_select(orc_handle *h, int32_t slot, float density, int32_t
   }
   return SOSBA_OK;
 }
+
+ORC_API int orc_init_calc_res_and_gs(orc_handle *h, int32_t lvl, int32_t ref_slot, int32_t new_slot, const double refToNew[12], const float aff[2],
+                                     const float tlog[3], float alphaW, float alphaK, float couplingWeight, sosba_init_points *pts, float H[64], float b[8],
+                                     float Hsc[64], float bsc[8], float res3[3]) {
+  Oracle &o = h->o;
+  auto bad = [&](int s) { return s < 0 || s >= (int)o.slots.size() || !o.slots[s].valid; };
+  if (lvl < 0 || lvl >= o.levels || bad(ref_slot) || bad(new_slot) || !refToNew || !aff || !tlog || !pts || pts->n < 0) return SOSBA_E_ARG;
+  init_calcResAndGS(o, lvl, ref_slot, new_slot, refToNew, aff, tlog, alphaW, alphaK, couplingWeight, pts, H, b, Hsc, bsc, res3);
+  return SOSBA_OK;
+}

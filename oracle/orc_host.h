@@ -66,6 +66,8 @@ void trace_immature(Oracle &o, int frame_slot, int nhosts, const float *KRKi, co
 void optimize_immature(Oracle &o, const sosba_activation_window *win, const sosba_immature *pts, int8_t *result, float *idepth, uint8_t *res_state);
 void tracker_calcResPose(Oracle &o, int lvl, int slot, const double refToNew[12], const float affLL[2], float cutoffTH, double out6[6], int32_t counts[3]);
 void loop_calcRes(Oracle &o, int lvl, int slot, const double refToNew[12], const float affLL[2], float cutoffTH, double out6[6], int32_t counts[3]);
+void init_calcResAndGS(Oracle &o, int lvl, int ref_slot, int new_slot, const double refToNew[12], const float aff[2], const float tlog[3], float alphaW,
+                       float alphaK, float couplingWeight, sosba_init_points *pts, float H[64], float b[8], float Hsc[64], float bsc[8], float res3[3]);
 void tracker_calcGSSSEPose(Oracle &o, int lvl, float a, float b0, double H[64], double b[8]);
 void scale_calcRes(Oracle &o, int lvl, int slot, float scale, float cutoffTH, double out6[6], int32_t counts[3]);
 void scale_calcGSSSE(Oracle &o, int lvl, float scale, float *H, float *b);

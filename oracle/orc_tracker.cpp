@@ -5,6 +5,7 @@
 //   CoarseTracker::calcResPose            src/FullSystem/CoarseTracker.cpp:612-764
 //   CoarseTracker::calcGSSSEPose          src/FullSystem/CoarseTracker.cpp:554-610
 //   PoseEstimator::calcRes / calcGSSSE    src/LoopClosure/PoseEstimator.cpp:147-284, 75-145
+//   CoarseInitializer::calcResAndGS       src/FullSystem/CoarseInitializer.cpp:450-673
 //   ScaleOptimizer::calcResScale          src/FullSystem/ScaleOptimizer.cpp:273-437
 //   ScaleOptimizer::calcGSSSEScale        src/FullSystem/ScaleOptimizer.cpp:232-271
 //   Accumulator9::updateSSE_eighted       src/OptimizationBackend/MatrixAccumulators.h:1314-1432
@@ -191,6 +192,132 @@ void loop_calcRes(Oracle &o, int lvl, int slot, const double refToNew[12], const
   o.bw_n = numTermsInWarped;
   out6[0] = E; out6[1] = numTermsInE; out6[2] = sumSquaredShiftT / (sumSquaredShiftNum + 0.1); out6[3] = 0;
   out6[4] = sumSquaredShiftRT / (sumSquaredShiftNum + 0.1); out6[5] = numSaturated / (float)numTermsInE;
+}
+
+// CoarseInitializer::calcResAndGS (src/FullSystem/CoarseInitializer.cpp:450-673)
+void init_calcResAndGS(Oracle &o, int lvl, int ref_slot, int new_slot, const double refToNew[12], const float aff[2], const float tlog[3], float alphaW,
+                       float alphaK, float couplingWeight, sosba_init_points *P, float H_out[64], float b_out[8], float H_out_sc[64], float b_out_sc[8],
+                       float res3[3]) {
+  const int wl = o.wl[lvl], hl = o.hl[lvl];
+  const float *colorRef = o.slots[ref_slot].lvl[lvl].dI.data(), *colorNew = o.slots[new_slot].lvl[lvl].dI.data();
+  M3<float> Rf; V3<float> t;
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) Rf(i, j) = (float)refToNew[i * 4 + j]; t[i] = (float)refToNew[i * 4 + 3]; }
+  const M3<float> RKi = mul(Rf, o.tKi[lvl]);
+  const float r2new_aff[2] = {(float)exp((double)aff[0]), aff[1]};   // Eigen::Vector2f(exp(refToNew_aff.a), refToNew_aff.b): a is a double in AffLight
+  const float fxl = o.tfx[lvl], fyl = o.tfy[lvl], cxl = o.tcx[lvl], cyl = o.tcy[lvl];
+  const float huberTH = o.cfg.huber_th;
+  Accumulator11 E;
+  Accumulator9 acc9, acc9SC;
+  acc9.initialize();
+  E.initialize();
+  const int npts = P->n;
+  for (int i = 0; i < npts; i++) {
+    P->maxstep[i] = 1e10;
+    float *Jb = P->JbBuffer_new + 10 * (size_t)i;
+    if (!P->isGood[i]) {
+      E.updateSingle(P->energy[2 * i]);
+      P->energy_new[2 * i] = P->energy[2 * i]; P->energy_new[2 * i + 1] = P->energy[2 * i + 1];
+      P->isGood_new[i] = 0;
+      continue;
+    }
+    float dp[8][8], dd[8], r[8];
+    for (int k = 0; k < 10; k++) Jb[k] = 0;
+    bool isGood = true;
+    float energy = 0;
+    const float pu = P->u[i], pv = P->v[i], idn = P->idepth_new[i];
+    for (int idx = 0; idx < 8; idx++) {
+      const int dx = patternP[idx][0], dy = patternP[idx][1];
+      V3<float> xy1{{pu + dx, pv + dy, 1}};
+      V3<float> pt = mul(RKi, xy1);
+      for (int k = 0; k < 3; k++) pt[k] = pt[k] + t[k] * idn;
+      float u = pt[0] / pt[2], v = pt[1] / pt[2];
+      float Ku = fxl * u + cxl, Kv = fyl * v + cyl;
+      float new_idepth = idn / pt[2];
+      if (!(Ku > 1 && Kv > 1 && Ku < wl - 2 && Kv < hl - 2 && new_idepth > 0)) { isGood = false; break; }
+      float hitColor[3];
+      interp33(colorNew, Ku, Kv, wl, hitColor);
+      float rl3[3];
+      interp33(colorRef, pu + dx, pv + dy, wl, rl3);   // getInterpolatedElement31: channel 0 of the same bilinear formula
+      float rlR = rl3[0];
+      if (!std::isfinite(rlR) || !std::isfinite(hitColor[0])) { isGood = false; break; }
+      float residual = hitColor[0] - r2new_aff[0] * rlR - r2new_aff[1];
+      float hw = fabs(residual) < huberTH ? 1 : huberTH / fabs(residual);
+      energy += hw * residual * residual * (2 - hw);
+      float dxdd = (t[0] - t[2] * u) / pt[2];
+      float dydd = (t[1] - t[2] * v) / pt[2];
+      if (hw < 1) hw = sqrtf(hw);
+      float dxInterp = hw * hitColor[1] * fxl;
+      float dyInterp = hw * hitColor[2] * fyl;
+      dp[0][idx] = new_idepth * dxInterp;
+      dp[1][idx] = new_idepth * dyInterp;
+      dp[2][idx] = -new_idepth * (u * dxInterp + v * dyInterp);
+      dp[3][idx] = -u * v * dxInterp - (1 + v * v) * dyInterp;
+      dp[4][idx] = (1 + u * u) * dxInterp + u * v * dyInterp;
+      dp[5][idx] = -v * dxInterp + u * dyInterp;
+      dp[6][idx] = -hw * r2new_aff[0] * rlR;
+      dp[7][idx] = -hw * 1;
+      dd[idx] = dxInterp * dxdd + dyInterp * dydd;
+      r[idx] = hw * residual;
+      float mx = dxdd * fxl, my = dydd * fyl;
+      float maxstep = 1.0f / sqrtf(mx * mx + my * my);
+      if (maxstep < P->maxstep[i]) P->maxstep[i] = maxstep;
+      for (int k = 0; k < 8; k++) Jb[k] += dp[k][idx] * dd[idx];
+      Jb[8] += r[idx] * dd[idx];
+      Jb[9] += dd[idx] * dd[idx];
+    }
+    if (!isGood || energy > P->outlierTH[i] * 20) {
+      E.updateSingle(P->energy[2 * i]);
+      P->isGood_new[i] = 0;
+      P->energy_new[2 * i] = P->energy[2 * i]; P->energy_new[2 * i + 1] = P->energy[2 * i + 1];
+      continue;
+    }
+    E.updateSingle(energy);
+    P->isGood_new[i] = 1;
+    P->energy_new[2 * i] = energy;
+    for (int g = 0; g + 3 < 8; g += 4) {
+      float J[9][4];
+      for (int l = 0; l < 4; l++) { for (int k = 0; k < 8; k++) J[k][l] = dp[k][g + l]; J[8][l] = r[g + l]; }
+      acc9.updateSSE(J);
+    }
+  }
+  E.finish();
+  acc9.finish();
+  // alpha energy: the reference adds these terms to E (after E.finish()) and leaves EAlpha at zero (:606-617)
+  for (int i = 0; i < npts; i++) {
+    if (!P->isGood_new[i]) E.updateSingle(P->energy[2 * i + 1]);
+    else {
+      P->energy_new[2 * i + 1] = (P->idepth_new[i] - 1) * (P->idepth_new[i] - 1);
+      E.updateSingle(P->energy_new[2 * i + 1]);
+    }
+  }
+  const float EAlphaA = 0;
+  const double tsq = refToNew[3] * refToNew[3] + refToNew[7] * refToNew[7] + refToNew[11] * refToNew[11];
+  float alphaEnergy = alphaW * (EAlphaA + tsq * npts);
+  float alphaOpt;
+  if (alphaEnergy > alphaK * npts) { alphaOpt = 0; alphaEnergy = alphaK * npts; }
+  else alphaOpt = alphaW;
+  acc9SC.initialize();
+  for (int i = 0; i < npts; i++) {
+    if (!P->isGood_new[i]) continue;
+    float *Jb = P->JbBuffer_new + 10 * (size_t)i;
+    P->lastHessian_new[i] = Jb[9];
+    Jb[8] += alphaOpt * (P->idepth_new[i] - 1);
+    Jb[9] += alphaOpt;
+    if (alphaOpt == 0) {
+      Jb[8] += couplingWeight * (P->idepth_new[i] - P->iR[i]);
+      Jb[9] += couplingWeight;
+    }
+    Jb[9] = 1 / (1 + Jb[9]);
+    acc9SC.updateSingleWeighted(Jb, Jb[9]);
+  }
+  acc9SC.finish();
+  for (int rr = 0; rr < 8; rr++) {
+    for (int c = 0; c < 8; c++) { H_out[8 * rr + c] = acc9.H[rr][c]; H_out_sc[8 * rr + c] = acc9SC.H[rr][c]; }
+    b_out[rr] = acc9.H[rr][8]; b_out_sc[rr] = acc9SC.H[rr][8];
+  }
+  H_out[0] += alphaOpt * npts; H_out[9] += alphaOpt * npts; H_out[18] += alphaOpt * npts;
+  b_out[0] += tlog[0] * alphaOpt * npts; b_out[1] += tlog[1] * alphaOpt * npts; b_out[2] += tlog[2] * alphaOpt * npts;
+  res3[0] = E.A; res3[1] = alphaEnergy; res3[2] = (float)E.num;
 }
 
 void tracker_calcGSSSEPose(Oracle &o, int lvl, float a, float b0, double H_out[64], double b_out[8]) {

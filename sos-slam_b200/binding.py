@@ -83,6 +83,12 @@ class Immature(C.Structure):
                 ("last_trace_pixel_interval", f32p)]
 
 
+class InitPoints(C.Structure):
+    _fields_ = [("n", C.c_int32), ("reserved0", C.c_int32), ("u", f32p), ("v", f32p), ("idepth_new", f32p), ("iR", f32p), ("energy", f32p),
+                ("outlierTH", f32p), ("isGood", u8p), ("energy_new", f32p), ("isGood_new", u8p), ("maxstep", f32p), ("lastHessian_new", f32p),
+                ("JbBuffer_new", f32p)]
+
+
 class ActivationWindow(C.Structure):
     _fields_ = [("nf", C.c_int32), ("min_obs", C.c_int32), ("frame_slot", i32p), ("RTll", f32p), ("tTll", f32p), ("aff", f32p),
                 ("calib", C.c_float * 4), ("reserved0", C.c_int32), ("reserved1", C.c_int32)]
@@ -144,7 +150,7 @@ class Lib:
                   "accumulate", "points_get_acc", "solve_system", "resubstitute", "marginalize_points",
                   "tracker_make_k", "tracker_set_ref", "tracker_calc_res_pose", "tracker_calc_gs_pose",
                   "scale_set_stereo", "scale_calc_res", "scale_calc_gs", "optimize", "ba_upload", "ba_iterate",
-                  "ba_download", "ba_optimize", "pyr_levels", "immature_init", "trace_immature", "optimize_immature", "undistort_set", "frame_make_images_raw", "loop_set_points", "loop_calc_res", "loop_calc_gs", "pixel_selector_set", "pixel_select"):
+                  "ba_download", "ba_optimize", "pyr_levels", "immature_init", "trace_immature", "optimize_immature", "undistort_set", "frame_make_images_raw", "loop_set_points", "loop_calc_res", "loop_calc_gs", "pixel_selector_set", "pixel_select", "init_calc_res_and_gs"):
             self.f(n).restype = C.c_int
         self.f("destroy").restype = None
         if self.has("launch_count"):
@@ -404,6 +410,30 @@ class Handle:
     def tracker_set_ref(self, lvl, u, v, idepth, color):
         u, v, idepth, color = _f32(u), _f32(v), _f32(idepth), _f32(color)
         self._ck(self.lib.f("tracker_set_ref")(self.h, C.c_int32(lvl), C.c_int32(u.size), _p(u, f32p), _p(v, f32p), _p(idepth, f32p), _p(color, f32p)), "tracker_set_ref")
+
+    # ---- CoarseInitializer::calcResAndGS (FullSystem/CoarseInitializer.cpp:450-673)
+    def init_calc_res_and_gs(self, lvl, ref_slot, new_slot, refToNew34, aff, tlog, pts, alphaW=150.0 * 150.0, alphaK=2.5 * 2.5, couplingWeight=1.0):
+        """pts: dict(u, v, idepth_new, iR, energy [n,2], outlierTH, isGood) -> dict(H, b, Hsc, bsc, res3, energy_new, isGood_new, maxstep,
+        lastHessian_new, JbBuffer_new)."""
+        T = _f64(refToNew34).reshape(12)
+        n = len(pts["u"])
+        i_ = {k: _f32(pts[k]) for k in ("u", "v", "idepth_new", "iR", "energy", "outlierTH")}
+        good = _u8(pts["isGood"])
+        o = dict(energy_new=np.zeros((n, 2), np.float32), isGood_new=np.zeros(n, np.uint8), maxstep=np.zeros(n, np.float32),
+                 lastHessian_new=_f32(pts.get("lastHessian_new", np.zeros(n))).copy(), JbBuffer_new=_f32(pts.get("JbBuffer_new", np.zeros((n, 10)))).copy())
+        ip = InitPoints(n=n, reserved0=0, u=_p(i_["u"], f32p), v=_p(i_["v"], f32p), idepth_new=_p(i_["idepth_new"], f32p), iR=_p(i_["iR"], f32p),
+                        energy=_p(i_["energy"], f32p), outlierTH=_p(i_["outlierTH"], f32p), isGood=_p(good, u8p), energy_new=_p(o["energy_new"], f32p),
+                        isGood_new=_p(o["isGood_new"], u8p), maxstep=_p(o["maxstep"], f32p), lastHessian_new=_p(o["lastHessian_new"], f32p),
+                        JbBuffer_new=_p(o["JbBuffer_new"], f32p))
+        H = np.zeros((8, 8), np.float32); b = np.zeros(8, np.float32); Hsc = np.zeros((8, 8), np.float32); bsc = np.zeros(8, np.float32)
+        r3 = np.zeros(3, np.float32)
+        a2 = (C.c_float * 2)(float(aff[0]), float(aff[1]))
+        t3 = (C.c_float * 3)(*[float(x) for x in tlog])
+        self._ck(self.lib.f("init_calc_res_and_gs")(self.h, C.c_int32(lvl), C.c_int32(ref_slot), C.c_int32(new_slot), _p(T, f64p), a2, t3,
+                                                    C.c_float(alphaW), C.c_float(alphaK), C.c_float(couplingWeight), C.byref(ip), _p(H, f32p), _p(b, f32p),
+                                                    _p(Hsc, f32p), _p(bsc, f32p), _p(r3, f32p)), "init_calc_res_and_gs")
+        o.update(H=H, b=b, Hsc=Hsc, bsc=bsc, res3=r3)
+        return o
 
     # ---- pixel selection (FullSystem/PixelSelector2.cpp)
     def pixel_selector_set(self, random_pattern, current_potential=3):

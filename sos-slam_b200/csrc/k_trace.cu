@@ -395,8 +395,149 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_optimize_immature(ActivateArg
   a.idepth[k] = currentIdepth;
 }
 
+
+// ---- initializer ----------------------------------------------------------------------------------
+//   k_init_res   CoarseInitializer::calcResAndGS   src/FullSystem/CoarseInitializer.cpp:450-673
+// One thread per Pnt: the 8 pattern taps in order (per-point outputs -- energy_new, isGood_new, maxstep, JbBuffer_new,
+// lastHessian_new -- are bit-exact), its 45 + 45 upper-triangle products for acc9 / acc9SC in registers, then a shuffle tree
+// and one fp64 red.global per entry per block (the reference's 4-lane float accumulators sum in a different order: H, b
+// agree to float rounding).  alphaOpt is known before the launch: the reference's EAlpha never receives a term (:606-617
+// add to E), so alphaEnergy = alphaW * |t|^2 * npts does not depend on the points.
+template <int NV> __device__ __forceinline__ void block_sum_to(float (&v)[NV], double *__restrict__ dst) {
+  __shared__ float s_part[4][NV];
+#pragma unroll
+  for (int q = 0; q < NV; q++)
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+#pragma unroll
+    for (int q = 0; q < NV; q++) s_part[warp][q] = v[q];
+  __syncthreads();
+  for (int q = threadIdx.x; q < NV; q += blockDim.x) {
+    double s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += (double)s_part[w][q];
+    if (s != 0.0) atomicAdd(dst + q, s);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) k_init_res(InitArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc[45];
+#pragma unroll
+  for (int q = 0; q < 45; q++) acc[q] = 0.f;
+  float Jb[10];
+#pragma unroll
+  for (int q = 0; q < 10; q++) Jb[q] = 0.f;
+  float E = 0.f;
+  bool good_new = false;
+  if (i < a.n) {
+    float maxstep_pt = 1e10f;
+    const float e0 = a.energy[2 * i], e1 = a.energy[2 * i + 1];
+    bool isGood = a.isGood[i] != 0;
+    float energy = 0.f;
+    if (isGood) {
+      const float pu = a.u[i], pv = a.v[i], idn = a.idepth_new[i];
+      for (int idx = 0; idx < 8; idx++) {
+        const int dx = t_pattern[idx][0], dy = t_pattern[idx][1];
+        const float x = pu + dx, y = pv + dy;
+        float pt[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) pt[k] = ((a.RKi[3 * k] * x + a.RKi[3 * k + 1] * y) + a.RKi[3 * k + 2] * 1.0f) + a.t[k] * idn;
+        const float u = pt[0] / pt[2], v = pt[1] / pt[2];
+        const float Ku = a.fx * u + a.cx, Kv = a.fy * v + a.cy;
+        const float new_idepth = idn / pt[2];
+        if (!(Ku > 1 && Kv > 1 && Ku < a.w - 2 && Kv < a.h - 2 && new_idepth > 0)) { isGood = false; break; }
+        const float3 hit = interp33(a.imgNew, Ku, Kv, a.w);
+        const float rlR = interp31(a.imgRef, x, y, a.w);
+        if (!isfinite(rlR) || !isfinite(hit.x)) { isGood = false; break; }
+        const float residual = hit.x - a.aff0 * rlR - a.aff1;
+        float hw = fabsf(residual) < a.huberTH ? 1 : a.huberTH / fabsf(residual);
+        energy += hw * residual * residual * (2 - hw);
+        const float dxdd = (a.t[0] - a.t[2] * u) / pt[2];
+        const float dydd = (a.t[1] - a.t[2] * v) / pt[2];
+        if (hw < 1) hw = sqrtf(hw);
+        const float dxInterp = hw * hit.y * a.fx, dyInterp = hw * hit.z * a.fy;
+        float J[9];
+        J[0] = new_idepth * dxInterp;
+        J[1] = new_idepth * dyInterp;
+        J[2] = -new_idepth * (u * dxInterp + v * dyInterp);
+        J[3] = -u * v * dxInterp - (1 + v * v) * dyInterp;
+        J[4] = (1 + u * u) * dxInterp + u * v * dyInterp;
+        J[5] = -v * dxInterp + u * dyInterp;
+        J[6] = -hw * a.aff0 * rlR;
+        J[7] = -hw * 1;
+        J[8] = hw * residual;
+        const float dd = dxInterp * dxdd + dyInterp * dydd;
+        const float mx = dxdd * a.fx, my = dydd * a.fy;
+        const float maxstep = 1.0f / sqrtf(mx * mx + my * my);
+        if (maxstep < maxstep_pt) maxstep_pt = maxstep;
+#pragma unroll
+        for (int k = 0; k < 8; k++) Jb[k] += J[k] * dd;
+        Jb[8] += J[8] * dd;
+        Jb[9] += dd * dd;
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < 9; r++)
+#pragma unroll
+          for (int c = r; c < 9; c++) acc[q++] += J[r] * J[c];
+      }
+    }
+    // (a point that was not good keeps a zero JbBuffer row only if it was good on entry: the reference zeroes the row after
+    // the isGood test, :485-499)
+    good_new = isGood && !(energy > a.outlierTH[i] * 20);
+    a.maxstep[i] = maxstep_pt;
+    a.isGood_new[i] = good_new ? 1 : 0;
+    if (good_new) {
+      E = energy;
+      a.energy_new[2 * i] = energy;
+      a.energy_new[2 * i + 1] = (a.idepth_new[i] - 1) * (a.idepth_new[i] - 1);
+    } else {
+      E = e0;
+      a.energy_new[2 * i] = e0; a.energy_new[2 * i + 1] = e1;
+#pragma unroll
+      for (int q = 0; q < 45; q++) acc[q] = 0.f;
+    }
+    if (a.isGood[i] != 0) {   // JbBuffer_new[i] before the Schur step
+      if (good_new) {
+        a.lastHessian_new[i] = Jb[9];
+        Jb[8] += a.alphaOpt * (a.idepth_new[i] - 1);
+        Jb[9] += a.alphaOpt;
+        if (a.alphaOpt == 0) {
+          Jb[8] += a.couplingWeight * (a.idepth_new[i] - a.iR[i]);
+          Jb[9] += a.couplingWeight;
+        }
+        Jb[9] = 1 / (1 + Jb[9]);
+      }
+#pragma unroll
+      for (int q = 0; q < 10; q++) a.Jb[10 * (size_t)i + q] = Jb[q];
+    }
+  }
+  block_sum_to<45>(acc, a.acc);
+  // acc9SC.updateSingleWeighted (MatrixAccumulators.h:1543-1660): diagonal (Jr * Jr) * w, then Jr *= w and Jc * Jr
+  {
+    int q = 0;
+    const float w = Jb[9];
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+      acc[q++] = good_new ? Jb[r] * Jb[r] * w : 0.f;
+      const float Jr = Jb[r] * w;
+#pragma unroll
+      for (int c = r + 1; c < 9; c++) acc[q++] = good_new ? Jb[c] * Jr : 0.f;
+    }
+  }
+  block_sum_to<45>(acc, a.acc + 45);
+  float e1v[1] = {E};
+  block_sum_to<1>(e1v, a.acc + 90);
+}
+
 }  // namespace
 
+void launch_init_res(sosba *h, const InitArgs &a) {
+  if (a.n == 0) return;
+  k_init_res<<<(a.n + 127) / 128, 128, 0, h->stream>>>(a);
+  h->launches++;
+}
 void launch_optimize_immature(sosba *h, const ActivateArgs &a) {
   if (a.n == 0) return;
   k_optimize_immature<<<(a.n + TRACE_PPB - 1) / TRACE_PPB, TRACE_THREADS, 0, h->stream>>>(a);

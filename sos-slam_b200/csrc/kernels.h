@@ -275,6 +275,18 @@ struct ActivateArgs {
   uint8_t *res_state;                  // [n * nf]
 };
 void launch_optimize_immature(sosba *h, const ActivateArgs &a);
+struct InitArgs {   // CoarseInitializer::calcResAndGS
+  int n, w, h;
+  const float4 *imgRef, *imgNew;   // level images of firstFrame / newFrame
+  float RKi[9], t[3];
+  float fx, fy, cx, cy, aff0 /* exp(a) */, aff1, huberTH, alphaOpt, couplingWeight;
+  const float *u, *v, *idepth_new, *iR, *energy, *outlierTH;
+  const uint8_t *isGood;
+  float *energy_new, *maxstep, *lastHessian_new, *Jb;
+  uint8_t *isGood_new;
+  double *acc;                      // [0..45) acc9, [45..90) acc9SC, [90] E.A
+};
+void launch_init_res(sosba *h, const InitArgs &a);
 void launch_immature_init(sosba *h, const TraceArgs &a);
 void launch_trace_on(sosba *h, const TraceArgs &a);
 

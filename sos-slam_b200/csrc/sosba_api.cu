@@ -71,6 +71,8 @@ struct HostSide {
   int *d_sel_int = nullptr;            // totals[8] | chunk_cnt | chunk_off | cnt A | cnt B | base
   int2 *d_sel_list = nullptr;
   int2 *pin_sel_list = nullptr;        // pinned mirror of the first SEL_LIST_FAST entries + totals
+  float *d_init = nullptr;      // CoarseInitializer points of one level (sosba_init_calc_res_and_gs) + 91 fp64 sums
+  size_t init_cap = 0;
   float *d_act = nullptr;       // activation outputs: [idepth n floats][result n bytes][res_state n*nf bytes]
   size_t act_cap = 0;
   float *d_act_win = nullptr;   // PRE_RTll / PRE_tTll / PRE_aff_mode per frame pair
@@ -1936,5 +1938,95 @@ API int sosba_pixel_select(sosba_t *h, int32_t slot, float density, int32_t recu
   hs->sel_pot = idealPotential;
   if (n_selected) *n_selected = numHaveSub;
   if (current_potential) *current_potential = hs->sel_pot;
+  return SOSBA_OK;
+}
+
+// ---- 8f rank 4, second half: CoarseInitializer::calcResAndGS (CoarseInitializer.cpp:450-673) ----------------------
+API int sosba_init_calc_res_and_gs(sosba_t *h, int32_t lvl, int32_t ref_slot, int32_t new_slot, const double refToNew[12], const float aff[2],
+                                   const float tlog[3], float alphaW, float alphaK, float couplingWeight, sosba_init_points *pts, float H[64], float b[8],
+                                   float Hsc[64], float bsc[8], float res3[3]) {
+  CHECK_H(h);
+  HostSide *hs = HS(h);
+  if (!h->t_haveK) { sosba_set_error("tracker_make_k first"); return SOSBA_E_STATE; }
+  auto bad = [&](int s) { return s < 0 || s >= (int)h->slot_img.size() || !h->slot_valid[s]; };
+  if (lvl < 0 || lvl >= h->levels || bad(ref_slot) || bad(new_slot) || !refToNew || !aff || !tlog || !pts || pts->n < 0 || !H || !b || !Hsc || !bsc || !res3) {
+    sosba_set_error("init_calc_res_and_gs: bad arguments");
+    return SOSBA_E_ARG;
+  }
+  const int n = pts->n;
+  if (n > 0 && (!pts->u || !pts->v || !pts->idepth_new || !pts->iR || !pts->energy || !pts->outlierTH || !pts->isGood || !pts->energy_new ||
+                !pts->isGood_new || !pts->maxstep || !pts->lastHessian_new || !pts->JbBuffer_new)) {
+    sosba_set_error("null buffer");
+    return SOSBA_E_ARG;
+  }
+  for (int i = 0; i < n; i++)   // the reference tap of firstFrame reads (u + dx, v + dy) .. +1 without a bounds test (:518-519)
+    if (!(pts->u[i] >= 2 && pts->v[i] >= 2 && pts->u[i] < h->wl[lvl] - 3 && pts->v[i] < h->hl[lvl] - 3)) { sosba_set_error("point %d outside the pattern margin", i); return SOSBA_E_ARG; }
+  int rc;
+  const size_t N = ((size_t)n + 63) & ~(size_t)63;
+  // arena (floats): in [u][v][idepth_new][iR][energy 2][outlierTH][isGood (bytes, N)] | out [energy_new 2][maxstep][lastHessian_new][Jb 10][isGood_new (bytes)] | 91 doubles
+  const size_t in_f = 7 * N + N / 4, out_f = 14 * N + N / 4, total_f = in_f + out_f + 2 * 92;
+  if (total_f > hs->init_cap) {
+    dfree(h, hs->d_init);
+    hs->init_cap = total_f + total_f / 4;
+    DALLOC(h, hs->d_init, hs->init_cap);
+  }
+  float *d = hs->d_init;
+  float *d_out = d + in_f;
+  double *d_acc = (double *)(d + in_f + out_f);
+  InitArgs a = {};
+  a.n = n; a.w = h->wl[lvl]; a.h = h->hl[lvl];
+  a.imgRef = h->slot_img[ref_slot] + h->lvl_off[lvl]; a.imgNew = h->slot_img[new_slot] + h->lvl_off[lvl];
+  float R[9], Ki[9];
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) R[3 * i + j] = (float)refToNew[4 * i + j]; a.t[i] = (float)refToNew[4 * i + 3]; }
+  make_Ki(h->t_K[lvl], Ki);
+  mul33f(R, Ki, a.RKi);
+  a.fx = h->t_K[lvl][0]; a.fy = h->t_K[lvl][1]; a.cx = h->t_K[lvl][2]; a.cy = h->t_K[lvl][3];
+  a.aff0 = (float)exp((double)aff[0]); a.aff1 = aff[1]; a.huberTH = h->cfg.huber_th; a.couplingWeight = couplingWeight;
+  // alpha energy (:618-630): EAlpha stays empty in the reference, so the decision depends on the translation only
+  const double tsq = refToNew[3] * refToNew[3] + refToNew[7] * refToNew[7] + refToNew[11] * refToNew[11];
+  float alphaEnergy = alphaW * (0.f + tsq * n);
+  float alphaOpt;
+  if (alphaEnergy > alphaK * n) { alphaOpt = 0; alphaEnergy = alphaK * n; }
+  else alphaOpt = alphaW;
+  a.alphaOpt = alphaOpt;
+  a.u = d; a.v = d + N; a.idepth_new = d + 2 * N; a.iR = d + 3 * N; a.energy = d + 4 * N; a.outlierTH = d + 6 * N; a.isGood = (const uint8_t *)(d + 7 * N);
+  a.energy_new = d_out; a.maxstep = d_out + 2 * N; a.lastHessian_new = d_out + 3 * N; a.Jb = d_out + 4 * N; a.isGood_new = (uint8_t *)(d_out + 14 * N);
+  a.acc = d_acc;
+  if (n > 0) {
+    const size_t in_bytes = in_f * 4, out_bytes = out_f * 4;
+    if (in_bytes + out_bytes > hs->stage_cap / 2) { sosba_set_error("too many initializer points"); return SOSBA_E_ARG; }
+    char *blk;
+    if ((rc = stage_reserve(h, in_bytes + out_bytes, &blk))) return rc;
+    float *sf = (float *)blk;
+    memcpy(sf, pts->u, 4 * (size_t)n); memcpy(sf + N, pts->v, 4 * (size_t)n); memcpy(sf + 2 * N, pts->idepth_new, 4 * (size_t)n);
+    memcpy(sf + 3 * N, pts->iR, 4 * (size_t)n); memcpy(sf + 4 * N, pts->energy, 8 * (size_t)n); memcpy(sf + 6 * N, pts->outlierTH, 4 * (size_t)n);
+    memcpy(sf + 7 * N, pts->isGood, (size_t)n);
+    // in/out members the kernel only partly rewrites: lastHessian_new and JbBuffer_new keep the caller's values for rejected points
+    float *so = sf + in_f;
+    memcpy(so + 3 * N, pts->lastHessian_new, 4 * (size_t)n); memcpy(so + 4 * N, pts->JbBuffer_new, 40 * (size_t)n);
+    SOSBA_CUDA(cudaMemcpyAsync(d, sf, in_bytes + out_bytes, cudaMemcpyHostToDevice, h->stream));
+    SOSBA_CUDA(cudaMemsetAsync(d_acc, 0, 92 * sizeof(double), h->stream));
+    launch_init_res(h, a);
+    SOSBA_CUDA(cudaGetLastError());
+    SOSBA_CUDA(cudaMemcpyAsync(so, d_out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = down(h, hs->pin_d, (const double *)d_acc, 91))) return rc;
+    if ((rc = sync(h))) return rc;
+    memcpy(pts->energy_new, so, 8 * (size_t)n); memcpy(pts->maxstep, so + 2 * N, 4 * (size_t)n); memcpy(pts->lastHessian_new, so + 3 * N, 4 * (size_t)n);
+    memcpy(pts->JbBuffer_new, so + 4 * N, 40 * (size_t)n); memcpy(pts->isGood_new, so + 14 * N, (size_t)n);
+  } else {
+    for (int i = 0; i < 91; i++) hs->pin_d[i] = 0;
+  }
+  float A[2][9][9];
+  for (int m = 0; m < 2; m++) {
+    int q = 45 * m;
+    for (int r = 0; r < 9; r++) for (int c = r; c < 9; c++) { A[m][r][c] = A[m][c][r] = (float)hs->pin_d[q++]; }
+  }
+  for (int r = 0; r < 8; r++) {
+    for (int c = 0; c < 8; c++) { H[8 * r + c] = A[0][r][c]; Hsc[8 * r + c] = A[1][r][c]; }
+    b[r] = A[0][r][8]; bsc[r] = A[1][r][8];
+  }
+  H[0] += alphaOpt * n; H[9] += alphaOpt * n; H[18] += alphaOpt * n;
+  b[0] += tlog[0] * alphaOpt * n; b[1] += tlog[1] * alphaOpt * n; b[2] += tlog[2] * alphaOpt * n;
+  res3[0] = (float)hs->pin_d[90]; res3[1] = alphaEnergy; res3[2] = (float)(2 * (size_t)n);   // E.num: both loops update E (:606-617)
   return SOSBA_OK;
 }

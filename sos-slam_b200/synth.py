@@ -395,3 +395,17 @@ def loop_case(scene: Scene, matched: int, levels: int, level_images, n: int = 30
         dxdy = dx * dy
         color[:, l] = dxdy * img[iy + 1, ix + 1] + (dy - dxdy) * img[iy + 1, ix] + (dx - dxdy) * img[iy, ix + 1] + (1 - dx - dy + dxdy) * img[iy, ix]
     return dict(xyz=xyz, color=color)
+
+
+def init_case(scene: Scene, lvl: int, n: int = 2500, seed: int = 13):
+    """CoarseInitializer::Pnt arrays of one level in the state trackFrame leaves them between iterations: integer pixels of
+    the first frame (level coordinates), inverse depths around 1 (the initializer's normalisation), some points already
+    marked bad.  -> dict(u, v, idepth_new, iR, energy [n,2], outlierTH, isGood)."""
+    rng = np.random.default_rng(seed)
+    wl, hl = scene.w >> lvl, scene.h >> lvl
+    u = rng.integers(5, wl - 6, n).astype(np.float32)
+    v = rng.integers(5, hl - 6, n).astype(np.float32)
+    return dict(u=u, v=v, idepth_new=rng.uniform(0.7, 1.3, n).astype(np.float32), iR=rng.uniform(0.8, 1.2, n).astype(np.float32),
+                energy=np.stack([rng.uniform(0, 400, n), rng.uniform(0, 0.1, n)], 1).astype(np.float32),
+                outlierTH=np.full(n, 8 * 12 * 12, np.float32) * rng.choice([1.0, 0.02], n, p=[0.9, 0.1]).astype(np.float32),
+                isGood=(rng.uniform(0, 1, n) > 0.1).astype(np.uint8))

@@ -854,3 +854,87 @@ def sel_make_maps_ref(dI0, absg, random_pattern, potential, density, recursions_
         flat[nz[drop]] = 0
         sub -= int(drop.sum())
     return m, sub, ideal
+
+
+# ---- CoarseInitializer::calcResAndGS (second half) -----------------------------------
+def init_calc_res_and_gs_ref(dIref, dInew, K_lvl, refToNew, aff, tlog, pts, alphaW=F(150 * 150), alphaK=F(2.5 * 2.5), coupling=F(1), huber=F(9)):
+    """CoarseInitializer.cpp:450-673, vectorised over the points (the pattern loop stays sequential, a per-point `alive` mask
+    plays the role of `break`).  Per-point outputs in float32 with the reference's expression order; H, b in float64."""
+    h, w = dInew.shape[:2]
+    fx, fy, cx, cy = [F(x) for x in K_lvl]
+    T = np.asarray(refToNew, np.float64)
+    R = T[:3, :3].astype(F); t = T[:3, 3].astype(F)
+    Ki = np.array([[F(1) / fx, 0, -cx / fx], [0, F(1) / fy, -cy / fy], [0, 0, 1]], F)
+    RKi = np.zeros((3, 3), F)
+    for i in range(3):
+        for j in range(3):
+            RKi[i, j] = (R[i, 0] * Ki[0, j] + R[i, 1] * Ki[1, j]) + R[i, 2] * Ki[2, j]
+    a0, a1 = F(np.exp(np.float64(F(aff[0])))), F(aff[1])
+    u0, v0, idn = [np.asarray(pts[k], F) for k in ("u", "v", "idepth_new")]
+    n = len(u0)
+    good_in = np.asarray(pts["isGood"]).astype(bool)
+    alive = good_in.copy()
+    energy = np.zeros(n, F); maxstep = np.full(n, F(1e10), F)
+    Jb = np.zeros((n, 10), F)
+    Jall = np.zeros((n, 8, 9), F)
+    with np.errstate(all="ignore"):
+        for idx, (px, py) in enumerate(PATTERN):
+            x = u0 + F(px); y = v0 + F(py)
+            pt = [((RKi[k, 0] * x + RKi[k, 1] * y) + RKi[k, 2]) + t[k] * idn for k in range(3)]
+            uu, vv = pt[0] / pt[2], pt[1] / pt[2]
+            Ku, Kv = fx * uu + cx, fy * vv + cy
+            nid = idn / pt[2]
+            ok = (Ku > 1) & (Kv > 1) & (Ku < w - 2) & (Kv < h - 2) & (nid > 0)
+            hit = _bilin(dInew, np.where(ok, Ku, F(2)), np.where(ok, Kv, F(2)))
+            rl = _bilin(dIref, x, y)[:, 0]
+            ok &= np.isfinite(rl) & np.isfinite(hit[:, 0])
+            alive &= ok
+            res = hit[:, 0] - a0 * rl - a1
+            hw = np.where(np.abs(res) < huber, F(1), huber / np.abs(res)).astype(F)
+            energy = np.where(alive, energy + hw * res * res * (F(2) - hw), energy).astype(F)
+            dxdd = (t[0] - t[2] * uu) / pt[2]; dydd = (t[1] - t[2] * vv) / pt[2]
+            hw = np.where(hw < 1, np.sqrt(hw), hw).astype(F)
+            dxi = hw * hit[:, 1] * fx; dyi = hw * hit[:, 2] * fy
+            J = np.stack([nid * dxi, nid * dyi, -nid * (uu * dxi + vv * dyi), -uu * vv * dxi - (F(1) + vv * vv) * dyi,
+                          (F(1) + uu * uu) * dxi + uu * vv * dyi, -vv * dxi + uu * dyi, -hw * a0 * rl, -hw * F(1), hw * res], 1).astype(F)
+            dd = (dxi * dxdd + dyi * dydd).astype(F)
+            mx = dxdd * fx; my = dydd * fy
+            ms = F(1) / np.sqrt(mx * mx + my * my)
+            maxstep = np.where(alive & (ms < maxstep), ms, maxstep).astype(F)
+            upd = np.concatenate([J[:, :8] * dd[:, None], (J[:, 8] * dd)[:, None], (dd * dd)[:, None]], 1).astype(F)
+            Jb = np.where(alive[:, None], Jb + upd, Jb).astype(F)
+            Jall[:, idx] = np.where(alive[:, None], J, 0)
+    en_in = np.asarray(pts["energy"], F).reshape(n, 2)
+    good = alive & ~(energy > np.asarray(pts["outlierTH"], F) * F(20))
+    energy_new = en_in.copy()
+    energy_new[good, 0] = energy[good]
+    energy_new[good, 1] = ((idn - F(1)) * (idn - F(1)))[good]
+    E = float(np.sum(np.where(good, energy, en_in[:, 0]).astype(np.float64)))
+    Jg = Jall[good].astype(np.float64).reshape(-1, 9)
+    A = Jg.T @ Jg
+    tsq = float(T[0, 3] ** 2 + T[1, 3] ** 2 + T[2, 3] ** 2)
+    alphaEnergy = F(alphaW * (0.0 + tsq * n))
+    if alphaEnergy > alphaK * n:
+        alphaOpt, alphaEnergy = F(0), F(alphaK * n)
+    else:
+        alphaOpt = F(alphaW)
+    lastH = np.asarray(pts.get("lastHessian_new", np.zeros(n)), F).copy()
+    lastH[good] = Jb[good, 9]
+    Jb2 = Jb.copy()
+    iR = np.asarray(pts["iR"], F)
+    Jb2[:, 8] = Jb2[:, 8] + alphaOpt * (idn - F(1))
+    Jb2[:, 9] = Jb2[:, 9] + alphaOpt
+    if alphaOpt == 0:
+        Jb2[:, 8] = Jb2[:, 8] + coupling * (idn - iR)
+        Jb2[:, 9] = Jb2[:, 9] + coupling
+    Jb2[:, 9] = F(1) / (F(1) + Jb2[:, 9])
+    Jb_out = np.where(good[:, None], Jb2, Jb).astype(F)
+    Jb_out[~good_in] = np.asarray(pts.get("JbBuffer_new", np.zeros((n, 10))), F)[~good_in]
+    Js = Jb2[good].astype(np.float64)
+    Asc = (Js[:, :9] * Js[:, 9:10]).T @ Js[:, :9]
+    H = A[:8, :8].copy(); b = A[:8, 8].copy()
+    for k in range(3):
+        H[k, k] += float(alphaOpt) * n
+        b[k] += float(tlog[k]) * float(alphaOpt) * n
+    return dict(H=H, b=b, Hsc=Asc[:8, :8], bsc=Asc[:8, 8], res3=np.array([E, alphaEnergy, 2 * n]), energy_new=energy_new, isGood_new=good.astype(np.uint8),
+                maxstep=maxstep, lastHessian_new=lastH, JbBuffer_new=Jb_out)

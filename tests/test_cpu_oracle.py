@@ -602,3 +602,38 @@ def test_pixel_make_maps_vs_numpy(orc, density, pot0):
     assert np.array_equal(got["map"], ref)
     assert got["n"] == int(np.count_nonzero(ref)) == got["u"].size
     h.close()
+
+
+# ---- next row (second half): CoarseInitializer::calcResAndGS ----------------------
+def _init_setup(lib, sc, big_t):
+    from sos_slam_b200 import synth
+    h = open_handle(lib, sc)
+    h.tracker_make_k(sc.K.astype(np.float32))
+    xi = np.array([0.002, -0.001, 0.0015, 0.0004, -0.0006, 0.0003]) * (40.0 if big_t else 1.0)
+    T = synth.se3_exp(xi)[:3, :4]
+    return h, T, xi[:3].astype(np.float32)
+
+
+@pytest.mark.parametrize("big_t", [False, True], ids=["alphaW", "alphaOpt0"])
+def test_init_calc_res_and_gs_vs_numpy(orc, big_t):
+    """CoarseInitializer::calcResAndGS (CoarseInitializer.cpp:450-673) on every level, in both regimes of the alpha energy
+    (small translation: alphaOpt = alphaW; large: alphaOpt = 0 + coupling to iR): per-point outputs bit for bit against the
+    numpy restatement, H / b / Hsc / bsc / E to float summation accuracy."""
+    from sos_slam_b200 import synth
+    sc = scene(**SMALLC)
+    h, T, tlog = _init_setup(orc, sc, big_t)
+    for lvl in range(h.levels):
+        pts = synth.init_case(sc, lvl, n=1200 >> lvl)
+        got = h.init_calc_res_and_gs(lvl, 0, 1, T, (0.02, -1.0), tlog, pts)
+        Kl = np.array([sc.K[0] / (1 << lvl), sc.K[1] / (1 << lvl), (sc.K[2] + 0.5) / (1 << lvl) - 0.5, (sc.K[3] + 0.5) / (1 << lvl) - 0.5], np.float32)
+        dIr = np.asarray(h.frame_get_level(0, lvl)[0], np.float32).reshape(sc.h >> lvl, sc.w >> lvl, 3)
+        dIn = np.asarray(h.frame_get_level(1, lvl)[0], np.float32).reshape(sc.h >> lvl, sc.w >> lvl, 3)
+        ref = np_ref.init_calc_res_and_gs_ref(dIr, dIn, Kl, T, (0.02, -1.0), tlog, pts)
+        for k in ("isGood_new", "energy_new", "maxstep", "lastHessian_new", "JbBuffer_new"):
+            assert np.array_equal(got[k], ref[k]), (lvl, k, int(np.sum(got[k] != ref[k])))
+        for k in ("H", "b", "Hsc", "bsc"):
+            assert relerr(got[k], ref[k]) < 2e-5, (lvl, k, relerr(got[k], ref[k]))
+        np.testing.assert_allclose(got["res3"], ref["res3"], rtol=2e-5)
+        assert (got["res3"][1] == 6.25 * len(pts["u"])) == big_t
+        assert 0.3 < got["isGood_new"].mean() < 0.95
+    h.close()

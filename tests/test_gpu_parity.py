@@ -461,3 +461,38 @@ def test_pixel_select_degenerate_directions(gpu, orc, kind):
         assert g["n"] == o["n"] and g["potential"] == o["potential"], (g["n"], o["n"])
         assert np.array_equal(g["map"], o["map"]), int(np.sum(g["map"] != o["map"]))
     assert outs[0][0]["n"] > (500 if kind == "mixed" else 0)
+
+
+# ---- next row (second half): CoarseInitializer::calcResAndGS ---------------------
+@pytest.mark.parametrize("big_t", [False, True], ids=["alphaW", "alphaOpt0"])
+@pytest.mark.parametrize("cfg", [SMALL, CONFIG_B], ids=["small", "configB"])
+def test_init_calc_res_and_gs(gpu, orc, cfg, big_t):
+    """CoarseInitializer::calcResAndGS (CoarseInitializer.cpp:450-673) on every level, both alpha regimes: the per-point
+    outputs (isGood_new, energy_new, maxstep, lastHessian_new, JbBuffer_new) bit for bit, H / b / Hsc / bsc 1e-4, E 2e-5."""
+    from sos_slam_b200 import binding, synth
+    sc = scene(**cfg)
+    xi = np.array([0.002, -0.001, 0.0015, 0.0004, -0.0006, 0.0003]) * (40.0 if big_t else 1.0)
+    T = synth.se3_exp(xi)[:3, :4]
+    tlog = xi[:3].astype(np.float32)
+    hs = []
+    for lib in (gpu, orc):
+        h = open_handle(lib, sc)
+        h.tracker_make_k(sc.K.astype(np.float32))
+        hs.append(h)
+    hg, ho = hs
+    for lvl in range(hg.levels):
+        pts = synth.init_case(sc, lvl, n=max(100, 9000 >> (2 * lvl)))
+        pts["JbBuffer_new"] = np.full((len(pts["u"]), 10), 0.25, np.float32)      # rows of points that are bad on entry must survive
+        pts["lastHessian_new"] = np.full(len(pts["u"]), 3.0, np.float32)
+        g = hg.init_calc_res_and_gs(lvl, 0, 1, T, (0.02, -1.0), tlog, pts)
+        o = ho.init_calc_res_and_gs(lvl, 0, 1, T, (0.02, -1.0), tlog, pts)
+        for k in ("isGood_new", "energy_new", "maxstep", "lastHessian_new", "JbBuffer_new"):
+            assert np.array_equal(g[k], o[k]), (lvl, k, int(np.sum(g[k] != o[k])))
+        for k in ("H", "b", "Hsc", "bsc"):
+            assert relerr(g[k], o[k]) < 1e-4, (lvl, k, relerr(g[k], o[k]))
+        assert np.allclose(g["res3"], o["res3"], rtol=2e-5)
+        assert np.all(g["JbBuffer_new"][pts["isGood"] == 0] == 0.25) and 0.3 < g["isGood_new"].mean() < 0.95
+    with pytest.raises(binding.SosbaError):
+        bad = dict(pts); bad["u"] = pts["u"].copy(); bad["u"][0] = 0.0
+        hg.init_calc_res_and_gs(0, 0, 1, T, (0.0, 0.0), tlog, bad)
+    hg.close(); ho.close()

@@ -192,6 +192,10 @@ struct SolveArgs {
   const int *res_in;           // resInA of the accumulation this solve consumes ...
   int *res_out;                // ... copied where the table clearing of the next linearisation does not reach
   double *zero_rstats;         // non-null: clear the 4 back-substitution sums the following k_resubstitute accumulates into
+  // point shards: setNewFrameEnergyTH of the previous linearisation (its energies arrived with the all-reduce in front of
+  // this launch) runs in a second CTA beside the solve instead of as a launch of its own
+  ThArgs th;
+  int do_th;
 };
 int launch_solve(sosba *h, const SolveArgs &a);
 

@@ -939,7 +939,9 @@ static SCArgs sc_args(sosba *h, int mode, const int *plist, int n_plist, int shi
 
 // the block tables of accumulateAF_MT / accumulateLF_MT / accumulateSCF_MT (EnergyFunctional.cpp:197-254):
 // one memset, top blocks (A, and L when linearised residuals exist), per-point sums + Schur Gram, all-reduce
-static int enqueue_blocks(sosba *h) {
+// defer_th (point shards, loop path): the caller runs the pending setNewFrameEnergyTH in the spare CTA of its k_solve launch
+static int enqueue_blocks(sosba *h, ThArgs *defer_th = nullptr, int *deferred = nullptr) {
+  if (deferred) *deferred = 0;
   HostSide *hs = HS(h);
   const int nf = h->nf;
   const size_t n2 = (size_t)nf * nf;
@@ -987,7 +989,13 @@ static int enqueue_blocks(sosba *h) {
   int th_done = 0;
   int rc = sosba_allreduce_acc(h, shard_th ? 1 : 0, hs->gate, hs->gate ? hs->d_ctl + 2 : nullptr, shard_th ? &th : nullptr, &th_done);
   if (rc) return rc;
-  if (shard_th) { if (!th_done) launch_energy_th(h, th, hs->gate); hs->th_pending = false; }
+  if (shard_th) {
+    if (!th_done) {
+      if (defer_th) { *defer_th = th; *deferred = 1; }
+      else launch_energy_th(h, th, hs->gate);
+    }
+    hs->th_pending = false;
+  }
   return SOSBA_OK;
 }
 
@@ -1048,10 +1056,13 @@ static StepArgs step_args(sosba *h) {
 static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int do_step, bool want_final = false) {
   HostSide *hs = HS(h);
   const int nf = h->nf, D = 4 + 8 * nf;
-  int rc = enqueue_blocks(h);
+  ThArgs th_def = {};
+  int th_deferred = 0;
+  int rc = enqueue_blocks(h, &th_def, &th_deferred);
   if (rc) return rc;
   launch_stitch_raw(h, h->d_accTop, h->d_adHost, h->d_adTarget, nf, hs->n_lin > 0 ? 2 : 1, Hpart(h, 0), bpart(h, 0));
   SolveArgs s;
+  s.th = th_def; s.do_th = th_deferred;
   s.nf = nf; s.D = D;
   s.Htop = Hpart(h, 0); s.btop = bpart(h, 0); s.accSC = h->d_accSC;
   s.HM = d_HM; s.bM = d_bM; s.wprior = h->d_wprior; s.cDeltaF = h->d_calib + 6;

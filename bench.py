@@ -425,6 +425,16 @@ def main():
                 t0 = time.perf_counter()
                 trace_counts = h.trace_immature(sc.nf - 1, case["host"], case["KRKi"], case["Kt"], case["aff"], ipc)
                 trace_ms.append(1e3 * (time.perf_counter() - t0))
+            # the same trace with the points resident in HBM (sosba_immature_pool_*): only the per-host tables go up
+            h.immature_pool_set(case["host"], {k: x.copy() for k, x in ip.items()})
+            h.immature_pool_trace(sc.nf - 1, case["KRKi"], case["Kt"], case["aff"])
+            pool_ms = []
+            for _ in range(5):
+                h.immature_pool_set(case["host"], {k: x.copy() for k, x in ip.items()})
+                h.synchronize()
+                t0 = time.perf_counter()
+                h.immature_pool_trace(sc.nf - 1, case["KRKi"], case["Kt"], case["aff"])
+                pool_ms.append(1e3 * (time.perf_counter() - t0))
             okp = np.isfinite(ipc["idepth_max"])
             sub = {k: x[okp] for k, x in ipc.items()}
             win = synth.activation_case(sc)
@@ -437,7 +447,7 @@ def main():
                      "optimize_immature_activated": int((act[0] == 1).sum()), "pixel_select_ms": float(np.median(sel_ms)), "pixel_select_n": int(sel["n"]), "make_images_raw_ms": raw_ms,
                      "make_images_raw_note": f"{uc['w_org']}x{uc['h_org']} 8-bit raw frame in: H2D + response/vignette + rectification + 4 levels, host wall per call",
                      "make_images_ms": pyr_ms, "make_images_note": f"{sc.w}x{sc.h}, H2D + 4 levels, host wall per call",
-                     "trace_immature_ms": float(np.median(trace_ms)), "trace_immature_points": int(case["host"].size),
+                     "trace_immature_ms": float(np.median(trace_ms)), "trace_immature_resident_ms": float(np.median(pool_ms)), "trace_immature_points": int(case["host"].size),
                      "trace_immature_counts": [int(x) for x in trace_counts],
                      "trace_note": "first trace (unbounded interval: the longest epipolar search), host SoA in and out, host wall per call",
                      "tracker_calcRes_plus_calcGS_ms": trk_ms, "scale_calcRes_plus_calcGS_ms": scl_ms,

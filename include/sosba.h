@@ -349,6 +349,15 @@ int sosba_immature_init(sosba_t *h, int32_t host_slot, int32_t n, const int32_t 
 int sosba_trace_immature(sosba_t *h, int32_t frame_slot, int32_t nhosts, const float *KRKi, const float *Kt, const float *aff,
                          sosba_immature *pts, int32_t counts[6]);
 
+/* Resident variant: immature points live for many frames and only the traced-into frame changes, so the pool stays in HBM.
+ * pool_set uploads every member of `pts` once (after makeNewTraces / whenever the host adds or deletes points),
+ * pool_trace runs traceNewCoarse on it in place (per call: 14 floats per host up, 6 counters down), pool_get reads the
+ * in/out members (idepth_min/max, quality, last_trace_status / uv / pixel_interval) back into `pts` when the host needs
+ * them (activatePointsMT).  pts->n of pool_get must equal the pool size. */
+int sosba_immature_pool_set(sosba_t *h, const sosba_immature *pts);
+int sosba_immature_pool_trace(sosba_t *h, int32_t frame_slot, int32_t nhosts, const float *KRKi, const float *Kt, const float *aff, int32_t counts[6]);
+int sosba_immature_pool_get(sosba_t *h, sosba_immature *pts);
+
 /* The frame pairs of the window as FullSystem::activatePointsMT sees them (FullSystem.cpp:377-505): per (host, target)
  * FrameFramePrecalc::PRE_RTll / PRE_tTll / PRE_aff_mode (HessianBlocks.cpp:184-214), row (host * nf + target). */
 typedef struct sosba_activation_window {

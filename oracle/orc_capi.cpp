@@ -7,6 +7,8 @@
 #include <new>
 
 #include "orc_core.h"
+#include <map>
+
 #include "orc_host.h"
 
 using namespace orc;
@@ -508,5 +510,48 @@ ORC_API int orc_init_calc_res_and_gs(orc_handle *h, int32_t lvl, int32_t ref_slo
   auto bad = [&](int s) { return s < 0 || s >= (int)o.slots.size() || !o.slots[s].valid; };
   if (lvl < 0 || lvl >= o.levels || bad(ref_slot) || bad(new_slot) || !refToNew || !aff || !tlog || !pts || pts->n < 0) return SOSBA_E_ARG;
   init_calcResAndGS(o, lvl, ref_slot, new_slot, refToNew, aff, tlog, alphaW, alphaK, couplingWeight, pts, H, b, Hsc, bsc, res3);
+  return SOSBA_OK;
+}
+
+// resident pool: the CPU side simply keeps a copy of the arrays
+struct OrcPool {
+  std::vector<int32_t> host;
+  std::vector<float> u, v, color, weights, gradH, eth, idmin, idmax, quality, uv, pixint;
+  std::vector<uint8_t> status;
+};
+static std::map<orc_handle *, OrcPool> g_pools;
+static sosba_immature pool_view(OrcPool &p) {
+  sosba_immature m = {};
+  m.n = (int32_t)p.host.size(); m.host = p.host.data(); m.u = p.u.data(); m.v = p.v.data(); m.color = p.color.data(); m.weights = p.weights.data();
+  m.gradH = p.gradH.data(); m.energy_th = p.eth.data(); m.idepth_min = p.idmin.data(); m.idepth_max = p.idmax.data(); m.quality = p.quality.data();
+  m.last_trace_status = p.status.data(); m.last_trace_uv = p.uv.data(); m.last_trace_pixel_interval = p.pixint.data();
+  return m;
+}
+ORC_API int orc_immature_pool_set(orc_handle *h, const sosba_immature *pts) {
+  if (!pts || pts->n < 0) return SOSBA_E_ARG;
+  OrcPool &p = g_pools[h];
+  const size_t n = pts->n;
+  p.host.assign(pts->host, pts->host + n); p.u.assign(pts->u, pts->u + n); p.v.assign(pts->v, pts->v + n);
+  p.color.assign(pts->color, pts->color + 8 * n); p.weights.assign(pts->weights, pts->weights + 8 * n); p.gradH.assign(pts->gradH, pts->gradH + 4 * n);
+  p.eth.assign(pts->energy_th, pts->energy_th + n); p.idmin.assign(pts->idepth_min, pts->idepth_min + n); p.idmax.assign(pts->idepth_max, pts->idepth_max + n);
+  p.quality.assign(pts->quality, pts->quality + n); p.status.assign(pts->last_trace_status, pts->last_trace_status + n);
+  p.uv.assign(pts->last_trace_uv, pts->last_trace_uv + 2 * n); p.pixint.assign(pts->last_trace_pixel_interval, pts->last_trace_pixel_interval + n);
+  return SOSBA_OK;
+}
+ORC_API int orc_immature_pool_trace(orc_handle *h, int32_t frame_slot, int32_t nhosts, const float *KRKi, const float *Kt, const float *aff, int32_t counts[6]) {
+  auto it = g_pools.find(h);
+  if (it == g_pools.end()) return SOSBA_E_STATE;
+  sosba_immature m = pool_view(it->second);
+  return orc_trace_immature(h, frame_slot, nhosts, KRKi, Kt, aff, &m, counts);
+}
+ORC_API int orc_immature_pool_get(orc_handle *h, sosba_immature *pts) {
+  auto it = g_pools.find(h);
+  if (it == g_pools.end()) return SOSBA_E_STATE;
+  OrcPool &p = it->second;
+  const size_t n = p.host.size();
+  if (!pts || (size_t)pts->n != n) return SOSBA_E_ARG;
+  memcpy(pts->idepth_min, p.idmin.data(), 4 * n); memcpy(pts->idepth_max, p.idmax.data(), 4 * n); memcpy(pts->quality, p.quality.data(), 4 * n);
+  memcpy(pts->last_trace_status, p.status.data(), n); memcpy(pts->last_trace_uv, p.uv.data(), 8 * n);
+  memcpy(pts->last_trace_pixel_interval, p.pixint.data(), 4 * n);
   return SOSBA_OK;
 }

@@ -150,7 +150,7 @@ class Lib:
                   "accumulate", "points_get_acc", "solve_system", "resubstitute", "marginalize_points",
                   "tracker_make_k", "tracker_set_ref", "tracker_calc_res_pose", "tracker_calc_gs_pose",
                   "scale_set_stereo", "scale_calc_res", "scale_calc_gs", "optimize", "ba_upload", "ba_iterate",
-                  "ba_download", "ba_optimize", "pyr_levels", "immature_init", "trace_immature", "optimize_immature", "undistort_set", "frame_make_images_raw", "loop_set_points", "loop_calc_res", "loop_calc_gs", "pixel_selector_set", "pixel_select", "init_calc_res_and_gs"):
+                  "ba_download", "ba_optimize", "pyr_levels", "immature_init", "trace_immature", "optimize_immature", "undistort_set", "frame_make_images_raw", "loop_set_points", "loop_calc_res", "loop_calc_gs", "pixel_selector_set", "pixel_select", "init_calc_res_and_gs", "immature_pool_set", "immature_pool_trace", "immature_pool_get"):
             self.f(n).restype = C.c_int
         self.f("destroy").restype = None
         if self.has("launch_count"):
@@ -520,6 +520,34 @@ class Handle:
         self._ck(self.lib.f("trace_immature")(self.h, C.c_int32(frame_slot), C.c_int32(KRKi.size // 9), _p(KRKi, f32p), _p(Kt, f32p), _p(aff, f32p),
                                               C.byref(ip), _p(counts, i32p)), "trace_immature")
         return counts
+
+    def _immature_struct(self, host, pts):
+        host = _i32(host)
+        for k in ("u", "v", "color", "weights", "gradH", "energy_th", "idepth_min", "idepth_max", "quality", "uv", "pixel_interval"):
+            pts[k] = _f32(pts[k])
+        pts["status"] = _u8(pts["status"])
+        ip = Immature(n=host.size, reserved0=0, host=_p(host, i32p), u=_p(pts["u"], f32p), v=_p(pts["v"], f32p), color=_p(pts["color"], f32p),
+                      weights=_p(pts["weights"], f32p), gradH=_p(pts["gradH"], f32p), energy_th=_p(pts["energy_th"], f32p),
+                      idepth_min=_p(pts["idepth_min"], f32p), idepth_max=_p(pts["idepth_max"], f32p), quality=_p(pts["quality"], f32p),
+                      last_trace_status=_p(pts["status"], u8p), last_trace_uv=_p(pts["uv"], f32p),
+                      last_trace_pixel_interval=_p(pts["pixel_interval"], f32p))
+        return ip, host
+
+    def immature_pool_set(self, host, pts):
+        ip, keep = self._immature_struct(host, pts)
+        self._ck(self.lib.f("immature_pool_set")(self.h, C.byref(ip)), "immature_pool_set")
+
+    def immature_pool_trace(self, frame_slot, KRKi, Kt, aff, want_counts=True):
+        KRKi, Kt, aff = _f32(KRKi), _f32(Kt), _f32(aff)
+        counts = np.zeros(6, np.int32) if want_counts else None
+        self._ck(self.lib.f("immature_pool_trace")(self.h, C.c_int32(frame_slot), C.c_int32(KRKi.size // 9), _p(KRKi, f32p), _p(Kt, f32p), _p(aff, f32p),
+                                                   _p(counts, i32p)), "immature_pool_trace")
+        return counts
+
+    def immature_pool_get(self, host, pts):
+        """reads idepth_min/max, quality, status, uv, pixel_interval of the resident pool back into `pts` (in place)."""
+        ip, keep = self._immature_struct(host, pts)
+        self._ck(self.lib.f("immature_pool_get")(self.h, C.byref(ip)), "immature_pool_get")
 
     def optimize_immature(self, frame_slot, RTll, tTll, aff, calib, host, pts, min_obs=1):
         """optimizeImmaturePoint (FullSystemOptPoint.cpp:47-192) of every point of `pts` (dict of immature_init, after tracing).

@@ -73,6 +73,9 @@ struct HostSide {
   int2 *pin_sel_list = nullptr;        // pinned mirror of the first SEL_LIST_FAST entries + totals
   float *d_init = nullptr;      // CoarseInitializer points of one level (sosba_init_calc_res_and_gs) + 91 fp64 sums
   size_t init_cap = 0;
+  float *d_pool = nullptr;      // resident immature points (sosba_immature_pool_*): same arena layout as one pass of sosba_trace_immature
+  size_t pool_cap = 0;
+  int pool_n = 0, pool_hosts = 0;
   float *d_act = nullptr;       // activation outputs: [idepth n floats][result n bytes][res_state n*nf bytes]
   size_t act_cap = 0;
   float *d_act_win = nullptr;   // PRE_RTll / PRE_tTll / PRE_aff_mode per frame pair
@@ -2039,5 +2042,113 @@ API int sosba_init_calc_res_and_gs(sosba_t *h, int32_t lvl, int32_t ref_slot, in
   H[0] += alphaOpt * n; H[9] += alphaOpt * n; H[18] += alphaOpt * n;
   b[0] += tlog[0] * alphaOpt * n; b[1] += tlog[1] * alphaOpt * n; b[2] += tlog[2] * alphaOpt * n;
   res3[0] = (float)hs->pin_d[90]; res3[1] = alphaEnergy; res3[2] = (float)(2 * (size_t)n);   // E.num: both loops update E (:606-617)
+  return SOSBA_OK;
+}
+
+// ---- resident immature-point pool ---------------------------------------------------------------
+// arena of N = pool_n points (floats): [u][v][color 8][weights 8][gradH 4][energyTH] | [idmin][idmax][quality][uv 2][pixint] [host (int)] [status (bytes)]
+static TraceArgs pool_trace_args(sosba *h, float *d, size_t N, int frame_slot) {
+  TraceArgs a = {};
+  a.n = (int)N; a.w = h->wl[0]; a.h = h->hl[0]; a.img = h->slot_img[frame_slot] + h->lvl_off[0];
+  a.u = d; a.v = d + N; a.color = d + 2 * N; a.weights = d + 10 * N; a.gradH = d + 18 * N; a.energyTH = d + 22 * N;
+  a.idepth_min = d + 23 * N; a.idepth_max = d + 24 * N; a.quality = d + 25 * N; a.uv = d + 26 * N; a.pixint = d + 28 * N;
+  a.host = (const int *)(d + 29 * N); a.status = (uint8_t *)(d + 30 * N);
+  a.huberTH = h->cfg.huber_th;
+  return a;
+}
+
+API int sosba_immature_pool_set(sosba_t *h, const sosba_immature *pts) {
+  CHECK_H(h);
+  if (!pts || pts->n < 0) { sosba_set_error("pool_set: bad arguments"); return SOSBA_E_ARG; }
+  HostSide *hs = HS(h);
+  const int n = pts->n;
+  hs->pool_n = 0;
+  if (n == 0) return SOSBA_OK;
+  if (!pts->host || !pts->u || !pts->v || !pts->color || !pts->weights || !pts->gradH || !pts->energy_th || !pts->idepth_min || !pts->idepth_max ||
+      !pts->quality || !pts->last_trace_status || !pts->last_trace_uv || !pts->last_trace_pixel_interval) {
+    sosba_set_error("null buffer");
+    return SOSBA_E_ARG;
+  }
+  const size_t N = (size_t)n, bytes = 30 * N * sizeof(float) + N;
+  int rc;
+  if (31 * N > hs->pool_cap) {
+    dfree(h, hs->d_pool);
+    hs->pool_cap = 31 * (N + N / 4 + 256);
+    DALLOC(h, hs->d_pool, hs->pool_cap);
+  }
+  std::vector<char> tmp;
+  char *blk;
+  if (bytes <= hs->stage_cap / 2) { if ((rc = stage_reserve(h, bytes, &blk))) return rc; }
+  else { tmp.resize(bytes); blk = tmp.data(); }
+  float *s = (float *)blk;
+  memcpy(s, pts->u, 4 * N); memcpy(s + N, pts->v, 4 * N); memcpy(s + 2 * N, pts->color, 32 * N); memcpy(s + 10 * N, pts->weights, 32 * N);
+  memcpy(s + 18 * N, pts->gradH, 16 * N); memcpy(s + 22 * N, pts->energy_th, 4 * N);
+  memcpy(s + 23 * N, pts->idepth_min, 4 * N); memcpy(s + 24 * N, pts->idepth_max, 4 * N); memcpy(s + 25 * N, pts->quality, 4 * N);
+  memcpy(s + 26 * N, pts->last_trace_uv, 8 * N); memcpy(s + 28 * N, pts->last_trace_pixel_interval, 4 * N);
+  memcpy(s + 29 * N, pts->host, 4 * N); memcpy(s + 30 * N, pts->last_trace_status, N);
+  SOSBA_CUDA(cudaMemcpyAsync(hs->d_pool, s, bytes, cudaMemcpyHostToDevice, h->stream));
+  if (blk == tmp.data()) { if ((rc = sync(h))) return rc; }
+  hs->pool_n = n;
+  hs->pool_hosts = 0;
+  for (int i = 0; i < n; i++) hs->pool_hosts = std::max(hs->pool_hosts, pts->host[i] + 1);
+  for (int i = 0; i < n; i++) if (pts->host[i] < 0) { hs->pool_n = 0; sosba_set_error("point %d: negative host", i); return SOSBA_E_ARG; }
+  return SOSBA_OK;
+}
+
+API int sosba_immature_pool_trace(sosba_t *h, int32_t frame_slot, int32_t nhosts, const float *KRKi, const float *Kt, const float *aff, int32_t counts[6]) {
+  CHECK_H(h);
+  HostSide *hs = HS(h);
+  if (frame_slot < 0 || frame_slot >= (int)h->slot_img.size() || !h->slot_valid[frame_slot] || nhosts < 0) { sosba_set_error("bad slot"); return SOSBA_E_ARG; }
+  if (counts) for (int i = 0; i < 6; i++) counts[i] = 0;
+  if (hs->pool_n == 0) return SOSBA_OK;
+  if (!KRKi || !Kt || !aff || nhosts < hs->pool_hosts) { sosba_set_error("pool_trace: %d hosts given, the pool refers to %d", nhosts, hs->pool_hosts); return SOSBA_E_ARG; }
+  int rc;
+  if ((rc = ensure_immature(h, 1, nhosts))) return rc;
+  float *dh = hs->d_imm_host;
+  int *d_counts = (int *)(dh + 14 * (size_t)hs->imm_host_cap);
+  // the per-host tables go up as ONE block: [KRKi 9 x cap][Kt 3 x cap][aff 2 x cap] is how the kernel addresses them
+  {
+    char *blk;
+    const size_t cap = hs->imm_host_cap, bytes = 14 * cap * sizeof(float);
+    if ((rc = stage_reserve(h, bytes, &blk))) return rc;
+    float *s = (float *)blk;
+    memcpy(s, KRKi, 36 * (size_t)nhosts); memcpy(s + 9 * cap, Kt, 12 * (size_t)nhosts); memcpy(s + 12 * cap, aff, 8 * (size_t)nhosts);
+    SOSBA_CUDA(cudaMemcpyAsync(dh, s, bytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  SOSBA_CUDA(cudaMemsetAsync(d_counts, 0, 6 * sizeof(int), h->stream));
+  TraceArgs a = pool_trace_args(h, hs->d_pool, (size_t)hs->pool_n, frame_slot);
+  a.KRKi = dh; a.Kt = dh + 9 * (size_t)hs->imm_host_cap; a.aff = dh + 12 * (size_t)hs->imm_host_cap; a.counts = d_counts;
+  launch_trace_on(h, a);
+  SOSBA_CUDA(cudaGetLastError());
+  if (counts) {
+    if ((rc = down(h, hs->pin_i, (const int *)d_counts, 6))) return rc;
+    if ((rc = sync(h))) return rc;
+    for (int i = 0; i < 6; i++) counts[i] = hs->pin_i[i];
+  }
+  return SOSBA_OK;
+}
+
+API int sosba_immature_pool_get(sosba_t *h, sosba_immature *pts) {
+  CHECK_H(h);
+  HostSide *hs = HS(h);
+  if (!pts || pts->n != hs->pool_n) { sosba_set_error("pool_get: pts->n must equal the pool size %d", hs->pool_n); return SOSBA_E_ARG; }
+  const size_t N = (size_t)hs->pool_n;
+  if (N == 0) return SOSBA_OK;
+  if (!pts->idepth_min || !pts->idepth_max || !pts->quality || !pts->last_trace_status || !pts->last_trace_uv || !pts->last_trace_pixel_interval) {
+    sosba_set_error("null buffer");
+    return SOSBA_E_ARG;
+  }
+  int rc;
+  const size_t bytes = 7 * N * sizeof(float) + N;   // [idmin .. host] + status
+  std::vector<char> tmp;
+  char *blk;
+  if (bytes <= hs->stage_cap / 2) { if ((rc = stage_reserve(h, bytes, &blk))) return rc; }
+  else { tmp.resize(bytes); blk = tmp.data(); }
+  SOSBA_CUDA(cudaMemcpyAsync(blk, hs->d_pool + 23 * N, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if ((rc = sync(h))) return rc;
+  const float *s = (const float *)blk;
+  memcpy(pts->idepth_min, s, 4 * N); memcpy(pts->idepth_max, s + N, 4 * N); memcpy(pts->quality, s + 2 * N, 4 * N);
+  memcpy(pts->last_trace_uv, s + 3 * N, 8 * N); memcpy(pts->last_trace_pixel_interval, s + 5 * N, 4 * N);
+  memcpy(pts->last_trace_status, s + 7 * N, N);
   return SOSBA_OK;
 }

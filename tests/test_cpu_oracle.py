@@ -637,3 +637,21 @@ def test_init_calc_res_and_gs_vs_numpy(orc, big_t):
         assert (got["res3"][1] == 6.25 * len(pts["u"])) == big_t
         assert 0.3 < got["isGood_new"].mean() < 0.95
     h.close()
+
+
+def test_immature_pool_matches_per_call(orc):
+    """sosba_immature_pool_*: the resident variant is the per-call trace on stored arrays."""
+    from sos_slam_b200 import synth
+    sc = scene(**SMALLC)
+    h = open_handle(orc, sc)
+    case = synth.trace_case(sc, sc.nf - 1, n_per_host=50, seed=2)
+    pts = trace_points_cpu(h, sc, case["host"], case["u"], case["v"])
+    ref = {k: v.copy() for k, v in pts.items()}
+    h.immature_pool_set(case["host"], pts)
+    c1 = h.immature_pool_trace(sc.nf - 1, case["KRKi"], case["Kt"], case["aff"])
+    c2 = h.trace_immature(sc.nf - 1, case["host"], case["KRKi"], case["Kt"], case["aff"], ref)
+    assert np.array_equal(c1, c2)
+    h.immature_pool_get(case["host"], pts)
+    for k in pts:
+        assert np.array_equal(pts[k], ref[k], equal_nan=True), k
+    h.close()

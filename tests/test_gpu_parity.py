@@ -496,3 +496,30 @@ def test_init_calc_res_and_gs(gpu, orc, cfg, big_t):
         bad = dict(pts); bad["u"] = pts["u"].copy(); bad["u"][0] = 0.0
         hg.init_calc_res_and_gs(0, 0, 1, T, (0.0, 0.0), tlog, bad)
     hg.close(); ho.close()
+
+
+def test_immature_pool_resident(gpu, orc):
+    """The resident pool (sosba_immature_pool_set / _trace / _get) gives exactly what the per-call path gives: three traces
+    on the device without the points leaving HBM, then one read-back, against the oracle's per-call results."""
+    from sos_slam_b200 import synth
+    sc = scene(**CONFIG_B)
+    hg, ho = open_handle(gpu, sc), open_handle(orc, sc)
+    first = sc.nf - 3
+    base = synth.trace_case(sc, first, n_per_host=700, seed=33)
+    keep = base["host"] < first
+    sel = dict(host=base["host"][keep], u=base["u"][keep], v=base["v"][keep])
+    pg, po = trace_points(hg, sc, sel), trace_points(ho, sc, sel)
+    hg.immature_pool_set(sel["host"], pg)
+    for new_frame in (first, first + 1, first + 2):
+        case = synth.trace_case(sc, new_frame, n_per_host=1, seed=33)
+        cg = hg.immature_pool_trace(new_frame, case["KRKi"], case["Kt"], case["aff"])
+        co = ho.trace_immature(new_frame, sel["host"], case["KRKi"], case["Kt"], case["aff"], po)
+        assert np.array_equal(cg, co), (new_frame, cg, co)
+    untouched = {k: v.copy() for k, v in pg.items()}
+    hg.immature_pool_get(sel["host"], pg)
+    for k in pg:
+        assert np.array_equal(pg[k], po[k], equal_nan=True), k
+    assert not np.array_equal(untouched["status"], pg["status"])          # the host copy only changes at pool_get
+    hg.immature_pool_set(sel["host"][:0], {k: v[:0] for k, v in pg.items()})
+    assert hg.immature_pool_trace(first, case["KRKi"], case["Kt"], case["aff"]).sum() == 0
+    hg.close(); ho.close()

@@ -18,7 +18,8 @@ def make_inputs():
     uc = synth.undistort_case(sc.w, sc.h, w_org=sc.w + 16, h_org=sc.h + 12, seed=4)
     return {"in_images": np.stack([np.clip(np.rint(i), 0, 255).astype(np.uint8) for i in sc.images]), "in_K": sc.K, "in_evalPT": sc.evalPT,
             "in_pt_host": sc.pt_host, "in_pt_u": sc.pt_u, "in_pt_v": sc.pt_v, "in_pt_idepth": sc.pt_idepth, "in_pt_color": sc.pt_color,
-            "fin_random_pattern": rng.integers(0, 256, sc.w * sc.h).astype(np.uint8), "fin_raw": uc["raw"], "fin_G": uc["G"]}
+            "fin_random_pattern": rng.integers(0, 256, sc.w * sc.h).astype(np.uint8), "fin_raw": uc["raw"], "fin_G": uc["G"],
+            **{"fin_init_" + k: v for k, v in synth.init_case(sc, 0, n=400, seed=6).items()}}
 
 
 def run(lib, F):
@@ -91,11 +92,22 @@ def run(lib, F):
     o6, cnt = h.loop_calc_res(0, 3, T, (1.0, 0.0), 20.0)
     H, b = h.loop_calc_gs(0, 1.0, 0.0)
     out["loop_out6"], out["loop_counts"], out["loop_H"], out["loop_b"] = o6, cnt, H, b
+    # 8f-4 CoarseInitializer::calcResAndGS on level 0, frame 0 -> frame 1, both alpha regimes
+    ipts = {k[len("fin_init_"):]: F[k] for k in F.keys() if k.startswith("fin_init_")}
+    for tag, scale in (("a", 1.0), ("b", 40.0)):
+        xi = np.array([0.002, -0.001, 0.0015, 0.0004, -0.0006, 0.0003]) * scale
+        from sos_slam_b200 import synth as _s
+        Ti = _s.se3_exp(xi)[:3, :4]
+        r = h.init_calc_res_and_gs(0, 0, 1, Ti, (0.02, -1.0), xi[:3].astype(np.float32), ipts)
+        for k in ("isGood_new", "energy_new", "maxstep", "lastHessian_new", "JbBuffer_new"):
+            out[f"init{tag}_{k}"] = r[k]
+        out[f"init{tag}_H"], out[f"init{tag}_b"], out[f"init{tag}_Hsc"], out[f"init{tag}_bsc"], out[f"init{tag}_res3"] = r["H"], r["b"], r["Hsc"], r["bsc"], r["res3"]
     h.close()
     return out
 
 
 EXACT = ("und_image_crc", "und_image_row", "und_pyr2_dI", "und_pyr2_abs", "sel_n", "sel_potential", "sel_map0", "sel_map1", "imm_color", "imm_weights", "imm_gradH",
          "trace_counts", "trace_idepth_min", "trace_idepth_max", "trace_quality", "trace_status", "trace_uv", "trace_pixel_interval", "act_result",
-         "act_idepth", "act_states", "loop_counts")
-CLOSE = (("loop_out6", 2e-5), ("loop_H", 1e-4), ("loop_b", 1e-4))
+         "act_idepth", "act_states", "loop_counts") + tuple(f"init{t}_{k}" for t in "ab" for k in ("isGood_new", "energy_new", "maxstep",
+                                                                                                   "lastHessian_new", "JbBuffer_new"))
+CLOSE = (("loop_out6", 2e-5), ("loop_H", 1e-4), ("loop_b", 1e-4)) + tuple((f"init{t}_{k}", 1e-4) for t in "ab" for k in ("H", "b", "Hsc", "bsc", "res3"))

@@ -76,6 +76,10 @@ struct HostSide {
   float *d_pool = nullptr;      // resident immature points (sosba_immature_pool_*): same arena layout as one pass of sosba_trace_immature
   size_t pool_cap = 0;
   int pool_n = 0, pool_hosts = 0;
+  // sosba_optimize: the read-back of sosba_ba_download rides on the one synchronisation of sosba_ba_optimize
+  bool fold_download = false, download_ready = false;
+  float *pin_idepth = nullptr;
+  size_t pin_idepth_cap = 0;
   float *d_act = nullptr;       // activation outputs: [idepth n floats][result n bytes][res_state n*nf bytes]
   size_t act_cap = 0;
   float *d_act_win = nullptr;   // PRE_RTll / PRE_tTll / PRE_aff_mode per frame pair
@@ -311,6 +315,7 @@ API void sosba_destroy(sosba_t *h) {
   if (hs->pin_i) cudaFreeHost(hs->pin_i);
   if (hs->pin_f) cudaFreeHost(hs->pin_f);
   if (hs->pin_sel_list) cudaFreeHost(hs->pin_sel_list);
+  if (hs->pin_idepth) cudaFreeHost(hs->pin_idepth);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h->ba;
   { std::lock_guard<std::mutex> lk(g_mu); g_side.erase(h); }
@@ -1472,14 +1477,25 @@ static int upload_frame_state(sosba *h) {
 }
 
 // device frame / calibration state -> host mirror
-static int download_frame_state(sosba *h) {
+static const int PIN_FS_OFF = 1024;   // doubles: where a prefetched copy of the frame states sits in pin_d
+static int enqueue_frame_state_download(sosba *h, double *p) {
   BA *ba = h->ba;
   HostSide *hs = HS(h);
   const int nf = (int)ba->st.frames.size();
   int rc;
-  double *p = hs->pin_d;
   if ((rc = down(h, p, hs->d_fs, (size_t)nf * SOSBA_FS)) || (rc = down(h, p + nf * SOSBA_FS, hs->d_cs, 16)) || (rc = down(h, hs->pin_f, h->d_frameEnergyTH, nf))) return rc;
-  if ((rc = sync(h))) return rc;
+  return SOSBA_OK;
+}
+static int download_frame_state(sosba *h, bool prefetched = false) {
+  BA *ba = h->ba;
+  HostSide *hs = HS(h);
+  const int nf = (int)ba->st.frames.size();
+  int rc;
+  double *p = prefetched ? hs->pin_d + PIN_FS_OFF : hs->pin_d;
+  if (!prefetched) {
+    if ((rc = enqueue_frame_state_download(h, p))) return rc;
+    if ((rc = sync(h))) return rc;
+  }
   for (int f = 0; f < nf; f++) {
     sosba_host::FrameH &F = ba->st.frames[f];
     const double *q = p + SOSBA_FS * f;
@@ -1552,10 +1568,14 @@ API int sosba_ba_iterate(sosba_t *h, int32_t n, int32_t *n_res) {
 API int sosba_ba_download(sosba_t *h, sosba_ba_problem *prob) {
   CHECK_H(h);
   if (!prob || !h->ba->st.loaded) return SOSBA_E_STATE;
-  int rc0 = download_frame_state(h);
+  HostSide *hs = HS(h);
+  const bool ready = hs->download_ready;
+  hs->download_ready = false;
+  int rc0 = download_frame_state(h, ready);
   if (rc0) return rc0;
   h->ba->st.store(prob);
   if (prob->idepth_out) {
+    if (ready && hs->pin_idepth) { memcpy(prob->idepth_out, hs->pin_idepth, sizeof(float) * (size_t)h->P); return SOSBA_OK; }
     int rc = down(h, prob->idepth_out, h->p_idepth, h->P);
     if (rc) return rc;
     return sync(h);
@@ -1602,8 +1622,18 @@ API int sosba_ba_optimize(sosba_t *h, int32_t mnumOptIts, sosba_optimize_out *ou
   SOSBA_CUDA(cudaGetLastError());
   const int D = 4 + 8 * nf;
   if ((rc = down(h, hs->pin_i, hs->d_ctl, 4)) || (rc = down(h, hs->pin_d + 16, hs->d_stash, 12)) || (rc = down(h, hs->pin_d + 32, h->d_x, D))) return rc;
+  hs->download_ready = false;
+  if (hs->fold_download && (size_t)nf * SOSBA_FS + 16 + PIN_FS_OFF <= 4096) {   // what sosba_ba_download will want, on the same synchronisation
+    if ((size_t)h->P > hs->pin_idepth_cap) {
+      if (hs->pin_idepth) cudaFreeHost(hs->pin_idepth);
+      hs->pin_idepth_cap = (size_t)h->P + h->P / 4 + 256;
+      SOSBA_CUDA(cudaMallocHost((void **)&hs->pin_idepth, hs->pin_idepth_cap * sizeof(float)));
+    }
+    if ((rc = enqueue_frame_state_download(h, hs->pin_d + PIN_FS_OFF)) || (rc = down(h, hs->pin_idepth, (const float *)h->p_idepth, h->P))) return rc;
+    hs->download_ready = true;
+  }
   sosba_linearize_out lo;
-  if ((rc = read_linearize_out(h, &lo))) return rc;   // the one synchronisation
+  if ((rc = read_linearize_out(h, &lo))) { hs->download_ready = false; return rc; }   // the one synchronisation
   if (hs->pin_i[2]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
   {
     const int *c0 = (const int *)(hs->pin_d + 16 + 2);
@@ -1630,7 +1660,10 @@ API int sosba_optimize(sosba_t *h, sosba_ba_problem *prob, int32_t mnumOptIts, s
   int rc = sosba_ba_upload(h, prob);
   if (rc) return rc;
   const auto t1 = now();
-  if ((rc = sosba_ba_optimize(h, mnumOptIts, out))) return rc;
+  HS(h)->fold_download = true;
+  rc = sosba_ba_optimize(h, mnumOptIts, out);
+  HS(h)->fold_download = false;
+  if (rc) { HS(h)->download_ready = false; return rc; }
   const auto t2 = now();
   rc = sosba_ba_download(h, prob);
   if (timing) {

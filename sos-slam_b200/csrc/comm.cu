@@ -260,6 +260,8 @@ API int sosba_comm_destroy(sosba_t *h) {
     g_nccl.CommDestroy((ncclComm_t)h->comm);   // (a collective: every peer has stopped writing into this rank's mailbox)
     if (h->p2p_mbox) cudaFree(h->p2p_mbox);
     if (h->p2p_ticket) cudaFree(h->p2p_ticket);
+    if (h->d_comm_int) cudaFree(h->d_comm_int);
+    h->d_comm_int = nullptr;
     h->p2p_mbox = nullptr; h->p2p_ticket = nullptr; h->p2p = false;
     h->comm = nullptr; h->world = 1; h->rank = 0;
   }
@@ -328,13 +330,12 @@ int sosba_allreduce_lin(sosba *h, int with_stats) {
 int sosba_comm_max_int(sosba *h, int v, int *out) {
   *out = v;
   if (!h->comm || h->world <= 1) return SOSBA_OK;
-  int *d = nullptr;
-  if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return SOSBA_E_CUDA;
+  if (!h->d_comm_int && cudaMalloc(&h->d_comm_int, sizeof(int)) != cudaSuccess) return SOSBA_E_CUDA;   // kept: a per-call cudaMalloc / cudaFree costs more than the reduction
+  int *d = h->d_comm_int;
   cudaMemcpyAsync(d, &v, sizeof(int), cudaMemcpyHostToDevice, h->stream);
   ncclResult_t r = g_nccl.AllReduce(d, d, 1, ncclInt32, ncclMax, (ncclComm_t)h->comm, h->stream);
   cudaMemcpyAsync(out, d, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
   cudaStreamSynchronize(h->stream);
-  cudaFree(d);
   if (r != 0) { sosba_set_error("ncclAllReduce(max) -> %s", g_nccl.GetErrorString(r)); return SOSBA_E_NCCL; }
   return SOSBA_OK;
 }

@@ -58,6 +58,7 @@ struct HostSide {
   float2 *d_remap = nullptr;
   float *d_G = nullptr, *d_vig = nullptr;
   unsigned char *d_raw = nullptr;
+  std::vector<int> seen_tmp, tiles_tmp;   // residuals_set scratch
   std::vector<char> big_stage;        // pageable staging for uploads larger than half the pinned ring
   float *p_arena = nullptr;           // uploaded members of the points (carve_points)
   unsigned char *r_arena = nullptr;   // ids / energies / flags of the residuals (carve_residuals)
@@ -648,6 +649,10 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
   std::vector<int> &host = hs->r_host_tmp;   // scratch vectors live in the handle: no allocation per keyframe
   host.resize(n);
   hs->res_begin.assign(P + 1, 0);
+  // one pass: validation, host of every residual, CSR counts, and "no point sees a target twice" (what the fused accumulation needs)
+  std::vector<int> &seen = hs->seen_tmp;
+  seen.assign(nf, -1);
+  bool twice = false;
   int prev = -1;
   for (int i = 0; i < n; i++) {
     const int p = r->point[i], t = r->target[i];
@@ -656,18 +661,15 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
     host[i] = hs->p_host[p];
     if (host[i] < 0 || host[i] >= nf) { sosba_set_error("point %d: host %d invalid", p, host[i]); return SOSBA_E_ARG; }
     hs->res_begin[p + 1]++;
+    twice |= seen[t] == p;
+    seen[t] = p;
   }
   for (int p = 0; p < P; p++) hs->res_begin[p + 1] += hs->res_begin[p];
   {  // the fused accumulation stages the residuals of up to 32 consecutive points of ONE host and lists them per target
-    hs->fused_acc_ok = true;
+    hs->fused_acc_ok = !twice;
     hs->max_res_per_tile = 0;
-    std::vector<int> seen(nf, -1);
-    for (int p = 0; p < P && hs->fused_acc_ok; p++)
-      for (int i = hs->res_begin[p]; i < hs->res_begin[p + 1]; i++) {
-        if (seen[r->target[i]] == p) { hs->fused_acc_ok = false; break; }
-        seen[r->target[i]] = p;
-      }
-    std::vector<int> tiles;
+    std::vector<int> &tiles = hs->tiles_tmp;
+    tiles.clear();
     for (int p0 = 0; p0 < P;) {
       int np = 1;
       while (np < 32 && p0 + np < P && hs->p_host[p0 + np] == hs->p_host[p0]) np++;

@@ -157,6 +157,7 @@ struct sosba {
   int p2p_epoch = 0;
   int *p2p_ticket = nullptr;                  // last-CTA counter of the push kernel
   bool p2p = false;
+  int *d_comm_int = nullptr;                  // scratch of sosba_comm_max_int
 };
 
 void sosba_set_error(const char *fmt, ...);

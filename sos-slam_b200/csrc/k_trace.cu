@@ -345,9 +345,13 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_optimize_immature(ActivateArg
   p.u = a.u[k]; p.v = a.v[k]; p.energyTH = a.energyTH[k]; p.host = a.host[k];
   p.color = a.color[8 * (size_t)k + tap];
   { const float w = a.weights[8 * (size_t)k + tap]; p.w2 = w * w; }
-  // ImmaturePointTemporaryResidual per target frame (slot of the host unused); identical in the 8 lanes
-  uint8_t st[SOSBA_ACT_MAXF], nst[SOSBA_ACT_MAXF];
-  float en[SOSBA_ACT_MAXF], nen[SOSBA_ACT_MAXF];
+  // ImmaturePointTemporaryResidual per target frame (slot of the host unused).  The 8 lanes of a point hold identical values
+  // and all of them write, so every lane only ever reads back what it wrote itself: shared memory instead of four
+  // dynamically indexed local arrays, no synchronisation needed.
+  __shared__ uint8_t s_st[TRACE_PPB][2][SOSBA_ACT_MAXF];
+  __shared__ float s_en[TRACE_PPB][2][SOSBA_ACT_MAXF];
+  uint8_t *st = s_st[grp][0], *nst = s_st[grp][1];
+  float *en = s_en[grp][0], *nen = s_en[grp][1];
   const int nf = a.nf;
   for (int f = 0; f < nf; f++) { st[f] = SOSBA_RES_IN; nst[f] = SOSBA_RES_OUTLIER; en[f] = nen[f] = 0.f; }
   float lastEnergy = 0, lastHdd = 0, lastbd = 0;
@@ -356,6 +360,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_optimize_immature(ActivateArg
     if (f == p.host) continue;
     const float e = linearize_residual(a, p, gmask, tap, 1000.f, f, st[f], en[f], nst[f], nen[f], lastHdd, lastbd, currentIdepth);
     lastEnergy = (float)((double)lastEnergy + (double)e);   // float += double (FullSystemOptPoint.cpp:70)
+    __syncwarp(gmask);   // every lane has read the old state before any lane commits the new one
     st[f] = nst[f]; en[f] = nen[f];
   }
   int result = SOSBA_ACT_ACTIVATED;
@@ -376,7 +381,9 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_optimize_immature(ActivateArg
       if (!isfinite(lastEnergy) || newHdd < 100.f) { result = SOSBA_ACT_SKIP; break; }
       if (newEnergy < lastEnergy) {
         currentIdepth = newIdepth; lastHdd = newHdd; lastbd = newbd; lastEnergy = newEnergy;
+        __syncwarp(gmask);
         for (int f = 0; f < nf; f++) { st[f] = nst[f]; en[f] = nen[f]; }
+        __syncwarp(gmask);
         lambda = (float)((double)lambda * 0.5);
       } else {
         lambda *= 5;
@@ -384,6 +391,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_optimize_immature(ActivateArg
       if ((double)fabsf(step) < 0.0001 * (double)currentIdepth) break;
     }
   }
+  __syncwarp(gmask);
   if (tap != 0) return;
   int good = 0;
   for (int f = 0; f < nf; f++) {

@@ -53,7 +53,7 @@ int load_nccl() {
 // later, which a peer can only reach after it has received this rank's words of the exchange in between, i.e. after this
 // rank finished reading.  Every word carries the exchange number; a spin that does not see it within ~2 s raises the
 // solver's non-finite flag instead of hanging the stream.
-#define P2P_FLAG_BYTES 256   // 2 parities x 8 ranks x int, padded
+#define P2P_FLAG_BYTES 256   // mailbox header (unused by the in-band-flag protocol; keeps the slots 256-byte aligned)
 #define P2P_MAX_NEWE 16384   // floats of newest-frame energies per rank a slot can carry
 
 struct XchgArgs {

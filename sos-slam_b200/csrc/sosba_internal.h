@@ -151,7 +151,7 @@ struct sosba {
   int *d_newE_cnt = nullptr;        // ... [world] lengths, stored right behind the segments
   int newE_cap = 0;
   // peer-memory exchange (comm.cu): every rank pushes its partial tables into the other ranks' mailboxes over NVLink
-  unsigned char *p2p_mbox = nullptr;          // this rank's mailbox: [flags 2 x 8 ints (padded)] [2 parities][world slots]
+  unsigned char *p2p_mbox = nullptr;          // this rank's mailbox: [256-byte header] [2 parities][world slots of {payload, exchange number} words]
   unsigned char *p2p_peer[8] = {nullptr};     // the mailboxes of all ranks as mapped into this process (p2p_peer[rank] = own)
   size_t p2p_slot_bytes = 0;
   int p2p_epoch = 0;

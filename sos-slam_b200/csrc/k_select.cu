@@ -6,7 +6,8 @@
 //
 // select() is sequential in the reference only through `randomPattern[n2]`: the direction of every block is indexed by the
 // number of level-0 selections made so far in scan order.  Here one warp owns one (4*pot)^2 block (sel_block); the running
-// count at the block's start comes from an exclusive scan of per-block counts taken in a first (count-only) pass.  Whether a pot-block selects a pixel depends on its direction only when every
+// count at the block's start comes from an exclusive scan of per-block counts taken in a first, direction-free pass
+// (k_sel_count0).  Whether a pot-block selects a pixel depends on its direction only when every
 // candidate gradient is exactly orthogonal to it, so the counts of the first pass are almost always already final; the
 // second pass re-counts with the true directions and raises a flag if any block disagrees, and the host repeats the
 // scan + pass until the counts are a fixed point (then they are the sequential result).
@@ -172,7 +173,29 @@ template <bool WRITE> __device__ __forceinline__ int3 sel_block(const SelectArgs
   return make_int3(n2 - n2_start, n3, n4);
 }
 
-// One warp per (4*pot)^2 block.  WRITE = false: count-only pass (directions from base 0 are good enough for counting).
+// First pass: how many pot-blocks of each (4*pot)^2 block hold a pixel above the level-0 threshold.  That is the number of
+// level-0 selections the block will make unless every candidate gradient of a pot-block is exactly orthogonal to its
+// direction (the write pass checks).  No direction, no arg-max, no order: the lanes sweep the block's pixels with independent
+// loads and OR one bit per pot-block.
+__global__ void __launch_bounds__(128) k_sel_count0(SelectArgs a) {
+  const int B = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (B >= a.nbx * a.nby) return;
+  const int pot = a.pot, w = a.w, h = a.h;
+  const int x4 = (B % a.nbx) * 4 * pot, y4 = (B / a.nbx) * 4 * pot;
+  const int my3 = min(4 * pot, h - y4), mx3 = min(4 * pot, w - x4);
+  unsigned mask = 0;
+  for (int o = lane; o < mx3 * my3; o += 32) {
+    const int x = o % mx3, y = o / mx3, xf = x4 + x, yf = y4 + y;
+    if (xf < 4 || xf >= w - 5 || yf < 4 || yf > h - 4) continue;
+    const float pixelTH0 = __ldg(a.thsSmoothed + (xf >> 5) + (yf >> 5) * a.w32);
+    const float ag0 = __ldg(&a.img0[xf + w * yf].w);
+    if (ag0 > pixelTH0 * a.thFactor) mask |= 1u << ((y / pot) * 4 + x / pot);
+  }
+  mask = __reduce_or_sync(0xffffffffu, mask);
+  if (lane == 0) a.cnt_out[B] = __popc(mask);
+}
+
+// One warp per (4*pot)^2 block (WRITE = false would only count: the first pass uses the cheaper k_sel_count0 instead).
 template <bool WRITE> __global__ void __launch_bounds__(128) k_sel_blocks(SelectArgs a) {
   const int B = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (B >= a.nbx * a.nby) return;
@@ -275,7 +298,7 @@ void launch_select_hists(sosba *h, const SelectArgs &a) {
 void launch_select_blocks(sosba *h, const SelectArgs &a, bool write) {
   const int nb = a.nbx * a.nby;
   if (write) k_sel_blocks<true><<<(nb + 3) / 4, 128, 0, h->stream>>>(a);
-  else k_sel_blocks<false><<<(nb + 3) / 4, 128, 0, h->stream>>>(a);
+  else k_sel_count0<<<(nb + 3) / 4, 128, 0, h->stream>>>(a);
   h->launches++;
 }
 void launch_select_serial(sosba *h, const SelectArgs &a) {

@@ -938,3 +938,80 @@ def init_calc_res_and_gs_ref(dIref, dInew, K_lvl, refToNew, aff, tlog, pts, alph
         b[k] += float(tlog[k]) * float(alphaOpt) * n
     return dict(H=H, b=b, Hsc=Asc[:8, :8], bsc=Asc[:8, 8], res3=np.array([E, alphaEnergy, 2 * n]), energy_new=energy_new, isGood_new=good.astype(np.uint8),
                 maxstep=maxstep, lastHessian_new=lastH, JbBuffer_new=Jb_out)
+
+
+# ---- coarse tracker / scale optimizer (rows a14, a15, a17) --------------------------------------------------
+def align_calc_res_ref(dI, K_lvl, pc, R, t, lvl, cutoff, kind="pose", affLL=(1.0, 0.0), scale=1.0, Ki_lvl=None, huber=F(9)):
+    """CoarseTracker::calcResPose (CoarseTracker.cpp:612-764) and ScaleOptimizer::calcResScale (ScaleOptimizer.cpp:273-437),
+    vectorised float32.  dI (h, w, 3) level image of the new frame; K_lvl = fx fy cx cy of the camera the points are
+    projected INTO; Ki_lvl = fx fy cx cy of the reference camera (defaults to K_lvl); pc = (u, v, idepth, color).
+    -> out6 (float64), counts, warped buffers (dict, un-padded; rx* instead of idepth/u/v for kind == "scale")."""
+    h, w = dI.shape[:2]
+    fx, fy, cx, cy = [F(x) for x in K_lvl]
+    kfx, kfy, kcx, kcy = [F(x) for x in (K_lvl if Ki_lvl is None else Ki_lvl)]
+    Ki = np.array([[F(1) / kfx, 0, -kcx / kfx], [0, F(1) / kfy, -kcy / kfy], [0, 0, 1]], F)
+    R = np.asarray(R, np.float64).astype(F); t = np.asarray(t, np.float64).astype(F)
+    RKi = np.zeros((3, 3), F)
+    for i in range(3):
+        for j in range(3):
+            RKi[i, j] = (R[i, 0] * Ki[0, j] + R[i, 1] * Ki[1, j]) + R[i, 2] * Ki[2, j]
+    s = F(scale)
+    M = (s * RKi).astype(F) if kind == "scale" else RKi
+    Mk = (s * Ki).astype(F) if kind == "scale" else Ki
+    x, y, idp, col = [np.asarray(a, F) for a in pc]
+
+    def proj(A, sign):
+        p = [((A[k, 0] * x + A[k, 1] * y) + A[k, 2]) + F(sign) * t[k] * idp if sign >= 0 else ((A[k, 0] * x + A[k, 1] * y) + A[k, 2]) - t[k] * idp
+             for k in range(3)]
+        return p
+
+    with np.errstate(all="ignore"):
+        pt = proj(M, 1)
+        u, v = pt[0] / pt[2], pt[1] / pt[2]
+        Ku, Kv = fx * u + cx, fy * v + cy
+        nid = idp / pt[2]
+        rxs = [(((RKi[k, 0] * x + RKi[k, 1] * y) + RKi[k, 2]) / idp).astype(F) for k in range(3)]
+        sT = sRT = sN = F(0)
+        if lvl == 0:
+            pT, pT2, p3 = proj(Mk, 1), proj(Mk, -1), proj(M, -1)
+            KuT, KvT = fx * (pT[0] / pT[2]) + cx, fy * (pT[1] / pT[2]) + cy
+            KuT2, KvT2 = fx * (pT2[0] / pT2[2]) + cx, fy * (pT2[1] / pT2[2]) + cy
+            Ku3, Kv3 = fx * (p3[0] / p3[2]) + cx, fy * (p3[1] / p3[2]) + cy
+            for i in range(0, len(x), 32):
+                sT += (KuT[i] - x[i]) * (KuT[i] - x[i]) + (KvT[i] - y[i]) * (KvT[i] - y[i])
+                sT += (KuT2[i] - x[i]) * (KuT2[i] - x[i]) + (KvT2[i] - y[i]) * (KvT2[i] - y[i])
+                sRT += (Ku[i] - x[i]) * (Ku[i] - x[i]) + (Kv[i] - y[i]) * (Kv[i] - y[i])
+                sRT += (Ku3[i] - x[i]) * (Ku3[i] - x[i]) + (Kv3[i] - y[i]) * (Kv3[i] - y[i])
+                sN += F(2)
+    ok = (Ku > 2) & (Kv > 2) & (Ku < w - 3) & (Kv < h - 3) & (nid > 0)
+    hit = _bilin(dI, np.where(ok, Ku, F(3)), np.where(ok, Kv, F(3)))
+    ok &= np.isfinite(hit[:, 0])
+    res = hit[:, 0] - ((F(affLL[0]) * col + F(affLL[1])).astype(F) if kind == "pose" else col)
+    ares = np.abs(res)
+    hw = np.where(ares < huber, F(1), huber / np.maximum(ares, F(1e-30))).astype(F)
+    sat = ok & (ares > F(cutoff))
+    inw = ok & ~sat
+    maxE = F(2) * huber * F(cutoff) - huber * huber
+    terms = np.where(sat, maxE, hw * res * res * (F(2) - hw)).astype(F)
+    E = F(0)
+    for k in np.flatnonzero(ok):
+        E += terms[k]
+    nE, nW, nS = int(ok.sum()), int(inw.sum()), int(sat.sum())
+    out6 = np.array([E, nE, sT / (sN + F(0.1)), 0, sRT / (sN + F(0.1)), F(nS) / F(max(nE, 1))], np.float64)
+    buf = dict(dx=hit[inw, 1], dy=hit[inw, 2], residual=res[inw], weight=hw[inw], ref=col[inw])
+    if kind == "pose":
+        buf.update(idepth=nid[inw], u=u[inw], v=v[inw])
+    else:
+        buf.update(rx1=rxs[0][inw], rx2=rxs[1][inw], rx3=rxs[2][inw])
+    return out6, np.array([nE, nW, nS], np.int32), buf
+
+
+def scale_gs_ref(buf, fx1, fy1, scale, t):
+    """ScaleOptimizer::calcGSSSEScale (ScaleOptimizer.cpp:232-271) in float64: H = sum w J0^2 / n', b = sum w J0 r / n'."""
+    dxfx = buf["dx"].astype(np.float64) * fx1; dyfy = buf["dy"].astype(np.float64) * fy1
+    rx1, rx2, rx3 = [buf[k].astype(np.float64) for k in ("rx1", "rx2", "rx3")]
+    deno = 1.0 / (scale * rx3 + t[2]) ** 2
+    J0 = dxfx * (deno * (rx1 * t[2] - rx3 * t[0])) + dyfy * (deno * (rx2 * t[2] - rx3 * t[1]))
+    w = buf["weight"].astype(np.float64)
+    n = (len(w) + 3) // 4 * 4
+    return float(np.sum(w * J0 * J0) / n), float(np.sum(w * J0 * buf["residual"].astype(np.float64)) / n)

@@ -655,3 +655,54 @@ def test_immature_pool_matches_per_call(orc):
     for k in pts:
         assert np.array_equal(pts[k], ref[k], equal_nan=True), k
     h.close()
+
+
+# ---- a14 / a15 / a17: coarse tracker and scale optimizer against numpy ---------------------------------
+def _pc(sc, h, lvl, n, rng):
+    w, hh = sc.w >> lvl, sc.h >> lvl
+    u = rng.integers(2, w - 2, n).astype(np.float32)
+    v = rng.integers(2, hh - 2, n).astype(np.float32)
+    idepth = rng.uniform(0.35, 0.65, n).astype(np.float32)
+    dI, _ = h.frame_get_level(0, lvl)
+    return u, v, idepth, np.asarray(dI, np.float32).reshape(hh, w, 3)[v.astype(int), u.astype(int), 0].copy()
+
+
+def test_tracker_and_scale_vs_numpy(orc):
+    """CoarseTracker::calcResPose / calcGSSSEPose and ScaleOptimizer::calcResScale / calcGSSSEScale on every level: counts
+    exact, energy and flow indicators to float rounding, the normal equations to 2e-5 (the oracle sums in 4 float lanes)."""
+    from sos_slam_b200 import synth
+    sc = scene(**SMALLC)
+    h = open_handle(orc, sc)
+    K = sc.K.astype(np.float32)
+    K1 = K * np.array([1.01, 0.99, 1.0, 1.0], np.float32)
+    T = (np.linalg.inv(sc.camToWorld_true[1]) @ sc.camToWorld_true[0])[:3, :4]
+    T10 = synth.se3_exp([0.1, 0.002, -0.001, 0.001, -0.002, 0.0005])[:3, :4]
+    h.tracker_make_k(K)
+    h.scale_set_stereo(T10, K1)
+
+    def lvlK(Kc, l):
+        return np.array([Kc[0] / (1 << l), Kc[1] / (1 << l), (Kc[2] + 0.5) / (1 << l) - 0.5, (Kc[3] + 0.5) / (1 << l) - 0.5], np.float32)
+
+    for lvl in range(h.levels):
+        rng = np.random.default_rng(50 + lvl)
+        pc = _pc(sc, h, lvl, max(64, 3000 >> (2 * lvl)), rng)
+        h.tracker_set_ref(lvl, *pc)
+        dI1 = np.asarray(h.frame_get_level(1, lvl)[0], np.float32).reshape(sc.h >> lvl, sc.w >> lvl, 3)
+        dI2 = np.asarray(h.frame_get_level(2, lvl)[0], np.float32).reshape(sc.h >> lvl, sc.w >> lvl, 3)
+        for cutoff in (20.0, 6.0):
+            o6, cnt = h.tracker_calc_res_pose(lvl, 1, T, (1.02, -3.0), cutoff)
+            r6, rc, buf = np_ref.align_calc_res_ref(dI1, lvlK(K, lvl), pc, T[:, :3], T[:, 3], lvl, cutoff, "pose", (1.02, -3.0))
+            assert np.array_equal(cnt, rc), (lvl, cutoff, cnt, rc)
+            np.testing.assert_allclose(o6, r6, rtol=3e-5, atol=1e-6)
+            H, b = h.tracker_calc_gs_pose(lvl, 1.02, 0.004)
+            Hr, br = np_ref.pose_gs_ref(buf, float(lvlK(K, lvl)[0]), float(lvlK(K, lvl)[1]), 1.02, 0.004)
+            assert relerr(H, Hr) < 2e-5 and relerr(b, br) < 2e-5, (lvl, relerr(H, Hr), relerr(b, br))
+        for s in (1.0, 0.8):
+            o6, cnt = h.scale_calc_res(lvl, 2, s, 20.0)
+            r6, rc, buf = np_ref.align_calc_res_ref(dI2, lvlK(K1, lvl), pc, T10[:, :3], T10[:, 3], lvl, 20.0, "scale", scale=s, Ki_lvl=lvlK(K, lvl))
+            assert np.array_equal(cnt, rc), (lvl, s, cnt, rc)
+            np.testing.assert_allclose(o6, r6, rtol=3e-5, atol=1e-6)
+            Hs, bs = h.scale_calc_gs(lvl, s)
+            Hr, br = np_ref.scale_gs_ref(buf, float(lvlK(K1, lvl)[0]), float(lvlK(K1, lvl)[1]), s, T10[:, 3])
+            assert Hs == pytest.approx(Hr, rel=3e-5) and bs == pytest.approx(br, rel=3e-5, abs=1e-6 * abs(Hr))
+    h.close()

@@ -706,3 +706,54 @@ def test_tracker_and_scale_vs_numpy(orc):
             Hr, br = np_ref.scale_gs_ref(buf, float(lvlK(K1, lvl)[0]), float(lvlK(K1, lvl)[1]), s, T10[:, 3])
             assert Hs == pytest.approx(Hr, rel=3e-5) and bs == pytest.approx(br, rel=3e-5, abs=1e-6 * abs(Hr))
     h.close()
+
+
+# ---- a13 + marginalizePointsF against dense fp64 algebra ------------------------------------------------
+def test_fix_linearization_and_marginalize_vs_dense(orc):
+    """EFResidual::fixLinearizationF (EnergyFunctionalStructs.cpp:75-103): res_toZeroF = resF - J delta with the window's
+    deltas; EnergyFunctional::marginalizePointsF (EnergyFunctional.cpp:891-936): the prior of the marginalised points equals
+    the dense normal equations of their residuals (r = res_toZeroF) with the depths eliminated."""
+    from sos_slam_b200 import problem
+    sc = scene(**TINY)
+    frames = problem.frames_of(sc)
+    val, val0 = problem.calib_of(sc, (2e-4, 1e-4, -1e-4, 3e-4))
+    win = np_ref.window_tables(frames, val, val0)
+    pts, res = problem.points_of(sc), problem.residuals_of(sc)
+    h = open_handle(orc, sc)
+    h.window_set(win); h.points_set(pts); h.residuals_set(res)
+    h.reset_oob(); h.linearize_all(False); h.apply_res()
+    st = h.get_state()
+    J = h.get_jacobians(True).astype(np.float64)
+    counts = np.bincount(sc.res_point, minlength=sc.n_points)
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    chosen = np.arange(0, sc.n_points, 5, dtype=np.int32)
+    rids = np.concatenate([np.arange(starts[p], starts[p + 1]) for p in chosen]).astype(np.int32)
+    rids = rids[st["is_active"][rids] == 1]
+    h.fix_linearization(rids)
+    rtz = h.get_aux()["res_toZeroF"]
+    nf = sc.nf
+    adHTdelta = np.asarray(win["adHTdeltaF"], np.float64).reshape(nf * nf, 8)
+    cDelta = np.asarray(win["cDeltaF"], np.float64)
+    rp, rt = np.asarray(res["point"]), np.asarray(res["target"])
+    rh = np.asarray(pts["host"])[rp]
+    for r in rids:
+        j = J[r]
+        resF, Jxi, Jc, Jd = j[0:8], j[8:20].reshape(2, 6), j[20:28].reshape(2, 4), j[28:30]
+        JI, Jab = j[30:46].reshape(2, 8), j[46:62].reshape(2, 8)
+        dp = adHTdelta[rh[r] + nf * rt[r]]
+        Jp_delta = Jxi @ dp[:6] + Jc @ cDelta + Jd * float(pts["deltaF"][rp[r]])
+        ref = resF - JI.T @ Jp_delta - Jab.T @ dp[6:8]
+        np.testing.assert_allclose(rtz[r], ref, rtol=1e-4, atol=2e-4)
+    assert np.abs(rtz[rids] - J[rids, 0:8]).max() > 1e-3        # the deltas are not a no-op in this window
+    # marginalisation prior of the chosen points
+    Hm, bm, n_m = h.marginalize_points(chosen)
+    Jz = J.copy()
+    Jz[rids, 0:8] = rtz[rids]
+    sel = np.zeros(len(rp), bool)
+    sel[rids] = True
+    H, b, Hcd, Hdd, bd = np_ref.dense_system(win, pts, res, Jz, sel, sc.n_points)
+    Hsc, bsc = np_ref.schur(Hcd, Hdd, bd)
+    assert n_m == len(rids)
+    assert relerr(Hm, H - Hsc) < 1e-4 and relerr(bm, b - bsc) < 1e-4, (relerr(Hm, H - Hsc), relerr(bm, b - bsc))
+    assert np.allclose(Hm, Hm.T, rtol=0, atol=1e-6 * np.abs(Hm).max())
+    h.close()

@@ -2,9 +2,12 @@
 analytic properties, the host-side sharding logic (gloo, world size 2), and the C-ABI surface of libsosba.so.
 
 The reference ships no golden vectors for this path and cannot be built here, so the oracle is
-pinned by (i) this second restatement written from the reference sources (np_ref.py), (ii) properties: finite
-differences, the dense Schur identity, thread-count invariance, convergence to ground truth.  The reference itself
-cannot be compiled here, not even header by header: every file of the path includes Eigen."""
+pinned by (i) this second restatement written from the reference sources (np_ref.py) -- pyramid, linearize, window
+tables, tracker / scale optimizer, loop-closure alignment, initializer, immature points (constructor, traceOn,
+activation), raw-frame undistortion, pixel selection -- (ii) dense fp64 algebra: the Schur identity of the accumulators,
+fixLinearizationF, marginalizePointsF, the solve and the back-substitution, (iii) properties: finite differences,
+thread-count invariance, convergence to ground truth.  The reference itself cannot be compiled here, not even header by
+header: every file of the path includes Eigen."""
 import os
 import re
 

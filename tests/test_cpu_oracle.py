@@ -760,3 +760,30 @@ def test_fix_linearization_and_marginalize_vs_dense(orc):
     assert relerr(Hm, H - Hsc) < 1e-4 and relerr(bm, b - bsc) < 1e-4, (relerr(Hm, H - Hsc), relerr(bm, b - bsc))
     assert np.allclose(Hm, Hm.T, rtol=0, atol=1e-6 * np.abs(Hm).max())
     h.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_pixel_select_random_images(orc, seed):
+    """select() on noisy random images (many candidates per block, gradients of every orientation, image size not a multiple
+    of 32): oracle == independent formulation for potentials 1..4."""
+    from sos_slam_b200 import binding
+    w, h = 112, 80
+    rng = np.random.default_rng(seed)
+    ys, xs = np.mgrid[0:h, 0:w]
+    img = (128 + 60 * np.sin(xs * rng.uniform(0.1, 0.4) + ys * rng.uniform(-0.3, 0.3)) + rng.normal(0, 12, (h, w))).astype(np.float32)
+    rp = rng.integers(0, 256, w * h).astype(np.uint8)
+    cfg = orc.config_default(w, h)
+    cfg.max_frames = 1
+    cfg.pyr_levels = 3
+    hd = binding.Handle(orc, cfg)
+    hd.frame_make_images(0, img)
+    lv = [hd.frame_get_level(0, l) for l in range(3)]
+    dI0 = np.asarray(lv[0][0], np.float32).reshape(h, w, 3)
+    absg = [np.asarray(lv[l][1], np.float32).reshape(h >> l, w >> l) for l in range(3)]
+    _, ths_s = np_ref.sel_hists_ref(absg[0])
+    for pot in (1, 2, 3, 4):
+        hd.pixel_selector_set(rp, pot)
+        got = hd.pixel_select(0, 1e9, recursions_left=0, cap=w * h)
+        ref, n = np_ref.sel_select_ref(dI0, absg, ths_s, rp, pot)
+        assert got["n"] == sum(n) and np.array_equal(got["map"], ref), (pot, got["n"], n)
+    hd.close()

@@ -523,3 +523,36 @@ def test_immature_pool_resident(gpu, orc):
     hg.immature_pool_set(sel["host"][:0], {k: v[:0] for k, v in pg.items()})
     assert hg.immature_pool_trace(first, case["KRKi"], case["Kt"], case["aff"]).sum() == 0
     hg.close(); ho.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_pixel_select_random_images(gpu, orc, seed):
+    """Noisy random 112x80 images (not a multiple of the 32-pixel threshold blocks, pyramid forced to 3 levels): maps and
+    counts identical to the oracle for potentials 1..4 and through makeMaps."""
+    from sos_slam_b200 import binding
+    w, h = 112, 80
+    rng = np.random.default_rng(seed)
+    ys, xs = np.mgrid[0:h, 0:w]
+    img = (128 + 60 * np.sin(xs * rng.uniform(0.1, 0.4) + ys * rng.uniform(-0.3, 0.3)) + rng.normal(0, 12, (h, w))).astype(np.float32)
+    rp = rng.integers(0, 256, w * h).astype(np.uint8)
+    hs = []
+    for lib in (gpu, orc):
+        cfg = lib.config_default(w, h)
+        cfg.max_frames = 1
+        cfg.pyr_levels = 3
+        hd = binding.Handle(lib, cfg)
+        hd.frame_make_images(0, img)
+        hs.append(hd)
+    for pot in (1, 2, 3, 4):
+        outs = []
+        for hd in hs:
+            hd.pixel_selector_set(rp, pot)
+            outs.append(hd.pixel_select(0, 1e9, recursions_left=0, cap=w * h))
+        assert outs[0]["n"] == outs[1]["n"] and np.array_equal(outs[0]["map"], outs[1]["map"]), (pot, outs[0]["n"], outs[1]["n"])
+    for hd in hs:
+        hd.pixel_selector_set(rp, 3)
+    for density in (60.0, 400.0, 2500.0):
+        g, o = hs[0].pixel_select(0, density, cap=w * h), hs[1].pixel_select(0, density, cap=w * h)
+        assert (g["n"], g["potential"]) == (o["n"], o["potential"]) and np.array_equal(g["map"], o["map"]), density
+    for hd in hs:
+        hd.close()

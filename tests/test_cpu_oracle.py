@@ -417,12 +417,17 @@ def test_immature_init_vs_numpy(orc):
     h.close()
 
 
-def test_trace_immature_vs_numpy(orc):
+FORWARD = dict(w=384, h=160, nf=5, n_points=300, seed=9, forward_motion=True)      # KITTI-like: motion along the optical axis
+
+
+@pytest.mark.parametrize("cfg", [SMALLC, FORWARD], ids=["sideways", "forward"])
+def test_trace_immature_vs_numpy(orc, cfg):
     """ImmaturePoint::traceOn (ImmaturePoint.cpp:70-415) over two consecutive frames: first trace with an unbounded
     interval, second with the interval of the first.  Statuses must agree for every point; intervals to float rounding
-    (the numpy restatement sums the pattern energies in the same order but vectorised)."""
+    (the numpy restatement sums the pattern energies in the same order but vectorised).  Two camera motions: sideways
+    (long, nearly horizontal epipolar segments) and forward (short radial ones, more OOB / SKIPPED / BADCONDITION)."""
     from sos_slam_b200 import synth
-    sc = scene(**SMALLC)
+    sc = scene(**cfg)
     h = open_handle(orc, sc)
     seen = set()
     pts = None
@@ -457,11 +462,12 @@ def trace_points_cpu(h, sc, host, u, v):
     return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
 
 
-def test_optimize_immature_vs_numpy(orc):
+@pytest.mark.parametrize("cfg", [SMALLC, FORWARD], ids=["sideways", "forward"])
+def test_optimize_immature_vs_numpy(orc, cfg):
     """FullSystem::optimizeImmaturePoint + ImmaturePoint::linearizeResidual (FullSystemOptPoint.cpp:47-192,
     ImmaturePoint.cpp:475-545) on points traced twice: result code and residual states identical, idepth to rounding."""
     from sos_slam_b200 import synth
-    sc = scene(**SMALLC)
+    sc = scene(**cfg)
     h = open_handle(orc, sc)
     case = synth.trace_case(sc, sc.nf - 2, n_per_host=80, seed=5)
     keep = case["host"] < sc.nf - 2

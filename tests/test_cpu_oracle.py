@@ -105,9 +105,10 @@ def _setup_via_tables(lib, sc, win, pts, res):
     return h
 
 
-def test_linearize_bit_exact_vs_numpy(orc):
+@pytest.mark.parametrize("cfg", ["sideways", "forward"])
+def test_linearize_bit_exact_vs_numpy(orc, cfg):
     from sos_slam_b200 import problem
-    sc = scene(**SMALLC)
+    sc = scene(**(SMALLC if cfg == "sideways" else dict(w=384, h=160, nf=5, n_points=300, seed=9, forward_motion=True)))
     frames = problem.frames_of(sc)
     val, val0 = problem.calib_of(sc)
     win = np_ref.window_tables(frames, val, val0)
@@ -122,7 +123,7 @@ def test_linearize_bit_exact_vs_numpy(orc):
     ref = np_ref.linearize(win, pts, res, dI, sc.w, sc.h)
     assert np.array_equal(st["new_state"], ref["new_state"])
     live = ref["new_state"] != np_ref.RES_OOB
-    assert live.sum() > 0.8 * live.size
+    assert live.sum() > 0.6 * live.size
     assert np.array_equal(st["new_energy"][live], ref["new_energy"][live])
     assert np.array_equal(st["new_energy_wo"][live], ref["new_energy_wo"][live])
     assert np.array_equal(J[live], ref["J"][live])

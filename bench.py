@@ -46,13 +46,15 @@ def load():
 
 
 WORKLOADS = {"configB": WORKLOAD,
-             "kitti": "KITTI-shaped 1232x368 stereo, 12-KF window, 4000 active points, BA only (BASELINE.json configs[3] shape, 1 GPU)"}
+             "euroc": "EuRoC-shaped 752x480 stereo, 8-KF window, 2000 active points, BA only, IMU off (BASELINE.json configs[2] shape)",
+             "kitti": "KITTI-shaped 1232x368 stereo, 12-KF window, 4000 active points, BA only (BASELINE.json configs[3] shape)",
+             "tumvi": "TUM-VI-shaped 512x512, 8-KF window, 2000 active points, BA only, hot path only (BASELINE.json configs[4] shape)"}
 _workload = "configB"
 
 
 def get_scene(synth, n_points_factor=1):
-    from _scenes import CONFIG_B, KITTI, scene
-    sc = scene(**(KITTI if _workload == "kitti" else CONFIG_B))
+    from _scenes import CONFIG_B, EUROC, KITTI, TUMVI, scene
+    sc = scene(**{"configB": CONFIG_B, "euroc": EUROC, "kitti": KITTI, "tumvi": TUMVI}[_workload])
     if n_points_factor > 1:
         sc = synth.replicate_points(sc, n_points_factor)
     return sc
@@ -152,12 +154,63 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
+L2_NOTE = "GPU arm: L2 flushed between steps (256 MiB fill), per-step CUDA events on the launch stream; CPU arm: host wall clock"
+
+
+def config_of(sc, factor, scaling):
+    """The same dictionary in both arms (the driver compares them)."""
+    wl = WORKLOAD if factor == 1 else WORKLOAD + f" x{factor} points"
+    return {"workload": wl, "points": int(sc.n_points), "residuals": int(sc.n_residuals), "gn_iterations_per_step": ITERS,
+            "linearizations_per_step": ITERS + 2, "scaling": scaling, "l2": L2_NOTE}
+
+
 def forced_cfg(lib, sc, threads=1):
     cfg = lib.config_default(sc.w, sc.h)
     cfg.num_threads = threads
     cfg.max_frames = sc.nf + 2
     cfg.min_opt_iterations = 1000   # never break early: every step runs exactly ITERS Gauss-Newton iterations
     return cfg
+
+
+def _ref_factor(args):
+    """Problem size of the CPU arm = the GPU arm's: weak scaling multiplies the points by the GPU count, strong keeps them."""
+    return args.points_factor or (max(1, args.gpus) if args.scaling == "weak" else 1)
+
+
+def _time_cpu_steps(binding, problem, lib, sc, threads, steps, warmup, budget_s=None):
+    """`steps` FullSystem::optimize(6) calls of the oracle speed build on window `sc` with `threads` IndexThreadReduce
+    workers.  The caller's problem struct is built once (as the GPU arm's e2e does) and its in/out members are restored
+    before every step; the step itself = makeImages of the newest keyframe + optimize()."""
+    import ctypes
+    cfg = forced_cfg(lib, sc, threads=threads)
+    h = binding.Handle(lib, cfg)
+    for i, img in enumerate(sc.images):
+        h.frame_make_images(i, img)
+    val, val0 = problem.calib_of(sc)
+    P, keep = h.make_problem(problem.frames_of(sc), val, val0, problem.points_of(sc), problem.residuals_of(sc))
+    frames0 = bytes(ctypes.string_at(ctypes.addressof(keep[0]), ctypes.sizeof(keep[0])))
+    calib0 = list(P.calib_value)
+
+    def step():
+        ctypes.memmove(ctypes.addressof(keep[0]), frames0, len(frames0))
+        for i in range(4):
+            P.calib_value[i] = calib0[i]
+        h.frame_make_images(sc.nf - 1, sc.images[-1])
+        return h.optimize(P, ITERS)
+
+    for _ in range(warmup):
+        step()
+    nres, n, dt = 0, 0, 0.0
+    while n < steps:
+        t0 = time.perf_counter()
+        out = step()
+        dt += time.perf_counter() - t0
+        nres += out["reserved0"] * 8 * (out["iterations"] + 2)
+        n += 1
+        if budget_s is not None and dt > budget_s and n >= 3:
+            break
+    h.close()
+    return nres, dt, n
 
 
 def run_reference(args):
@@ -171,35 +224,21 @@ def run_reference(args):
         import __graft_entry__ as g
         g.build()
     lib = binding.Lib(path, "orc")
-    sc = get_scene(synth, max(1, args.gpus))
+    factor = _ref_factor(args)
+    sc = get_scene(synth, factor)
     cores = os.cpu_count() or 1
-    cfg = forced_cfg(lib, sc, threads=cores)
-    h = binding.Handle(lib, cfg)
-    for i, img in enumerate(sc.images):
-        h.frame_make_images(i, img)
-    val, val0 = problem.calib_of(sc)
-
-    def step():
-        h.frame_make_images(sc.nf - 1, sc.images[-1])
-        P, keep = h.make_problem(problem.frames_of(sc), val, val0, problem.points_of(sc), problem.residuals_of(sc))
-        return h.optimize(P, ITERS)
-
-    for _ in range(args.warmup):
-        out = step()
-    t0 = time.perf_counter()
-    nres = 0
-    for _ in range(args.steps):
-        out = step()
-        nres += out["reserved0"] * 8 * (out["iterations"] + 2)
-    dt = time.perf_counter() - t0
+    nres, dt, n = _time_cpu_steps(binding, problem, lib, sc, cores, args.steps, args.warmup)
     v = nres / dt
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / args.steps, "gn_iter_ms": 1e3 * dt / args.steps / ITERS, "higher_is_better": True, "scaling": "weak",
+    # the reference's own threading: NUM_THREADS = 6 workers (util/NumType.h:37), bounded sample
+    nres6, dt6, n6 = _time_cpu_steps(binding, problem, lib, sc, 6, min(args.steps, 10), 1, budget_s=10.0)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / n, "gn_iter_ms": 1e3 * dt / n / ITERS, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "points": sc.n_points, "residuals": sc.n_residuals, "gn_iterations_per_step": ITERS,
-                       "linearizations_per_step": ITERS + 2},
+            "config": config_of(sc, factor, args.scaling),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} full optimize() steps of the workload, oracle speed build (-O3 -mavx2 -mfma), {cores} IndexThreadReduce workers"},
+                             "sample": f"{n} full optimize() steps of the workload, oracle speed build (-O3 -mavx2 -mfma), {cores} IndexThreadReduce workers",
+                             "reference_threading": {"workers": 6, "value": nres6 / dt6, "ms_per_step": 1e3 * dt6 / n6, "steps": n6,
+                                                     "note": "NUM_THREADS = 6 as the reference hard-codes it (util/NumType.h:37)"}},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -212,6 +251,9 @@ def main():
     ap.add_argument("--impl", default="sosba")
     ap.add_argument("--points-factor", type=int, default=0, help="scaling sweep: multiply the 2000 points (default: = gpus)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = N x the workload's points (2000 per GPU), strong = the workload's points split over the N GPUs")
+    ap.add_argument("--no-other", action="store_true", help="skip the per-call timings of the rows next to the BA loop")
     ap.add_argument("--workload", default="configB", choices=sorted(WORKLOADS), help="configB = the benchmark workload (BASELINE.json configs[1]); others are extra data points")
     args = ap.parse_args()
     global _workload, WORKLOAD
@@ -232,7 +274,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg, binding, problem, synth = load()
     lib = pkg.load()
-    factor = args.points_factor or max(1, world)
+    factor = args.points_factor or (max(1, world) if args.scaling == "weak" else 1)
     sc = get_scene(synth, factor)
     cfg = forced_cfg(lib, sc)
     h = binding.Handle(lib, cfg, device=local)
@@ -365,7 +407,7 @@ def main():
 
     # ---- the other kernels of the path: per-call time, host buffers in ------------
     other = None
-    if rank == 0:
+    if rank == 0 and not args.no_other:
         try:
             reps = 30
             t0 = time.perf_counter()
@@ -455,6 +497,40 @@ def main():
         except Exception as ex:   # the BA numbers above do not depend on this block
             other = {"error": str(ex)}
 
+    # ---- point shards against one GPU on the same window (pytest -m gpu runs on a 1-GPU box, so the check lives here) ----
+    shard_parity = None
+    if world > 1:
+        def final_of(hh, Pp, kk):
+            o = hh.optimize(Pp, ITERS)
+            return o, hh.problem_result(Pp, kk)
+        Ps, ks = h.make_problem(frames, val, val0, pts, res)
+        o_s, r_s = final_of(h, Ps, ks)
+        t = torch.tensor(np.concatenate([r_s["state"].ravel(), r_s["frame_energy_th"].astype(np.float64), [o_s["iterations"], o_s["energy_final"], o_s["res_in_a"]]]), device="cuda")
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ranks_identical = bool((hi == lo).all().item())
+        if rank == 0:
+            h1 = binding.Handle(lib, cfg, device=local)
+            for i, img in enumerate(sc.images):
+                h1.frame_make_images(i, img)
+            P1, k1 = h1.make_problem(frames, val, val0, problem.points_of(sc), problem.residuals_of(sc))
+            o_1, r_1 = final_of(h1, P1, k1)
+            h1.close()
+            upd = np.abs(r_1["state"] - sc.state).max(axis=0) + 1e-12
+            dev = float(np.max(np.abs(r_s["state"] - r_1["state"]).max(axis=0) / upd))
+            p0, p1 = problem.shard_points(sc.res_point, sc.n_points, world)[0]
+            did = float(np.max(np.abs(r_s["idepth"] - r_1["idepth"][p0:p1]) / (np.abs(r_1["idepth"][p0:p1]) + 1e-3)))
+            shard_parity = {"ranks_bit_identical": ranks_identical, "iterations": [int(o_s["iterations"]), int(o_1["iterations"])],
+                            "res_in_a": [int(o_s["res_in_a"]), int(o_1["res_in_a"])], "n_removed": [int(o_s["n_removed"]), int(o_1["n_removed"])],
+                            "energy_final_rel": abs(o_s["energy_final"] - o_1["energy_final"]) / abs(o_1["energy_final"]),
+                            "state_dev_over_update": dev, "idepth_rel_rank0": did,
+                            "frame_energy_th_rel": float(np.max(np.abs(r_s["frame_energy_th"] - r_1["frame_energy_th"]) / np.abs(r_1["frame_energy_th"]))),
+                            "reference": "the same window optimised on one GPU (rank 0, all points)"}
+            shard_parity["ok"] = bool(ranks_identical and o_s["iterations"] == o_1["iterations"] and abs(o_s["res_in_a"] - o_1["res_in_a"]) <= 2
+                                      and shard_parity["energy_final_rel"] < 1e-3 and dev < 5e-3 and did < 2e-3 and shard_parity["frame_energy_th_rel"] < 1e-3)
+        barrier()
+
     # ---- roofline of the dominant kernel (linearize) ---------------------------------------------------
     peak, peak_src = measured_peak()
     R_lin = out["reserved0"]
@@ -542,12 +618,13 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": tot_ms / args.steps, "gn_iter_ms": gn_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": tot_ms / args.steps, "gn_iter_ms": gn_ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD if factor == 1 else WORKLOAD + f" x{factor} points, point-sharded", "points": sc.n_points,
-                           "residuals": sc.n_residuals, "gn_iterations_per_step": ITERS, "linearizations_per_step": ITERS + 2,
-                           "l2": "flushed between steps (256 MiB fill); per-step CUDA events on the launch stream", "parallelism": f"points/{world}",
-                           "exchange": "none" if world == 1 else ("peer-memory push over NVLink (comm.cu)" if h.comm_uses_peer_memory() else "nccl all-reduce")},
+                "config": config_of(sc, factor, args.scaling),
+                "sharding": {"parallelism": f"points/{world}", "points_per_rank": int(len(pts["u"])),
+                             "exchange": "none" if world == 1 else ("stitch fused with a peer-memory push over NVLink, one launch per GN iteration (k_xchg.cu)"
+                                                                    if h.comm_uses_peer_memory() else "nccl all-reduce of the block tables")},
+                "shard_parity": shard_parity,
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                                           "ms_per_step": e2e_ms / args.steps},
                 "e2e_raw_frame": e2e_raw, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "other_kernels": other,

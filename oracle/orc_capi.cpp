@@ -134,6 +134,7 @@ ORC_API int orc_points_update(orc_handle *h, const float *idepth, const float *i
 }
 ORC_API int orc_residuals_set(orc_handle *h, const sosba_residuals *r) {
   Oracle &o = h->o;
+  if (!r || r->n < 0 || (r->n > 0 && (!r->point || !r->target))) return SOSBA_E_ARG;
   o.res.assign(r->n, Res());
   int prev = -1;
   for (auto &p : o.pts) p.res_begin = p.res_end = 0;
@@ -141,7 +142,7 @@ ORC_API int orc_residuals_set(orc_handle *h, const sosba_residuals *r) {
     Res &q = o.res[i];
     memset(&q, 0, sizeof(q));
     q.point = r->point[i];
-    if (q.point < prev || q.point >= (int)o.pts.size()) return SOSBA_E_ARG;
+    if (q.point < 0 || q.point < prev || q.point >= (int)o.pts.size() || r->target[i] < 0 || r->target[i] >= o.nf) return SOSBA_E_ARG;
     if (q.point != prev) { o.pts[q.point].res_begin = i; prev = q.point; }
     o.pts[q.point].res_end = i + 1;
     q.host = o.pts[q.point].host; q.target = r->target[i];
@@ -313,12 +314,12 @@ ORC_API int orc_scale_calc_gs(orc_handle *h, int32_t lvl, float scale, float *H,
 
 // ---- composed GN loop ---------------------------------------------------------------------------
 ORC_API int orc_ba_upload(orc_handle *h, const sosba_ba_problem *prob) {
+  Oracle &o = h->o;
+  o.nf = prob->nf;
   int rc = orc_points_set(h, &prob->points);
   if (rc) return rc;
   rc = orc_residuals_set(h, &prob->residuals);
   if (rc) return rc;
-  Oracle &o = h->o;
-  o.nf = prob->nf;
   o.frame_slot.resize(prob->nf);
   for (int i = 0; i < prob->nf; i++) o.frame_slot[i] = prob->frames[i].slot;
   h->ba.load(o, prob);

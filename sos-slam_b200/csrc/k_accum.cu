@@ -20,22 +20,9 @@
 #include "energy_th.cuh"
 #include "kernels.h"
 #include "resub.cuh"
+#include "top_entries.cuh"
 
 namespace {
-
-// entry e of the 91 (10x10 upper triangle row-major, then 10x3 TopRight, then 6 BotRight)
-struct EntryDesc { int p, q, kind; };  // kind 0: 10x10 (r=p,c=q)  1: TopRight (i=p,j=q)  2: BotRight (k=p)  3: none
-__device__ __forceinline__ EntryDesc entry_desc(int e) {
-  EntryDesc d;
-  if (e < 55) {
-    int r = 0, base = 0;
-    while (e >= base + (10 - r)) { base += 10 - r; r++; }
-    d.p = r; d.q = r + (e - base); d.kind = 0;
-  } else if (e < 85) { d.p = (e - 55) / 3; d.q = (e - 55) % 3; d.kind = 1; }
-  else if (e < 91) { d.p = e - 85; d.q = 0; d.kind = 2; }
-  else { d.p = d.q = 0; d.kind = 3; }
-  return d;
-}
 
 __device__ __forceinline__ float entry_value(const float *s, const EntryDesc &d) {
   if (d.kind == 0) {
@@ -704,12 +691,6 @@ void launch_stitch_top(sosba *h, const double *accTop, const double *adHost, con
   k_stitch_top<<<nf * nf, 64, 0, h->stream>>>(accTop, adHost, adTarget, nf, H, b);
   k_finalize_top<<<1, 256, 0, h->stream>>>(nf, H, b, usePrior, wprior, cDeltaF);
   h->launches += 2;
-}
-
-// hot path: both tables (A | L) into one raw H, b; symmetrisation and priors happen inside k_solve
-void launch_stitch_raw(sosba *h, const double *accTop2, const double *adHost, const double *adTarget, int nf, int ntables, double *H, double *b) {
-  launch_pdl(k_stitch_top, ntables * nf * nf, 64, 0, h->stream, accTop2, adHost, adTarget, nf, H, b);
-  h->launches++;
 }
 
 void launch_finalize_sc(sosba *h, const double *accSC, int nf, double *H, double *b) {

@@ -1,7 +1,7 @@
 // k_solve.cu — EnergyFunctional::solveSystemF without IMU (EnergyFunctional.cpp:1029-1184) as ONE single-CTA
-// fp64 kernel.  Input is the raw stitch of the top blocks (A and L passes summed, not yet symmetrised), the
+// fp64 kernel.  Input is the stitch of the top blocks (A and L passes summed, symmetrised: k_stitch_xchg), the
 // stitched-space Schur Gram matrix, the priors and (optionally) the marginalisation prior HM, bM:
-//   HFinal = sym(Htop) + priors (+HM), b = btop + prior*delta_prior (+bM + HM*delta); diag *= (1+1e-5);
+//   HFinal = Htop + priors (+HM), b = btop + prior*delta_prior (+bM + HM*delta); diag *= (1+1e-5);
 //   HFinal -= H_sc/(1+1e-5); b -= b_sc; Jacobi scaling 1/sqrt(diag+10); LDL^T with the transposition order of
 //   Eigen::LDLT (the solver called at :1147-1148); back-substitution; x = S * y; then
 //   xAd[h*nf+t] = x_h^T adHostF[h+nf*t] + x_t^T adTargetF[h+nf*t] for resubstituteF_MT (:496-524).
@@ -17,12 +17,6 @@
 #include "resub.cuh"
 
 namespace {
-
-// final (undamped) top value at (r,c), r >= c, from the raw stitch (AccumulatedTopHessian.h:107-126 epilogue)
-__device__ __forceinline__ double top_entry(const double *__restrict__ Hraw, int D, int r, int c) {
-  if (c >= 4 && ((r - 4) >> 3) != ((c - 4) >> 3)) return Hraw[(size_t)r * D + c] + Hraw[(size_t)c * D + r];
-  return Hraw[(size_t)r * D + c];
-}
 
 // 256 threads as a 16x16 grid.  Thread (ty,tx) keeps the entries {(ty+16(kb+a), tx+16(kb+b))} of the trailing part of
 // the augmented, permuted, preconditioned lower triangle in registers (T = ceil((D+1)/16) tile rows/columns).
@@ -237,7 +231,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
         const double *it = a.step.iter;   // sumA, sumB, sumT, sumR of the previous body (already / nf)
         const float sumA = (float)it[0], sumB = (float)it[1], sumT = (float)it[2], sumR = (float)it[3];
         const float numID = (float)a.prev_rstats[2];
-        const float sumNID = numID > 0 ? (float)a.prev_rstats[1] / numID : 0.f;
+        const float sumNID = (float)a.prev_rstats[1] / numID;   // no points: 0/0 = NaN and the loop never breaks, like the reference (FullSystemOptimize.cpp:228-256)
         const float th = a.th_opt;
         stop = sqrtf(sumA) < 0.0005 * th && sqrtf(sumB) < 0.00005 * th && sqrtf(sumR) < 0.00005 * th && sqrtf(sumT) * sumNID < 0.00005 * th;
         if (stop) a.ctl[0] = 1;
@@ -332,11 +326,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
       const int i = lo ? rr : D - 1 - rr, j = lo ? cc : cc - rr - 1;
       const int pi = perm[i], pj = perm[j];
       const int r = max(pi, pj), c = min(pi, pj);
-      const double h1 = Hsrc[(size_t)r * D + c], h2 = Hsrc[(size_t)c * D + r];
+      const double h1 = Hsrc[(size_t)r * D + c];   // symmetrised by the stitch (AccumulatedTopHessian.h:107-126 epilogue)
       const double hs = Ssrc[(size_t)c * DP + r];
       const double hm = a.HM ? HMsrc[(size_t)r * D + c] : 0.0;
-      const bool offdiag = c >= 4 && ((r - 4) >> 3) != ((c - 4) >> 3);   // AccumulatedTopHessian.h:107-126 epilogue
-      double u = (offdiag ? h1 + h2 : h1) + hm;
+      double u = h1 + hm;
       u -= hs * sc;
       u = r == c ? dtmp[r] : u;
       if (a.Hfinal) { a.Hfinal[(size_t)r * D + c] = u; a.Hfinal[(size_t)c * D + r] = u; }
@@ -425,7 +418,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
   double *y = key;   // x in original order
   bool bad = false;
   for (int j = tid; j < D; j += SOLVE_THREADS) { const int r = perm[j]; const double xi = S[r] * z[j]; y[r] = xi; a.x[r] = xi; if (!isfinite(xi)) bad = true; }
-  if (bad && a.status) a.status[0] = 1;
+  if (bad && a.status) atomicOr(a.status, 1);
   __syncthreads();
   SOLVE_TS(6);
   // ---- xAd (EnergyFunctional.cpp:509-513) and xc ------------------------------------------------------

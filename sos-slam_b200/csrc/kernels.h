@@ -164,14 +164,37 @@ bool launch_accumulate_fused(sosba *h, const FusedAccArgs &a, int max_res_per_ti
 // top blocks -> H (D*D), b (D): AccumulatedTopHessianSSE::stitchDoubleInternal + stitchDoubleMT epilogue
 void launch_stitch_top(sosba *h, const double *accTop, const double *adHost, const double *adTarget, int nf, double *H, double *b,
                        int usePrior, const double *wprior, const float *cDeltaF);
-void launch_stitch_raw(sosba *h, const double *accTop2, const double *adHost, const double *adTarget, int nf, int ntables, double *H, double *b);
+
+// ---- k_xchg.cu: gather-form stitch of the top blocks (A + L tables) into the final symmetric H, b, fused with the
+// point-shard exchange over peer memory (push = 1): H, b, the Schur Gram matrix, the back-substitution sums, the residual
+// counters are summed over ranks in rank order, the newest-frame energies concatenated
+struct StitchXchgArgs {
+  int nf, D;
+  const double *accTop;        // [2][nf*nf*92]: A | L
+  const double *adHost, *adTarget;
+  double *H, *b;               // out: D*D (both triangles), D
+  double *accSC;               // (D+1)^2 Schur Gram matrix, upper triangle; summed in place when push
+  double *rstats;              // [8] back-substitution sums of both loop-body parities; summed in place when push
+  int *cnt;                    // [2] resInA, resInL; summed in place when push
+  int rank, world, push;
+  unsigned char *peer[8];      // mailboxes of all ranks as mapped into this process
+  size_t slot_bytes;
+  int *epoch;                  // device: [0] exchange number (starts at 1), [1] CTA ticket
+  float *newE_all;             // [world][newE_cap] newest-frame energies, own segment filled by the linearisation
+  int *newE_cnt;               // [world]
+  int newE_cap, with_newE;
+  const int *gate;             // non-null: skip when *gate != 0 (the loop broke on the device -- on every rank alike)
+  int *err;                    // set to 2 when a peer's words did not arrive in time
+};
+size_t stitch_xchg_slot_bytes(int nf_max, int newE_cap);
+void launch_stitch_xchg(sosba *h, const StitchXchgArgs &a, int local_points);
 // accSC -> Hsc (D*D), bsc (D)
 void launch_finalize_sc(sosba *h, const double *accSC, int nf, double *H, double *b);
 
 // ---- k_solve.cu ---------------------------------------------------------------------------------
 struct SolveArgs {
   int nf, D;
-  const double *Htop, *btop;   // raw stitch of the A and L top blocks (k_stitch_top output, not symmetrised)
+  const double *Htop, *btop;   // stitched A + L top blocks, symmetric (k_stitch_xchg output)
   const double *accSC;         // (D+1)^2 Gram matrix of the Schur term, upper tiles
   const double *HM, *bM;       // may be null
   const double *wprior;        // cPrior[4] | frame_prior | frame_delta_prior | frame_delta

@@ -21,12 +21,12 @@
 void launch_make_xad(sosba *h, const double *d_x, int nf, const float *adHostF, const float *adTargetF, float *xAd);
 void launch_scale_prior(sosba *h, float *priorF, const int *ids, int n, float fac);
 void launch_fill_f32(sosba *h, float *dst, int n, float v);
-void launch_stitch_raw(sosba *h, const double *accTop2, const double *adHost, const double *adTarget, int nf, int ntables, double *H, double *b);
 
 using sosba_host::BAState;
 using sosba_host::WindowTables;
 
-int sosba_allreduce_acc(sosba *h, int with_newE, const int *gate, int *err, const ThArgs *th, int *th_done);  // comm.cu: no-ops without a communicator
+int sosba_allreduce_acc(sosba *h, int with_newE);  // comm.cu: no-ops without a communicator
+void sosba_xchg_args(sosba *h, StitchXchgArgs *a, int with_newE);
 int sosba_allreduce_lin(sosba *h, int with_stats);
 int sosba_comm_max_int(sosba *h, int v, int *out);
 static thread_local char g_err[512] = "";
@@ -477,18 +477,20 @@ static int ensure_window(sosba *h, int nf) {
   DALLOC(h, h->d_calib, 16);
   DALLOC(h, h->d_wprior, 4 + 24 * (size_t)nf);
   DALLOC(h, h->d_img0, nf);
-  {  // one scratch region zeroed by a single memset per solve: top tables (A | L), Schur Gram, H parts A | L | SC,
-     // back-substitution sums [4], counters (ints) ; H part 3 (final system) follows and is never cleared
+  {  // one scratch region zeroed by a single memset per API-level solve: top tables (A | L), Schur Gram, counters (ints),
+     // H parts A | L | SC, back-substitution sums [4] ; H part 3 (final system) follows and is never cleared.
+     // Inside the Gauss-Newton loop only tables + Gram + counters are cleared (by the fused linearisation): the stitch of
+     // the loop (k_stitch_xchg) writes every entry of H part 0 and needs no zeroed target.
     const size_t HB = (size_t)D * D + D;
     const size_t scpad = (((size_t)(D + 1) * (D + 1)) + 1) & ~(size_t)1;   // even: H, b behind it stay 16-byte aligned (TMA bulk copies in k_solve)
-    hs->scratch_doubles = 2 * n2 * SOSBA_TOPB + scpad + 3 * HB + 2 + 8 + 2;
+    hs->scratch_doubles = 2 * n2 * SOSBA_TOPB + scpad + 2 + 3 * HB + 8 + 2;
     DALLOC(h, hs->d_scratch, hs->scratch_doubles + HB);
     h->d_accTop = hs->d_scratch;
     h->d_accSC = h->d_accTop + 2 * n2 * SOSBA_TOPB;
-    h->d_H = h->d_accSC + scpad;
-    hs->d_cnt = (int *)(h->d_H + 3 * HB);                   // [0] resInA [1] resInL (cleared with the tables)
-    hs->d_rstats = h->d_H + 3 * HB + 2;                     // 2 x 4 doubles: back-substitution sums by loop body parity
-    hs->scratch_zero_doubles = (size_t)(hs->d_rstats - hs->d_scratch) & ~(size_t)1;
+    hs->d_cnt = (int *)(h->d_accSC + scpad);                // [0] resInA [1] resInL (cleared with the tables)
+    h->d_H = h->d_accSC + scpad + 2;
+    hs->d_rstats = h->d_H + 3 * HB;                         // 2 x 4 doubles: back-substitution sums by loop body parity
+    hs->scratch_zero_doubles = (size_t)(h->d_H - hs->d_scratch);
     h->d_rstats_all = hs->d_rstats; h->d_cnt_all = hs->d_cnt;
     hs->d_Hfinal = hs->d_scratch + hs->scratch_doubles;
   }
@@ -574,6 +576,10 @@ static void carve_points(sosba *h, size_t N) {
 API int sosba_points_set(sosba_t *h, const sosba_points *p) {
   CHECK_H(h);
   if (!p || p->n < 0) return SOSBA_E_ARG;
+  if (p->n > 0 && (!p->u || !p->v || !p->idepth || !p->idepth_zero || !p->color || !p->weights || !p->host)) {
+    sosba_set_error("points_set: u, v, idepth, idepth_zero, color, weights and host are mandatory");
+    return SOSBA_E_ARG;
+  }
   int rc = ensure_points(h, p->n);
   if (rc) return rc;
   const size_t n = p->n;
@@ -639,6 +645,7 @@ static void clear_gathered_energies(sosba *h);
 API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
   CHECK_H(h);
   if (!r || r->n < 0 || h->nf <= 0) { sosba_set_error("residuals_set needs window_set/points_set first"); return SOSBA_E_STATE; }
+  if (r->n > 0 && (!r->point || !r->target)) { sosba_set_error("residuals_set: point and target are mandatory"); return SOSBA_E_ARG; }
   int rc = ensure_residuals(h, r->n);
   if (rc) return rc;
   HostSide *hs = HS(h);
@@ -656,7 +663,7 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
   int prev = -1;
   for (int i = 0; i < n; i++) {
     const int p = r->point[i], t = r->target[i];
-    if (p < prev || p >= P || t < 0 || t >= nf) { sosba_set_error("residual %d: point %d / target %d invalid or not point-major", i, p, t); return SOSBA_E_ARG; }
+    if (p < 0 || p < prev || p >= P || t < 0 || t >= nf) { sosba_set_error("residual %d: point %d / target %d invalid or not point-major", i, p, t); return SOSBA_E_ARG; }
     prev = p;
     host[i] = hs->p_host[p];
     if (host[i] < 0 || host[i] >= nf) { sosba_set_error("point %d: host %d invalid", p, host[i]); return SOSBA_E_ARG; }
@@ -948,13 +955,17 @@ static SCArgs sc_args(sosba *h, int mode, const int *plist, int n_plist, int shi
 }
 
 // the block tables of accumulateAF_MT / accumulateLF_MT / accumulateSCF_MT (EnergyFunctional.cpp:197-254):
-// one memset, top blocks (A, and L when linearised residuals exist), per-point sums + Schur Gram, all-reduce
-// defer_th (point shards, loop path): the caller runs the pending setNewFrameEnergyTH in the spare CTA of its k_solve launch
-static int enqueue_blocks(sosba *h, ThArgs *defer_th = nullptr, int *deferred = nullptr) {
+// one memset, top blocks (A, and L when linearised residuals exist), per-point sums + Schur Gram.
+// Point shards: with `nccl_reduce` the un-stitched tables are summed over ranks by NCCL right here (API-level calls, and
+// the loop when the peer mailboxes are unavailable) and the pending newest-frame energies ride along; otherwise the caller
+// (enqueue_solve) sums the STITCHED system inside k_stitch_xchg.  Either way the pending setNewFrameEnergyTH of a sharded
+// window is handed back in `defer_th` so that it runs in the spare CTA of the caller's k_solve launch.
+static int enqueue_blocks(sosba *h, bool nccl_reduce, ThArgs *defer_th = nullptr, int *deferred = nullptr) {
   if (deferred) *deferred = 0;
   HostSide *hs = HS(h);
   const int nf = h->nf;
   const size_t n2 = (size_t)nf * nf;
+  const bool sharded = h->comm && h->world > 1;
   if (!hs->tables_clean) cudaMemsetAsync(hs->d_scratch, 0, sizeof(double) * hs->scratch_doubles, h->stream);
   // (clean tables: the back-substitution sums of this body are cleared by k_solve)
   hs->tables_clean = false;
@@ -962,7 +973,7 @@ static int enqueue_blocks(sosba *h, ThArgs *defer_th = nullptr, int *deferred = 
   if (hs->fused_acc_ok) {
     if (hs->n_lin > 0) launch_prep_records(h, lin_args(h), 1, nullptr, h->R);
     FusedAccArgs f;
-    f.P = h->P; f.nf = nf; f.D = 4 + 8 * nf; f.R = h->R; f.shiftPriorToZero = 1; f.do_th = (hs->th_pending && !(h->comm && h->world > 1)) ? 1 : 0;
+    f.P = h->P; f.nf = nf; f.D = 4 + 8 * nf; f.R = h->R; f.shiftPriorToZero = 1; f.do_th = (hs->th_pending && !sharded) ? 1 : 0;
     f.tiles = (const int4 *)hs->d_tiles;
     f.res_begin = h->p_res_begin; f.r_target = h->r_target; f.p_host = h->p_host;
     f.r_is_lin = h->r_is_lin; f.r_is_active = h->r_is_active; f.r_dropped = h->r_dropped; f.rec = h->r_rec;
@@ -976,35 +987,29 @@ static int enqueue_blocks(sosba *h, ThArgs *defer_th = nullptr, int *deferred = 
     if (fused && f.do_th) hs->th_pending = false;
   }
   if (!fused) {
-  if (!(h->comm && h->world > 1)) flush_pending_th(h);
-  AccArgs a;
-  a.R = h->R; a.P = h->P; a.nf = nf; a.n_list = h->R; a.list = h->r_by_block; a.mode = 0;
-  a.r_point = h->r_point; a.r_target = h->r_target; a.r_host = h->r_host;
-  a.r_is_lin = h->r_is_lin; a.r_is_active = h->r_is_active; a.r_dropped = h->r_dropped;
-  a.rec = h->r_rec; a.accTop = h->d_accTop; a.n_acc = hs->d_cnt;
-  launch_top_accumulate(h, a);
-  if (hs->n_lin > 0) {
-    launch_prep_records(h, lin_args(h), 1, nullptr, h->R);
-    AccArgs l = a;
-    l.mode = 1; l.accTop = h->d_accTop + n2 * SOSBA_TOPB; l.n_acc = hs->d_cnt + 1;
-    launch_top_accumulate(h, l);
-  }
-  launch_point_sc(h, sc_args(h, 0, nullptr, 0, 1));
-  }
-  // points are sharded across ranks: sum the block tables (identical on every rank afterwards); the pending newest-frame
-  // energies ride along and the threshold selection runs right behind the reduction
-  const bool shard_th = h->comm && h->world > 1 && hs->th_pending;
-  ThArgs th = {};
-  if (shard_th) th = lin_args(h).th;
-  int th_done = 0;
-  int rc = sosba_allreduce_acc(h, shard_th ? 1 : 0, hs->gate, hs->gate ? hs->d_ctl + 2 : nullptr, shard_th ? &th : nullptr, &th_done);
-  if (rc) return rc;
-  if (shard_th) {
-    if (!th_done) {
-      if (defer_th) { *defer_th = th; *deferred = 1; }
-      else launch_energy_th(h, th, hs->gate);
+    if (!sharded) flush_pending_th(h);
+    AccArgs a;
+    a.R = h->R; a.P = h->P; a.nf = nf; a.n_list = h->R; a.list = h->r_by_block; a.mode = 0;
+    a.r_point = h->r_point; a.r_target = h->r_target; a.r_host = h->r_host;
+    a.r_is_lin = h->r_is_lin; a.r_is_active = h->r_is_active; a.r_dropped = h->r_dropped;
+    a.rec = h->r_rec; a.accTop = h->d_accTop; a.n_acc = hs->d_cnt;
+    launch_top_accumulate(h, a);
+    if (hs->n_lin > 0) {
+      launch_prep_records(h, lin_args(h), 1, nullptr, h->R);
+      AccArgs l = a;
+      l.mode = 1; l.accTop = h->d_accTop + n2 * SOSBA_TOPB; l.n_acc = hs->d_cnt + 1;
+      launch_top_accumulate(h, l);
     }
-    hs->th_pending = false;
+    launch_point_sc(h, sc_args(h, 0, nullptr, 0, 1));
+  }
+  const bool shard_th = sharded && hs->th_pending;
+  if (nccl_reduce) {
+    int rc = sosba_allreduce_acc(h, shard_th ? 1 : 0);
+    if (rc) return rc;
+  }
+  if (shard_th) {
+    if (defer_th) { *defer_th = lin_args(h).th; *deferred = 1; }
+    else if (nccl_reduce) { launch_energy_th(h, lin_args(h).th, hs->gate); hs->th_pending = false; }
   }
   return SOSBA_OK;
 }
@@ -1013,8 +1018,10 @@ static int enqueue_blocks(sosba *h, ThArgs *defer_th = nullptr, int *deferred = 
 static int enqueue_accumulate(sosba *h) {
   const int nf = h->nf;
   const size_t n2 = (size_t)nf * nf;
-  int rc = enqueue_blocks(h);
+  const bool only_tables_clean = HS(h)->tables_clean;   // a loop body cleared the tables, not the H parts the stitch adds into
+  int rc = enqueue_blocks(h, true);
   if (rc) return rc;
+  if (only_tables_clean) cudaMemsetAsync(h->d_H, 0, sizeof(double) * 3 * ((size_t)(4 + 8 * nf) * (4 + 8 * nf) + 4 + 8 * nf), h->stream);
   launch_stitch_top(h, h->d_accTop, h->d_adHost, h->d_adTarget, nf, Hpart(h, 0), bpart(h, 0), 0, h->d_wprior, h->d_calib + 6);
   launch_stitch_top(h, h->d_accTop + n2 * SOSBA_TOPB, h->d_adHost, h->d_adTarget, nf, Hpart(h, 1), bpart(h, 1), 1, h->d_wprior, h->d_calib + 6);
   launch_finalize_sc(h, h->d_accSC, nf, Hpart(h, 2), bpart(h, 2));
@@ -1040,6 +1047,13 @@ API int sosba_accumulate(sosba_t *h, double *HA, double *bA, double *HL, double 
 }
 
 // ---- a10/a11 ------------------------------------------------------------------------------------
+// the device error word of a solve (d_ctl[2]): k_solve raises 1 for a non-finite step (the reference: isLost), the peer
+// exchange raises bit 1 when a rank's words did not arrive in time (its results are then not stored)
+static int solve_flag_error(int flag) {
+  if (flag & 2) { sosba_set_error("point-shard exchange timed out: a peer rank did not deliver its part of the system"); return SOSBA_E_NCCL; }
+  sosba_set_error("non-finite solution");
+  return SOSBA_E_NONFINITE;
+}
 static ResubArgs resub_args(sosba *h, int do_step) {
   ResubArgs r;
   r.P = h->P; r.nf = h->nf; r.res_begin = h->p_res_begin; r.r_target = h->r_target; r.p_host = h->p_host;
@@ -1068,9 +1082,17 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
   const int nf = h->nf, D = 4 + 8 * nf;
   ThArgs th_def = {};
   int th_deferred = 0;
-  int rc = enqueue_blocks(h, &th_def, &th_deferred);
+  StitchXchgArgs x;
+  memset(&x, 0, sizeof(x));
+  sosba_xchg_args(h, &x, hs->th_pending ? 1 : 0);   // push = 1: the ranks' stitched systems are summed over peer memory
+  const bool sharded = h->comm && h->world > 1;
+  int rc = enqueue_blocks(h, sharded && !x.push, &th_def, &th_deferred);
   if (rc) return rc;
-  launch_stitch_raw(h, h->d_accTop, h->d_adHost, h->d_adTarget, nf, hs->n_lin > 0 ? 2 : 1, Hpart(h, 0), bpart(h, 0));
+  x.nf = nf; x.D = D; x.accTop = h->d_accTop; x.adHost = h->d_adHost; x.adTarget = h->d_adTarget;
+  x.H = Hpart(h, 0); x.b = bpart(h, 0); x.accSC = h->d_accSC; x.rstats = h->d_rstats_all; x.cnt = h->d_cnt_all;
+  x.gate = hs->gate; x.err = hs->d_ctl + 2;
+  launch_stitch_xchg(h, x, h->P);
+  if (th_deferred) hs->th_pending = false;   // runs in the spare CTA of the solve launch below
   SolveArgs s;
   s.th = th_def; s.do_th = th_deferred;
   s.nf = nf; s.D = D;
@@ -1123,7 +1145,7 @@ API int sosba_solve_system(sosba_t *h, const double *HM, const double *bM, doubl
       (rc = down(h, hs->pin_i, hs->d_ctl + 2, 1)))
     return rc;
   if ((rc = sync(h))) return rc;
-  if (hs->pin_i[0]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
+  if (hs->pin_i[0]) return solve_flag_error(hs->pin_i[0]);
   return SOSBA_OK;
 }
 
@@ -1173,7 +1195,7 @@ API int sosba_marginalize_points(sosba_t *h, const int32_t *ids, int32_t n, doub
   a.rec = h->r_rec; a.accTop = h->d_accTop; a.n_acc = hs->d_cnt;
   launch_top_accumulate(h, a);
   launch_point_sc(h, sc_args(h, 2, d_pl, n, 0));
-  if ((rc = sosba_allreduce_acc(h, 0, nullptr, nullptr, nullptr, nullptr))) return rc;
+  if ((rc = sosba_allreduce_acc(h, 0))) return rc;
   launch_stitch_top(h, h->d_accTop, h->d_adHost, h->d_adTarget, nf, Hpart(h, 0), bpart(h, 0), 0, h->d_wprior, h->d_calib + 6);
   launch_finalize_sc(h, h->d_accSC, nf, Hpart(h, 2), bpart(h, 2));
   SOSBA_CUDA(cudaGetLastError());
@@ -1562,7 +1584,7 @@ API int sosba_ba_iterate(sosba_t *h, int32_t n, int32_t *n_res) {
   flush_pending_th(h);
   if ((rc = down(h, hs->pin_i, hs->d_ctl + 2, 1))) return rc;
   if ((rc = sync(h))) return rc;
-  if (hs->pin_i[0]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
+  if (hs->pin_i[0]) return solve_flag_error(hs->pin_i[0]);
   if (n_res) *n_res = h->R - hs->n_lin;
   return SOSBA_OK;
 }
@@ -1636,7 +1658,7 @@ API int sosba_ba_optimize(sosba_t *h, int32_t mnumOptIts, sosba_optimize_out *ou
   }
   sosba_linearize_out lo;
   if ((rc = read_linearize_out(h, &lo))) { hs->download_ready = false; return rc; }   // the one synchronisation
-  if (hs->pin_i[2]) { sosba_set_error("non-finite solution"); return SOSBA_E_NONFINITE; }
+  if (hs->pin_i[2]) return solve_flag_error(hs->pin_i[2]);
   {
     const int *c0 = (const int *)(hs->pin_d + 16 + 2);
     out->reserved0 = c0[0] + c0[1] + c0[2];   // residuals linearised per pass (bench bookkeeping)

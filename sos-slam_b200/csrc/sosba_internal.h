@@ -150,12 +150,11 @@ struct sosba {
   float *d_newE_all = nullptr;      // [world][newE_cap] newest-frame energies, one segment per rank ...
   int *d_newE_cnt = nullptr;        // ... [world] lengths, stored right behind the segments
   int newE_cap = 0;
-  // peer-memory exchange (comm.cu): every rank pushes its partial tables into the other ranks' mailboxes over NVLink
-  unsigned char *p2p_mbox = nullptr;          // this rank's mailbox: [256-byte header] [2 parities][world slots of {payload, exchange number} words]
+  // peer-memory exchange (k_xchg.cu, comm.cu): every rank pushes its stitched values into the other ranks' mailboxes over NVLink
+  unsigned char *p2p_mbox = nullptr;          // this rank's mailbox: [2 parities][world slots of {payload, exchange number} words]
   unsigned char *p2p_peer[8] = {nullptr};     // the mailboxes of all ranks as mapped into this process (p2p_peer[rank] = own)
   size_t p2p_slot_bytes = 0;
-  int p2p_epoch = 0;
-  int *p2p_ticket = nullptr;                  // last-CTA counter of the push kernel
+  int *p2p_epoch_dev = nullptr;               // device: [0] exchange number (advanced by the exchange kernel itself), [1] its CTA ticket
   bool p2p = false;
   int *d_comm_int = nullptr;                  // scratch of sosba_comm_max_int
 };

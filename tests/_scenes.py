@@ -42,6 +42,9 @@ def scene(**kw):
 SMALL = dict(w=320, h=240, nf=5, n_points=400, seed=3)
 CONFIG_B = dict(w=640, h=480, nf=8, n_points=2000, seed=1234)       # BASELINE.json configs[1]
 KITTI = dict(w=1232, h=368, nf=12, n_points=4000, seed=5, forward_motion=True)  # configs[3] shape
+# configs[2] shape: EuRoC 752x480 with the intrinsics of tests/EuRoC/camera0.txt (relative K of Undistort::readFromFile, pre-rectified)
+EUROC = dict(w=752, h=480, nf=8, n_points=2000, seed=11, fx=0.6099 * 752, fy=0.9527 * 480, cx=0.4890 * 752 - 0.5, cy=0.5185 * 480 - 0.5)
+TUMVI = dict(w=512, h=512, nf=8, n_points=2000, seed=12)   # configs[4] shape: 512x512, 4 pyramid levels
 
 
 def open_handle(lib, sc, threads=1):

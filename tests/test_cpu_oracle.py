@@ -794,3 +794,19 @@ def test_pixel_select_random_images(orc, seed):
         ref, n = np_ref.sel_select_ref(dI0, absg, ths_s, rp, pot)
         assert got["n"] == sum(n) and np.array_equal(got["map"], ref), (pot, got["n"], n)
     hd.close()
+
+
+def test_residuals_set_rejects_bad_indices(orc):
+    """a point index of -1 (and a target outside the window) is an argument error, not an out-of-bounds read."""
+    from sos_slam_b200 import binding, problem
+    sc = scene(**TINY)
+    h = open_handle(orc, sc)
+    upload(h, sc)
+    res = problem.residuals_of(sc)
+    for field, idx, val in (("point", 0, -1), ("target", 2, -1), ("target", 2, sc.nf)):
+        bad = {k: v.copy() for k, v in res.items()}
+        bad[field][idx] = val
+        with pytest.raises(binding.SosbaError):
+            h.residuals_set(bad)
+    h.residuals_set(res)
+    h.close()

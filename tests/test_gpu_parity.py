@@ -277,6 +277,38 @@ def test_edge_cases(gpu, orc):
         h.close()
 
 
+def test_bad_arguments_are_rejected(gpu):
+    """The C ABI turns bad caller input into SOSBA_E_ARG instead of reading out of bounds: a negative point index, a target
+    outside the window, residuals that are not point-major, and null mandatory arrays."""
+    import ctypes as C
+    from sos_slam_b200 import binding, problem
+    sc = scene(**SMALL)
+    h = open_handle(gpu, sc)
+    upload(h, sc)
+    res = problem.residuals_of(sc)
+    for field, idx, val in (("point", 0, -1), ("point", 5, 10 ** 6), ("target", 3, -1), ("target", 3, sc.nf)):
+        bad = {k: v.copy() for k, v in res.items()}
+        bad[field][idx] = val
+        with pytest.raises(binding.SosbaError) as e:
+            h.residuals_set(bad)
+        assert "rc=-1" in str(e.value)
+    bad = {k: v.copy() for k, v in res.items()}
+    bad["point"][[0, -1]] = bad["point"][[-1, 0]]
+    with pytest.raises(binding.SosbaError):
+        h.residuals_set(bad)
+    S, keep = h._residuals_struct(res)
+    S.point = None
+    assert gpu.f("residuals_set")(h.h, C.byref(S)) == -1
+    S, keep = h._points_struct(problem.points_of(sc))
+    S.color = None
+    assert gpu.f("points_set")(h.h, C.byref(S)) == -1
+    # the handle is still usable
+    h.points_set(problem.points_of(sc))
+    h.residuals_set(res)
+    assert h.linearize_all(False)["n_in"] > 0
+    h.close()
+
+
 # ---- next row (SURVEY.md 8f rank 1): immature points ------------------------------------------------
 @pytest.mark.parametrize("cfg", [SMALL, CONFIG_B, KITTI], ids=["small", "configB", "kitti"])
 def test_immature_trace_bit_exact(gpu, orc, cfg):

@@ -48,8 +48,6 @@ int load_nccl() {
 // handles all-gathered through the NCCL communicator that exists anyway) and the NCCL collectives of the API-level calls
 // outside the loop (sosba_accumulate, sosba_marginalize_points, sosba_linearize_all) and of the fallback when peer
 // mapping is unavailable (SOSBA_COMM_NCCL=1 forces it).
-#define P2P_MAX_NF 13        // k_solve's limit
-#define P2P_MAX_NEWE 16384   // newest-frame energies per rank a mailbox slot can carry
 
 #define API extern "C" __attribute__((visibility("default")))
 
@@ -57,7 +55,7 @@ int load_nccl() {
 static int p2p_setup(sosba *h) {
   h->p2p = false;
   if (h->world < 2 || h->world > 8 || getenv("SOSBA_COMM_NCCL")) return SOSBA_OK;
-  h->p2p_slot_bytes = stitch_xchg_slot_bytes(P2P_MAX_NF, P2P_MAX_NEWE);
+  h->p2p_slot_bytes = stitch_xchg_slot_bytes(SOSBA_XCHG_MAX_NF, SOSBA_XCHG_MAX_NEWE);
   const size_t bytes = 2 * (size_t)h->world * h->p2p_slot_bytes;
   int ok = 1;
   if (cudaMalloc((void **)&h->p2p_mbox, bytes) != cudaSuccess) { cudaGetLastError(); ok = 0; }
@@ -176,7 +174,7 @@ void sosba_xchg_args(sosba *h, StitchXchgArgs *a, int with_newE) {
   a->epoch = h->p2p_epoch_dev;
   a->newE_all = h->d_newE_all; a->newE_cnt = h->d_newE_cnt; a->newE_cap = h->newE_cap;
   a->with_newE = with_newE && h->d_newE_all;
-  a->push = (h->comm && h->world > 1 && h->p2p && h->nf <= P2P_MAX_NF && h->newE_cap <= P2P_MAX_NEWE) ? 1 : 0;
+  a->push = (h->comm && h->world > 1 && h->p2p && h->nf <= SOSBA_XCHG_MAX_NF && h->newE_cap <= SOSBA_XCHG_MAX_NEWE) ? 1 : 0;
 }
 
 // the linearisation sums of an API-level linearizeAll: energy (1 double), state histogram + removals (4 ints), energies

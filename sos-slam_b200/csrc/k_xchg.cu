@@ -94,22 +94,101 @@ __device__ __forceinline__ bool ll8_load(const unsigned char *p, unsigned ep, un
   }
 }
 
-// the 13x13 block of one (host,target) pair, A and L passes summed, into shared memory (symmetric); 64 threads
-__device__ __forceinline__ void load_block(const StitchXchgArgs &a, int blk, int l, double (*accH)[13]) {
-  const int n2 = a.nf * a.nf;
-  for (int e = l; e < 91; e += 64) {
-    const double v = a.accTop[(size_t)blk * SOSBA_TOPB + e] + a.accTop[((size_t)n2 + blk) * SOSBA_TOPB + e];
-    int r, c;
-    entry_rc(e, r, c);
-    accH[r][c] = v; accH[c][r] = v;
+// newest-frame energies: every rank's segment is copied into every other rank's list (8-byte {float, exchange number}
+// words behind `ebase` of the slot, word 0 = the segment length); CTA `cta` of `ncta`
+__device__ __forceinline__ void exchange_energies(const StitchXchgArgs &a, unsigned ep, int parity, size_t ebase, int cta, int ncta, long long t0, bool &ok) {
+  const int first = cta * XT + (int)threadIdx.x, stride = ncta * XT;
+  const int my_n = min(a.newE_cnt[a.rank], a.newE_cap);
+  const float *src = a.newE_all + (size_t)a.rank * a.newE_cap;
+  for (int p = 0; p < a.world; p++) {
+    if (p == a.rank) continue;
+    unsigned char *dst = slot_of(a, p, parity, a.rank) + ebase;
+    if (first == 0) ll8_store(dst, (unsigned)my_n, ep);
+    for (int k = first; k < my_n; k += stride) ll8_store(dst + 8 * (size_t)(1 + k), __float_as_uint(src[k]), ep);
+  }
+  for (int r = 0; r < a.world && ok; r++) {
+    if (r == a.rank) continue;
+    const unsigned char *s8 = slot_of(a, a.rank, parity, r) + ebase;
+    unsigned n = 0;
+    ok = ll8_load(s8, ep, n, t0);
+    if (!ok) break;
+    if ((int)n > a.newE_cap) n = (unsigned)a.newE_cap;
+    if (first == 0) a.newE_cnt[r] = (int)n;
+    float *dst = a.newE_all + (size_t)r * a.newE_cap;
+    for (int k = first; k < (int)n && ok; k += stride) {
+      unsigned v;
+      ok = ll8_load(s8 + 8 * (size_t)(1 + k), ep, v, t0);
+      if (ok) dst[k] = __uint_as_float(v);
+    }
   }
 }
 
-__global__ void __launch_bounds__(XT) k_stitch_xchg(StitchXchgArgs a, Layout L) {
-  __shared__ double s_acc[4][13][13];
-  __shared__ double s_M[4][2][64];
-  __shared__ double s_X[4][64];
-  __shared__ double s_part[12][64 + 32 + 8];
+// the CTA that finishes last advances the exchange number (every CTA read it before it could finish)
+__device__ __forceinline__ void finish_exchange(const StitchXchgArgs &a, unsigned ep) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(a.epoch + 1, 1) == (int)gridDim.x - 1) {
+      a.epoch[1] = 0;
+      a.epoch[0] = ep + 1u == 0u ? 1 : (int)(ep + 1u);
+    }
+  }
+}
+
+// Shared-memory staging of the (host,target) blocks one CTA needs ("terms"): all of them are fetched in ONE phase (a single
+// global-memory round trip), A and L passes summed.  Per term: P = block[4:12,4:12] (8x8, symmetric), C = block[4:12,0:4]
+// (8x4) followed by r = block[4:12,12] (8), the left adjoint ML (and for off-diagonal tiles the right adjoint MR).
+constexpr int X_MAXT = 24;              // terms per CTA: 2 (nf - 1) for a diagonal tile, nf <= 13
+constexpr int XS_P = 0, XS_C = XS_P + X_MAXT * 64, XS_ML = XS_C + X_MAXT * 40, XS_X = XS_ML + X_MAXT * 64, XS_TOTAL = XS_X + X_MAXT * 64;
+
+// where entry e of a block lands in the staging area: bits 0..7 first offset, 8..15 mirrored offset (0xff = none), bit 16 = C/r
+// area (else P), 0xffffffff = not needed (calibration rows, rr)
+__device__ __forceinline__ unsigned stage_slot(int e) {
+  int r, c;
+  entry_rc(e, r, c);   // r <= c
+  if (r >= 4) {
+    if (c < 12) return (unsigned)((r - 4) * 8 + c - 4) | ((unsigned)((c - 4) * 8 + r - 4) << 8);
+    if (r < 12) return (unsigned)(32 + r - 4) | 0xff00u | 0x10000u;
+    return 0xffffffffu;
+  }
+  if (c >= 4 && c < 12) return (unsigned)((c - 4) * 4 + r) | 0xff00u | 0x10000u;
+  return 0xffffffffu;
+}
+
+// BLK(k) -> block index of term k.  All loads of a thread are issued before the first one is consumed.
+template <int ITERS, class BlkFn>
+__device__ __forceinline__ void stage_blocks(const StitchXchgArgs &a, BlkFn blk_of, int nterms, double *sm, int tid) {
+  const int n2 = a.nf * a.nf, total = nterms * 91;
+  double va[ITERS], vl[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; it++) {
+    const int idx = tid + it * XT;
+    va[it] = vl[it] = 0.0;
+    if (idx < total) {
+      const int term = idx / 91, e = idx - term * 91, blk = blk_of(term);
+      va[it] = a.accTop[(size_t)blk * SOSBA_TOPB + e];
+      vl[it] = a.accTop[((size_t)n2 + blk) * SOSBA_TOPB + e];
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < ITERS; it++) {
+    const int idx = tid + it * XT;
+    if (idx < total) {
+      const int term = idx / 91, e = idx - term * 91;
+      const unsigned sl = stage_slot(e);
+      if (sl != 0xffffffffu) {
+        const double v = va[it] + vl[it];
+        double *dst = sm + ((sl & 0x10000u) ? XS_C + term * 40 : XS_P + term * 64);
+        dst[sl & 0xff] = v;
+        if (((sl >> 8) & 0xff) != 0xff) dst[(sl >> 8) & 0xff] = v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(XT, 1) k_stitch_xchg(StitchXchgArgs a, Layout L) {
+  __shared__ double sm[XS_TOTAL];
+  __shared__ int s_blk[X_MAXT];
   PDL_ENTER();
   if (a.gate && *a.gate) return;
   const int tid = threadIdx.x, g = tid >> 6, l = tid & 63, i = l >> 3, j = l & 7;
@@ -123,48 +202,59 @@ __global__ void __launch_bounds__(XT) k_stitch_xchg(StitchXchgArgs a, Layout L) 
   if (bid < L.cta_pair) {
     // ---- diagonal tile of frame af: H[af,af], H[af,calib], b[af] ------------------------------------------------
     // = sum over targets t != af of the host terms Ah P Ah^T (block af + nf t) + sum over hosts h != af of the target terms
-    //   At P At^T (block h + nf af), four terms at a time (one per 64-thread group), partial sums added in group order
+    //   At P At^T (block h + nf af); the terms are dealt round-robin to the four 64-thread groups, partial sums added in
+    //   group order
     const int af = bid, nterms = 2 * (nf - 1);
-    double o = 0.0, fc = 0.0, bb = 0.0;
-    for (int k0 = 0; k0 < nterms; k0 += 4) {
-      const int k = k0 + g;
-      const bool act = k < nterms;
-      if (act) {
-        int blk;
-        const double *Msrc;
-        if (k < nf - 1) { const int t = k < af ? k : k + 1; blk = af + nf * t; Msrc = a.adHost + 64 * (size_t)blk; }
-        else { const int kk = k - (nf - 1), hh = kk < af ? kk : kk + 1; blk = hh + nf * af; Msrc = a.adTarget + 64 * (size_t)blk; }
-        load_block(a, blk, l, s_acc[g]);
-        s_M[g][0][l] = Msrc[l];
+    auto blk_of = [&](int k) -> int {
+      if (k < nf - 1) { const int t = k < af ? k : k + 1; return af + nf * t; }
+      const int kk = k - (nf - 1), hh = kk < af ? kk : kk + 1;
+      return hh + nf * af;
+    };
+    {  // adjoints: adHost of the host terms, adTarget of the target terms
+      double m[(X_MAXT * 64 + XT - 1) / XT];
+#pragma unroll
+      for (int it = 0; it < (X_MAXT * 64 + XT - 1) / XT; it++) {
+        const int idx = tid + it * XT, k = idx >> 6;
+        m[it] = idx < nterms * 64 ? (k < nf - 1 ? a.adHost : a.adTarget)[64 * (size_t)blk_of(k) + (idx & 63)] : 0.0;
       }
-      __syncthreads();
-      if (act) {
-        double x = 0.0;
+      stage_blocks<(X_MAXT * 91 + XT - 1) / XT>(a, blk_of, nterms, sm, tid);
 #pragma unroll
-        for (int q = 0; q < 8; q++) x += s_M[g][0][i * 8 + q] * s_acc[g][4 + q][4 + j];
-        s_X[g][l] = x;
+      for (int it = 0; it < (X_MAXT * 64 + XT - 1) / XT; it++) {
+        const int idx = tid + it * XT;
+        if (idx < nterms * 64) sm[XS_ML + idx] = m[it];
       }
-      __syncthreads();
-      if (act) {
-        const int ii = max(i, j), jj = min(i, j);   // both triangles from the same expression: exactly symmetric
-#pragma unroll
-        for (int q = 0; q < 8; q++) o += s_X[g][ii * 8 + q] * s_M[g][0][jj * 8 + q];
-        if (j < 4) {
-#pragma unroll
-          for (int q = 0; q < 8; q++) fc += s_M[g][0][i * 8 + q] * s_acc[g][4 + q][j];
-        } else if (j == 4) {
-#pragma unroll
-          for (int q = 0; q < 8; q++) bb += s_M[g][0][i * 8 + q] * s_acc[g][4 + q][12];
-        }
-      }
-      __syncthreads();
     }
-    s_part[g][l] = o;
-    if (j < 4) s_part[g][64 + i * 4 + j] = fc;
-    else if (j == 4) s_part[g][96 + i] = bb;
+    __syncthreads();
+    for (int k = g; k < nterms; k += 4) {
+      const double *M = sm + XS_ML + k * 64, *P = sm + XS_P + k * 64;
+      double x = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) x += M[i * 8 + q] * P[q * 8 + j];
+      sm[XS_X + k * 64 + l] = x;
+    }
+    __syncthreads();
+    double o = 0.0, fc = 0.0;
+    const int ii = max(i, j), jj = min(i, j);   // both triangles from the same expression: exactly symmetric
+    for (int k = g; k < nterms; k += 4) {
+      const double *M = sm + XS_ML + k * 64, *X = sm + XS_X + k * 64, *C = sm + XS_C + k * 40;
+#pragma unroll
+      for (int q = 0; q < 8; q++) o += X[ii * 8 + q] * M[jj * 8 + q];
+      if (j < 4) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) fc += M[i * 8 + q] * C[q * 4 + j];
+      } else if (j == 4) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) fc += M[i * 8 + q] * C[32 + q];
+      }
+    }
+    __syncthreads();
+    double *part = sm + XS_P;   // [4][XW_DIAG], the staged blocks are consumed
+    part[g * XW_DIAG + l] = o;
+    if (j < 4) part[g * XW_DIAG + 64 + i * 4 + j] = fc;
+    else if (j == 4) part[g * XW_DIAG + 96 + i] = fc;
     __syncthreads();
     if (tid < XW_DIAG) {
-      double v = ((s_part[0][tid] + s_part[1][tid]) + s_part[2][tid]) + s_part[3][tid];
+      double v = ((part[tid] + part[XW_DIAG + tid]) + part[2 * XW_DIAG + tid]) + part[3 * XW_DIAG + tid];
       if (push) v = xchg_sum(a, ep, parity, af * XW_DIAG + tid, v, t0, ok);
       if (ok) {
         const int r0 = 4 + 8 * af;
@@ -175,32 +265,40 @@ __global__ void __launch_bounds__(XT) k_stitch_xchg(StitchXchgArgs a, Layout L) 
     }
   } else if (bid < L.cta_misc) {
     // ---- four off-diagonal tiles, one per 64-thread group: H[fa,fb] = Ah P At^T of block (fa,fb) + (Ah P At^T of block (fb,fa))^T
+    // terms 2g, 2g+1 of group g; left / right factors: (adHost, adTarget) of block (fa,fb), then (adTarget, adHost) of block (fb,fa)
     const int q = 4 * (bid - L.cta_pair) + g;
     const bool act = q < L.npairs;
     int fa = 0, fb = 1;
     if (act) { int rem = q; while (rem >= nf - 1 - fa) { rem -= nf - 1 - fa; fa++; } fb = fa + 1 + rem; }
-    double o = 0.0;
+    const int b0 = fa + nf * fb, b1 = fb + nf * fa;
+    if (l < 2) s_blk[2 * g + l] = l == 0 ? b0 : b1;
+    double *MR = sm + XS_ML + 8 * 64;   // right factors of the 8 terms, behind the 8 left factors
+    const double m0 = a.adHost[64 * (size_t)b0 + l], m1 = a.adTarget[64 * (size_t)b0 + l];
+    const double m2 = a.adTarget[64 * (size_t)b1 + l], m3 = a.adHost[64 * (size_t)b1 + l];
+    __syncthreads();
+    stage_blocks<(8 * 91 + XT - 1) / XT>(a, [&](int k) -> int { return s_blk[k]; }, 8, sm, tid);
+    sm[XS_ML + (2 * g) * 64 + l] = m0;
+    MR[(2 * g) * 64 + l] = m1;
+    sm[XS_ML + (2 * g + 1) * 64 + l] = m2;
+    MR[(2 * g + 1) * 64 + l] = m3;
+    __syncthreads();
+#pragma unroll
     for (int term = 0; term < 2; term++) {
-      const int blk = term == 0 ? fa + nf * fb : fb + nf * fa;
-      if (act) {
-        load_block(a, blk, l, s_acc[g]);
-        // left factor, right factor: (adHost, adTarget) of block (fa,fb), then (adTarget, adHost) of block (fb,fa)
-        s_M[g][0][l] = (term == 0 ? a.adHost : a.adTarget)[64 * (size_t)blk + l];
-        s_M[g][1][l] = (term == 0 ? a.adTarget : a.adHost)[64 * (size_t)blk + l];
-      }
-      __syncthreads();
-      if (act) {
-        double x = 0.0;
+      const int k = 2 * g + term;
+      const double *M = sm + XS_ML + k * 64, *P = sm + XS_P + k * 64;
+      double x = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) x += s_M[g][0][i * 8 + k] * s_acc[g][4 + k][4 + j];
-        s_X[g][l] = x;
-      }
-      __syncthreads();
-      if (act) {
+      for (int qq = 0; qq < 8; qq++) x += M[i * 8 + qq] * P[qq * 8 + j];
+      sm[XS_X + k * 64 + l] = x;
+    }
+    __syncthreads();
+    double o = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) o += s_X[g][i * 8 + k] * s_M[g][1][j * 8 + k];
-      }
-      __syncthreads();
+    for (int term = 0; term < 2; term++) {
+      const int k = 2 * g + term;
+      const double *X = sm + XS_X + k * 64, *R = MR + k * 64;
+#pragma unroll
+      for (int qq = 0; qq < 8; qq++) o += X[i * 8 + qq] * R[j * 8 + qq];
     }
     if (act) {
       double v = o;
@@ -218,14 +316,19 @@ __global__ void __launch_bounds__(XT) k_stitch_xchg(StitchXchgArgs a, Layout L) 
       int e;
       if (ent < 16) { const int r = min(ent >> 2, ent & 3), c = max(ent >> 2, ent & 3); e = r * 10 - r * (r - 1) / 2 + (c - r); }
       else e = 55 + 3 * (ent - 16) + 2;
+      constexpr int MI = (2 * (X_MAXT / 2 + 1) * (X_MAXT / 2 + 1) + 11) / 12;   // all loads in flight before the first add
+      double v[MI];
+#pragma unroll
+      for (int it = 0; it < MI; it++) { const int blk = slice + 12 * it; v[it] = blk < nblk ? a.accTop[(size_t)blk * SOSBA_TOPB + e] : 0.0; }
       double s = 0.0;
-      for (int blk = slice; blk < nblk; blk += 12) s += a.accTop[(size_t)blk * SOSBA_TOPB + e];
-      s_part[slice][ent] = s;
+#pragma unroll
+      for (int it = 0; it < MI; it++) s += v[it];
+      sm[slice * 20 + ent] = s;
     }
     __syncthreads();
     if (tid < 30) {
       double v;
-      if (tid < 20) { v = 0.0; for (int s = 0; s < 12; s++) v += s_part[s][tid]; }
+      if (tid < 20) { v = 0.0; for (int s = 0; s < 12; s++) v += sm[s * 20 + tid]; }
       else if (tid < 28) v = a.rstats[tid - 20];
       else v = (double)a.cnt[tid - 28];
       if (push) v = xchg_sum(a, ep, parity, L.base_misc + tid, v, t0, ok);
@@ -246,44 +349,33 @@ __global__ void __launch_bounds__(XT) k_stitch_xchg(StitchXchgArgs a, Layout L) 
       }
     }
   } else if (push && a.with_newE) {
-    // ---- newest-frame energies: every rank's segment is copied into every other rank's list ------------------------
-    const int ne = gridDim.x - L.cta_e, first = (bid - L.cta_e) * XT + tid, stride = ne * XT;
-    const size_t ebase = (size_t)L.nv * 16;
-    const int my_n = a.newE_cnt[a.rank];
-    const float *src = a.newE_all + (size_t)a.rank * a.newE_cap;
-    for (int p = 0; p < a.world; p++) {
-      if (p == a.rank) continue;
-      unsigned char *dst = slot_of(a, p, parity, a.rank) + ebase;
-      if (first == 0) ll8_store(dst, (unsigned)my_n, ep);
-      for (int k = first; k < my_n; k += stride) ll8_store(dst + 8 * (size_t)(1 + k), __float_as_uint(src[k]), ep);
-    }
-    for (int r = 0; r < a.world && ok; r++) {
-      if (r == a.rank) continue;
-      const unsigned char *s8 = slot_of(a, a.rank, parity, r) + ebase;
-      unsigned n = 0;
-      ok = ll8_load(s8, ep, n, t0);
-      if (!ok) break;
-      if ((int)n > a.newE_cap) n = (unsigned)a.newE_cap;
-      if (first == 0) a.newE_cnt[r] = (int)n;
-      float *dst = a.newE_all + (size_t)r * a.newE_cap;
-      for (int k = first; k < (int)n && ok; k += stride) {
-        unsigned v;
-        ok = ll8_load(s8 + 8 * (size_t)(1 + k), ep, v, t0);
-        if (ok) dst[k] = __uint_as_float(v);
-      }
-    }
+    exchange_energies(a, ep, parity, (size_t)L.nv * 16, bid - L.cta_e, gridDim.x - L.cta_e, t0, ok);
   }
   if (!ok && a.err) atomicOr(a.err, 2);   // reported by the caller as SOSBA_E_NCCL (peer exchange timed out)
-  if (!push) return;
-  // ---- the CTA that finishes last advances the exchange number (every CTA read it before it could finish) ------------
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    if (atomicAdd(a.epoch + 1, 1) == (int)gridDim.x - 1) {
-      a.epoch[1] = 0;
-      a.epoch[0] = ep + 1u == 0u ? 1 : (int)(ep + 1u);
+  if (push) finish_exchange(a, ep);
+}
+
+// The sums of an API-level linearizeAll outside the loop over the ranks (FullSystemOptimize.cpp:125-182: energy, state
+// histogram, removals) and the newest-frame energies for setNewFrameEnergyTH, through the same mailboxes.
+// CTA 0: sums; CTAs 1..: energies.  with_stats = 0: energies only (the pending selection of a fused linearisation).
+__global__ void __launch_bounds__(XT) k_lin_xchg(StitchXchgArgs a, double *stats, int *counts, int with_stats) {
+  PDL_ENTER();
+  if (a.gate && *a.gate) return;
+  const unsigned ep = (unsigned)a.epoch[0];
+  const int parity = (int)(ep & 1u), tid = threadIdx.x;
+  const long long t0 = clock64();
+  bool ok = true;
+  if (blockIdx.x == 0) {
+    if (with_stats && tid < 5) {
+      double v = tid == 0 ? stats[0] : (double)counts[tid - 1];
+      v = xchg_sum(a, ep, parity, tid, v, t0, ok);
+      if (ok) { if (tid == 0) stats[0] = v; else counts[tid - 1] = (int)v; }
     }
+  } else if (a.with_newE) {
+    exchange_energies(a, ep, parity, 16 * 16, blockIdx.x - 1, gridDim.x - 1, t0, ok);
   }
+  if (!ok && a.err) atomicOr(a.err, 2);
+  finish_exchange(a, ep);
 }
 
 }  // namespace
@@ -293,10 +385,19 @@ size_t stitch_xchg_slot_bytes(int nf_max, int newE_cap) {
   return (((size_t)L.nv * 16 + 8 * (size_t)(1 + newE_cap)) + 255) & ~(size_t)255;
 }
 
-void launch_stitch_xchg(sosba *h, const StitchXchgArgs &a0, int local_points) {
+int launch_stitch_xchg(sosba *h, const StitchXchgArgs &a0, int local_points) {
   StitchXchgArgs a = a0;
+  if (2 * (a.nf - 1) > X_MAXT) { sosba_set_error("the fused stitch supports nf <= %d, got %d", X_MAXT / 2 + 1, a.nf); return SOSBA_E_ARG; }
   const int ne = (a.push && a.with_newE) ? (local_points + XT - 1) / XT + 1 : 0;
   const Layout L = make_layout(a.nf, ne);
   launch_pdl(k_stitch_xchg, a.push ? L.n_cta : L.cta_sc, XT, 0, h->stream, a, L);   // without peers the Schur matrix stays as it is
+  h->launches++;
+  return SOSBA_OK;
+}
+
+// point shards, outside the loop: see k_lin_xchg.  Only with the peer mailboxes (a.push); the caller falls back to NCCL.
+void launch_lin_xchg(sosba *h, const StitchXchgArgs &a, double *stats, int *counts, int with_stats, int local_points) {
+  const int ne = a.with_newE ? (local_points + XT - 1) / XT + 1 : 0;
+  launch_pdl(k_lin_xchg, 1 + ne, XT, 0, h->stream, a, stats, counts, with_stats);
   h->launches++;
 }

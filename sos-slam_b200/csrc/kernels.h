@@ -186,8 +186,11 @@ struct StitchXchgArgs {
   const int *gate;             // non-null: skip when *gate != 0 (the loop broke on the device -- on every rank alike)
   int *err;                    // set to 2 when a peer's words did not arrive in time
 };
+#define SOSBA_XCHG_MAX_NF 13        // k_solve's limit
+#define SOSBA_XCHG_MAX_NEWE 16384   // newest-frame energies per rank a mailbox slot can carry
 size_t stitch_xchg_slot_bytes(int nf_max, int newE_cap);
-void launch_stitch_xchg(sosba *h, const StitchXchgArgs &a, int local_points);
+int launch_stitch_xchg(sosba *h, const StitchXchgArgs &a, int local_points);
+void launch_lin_xchg(sosba *h, const StitchXchgArgs &a, double *stats, int *counts, int with_stats, int local_points);
 // accSC -> Hsc (D*D), bsc (D)
 void launch_finalize_sc(sosba *h, const double *accSC, int nf, double *H, double *b);
 
@@ -235,7 +238,7 @@ struct ResubArgs {
   double *stats;  // [1] sum step^2  [2] sum |idepth_backup|  [3] count
   const int *gate;     // non-null: skip when *gate != 0
   double *zero_lin;    // non-null: clear the linearisation sums (2 doubles + 5 ints) for the launch that follows
-  float *zero_newE;    // non-null (point shards): clear all ranks' newest-frame energy segments + their counts
+  float *zero_newE;    // non-null (point shards): clear the newest-frame energy counts (NCCL fallback: all ranks' segments too)
   int zero_newE_n;     // floats + ints to clear, as 4-byte words
 };
 void launch_resubstitute(sosba *h, const ResubArgs &a);

@@ -118,6 +118,7 @@ struct HostSide {
   std::vector<cudaEvent_t> prof_ev;   // (start, stop) pairs around the linearize kernel
 };
 static HostSide *HS(sosba *h);
+static int solve_flag_error(int flag);
 
 #define API extern "C" __attribute__((visibility("default")))
 #define CHECK_H(h) do { if (!(h)) { sosba_set_error("null handle"); return SOSBA_E_ARG; } cudaSetDevice((h)->device); } while (0)
@@ -697,7 +698,10 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
   }
   if (h->comm && h->world > 1) {   // point shards: room for every rank's newest-frame energies (one per local point at most)
     int cap = 0;
-    if ((rc = sosba_comm_max_int(h, ((P + 63) / 64 + 1) * 64, &cap))) return rc;
+    if (h->p2p) {   // peer mailboxes: a fixed capacity, so no collective (and no synchronisation) per keyframe
+      cap = SOSBA_XCHG_MAX_NEWE;
+      if (P > cap) { sosba_set_error("%d points in one shard: the peer exchange carries at most %d (set SOSBA_COMM_NCCL=1)", P, cap); return SOSBA_E_ARG; }
+    } else if ((rc = sosba_comm_max_int(h, ((P + 63) / 64 + 1) * 64, &cap))) return rc;
     if (cap > h->newE_cap) {
       dfree(h, h->d_newE_all);
       DALLOC(h, h->d_newE_all, (size_t)h->world * cap + h->world);
@@ -778,14 +782,31 @@ API int sosba_reset_oob(sosba_t *h) {
 }
 
 // the threshold selection of a fused linearisation that no accumulation picked up yet
-static void clear_gathered_energies(sosba *h) {   // point shards: every segment must be empty before the next append / reduce
-  if (h->d_newE_all) cudaMemsetAsync(h->d_newE_all, 0, ((size_t)h->world * h->newE_cap + h->world) * 4, h->stream);
+static void clear_gathered_energies(sosba *h) {   // point shards: the list must be empty before the next append
+  if (!h->d_newE_all) return;
+  // peer mailboxes: only the lengths (the exchange overwrites the other ranks' segments); NCCL: a sum with zeros is the
+  // concatenation, so every segment has to be zero
+  if (h->p2p) cudaMemsetAsync(h->d_newE_cnt, 0, (size_t)h->world * 4, h->stream);
+  else cudaMemsetAsync(h->d_newE_all, 0, ((size_t)h->world * h->newE_cap + h->world) * 4, h->stream);
+}
+
+// point shards: the sums of a linearizeAll outside the loop (with_stats) and the newest-frame energies over the ranks
+static int exchange_lin(sosba *h, int with_stats) {
+  if (!h->comm || h->world <= 1) return SOSBA_OK;
+  StitchXchgArgs x;
+  memset(&x, 0, sizeof(x));
+  sosba_xchg_args(h, &x, 1);
+  if (!x.push) return sosba_allreduce_lin(h, with_stats);
+  HostSide *hs = HS(h);
+  x.gate = hs->gate; x.err = hs->d_ctl + 2;
+  launch_lin_xchg(h, x, h->d_stats, h->d_counts, with_stats, h->P);
+  return SOSBA_OK;
 }
 
 static void flush_pending_th(sosba *h) {
   HostSide *hs = HS(h);
   if (!hs->th_pending) return;
-  sosba_allreduce_lin(h, 0);
+  exchange_lin(h, 0);
   launch_energy_th(h, lin_args(h).th, hs->gate);
   clear_gathered_energies(h);
   hs->th_pending = false;
@@ -799,7 +820,7 @@ static void enqueue_linearize(sosba *h, int fix) {
   LinArgs a = lin_args(h);
   launch_linearize(h, a);   // (the bench roofline brackets the fused launches of the loop, enqueue_linearize_apply)
   if (fix) launch_apply_res(h, a, 1);
-  sosba_allreduce_lin(h, 1);   // point shards: global energy, state histogram, removals, newest-frame energies
+  exchange_lin(h, 1);   // point shards: global energy, state histogram, removals, newest-frame energies
   launch_energy_th(h, a.th);
   clear_gathered_energies(h);
 }
@@ -809,7 +830,10 @@ static int read_linearize_out(sosba *h, sosba_linearize_out *out) {
   int rc;
   flush_pending_th(h);
   if ((rc = down(h, hs->pin_d, h->d_stats, 12))) return rc;   // energy | pad | counts[16] | thOut[4]
+  const bool sharded = h->comm && h->world > 1 && hs->d_ctl;
+  if (sharded && (rc = down(h, hs->pin_i + 8, hs->d_ctl + 2, 1))) return rc;
   if ((rc = sync(h))) return rc;
+  if (sharded && (hs->pin_i[8] & 2)) return solve_flag_error(hs->pin_i[8]);
   if (out) {
     const int *ci = (const int *)(hs->pin_d + 2);
     out->energy = hs->pin_d[0];
@@ -823,6 +847,7 @@ static int read_linearize_out(sosba *h, sosba_linearize_out *out) {
 API int sosba_linearize_all(sosba_t *h, int32_t fix, sosba_linearize_out *out) {
   CHECK_H(h);
   if (h->nf <= 0) { sosba_set_error("no window"); return SOSBA_E_STATE; }
+  if (h->comm && h->world > 1 && HS(h)->d_ctl) cudaMemsetAsync(HS(h)->d_ctl + 2, 0, sizeof(int), h->stream);   // exchange error word
   enqueue_linearize(h, fix != 0);
   SOSBA_CUDA(cudaGetLastError());
   return read_linearize_out(h, out);
@@ -1091,7 +1116,7 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
   x.nf = nf; x.D = D; x.accTop = h->d_accTop; x.adHost = h->d_adHost; x.adTarget = h->d_adTarget;
   x.H = Hpart(h, 0); x.b = bpart(h, 0); x.accSC = h->d_accSC; x.rstats = h->d_rstats_all; x.cnt = h->d_cnt_all;
   x.gate = hs->gate; x.err = hs->d_ctl + 2;
-  launch_stitch_xchg(h, x, h->P);
+  if ((rc = launch_stitch_xchg(h, x, h->P))) return rc;
   if (th_deferred) hs->th_pending = false;   // runs in the spare CTA of the solve launch below
   SolveArgs s;
   s.th = th_def; s.do_th = th_deferred;
@@ -1119,7 +1144,10 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
     ResubArgs ra = resub_args(h, do_step);
     if (do_step) {   // the fused linearisation follows: no memsets on the stream
       ra.zero_lin = h->d_stats;
-      if (h->d_newE_all) { ra.zero_newE = h->d_newE_all; ra.zero_newE_n = h->world * h->newE_cap + h->world; }
+      if (h->d_newE_all) {
+        if (h->p2p) { ra.zero_newE = (float *)h->d_newE_cnt; ra.zero_newE_n = h->world; }
+        else { ra.zero_newE = h->d_newE_all; ra.zero_newE_n = h->world * h->newE_cap + h->world; }
+      }
     }
     if (do_step) launch_step(h, ra, step_args(h));
     else launch_resubstitute(h, ra);

@@ -23,5 +23,5 @@ __device__ __forceinline__ void entry_rc(int e, int &r, int &c) {
   const EntryDesc d = entry_desc(e);
   if (d.kind == 0) { r = d.p; c = d.q; }
   else if (d.kind == 1) { r = d.p; c = 10 + d.q; }
-  else { const int rr[6] = {10, 10, 10, 11, 11, 12}, cc[6] = {10, 11, 12, 11, 12, 12}; r = rr[d.p]; c = cc[d.p]; }
+  else { r = d.p < 3 ? 10 : d.p < 5 ? 11 : 12; c = d.p < 3 ? 10 + d.p : d.p < 5 ? 8 + d.p : 12; }   // BotRight: (10,10) (10,11) (10,12) (11,11) (11,12) (12,12)
 }

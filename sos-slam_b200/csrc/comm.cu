@@ -174,6 +174,9 @@ void sosba_xchg_args(sosba *h, StitchXchgArgs *a, int with_newE) {
   a->epoch = h->p2p_epoch_dev;
   a->newE_all = h->d_newE_all; a->newE_cnt = h->d_newE_cnt; a->newE_cap = h->newE_cap;
   a->with_newE = with_newE && h->d_newE_all;
+  static const char *bo = getenv("SOSBA_XCHG_BACKOFF");
+  a->backoff_ns = bo ? (unsigned)atoi(bo) : 0u;
+  a->dbg = nullptr;
   a->push = (h->comm && h->world > 1 && h->p2p && h->nf <= SOSBA_XCHG_MAX_NF && h->newE_cap <= SOSBA_XCHG_MAX_NEWE) ? 1 : 0;
 }
 

@@ -1,20 +1,24 @@
 // energy_th.cuh — FullSystem::setNewFrameEnergyTH (FullSystemOptimize.cpp:84-124) as a CTA-wide device function:
 // exact k-th smallest (std::nth_element) of the newest-frame residual energies by a 4-pass radix select on the bit
 // patterns of the (non-negative) floats.  The values are read from global memory once (kept in registers when the list
-// fits 8 per thread), histogram updates are aggregated per warp (most energies share their top byte).
+// fits 8 per thread, else in the caller's shared-memory scratch when it fits there), histogram updates are aggregated per
+// warp (most energies share their top byte).
 // Included by k_exact.cu (stand-alone launch, last CTA of the linearisation) and k_accum.cu (spare CTA of the
 // accumulation); the float formula uses explicit _rn intrinsics so both translation units round identically.
 #pragma once
 #include "kernels.h"
 
-__device__ __forceinline__ void energy_th_hist_add(unsigned *hist, unsigned bin, bool valid) {
+// `aggregate`: the pass over the top byte, where most energies of a warp share a bin (one atomic per distinct bin); the
+// lower bytes are spread over the bins, where match.any would loop once per distinct value: plain shared atomics there
+__device__ __forceinline__ void energy_th_hist_add(unsigned *hist, unsigned bin, bool valid, bool aggregate) {
+  if (!aggregate) { if (valid) atomicAdd(&hist[bin], 1u); return; }
   const unsigned act = __ballot_sync(0xffffffffu, valid);   // called by whole warps
   if (!valid) return;
   const unsigned peers = __match_any_sync(act, bin);
   if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
 }
 
-__device__ inline void energy_th_body(const ThArgs &a) {
+__device__ inline void energy_th_body(const ThArgs &a, unsigned *cache = nullptr, int cache_n = 0) {
   __shared__ unsigned hist[256];
   __shared__ unsigned s_prefix, s_k;
   __shared__ int s_off[17];   // prefix sums of the segment lengths
@@ -43,6 +47,16 @@ __device__ inline void energy_th_body(const ThArgs &a) {
 #pragma unroll
     for (int q = 0; q < KEEP; q++) { const int i = threadIdx.x + q * nt; mine[q] = i < n ? elem(i) : 0u; }
   }
+  const bool in_smem = !cached && cache && n <= cache_n;
+  if (in_smem) {   // one pass over global memory, four loads in flight per thread
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * nt) {
+      unsigned x[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const int i = i0 + q * nt; x[q] = i < n ? elem(i) : 0u; }
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const int i = i0 + q * nt; if (i < n) cache[i] = x[q]; }
+    }
+  }
   if (threadIdx.x == 0) { s_prefix = 0; s_k = (unsigned)(int)(a.thN * n); }
   for (int pass = 3; pass >= 0; pass--) {
     for (int i = threadIdx.x; i < 256; i += nt) hist[i] = 0;
@@ -54,13 +68,13 @@ __device__ inline void energy_th_body(const ThArgs &a) {
       for (int q = 0; q < KEEP; q++) {
         const int i = threadIdx.x + q * nt;
         const unsigned x = mine[q];
-        energy_th_hist_add(hist, (x >> shift) & 255u, i < n && (x & himask) == prefix);
+        energy_th_hist_add(hist, (x >> shift) & 255u, i < n && (x & himask) == prefix, pass == 3);
       }
     } else {
       for (int i0 = 0; i0 < n; i0 += nt) {
         const int i = i0 + threadIdx.x;
-        const unsigned x = i < n ? elem(i) : 0u;
-        energy_th_hist_add(hist, (x >> shift) & 255u, i < n && (x & himask) == prefix);
+        const unsigned x = i < n ? (in_smem ? cache[i] : elem(i)) : 0u;
+        energy_th_hist_add(hist, (x >> shift) & 255u, i < n && (x & himask) == prefix, pass == 3);
       }
     }
     __syncthreads();

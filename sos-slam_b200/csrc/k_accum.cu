@@ -297,12 +297,12 @@ __device__ __forceinline__ unsigned smem_u32a(const void *p) { return (unsigned)
 constexpr int ADJ_ST = 68;   // floats per staged 8x8 adjoint (64 + 4: float4 rows of different targets fall into different banks)
 
 constexpr int ACC_THREADS = 512;   // warps 0..7: point sums (8 lanes per point), warps 8..15: top blocks (one target each), concurrently
-__global__ void __launch_bounds__(ACC_THREADS) k_accumulate_fused(FusedAccArgs a, int DP, int DPAD, int ntiles4, int tiles_total, int max_res) {
+__global__ void __launch_bounds__(ACC_THREADS) k_accumulate_fused(FusedAccArgs a, int DP, int DPAD, int ntiles4, int tiles_total, int max_res, int smem_words) {
   extern __shared__ __align__(16) float smem[];
   PDL_ENTER();
   if (a.gate && *a.gate) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (a.do_th && blockIdx.x == gridDim.x - 1) { energy_th_body(a.th); return; }
+  if (a.do_th && blockIdx.x == gridDim.x - 1) { energy_th_body(a.th, (unsigned *)smem, smem_words); return; }
   const int nf = a.nf, D = a.D;
   float *Rs = smem;                                   // [max_res][SOSBA_CREC]
   float *Gs = Rs + (size_t)max_res * SOSBA_CREC;      // [SC_TP][DPAD]
@@ -723,7 +723,7 @@ bool launch_accumulate_fused(sosba *h, const FusedAccArgs &a, int max_res_per_ti
     configured = 200 * 1024;
   }
   int workers = tiles_total < 2 * h->sm_count ? tiles_total : 2 * h->sm_count;
-  launch_pdl(k_accumulate_fused, workers + (a.do_th ? 1 : 0), ACC_THREADS, smem, h->stream, a, DP, DPAD, ntiles4, tiles_total, max_res);
+  launch_pdl(k_accumulate_fused, workers + (a.do_th ? 1 : 0), ACC_THREADS, smem, h->stream, a, DP, DPAD, ntiles4, tiles_total, max_res, (int)(smem / 4));
   h->launches++;
   return true;
 }

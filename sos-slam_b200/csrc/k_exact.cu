@@ -522,8 +522,9 @@ __global__ void __launch_bounds__(256) k_prep_records(LinArgs a, int mode, const
 // ------------------------------------------------------------------------------------------------
 // setNewFrameEnergyTH: energy_th.cuh
 __global__ void __launch_bounds__(1024) k_energy_th(ThArgs a, const int *gate) {
+  __shared__ unsigned s_cache[10240];   // lists beyond 8 energies per thread (point shards of many ranks) are staged here
   if (gate && *gate) return;
-  energy_th_body(a);
+  energy_th_body(a, s_cache, 10240);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
     // spare CTA (point shards).  The selection belongs to the linearisation of the previous body, so it runs whenever the
     // loop had not broken BEFORE this launch: body i-1's solve left ctl[1] = i unless the latch was already set (CTA 0 of
     // this launch may be raising it to i+1 right now -- either value says "not broken before").
-    if (a.do_th && (!a.ctl || a.ctl[1] >= a.iter_index)) energy_th_body(a.th);
+    if (a.do_th && (!a.ctl || a.ctl[1] >= a.iter_index)) energy_th_body(a.th, (unsigned *)sm, a.smem_words);   // this CTA's share of the dynamic shared memory is free
     return;
   }
   SOLVE_TS(0);
@@ -695,6 +695,7 @@ static int launch_solve_t(sosba *h, SolveArgs &a) {
   if (smem + bytesS <= dyn_max) { a.stage_sc = 1; smem += bytesS; }
   if (a.stage_sc && a.HM && smem + (size_t)D * D * 8 <= dyn_max) { a.stage_hm = 1; smem += (size_t)D * D * 8; }
   if (smem > dyn_max) { sosba_set_error("window too large for the single-CTA solve (D=%d)", D); return SOSBA_E_ARG; }
+  a.smem_words = (int)(smem / 4);
   SOSBA_CUDA(launch_pdl(k_solve<T>, a.do_th ? 2 : 1, SOLVE_THREADS, smem, h->stream, a));
   SOSBA_CUDA(cudaGetLastError());
   h->launches++;

@@ -74,12 +74,20 @@ __device__ __forceinline__ double xchg_sum(const StitchXchgArgs &a, unsigned ep,
       while (fl[r] != ep || fh[r] != ep) {   // each 8-byte half validates itself, so tearing between the halves is harmless
         const unsigned char *src = slot_of(a, a.rank, parity, r) + (size_t)widx * 16;
         asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rl[r]), "=r"(fl[r]), "=r"(rh[r]), "=r"(fh[r]) : "l"(src) : "memory");
+        if (a.backoff_ns) __nanosleep(a.backoff_ns);
         if ((++spins & 255) == 0 && clock64() - t0 > X_TIMEOUT) { ok = false; break; }
       }
       s += __hiloint2double((int)rh[r], (int)rl[r]);
     }
   return s;
 }
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define X_TS(slot) do { if (a.dbg && threadIdx.x == 0) a.dbg[slot] = gtime(); } while (0)
 
 __device__ __forceinline__ void ll8_store(unsigned char *p, unsigned v, unsigned ep) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v), "r"(ep) : "memory");
@@ -90,6 +98,7 @@ __device__ __forceinline__ bool ll8_load(const unsigned char *p, unsigned ep, un
   for (;;) {
     asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(p) : "memory");
     if (f == ep) return true;
+    __nanosleep(40);
     if ((++spins & 255) == 0 && clock64() - t0 > X_TIMEOUT) return false;
   }
 }
@@ -106,20 +115,40 @@ __device__ __forceinline__ void exchange_energies(const StitchXchgArgs &a, unsig
     if (first == 0) ll8_store(dst, (unsigned)my_n, ep);
     for (int k = first; k < my_n; k += stride) ll8_store(dst + 8 * (size_t)(1 + k), __float_as_uint(src[k]), ep);
   }
-  for (int r = 0; r < a.world && ok; r++) {
-    if (r == a.rank) continue;
-    const unsigned char *s8 = slot_of(a, a.rank, parity, r) + ebase;
-    unsigned n = 0;
-    ok = ll8_load(s8, ep, n, t0);
-    if (!ok) break;
-    if ((int)n > a.newE_cap) n = (unsigned)a.newE_cap;
-    if (first == 0) a.newE_cnt[r] = (int)n;
-    float *dst = a.newE_all + (size_t)r * a.newE_cap;
-    for (int k = first; k < (int)n && ok; k += stride) {
-      unsigned v;
-      ok = ll8_load(s8 + 8 * (size_t)(1 + k), ep, v, t0);
-      if (ok) dst[k] = __uint_as_float(v);
+  // receive: the words of all peers are requested before any is checked (one round trip, not one per rank)
+  unsigned cn[8], cf[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    cn[r] = 0; cf[r] = ep;
+    if (r < a.world && r != a.rank) {
+      const unsigned char *s8 = slot_of(a, a.rank, parity, r) + ebase;
+      asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(cn[r]), "=r"(cf[r]) : "l"(s8) : "memory");
     }
+  }
+  int maxn = 0;
+#pragma unroll
+  for (int r = 0; r < 8; r++)
+    if (r < a.world && r != a.rank) {
+      if (cf[r] != ep) ok = ok && ll8_load(slot_of(a, a.rank, parity, r) + ebase, ep, cn[r], t0);
+      if (!ok) cn[r] = 0;
+      if ((int)cn[r] > a.newE_cap) cn[r] = (unsigned)a.newE_cap;
+      if (first == 0 && ok) a.newE_cnt[r] = (int)cn[r];
+      maxn = max(maxn, (int)cn[r]);
+    }
+  for (int k = first; k < maxn && ok; k += stride) {
+    unsigned v[8], f[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      if (r < a.world && r != a.rank && k < (int)cn[r]) {
+        const unsigned char *s8 = slot_of(a, a.rank, parity, r) + ebase + 8 * (size_t)(1 + k);
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v[r]), "=r"(f[r]) : "l"(s8) : "memory");
+      }
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+      if (r < a.world && r != a.rank && k < (int)cn[r]) {
+        if (f[r] != ep) ok = ok && ll8_load(slot_of(a, a.rank, parity, r) + ebase + 8 * (size_t)(1 + k), ep, v[r], t0);
+        if (ok) a.newE_all[(size_t)r * a.newE_cap + k] = __uint_as_float(v[r]);
+      }
   }
 }
 
@@ -135,172 +164,133 @@ __device__ __forceinline__ void finish_exchange(const StitchXchgArgs &a, unsigne
   }
 }
 
-// Shared-memory staging of the (host,target) blocks one CTA needs ("terms"): all of them are fetched in ONE phase (a single
-// global-memory round trip), A and L passes summed.  Per term: P = block[4:12,4:12] (8x8, symmetric), C = block[4:12,0:4]
-// (8x4) followed by r = block[4:12,12] (8), the left adjoint ML (and for off-diagonal tiles the right adjoint MR).
+// Shared-memory staging of the (host,target) blocks one CTA needs ("terms"): every term's 92-double table row (A pass and L
+// pass) and its 8x8 adjoint arrive by TMA bulk copies (cp.async.bulk + mbarrier) issued by one thread each, all in flight at
+// once; the code that consumes them is a few compact loops (a fully unrolled gather is instruction-fetch bound here: every
+// instruction of this kernel runs once).
 constexpr int X_MAXT = 24;              // terms per CTA: 2 (nf - 1) for a diagonal tile, nf <= 13
-constexpr int XS_P = 0, XS_C = XS_P + X_MAXT * 64, XS_ML = XS_C + X_MAXT * 40, XS_X = XS_ML + X_MAXT * 64, XS_TOTAL = XS_X + X_MAXT * 64;
+constexpr int XS_A = 0, XS_L = XS_A + X_MAXT * SOSBA_TOPB, XS_M = XS_L + X_MAXT * SOSBA_TOPB, XS_TOTAL = XS_M + X_MAXT * 64;
+constexpr int XS_X = XS_L;              // the L rows are consumed once they are added to the A rows: X = M P lives there
 
-// where entry e of a block lands in the staging area: bits 0..7 first offset, 8..15 mirrored offset (0xff = none), bit 16 = C/r
-// area (else P), 0xffffffff = not needed (calibration rows, rr)
-__device__ __forceinline__ unsigned stage_slot(int e) {
-  int r, c;
-  entry_rc(e, r, c);   // r <= c
-  if (r >= 4) {
-    if (c < 12) return (unsigned)((r - 4) * 8 + c - 4) | ((unsigned)((c - 4) * 8 + r - 4) << 8);
-    if (r < 12) return (unsigned)(32 + r - 4) | 0xff00u | 0x10000u;
-    return 0xffffffffu;
-  }
-  if (c >= 4 && c < 12) return (unsigned)((c - 4) * 4 + r) | 0xff00u | 0x10000u;
-  return 0xffffffffu;
+__device__ __forceinline__ unsigned xs_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void xs_bulk(void *dst, const void *src, unsigned bytes, unsigned long long *mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(xs_u32(dst)), "l"(src), "r"(bytes),
+               "r"(xs_u32(mbar))
+               : "memory");
 }
-
-// BLK(k) -> block index of term k.  All loads of a thread are issued before the first one is consumed.
-template <int ITERS, class BlkFn>
-__device__ __forceinline__ void stage_blocks(const StitchXchgArgs &a, BlkFn blk_of, int nterms, double *sm, int tid) {
-  const int n2 = a.nf * a.nf, total = nterms * 91;
-  double va[ITERS], vl[ITERS];
-#pragma unroll
-  for (int it = 0; it < ITERS; it++) {
-    const int idx = tid + it * XT;
-    va[it] = vl[it] = 0.0;
-    if (idx < total) {
-      const int term = idx / 91, e = idx - term * 91, blk = blk_of(term);
-      va[it] = a.accTop[(size_t)blk * SOSBA_TOPB + e];
-      vl[it] = a.accTop[((size_t)n2 + blk) * SOSBA_TOPB + e];
-    }
-  }
-#pragma unroll
-  for (int it = 0; it < ITERS; it++) {
-    const int idx = tid + it * XT;
-    if (idx < total) {
-      const int term = idx / 91, e = idx - term * 91;
-      const unsigned sl = stage_slot(e);
-      if (sl != 0xffffffffu) {
-        const double v = va[it] + vl[it];
-        double *dst = sm + ((sl & 0x10000u) ? XS_C + term * 40 : XS_P + term * 64);
-        dst[sl & 0xff] = v;
-        if (((sl >> 8) & 0xff) != 0xff) dst[(sl >> 8) & 0xff] = v;
-      }
-    }
-  }
+__device__ __forceinline__ void xs_wait(unsigned long long *mbar) {
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(xs_u32(mbar)), "r"(0u) : "memory");
+}
+// index of entry (r, c), r <= c, of the symmetric 13x13 block inside a table row (inverse of entry_rc)
+__device__ __forceinline__ int entry_index(int r, int c) {
+  if (c < 10) return r * 10 - r * (r - 1) / 2 + (c - r);
+  if (r < 10) return 55 + 3 * r + (c - 10);
+  return r == 10 ? 85 + (c - 10) : r == 11 ? 88 + (c - 11) : 90;
 }
 
 __global__ void __launch_bounds__(XT, 1) k_stitch_xchg(StitchXchgArgs a, Layout L) {
-  __shared__ double sm[XS_TOTAL];
-  __shared__ int s_blk[X_MAXT];
+  __shared__ __align__(16) double sm[XS_TOTAL];
+  __shared__ __align__(8) unsigned long long mbar;
   PDL_ENTER();
   if (a.gate && *a.gate) return;
   const int tid = threadIdx.x, g = tid >> 6, l = tid & 63, i = l >> 3, j = l & 7;
-  const int nf = a.nf, D = a.D, bid = blockIdx.x;
+  const int nf = a.nf, D = a.D, bid = blockIdx.x, n2 = nf * nf;
   const bool push = a.push != 0;
   const unsigned ep = push ? (unsigned)a.epoch[0] : 0u;
   const int parity = (int)(ep & 1u);
   const long long t0 = clock64();
   bool ok = true;
 
-  if (bid < L.cta_pair) {
-    // ---- diagonal tile of frame af: H[af,af], H[af,calib], b[af] ------------------------------------------------
-    // = sum over targets t != af of the host terms Ah P Ah^T (block af + nf t) + sum over hosts h != af of the target terms
-    //   At P At^T (block h + nf af); the terms are dealt round-robin to the four 64-thread groups, partial sums added in
-    //   group order
-    const int af = bid, nterms = 2 * (nf - 1);
-    auto blk_of = [&](int k) -> int {
-      if (k < nf - 1) { const int t = k < af ? k : k + 1; return af + nf * t; }
-      const int kk = k - (nf - 1), hh = kk < af ? kk : kk + 1;
-      return hh + nf * af;
-    };
-    {  // adjoints: adHost of the host terms, adTarget of the target terms
-      double m[(X_MAXT * 64 + XT - 1) / XT];
-#pragma unroll
-      for (int it = 0; it < (X_MAXT * 64 + XT - 1) / XT; it++) {
-        const int idx = tid + it * XT, k = idx >> 6;
-        m[it] = idx < nterms * 64 ? (k < nf - 1 ? a.adHost : a.adTarget)[64 * (size_t)blk_of(k) + (idx & 63)] : 0.0;
-      }
-      stage_blocks<(X_MAXT * 91 + XT - 1) / XT>(a, blk_of, nterms, sm, tid);
-#pragma unroll
-      for (int it = 0; it < (X_MAXT * 64 + XT - 1) / XT; it++) {
-        const int idx = tid + it * XT;
-        if (idx < nterms * 64) sm[XS_ML + idx] = m[it];
-      }
+  if (bid < L.cta_misc) {
+    // ---- tiles of H: a diagonal tile (CTA af < nf: H[af,af], H[af,calib], b[af]) or four off-diagonal tiles ------------
+    const bool diag = bid < L.cta_pair;
+    const int af = bid;
+    // diagonal: terms k < nf-1 are the host terms Ah P Ah^T of blocks (af, t), t != af; the others the target terms
+    //           At P At^T of blocks (h, af), h != af; dealt round-robin to the four 64-thread groups
+    // off-diagonal: group g owns tile q = (fa, fb), fa < fb: H[fa,fb] = Ah P At^T of block (fa,fb) + (Ah P At^T of (fb,fa))^T,
+    //           terms 2g, 2g+1 with left / right factors (adHost, adTarget) of (fa,fb), then (adTarget, adHost) of (fb,fa)
+    const int nterms = diag ? 2 * (nf - 1) : 8;
+    const int q = 4 * (bid - L.cta_pair) + g;
+    const bool act = diag || q < L.npairs;
+    int fa = 0, fb = 1;
+    if (!diag && q < L.npairs) { int rem = q; while (rem >= nf - 1 - fa) { rem -= nf - 1 - fa; fa++; } fb = fa + 1 + rem; }
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xs_u32(&mbar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const unsigned total = (unsigned)nterms * (2u * SOSBA_TOPB * 8u + (diag ? 512u : 1024u));
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xs_u32(&mbar)), "r"(total) : "memory");
     }
     __syncthreads();
-    for (int k = g; k < nterms; k += 4) {
-      const double *M = sm + XS_ML + k * 64, *P = sm + XS_P + k * 64;
+    if (tid < nterms) {   // one thread per term: its A row, its L row, its adjoint(s)
+      const int k = tid;
+      int blk, left_is_host;
+      if (diag) {
+        left_is_host = k < nf - 1;
+        if (left_is_host) { const int t = k < af ? k : k + 1; blk = af + nf * t; }
+        else { const int kk = k - (nf - 1), hh = kk < af ? kk : kk + 1; blk = hh + nf * af; }
+      } else {   // (an idle group stages the blocks of tile (0,1) and drops the result)
+        int pa = 0, pb = 1, rem = 4 * (bid - L.cta_pair) + (k >> 1);
+        if (rem < L.npairs) { while (rem >= nf - 1 - pa) { rem -= nf - 1 - pa; pa++; } pb = pa + 1 + rem; }
+        left_is_host = (k & 1) == 0;
+        blk = left_is_host ? pa + nf * pb : pb + nf * pa;
+      }
+      xs_bulk(sm + XS_A + k * SOSBA_TOPB, a.accTop + (size_t)blk * SOSBA_TOPB, SOSBA_TOPB * 8, &mbar);
+      xs_bulk(sm + XS_L + k * SOSBA_TOPB, a.accTop + ((size_t)n2 + blk) * SOSBA_TOPB, SOSBA_TOPB * 8, &mbar);
+      xs_bulk(sm + XS_M + k * 64, (left_is_host ? a.adHost : a.adTarget) + 64 * (size_t)blk, 512, &mbar);
+      if (!diag) xs_bulk(sm + XS_M + (8 + k) * 64, (left_is_host ? a.adTarget : a.adHost) + 64 * (size_t)blk, 512, &mbar);   // right factors behind the 8 left ones
+    }
+    // where this thread's operands sit inside a table row: P[q][j] = block(4+q, 4+j), C[q][j] = block(j, 4+q), r[q] = block(4+q, 12)
+    int pe[8], ce[8];
+#pragma unroll
+    for (int qq = 0; qq < 8; qq++) {
+      pe[qq] = entry_index(min(4 + qq, 4 + j), max(4 + qq, 4 + j));
+      ce[qq] = j < 4 ? entry_index(j, 4 + qq) : entry_index(4 + qq, 12);
+    }
+    xs_wait(&mbar);
+    for (int idx = tid; idx < nterms * SOSBA_TOPB; idx += XT) sm[XS_A + idx] += sm[XS_L + idx];
+    __syncthreads();
+    const int kstep = diag ? 4 : 1, kbeg = diag ? g : 2 * g, kend = diag ? nterms : 2 * g + 2;
+    for (int k = kbeg; k < kend; k += kstep) {
+      const double *M = sm + XS_M + k * 64, *B = sm + XS_A + k * SOSBA_TOPB;
       double x = 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; q++) x += M[i * 8 + q] * P[q * 8 + j];
+      for (int qq = 0; qq < 8; qq++) x += M[i * 8 + qq] * B[pe[qq]];
       sm[XS_X + k * 64 + l] = x;
     }
     __syncthreads();
     double o = 0.0, fc = 0.0;
-    const int ii = max(i, j), jj = min(i, j);   // both triangles from the same expression: exactly symmetric
-    for (int k = g; k < nterms; k += 4) {
-      const double *M = sm + XS_ML + k * 64, *X = sm + XS_X + k * 64, *C = sm + XS_C + k * 40;
+    const int ii = diag ? max(i, j) : i, jj = diag ? min(i, j) : j;   // diagonal tile: both triangles from the same expression
+    for (int k = kbeg; k < kend; k += kstep) {
+      const double *M = sm + XS_M + k * 64, *R = sm + XS_M + (diag ? k : 8 + k) * 64, *X = sm + XS_X + k * 64, *B = sm + XS_A + k * SOSBA_TOPB;
 #pragma unroll
-      for (int q = 0; q < 8; q++) o += X[ii * 8 + q] * M[jj * 8 + q];
-      if (j < 4) {
+      for (int qq = 0; qq < 8; qq++) o += X[ii * 8 + qq] * R[jj * 8 + qq];
+      if (diag && j <= 4) {
 #pragma unroll
-        for (int q = 0; q < 8; q++) fc += M[i * 8 + q] * C[q * 4 + j];
-      } else if (j == 4) {
-#pragma unroll
-        for (int q = 0; q < 8; q++) fc += M[i * 8 + q] * C[32 + q];
+        for (int qq = 0; qq < 8; qq++) fc += M[i * 8 + qq] * B[ce[qq]];
       }
     }
-    __syncthreads();
-    double *part = sm + XS_P;   // [4][XW_DIAG], the staged blocks are consumed
-    part[g * XW_DIAG + l] = o;
-    if (j < 4) part[g * XW_DIAG + 64 + i * 4 + j] = fc;
-    else if (j == 4) part[g * XW_DIAG + 96 + i] = fc;
-    __syncthreads();
-    if (tid < XW_DIAG) {
-      double v = ((part[tid] + part[XW_DIAG + tid]) + part[2 * XW_DIAG + tid]) + part[3 * XW_DIAG + tid];
-      if (push) v = xchg_sum(a, ep, parity, af * XW_DIAG + tid, v, t0, ok);
-      if (ok) {
-        const int r0 = 4 + 8 * af;
-        if (tid < 64) a.H[(size_t)(r0 + i) * D + r0 + j] = v;
-        else if (tid < 96) { const int e = tid - 64, fi = e >> 2, cj = e & 3; a.H[(size_t)(r0 + fi) * D + cj] = v; a.H[(size_t)cj * D + r0 + fi] = v; }
-        else a.b[r0 + tid - 96] = v;
+    if (diag) {
+      __syncthreads();
+      double *part = sm + XS_A;   // [4][XW_DIAG], the staged rows are consumed
+      part[g * XW_DIAG + l] = o;
+      if (j < 4) part[g * XW_DIAG + 64 + i * 4 + j] = fc;
+      else if (j == 4) part[g * XW_DIAG + 96 + i] = fc;
+      __syncthreads();
+      if (tid < XW_DIAG) {
+        double v = ((part[tid] + part[XW_DIAG + tid]) + part[2 * XW_DIAG + tid]) + part[3 * XW_DIAG + tid];
+        if (af == 0) X_TS(3);
+        if (push) v = xchg_sum(a, ep, parity, af * XW_DIAG + tid, v, t0, ok);
+        if (af == 0) X_TS(4);
+        if (ok) {
+          const int r0 = 4 + 8 * af;
+          if (tid < 64) a.H[(size_t)(r0 + i) * D + r0 + j] = v;
+          else if (tid < 96) { const int e = tid - 64, fi = e >> 2, cj = e & 3; a.H[(size_t)(r0 + fi) * D + cj] = v; a.H[(size_t)cj * D + r0 + fi] = v; }
+          else a.b[r0 + tid - 96] = v;
+        }
       }
-    }
-  } else if (bid < L.cta_misc) {
-    // ---- four off-diagonal tiles, one per 64-thread group: H[fa,fb] = Ah P At^T of block (fa,fb) + (Ah P At^T of block (fb,fa))^T
-    // terms 2g, 2g+1 of group g; left / right factors: (adHost, adTarget) of block (fa,fb), then (adTarget, adHost) of block (fb,fa)
-    const int q = 4 * (bid - L.cta_pair) + g;
-    const bool act = q < L.npairs;
-    int fa = 0, fb = 1;
-    if (act) { int rem = q; while (rem >= nf - 1 - fa) { rem -= nf - 1 - fa; fa++; } fb = fa + 1 + rem; }
-    const int b0 = fa + nf * fb, b1 = fb + nf * fa;
-    if (l < 2) s_blk[2 * g + l] = l == 0 ? b0 : b1;
-    double *MR = sm + XS_ML + 8 * 64;   // right factors of the 8 terms, behind the 8 left factors
-    const double m0 = a.adHost[64 * (size_t)b0 + l], m1 = a.adTarget[64 * (size_t)b0 + l];
-    const double m2 = a.adTarget[64 * (size_t)b1 + l], m3 = a.adHost[64 * (size_t)b1 + l];
-    __syncthreads();
-    stage_blocks<(8 * 91 + XT - 1) / XT>(a, [&](int k) -> int { return s_blk[k]; }, 8, sm, tid);
-    sm[XS_ML + (2 * g) * 64 + l] = m0;
-    MR[(2 * g) * 64 + l] = m1;
-    sm[XS_ML + (2 * g + 1) * 64 + l] = m2;
-    MR[(2 * g + 1) * 64 + l] = m3;
-    __syncthreads();
-#pragma unroll
-    for (int term = 0; term < 2; term++) {
-      const int k = 2 * g + term;
-      const double *M = sm + XS_ML + k * 64, *P = sm + XS_P + k * 64;
-      double x = 0.0;
-#pragma unroll
-      for (int qq = 0; qq < 8; qq++) x += M[i * 8 + qq] * P[qq * 8 + j];
-      sm[XS_X + k * 64 + l] = x;
-    }
-    __syncthreads();
-    double o = 0.0;
-#pragma unroll
-    for (int term = 0; term < 2; term++) {
-      const int k = 2 * g + term;
-      const double *X = sm + XS_X + k * 64, *R = MR + k * 64;
-#pragma unroll
-      for (int qq = 0; qq < 8; qq++) o += X[i * 8 + qq] * R[j * 8 + qq];
-    }
-    if (act) {
+    } else if (act) {
       double v = o;
       if (push) v = xchg_sum(a, ep, parity, L.base_pair + q * 64 + l, v, t0, ok);
       if (ok) {
@@ -311,6 +301,7 @@ __global__ void __launch_bounds__(XT, 1) k_stitch_xchg(StitchXchgArgs a, Layout 
   } else if (bid < L.cta_sc) {
     // ---- calibration block, b[calib], back-substitution sums, residual counters ------------------------------------
     const int nblk = 2 * nf * nf;
+    X_TS(0);
     if (tid < 240) {   // 20 entries x 12 slices of the block list
       const int ent = tid % 20, slice = tid / 20;
       int e;
@@ -331,7 +322,9 @@ __global__ void __launch_bounds__(XT, 1) k_stitch_xchg(StitchXchgArgs a, Layout 
       if (tid < 20) { v = 0.0; for (int s = 0; s < 12; s++) v += sm[s * 20 + tid]; }
       else if (tid < 28) v = a.rstats[tid - 20];
       else v = (double)a.cnt[tid - 28];
+      X_TS(1);
       if (push) v = xchg_sum(a, ep, parity, L.base_misc + tid, v, t0, ok);
+      X_TS(2);
       if (ok) {
         if (tid < 16) a.H[(size_t)(tid >> 2) * D + (tid & 3)] = v;
         else if (tid < 20) a.b[tid - 16] = v;
@@ -349,7 +342,9 @@ __global__ void __launch_bounds__(XT, 1) k_stitch_xchg(StitchXchgArgs a, Layout 
       }
     }
   } else if (push && a.with_newE) {
+    if (bid == L.cta_e) X_TS(5);
     exchange_energies(a, ep, parity, (size_t)L.nv * 16, bid - L.cta_e, gridDim.x - L.cta_e, t0, ok);
+    if (bid == L.cta_e) X_TS(6);
   }
   if (!ok && a.err) atomicOr(a.err, 2);   // reported by the caller as SOSBA_E_NCCL (peer exchange timed out)
   if (push) finish_exchange(a, ep);

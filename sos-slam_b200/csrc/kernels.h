@@ -185,6 +185,8 @@ struct StitchXchgArgs {
   int newE_cap, with_newE;
   const int *gate;             // non-null: skip when *gate != 0 (the loop broke on the device -- on every rank alike)
   int *err;                    // set to 2 when a peer's words did not arrive in time
+  unsigned backoff_ns;         // nanosleep between polls of a word that has not arrived (0 = spin)
+  long long *dbg;              // optional: globaltimer stamps of one launch (SOSBA_XCHG_DEBUG)
 };
 #define SOSBA_XCHG_MAX_NF 13        // k_solve's limit
 #define SOSBA_XCHG_MAX_NEWE 16384   // newest-frame energies per rank a mailbox slot can carry
@@ -222,6 +224,7 @@ struct SolveArgs {
   // this launch) runs in a second CTA beside the solve instead of as a launch of its own
   ThArgs th;
   int do_th;
+  int smem_words;              // set by launch_solve: 4-byte words of dynamic shared memory (scratch of the spare CTA)
 };
 int launch_solve(sosba *h, const SolveArgs &a);
 

@@ -32,6 +32,8 @@ int sosba_comm_max_int(sosba *h, int v, int *out);
 static thread_local char g_err[512] = "";
 static long long *g_dbg = nullptr;   // SOSBA_SOLVE_DEBUG: k_solve phase timestamps (clock64), 16 per launch
 static long g_dbg_n = 0;
+static long long *g_xdbg = nullptr;   // SOSBA_XCHG_DEBUG: k_stitch_xchg globaltimer stamps, 8 per launch
+static long g_xdbg_n = 0;
 void sosba_set_error(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -307,6 +309,16 @@ API void sosba_destroy(sosba_t *h) {
               q[1] - q[0], q[2] - q[1], q[6] - q[1], q[3] - q[6], q[4] - q[3], q[5] - q[4]);
     }
     g_dbg_n = 0;
+  }
+  if (g_xdbg && g_xdbg_n > 8) {   // per launch: [0] misc CTA start, [1] its values ready, [2] summed; [3],[4] diagonal tile 0 ready / summed; [5],[6] energies start / done
+    std::vector<long long> t(64 * 8);
+    cudaMemcpy(t.data(), g_xdbg, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    const int n = (int)std::min<long>(g_xdbg_n, 64);
+    auto med = [&](int hi, int lo) { std::vector<long long> v; for (int k = 0; k < n; k++) v.push_back(t[8 * k + hi] - t[8 * k + lo]); std::sort(v.begin(), v.end()); return v[v.size() / 2]; };
+    auto mx = [&](int hi, int lo) { long long m = 0; for (int k = 0; k < n; k++) m = std::max(m, t[8 * k + hi] - t[8 * k + lo]); return m; };
+    fprintf(stderr, "[rank %d] k_stitch_xchg ns (median / max of last %d launches): misc compute %lld/%lld, misc exchange %lld/%lld, diag0 ready after misc start %lld/%lld, "
+            "diag0 exchange %lld/%lld, energies %lld/%lld\n", h->rank, n, med(1, 0), mx(1, 0), med(2, 1), mx(2, 1), med(3, 0), mx(3, 0), med(4, 3), mx(4, 3), med(6, 5), mx(6, 5));
+    g_xdbg_n = 0;
   }
   sosba_comm_destroy(h);
   HostSide *hs = HS(h);
@@ -1116,6 +1128,11 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
   x.nf = nf; x.D = D; x.accTop = h->d_accTop; x.adHost = h->d_adHost; x.adTarget = h->d_adTarget;
   x.H = Hpart(h, 0); x.b = bpart(h, 0); x.accSC = h->d_accSC; x.rstats = h->d_rstats_all; x.cnt = h->d_cnt_all;
   x.gate = hs->gate; x.err = hs->d_ctl + 2;
+  static const bool xchg_debug = getenv("SOSBA_XCHG_DEBUG") != nullptr;
+  if (xchg_debug) {   // globaltimer stamps of the last 64 launches, printed by sosba_destroy
+    if (!g_xdbg) { cudaMalloc(&g_xdbg, 64 * 8 * sizeof(long long)); cudaMemset(g_xdbg, 0, 64 * 8 * sizeof(long long)); }
+    x.dbg = g_xdbg + 8 * (g_xdbg_n++ % 64);
+  }
   if ((rc = launch_stitch_xchg(h, x, h->P))) return rc;
   if (th_deferred) hs->th_pending = false;   // runs in the spare CTA of the solve launch below
   SolveArgs s;

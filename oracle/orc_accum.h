@@ -1,4 +1,7 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.h header).  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.h header).
+// PARITY PINNED for this file: tests/test_ref_pin.py runs every class below against the reference class itself, compiled
+// unmodified from /root/reference/src/OptimizationBackend/{MatrixAccumulators,ScaleAccumulator}.h (oracle/ref_build.sh), on
+// random streams that cross both shiftUp tiers — bit-identical results.
 //
 // Restatement of src/OptimizationBackend/MatrixAccumulators.h and ScaleAccumulator.h: the
 // numerically tiered (1 / 1k / 1M) float accumulators.  4-lane SSE members are restated as

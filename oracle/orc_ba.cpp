@@ -17,6 +17,7 @@
 #include <cstdio>
 
 #include "orc_core.h"
+#include "orc_sample.h"
 
 namespace orc {
 
@@ -63,17 +64,6 @@ void make_images(Oracle &o, int slot, const float *color, const float *B) {
     }
   }
   P.valid = true;
-}
-
-// globalFuncs.h:68-82
-static inline void interp33(const float *mat, float x, float y, int width, float out[3]) {
-  int ix = (int)x, iy = (int)y;
-  float dx = x - ix, dy = y - iy;
-  float dxdy = dx * dy;
-  const float *bp = mat + 3 * (ix + iy * width);
-  const float w11 = dxdy, w01 = dy - dxdy, w10 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
-  for (int c = 0; c < 3; c++)
-    out[c] = w11 * bp[3 * (1 + width) + c] + w01 * bp[3 * width + c] + w10 * bp[3 + c] + w00 * bp[c];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -12,39 +12,13 @@
 #include <vector>
 
 #include "orc_core.h"
+#include "orc_sample.h"
 
 namespace orc {
 
 static const float s_maxPixSearch = 0.027f, s_trace_stepsize = 1.0f, s_trace_GNThreshold = 0.1f, s_trace_extraSlackOnTH = 1.2f,
                    s_trace_slackInterval = 1.5f, s_trace_minImprovementFactor = 2.f, s_outlierTH = 12 * 12;   // settings.cpp:82,128-143
 static const int s_trace_GNIterations = 3, s_minTraceTestRadius = 2;
-
-static inline float interp31(const float *mat, float x, float y, int width) {   // globalFuncs.h:122-136 (channel 0 of Vector3f)
-  int ix = (int)x, iy = (int)y;
-  float dx = x - ix, dy = y - iy;
-  float dxdy = dx * dy;
-  const float *bp = mat + 3 * (ix + iy * width);
-  return dxdy * bp[3 * (1 + width)] + (dy - dxdy) * bp[3 * width] + (dx - dxdy) * bp[3] + (1 - dx - dy + dxdy) * bp[0];
-}
-static inline void interp33t(const float *mat, float x, float y, int width, float out[3]) {   // globalFuncs.h:68-82
-  int ix = (int)x, iy = (int)y;
-  float dx = x - ix, dy = y - iy;
-  float dxdy = dx * dy;
-  const float *bp = mat + 3 * (ix + iy * width);
-  for (int c = 0; c < 3; c++)
-    out[c] = dxdy * bp[3 * (1 + width) + c] + (dy - dxdy) * bp[3 * width + c] + (dx - dxdy) * bp[3 + c] + (1 - dx - dy + dxdy) * bp[c];
-}
-static inline void interp33BiLin(const float *mat, float x, float y, int width, float out[3]) {   // globalFuncs.h:161-182
-  int ix = (int)x, iy = (int)y;
-  const float *bp = mat + 3 * (ix + iy * width);
-  float tl = bp[0], tr = bp[3], bl = bp[3 * width], br = bp[3 * (width + 1)];
-  float dx = x - ix, dy = y - iy;
-  float topInt = dx * tr + (1 - dx) * tl;
-  float botInt = dx * br + (1 - dx) * bl;
-  float leftInt = dy * bl + (1 - dy) * tl;
-  float rightInt = dy * br + (1 - dy) * tr;
-  out[0] = dx * rightInt + (1 - dx) * leftInt; out[1] = rightInt - leftInt; out[2] = botInt - topInt;
-}
 
 // ImmaturePoint::ImmaturePoint (ImmaturePoint.cpp:28-60)
 void immature_init(Oracle &o, int slot, int n, const int32_t *u, const int32_t *v, float *color, float *weights, float *gradH, float *energyTH) {
@@ -169,7 +143,7 @@ static int traceOn(const Oracle &o, IP &p, const float *dI, const float *KRKi, c
     float H = 1, bb = 0, energy = 0;
     for (int idx = 0; idx < 8; idx++) {
       float hit[3];
-      interp33t(dI, (float)(bestU + rot[idx][0]), (float)(bestV + rot[idx][1]), wG, hit);
+      interp33(dI, (float)(bestU + rot[idx][0]), (float)(bestV + rot[idx][1]), wG, hit);
       if (!std::isfinite(hit[0])) { energy += 1e5; continue; }
       float residual = hit[0] - (aff[0] * p.color[idx] + aff[1]);
       float dResdDist = dx * hit[1] + dy * hit[2];
@@ -277,7 +251,7 @@ static double linearizeResidual(const Oracle &o, const sosba_activation_window *
     }
     if (!ok) { tr.state_NewState = SOSBA_RES_OOB; return tr.state_energy; }
     float hit[3];
-    interp33t(dIl, Ku, Kv, wG, hit);
+    interp33(dIl, Ku, Kv, wG, hit);
     if (!std::isfinite(hit[0])) { tr.state_NewState = SOSBA_RES_OOB; return tr.state_energy; }
     float residual = hit[0] - (affLL[0] * p.color[idx] + affLL[1]);
     float hw = fabsf(residual) < huberTH ? 1 : huberTH / fabsf(residual);

@@ -13,18 +13,10 @@
 #include <cmath>
 
 #include "orc_core.h"
+#include "orc_sample.h"
 #include "orc_host.h"
 
 namespace orc {
-
-static inline void interp33(const float *mat, float x, float y, int width, float out[3]) {  // globalFuncs.h:68-82
-  int ix = (int)x, iy = (int)y;
-  float dx = x - ix, dy = y - iy;
-  float dxdy = dx * dy;
-  const float *bp = mat + 3 * (ix + iy * width);
-  const float w11 = dxdy, w01 = dy - dxdy, w10 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
-  for (int c = 0; c < 3; c++) out[c] = w11 * bp[3 * (1 + width) + c] + w01 * bp[3 * width + c] + w10 * bp[3 + c] + w00 * bp[c];
-}
 
 void tracker_makeK(Oracle &o, const float calib[4]) {
   o.tfx[0] = calib[0]; o.tfy[0] = calib[1]; o.tcx[0] = calib[2]; o.tcy[0] = calib[3];

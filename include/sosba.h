@@ -263,6 +263,62 @@ int sosba_scale_calc_res(sosba_t *h, int32_t lvl, int32_t stereo_slot, float sca
                          double out6[6], int32_t counts[3]);
 int sosba_scale_calc_gs(sosba_t *h, int32_t lvl, float scale, float *H, float *b);
 
+/* ---- a16: the direct-alignment control loops, resident on the device --------------------------------
+ * CoarseTracker::makeCoarseDepthL0 (CoarseTracker.cpp:56-230) as called by setCoarseTrackingRef (:232-242): splat the centre
+ * projections of the IN residuals on the newest keyframe (PointFrameResidual::centerProjectedTo {u, v, new_idepth}, weight
+ * sqrt(1e-3 / (HdiF + 1e-12))), 2x2 sum-pool up the pyramid, dilate, normalise, and emit pc_u / pc_v / pc_idepth / pc_color per
+ * level (raster order, 2 <= x < w-2).  ref_slot holds lastRef's pyramid.  The lists replace what sosba_tracker_set_ref uploads.
+ * center_projected_to: [n*3], HdiF: [n] (EFPoint::HdiF), in the order FullSystem walks frameHessians / pointHessians.
+ * pc_n_out: [levels] or NULL.  (Where the reference's dilation reads one element before / behind the map — index -1 at
+ * i = w on levels 0 and 1, index w*h at i = w*h-w-1 — the neighbour counts as empty here.) */
+int sosba_tracker_make_coarse_depth(sosba_t *h, int32_t ref_slot, int32_t n, const float *center_projected_to, const float *HdiF,
+                                    int32_t *pc_n_out);
+/* read back one level of the reference-frame point lists (any pointer may be NULL); returns pc_n[lvl] in *n */
+int sosba_tracker_get_ref(sosba_t *h, int32_t lvl, int32_t *n, float *pc_u, float *pc_v, float *pc_idepth, float *pc_color);
+/* CoarseTracker::scaleCoarseDepthL0 (CoarseTracker.cpp:244-263) on the resident lists */
+int sosba_tracker_scale_coarse_depth(sosba_t *h, float scale);
+
+#define SOSBA_TRACK_MAX_PASSES 8   /* pyramid levels + the one repeated level (CoarseTracker.cpp:516-519) */
+/* One pose hypothesis of FullSystem::trackNewCoarse (FullSystem.cpp:175-231) = one call of
+ * CoarseTracker::trackNewestCoarse (CoarseTracker.cpp:366-552).  Poses as Sophus::SE3d stores them: unit quaternion
+ * (x, y, z, w) + translation. */
+typedef struct sosba_track_hypothesis {
+  double q[4], t[3];             /* in: lastToNew_out; out: refToNew_current when the loop ran through (else unchanged) */
+  double aff_g2l[2];             /* in/out: aff_g2l_out (a, b) */
+  double min_res_for_abort[5];   /* in: minResForAbort (NaN = never abort, as in the first try) */
+  double last_residuals[5];      /* out: lastResiduals (NaN where a level was not reached) */
+  double flow_indicators[3];     /* out: lastFlowIndicators of the last level that ran */
+  int32_t ok;                    /* out: the return value */
+  int32_t n_passes;              /* out: level passes executed (levels + 1 when a level was repeated) */
+  int32_t pass_lvl[SOSBA_TRACK_MAX_PASSES];         /* out */
+  int32_t pass_iterations[SOSBA_TRACK_MAX_PASSES];  /* out: LM iterations of the pass */
+  uint64_t pass_accept[SOSBA_TRACK_MAX_PASSES];     /* out: bit i = iteration i accepted */
+  double pass_residual[SOSBA_TRACK_MAX_PASSES];     /* out: sqrt(resOld[0] / resOld[1]) at the end of the pass */
+  float pass_cutoff_repeat[SOSBA_TRACK_MAX_PASSES]; /* out: levelCutoffRepeat of the pass */
+} sosba_track_hypothesis;
+/* n_hyp independent hypotheses against the frame in new_slot: the whole Levenberg-Marquardt loop of every hypothesis (calcResPose,
+ * calcGSSSEPose, the damped 8x8 LDL^T solve, SE3::exp update, accept / reject, level schedule, abort and final checks) runs on
+ * the device, one thread block per hypothesis, ONE synchronisation per call.  ref_ab_exposure / ref_aff_g2l: lastRef->ab_exposure,
+ * lastRef_aff_g2l; new_ab_exposure: newFrame->ab_exposure.  Needs sosba_tracker_make_k and the reference lists
+ * (sosba_tracker_make_coarse_depth or sosba_tracker_set_ref on every level <= coarsest_lvl). */
+int sosba_tracker_track(sosba_t *h, int32_t new_slot, float ref_ab_exposure, float new_ab_exposure, const double ref_aff_g2l[2],
+                        int32_t coarsest_lvl, int32_t n_hyp, sosba_track_hypothesis *hyps);
+
+/* One start value of ScaleOptimizer::optimizeScale (ScaleOptimizer.cpp:120-230; FullSystem::optimizeScale tries 7 of them until
+ * the scale is trapped, FullSystem.cpp:1133-1146). */
+typedef struct sosba_scale_hypothesis {
+  float scale;                   /* in/out */
+  float error;                   /* out: the return value last_residuals[0] */
+  double last_residuals[5];      /* out */
+  int32_t n_passes;
+  int32_t pass_lvl[SOSBA_TRACK_MAX_PASSES];
+  int32_t pass_iterations[SOSBA_TRACK_MAX_PASSES];
+  uint64_t pass_accept[SOSBA_TRACK_MAX_PASSES];
+  int32_t reserved0;
+} sosba_scale_hypothesis;
+/* camera-1 frame in stereo_slot; needs sosba_scale_set_stereo and the reference lists. */
+int sosba_scale_optimize(sosba_t *h, int32_t stereo_slot, int32_t coarsest_lvl, int32_t n_hyp, sosba_scale_hypothesis *hyps);
+
 /* ---- a4/a10/a11 composed: the Gauss-Newton loop body of FullSystem::optimize ------------------ */
 /* Frame state as FullSystem keeps it (HessianBlocks.h:136-424). */
 typedef struct sosba_frame_state {

@@ -296,6 +296,47 @@ ORC_API int orc_tracker_calc_gs_pose(orc_handle *h, int32_t lvl, float a, float 
   tracker_calcGSSSEPose(h->o, lvl, a, b0, H, b);
   return SOSBA_OK;
 }
+// ---- a16: control loops of the direct alignment (orc_lm.cpp) --------------------------------------------------
+ORC_API int orc_tracker_make_coarse_depth(orc_handle *h, int32_t ref_slot, int32_t n, const float *cpt, const float *HdiF, int32_t *pc_n_out) {
+  Oracle &o = h->o;
+  if (ref_slot < 0 || ref_slot >= (int)o.slots.size() || !o.slots[ref_slot].valid || n < 0 || (n > 0 && (!cpt || !HdiF))) return SOSBA_E_ARG;
+  for (int i = 0; i < n; i++) {
+    const int u = cpt[3 * i] + 0.5f, v = cpt[3 * i + 1] + 0.5f;
+    if (!(cpt[3 * i] >= 0) || !(cpt[3 * i + 1] >= 0) || u >= o.wl[0] || v >= o.hl[0]) return SOSBA_E_ARG;
+  }
+  tracker_makeCoarseDepth(o, ref_slot, n, cpt, HdiF);
+  if (pc_n_out) for (int l = 0; l < o.levels; l++) pc_n_out[l] = (int)o.pc_u[l].size();
+  return SOSBA_OK;
+}
+ORC_API int orc_tracker_get_ref(orc_handle *h, int32_t lvl, int32_t *n, float *u, float *v, float *id, float *c) {
+  Oracle &o = h->o;
+  if (lvl < 0 || lvl >= o.levels) return SOSBA_E_ARG;
+  const size_t m = o.pc_u[lvl].size();
+  if (n) *n = (int)m;
+  if (u) memcpy(u, o.pc_u[lvl].data(), 4 * m);
+  if (v) memcpy(v, o.pc_v[lvl].data(), 4 * m);
+  if (id) memcpy(id, o.pc_idepth[lvl].data(), 4 * m);
+  if (c) memcpy(c, o.pc_color[lvl].data(), 4 * m);
+  return SOSBA_OK;
+}
+ORC_API int orc_tracker_scale_coarse_depth(orc_handle *h, float scale) { tracker_scaleCoarseDepth(h->o, scale); return SOSBA_OK; }
+ORC_API int orc_tracker_track(orc_handle *h, int32_t new_slot, float ref_exp, float new_exp, const double ref_aff[2], int32_t coarsest, int32_t n_hyp,
+                              sosba_track_hypothesis *hyps) {
+  Oracle &o = h->o;
+  if (new_slot < 0 || new_slot >= (int)o.slots.size() || !o.slots[new_slot].valid || coarsest < 0 || coarsest >= o.levels || coarsest >= 5 || n_hyp < 0 ||
+      (n_hyp > 0 && !hyps) || !ref_aff)
+    return SOSBA_E_ARG;
+  for (int i = 0; i < n_hyp; i++) tracker_track(o, new_slot, ref_exp, new_exp, ref_aff, coarsest, hyps + i);
+  return SOSBA_OK;
+}
+ORC_API int orc_scale_optimize(orc_handle *h, int32_t stereo_slot, int32_t coarsest, int32_t n_hyp, sosba_scale_hypothesis *hyps) {
+  Oracle &o = h->o;
+  if (stereo_slot < 0 || stereo_slot >= (int)o.slots.size() || !o.slots[stereo_slot].valid || coarsest < 0 || coarsest >= o.levels || coarsest >= 5 ||
+      n_hyp < 0 || (n_hyp > 0 && !hyps))
+    return SOSBA_E_ARG;
+  for (int i = 0; i < n_hyp; i++) scale_optimize(o, stereo_slot, coarsest, hyps + i);
+  return SOSBA_OK;
+}
 ORC_API int orc_scale_set_stereo(orc_handle *h, const double T10[12], const float K1[4]) {
   Oracle &o = h->o;
   o.tfmF0ToF1 = SE3::from_rowmajor34(T10);

@@ -71,5 +71,10 @@ void init_calcResAndGS(Oracle &o, int lvl, int ref_slot, int new_slot, const dou
 void tracker_calcGSSSEPose(Oracle &o, int lvl, float a, float b0, double H[64], double b[8]);
 void scale_calcRes(Oracle &o, int lvl, int slot, float scale, float cutoffTH, double out6[6], int32_t counts[3]);
 void scale_calcGSSSE(Oracle &o, int lvl, float scale, float *H, float *b);
+// orc_lm.cpp
+void tracker_makeCoarseDepth(Oracle &o, int ref_slot, int n, const float *center_projected_to, const float *HdiF);
+void tracker_scaleCoarseDepth(Oracle &o, float scale);
+bool tracker_track(Oracle &o, int new_slot, float ref_ab_exposure, float new_ab_exposure, const double ref_aff_g2l[2], int coarsestLvl, sosba_track_hypothesis *hy);
+void scale_optimize(Oracle &o, int stereo_slot, int coarsestLvl, sosba_scale_hypothesis *hy);
 
 }  // namespace orc

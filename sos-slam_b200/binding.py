@@ -98,6 +98,23 @@ ACT_SKIP, ACT_ACTIVATED, ACT_DELETE = 0, 1, -1
 IPS_GOOD, IPS_OOB, IPS_OUTLIER, IPS_SKIPPED, IPS_BADCONDITION, IPS_UNINITIALIZED = range(6)
 
 
+TRACK_MAX_PASSES = 8
+
+
+class TrackHypothesis(C.Structure):
+    _fields_ = [("q", C.c_double * 4), ("t", C.c_double * 3), ("aff_g2l", C.c_double * 2), ("min_res_for_abort", C.c_double * 5),
+                ("last_residuals", C.c_double * 5), ("flow_indicators", C.c_double * 3), ("ok", C.c_int32), ("n_passes", C.c_int32),
+                ("pass_lvl", C.c_int32 * TRACK_MAX_PASSES), ("pass_iterations", C.c_int32 * TRACK_MAX_PASSES),
+                ("pass_accept", C.c_uint64 * TRACK_MAX_PASSES), ("pass_residual", C.c_double * TRACK_MAX_PASSES),
+                ("pass_cutoff_repeat", C.c_float * TRACK_MAX_PASSES)]
+
+
+class ScaleHypothesis(C.Structure):
+    _fields_ = [("scale", C.c_float), ("error", C.c_float), ("last_residuals", C.c_double * 5), ("n_passes", C.c_int32),
+                ("pass_lvl", C.c_int32 * TRACK_MAX_PASSES), ("pass_iterations", C.c_int32 * TRACK_MAX_PASSES),
+                ("pass_accept", C.c_uint64 * TRACK_MAX_PASSES), ("reserved0", C.c_int32)]
+
+
 class OptimizeOut(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("res_in_a", C.c_int32), ("energy_initial", C.c_double),
                 ("energy_final", C.c_double), ("rmse", C.c_float), ("n_removed", C.c_int32),
@@ -410,6 +427,56 @@ class Handle:
     def tracker_set_ref(self, lvl, u, v, idepth, color):
         u, v, idepth, color = _f32(u), _f32(v), _f32(idepth), _f32(color)
         self._ck(self.lib.f("tracker_set_ref")(self.h, C.c_int32(lvl), C.c_int32(u.size), _p(u, f32p), _p(v, f32p), _p(idepth, f32p), _p(color, f32p)), "tracker_set_ref")
+
+    # ---- a16: makeCoarseDepthL0 / trackNewestCoarse / optimizeScale, resident on the device
+    def tracker_make_coarse_depth(self, ref_slot, center_projected_to, HdiF):
+        """-> pc_n per level"""
+        c, hd = _f32(center_projected_to).reshape(-1, 3), _f32(HdiF)
+        out = np.zeros(8, np.int32)
+        self._ck(self.lib.f("tracker_make_coarse_depth")(self.h, C.c_int32(ref_slot), C.c_int32(hd.size), _p(c, f32p), _p(hd, f32p), _p(out, i32p)),
+                 "tracker_make_coarse_depth")
+        return out[:self.levels].copy()
+
+    def tracker_get_ref(self, lvl):
+        n = C.c_int32(0)
+        self._ck(self.lib.f("tracker_get_ref")(self.h, C.c_int32(lvl), C.byref(n), None, None, None, None), "tracker_get_ref")
+        a = [np.zeros(n.value, np.float32) for _ in range(4)]
+        self._ck(self.lib.f("tracker_get_ref")(self.h, C.c_int32(lvl), C.byref(n), *[_p(x, f32p) for x in a]), "tracker_get_ref")
+        return tuple(a)
+
+    def tracker_scale_coarse_depth(self, scale):
+        self._ck(self.lib.f("tracker_scale_coarse_depth")(self.h, C.c_float(scale)), "tracker_scale_coarse_depth")
+
+    def tracker_track(self, new_slot, ref_ab_exposure, new_ab_exposure, ref_aff_g2l, coarsest_lvl, hyps):
+        """hyps: list of dicts {q (x, y, z, w), t, aff_g2l (a, b), min_res_for_abort (5, optional)} -> list of result dicts."""
+        n = len(hyps)
+        arr = (TrackHypothesis * max(n, 1))()
+        for i, hy in enumerate(hyps):
+            arr[i].q = (C.c_double * 4)(*[float(x) for x in hy["q"]])
+            arr[i].t = (C.c_double * 3)(*[float(x) for x in hy["t"]])
+            arr[i].aff_g2l = (C.c_double * 2)(*[float(x) for x in hy.get("aff_g2l", (0.0, 0.0))])
+            arr[i].min_res_for_abort = (C.c_double * 5)(*[float(x) for x in hy.get("min_res_for_abort", [float("nan")] * 5)])
+        ra = (C.c_double * 2)(float(ref_aff_g2l[0]), float(ref_aff_g2l[1]))
+        self._ck(self.lib.f("tracker_track")(self.h, C.c_int32(new_slot), C.c_float(ref_ab_exposure), C.c_float(new_ab_exposure), ra,
+                                             C.c_int32(coarsest_lvl), C.c_int32(n), arr), "tracker_track")
+        out = []
+        for i in range(n):
+            a = arr[i]
+            k = a.n_passes
+            out.append(dict(ok=bool(a.ok), q=np.array(a.q[:]), t=np.array(a.t[:]), aff_g2l=np.array(a.aff_g2l[:]), last_residuals=np.array(a.last_residuals[:]),
+                            flow_indicators=np.array(a.flow_indicators[:]), n_passes=k, pass_lvl=list(a.pass_lvl[:k]), pass_iterations=list(a.pass_iterations[:k]),
+                            pass_accept=list(a.pass_accept[:k]), pass_residual=list(a.pass_residual[:k]), pass_cutoff_repeat=list(a.pass_cutoff_repeat[:k])))
+        return out
+
+    def scale_optimize(self, stereo_slot, coarsest_lvl, scales):
+        n = len(scales)
+        arr = (ScaleHypothesis * max(n, 1))()
+        for i, sc in enumerate(scales):
+            arr[i].scale = float(sc)
+        self._ck(self.lib.f("scale_optimize")(self.h, C.c_int32(stereo_slot), C.c_int32(coarsest_lvl), C.c_int32(n), arr), "scale_optimize")
+        return [dict(scale=arr[i].scale, error=arr[i].error, last_residuals=np.array(arr[i].last_residuals[:]), n_passes=arr[i].n_passes,
+                     pass_lvl=list(arr[i].pass_lvl[:arr[i].n_passes]), pass_iterations=list(arr[i].pass_iterations[:arr[i].n_passes]),
+                     pass_accept=list(arr[i].pass_accept[:arr[i].n_passes])) for i in range(n)]
 
     # ---- CoarseInitializer::calcResAndGS (FullSystem/CoarseInitializer.cpp:450-673)
     def init_calc_res_and_gs(self, lvl, ref_slot, new_slot, refToNew34, aff, tlog, pts, alphaW=150.0 * 150.0, alphaK=2.5 * 2.5, couplingWeight=1.0):

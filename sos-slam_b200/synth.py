@@ -120,6 +120,18 @@ class _Surface:
         return s, X, Y  # dirs have z_c = 1 so s is the camera-frame depth
 
 
+def render_view(seed, w, h, K, camToWorld, aff=(0.0, 0.0)) -> np.ndarray:
+    """The surface of make_scene(seed=...) seen from an arbitrary pose (e.g. camera 1 of a stereo pair, or a frame between
+    keyframes): float32 irradiance image, I = exp(a) * texture + b like the window's frames."""
+    fx, fy, cx, cy = [float(x) for x in K]
+    surf = _Surface(np.random.default_rng(seed))
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float64)
+    dirs = np.stack([(xs - cx) / fx, (ys - cy) / fy, np.ones_like(xs)], -1)
+    z, X, Y = surf.cast(np.asarray(camToWorld, np.float64), dirs)
+    img = np.clip(np.exp(aff[0]) * np.clip(surf.T(X, Y), 8.0, 247.0) + aff[1], 0.0, 255.0)
+    return np.ascontiguousarray(img.astype(np.float32))
+
+
 def make_scene(w=640, h=480, nf=8, n_points=2000, seed=1234, fx=None, fy=None, cx=None, cy=None,
                pose_noise=2e-3, idepth_noise=0.03, forward_motion=False, dtype=np.float32) -> Scene:
     rng = np.random.default_rng(seed)

@@ -1015,3 +1015,197 @@ def scale_gs_ref(buf, fx1, fy1, scale, t):
     w = buf["weight"].astype(np.float64)
     n = (len(w) + 3) // 4 * 4
     return float(np.sum(w * J0 * J0) / n), float(np.sum(w * J0 * buf["residual"].astype(np.float64)) / n)
+
+
+# ---- a16: makeCoarseDepthL0 / trackNewestCoarse / optimizeScale (independent numpy formulations) -----------------
+def make_coarse_depth_ref(dI_levels, cpt, HdiF):
+    """CoarseTracker::makeCoarseDepthL0 (CoarseTracker.cpp:56-230) with array operations: np.add.at splat, reshape-sum pooling,
+    shifted-array dilation (neighbours outside the map count as empty), row-major compaction.
+    dI_levels: per level (h, w, 3).  -> per level (pc_u, pc_v, pc_idepth, pc_color)."""
+    L = len(dI_levels)
+    h0, w0 = dI_levels[0].shape[:2]
+    cpt = np.asarray(cpt, F).reshape(-1, 3)
+    u = (cpt[:, 0] + F(0.5)).astype(np.int64); v = (cpt[:, 1] + F(0.5)).astype(np.int64)
+    wgt = np.sqrt((1e-3 / (np.asarray(HdiF, F).astype(np.float64) + 1e-12)).astype(F))      # sqrtf of the double quotient cast to float
+    idp = [np.zeros((h0, w0), F)]; ws = [np.zeros((h0, w0), F)]
+    for k in range(len(u)):           # float += in point order (collisions are order-sensitive)
+        idp[0][v[k], u[k]] += cpt[k, 2] * wgt[k]
+        ws[0][v[k], u[k]] += wgt[k]
+    for l in range(1, L):
+        hl, wl = dI_levels[l].shape[:2]
+        def pool(a):
+            a = a[:2 * hl, :2 * wl]
+            return ((a[0::2, 0::2] + a[0::2, 1::2]) + a[1::2, 0::2]) + a[1::2, 1::2]
+        idp.append(pool(idp[l - 1]).astype(F)); ws.append(pool(ws[l - 1]).astype(F))
+    out = []
+    for l in range(L):
+        hl, wl = dI_levels[l].shape[:2]
+        bak = ws[l].copy()
+        offs = [(1, 1), (-1, -1), (1, -1), (-1, 1)] if l < 2 else [(0, 1), (0, -1), (1, 0), (-1, 0)]     # (dy, dx) in the reference's order
+        flat_b, flat_i = bak.ravel(), idp[l].ravel().copy()
+        N = hl * wl
+        idx = np.arange(wl, N - wl)
+        s = np.zeros(len(idx), F); num = np.zeros(len(idx), F); numn = np.zeros(len(idx), F)
+        for dy, dx in offs:
+            j = idx + dy * wl + dx      # FLAT neighbour index like the reference (wraps across rows at the borders)
+            okj = (j >= 0) & (j < N)
+            jj = np.where(okj, j, 0)
+            m = okj & (flat_b[jj] > 0)
+            s = np.where(m, s + flat_i[jj], s).astype(F); num = np.where(m, num + flat_b[jj], num).astype(F); numn = np.where(m, numn + F(1), numn).astype(F)
+        fill = (flat_b[idx] <= 0) & (numn > 0)
+        new_i = idp[l].ravel().copy(); new_w = ws[l].ravel().copy()
+        with np.errstate(all="ignore"):
+            new_i[idx[fill]] = (s[fill] / numn[fill]).astype(F); new_w[idx[fill]] = (num[fill] / numn[fill]).astype(F)
+        I = new_i.reshape(hl, wl); W = new_w.reshape(hl, wl)
+        ys, xs = np.mgrid[2:hl - 2, 2:wl - 2]
+        Wc = W[2:hl - 2, 2:wl - 2]; Ic = I[2:hl - 2, 2:wl - 2]
+        with np.errstate(all="ignore"):
+            nid = np.where(Wc > 0, Ic / np.where(Wc > 0, Wc, F(1)), F(-1)).astype(F)
+        col = dI_levels[l][2:hl - 2, 2:wl - 2, 0]
+        keep = (Wc > 0) & np.isfinite(col) & (nid > 0)
+        out.append((xs[keep].astype(F), ys[keep].astype(F), nid[keep], col[keep].astype(F)))
+    return out
+
+
+def quat_to_R(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]], np.float64)
+
+
+def track_newest_coarse_ref(dI_new_levels, K, pcs, T0, aff0, ref_exp, new_exp, ref_aff, coarsest, min_res_abort=None, cutoff_th=20.0, huber=F(9)):
+    """CoarseTracker::trackNewestCoarse (CoarseTracker.cpp:366-552), affine modes 0/0, poses as 4x4 matrices, numpy solves.
+    -> dict(ok, T, aff, last_residuals, flow, passes=[(lvl, iterations, accept_mask, residual)])."""
+    maxIt = [10, 20, 50, 50, 50]
+    T = np.array(T0, np.float64); aff = np.array(aff0, np.float64)
+    last = np.full(5, np.nan); flow = np.full(3, 1000.0)
+    mra = np.full(5, np.nan) if min_res_abort is None else np.asarray(min_res_abort, np.float64)
+    passes = []
+    haveRepeated = False
+
+    def lvlK(l):
+        return np.array([K[0] / (1 << l), K[1] / (1 << l), (K[2] + 0.5) / (1 << l) - 0.5, (K[3] + 0.5) / (1 << l) - 0.5], np.float32)
+
+    def affLL(a):
+        aa, bb = aff_from_to(ref_exp, new_exp, ref_aff[0], ref_aff[1], a[0], a[1])
+        return aa, bb
+
+    def calc_res(l, Tm, a, cutoff):
+        aa, bb = affLL(a)
+        return align_calc_res_ref(dI_new_levels[l], lvlK(l), pcs[l], Tm[:3, :3], Tm[:3, 3], l, cutoff, "pose", (F(aa), F(bb)), huber=huber)
+
+    lvl = coarsest
+    while lvl >= 0:
+        rep = F(1)
+        resOld, _, buf = calc_res(lvl, T, aff, F(cutoff_th) * rep)
+        while resOld[5] > 0.6 and rep < 50:
+            rep = rep * F(2)
+            resOld, _, buf = calc_res(lvl, T, aff, F(cutoff_th) * rep)
+        k = lvlK(lvl)
+        H, b = pose_gs_ref(buf, float(k[0]), float(k[1]), float(F(affLL(aff)[0])), float(F(ref_aff[1])))
+        lam = F(0.01)
+        acc_mask, it = 0, 0
+        while it < maxIt[lvl]:
+            Hl = H.copy()
+            Hl[np.arange(8), np.arange(8)] *= (1 + float(lam))
+            inc = np.linalg.solve(Hl, -b)
+            extrap = F(1)
+            if lam < F(0.001):
+                extrap = F(np.sqrt(np.sqrt(np.float64(F(0.001)) / np.float64(lam))))
+            inc = inc * float(extrap)
+            incS = inc * np.array([1, 1, 1, 0.5, 0.5, 0.5, 10, 1000.0])
+            if not np.isfinite(incS.sum()):
+                incS[:] = 0
+            Tn = se3_exp(incS[:6]) @ T
+            an = aff + incS[6:8]
+            resNew, _, bufn = calc_res(lvl, Tn, an, F(cutoff_th) * rep)
+            accept = (resNew[0] / resNew[1]) < (resOld[0] / resOld[1])
+            if accept:
+                H, b = pose_gs_ref(bufn, float(k[0]), float(k[1]), float(F(affLL(an)[0])), float(F(ref_aff[1])))
+                resOld, aff, T = resNew, an, Tn
+                lam = lam * F(0.5)
+                acc_mask |= 1 << it
+            else:
+                lam = lam * F(4)
+                if lam < F(0.001):
+                    lam = F(0.001)
+            it += 1
+            if not (np.linalg.norm(inc) > 1e-3):
+                break
+        last[lvl] = F(np.sqrt(F(resOld[0] / resOld[1])))
+        flow = resOld[2:5].copy()
+        passes.append((lvl, it, acc_mask, float(last[lvl])))
+        if last[lvl] > 1.5 * mra[lvl]:
+            return dict(ok=False, T=np.array(T0, np.float64), aff=np.array(aff0, np.float64), last_residuals=last, flow=flow, passes=passes)
+        if rep > 1 and not haveRepeated:
+            haveRepeated = True
+        else:
+            lvl -= 1
+    ok = True
+    aa, bb = affLL(aff)
+    if abs(np.log(F(aa))) > 1.5 or abs(F(bb)) > 200:
+        ok = False
+    return dict(ok=ok, T=T, aff=aff, last_residuals=last, flow=flow, passes=passes)
+
+
+def optimize_scale_ref(dI_stereo_levels, K0, K1, pcs, T10, scale0, coarsest, cutoff_th=20.0):
+    """ScaleOptimizer::optimizeScale (ScaleOptimizer.cpp:120-230). -> dict(scale, error, last_residuals, passes)."""
+    maxIt = [10, 20, 50, 50, 50]
+    last = np.full(5, np.nan)
+    s_cur = F(scale0)
+    passes = []
+    haveRepeated = False
+    T10 = np.asarray(T10, np.float64)
+
+    def lvlK(Kc, l):
+        return np.array([Kc[0] / (1 << l), Kc[1] / (1 << l), (Kc[2] + 0.5) / (1 << l) - 0.5, (Kc[3] + 0.5) / (1 << l) - 0.5], np.float32)
+
+    def calc_res(l, s, cutoff):
+        return align_calc_res_ref(dI_stereo_levels[l], lvlK(K1, l), pcs[l], T10[:3, :3], T10[:3, 3], l, cutoff, "scale", scale=s, Ki_lvl=lvlK(K0, l))
+
+    lvl = coarsest
+    while lvl >= 0:
+        rep = F(1)
+        resOld, _, buf = calc_res(lvl, s_cur, F(cutoff_th) * rep)
+        while resOld[5] > 0.6 and rep < 50:
+            rep = rep * F(2)
+            resOld, _, buf = calc_res(lvl, s_cur, F(cutoff_th) * rep)
+        k1 = lvlK(K1, lvl)
+        H, b = scale_gs_ref(buf, float(k1[0]), float(k1[1]), float(s_cur), T10[:3, 3])
+        H, b = F(H), F(b)
+        lam = F(0.01)
+        acc_mask, it = 0, 0
+        while it < maxIt[lvl]:
+            Hl = F(H * (F(1) + lam))
+            with np.errstate(all="ignore"):
+                inc = F(-b / Hl)
+            extrap = F(1)
+            if lam < F(0.001):
+                extrap = F(np.sqrt(np.sqrt(np.float64(F(0.001)) / np.float64(lam))))
+            inc = F(inc * extrap)
+            if not np.isfinite(inc) or abs(inc) > s_cur:
+                inc = F(0)
+            s_new = F(s_cur + inc)
+            resNew, _, bufn = calc_res(lvl, s_new, F(cutoff_th) * rep)
+            accept = (resNew[0] / resNew[1]) < (resOld[0] / resOld[1])
+            if accept:
+                H, b = scale_gs_ref(bufn, float(k1[0]), float(k1[1]), float(s_new), T10[:3, 3])
+                H, b = F(H), F(b)
+                resOld, s_cur = resNew, s_new
+                lam = lam * F(0.5)
+                acc_mask |= 1 << it
+            else:
+                lam = lam * F(4)
+                if lam < F(0.001):
+                    lam = F(0.001)
+            it += 1
+            if not (inc > 1e-3):
+                break
+        last[lvl] = F(np.sqrt(F(resOld[0] / resOld[1])))
+        passes.append((lvl, it, acc_mask))
+        if rep > 1 and not haveRepeated:
+            haveRepeated = True
+        else:
+            lvl -= 1
+    return dict(scale=float(s_cur), error=float(last[0]), last_residuals=last, passes=passes)

@@ -810,3 +810,88 @@ def test_residuals_set_rejects_bad_indices(orc):
             h.residuals_set(bad)
     h.residuals_set(res)
     h.close()
+
+
+# ---- a16 / a17: the control loops of the direct alignment against independent numpy formulations ----------------------
+def test_make_coarse_depth_vs_numpy(orc):
+    """CoarseTracker::makeCoarseDepthL0 (CoarseTracker.cpp:56-230): the point lists of every level identical (positions,
+    order, count), idepth / colour bit-identical, against an array formulation (np.add.at-style splat, strided pooling,
+    shifted-array dilation)."""
+    from _track_case import coarse_depth_input
+    for cfg in (TINY, SMALLC):
+        sc = scene(**cfg)
+        h = open_handle(orc, sc)
+        cpt, hdi = coarse_depth_input(h, sc)
+        assert len(hdi) > 50
+        # a few collisions (3 points on one pixel) so that the order-sensitive float sums are exercised
+        cpt = np.concatenate([cpt, cpt[:3] * 0 + cpt[5], cpt[7:9] * 0 + cpt[5]])
+        hdi = np.concatenate([hdi, hdi[:3] * 1.7, hdi[7:9] * 0.3])
+        n = h.tracker_make_coarse_depth(sc.nf - 1, cpt, hdi)
+        dIs = [np.asarray(h.frame_get_level(sc.nf - 1, l)[0], np.float32).reshape(sc.h >> l, sc.w >> l, 3) for l in range(h.levels)]
+        ref = np_ref.make_coarse_depth_ref(dIs, cpt, hdi)
+        for l in range(h.levels):
+            got = h.tracker_get_ref(l)
+            assert n[l] == len(ref[l][0]) == len(got[0]) and n[l] > 0, (l, n[l], len(ref[l][0]))
+            for a, b in zip(got, ref[l]):
+                assert np.array_equal(a.view(np.uint32), np.asarray(b, np.float32).view(np.uint32)), l
+        assert n[0] >= len(hdi) - 5 - 8 and n[0] > n[-1]     # level 0: at least one entry per splatted pixel (dilation adds more), minus collisions / border
+        h.tracker_scale_coarse_depth(2.0)
+        assert np.array_equal(h.tracker_get_ref(0)[2], (np.asarray(ref[0][2], np.float32) / np.float32(2.0)))
+        h.close()
+
+
+def test_track_newest_coarse_vs_numpy(orc):
+    """CoarseTracker::trackNewestCoarse (CoarseTracker.cpp:366-552): level schedule, iteration counts, accept / reject sequence
+    and abort identical to a numpy restatement; final pose and affine to 1e-6; converges to the true relative pose."""
+    from _track_case import coarse_depth_input, hypotheses, quat_to_T, ref_affine
+    sc = scene(**SMALLC)
+    h = open_handle(orc, sc)
+    cpt, hdi = coarse_depth_input(h, sc)
+    h.tracker_make_k(sc.K.astype(np.float32))
+    h.tracker_make_coarse_depth(sc.nf - 1, cpt, hdi)
+    pcs = [h.tracker_get_ref(l) for l in range(h.levels)]
+    dIs = [np.asarray(h.frame_get_level(sc.nf - 2, l)[0], np.float32).reshape(sc.h >> l, sc.w >> l, 3) for l in range(h.levels)]
+    Ttrue, hyps = hypotheses(sc, n_extra=1)
+    ref_aff, ref_exp, new_exp = ref_affine(sc)
+    hyps.append(dict(hyps[0], min_res_for_abort=[0.01] * 5))       # aborts after the coarsest level
+    out = h.tracker_track(sc.nf - 2, ref_exp, new_exp, ref_aff, h.levels - 1, hyps)
+    for hy, o in zip(hyps, out):
+        r = np_ref.track_newest_coarse_ref(dIs, sc.K.astype(np.float32), pcs, quat_to_T(hy["q"], hy["t"]), hy["aff_g2l"], ref_exp, new_exp, ref_aff,
+                                           h.levels - 1, hy.get("min_res_for_abort"))
+        assert o["ok"] == r["ok"]
+        assert [(a, b, c) for a, b, c in zip(o["pass_lvl"], o["pass_iterations"], o["pass_accept"])] == [(p[0], p[1], p[2]) for p in r["passes"]]
+        np.testing.assert_allclose(o["pass_residual"], [p[3] for p in r["passes"]], rtol=2e-5)
+        np.testing.assert_allclose(o["flow_indicators"], r["flow"], rtol=1e-4)
+        To = quat_to_T(o["q"], o["t"])
+        np.testing.assert_allclose(To, r["T"], atol=1e-6)
+        np.testing.assert_allclose(o["aff_g2l"], r["aff"], rtol=1e-5, atol=1e-5)
+    assert out[0]["ok"] and not out[-1]["ok"] and out[-1]["n_passes"] == 1
+    dT = np.linalg.inv(quat_to_T(out[0]["q"], out[0]["t"])) @ Ttrue
+    assert np.abs(dT - np.eye(4)).max() < 3e-3        # the loop finds the true relative pose of the synthetic frames
+    assert sum(out[0]["pass_iterations"]) >= 6 and out[0]["pass_lvl"][0] == h.levels - 1 and out[0]["pass_lvl"][-1] == 0
+    h.close()
+
+
+def test_optimize_scale_vs_numpy(orc):
+    """ScaleOptimizer::optimizeScale (ScaleOptimizer.cpp:120-230) from several start values: schedule, accept sequence, scale."""
+    from _track_case import coarse_depth_input, stereo_frame
+    sc = scene(**SMALLC)
+    h = open_handle(orc, sc)
+    cpt, hdi = coarse_depth_input(h, sc)
+    K = sc.K.astype(np.float32)
+    h.tracker_make_k(K)
+    h.tracker_make_coarse_depth(sc.nf - 1, cpt, hdi)
+    pcs = [h.tracker_get_ref(l) for l in range(h.levels)]
+    T10, img1 = stereo_frame(sc, SMALLC["seed"])
+    h.scale_set_stereo(T10, K)
+    slot = sc.nf                # a free slot holds camera 1 of the newest keyframe
+    h.frame_make_images(slot, img1)
+    dIs = [np.asarray(h.frame_get_level(slot, l)[0], np.float32).reshape(sc.h >> l, sc.w >> l, 3) for l in range(h.levels)]
+    starts = [0.5, 1.0, 2.0]
+    out = h.scale_optimize(slot, h.levels - 1, starts)
+    for s0, o in zip(starts, out):
+        r = np_ref.optimize_scale_ref(dIs, K, K, pcs, np_ref.to44(T10), s0, h.levels - 1)
+        assert [(a, b, c) for a, b, c in zip(o["pass_lvl"], o["pass_iterations"], o["pass_accept"])] == r["passes"], (s0, o, r)
+        assert o["scale"] == pytest.approx(r["scale"], rel=1e-5) and o["error"] == pytest.approx(r["error"], rel=2e-5)
+    assert abs(out[1]["scale"] - 1.0) < 0.02 and out[1]["error"] < 8        # the stereo pair was rendered at scale 1
+    h.close()

@@ -164,6 +164,62 @@ def config_of(sc, factor, scaling):
             "linearizations_per_step": ITERS + 2, "scaling": scaling, "l2": L2_NOTE}
 
 
+def lm_timings(h, sc, synth, reps=10, make_images=False):
+    """Host wall per call of makeCoarseDepthL0, trackNewestCoarse (1 and 32 hypotheses) and optimizeScale (the 7 start values of
+    FullSystem::optimizeScale) on the window's newest keyframe; the same calls time libsosba and the CPU port."""
+    from _track_case import hypotheses, ref_affine, stereo_frame
+    if make_images:
+        for i, img in enumerate(sc.images):
+            h.frame_make_images(i, img)
+    rng = np.random.default_rng(9)
+    nref = sc.nf - 1
+    # every active point hosted in an older keyframe projects into the newest one: (u, v, idepth) of the centre projections
+    m = sc.pt_host != nref
+    Tn = np.linalg.inv(sc.camToWorld_true[nref])
+    fx, fy, cx, cy = [float(x) for x in sc.K]
+    cpt = []
+    for hst in np.unique(sc.pt_host[m]):
+        q = m & (sc.pt_host == hst)
+        z = 1.0 / sc.pt_idepth_true[q]
+        P = np.stack([(sc.pt_u[q] - cx) / fx * z, (sc.pt_v[q] - cy) / fy * z, z, np.ones_like(z)], 0)
+        Pn = (Tn @ sc.camToWorld_true[hst] @ P)[:3]
+        cpt.append(np.stack([fx * Pn[0] / Pn[2] + cx, fy * Pn[1] / Pn[2] + cy, 1.0 / Pn[2]], 1))
+    cpt = np.concatenate(cpt).astype(np.float32)
+    ok = (cpt[:, 0] > 3) & (cpt[:, 1] > 3) & (cpt[:, 0] < sc.w - 4) & (cpt[:, 1] < sc.h - 4) & (cpt[:, 2] > 0)
+    cpt = cpt[ok]
+    hdi = rng.uniform(1e-4, 1e-2, len(cpt)).astype(np.float32)
+    K = sc.K.astype(np.float32)
+    h.tracker_make_k(K)
+    n = h.tracker_make_coarse_depth(nref, cpt, hdi)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        h.tracker_make_coarse_depth(nref, cpt, hdi)
+    cd_ms = 1e3 * (time.perf_counter() - t0) / reps
+    _, hyps = hypotheses(sc, n_extra=30, seed=2)
+    ref_aff, ref_exp, new_exp = ref_affine(sc)
+    out = {}
+    for tag, hy in (("1", hyps[:1]), ("32", hyps)):
+        h.tracker_track(sc.nf - 2, ref_exp, new_exp, ref_aff, h.levels - 1, hy)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = h.tracker_track(sc.nf - 2, ref_exp, new_exp, ref_aff, h.levels - 1, hy)
+        out["track_%s_hyp_ms" % tag] = 1e3 * (time.perf_counter() - t0) / reps
+        out["track_%s_lm_iterations" % tag] = int(sum(sum(x["pass_iterations"]) for x in r))
+    T10, img1 = stereo_frame(sc, 1234 if (sc.w, sc.h) == (640, 480) else 0)
+    h.scale_set_stereo(T10, K)
+    h.frame_make_images(sc.nf, img1)
+    starts = [0.1, 0.2, 0.5, 1, 2, 5, 10]
+    h.scale_optimize(sc.nf, h.levels - 1, starts)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        rs = h.scale_optimize(sc.nf, h.levels - 1, starts)
+    out.update({"make_coarse_depth_ms": cd_ms, "reference_points_per_level": [int(x) for x in n], "splatted_points": int(len(cpt)),
+                "optimize_scale_7_starts_ms": 1e3 * (time.perf_counter() - t0) / reps,
+                "optimize_scale_lm_iterations": int(sum(sum(x["pass_iterations"]) for x in rs)),
+                "note": "host wall per call incl. H2D of the inputs and D2H of the results; hypotheses = perturbed true pose, identity, 30 random"})
+    return out
+
+
 def forced_cfg(lib, sc, threads=1):
     cfg = lib.config_default(sc.w, sc.h)
     cfg.num_threads = threads
@@ -457,6 +513,8 @@ def main():
                 h.scale_calc_res(0, 1, 1.0, 20.0)                        # a17
                 h.scale_calc_gs(0, 1.0)
             scl_ms = 1e3 * (time.perf_counter() - t0) / reps
+            # a16 / a17: the direct-alignment control loops resident on the device (one launch, one synchronisation per call)
+            lm = lm_timings(h, sc, synth, reps=10)
             # 8f rank 1: traceNewCoarse of 2000 immature points per older keyframe into the newest one (host buffers in and out)
             case = synth.trace_case(sc, sc.nf - 1, n_per_host=2000, seed=3)
             ip_parts = [h.immature_init(hst, case["u"][case["host"] == hst], case["v"][case["host"] == hst]) for hst in range(sc.nf - 1)]
@@ -493,7 +551,8 @@ def main():
                      "trace_immature_counts": [int(x) for x in trace_counts],
                      "trace_note": "first trace (unbounded interval: the longest epipolar search), host SoA in and out, host wall per call",
                      "tracker_calcRes_plus_calcGS_ms": trk_ms, "scale_calcRes_plus_calcGS_ms": scl_ms,
-                     "tracker_note": f"level 0, {n_ref} reference points, results returned to the host each call (host wall)"}
+                     "tracker_note": f"level 0, {n_ref} reference points, results returned to the host each call (host wall)",
+                     "direct_alignment_loops": lm}
         except Exception as ex:   # the BA numbers above do not depend on this block
             other = {"error": str(ex)}
 
@@ -612,6 +671,12 @@ def main():
             except Exception as ex:
                 cpu_trace = {"error": str(ex)}
             oh.close()
+            try:
+                if cpu_trace is not None and "error" not in cpu_trace:
+                    cpu_trace["direct_alignment_loops"] = lm_timings(oh2 := binding.Handle(olib, forced_cfg(olib, sc1, threads=1)), sc1, synth, reps=2, make_images=True)
+                    oh2.close()
+            except Exception as ex:
+                cpu_trace["direct_alignment_loops"] = {"error": str(ex)}
             cpu = {"other_kernels": cpu_trace, "value": rcpu / tcpu, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{n - 1} optimize() steps of the same window ({tcpu:.1f} s), oracle speed build, {cores} IndexThreadReduce workers",
                    "ms_per_step": 1e3 * tcpu / (n - 1)}

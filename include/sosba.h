@@ -293,6 +293,8 @@ typedef struct sosba_track_hypothesis {
   int32_t pass_lvl[SOSBA_TRACK_MAX_PASSES];         /* out */
   int32_t pass_iterations[SOSBA_TRACK_MAX_PASSES];  /* out: LM iterations of the pass */
   uint64_t pass_accept[SOSBA_TRACK_MAX_PASSES];     /* out: bit i = iteration i accepted */
+  uint64_t pass_tie[SOSBA_TRACK_MAX_PASSES];        /* out: bit i = the two mean energies of iteration i were closer than 2e-5 relative: the
+                                                       decision was taken on energies re-added in point order like the reference's float sum */
   double pass_residual[SOSBA_TRACK_MAX_PASSES];     /* out: sqrt(resOld[0] / resOld[1]) at the end of the pass */
   float pass_cutoff_repeat[SOSBA_TRACK_MAX_PASSES]; /* out: levelCutoffRepeat of the pass */
 } sosba_track_hypothesis;
@@ -314,6 +316,7 @@ typedef struct sosba_scale_hypothesis {
   int32_t pass_lvl[SOSBA_TRACK_MAX_PASSES];
   int32_t pass_iterations[SOSBA_TRACK_MAX_PASSES];
   uint64_t pass_accept[SOSBA_TRACK_MAX_PASSES];
+  uint64_t pass_tie[SOSBA_TRACK_MAX_PASSES];
   int32_t reserved0;
 } sosba_scale_hypothesis;
 /* camera-1 frame in stereo_slot; needs sosba_scale_set_stereo and the reference lists. */

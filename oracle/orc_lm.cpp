@@ -111,7 +111,7 @@ bool tracker_track(Oracle &o, int new_slot, float ref_ab_exposure, float new_ab_
   bool haveRepeated = false;
   hy->n_passes = 0; hy->ok = 0;
   memset(hy->pass_lvl, 0, sizeof(hy->pass_lvl)); memset(hy->pass_iterations, 0, sizeof(hy->pass_iterations));
-  memset(hy->pass_accept, 0, sizeof(hy->pass_accept)); memset(hy->pass_residual, 0, sizeof(hy->pass_residual));
+  memset(hy->pass_accept, 0, sizeof(hy->pass_accept)); memset(hy->pass_tie, 0, sizeof(hy->pass_tie)); memset(hy->pass_residual, 0, sizeof(hy->pass_residual));
   memset(hy->pass_cutoff_repeat, 0, sizeof(hy->pass_cutoff_repeat));
   const float cutoffTH = o.cfg.coarse_cutoff_th;
   const float modeA = o.cfg.affine_opt_mode_a, modeB = o.cfg.affine_opt_mode_b;
@@ -193,6 +193,7 @@ bool tracker_track(Oracle &o, int new_slot, float ref_ab_exposure, float new_ab_
       double resNew[6];
       calcRes(lvl, refToNew_new, aff_new, cutoffTH * levelCutoffRepeat, resNew);
       const bool accept = (resNew[0] / resNew[1]) < (resOld[0] / resOld[1]);
+      if (iteration < 64 && fabs(resNew[0] / resNew[1] - resOld[0] / resOld[1]) <= 2e-5 * fabs(resOld[0] / resOld[1])) hy->pass_tie[pass] |= 1ull << iteration;   // (reported only)
       if (accept) {
         calcGS(lvl, aff_new, H, b);
         memcpy(resOld, resNew, sizeof(resOld));
@@ -240,6 +241,7 @@ void scale_optimize(Oracle &o, int stereo_slot, int coarsestLvl, sosba_scale_hyp
   bool haveRepeated = false;
   hy->n_passes = 0;
   memset(hy->pass_lvl, 0, sizeof(hy->pass_lvl)); memset(hy->pass_iterations, 0, sizeof(hy->pass_iterations)); memset(hy->pass_accept, 0, sizeof(hy->pass_accept));
+  memset(hy->pass_tie, 0, sizeof(hy->pass_tie));
   const float cutoffTH = o.cfg.coarse_cutoff_th;
   for (int lvl = coarsestLvl; lvl >= 0; lvl--) {
     float H, b;
@@ -267,6 +269,7 @@ void scale_optimize(Oracle &o, int stereo_slot, int coarsestLvl, sosba_scale_hyp
       const float scale_new = scale_current + inc;
       scale_calcRes(o, lvl, stereo_slot, scale_new, cutoffTH * levelCutoffRepeat, resNew, counts);
       const bool accept = (resNew[0] / resNew[1]) < (resOld[0] / resOld[1]);
+      if (iteration < 64 && fabs(resNew[0] / resNew[1] - resOld[0] / resOld[1]) <= 2e-5 * fabs(resOld[0] / resOld[1])) hy->pass_tie[pass] |= 1ull << iteration;   // (reported only)
       if (accept) {
         scale_calcGSSSE(o, lvl, scale_new, &H, &b);
         memcpy(resOld, resNew, sizeof(resOld));

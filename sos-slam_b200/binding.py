@@ -105,14 +105,14 @@ class TrackHypothesis(C.Structure):
     _fields_ = [("q", C.c_double * 4), ("t", C.c_double * 3), ("aff_g2l", C.c_double * 2), ("min_res_for_abort", C.c_double * 5),
                 ("last_residuals", C.c_double * 5), ("flow_indicators", C.c_double * 3), ("ok", C.c_int32), ("n_passes", C.c_int32),
                 ("pass_lvl", C.c_int32 * TRACK_MAX_PASSES), ("pass_iterations", C.c_int32 * TRACK_MAX_PASSES),
-                ("pass_accept", C.c_uint64 * TRACK_MAX_PASSES), ("pass_residual", C.c_double * TRACK_MAX_PASSES),
+                ("pass_accept", C.c_uint64 * TRACK_MAX_PASSES), ("pass_tie", C.c_uint64 * TRACK_MAX_PASSES), ("pass_residual", C.c_double * TRACK_MAX_PASSES),
                 ("pass_cutoff_repeat", C.c_float * TRACK_MAX_PASSES)]
 
 
 class ScaleHypothesis(C.Structure):
     _fields_ = [("scale", C.c_float), ("error", C.c_float), ("last_residuals", C.c_double * 5), ("n_passes", C.c_int32),
                 ("pass_lvl", C.c_int32 * TRACK_MAX_PASSES), ("pass_iterations", C.c_int32 * TRACK_MAX_PASSES),
-                ("pass_accept", C.c_uint64 * TRACK_MAX_PASSES), ("reserved0", C.c_int32)]
+                ("pass_accept", C.c_uint64 * TRACK_MAX_PASSES), ("pass_tie", C.c_uint64 * TRACK_MAX_PASSES), ("reserved0", C.c_int32)]
 
 
 class OptimizeOut(C.Structure):
@@ -465,7 +465,7 @@ class Handle:
             k = a.n_passes
             out.append(dict(ok=bool(a.ok), q=np.array(a.q[:]), t=np.array(a.t[:]), aff_g2l=np.array(a.aff_g2l[:]), last_residuals=np.array(a.last_residuals[:]),
                             flow_indicators=np.array(a.flow_indicators[:]), n_passes=k, pass_lvl=list(a.pass_lvl[:k]), pass_iterations=list(a.pass_iterations[:k]),
-                            pass_accept=list(a.pass_accept[:k]), pass_residual=list(a.pass_residual[:k]), pass_cutoff_repeat=list(a.pass_cutoff_repeat[:k])))
+                            pass_accept=list(a.pass_accept[:k]), pass_tie=list(a.pass_tie[:k]), pass_residual=list(a.pass_residual[:k]), pass_cutoff_repeat=list(a.pass_cutoff_repeat[:k])))
         return out
 
     def scale_optimize(self, stereo_slot, coarsest_lvl, scales):
@@ -476,7 +476,7 @@ class Handle:
         self._ck(self.lib.f("scale_optimize")(self.h, C.c_int32(stereo_slot), C.c_int32(coarsest_lvl), C.c_int32(n), arr), "scale_optimize")
         return [dict(scale=arr[i].scale, error=arr[i].error, last_residuals=np.array(arr[i].last_residuals[:]), n_passes=arr[i].n_passes,
                      pass_lvl=list(arr[i].pass_lvl[:arr[i].n_passes]), pass_iterations=list(arr[i].pass_iterations[:arr[i].n_passes]),
-                     pass_accept=list(arr[i].pass_accept[:arr[i].n_passes])) for i in range(n)]
+                     pass_accept=list(arr[i].pass_accept[:arr[i].n_passes]), pass_tie=list(arr[i].pass_tie[:arr[i].n_passes])) for i in range(n)]
 
     # ---- CoarseInitializer::calcResAndGS (FullSystem/CoarseInitializer.cpp:450-673)
     def init_calc_res_and_gs(self, lvl, ref_slot, new_slot, refToNew34, aff, tlog, pts, alphaW=150.0 * 150.0, alphaK=2.5 * 2.5, couplingWeight=1.0):

@@ -323,6 +323,7 @@ API void sosba_destroy(sosba_t *h) {
   sosba_comm_destroy(h);
   HostSide *hs = HS(h);
   for (void *p : hs->allocs) cudaFree(p);
+  for (void *p : h->lm_allocs) cudaFree(p);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (hs->pin_d) cudaFreeHost(hs->pin_d);
   if (hs->stage) cudaFreeHost(hs->stage);
@@ -1277,9 +1278,9 @@ static void mul33f(const float *A, const float *B, float *C) {
     for (int j = 0; j < 3; j++) C[3 * i + j] = (A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j]) + A[3 * i + 2] * B[6 + j];
 }
 
-API int sosba_tracker_set_ref(sosba_t *h, int32_t lvl, int32_t n, const float *u, const float *v, const float *id, const float *c) {
-  CHECK_H(h);
-  if (lvl < 0 || lvl >= h->levels || n < 0) return SOSBA_E_ARG;
+// room for n reference points on level lvl (pc_u | pc_v | pc_idepth | pc_color) and for the warped buffers of the per-call
+// calcRes / calcGSSSE entry points; shared by sosba_tracker_set_ref and sosba_tracker_make_coarse_depth (k_lm.cu)
+int sosba_tracker_reserve(sosba *h, int lvl, int n) {
   if (n > h->t_cap[lvl]) {
     dfree(h, h->t_pc[lvl]);
     h->t_cap[lvl] = n + n / 4 + 64;
@@ -1290,6 +1291,13 @@ API int sosba_tracker_set_ref(sosba_t *h, int32_t lvl, int32_t n, const float *u
     h->t_warp_cap = n + n / 4 + 64;
     DALLOC(h, h->t_warp, 8 * (size_t)h->t_warp_cap);
   }
+  return SOSBA_OK;
+}
+
+API int sosba_tracker_set_ref(sosba_t *h, int32_t lvl, int32_t n, const float *u, const float *v, const float *id, const float *c) {
+  CHECK_H(h);
+  if (lvl < 0 || lvl >= h->levels || n < 0) return SOSBA_E_ARG;
+  { int rc0 = sosba_tracker_reserve(h, lvl, n); if (rc0) return rc0; }
   h->t_n[lvl] = n;
   int rc;
   if ((rc = up(h, h->t_pc[lvl], u, n)) || (rc = up(h, h->t_pc[lvl] + n, v, n)) || (rc = up(h, h->t_pc[lvl] + 2 * (size_t)n, id, n)) ||

@@ -138,6 +138,18 @@ struct sosba {
   int t_warp_lvl = -1, t_warp_kind = 0;
   double *t_acc = nullptr;   // [64] tracker sums
 
+  // direct-alignment control loops on the device (k_lm.cu): makeCoarseDepthL0 maps and scratch, hypotheses
+  float *cd_idepth = nullptr, *cd_wsum = nullptr, *cd_wbak = nullptr;   // per-level maps in one arena (level offsets = lvl_off)
+  int *cd_cnt = nullptr;          // level 0: hits per pixel | lowest point index
+  uint8_t *cd_mark = nullptr;     // pixels that enter the point list
+  int2 *cd_list = nullptr;        // raster-order list per level
+  int *cd_scan = nullptr;         // compaction scratch
+  void *lm_hyp = nullptr;         // device copy of the hypotheses of one call
+  size_t lm_hyp_cap = 0;
+  float *lm_terms = nullptr;      // per hypothesis: energy terms of the accepted state and of the candidate
+  size_t lm_terms_cap = 0;
+  std::vector<void *> lm_allocs;
+
   // composed GN loop (host mirror of FullSystem state)
   struct BA *ba = nullptr;
 

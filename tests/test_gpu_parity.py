@@ -588,3 +588,125 @@ def test_pixel_select_random_images(gpu, orc, seed):
         assert (g["n"], g["potential"]) == (o["n"], o["potential"]) and np.array_equal(g["map"], o["map"]), density
     for hd in hs:
         hd.close()
+
+
+# ---- a16 / a17: the control loops of the direct alignment, resident on the device ---------------------------------------
+def _lm_case(orc, cfg):
+    """reference lists input (from the oracle's optimised window, so that both sides get identical arrays)"""
+    from _track_case import coarse_depth_input
+    sc = scene(**cfg)
+    ho = open_handle(orc, sc)
+    cpt, hdi = coarse_depth_input(ho, sc)
+    # three and four points on one pixel: the order-sensitive float sums of the splat
+    cpt = np.concatenate([cpt, cpt[:3] * 0 + cpt[5], cpt[7:9] * 0 + cpt[5], cpt[20:23] * 0 + cpt[30]])
+    hdi = np.concatenate([hdi, hdi[:3] * 1.7, hdi[7:9] * 0.3, hdi[20:23] * 0.9])
+    return sc, ho, cpt, hdi
+
+
+@pytest.mark.parametrize("cfg", [SMALL, CONFIG_B, KITTI], ids=["small", "configB", "kitti"])
+def test_make_coarse_depth_bit_exact(gpu, orc, cfg):
+    """CoarseTracker::makeCoarseDepthL0 (CoarseTracker.cpp:56-230): pc_u / pc_v / pc_idepth / pc_color of every level identical
+    to the oracle's (count, order, every bit), scaleCoarseDepthL0 included."""
+    sc, ho, cpt, hdi = _lm_case(orc, cfg)
+    hg = open_handle(gpu, sc)
+    ng = hg.tracker_make_coarse_depth(sc.nf - 1, cpt, hdi)
+    no = ho.tracker_make_coarse_depth(sc.nf - 1, cpt, hdi)
+    assert np.array_equal(ng, no) and ng[0] > len(hdi) // 2
+    for scale in (None, 1.7):
+        if scale:
+            hg.tracker_scale_coarse_depth(scale); ho.tracker_scale_coarse_depth(scale)
+        for l in range(hg.levels):
+            for a, b in zip(hg.tracker_get_ref(l), ho.tracker_get_ref(l)):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (l, scale)
+    # an empty reference (no IN residual on the newest keyframe): empty lists, and tracking it is not an error
+    assert not hg.tracker_make_coarse_depth(sc.nf - 1, np.zeros((0, 3), np.float32), np.zeros(0, np.float32)).any()
+    with pytest.raises(Exception):
+        hg.tracker_make_coarse_depth(sc.nf - 1, np.array([[sc.w + 5.0, 3.0, 1.0]], np.float32), np.ones(1, np.float32))
+    hg.close(); ho.close()
+
+
+@pytest.mark.parametrize("cfg", [SMALL, CONFIG_B], ids=["small", "configB"])
+def test_track_newest_coarse(gpu, orc, cfg):
+    """CoarseTracker::trackNewestCoarse (CoarseTracker.cpp:366-552), a batch of hypotheses in one launch: level schedule,
+    iteration counts, accept / reject sequence, cutoff doubling, abort and return value identical to the oracle; residuals
+    2e-5, flow indicators 1e-4, final pose and affine 1e-5 relative to the step the loop made."""
+    from _track_case import hypotheses, quat_to_T, ref_affine
+    sc, ho, cpt, hdi = _lm_case(orc, cfg)
+    hg = open_handle(gpu, sc)
+    Ttrue, hyps = hypotheses(sc, n_extra=6, seed=4)
+    hyps.append(dict(hyps[0], min_res_for_abort=[0.01] * 5))
+    hyps.append(dict(hyps[1], aff_g2l=(0.3, -20.0)))
+    ref_aff, ref_exp, new_exp = ref_affine(sc)
+    outs = []
+    for h in (hg, ho):
+        h.tracker_make_k(sc.K.astype(np.float32))
+        h.tracker_make_coarse_depth(sc.nf - 1, cpt, hdi)
+        outs.append(h.tracker_track(sc.nf - 2, ref_exp, new_exp, ref_aff, h.levels - 1, hyps))
+    n_ok = n_exact = 0
+    for hy, g, o in zip(hyps, *outs):
+        Tg, To, T0 = quat_to_T(g["q"], g["t"]), quat_to_T(o["q"], o["t"]), quat_to_T(hy["q"], hy["t"])
+        moved = max(np.abs(To - T0).max(), 1e-3)
+        n_ok += g["ok"]
+        same = g["pass_lvl"] == o["pass_lvl"] and g["pass_iterations"] == o["pass_iterations"] and g["pass_accept"] == o["pass_accept"]
+        if not same:
+            # The only licence to differ: an accept / reject decision taken on two mean energies closer than 2e-5 relative (flagged
+            # by either side; below the noise of the reference's own float sums, whose normal equations no parallel sum reproduces
+            # bit for bit).  Everything before that iteration is identical and the loop still ends at the same minimum.
+            p = next(i for i in range(min(g["n_passes"], o["n_passes"])) if (g["pass_lvl"][i], g["pass_iterations"][i], g["pass_accept"][i]) !=
+                     (o["pass_lvl"][i], o["pass_iterations"][i], o["pass_accept"][i]))
+            assert g["pass_lvl"][:p + 1] == o["pass_lvl"][:p + 1] and g["pass_cutoff_repeat"][:p + 1] == o["pass_cutoff_repeat"][:p + 1]
+            diff = g["pass_accept"][p] ^ o["pass_accept"][p]
+            k = (diff & -diff).bit_length() - 1 if diff else min(g["pass_iterations"][p], o["pass_iterations"][p]) - 1
+            assert ((g["pass_tie"][p] | o["pass_tie"][p]) >> k) & 1, (p, k, g, o)
+            assert g["ok"] == o["ok"]
+            np.testing.assert_allclose(g["last_residuals"], o["last_residuals"], rtol=2e-3, equal_nan=True)
+            assert np.abs(Tg - To).max() <= 2e-2 * moved
+            continue
+        n_exact += 1
+        assert g["ok"] == o["ok"] and g["n_passes"] == o["n_passes"] and g["pass_cutoff_repeat"] == o["pass_cutoff_repeat"]
+        np.testing.assert_allclose(g["pass_residual"], o["pass_residual"], rtol=2e-5)
+        np.testing.assert_allclose(g["last_residuals"], o["last_residuals"], rtol=2e-5, equal_nan=True)
+        np.testing.assert_allclose(g["flow_indicators"], o["flow_indicators"], rtol=1e-4, atol=1e-7)
+        assert np.abs(Tg - To).max() <= 1e-5 * moved + 1e-9, (np.abs(Tg - To).max(), moved)
+        np.testing.assert_allclose(g["aff_g2l"], o["aff_g2l"], rtol=1e-4, atol=1e-4)
+    assert n_exact >= len(hyps) - 2      # near-ties are the exception
+    assert n_ok >= len(hyps) - 3 and not outs[0][-2]["ok"]
+    dT = np.linalg.inv(quat_to_T(outs[0][0]["q"], outs[0][0]["t"])) @ Ttrue
+    assert np.abs(dT - np.eye(4)).max() < 3e-3
+    hg.close(); ho.close()
+
+
+def test_optimize_scale(gpu, orc):
+    """ScaleOptimizer::optimizeScale (ScaleOptimizer.cpp:120-230) from the 7 start values of FullSystem::optimizeScale
+    (FullSystem.cpp:1135) in one launch: schedule and accept sequence identical, scale 1e-5, error 2e-5."""
+    from _track_case import stereo_frame
+    sc, ho, cpt, hdi = _lm_case(orc, SMALL)
+    hg = open_handle(gpu, sc)
+    K = sc.K.astype(np.float32)
+    T10, img1 = stereo_frame(sc, SMALL["seed"])
+    starts = [0.1, 0.2, 0.5, 1, 2, 5, 10]
+    outs = []
+    for h in (hg, ho):
+        h.tracker_make_k(K)
+        h.tracker_make_coarse_depth(sc.nf - 1, cpt, hdi)
+        h.scale_set_stereo(T10, K)
+        h.frame_make_images(sc.nf, img1)
+        outs.append(h.scale_optimize(sc.nf, h.levels - 1, starts))
+    n_exact = 0
+    for s0, g, o in zip(starts, *outs):
+        same = g["pass_lvl"] == o["pass_lvl"] and g["pass_iterations"] == o["pass_iterations"] and g["pass_accept"] == o["pass_accept"]
+        if not same:    # only after a decision between two mean energies closer than 2e-5 relative (see test_track_newest_coarse)
+            p = next(i for i in range(min(g["n_passes"], o["n_passes"])) if (g["pass_lvl"][i], g["pass_iterations"][i], g["pass_accept"][i]) !=
+                     (o["pass_lvl"][i], o["pass_iterations"][i], o["pass_accept"][i]))
+            diff = g["pass_accept"][p] ^ o["pass_accept"][p]
+            k = (diff & -diff).bit_length() - 1 if diff else min(g["pass_iterations"][p], o["pass_iterations"][p]) - 1
+            assert ((g["pass_tie"][p] | o["pass_tie"][p]) >> k) & 1, (s0, p, k, g, o)
+            assert g["error"] == pytest.approx(o["error"], rel=2e-3)
+            continue
+        n_exact += 1
+        # the 1-DoF loop runs in float (inc = -b / H): one ulp in H or b moves the scale by ~1e-7 per iteration
+        assert g["scale"] == pytest.approx(o["scale"], rel=2e-5) and g["error"] == pytest.approx(o["error"], rel=5e-5), (s0, g, o)
+    assert n_exact >= len(starts) - 2
+    best = min((g for g in outs[0] if g["error"] > 0), key=lambda g: g["error"])
+    assert abs(best["scale"] - 1.0) < 0.03
+    hg.close(); ho.close()

@@ -460,6 +460,16 @@ int sosba_pixel_selector_set(sosba_t *h, const uint8_t *random_pattern, int32_t 
 int sosba_pixel_select(sosba_t *h, int32_t slot, float density, int32_t recursions_left, float th_factor, int32_t cap, int32_t *n_selected,
                        int32_t *u, int32_t *v, float *type, float *map_out, int32_t *current_potential);
 
+/* CoarseDistanceMap::makeDistanceMap + growDistBFS (src/FullSystem/CoarseTracker.cpp:789-916): the active points of the other
+ * keyframes are projected into level 1 of the newest keyframe (KRKi = K[1] R Ki[0], Kt = K[1] t per host frame, the caller's
+ * FullSystem.cpp:417-424 expressions), those pixels get distance 0 and a breadth-first flood with alternating 8- / 4-neighbour
+ * steps (k = 1 .. 39; sources on the image border do not spread) fills fwdWarpedIDDistFinal; unreached pixels keep 1000.
+ *   host [n] index into KRKi / Kt;  u, v, idepth [n]: PointHessian::u, v, idepth_scaled;  dist_out [w1*h1] (level-1 size).
+ * The sequential part of activatePointsMT (addIntoDistFinal after every accepted candidate, FullSystem.cpp:471-476) continues
+ * on the caller's copy of the map. */
+int sosba_distance_map(sosba_t *h, int32_t nhosts, const float *KRKi /*[nhosts*9]*/, const float *Kt /*[nhosts*3]*/, int32_t n, const int32_t *host,
+                       const float *u, const float *v, const float *idepth, float *dist_out);
+
 /* ---- next row: loop-closure direct alignment -----------------------------------------
  * PoseEstimator (src/LoopClosure/PoseEstimator.cpp): the LM loop of estimate() (:286-470) stays on the host and calls
  * these two per iteration.  K per level comes from sosba_tracker_make_k (PoseEstimator::makeK :53-73 uses the same

@@ -337,6 +337,13 @@ ORC_API int orc_scale_optimize(orc_handle *h, int32_t stereo_slot, int32_t coars
   for (int i = 0; i < n_hyp; i++) scale_optimize(o, stereo_slot, coarsest, hyps + i);
   return SOSBA_OK;
 }
+ORC_API int orc_distance_map(orc_handle *h, int32_t nhosts, const float *KRKi, const float *Kt, int32_t n, const int32_t *host, const float *u, const float *v,
+                             const float *idepth, float *dist_out) {
+  if (h->o.levels < 2 || nhosts < 0 || n < 0 || !dist_out || (n > 0 && (!KRKi || !Kt || !host || !u || !v || !idepth))) return SOSBA_E_ARG;
+  for (int i = 0; i < n; i++) if (host[i] < 0 || host[i] >= nhosts) return SOSBA_E_ARG;
+  distance_map(h->o, nhosts, KRKi, Kt, n, host, u, v, idepth, dist_out);
+  return SOSBA_OK;
+}
 ORC_API int orc_scale_set_stereo(orc_handle *h, const double T10[12], const float K1[4]) {
   Oracle &o = h->o;
   o.tfmF0ToF1 = SE3::from_rowmajor34(T10);

@@ -76,5 +76,7 @@ void tracker_makeCoarseDepth(Oracle &o, int ref_slot, int n, const float *center
 void tracker_scaleCoarseDepth(Oracle &o, float scale);
 bool tracker_track(Oracle &o, int new_slot, float ref_ab_exposure, float new_ab_exposure, const double ref_aff_g2l[2], int coarsestLvl, sosba_track_hypothesis *hy);
 void scale_optimize(Oracle &o, int stereo_slot, int coarsestLvl, sosba_scale_hypothesis *hy);
+void distance_map(Oracle &o, int nhosts, const float *KRKi, const float *Kt, int n, const int32_t *host, const float *u, const float *v, const float *idepth,
+                  float *dist);
 
 }  // namespace orc

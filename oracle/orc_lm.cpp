@@ -291,4 +291,37 @@ void scale_optimize(Oracle &o, int stereo_slot, int coarsestLvl, sosba_scale_hyp
   hy->error = (float)hy->last_residuals[0];
 }
 
+
+// ---- CoarseDistanceMap::makeDistanceMap + growDistBFS (CoarseTracker.cpp:789-916) --------------------------------------
+void distance_map(Oracle &o, int nhosts, const float *KRKi, const float *Kt, int n, const int32_t *host, const float *u, const float *v,
+                  const float *idepth, float *dist) {
+  const int w1 = o.wl[1], h1 = o.hl[1], wh1 = w1 * h1;
+  for (int i = 0; i < wh1; i++) dist[i] = 1000;
+  std::vector<int> l1x, l1y, l2x, l2y;
+  for (int i = 0; i < n; i++) {   // :801-821
+    const float *M = KRKi + 9 * host[i], *t = Kt + 3 * host[i];
+    const float p0 = ((M[0] * u[i] + M[1] * v[i]) + M[2] * 1) + t[0] * idepth[i];
+    const float p1 = ((M[3] * u[i] + M[4] * v[i]) + M[5] * 1) + t[1] * idepth[i];
+    const float p2 = ((M[6] * u[i] + M[7] * v[i]) + M[8] * 1) + t[2] * idepth[i];
+    const int uu = p0 / p2 + 0.5f, vv = p1 / p2 + 0.5f;
+    if (!(uu > 0 && vv > 0 && uu < w1 && vv < h1)) continue;
+    dist[uu + w1 * vv] = 0;
+    l1x.push_back(uu); l1y.push_back(vv);
+  }
+  for (int k = 1; k < 40; k++) {   // growDistBFS :830-916
+    std::swap(l1x, l2x); std::swap(l1y, l2y);
+    l1x.clear(); l1y.clear();
+    const int nn = (k % 2 == 0) ? 4 : 8;
+    const int dx[8] = {1, -1, 0, 0, 1, -1, -1, 1}, dy[8] = {0, 0, 1, -1, 1, 1, -1, -1};
+    for (size_t i = 0; i < l2x.size(); i++) {
+      const int x = l2x[i], y = l2y[i];
+      if (x == 0 || y == 0 || x == w1 - 1 || y == h1 - 1) continue;
+      for (int q = 0; q < nn; q++) {
+        const int idx = (x + dx[q]) + (y + dy[q]) * w1;
+        if (dist[idx] > k) { dist[idx] = k; l1x.push_back(x + dx[q]); l1y.push_back(y + dy[q]); }
+      }
+    }
+  }
+}
+
 }  // namespace orc

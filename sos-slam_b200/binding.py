@@ -444,6 +444,15 @@ class Handle:
         self._ck(self.lib.f("tracker_get_ref")(self.h, C.c_int32(lvl), C.byref(n), *[_p(x, f32p) for x in a]), "tracker_get_ref")
         return tuple(a)
 
+    def distance_map(self, KRKi, Kt, host, u, v, idepth):
+        """CoarseDistanceMap::makeDistanceMap -> (h1, w1) float32 map"""
+        KRKi, Kt, host, u, v, idepth = _f32(KRKi).reshape(-1, 9), _f32(Kt).reshape(-1, 3), _i32(host), _f32(u), _f32(v), _f32(idepth)
+        w1, h1 = self.cfg.w >> 1, self.cfg.h >> 1
+        out = np.zeros((h1, w1), np.float32)
+        self._ck(self.lib.f("distance_map")(self.h, C.c_int32(KRKi.shape[0]), _p(KRKi, f32p), _p(Kt, f32p), C.c_int32(host.size), _p(host, i32p), _p(u, f32p),
+                                            _p(v, f32p), _p(idepth, f32p), _p(out, f32p)), "distance_map")
+        return out
+
     def tracker_scale_coarse_depth(self, scale):
         self._ck(self.lib.f("tracker_scale_coarse_depth")(self.h, C.c_float(scale)), "tracker_scale_coarse_depth")
 

@@ -8,18 +8,12 @@
 #pragma once
 #include "kernels.h"
 
-// `aggregate`: the pass over the top byte, where most energies of a warp share a bin (one atomic per distinct bin); the
-// lower bytes are spread over the bins, where match.any would loop once per distinct value: plain shared atomics there
-__device__ __forceinline__ void energy_th_hist_add(unsigned *hist, unsigned bin, bool valid, bool aggregate) {
-  if (!aggregate) { if (valid) atomicAdd(&hist[bin], 1u); return; }
-  const unsigned act = __ballot_sync(0xffffffffu, valid);   // called by whole warps
-  if (!valid) return;
-  const unsigned peers = __match_any_sync(act, bin);
-  if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
-}
-
+// One 256-bin histogram per warp (shared-memory atomics never cross warps; inside a warp the hardware serialises lanes that hit the
+// same bin), summed into hist[] by the caller.  Up to ENERGY_TH_WARPS warps take part; further warps share the last copy.
+constexpr int ENERGY_TH_WARPS = 8;
 __device__ inline void energy_th_body(const ThArgs &a, unsigned *cache = nullptr, int cache_n = 0) {
   __shared__ unsigned hist[256];
+  __shared__ unsigned whist[ENERGY_TH_WARPS][256];
   __shared__ unsigned s_prefix, s_k;
   __shared__ int s_off[17];   // prefix sums of the segment lengths
   if (threadIdx.x == 0) {
@@ -58,8 +52,9 @@ __device__ inline void energy_th_body(const ThArgs &a, unsigned *cache = nullptr
     }
   }
   if (threadIdx.x == 0) { s_prefix = 0; s_k = (unsigned)(int)(a.thN * n); }
+  unsigned *myhist = whist[min((int)(threadIdx.x >> 5), ENERGY_TH_WARPS - 1)];
   for (int pass = 3; pass >= 0; pass--) {
-    for (int i = threadIdx.x; i < 256; i += nt) hist[i] = 0;
+    for (int i = threadIdx.x; i < ENERGY_TH_WARPS * 256; i += nt) (&whist[0][0])[i] = 0;
     __syncthreads();
     const unsigned prefix = s_prefix, shift = 8 * pass;
     const unsigned himask = pass == 3 ? 0u : (0xFFFFFFFFu << (shift + 8));
@@ -68,14 +63,21 @@ __device__ inline void energy_th_body(const ThArgs &a, unsigned *cache = nullptr
       for (int q = 0; q < KEEP; q++) {
         const int i = threadIdx.x + q * nt;
         const unsigned x = mine[q];
-        energy_th_hist_add(hist, (x >> shift) & 255u, i < n && (x & himask) == prefix, pass == 3);
+        if (i < n && (x & himask) == prefix) atomicAdd(&myhist[(x >> shift) & 255u], 1u);
       }
     } else {
       for (int i0 = 0; i0 < n; i0 += nt) {
         const int i = i0 + threadIdx.x;
         const unsigned x = i < n ? (in_smem ? cache[i] : elem(i)) : 0u;
-        energy_th_hist_add(hist, (x >> shift) & 255u, i < n && (x & himask) == prefix, pass == 3);
+        if (i < n && (x & himask) == prefix) atomicAdd(&myhist[(x >> shift) & 255u], 1u);
       }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += nt) {
+      unsigned s = 0;
+#pragma unroll
+      for (int w = 0; w < ENERGY_TH_WARPS; w++) s += whist[w][i];
+      hist[i] = s;
     }
     __syncthreads();
     if (threadIdx.x < 32) {  // warp 0: find the bin holding rank s_k (8 bins per lane, inclusive scan over lanes)

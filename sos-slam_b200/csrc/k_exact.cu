@@ -521,10 +521,10 @@ __global__ void __launch_bounds__(256) k_prep_records(LinArgs a, int mode, const
 
 // ------------------------------------------------------------------------------------------------
 // setNewFrameEnergyTH: energy_th.cuh
-__global__ void __launch_bounds__(1024) k_energy_th(ThArgs a, const int *gate) {
-  __shared__ unsigned s_cache[10240];   // lists beyond 8 energies per thread (point shards of many ranks) are staged here
+__global__ void __launch_bounds__(1024) k_energy_th(ThArgs a, const int *gate, int cache_words) {
+  extern __shared__ unsigned s_cache[];   // lists beyond 8 energies per thread (point shards of many ranks) are staged here
   if (gate && *gate) return;
-  energy_th_body(a, s_cache, 10240);
+  energy_th_body(a, s_cache, cache_words);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -689,7 +689,7 @@ void launch_linearize(sosba *h, const LinArgs &a) {
 }
 // linearizeAll(false) + setNewFrameEnergyTH + applyRes(true) in one launch (the loop body of FullSystem::optimize)
 void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j, bool th_inline) {
-  if (a.R == 0) { if (th_inline) { k_energy_th<<<1, 256, 0, h->stream>>>(a.th, a.gate); h->launches++; } return; }
+  if (a.R == 0) { if (th_inline) { k_energy_th<<<1, 256, 0, h->stream>>>(a.th, a.gate, 0); h->launches++; } return; }
   const int blocks = (a.R * 8 + 255) / 256;
   if (write_j) {
     if (th_inline) launch_pdl(k_linearize<true, true, true>, blocks, 256, 0, h->stream, a);
@@ -721,7 +721,10 @@ void launch_prep_records(sosba *h, const LinArgs &a, int mode, const int *d_list
   h->launches++;
 }
 void launch_energy_th(sosba *h, const ThArgs &a, const int *gate) {
-  k_energy_th<<<1, 1024, 0, h->stream>>>(a, gate);
+  // a single rank's list fits the registers (8 per thread); the gathered list of many point shards is staged in shared memory
+  const int words = a.nseg > 1 ? 36 * 1024 : 0;
+  if (words) cudaFuncSetAttribute(k_energy_th, cudaFuncAttributeMaxDynamicSharedMemorySize, words * 4);   // per device: set on every launch
+  k_energy_th<<<1, 1024, (size_t)words * 4, h->stream>>>(a, gate, words);
   h->launches++;
 }
 void launch_track_res(sosba *h, const TrackResArgs &a) {

@@ -135,6 +135,63 @@ __global__ void k_cd_scale(int n, float *idepth, float scale) {
   if (k < n) idepth[k] /= scale;
 }
 
+// ---- CoarseDistanceMap::makeDistanceMap + growDistBFS (CoarseTracker.cpp:789-916) -----------------------------------------------
+// The reference floods the level-1 map breadth first from the projected points with two explicit queues, 39 steps, alternating
+// 8- and 4-neighbourhoods.  What that computes is a level-synchronous rule with no queue: at step k a pixel still above k takes k
+// if one of its neighbours holds k - 1 and is not a border pixel (border pixels never spread, :836-838).  A step moves at most one
+// pixel per axis, so a tile plus a 39-pixel halo is self-contained: ONE launch, every block floods its tile in shared memory
+// (bytes, 255 = unreached), in place — a pixel set to k in this step is not k - 1, so it cannot feed another pixel of the same step.
+constexpr int DM_TILE = 64, DM_HALO = 39, DM_SPAN = DM_TILE + 2 * DM_HALO;
+__global__ void k_dm_seed(int n, const int *__restrict__ host, const float *__restrict__ u, const float *__restrict__ v, const float *__restrict__ idepth,
+                          const float *__restrict__ KRKi, const float *__restrict__ Kt, int w1, int h1, uint8_t *seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float *M = KRKi + 9 * host[i], *t = Kt + 3 * host[i];
+  const float x = u[i], y = v[i], id = idepth[i];
+  const float p0 = ((M[0] * x + M[1] * y) + M[2] * 1) + t[0] * id;
+  const float p1 = ((M[3] * x + M[4] * y) + M[5] * 1) + t[1] * id;
+  const float p2 = ((M[6] * x + M[7] * y) + M[8] * 1) + t[2] * id;
+  const float fu = p0 / p2 + 0.5f, fv = p1 / p2 + 0.5f;
+  if (!(fabsf(fu) < 1e9f) || !(fabsf(fv) < 1e9f)) return;   // (the reference's int conversion of such a value is undefined)
+  const int uu = (int)fu, vv = (int)fv;
+  if (!(uu > 0 && vv > 0 && uu < w1 && vv < h1)) return;
+  seed[uu + w1 * vv] = 1;
+}
+__global__ void __launch_bounds__(1024) k_dm_flood(int w1, int h1, const uint8_t *__restrict__ seed, float *__restrict__ dist) {
+  __shared__ uint8_t s[DM_SPAN * DM_SPAN];
+  const int x0 = blockIdx.x * DM_TILE - DM_HALO, y0 = blockIdx.y * DM_TILE - DM_HALO;
+  for (int e = threadIdx.x; e < DM_SPAN * DM_SPAN; e += blockDim.x) {
+    const int x = x0 + e % DM_SPAN, y = y0 + e / DM_SPAN;
+    s[e] = (x >= 0 && y >= 0 && x < w1 && y < h1 && seed[x + w1 * y]) ? 0 : 255;
+  }
+  __syncthreads();
+  for (int k = 1; k < 40; k++) {
+    for (int e = threadIdx.x; e < DM_SPAN * DM_SPAN; e += blockDim.x) {
+      if (s[e] <= k) continue;
+      const int lx = e % DM_SPAN, ly = e / DM_SPAN, x = x0 + lx, y = y0 + ly;
+      if (x < 0 || y < 0 || x >= w1 || y >= h1) continue;
+      bool hit = false;
+      const int nn = (k & 1) ? 8 : 4;
+      const int dx[8] = {1, -1, 0, 0, 1, -1, -1, 1}, dy[8] = {0, 0, 1, -1, 1, 1, -1, -1};
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        if (q >= nn) break;
+        const int qx = lx - dx[q], qy = ly - dy[q];           // the neighbour that would have spread to this pixel
+        if (qx < 0 || qy < 0 || qx >= DM_SPAN || qy >= DM_SPAN) continue;
+        const int gx = x0 + qx, gy = y0 + qy;
+        if (gx <= 0 || gy <= 0 || gx >= w1 - 1 || gy >= h1 - 1) continue;   // outside, or a border pixel: does not spread
+        if (s[qy * DM_SPAN + qx] == k - 1) hit = true;
+      }
+      if (hit) s[e] = (uint8_t)k;
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < DM_TILE * DM_TILE; e += blockDim.x) {
+    const int lx = DM_HALO + e % DM_TILE, ly = DM_HALO + e / DM_TILE, x = x0 + lx, y = y0 + ly;
+    if (x < w1 && y < h1) { const uint8_t v = s[ly * DM_SPAN + lx]; dist[x + w1 * y] = v == 255 ? 1000.f : (float)v; }
+  }
+}
+
 // ---- the per-iteration pass --------------------------------------------------------------------------------------
 struct LmLevel {
   int w, h, n;
@@ -876,4 +933,41 @@ API int sosba_scale_optimize(sosba_t *h, int32_t stereo_slot, int32_t coarsest_l
   if (rc) return rc;
   for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) a.R10[3 * i + j] = (float)h->t_T10[4 * i + j]; a.t10[i] = (float)h->t_T10[4 * i + 3]; }
   return lm_run(h, true, a, hyps, sizeof(sosba_scale_hypothesis) * (size_t)n_hyp, n_hyp);
+}
+
+API int sosba_distance_map(sosba_t *h, int32_t nhosts, const float *KRKi, const float *Kt, int32_t n, const int32_t *host, const float *u, const float *v,
+                           const float *idepth, float *dist_out) {
+  LM_CHECK_H(h);
+  if (h->levels < 2 || nhosts < 0 || n < 0 || !dist_out || (n > 0 && (!KRKi || !Kt || !host || !u || !v || !idepth))) { sosba_set_error("distance_map: bad arguments"); return SOSBA_E_ARG; }
+  for (int i = 0; i < n; i++) if (host[i] < 0 || host[i] >= nhosts) { sosba_set_error("distance_map: host %d of point %d", host[i], i); return SOSBA_E_ARG; }
+  const int w1 = h->wl[1], h1 = h->hl[1], N = w1 * h1;
+  const size_t in_floats = 4 * (size_t)n + 12 * (size_t)nhosts;
+  if (in_floats * 4 > h->h_pinned_bytes || (size_t)N * 4 > h->h_pinned_bytes) { sosba_set_error("distance_map: %d points exceed the staging buffer", n); return SOSBA_E_ARG; }
+  if (in_floats + N > h->dm_cap) {
+    float *p = nullptr;
+    int rc = lm_alloc(h, &p, (in_floats + N) * 2 + (size_t)N);
+    if (rc) return rc;
+    h->dm_buf = p; h->dm_cap = (in_floats + N) * 2;
+  }
+  cudaStream_t st = h->stream;
+  SOSBA_CUDA(cudaStreamSynchronize(st));
+  float *pin = h->h_pinned;
+  memcpy(pin, host, 4 * (size_t)n); memcpy(pin + n, u, 4 * (size_t)n); memcpy(pin + 2 * (size_t)n, v, 4 * (size_t)n); memcpy(pin + 3 * (size_t)n, idepth, 4 * (size_t)n);
+  memcpy(pin + 4 * (size_t)n, KRKi, 36 * (size_t)nhosts); memcpy(pin + 4 * (size_t)n + 9 * (size_t)nhosts, Kt, 12 * (size_t)nhosts);
+  float *d_in = h->dm_buf, *d_dist = h->dm_buf + in_floats;
+  uint8_t *d_seed = (uint8_t *)(d_dist + N);
+  if (in_floats) SOSBA_CUDA(cudaMemcpyAsync(d_in, pin, in_floats * 4, cudaMemcpyHostToDevice, st));
+  cudaMemsetAsync(d_seed, 0, N, st);
+  if (n > 0) {
+    k_dm_seed<<<(n + 255) / 256, 256, 0, st>>>(n, (const int *)d_in, d_in + n, d_in + 2 * (size_t)n, d_in + 3 * (size_t)n, d_in + 4 * (size_t)n,
+                                              d_in + 4 * (size_t)n + 9 * (size_t)nhosts, w1, h1, d_seed);
+    h->launches++;
+  }
+  k_dm_flood<<<dim3((w1 + DM_TILE - 1) / DM_TILE, (h1 + DM_TILE - 1) / DM_TILE), 1024, 0, st>>>(w1, h1, d_seed, d_dist);
+  h->launches++;
+  SOSBA_CUDA(cudaGetLastError());
+  SOSBA_CUDA(cudaMemcpyAsync(pin, d_dist, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+  SOSBA_CUDA(cudaStreamSynchronize(st));
+  memcpy(dist_out, pin, (size_t)N * 4);
+  return SOSBA_OK;
 }

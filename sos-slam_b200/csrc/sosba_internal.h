@@ -148,6 +148,8 @@ struct sosba {
   size_t lm_hyp_cap = 0;
   float *lm_terms = nullptr;      // per hypothesis: energy terms of the accepted state and of the candidate
   size_t lm_terms_cap = 0;
+  float *dm_buf = nullptr;        // CoarseDistanceMap: staged inputs | level-1 map | seed bytes
+  size_t dm_cap = 0;
   std::vector<void *> lm_allocs;
 
   // composed GN loop (host mirror of FullSystem state)

@@ -70,3 +70,28 @@ def stereo_frame(sc, seed, baseline=0.08):
     T10 = synth.se3_exp([-baseline, 0.001, 0.0015, 0.001, -0.002, 0.0005])
     c2w1 = sc.camToWorld_true[sc.nf - 1] @ np.linalg.inv(T10)
     return T10[:3, :4], synth.render_view(seed, sc.w, sc.h, sc.K, c2w1)
+
+
+def distance_map_case(sc, seed=0):
+    """inputs of CoarseDistanceMap::makeDistanceMap for the newest keyframe: every active point of the other keyframes with
+    KRKi = K[1] R Ki[0], Kt = K[1] t of its host (FullSystem.cpp:417-424), plus a few points that project outside / onto the border."""
+    nf = sc.nf
+    fx, fy, cx, cy = [np.float32(x) for x in sc.K]
+    K1 = np.array([[fx * np.float32(0.5), 0, (cx + np.float32(0.5)) / 2 - np.float32(0.5)], [0, fy * np.float32(0.5), (cy + np.float32(0.5)) / 2 - np.float32(0.5)], [0, 0, 1]], np.float32)
+    Ki0 = np.array([[1 / fx, 0, -cx / fx], [0, 1 / fy, -cy / fy], [0, 0, 1]], np.float32)
+    KRKi, Kt = [], []
+    for hst in range(nf):
+        T = np.linalg.inv(sc.camToWorld_true[nf - 1]) @ sc.camToWorld_true[hst]
+        KRKi.append((K1 @ T[:3, :3].astype(np.float32) @ Ki0).astype(np.float32).ravel())
+        Kt.append((K1 @ T[:3, 3].astype(np.float32)).astype(np.float32))
+    m = sc.pt_host != nf - 1
+    host, u, v, idp = sc.pt_host[m].astype(np.int32), sc.pt_u[m].copy(), sc.pt_v[m].copy(), sc.pt_idepth[m].copy()
+    rng = np.random.default_rng(seed)
+    extra = 12
+    host = np.concatenate([host, np.zeros(extra, np.int32)])
+    u = np.concatenate([u, rng.uniform(-200, sc.w + 200, extra).astype(np.float32)])
+    v = np.concatenate([v, rng.uniform(-200, sc.h + 200, extra).astype(np.float32)])
+    idp = np.concatenate([idp, np.full(extra, 0.5, np.float32)])
+    # a corner region without points far from everything keeps 1000; a point exactly on the border row does not spread
+    u[-1], v[-1], idp[-1] = 2.0 * 7 + 0.6, 0.4, 0.0
+    return np.array(KRKi), np.array(Kt), host, u, v, idp

@@ -1209,3 +1209,33 @@ def optimize_scale_ref(dI_stereo_levels, K0, K1, pcs, T10, scale0, coarsest, cut
         else:
             lvl -= 1
     return dict(scale=float(s_cur), error=float(last[0]), last_residuals=last, passes=passes)
+
+
+def distance_map_ref(w1, h1, KRKi, Kt, host, u, v, idepth):
+    """CoarseDistanceMap::makeDistanceMap + growDistBFS (CoarseTracker.cpp:789-916) as a level-synchronous PULL: at step k every
+    pixel still above k takes k if one of its (8 for odd k, 4 for even k) neighbours holds k - 1 and is not a border pixel."""
+    KRKi = np.asarray(KRKi, F).reshape(-1, 9); Kt = np.asarray(Kt, F).reshape(-1, 3)
+    M, t = KRKi[host], Kt[host]
+    u, v, idp = np.asarray(u, F), np.asarray(v, F), np.asarray(idepth, F)
+    p = [((M[:, 3 * k] * u + M[:, 3 * k + 1] * v) + M[:, 3 * k + 2] * F(1)) + t[:, k] * idp for k in range(3)]
+    with np.errstate(all="ignore"):
+        fu, fv = p[0] / p[2] + F(0.5), p[1] / p[2] + F(0.5)
+    okf = np.isfinite(fu) & np.isfinite(fv) & (np.abs(fu) < 1e9) & (np.abs(fv) < 1e9)
+    uu = np.where(okf, fu, -1).astype(np.int64); vv = np.where(okf, fv, -1).astype(np.int64)      # C cast: truncation toward zero
+    ok = okf & (uu > 0) & (vv > 0) & (uu < w1) & (vv < h1)
+    d = np.full((h1, w1), 1000, np.float32)
+    d[vv[ok], uu[ok]] = 0
+    border = np.zeros((h1, w1), bool)
+    border[0, :] = border[-1, :] = border[:, 0] = border[:, -1] = True
+    for k in range(1, 40):
+        src = (d == k - 1) & ~border
+        nb = [(0, 1), (0, -1), (1, 0), (-1, 0)] + ([(1, 1), (1, -1), (-1, -1), (-1, 1)] if k % 2 else [])
+        reach = np.zeros_like(src)
+        for dy, dx in nb:
+            sh = np.zeros_like(src)
+            ys, yd = (slice(0, h1 - dy), slice(dy, h1)) if dy >= 0 else (slice(-dy, h1), slice(0, h1 + dy))
+            xs, xd = (slice(0, w1 - dx), slice(dx, w1)) if dx >= 0 else (slice(-dx, w1), slice(0, w1 + dx))
+            sh[yd, xd] = src[ys, xs]
+            reach |= sh
+        d[reach & (d > k)] = k
+    return d

@@ -895,3 +895,21 @@ def test_optimize_scale_vs_numpy(orc):
         assert o["scale"] == pytest.approx(r["scale"], rel=1e-5) and o["error"] == pytest.approx(r["error"], rel=2e-5)
     assert abs(out[1]["scale"] - 1.0) < 0.02 and out[1]["error"] < 8        # the stereo pair was rendered at scale 1
     h.close()
+
+
+def test_distance_map_vs_numpy(orc):
+    """CoarseDistanceMap::makeDistanceMap / growDistBFS (CoarseTracker.cpp:789-916): the queue-based flood of the oracle against
+    a level-synchronous pull formulation — identical maps."""
+    from _track_case import distance_map_case
+    for cfg in (TINY, SMALLC):
+        sc = scene(**cfg)
+        h = open_handle(orc, sc)
+        KRKi, Kt, host, u, v, idp = distance_map_case(sc)
+        d = h.distance_map(KRKi, Kt, host, u, v, idp)
+        ref = np_ref.distance_map_ref(sc.w >> 1, sc.h >> 1, KRKi, Kt, host, u, v, idp)
+        assert np.array_equal(d, ref)
+        assert (d == 0).sum() > 20 and d.max() == 1000 or d.max() <= 39
+        # few points: most of the map stays unreached, the reach of a point is the 39-step octagon
+        d2 = h.distance_map(KRKi, Kt, host[:3], u[:3], v[:3], idp[:3])
+        assert np.array_equal(d2, np_ref.distance_map_ref(sc.w >> 1, sc.h >> 1, KRKi, Kt, host[:3], u[:3], v[:3], idp[:3])) and (d2 == 1000).any()
+        h.close()

@@ -415,7 +415,13 @@ def main():
     frames0 = bytes(ctypes.string_at(ctypes.addressof(kn[0]), ctypes.sizeof(kn[0])))
     calib0 = list(Pn.calib_value)
 
+    # the step's largest input, the newest keyframe's image, sits in pinned host memory (the e2e contract) as a camera driver's
+    # DMA buffer would: the library reads it in place instead of staging a pageable copy
+    img_pin = torch.from_numpy(sc.images[-1].copy()).pin_memory()
+    img_new = img_pin.numpy()
     raw8 = np.clip(np.rint(sc.images[-1]), 0, 255).astype(np.uint8)      # the camera frame as it arrives (8f rank 2 input)
+    raw_pin = torch.from_numpy(raw8.copy()).pin_memory()
+    raw8 = raw_pin.numpy()
 
     def e2e_step(raw=False):
         ctypes.memmove(ctypes.addressof(kn[0]), frames0, len(frames0))
@@ -424,7 +430,7 @@ def main():
         if raw:
             h.frame_make_images_raw(sc.nf - 1, raw8)
         else:
-            h.frame_make_images(sc.nf - 1, sc.images[-1])
+            h.frame_make_images(sc.nf - 1, img_new)
         return h.optimize(Pn, ITERS)
 
     def e2e_loop(raw):

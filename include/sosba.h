@@ -159,7 +159,10 @@ int sosba_frame_make_images_dev(sosba_t *h, int32_t slot, const float *color_dev
 int32_t sosba_pyr_levels(const sosba_t *h);
 
 /* ---- a1: FrameHessian::makeImages (HessianBlocks.cpp:121-176) -------------------------------- */
-/* color: w*h irradiance; B: 256-entry response (CalibHessian::B) or NULL (HCalib==0 branch). */
+/* color: w*h irradiance; B: 256-entry response (CalibHessian::B) or NULL (HCalib==0 branch).
+ * Host buffers of 64 KB and more that live in page-locked memory (cudaHostAlloc / cudaHostRegister) are read by the DMA in place:
+ * keep them unchanged until the next synchronising call (sosba_synchronize, any call that returns results).  Pageable buffers
+ * are copied into the library's own pinned staging ring before the call returns. */
 int sosba_frame_make_images(sosba_t *h, int32_t slot, const float *color, const float *B);
 /* dIp[lvl] as Eigen::Vector3f AoS (w_l*h_l*3) and absSquaredGrad[lvl] (w_l*h_l); either may be NULL.
  * First/last row of dx,dy,absSquaredGrad are uninitialised in the reference; here they are 0. */

@@ -62,6 +62,7 @@ struct HostSide {
   unsigned char *d_raw = nullptr;
   std::vector<int> seen_tmp, tiles_tmp;   // residuals_set scratch
   std::vector<char> big_stage;        // pageable staging for uploads larger than half the pinned ring
+  unsigned char *w_arena = nullptr;   // window tables (win_layout)
   float *p_arena = nullptr;           // uploaded members of the points (carve_points)
   unsigned char *r_arena = nullptr;   // ids / energies / flags of the residuals (carve_residuals)
   float *d_loop = nullptr;      // loop-closure points: x | y | z | colour[level] (3 + levels arrays of loop_n)
@@ -149,6 +150,15 @@ template <class T> static void dfree(sosba *h, T *&p) {
 static int up_bytes(sosba *h, void *dst, const void *src, size_t bytes) {
   if (bytes == 0) return SOSBA_OK;
   HostSide *hs = HS(h);
+  if (bytes >= 64 * 1024) {   // a large source in page-locked memory (cudaHostAlloc / cudaHostRegister) needs no staging copy:
+                              // the DMA reads it in place; the caller keeps it unchanged until the next synchronising call
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+      SOSBA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+      return SOSBA_OK;
+    }
+    cudaGetLastError();
+  }
   if (!hs->stage || bytes > hs->stage_cap / 2) {   // oversized: plain (synchronising) copy
     SOSBA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
     return SOSBA_OK;
@@ -474,23 +484,40 @@ API int sosba_frame_get_level(sosba_t *h, int32_t slot, int32_t lvl, float *dI3,
 }
 
 // ---- uploads ------------------------------------------------------------------------------------
+// The window tables live in ONE arena so that an upload is one staged copy (doubles first, everything 16-byte aligned):
+//   head (sosba_window_set only):  img0 [nf pointers, padded] | adHost [n64] | adTarget [n64] | adHostF [n64] | adTargetF [n64]
+//   tail (also sosba_window_update): wprior [4 + 24 nf doubles, padded] | precalc [n2*32] | adHTdeltaF [n2*8] | calib [16] | frameEnergyTH [nf, padded]
+struct WinLayout { size_t img0, adHost, adTarget, adHostF, adTargetF, tail, wprior, precalc, adHTdelta, calib, th, total; };
+static WinLayout win_layout(int nf) {
+  const size_t n2 = (size_t)nf * nf, n64 = n2 * 64;
+  auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  WinLayout L;
+  size_t o = 0;
+  L.img0 = o; o += al(sizeof(void *) * nf);
+  L.adHost = o; o += n64 * 8;
+  L.adTarget = o; o += n64 * 8;
+  L.adHostF = o; o += n64 * 4;
+  L.adTargetF = o; o += n64 * 4;
+  L.tail = o;
+  L.wprior = o; o += al(8 * (4 + 24 * (size_t)nf));
+  L.precalc = o; o += n2 * SOSBA_PRECALC_FLOATS * 4;
+  L.adHTdelta = o; o += n2 * 8 * 4;
+  L.calib = o; o += 16 * 4;
+  L.th = o; o += al(4 * (size_t)nf);
+  L.total = o;
+  return L;
+}
+
 static int ensure_window(sosba *h, int nf) {
   if (nf <= h->nf_alloc) return SOSBA_OK;
-  dfree(h, h->d_precalc); dfree(h, h->d_adHostF); dfree(h, h->d_adTargetF); dfree(h, h->d_adHTdeltaF); dfree(h, h->d_frameEnergyTH);
-  dfree(h, h->d_adHost); dfree(h, h->d_adTarget); dfree(h, h->d_calib); dfree(h, h->d_wprior); dfree(h, h->d_img0);
-  dfree(h, h->d_x); dfree(h, h->d_xAd);
   HostSide *hs = HS(h);
+  dfree(h, hs->w_arena);
+  dfree(h, h->d_x); dfree(h, h->d_xAd);
   dfree(h, hs->d_scratch); h->d_accTop = h->d_accSC = h->d_H = nullptr;
   dfree(h, hs->d_HMtmp); dfree(h, hs->d_bMtmp);
   const size_t n2 = (size_t)nf * nf;
   const int D = 4 + 8 * nf;
-  DALLOC(h, h->d_precalc, n2 * SOSBA_PRECALC_FLOATS);
-  DALLOC(h, h->d_adHostF, n2 * 64); DALLOC(h, h->d_adTargetF, n2 * 64); DALLOC(h, h->d_adHTdeltaF, n2 * 8);
-  DALLOC(h, h->d_frameEnergyTH, nf);
-  DALLOC(h, h->d_adHost, n2 * 64); DALLOC(h, h->d_adTarget, n2 * 64);
-  DALLOC(h, h->d_calib, 16);
-  DALLOC(h, h->d_wprior, 4 + 24 * (size_t)nf);
-  DALLOC(h, h->d_img0, nf);
+  DALLOC(h, hs->w_arena, win_layout(nf).total);
   {  // one scratch region zeroed by a single memset per API-level solve: top tables (A | L), Schur Gram, counters (ints),
      // H parts A | L | SC, back-substitution sums [4] ; H part 3 (final system) follows and is never cleared.
      // Inside the Gauss-Newton loop only tables + Gram + counters are cleared (by the fused linearisation): the stitch of
@@ -521,40 +548,51 @@ static int window_apply(sosba *h, const sosba_window *w, bool full) {
   if (nf <= 0 || nf > 16) { sosba_set_error("nf=%d out of range", nf); return SOSBA_E_ARG; }
   if (!full && nf != h->nf) { sosba_set_error("window_update before window_set"); return SOSBA_E_STATE; }
   int rc;
+  HostSide *hs = HS(h);
+  if (full && (rc = ensure_window(h, nf))) return rc;
+  // (the arena may be sized for a larger window: the tables of this one are laid out for ITS nf at the front)
+  const WinLayout L = win_layout(nf);
+  unsigned char *A = hs->w_arena;
+  h->d_img0 = (const float4 **)(A + L.img0);
+  h->d_adHost = (double *)(A + L.adHost); h->d_adTarget = (double *)(A + L.adTarget);
+  h->d_adHostF = (float *)(A + L.adHostF); h->d_adTargetF = (float *)(A + L.adTargetF);
+  h->d_wprior = (double *)(A + L.wprior); h->d_precalc = (float *)(A + L.precalc); h->d_adHTdeltaF = (float *)(A + L.adHTdelta);
+  h->d_calib = (float *)(A + L.calib); h->d_frameEnergyTH = (float *)(A + L.th);
+  const size_t first = full ? 0 : L.tail, bytes = L.total - first;
+  char *blk = nullptr;
+  if ((rc = stage_reserve(h, bytes, &blk))) return rc;
+  char *S = blk - first;   // S + offset = staging address of an arena offset
+  const size_t n2 = (size_t)nf * nf, n64 = n2 * 64;
   if (full) {
-    if ((rc = ensure_window(h, nf))) return rc;
     h->nf = nf;
     h->frame_slot.assign(w->frame_slot, w->frame_slot + nf);
-    std::vector<const float4 *> img(nf);
+    const float4 **img = (const float4 **)(S + L.img0);
     for (int i = 0; i < nf; i++) {
-      const int s = w->frame_slot[i];
-      if (s < 0 || s >= (int)h->slot_img.size()) { sosba_set_error("frame_slot[%d]=%d", i, s); return SOSBA_E_ARG; }
-      img[i] = h->slot_img[s];
+      const int sl = w->frame_slot[i];
+      if (sl < 0 || sl >= (int)h->slot_img.size()) { sosba_set_error("frame_slot[%d]=%d", i, sl); return SOSBA_E_ARG; }
+      img[i] = h->slot_img[sl];
     }
-    if ((rc = up(h, h->d_img0, img.data(), nf))) return rc;
-    const size_t n64 = (size_t)nf * nf * 64;
-    if ((rc = up(h, h->d_adHost, w->adHost, n64))) return rc;
-    if ((rc = up(h, h->d_adTarget, w->adTarget, n64))) return rc;
-    std::vector<float> f(2 * n64);
-    for (size_t i = 0; i < n64; i++) { f[i] = (float)w->adHost[i]; f[n64 + i] = (float)w->adTarget[i]; }
-    if ((rc = up(h, h->d_adHostF, f.data(), n64))) return rc;
-    if ((rc = up(h, h->d_adTargetF, f.data() + n64, n64))) return rc;
+    memcpy(S + L.adHost, w->adHost, n64 * 8);
+    memcpy(S + L.adTarget, w->adTarget, n64 * 8);
+    float *fh = (float *)(S + L.adHostF), *ft = (float *)(S + L.adTargetF);
+    for (size_t i = 0; i < n64; i++) { fh[i] = (float)w->adHost[i]; ft[i] = (float)w->adTarget[i]; }
   }
-  const size_t n2 = (size_t)nf * nf;
-  if ((rc = up(h, h->d_precalc, w->precalc, n2 * SOSBA_PRECALC_FLOATS))) return rc;
-  if ((rc = up(h, h->d_adHTdeltaF, w->adHTdeltaF, n2 * 8))) return rc;
-  if ((rc = up(h, h->d_frameEnergyTH, w->frame_energy_th, nf))) return rc;
+  memcpy(S + L.precalc, w->precalc, n2 * SOSBA_PRECALC_FLOATS * 4);
+  memcpy(S + L.adHTdelta, w->adHTdeltaF, n2 * 8 * 4);
+  memcpy(S + L.th, w->frame_energy_th, 4 * (size_t)nf);
   float *c = h->h_calib;
   for (int i = 0; i < 4; i++) c[i] = w->calib[i];
   c[4] = 1.0f / c[0]; c[5] = 1.0f / c[1];  // CalibHessian::setValue, HessianBlocks.h:495-496
   for (int i = 0; i < 4; i++) c[6 + i] = w->cDeltaF[i];
-  if ((rc = up(h, h->d_calib, c, 10))) return rc;
+  memcpy(S + L.calib, c, 10 * 4);
   h->h_wprior.resize(4 + 24 * (size_t)nf);
   double *wp = h->h_wprior.data();
   if (full) { for (int i = 0; i < 4; i++) wp[i] = w->cPrior[i]; memcpy(wp + 4, w->frame_prior, sizeof(double) * 8 * nf); }
   memcpy(wp + 4 + 8 * nf, w->frame_delta_prior, sizeof(double) * 8 * nf);
   memcpy(wp + 4 + 16 * nf, w->frame_delta, sizeof(double) * 8 * nf);
-  return up(h, h->d_wprior, wp, 4 + 24 * (size_t)nf);
+  memcpy(S + L.wprior, wp, 8 * (4 + 24 * (size_t)nf));
+  SOSBA_CUDA(cudaMemcpyAsync(A + first, blk, bytes, cudaMemcpyHostToDevice, h->stream));
+  return SOSBA_OK;
 }
 API int sosba_window_set(sosba_t *h, const sosba_window *w) { CHECK_H(h); if (!w) return SOSBA_E_ARG; return window_apply(h, w, true); }
 API int sosba_window_update(sosba_t *h, const sosba_window *w) { CHECK_H(h); if (!w) return SOSBA_E_ARG; return window_apply(h, w, false); }

@@ -377,6 +377,28 @@ int sosba_ba_optimize(sosba_t *h, int32_t max_iterations, sosba_optimize_out *ou
 int sosba_ba_iterate(sosba_t *h, int32_t n, int32_t *n_res_linearized);
 int sosba_ba_download(sosba_t *h, sosba_ba_problem *prob);
 
+/* ---- the loop body split around a caller-side solve (EnergyFunctional::solveSystemF with IMU) ---------------------------------
+ * With setting_enable_imu the reference widens the system between accumulation and solve: expandHbtoFitImu (8 -> 29 states per
+ * frame + the scale), getImuHessian, the marginalisation prior in the widened space, KKT rows of the spline constraints and the
+ * removal of unconstrained states (EnergyFunctional.cpp:1052-1140), then unpacks the step (:1150-1171).  That algebra works on the
+ * FrameHessian spline state and stays with the caller ("IMU spline math host-side"); the two calls below are the
+ * device part of the body on the window made resident by sosba_ba_upload:
+ *   sosba_ba_system  accumulateAF_MT + accumulateLF_MT (priors included, as usePrior does) + accumulateSCF_MT and their stitches
+ *                    (EnergyFunctional.cpp:1040-1047): H_top = HA + HL, b_top = bA + bL, H_sc, b_sc (D x D row-major, D = 4 + 8 nf);
+ *                    all-reduced over point shards.  One synchronisation.
+ *   sosba_ba_step    the rest of the body for the caller's x_dso (D doubles, = lastX): resubstituteF_MT, backupState,
+ *                    doStepFromBackup of points / frames / calibration (stepsize 1), setPrecalcValues, linearizeAll(false), applyRes.
+ *                    One synchronisation. */
+typedef struct sosba_step_out {
+  double energy;               /* linearizeAll(false) after the step */
+  float new_frame_energy_th;
+  int32_t n_in, n_oob, n_outlier;
+  double sum_a, sum_b, sum_t, sum_r;   /* doStepFromBackup: mean squared steps of the frames (FullSystemOptimize.cpp:228-236) */
+  double sum_id, sum_nid, num_id;      /* ... and of the points: sum step^2, sum |idepth_backup|, count (over all ranks) */
+} sosba_step_out;
+int sosba_ba_system(sosba_t *h, double *H_top, double *b_top, double *H_sc, double *b_sc, int32_t *resInA, int32_t *resInL);
+int sosba_ba_step(sosba_t *h, const double *x, sosba_step_out *out);
+
 /* ---- next row: immature points ------------------------------------------------ */
 /* ImmaturePointStatus, ImmaturePoint.h:40-47 */
 enum { SOSBA_IPS_GOOD = 0, SOSBA_IPS_OOB = 1, SOSBA_IPS_OUTLIER = 2, SOSBA_IPS_SKIPPED = 3, SOSBA_IPS_BADCONDITION = 4, SOSBA_IPS_UNINITIALIZED = 5 };

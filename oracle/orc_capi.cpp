@@ -171,7 +171,13 @@ ORC_API int orc_reset_oob(orc_handle *h) {
   }
   return SOSBA_OK;
 }
-ORC_API int orc_linearize_all(orc_handle *h, int32_t fix, sosba_linearize_out *out) { linearizeAll(h->o, fix != 0, out); return SOSBA_OK; }
+ORC_API int orc_linearize_all(orc_handle *h, int32_t fix, sosba_linearize_out *out) {
+  linearizeAll(h->o, fix != 0, out);
+  // setNewFrameEnergyTH writes newFrame->frameEnergyTH on the FrameHessian itself (FullSystemOptimize.cpp:116): keep the frame record
+  // of a resident window (orc_ba_upload) in step, so that the next setPrecalcValues does not bring the old threshold back
+  if (h->ba_loaded && !h->ba.frames.empty() && (int)h->ba.frames.size() == h->o.nf) h->ba.frames.back().frameEnergyTH = h->o.frameEnergyTH[h->o.nf - 1];
+  return SOSBA_OK;
+}
 ORC_API int orc_apply_res(orc_handle *h) {
   Oracle &o = h->o;
   auto fn = [&](int a, int b) { for (int k = a; k < b; k++) applyRes(o.res[o.activeResiduals[k]], true); };
@@ -401,6 +407,32 @@ ORC_API int orc_ba_iterate(orc_handle *h, int32_t n, int32_t *n_res) {
 ORC_API int orc_ba_download(orc_handle *h, sosba_ba_problem *prob) {
   if (!h->ba_loaded) return SOSBA_E_STATE;
   h->ba.store(h->o, prob);
+  return SOSBA_OK;
+}
+
+// the loop body split around a caller-side solve (IMU configurations): see include/sosba.h
+ORC_API int orc_ba_system(orc_handle *h, double *H_top, double *b_top, double *H_sc, double *b_sc, int32_t *resInA, int32_t *resInL) {
+  if (!h->ba_loaded) return SOSBA_E_STATE;
+  Oracle &o = h->o;
+  const int D = CPARS + 8 * o.nf;
+  std::vector<double> HA((size_t)D * D), bA(D), HL((size_t)D * D), bL(D), Hs((size_t)D * D), bs(D);
+  accumulateAF(o, HA.data(), bA.data());
+  accumulateLF(o, HL.data(), bL.data());
+  accumulateSCF(o, Hs.data(), bs.data());
+  for (size_t i = 0; i < (size_t)D * D; i++) { if (H_top) H_top[i] = HL[i] + HA[i]; if (H_sc) H_sc[i] = Hs[i]; }   // EnergyFunctional.cpp:1046-1047
+  for (int i = 0; i < D; i++) { if (b_top) b_top[i] = bL[i] + bA[i]; if (b_sc) b_sc[i] = bs[i]; }
+  if (resInA) *resInA = o.resInA;
+  if (resInL) *resInL = o.resInL;
+  return SOSBA_OK;
+}
+ORC_API int orc_ba_step(orc_handle *h, const double *x, sosba_step_out *out) {
+  if (!h->ba_loaded || !x || !out) return SOSBA_E_STATE;
+  Oracle &o = h->o;
+  sosba_linearize_out lo;
+  double sums[7];
+  h->ba.step_with_x(o, x, &lo, sums);
+  out->energy = lo.energy; out->new_frame_energy_th = lo.new_frame_energy_th; out->n_in = lo.n_in; out->n_oob = lo.n_oob; out->n_outlier = lo.n_outlier;
+  out->sum_a = sums[0]; out->sum_b = sums[1]; out->sum_t = sums[2]; out->sum_r = sums[3]; out->sum_id = sums[4]; out->sum_nid = sums[5]; out->num_id = sums[6];
   return SOSBA_OK;
 }
 

@@ -182,7 +182,7 @@ void BAState::setAdjoints(Oracle &o) {
 }
 
 // FullSystem::doStepFromBackup (FullSystemOptimize.cpp:185-257)
-bool BAState::doStepFromBackup(Oracle &o, float stepfac) {
+bool BAState::doStepFromBackup(Oracle &o, float stepfac, double *sums) {
   double pstepfac[10];
   for (int i = 0; i < 10; i++) pstepfac[i] = stepfac;
   float sumA = 0, sumB = 0, sumT = 0, sumR = 0, sumID = 0, numID = 0, sumNID = 0;
@@ -209,6 +209,7 @@ bool BAState::doStepFromBackup(Oracle &o, float stepfac) {
     ph.idepth_zero = nid; ph.idepth_zero_scaled = SCALE_IDEPTH * nid;
   }
   sumA /= nf; sumB /= nf; sumR /= nf; sumT /= nf;
+  if (sums) { sums[0] = sumA; sums[1] = sumB; sums[2] = sumT; sums[3] = sumR; sums[4] = sumID; sums[5] = sumNID; sums[6] = numID; }
   sumID /= numID; sumNID /= numID;
   setPrecalcValues(o);
   const float th = o.cfg.th_opt_iterations;
@@ -234,6 +235,20 @@ bool BAState::iterate(Oracle &o, const double *HM, const double *bM, sosba_linea
   frames.back().frameEnergyTH = o.frameEnergyTH[nf - 1];
   for (int id : o.activeResiduals) applyRes(o.res[id], true);
   return canbreak;
+}
+
+// the same body without the solve: the caller provides x (EnergyFunctional::solveSystemF with IMU ends in lastX = x_dso and
+// resubstituteF_MT, EnergyFunctional.cpp:1150-1182)
+void BAState::step_with_x(Oracle &o, const double *x, sosba_linearize_out *lo, double sums[7]) {
+  const int nf = (int)frames.size();
+  backupState(o);
+  resubstituteF(o, x);
+  for (int i = 0; i < 4; i++) calib.step[i] = -x[i];
+  for (int h = 0; h < nf; h++) { for (int i = 0; i < 8; i++) frames[h].step[i] = -x[CPARS + 8 * h + i]; frames[h].step[8] = frames[h].step[9] = 0; }
+  doStepFromBackup(o, 1.0f, sums);
+  linearizeAll(o, false, lo);
+  frames.back().frameEnergyTH = o.frameEnergyTH[nf - 1];
+  for (int id : o.activeResiduals) applyRes(o.res[id], true);
 }
 
 // FullSystem::optimize (FullSystemOptimize.cpp:305-489), IMU off

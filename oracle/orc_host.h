@@ -37,7 +37,8 @@ struct BAState {
   void store(Oracle &o, sosba_ba_problem *prob) const;
   void setPrecalcValues(Oracle &o);
   void setAdjoints(Oracle &o);
-  bool doStepFromBackup(Oracle &o, float stepfac);
+  bool doStepFromBackup(Oracle &o, float stepfac, double *sums = nullptr);
+  void step_with_x(Oracle &o, const double *x, sosba_linearize_out *lo, double sums[7]);
   void backupState(Oracle &o);
   bool iterate(Oracle &o, const double *HM, const double *bM, sosba_linearize_out *lo);
   void optimize(Oracle &o, const double *HM, const double *bM, int mnumOptIts, sosba_optimize_out *out);

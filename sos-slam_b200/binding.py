@@ -115,6 +115,12 @@ class ScaleHypothesis(C.Structure):
                 ("pass_accept", C.c_uint64 * TRACK_MAX_PASSES), ("pass_tie", C.c_uint64 * TRACK_MAX_PASSES), ("reserved0", C.c_int32)]
 
 
+class StepOut(C.Structure):
+    _fields_ = [("energy", C.c_double), ("new_frame_energy_th", C.c_float), ("n_in", C.c_int32), ("n_oob", C.c_int32), ("n_outlier", C.c_int32),
+                ("sum_a", C.c_double), ("sum_b", C.c_double), ("sum_t", C.c_double), ("sum_r", C.c_double), ("sum_id", C.c_double),
+                ("sum_nid", C.c_double), ("num_id", C.c_double)]
+
+
 class OptimizeOut(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("res_in_a", C.c_int32), ("energy_initial", C.c_double),
                 ("energy_final", C.c_double), ("rmse", C.c_float), ("n_removed", C.c_int32),
@@ -738,6 +744,22 @@ class Handle:
 
     def ba_upload(self, P):
         self._ck(self.lib.f("ba_upload")(self.h, C.byref(P)), "ba_upload")
+        self.nf_ba = int(P.nf)
+
+    def ba_system(self):
+        """-> dict(H_top, b_top, H_sc, b_sc, resInA, resInL): the device part of solveSystemF before a caller-side solve"""
+        D = 4 + 8 * self.nf_ba
+        o = {"H_top": np.zeros((D, D)), "b_top": np.zeros(D), "H_sc": np.zeros((D, D)), "b_sc": np.zeros(D)}
+        a, l = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.f("ba_system")(self.h, _p(o["H_top"], f64p), _p(o["b_top"], f64p), _p(o["H_sc"], f64p), _p(o["b_sc"], f64p), C.byref(a), C.byref(l)), "ba_system")
+        o["resInA"], o["resInL"] = a.value, l.value
+        return o
+
+    def ba_step(self, x) -> dict:
+        x = _f64(x)
+        out = StepOut()
+        self._ck(self.lib.f("ba_step")(self.h, _p(x, f64p), C.byref(out)), "ba_step")
+        return {n: getattr(out, n) for n, _ in StepOut._fields_}
 
     def ba_iterate(self, n: int) -> int:
         nres = C.c_int32(0)

@@ -181,10 +181,11 @@ void sosba_xchg_args(sosba *h, StitchXchgArgs *a, int with_newE) {
 }
 
 // the linearisation sums of an API-level linearizeAll: energy (1 double), state histogram + removals (4 ints), energies
-int sosba_allreduce_lin(sosba *h, int with_stats) {
+int sosba_allreduce_lin(sosba *h, int with_stats, double *extra, int n_extra) {
   if (!h->comm || h->world <= 1) return SOSBA_OK;
   ncclComm_t c = (ncclComm_t)h->comm;
   NCCLCHK(g_nccl.GroupStart());
+  if (extra && n_extra > 0) NCCLCHK(g_nccl.AllReduce(extra, extra, n_extra, ncclFloat64, ncclSum, c, h->stream));
   if (with_stats) {
     NCCLCHK(g_nccl.AllReduce(h->d_stats, h->d_stats, 1, ncclFloat64, ncclSum, c, h->stream));
     NCCLCHK(g_nccl.AllReduce(h->d_counts, h->d_counts, 4, ncclInt32, ncclSum, c, h->stream));

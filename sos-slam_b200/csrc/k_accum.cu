@@ -615,6 +615,18 @@ __global__ void __launch_bounds__(256) k_finalize_top(int nf, double *__restrict
   }
 }
 
+// the priors the linearised pass carries (AccumulatedTopHessian.cpp:292-300) onto an already symmetric H, b. One CTA.
+__global__ void __launch_bounds__(128) k_add_priors(int nf, double *__restrict__ H, double *__restrict__ b, const double *__restrict__ wprior,
+                                                    const float *__restrict__ cDeltaF) {
+  const int D = 4 + 8 * nf;
+  const double *cPrior = wprior, *fprior = wprior + 4, *fdp = wprior + 4 + 8 * nf;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const double pr = i < 4 ? cPrior[i] : fprior[i - 4], dp = i < 4 ? (double)cDeltaF[i] : fdp[i - 4];
+    H[(size_t)i * D + i] += pr;
+    b[i] += pr * dp;
+  }
+}
+
 // accSC (upper tiles of the (D+1)^2 Gram matrix) -> full symmetric Hsc and bsc. One CTA.
 __global__ void __launch_bounds__(256) k_finalize_sc(const double *__restrict__ accSC, int D, double *__restrict__ H, double *__restrict__ b) {
   const int DP = D + 1;
@@ -691,6 +703,11 @@ void launch_stitch_top(sosba *h, const double *accTop, const double *adHost, con
   k_stitch_top<<<nf * nf, 64, 0, h->stream>>>(accTop, adHost, adTarget, nf, H, b);
   k_finalize_top<<<1, 256, 0, h->stream>>>(nf, H, b, usePrior, wprior, cDeltaF);
   h->launches += 2;
+}
+
+void launch_add_priors(sosba *h, int nf, double *H, double *b, const double *wprior, const float *cDeltaF) {
+  k_add_priors<<<1, 128, 0, h->stream>>>(nf, H, b, wprior, cDeltaF);
+  h->launches++;
 }
 
 void launch_finalize_sc(sosba *h, const double *accSC, int nf, double *H, double *b) {

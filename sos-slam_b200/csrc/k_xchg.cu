@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(XT, 1) k_stitch_xchg(StitchXchgArgs a, Layout 
 // The sums of an API-level linearizeAll outside the loop over the ranks (FullSystemOptimize.cpp:125-182: energy, state
 // histogram, removals) and the newest-frame energies for setNewFrameEnergyTH, through the same mailboxes.
 // CTA 0: sums; CTAs 1..: energies.  with_stats = 0: energies only (the pending selection of a fused linearisation).
-__global__ void __launch_bounds__(XT) k_lin_xchg(StitchXchgArgs a, double *stats, int *counts, int with_stats) {
+__global__ void __launch_bounds__(XT) k_lin_xchg(StitchXchgArgs a, double *stats, int *counts, int with_stats, double *extra, int n_extra) {
   PDL_ENTER();
   if (a.gate && *a.gate) return;
   const unsigned ep = (unsigned)a.epoch[0];
@@ -365,6 +365,10 @@ __global__ void __launch_bounds__(XT) k_lin_xchg(StitchXchgArgs a, double *stats
       double v = tid == 0 ? stats[0] : (double)counts[tid - 1];
       v = xchg_sum(a, ep, parity, tid, v, t0, ok);
       if (ok) { if (tid == 0) stats[0] = v; else counts[tid - 1] = (int)v; }
+    }
+    if (tid >= 5 && tid < 5 + n_extra) {   // further sums of the caller (the step sums of sosba_ba_step)
+      const double v = xchg_sum(a, ep, parity, tid, extra[tid - 5], t0, ok);
+      if (ok) extra[tid - 5] = v;
     }
   } else if (a.with_newE) {
     exchange_energies(a, ep, parity, 16 * 16, blockIdx.x - 1, gridDim.x - 1, t0, ok);
@@ -391,8 +395,8 @@ int launch_stitch_xchg(sosba *h, const StitchXchgArgs &a0, int local_points) {
 }
 
 // point shards, outside the loop: see k_lin_xchg.  Only with the peer mailboxes (a.push); the caller falls back to NCCL.
-void launch_lin_xchg(sosba *h, const StitchXchgArgs &a, double *stats, int *counts, int with_stats, int local_points) {
+void launch_lin_xchg(sosba *h, const StitchXchgArgs &a, double *stats, int *counts, int with_stats, int local_points, double *extra, int n_extra) {
   const int ne = a.with_newE ? (local_points + XT - 1) / XT + 1 : 0;
-  launch_pdl(k_lin_xchg, 1 + ne, XT, 0, h->stream, a, stats, counts, with_stats);
+  launch_pdl(k_lin_xchg, 1 + ne, XT, 0, h->stream, a, stats, counts, with_stats, extra, n_extra > 10 ? 10 : n_extra);
   h->launches++;
 }

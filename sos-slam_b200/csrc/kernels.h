@@ -192,9 +192,10 @@ struct StitchXchgArgs {
 #define SOSBA_XCHG_MAX_NEWE 16384   // newest-frame energies per rank a mailbox slot can carry
 size_t stitch_xchg_slot_bytes(int nf_max, int newE_cap);
 int launch_stitch_xchg(sosba *h, const StitchXchgArgs &a, int local_points);
-void launch_lin_xchg(sosba *h, const StitchXchgArgs &a, double *stats, int *counts, int with_stats, int local_points);
+void launch_lin_xchg(sosba *h, const StitchXchgArgs &a, double *stats, int *counts, int with_stats, int local_points, double *extra = nullptr, int n_extra = 0);
 // accSC -> Hsc (D*D), bsc (D)
 void launch_finalize_sc(sosba *h, const double *accSC, int nf, double *H, double *b);
+void launch_add_priors(sosba *h, int nf, double *H, double *b, const double *wprior, const float *cDeltaF);
 
 // ---- k_solve.cu ---------------------------------------------------------------------------------
 struct SolveArgs {

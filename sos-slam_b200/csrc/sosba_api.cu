@@ -27,7 +27,7 @@ using sosba_host::WindowTables;
 
 int sosba_allreduce_acc(sosba *h, int with_newE);  // comm.cu: no-ops without a communicator
 void sosba_xchg_args(sosba *h, StitchXchgArgs *a, int with_newE);
-int sosba_allreduce_lin(sosba *h, int with_stats);
+int sosba_allreduce_lin(sosba *h, int with_stats, double *extra = nullptr, int n_extra = 0);
 int sosba_comm_max_int(sosba *h, int v, int *out);
 static thread_local char g_err[512] = "";
 static long long *g_dbg = nullptr;   // SOSBA_SOLVE_DEBUG: k_solve phase timestamps (clock64), 16 per launch
@@ -842,15 +842,15 @@ static void clear_gathered_energies(sosba *h) {   // point shards: the list must
 }
 
 // point shards: the sums of a linearizeAll outside the loop (with_stats) and the newest-frame energies over the ranks
-static int exchange_lin(sosba *h, int with_stats) {
+static int exchange_lin(sosba *h, int with_stats, double *extra = nullptr, int n_extra = 0) {
   if (!h->comm || h->world <= 1) return SOSBA_OK;
   StitchXchgArgs x;
   memset(&x, 0, sizeof(x));
   sosba_xchg_args(h, &x, 1);
-  if (!x.push) return sosba_allreduce_lin(h, with_stats);
+  if (!x.push) return sosba_allreduce_lin(h, with_stats, extra, n_extra);
   HostSide *hs = HS(h);
   x.gate = hs->gate; x.err = hs->d_ctl + 2;
-  launch_lin_xchg(h, x, h->d_stats, h->d_counts, with_stats, h->P);
+  launch_lin_xchg(h, x, h->d_stats, h->d_counts, with_stats, h->P, extra, n_extra);
   return SOSBA_OK;
 }
 
@@ -1677,6 +1677,81 @@ API int sosba_ba_iterate(sosba_t *h, int32_t n, int32_t *n_res) {
   if ((rc = sync(h))) return rc;
   if (hs->pin_i[0]) return solve_flag_error(hs->pin_i[0]);
   if (n_res) *n_res = h->R - hs->n_lin;
+  return SOSBA_OK;
+}
+
+// ---- the loop body split around a caller-side solve (IMU configurations; include/sosba.h) ---------------------------------
+API int sosba_ba_system(sosba_t *h, double *H_top, double *b_top, double *H_sc, double *b_sc, int32_t *resInA, int32_t *resInL) {
+  CHECK_H(h);
+  if (!h->ba->st.loaded) { sosba_set_error("ba_upload first"); return SOSBA_E_STATE; }
+  HostSide *hs = HS(h);
+  const int nf = h->nf, D = 4 + 8 * nf;
+  int rc;
+  cudaMemsetAsync(hs->d_ctl + 2, 0, sizeof(int), h->stream);
+  StitchXchgArgs x;
+  memset(&x, 0, sizeof(x));
+  sosba_xchg_args(h, &x, hs->th_pending ? 1 : 0);
+  const bool sharded = h->comm && h->world > 1;
+  ThArgs th_def = {};
+  int th_deferred = 0;
+  if ((rc = enqueue_blocks(h, sharded && !x.push, &th_def, &th_deferred))) return rc;
+  x.nf = nf; x.D = D; x.accTop = h->d_accTop; x.adHost = h->d_adHost; x.adTarget = h->d_adTarget;
+  x.H = Hpart(h, 0); x.b = bpart(h, 0); x.accSC = h->d_accSC; x.rstats = h->d_rstats_all; x.cnt = h->d_cnt_all;
+  x.gate = nullptr; x.err = hs->d_ctl + 2;
+  if ((rc = launch_stitch_xchg(h, x, h->P))) return rc;
+  if (th_deferred) { launch_energy_th(h, th_def); hs->th_pending = false; }
+  launch_add_priors(h, nf, Hpart(h, 0), bpart(h, 0), h->d_wprior, h->d_calib + 6);
+  launch_finalize_sc(h, h->d_accSC, nf, Hpart(h, 2), bpart(h, 2));
+  SOSBA_CUDA(cudaGetLastError());
+  if ((rc = fetch(h, H_top, Hpart(h, 0), (size_t)D * D)) || (rc = fetch(h, b_top, bpart(h, 0), D)) || (rc = fetch(h, H_sc, Hpart(h, 2), (size_t)D * D)) ||
+      (rc = fetch(h, b_sc, bpart(h, 2), D)) || (rc = down(h, hs->pin_i, hs->d_cnt, 2)) || (rc = down(h, hs->pin_i + 8, hs->d_ctl + 2, 1)))
+    return rc;
+  if ((rc = sync(h))) return rc;
+  if (hs->pin_i[8] & 2) return solve_flag_error(hs->pin_i[8]);
+  if (resInA) *resInA = hs->pin_i[0];
+  if (resInL) *resInL = hs->pin_i[1];
+  return SOSBA_OK;
+}
+
+API int sosba_ba_step(sosba_t *h, const double *x, sosba_step_out *out) {
+  CHECK_H(h);
+  if (!x || !out) return SOSBA_E_ARG;
+  if (!h->ba->st.loaded) { sosba_set_error("ba_upload first"); return SOSBA_E_STATE; }
+  HostSide *hs = HS(h);
+  const int nf = h->nf, D = 4 + 8 * nf;
+  int rc;
+  if ((rc = up(h, h->d_x, x, D))) return rc;
+  double *rst = hs->d_rstats + 4 * hs->rstats_par;   // [0] sum step^2 [1] sum |idepth_backup| [2] count of this body
+  cudaMemsetAsync(rst, 0, 4 * sizeof(double), h->stream);
+  cudaMemsetAsync(hs->d_ctl + 2, 0, sizeof(int), h->stream);
+  flush_pending_th(h);
+  {
+    ResubArgs ra = resub_args(h, 1);
+    ra.zero_lin = h->d_stats;
+    if (h->d_newE_all) {
+      if (h->p2p) { ra.zero_newE = (float *)h->d_newE_cnt; ra.zero_newE_n = h->world; }
+      else { ra.zero_newE = h->d_newE_all; ra.zero_newE_n = h->world * h->newE_cap + h->world; }
+    }
+    launch_step(h, ra, step_args(h));
+  }
+  enqueue_linearize_apply(h, true);
+  // sums over the point shards: energy, state histogram, the step sums of the points; then setNewFrameEnergyTH
+  if ((rc = exchange_lin(h, 1, rst, 3))) return rc;
+  if (hs->th_pending) { launch_energy_th(h, lin_args(h).th); clear_gathered_energies(h); hs->th_pending = false; }
+  h->ba->mirror_stale = true;
+  h->ba->iterations_done++;
+  SOSBA_CUDA(cudaGetLastError());
+  if ((rc = down(h, hs->pin_d, h->d_stats, 12)) || (rc = down(h, hs->pin_d + 16, hs->d_iter, 4)) || (rc = down(h, hs->pin_d + 24, rst, 3)) ||
+      (rc = down(h, hs->pin_i + 8, hs->d_ctl + 2, 1)))
+    return rc;
+  if ((rc = sync(h))) return rc;
+  if (hs->pin_i[8] & 2) return solve_flag_error(hs->pin_i[8]);
+  const int *ci = (const int *)(hs->pin_d + 2);
+  out->energy = hs->pin_d[0];
+  out->new_frame_energy_th = ((const float *)(ci + 16))[0];
+  out->n_in = ci[0]; out->n_oob = ci[1]; out->n_outlier = ci[2];
+  out->sum_a = hs->pin_d[16]; out->sum_b = hs->pin_d[17]; out->sum_t = hs->pin_d[18]; out->sum_r = hs->pin_d[19];
+  out->sum_id = hs->pin_d[24]; out->sum_nid = hs->pin_d[25]; out->num_id = hs->pin_d[26];
   return SOSBA_OK;
 }
 

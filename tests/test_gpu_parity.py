@@ -729,3 +729,51 @@ def test_distance_map_bit_exact(gpu, orc, cfg):
         assert np.array_equal(dg, do), (k, int((dg != do).sum()))
     assert (do == 1000).all() and (dg == 1000).all()
     hg.close(); ho.close()
+
+
+def _host_solve(sys, lam=1e-5):
+    """EnergyFunctional::solveSystemF (EnergyFunctional.cpp:1094-1148) without IMU and without marginalisation prior, on the host."""
+    H = sys["H_top"].copy()
+    b = sys["b_top"] - sys["b_sc"]
+    H[np.diag_indices_from(H)] *= (1 + lam)
+    H -= sys["H_sc"] * float(np.float32(1.0) / np.float32(1 + lam))
+    S = 1.0 / np.sqrt(np.diag(H) + 10.0)
+    return S * np.linalg.solve(S[:, None] * H * S[None, :], S * b)
+
+
+@pytest.mark.parametrize("cfg", [SMALL, EUROC], ids=["small", "euroc-752x480"])
+def test_split_body_with_caller_side_solve(gpu, orc, cfg):
+    """sosba_ba_system / sosba_ba_step: the loop body of FullSystem::optimize with the solve on the caller's side (what an IMU
+    configuration needs, EnergyFunctional.cpp:1052-1171).  (1) the stitched systems match the oracle's (1e-4); (2) fed with the same
+    x, the step + linearizeAll + applyRes leave identical residual states and energies (1e-6), step sums 1e-5; (3) three such
+    bodies with a host LDL^T land where the device-resident loop (sosba_ba_iterate) lands."""
+    sc = scene(**cfg)
+    hs = []
+    for lib in (gpu, orc, gpu):
+        h = open_handle(lib, sc)
+        upload(h, sc)
+        h.reset_oob(); h.linearize_all(False); h.apply_res()
+        hs.append(h)
+    hg, ho, hres = hs
+    for it in range(3):
+        sg, so = hg.ba_system(), ho.ba_system()
+        assert sg["resInA"] == so["resInA"] and sg["resInL"] == so["resInL"]
+        for k in ("H_top", "H_sc"):
+            assert relerr(sg[k], so[k]) < 1e-4, (it, k, relerr(sg[k], so[k]))
+        for k in ("b_top", "b_sc"):
+            assert relerr(sg[k], so[k]) < 2e-4, (it, k)
+        assert np.array_equal(sg["H_top"], sg["H_top"].T) and np.array_equal(sg["H_sc"], sg["H_sc"].T)
+        x = _host_solve(so)
+        og, oo = hg.ba_step(x), ho.ba_step(x)
+        assert (og["n_in"], og["n_oob"], og["n_outlier"]) == (oo["n_in"], oo["n_oob"], oo["n_outlier"])
+        assert og["energy"] == pytest.approx(oo["energy"], rel=1e-6) and og["new_frame_energy_th"] == pytest.approx(oo["new_frame_energy_th"], rel=1e-6)
+        for k in ("sum_a", "sum_b", "sum_t", "sum_r", "sum_id", "sum_nid", "num_id"):
+            assert og[k] == pytest.approx(oo[k], rel=2e-5, abs=1e-30), k
+        assert np.array_equal(hg.get_state()["state"], ho.get_state()["state"])
+    # the device-resident loop takes the same three steps (its LDL^T runs on the device)
+    hres.ba_iterate(3)
+    stg, str_ = hg.get_state(), hres.get_state()
+    assert int((stg["state"] != str_["state"]).sum()) <= max(2, stg["state"].size // 500)
+    assert np.abs(stg["energy"] - str_["energy"]).max() <= 2e-3 * np.abs(str_["energy"]).max()
+    for h in hs:
+        h.close()

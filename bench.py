@@ -48,13 +48,15 @@ def load():
 WORKLOADS = {"configB": WORKLOAD,
              "euroc": "EuRoC-shaped 752x480 stereo, 8-KF window, 2000 active points, BA only, IMU off (BASELINE.json configs[2] shape)",
              "kitti": "KITTI-shaped 1232x368 stereo, 12-KF window, 4000 active points, BA only (BASELINE.json configs[3] shape)",
-             "tumvi": "TUM-VI-shaped 512x512, 8-KF window, 2000 active points, BA only, hot path only (BASELINE.json configs[4] shape)"}
+             "tumvi": "TUM-VI-shaped 512x512, 8-KF window, 2000 active points, BA only, hot path only (BASELINE.json configs[4] shape)",
+             "euroc_imu": "EuRoC-shaped 752x480 stereo+IMU, 8-KF window, 2000 active points: visual system on the device, IMU/KKT widening and "
+                          "solve on the host with a stand-in IMU Hessian of the reference's shape (BASELINE.json configs[2])"}
 _workload = "configB"
 
 
 def get_scene(synth, n_points_factor=1):
     from _scenes import CONFIG_B, EUROC, KITTI, TUMVI, scene
-    sc = scene(**{"configB": CONFIG_B, "euroc": EUROC, "kitti": KITTI, "tumvi": TUMVI}[_workload])
+    sc = scene(**{"configB": CONFIG_B, "euroc": EUROC, "euroc_imu": EUROC, "kitti": KITTI, "tumvi": TUMVI}[_workload])
     if n_points_factor > 1:
         sc = synth.replicate_points(sc, n_points_factor)
     return sc
@@ -299,6 +301,165 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ---- configs[2]: the IMU configuration ---------------------------------------------------------------------------------------
+class ImuStandIn:
+    """Caller-side half of EnergyFunctional::solveSystemF with IMU (EnergyFunctional.cpp:1052-1171) for the benchmark: the widening
+    8 -> 29 states per frame + scale (expandHbtoFitImu :256-286), an IMU Hessian, the KKT rows of the spline constraints (6 per
+    consecutive frame pair, 3 for the last, :323-330), the removal of the scale column when scale optimisation is on (:1113), Jacobi
+    scaling, LDL^T, and the unpacking of x_dso (:1150-1171).  The IMU Hessian and the constraint Jacobians are a STAND-IN with the
+    reference's sparsity and magnitudes (bias random walk + a banded positive definite 29x29 block per frame, unit-scaled constraint
+    rows): getImuHessian needs the FrameHessian spline state and stays in the reference.  It measures the data path
+    of the configuration, not IMU physics."""
+
+    def __init__(self, nf, seed=0):
+        rng = np.random.default_rng(seed)
+        self.nf, self.dim = nf, 4 + 1 + 29 * nf
+        H = np.zeros((self.dim, self.dim))
+        b = np.zeros(self.dim)
+        for f in range(1, nf):
+            c, p = 5 + 29 * f, 5 + 29 * (f - 1)
+            A = rng.standard_normal((29, 29)) * 3.0
+            H[c:c + 29, c:c + 29] += A @ A.T + 50.0 * np.eye(29)
+            W = 1e3 * np.eye(6)
+            H[p + 8:p + 14, p + 8:p + 14] += W; H[c + 8:c + 14, c + 8:c + 14] += W
+            H[p + 8:p + 14, c + 8:c + 14] -= W; H[c + 8:c + 14, p + 8:p + 14] -= W
+            b[c:c + 29] += rng.standard_normal(29) * 0.1
+        self.H_imu, self.b_imu = H, b
+        rows = []
+        for f in range(1, nf):
+            n = 6 if f < nf - 1 else 3
+            J = np.zeros((n, self.dim))
+            c, p = 5 + 29 * f, 5 + 29 * (f - 1)
+            J[:3, p + 3:p + 6] = -np.eye(3); J[:3, c + 3:c + 6] = np.eye(3); J[:3, c + 14:c + 17] = -0.05 * np.eye(3)
+            if n == 6:
+                J[3:, p:p + 3] = 10 * np.eye(3); J[3:, c:c + 3] = -20 * np.eye(3); J[3:, c + 29:c + 32] = 10 * np.eye(3); J[3:, c + 17:c + 20] = -0.05 * np.eye(3)
+            rows.append(J)
+        self.J_cst = np.concatenate(rows)
+        self.r_cst = rng.standard_normal(len(self.J_cst)) * 1e-4
+        # scale optimisation on: the scale column is not a state; frame 0 has no valid spline: only its 8 + 6 bias states stay (:1113-1123)
+        self.keep = np.array([i for i in range(self.dim) if i != 4 and not (5 + 14 <= i < 5 + 29)])
+        self.start = np.cumsum([4] + [14] + [29] * (nf - 2))        # first compacted column of every frame
+
+    def expand(self, H, b):
+        nf, He, be = self.nf, np.zeros((self.dim, self.dim)), np.zeros(self.dim)
+        idx = np.concatenate([np.arange(4)] + [5 + 29 * f + np.arange(8) for f in range(nf)])
+        He[np.ix_(idx, idx)] = H
+        be[idx] = b
+        return He, be
+
+    def solve(self, sys, lam=1e-5):
+        H, b = self.expand(sys["H_top"], sys["b_top"])
+        Hs, bs = self.expand(sys["H_sc"], sys["b_sc"])
+        H += self.H_imu; b = b + self.b_imu
+        H[np.diag_indices_from(H)] *= (1 + lam)
+        H -= Hs * float(np.float32(1.0) / np.float32(1 + lam)); b = b - bs
+        H, b = H[np.ix_(self.keep, self.keep)], b[self.keep]
+        J = self.J_cst[:, self.keep]
+        n, c = len(b), len(J)
+        K = np.zeros((n + c, n + c)); K[:n, :n] = H; K[:n, n:] = J.T; K[n:, :n] = J
+        rhs = np.concatenate([b, self.r_cst])
+        S = 1.0 / np.sqrt(np.diag(K) + 10.0)
+        x = S * np.linalg.solve(S[:, None] * K * S[None, :], S * rhs)
+        xd = np.zeros(4 + 8 * self.nf)
+        xd[:4] = x[:4]
+        for f in range(self.nf):
+            xd[4 + 8 * f:12 + 8 * f] = x[self.start[f]:self.start[f] + 8]
+        return xd
+
+
+def run_imu_workload(args):
+    """configs[2]: one step = FullSystem::optimize(6) with the solve on the host (sosba_ba_system -> widened KKT solve -> sosba_ba_step
+    per iteration).  Host wall clock per step for both arms (the host solve is part of the step)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ref = args.impl == "reference"
+    if ref and rank != 0:
+        return
+    pkg, binding, problem, synth = load()
+    factor = args.points_factor or (max(1, args.gpus) if args.scaling == "weak" else 1)
+    sc = get_scene(synth, factor)
+    imu = ImuStandIn(sc.nf)
+    dist = None
+    if ref:
+        lib = binding.Lib(os.path.join(ROOT, "oracle", "_build", "liborc_speed.so"), "orc")
+        cfg = forced_cfg(lib, sc, threads=os.cpu_count() or 1)
+        h = binding.Handle(lib, cfg)
+    else:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        lib = pkg.load()
+        cfg = forced_cfg(lib, sc)
+        h = binding.Handle(lib, cfg, device=local)
+    for i, img in enumerate(sc.images):
+        h.frame_make_images(i, img)
+    val, val0 = problem.calib_of(sc)
+    pts, res = problem.points_of(sc), problem.residuals_of(sc)
+    if not ref and world > 1:
+        uid = [h.lib_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        h.comm_init(uid[0], rank, world)
+        p0, p1 = problem.shard_points(sc.res_point, sc.n_points, world)[rank]
+        pts, res = problem.shard_scene_arrays(pts, res, p0, p1)
+    P, keep = h.make_problem(problem.frames_of(sc), val, val0, pts, res)
+
+    def step():
+        h.ba_upload(P)
+        h.reset_oob()
+        lo = h.linearize_all(False)
+        h.apply_res()
+        nres, t_solve = lo["n_in"] + lo["n_oob"] + lo["n_outlier"], 0.0
+        for _ in range(ITERS):
+            sy = h.ba_system()
+            t0 = time.perf_counter()
+            x = imu.solve(sy)
+            t_solve += time.perf_counter() - t0
+            so = h.ba_step(x)
+        return nres * 8 * (ITERS + 1), so["energy"], t_solve
+
+    def barrier():
+        if dist is not None and world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    steps = args.steps if not ref else min(args.steps, 20)
+    t0 = time.perf_counter()
+    n_res, t_solve = 0, 0.0
+    for _ in range(steps):
+        n, e, ts = step()
+        n_res += n; t_solve += ts
+    barrier()
+    dt = time.perf_counter() - t0
+    if not ref and world > 1:
+        import torch
+        t = torch.tensor([dt, float(n_res)], dtype=torch.float64, device="cuda")
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dt, n_res = float(tmax[0]), float(tsum[1])
+    if rank == 0:
+        v = n_res / dt
+        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus if ref else world, "steps": steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": 1e3 * dt / steps, "gn_iter_ms": 1e3 * dt / steps / ITERS, "higher_is_better": True, "scaling": args.scaling,
+                "vs_baseline": None, "dtype": "f32 (system f64)", "data": "synthetic", "config": config_of(sc, factor, args.scaling),
+                "host_solve_ms_per_step": 1e3 * t_solve / steps, "system_dim": int(imu.dim - 1 + len(imu.J_cst)),
+                "timing": "host wall clock: the widened solve runs on the host inside every iteration (2 synchronisations per iteration)",
+                "final_energy": e,
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0 if ref else int(sum(np.asarray(a).nbytes for a in pts.values()) + sum(np.asarray(a).nbytes for a in res.values())),
+                        "d2h_bytes_per_step": 0 if ref else int(ITERS * 2 * 8 * ((4 + 8 * sc.nf) ** 2 + 4 + 8 * sc.nf))}}
+        if ref:
+            line["impl"] = "reference"
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": f"{steps} steps, oracle speed build + the same host solve"}
+        print(json.dumps(line), flush=True)
+    h.close()
+    if dist is not None and world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -315,6 +476,8 @@ def main():
     global _workload, WORKLOAD
     _workload = args.workload
     WORKLOAD = WORKLOADS[_workload]
+    if _workload == "euroc_imu":
+        return run_imu_workload(args)
     if args.impl == "reference":
         return run_reference(args)
 

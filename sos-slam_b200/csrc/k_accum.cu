@@ -299,10 +299,10 @@ constexpr int ADJ_ST = 68;   // floats per staged 8x8 adjoint (64 + 4: float4 ro
 constexpr int ACC_THREADS = 512;   // warps 0..7: point sums (8 lanes per point), warps 8..15: top blocks (one target each), concurrently
 __global__ void __launch_bounds__(ACC_THREADS) k_accumulate_fused(FusedAccArgs a, int DP, int DPAD, int ntiles4, int tiles_total, int max_res, int smem_words) {
   extern __shared__ __align__(16) float smem[];
-  PDL_ENTER();
+  PDL_ENTER_T(a.trace);
   if (a.gate && *a.gate) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (a.do_th && blockIdx.x == gridDim.x - 1) { energy_th_body(a.th, (unsigned *)smem, smem_words); return; }
+  if (a.do_th && blockIdx.x == gridDim.x - 1) { energy_th_body(a.th, (unsigned *)smem, smem_words); TRACE_EXIT(a.trace); return; }
   const int nf = a.nf, D = a.D;
   float *Rs = smem;                                   // [max_res][SOSBA_CREC]
   float *Gs = Rs + (size_t)max_res * SOSBA_CREC;      // [SC_TP][DPAD]
@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accumulate_fused(FusedAccArgs a
   ACC_TS(5);
   __syncthreads();
   if (tid < 2 && s_nacc[tid]) atomicAdd(a.n_acc + tid, s_nacc[tid]);
+  TRACE_EXIT(a.trace);
 }
 
 // ------------------------------------------------------------------------------------------------

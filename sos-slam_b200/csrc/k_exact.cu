@@ -13,6 +13,7 @@
 //   energy_th            FullSystem::setNewFrameEnergyTH              FullSystemOptimize.cpp:84-124
 //   track_res            CoarseTracker::calcResPose / ScaleOptimizer::calcResScale   CoarseTracker.cpp:612-764, ScaleOptimizer.cpp:273-437
 #include <math.h>
+#include <stdlib.h>
 
 #include "energy_th.cuh"
 #include "host_math.h"
@@ -366,6 +367,384 @@ __global__ void __launch_bounds__(256) k_linearize(LinArgs a) {
   }
 }
 
+// 128-bit read-only load that the compiler may not reorder against its siblings: a thread's taps stay back to back
+__device__ __forceinline__ float4 ldg_nc_v4(const float4 *p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// a3  LANES (1, 2 or 4) THREADS PER RESIDUAL, 8 / LANES pattern samples each (the default since round 2; the
+// 8-lanes-per-residual kernel above stays selectable with SOSBA_LIN_LANES=8).  A lane walks its samples like the scalar
+// loop of Residuals.cpp:177-256; the 2x2 sums are in-order float additions: lane 0 sums its samples from zero, every
+// following lane continues the running sums of its left neighbour (one shuffle per sum and hop), so the result is
+// bit-identical to the reference's sequential loop for every LANES.  LANES = 1: no shuffles at all, the centre
+// projection and the geometric derivatives once per residual, 32 independent 128-bit taps in flight per thread —
+// 7x fewer warp instructions than the 8-lane kernel: the variant for large windows (bandwidth regime).  LANES = 4: a
+// quarter of the dependent instruction chain per thread: the variant for the 10^4-residual window of the benchmark,
+// where the launch is one partial wave and its duration is the length of one thread's chain.
+// The last lane of a group decides the state and writes the records (12 x 16 B per commit record).
+// FIX: the bookkeeping of linearizeAll(true) (FullSystemOptimize.cpp:52-74, :148-179) fused in: maxRelBaseline / numGood of
+//      new residuals, removal of residuals that did not stay active.
+constexpr int LIN_T = 64;
+
+template <int LANES, bool APPLY, bool WRITE_J, bool FIX>
+__global__ void __launch_bounds__(LIN_T) k_linearize_t(LinArgs a) {
+  constexpr int SPL = 8 / LANES;           // samples per lane
+  constexpr int NS = APPLY ? 17 : 12;      // running sums
+  __shared__ double s_we[LIN_T / 32];
+  __shared__ int s_wc[LIN_T / 32][4];
+  PDL_ENTER_T(a.trace);
+  const int gid = blockIdx.x * LIN_T + threadIdx.x;
+  const int r = gid / LANES, sub = gid % LANES;
+  const int lane = threadIdx.x & 31;
+  const unsigned gmask = LANES == 1 ? (1u << lane) : (((1u << LANES) - 1u) << (lane & ~(LANES - 1)));
+  const bool writer = sub == LANES - 1;
+  const bool inr = r < a.R;
+  const int gate = a.gate ? *a.gate : 0;
+  // first round trip: every per-residual id / flag at once (independent loads)
+  const int m_lin = inr ? a.r_is_lin[r] : 1, m_drop = inr ? a.r_dropped[r] : 1, m_state = inr ? a.r_state[r] : 0;
+  const int pt = inr ? a.r_point[r] : 0, host = inr ? a.r_host[r] : 0, target = inr ? a.r_target[r] : 0;
+  const float old_energy = inr ? a.r_energy[r] : 0.f;
+  if (gate) return;   // the Gauss-Newton loop already converged (device-side break)
+  if (a.zero_n > 0) {   // clear the block tables of the accumulation that follows
+    double2 *zb = (double2 *)a.zero_buf;
+    for (int i = gid; i < a.zero_n; i += gridDim.x * LIN_T) zb[i] = make_double2(0.0, 0.0);
+  }
+#define LIN_TS(n, dep) do { if (a.trace && threadIdx.x == 0 && blockIdx.x == gridDim.x / 2) a.trace[4 + (n)] = clock64() + (long long)((dep) == 1.2345e-30f); } while (0)
+  LIN_TS(0, old_energy);
+  const bool live = inr && !(m_lin | m_drop);
+  int outcome = -1;        // state_NewState once decided
+  float ret_energy = 0.f;  // linearize() return value
+  float energyWO = -1.f;
+  int removed = 0;
+  // Straight-line code with group-uniform stage predicates instead of nested early returns: the votes and the shuffles of
+  // the running sums sit at convergent points of the warp (plain SHFL / VOTE, no per-shuffle reconvergence scaffolding).
+  // Lanes whose residual left early carry harmless garbage through the arithmetic; every memory access is guarded.
+  const bool s1 = live && m_state != SOSBA_RES_OOB;
+  if (live) { outcome = SOSBA_RES_OOB; ret_energy = old_energy; }   // every early return of the reference leaves exactly this
+  const float *pc = a.precalc + (size_t)(host * a.nf + target) * SOSBA_PRECALC_FLOATS;
+  const float4 q0 = __ldg((const float4 *)pc), q1 = __ldg((const float4 *)pc + 1), q2 = __ldg((const float4 *)pc + 2),
+               q3 = __ldg((const float4 *)pc + 3), q4 = __ldg((const float4 *)pc + 4), q5 = __ldg((const float4 *)pc + 5),
+               q6 = __ldg((const float4 *)pc + 6);
+  const float R0[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+  const float t0[3] = {q2.y, q2.z, q2.w};
+  const float KRKi[9] = {q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w, q5.x};
+  const float Kt[3] = {q5.y, q5.z, q5.w};
+  const float affLL0 = q6.x, affLL1 = q6.y, b0 = q6.z;
+  const float fxl = a.calib[0], fyl = a.calib[1], cxl = a.calib[2], cyl = a.calib[3], fxli = a.calib[4], fyli = a.calib[5];
+  const float pu = a.p_u[pt], pv = a.p_v[pt], idepth = a.p_idepth[pt] * kSCALE_IDEPTH, idepth_zero = a.p_idepth_zero[pt] * kSCALE_IDEPTH;
+  float color[SPL], weight[SPL];
+  if (SPL == 8) {
+    const float4 col0 = __ldg((const float4 *)(a.p_color + (size_t)pt * 8)), col1 = __ldg((const float4 *)(a.p_color + (size_t)pt * 8) + 1);
+    const float4 wgt0 = __ldg((const float4 *)(a.p_weights + (size_t)pt * 8)), wgt1 = __ldg((const float4 *)(a.p_weights + (size_t)pt * 8) + 1);
+    const float c8[8] = {col0.x, col0.y, col0.z, col0.w, col1.x, col1.y, col1.z, col1.w};
+    const float w8[8] = {wgt0.x, wgt0.y, wgt0.z, wgt0.w, wgt1.x, wgt1.y, wgt1.z, wgt1.w};
+#pragma unroll
+    for (int k = 0; k < SPL; k++) { color[k] = c8[k % 8]; weight[k] = w8[k % 8]; }
+  } else {
+#pragma unroll
+    for (int k = 0; k < SPL; k++) { color[k] = __ldg(a.p_color + (size_t)pt * 8 + sub * SPL + k); weight[k] = __ldg(a.p_weights + (size_t)pt * 8 + sub * SPL + k); }
+  }
+  const float th = fmaxf(a.frameEnergyTH[host], a.frameEnergyTH[target]);
+  int sel = 0;
+  if (WRITE_J) sel = inr ? a.r_sel[r] : 0;
+
+  // centre projection at the evaluation point (Residuals.cpp:102-169); every lane of the group evaluates it.  Only the
+  // bounds test is needed before the taps go out; the derivatives follow below, while the taps are in flight.
+  const float KliP[3] = {(pu + 0 - cxl) * fxli, (pv + 0 - cyl) * fyli, 1.f};
+  float cptp[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) cptp[i] = ((R0[3 * i] * KliP[0] + R0[3 * i + 1] * KliP[1]) + R0[3 * i + 2] * KliP[2]) + t0[i] * idepth_zero;
+  const float drescale = 1.0f / cptp[2];
+  const float c_new_idepth = idepth_zero * drescale;
+  const float cu = cptp[0] * drescale, cv = cptp[1] * drescale;
+  const float cKu = cu * fxl + cxl, cKv = cv * fyl + cyl;
+  const bool centre_ok = (drescale > 0) && (cKu > 1.1f && cKv > 1.1f && cKu < a.wM3G && cKv < a.hM3G);
+  const bool s2 = s1 && centre_ok;   // uniform across the lanes of a group
+  LIN_TS(1, cKu + th);
+
+  // this lane's pattern samples at the current state (Residuals.cpp:177-256): all projections first, then all taps
+  float Ku[SPL], Kv[SPL];
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < SPL; k++) {
+    const int idx = sub * SPL + k;
+    const float up = pu + c_pattern[idx][0], vp = pv + c_pattern[idx][1];
+    float ptp[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) ptp[i] = ((KRKi[3 * i] * up + KRKi[3 * i + 1] * vp) + KRKi[3 * i + 2] * 1.0f) + Kt[i] * idepth;
+    Ku[k] = ptp[0] / ptp[2]; Kv[k] = ptp[1] / ptp[2];
+    bad |= !(Ku[k] > 1.1f && Kv[k] > 1.1f && Ku[k] < a.wM3G && Kv[k] < a.hM3G);
+  }
+  if (LANES > 1) bad = (__ballot_sync(0xffffffffu, bad) & gmask) != 0u;
+  const bool s3 = s2 && !bad;
+  LIN_TS(2, Ku[0] + Kv[SPL - 1]);
+  float d_xi_x[6], d_xi_y[6], d_C_x[4], d_C_y[4], d_d_x, d_d_y;
+  float3 hit[SPL];
+  {   // getInterpolatedElement33 (globalFuncs.h:68-82) of all samples: the taps go out back to back
+    float4 t11[SPL], t01[SPL], t10[SPL], t00[SPL];
+#pragma unroll
+    for (int k = 0; k < SPL; k++) t11[k] = t01[k] = t10[k] = t00[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s3) {
+      const float4 *img = a.img[target];
+#pragma unroll
+      for (int k = 0; k < SPL; k++) {
+        const float4 *bp = img + (int)Ku[k] + (int)Kv[k] * a.w;
+        t11[k] = ldg_nc_v4(bp + 1 + a.w); t01[k] = ldg_nc_v4(bp + a.w); t10[k] = ldg_nc_v4(bp + 1); t00[k] = ldg_nc_v4(bp);
+      }
+    }
+    {  // the geometric derivatives (Residuals.cpp:121-169): independent of the taps, evaluated while they are in flight
+      const float u = cu, v = cv, new_idepth = c_new_idepth;
+      d_d_x = drescale * (t0[0] - t0[2] * u) * kSCALE_IDEPTH * fxl;
+      d_d_y = drescale * (t0[1] - t0[2] * v) * kSCALE_IDEPTH * fyl;
+
+      d_C_x[2] = drescale * (R0[6] * u - R0[0]);
+      d_C_x[3] = fxl * drescale * (R0[7] * u - R0[1]) * fyli;
+      d_C_x[0] = KliP[0] * d_C_x[2];
+      d_C_x[1] = KliP[1] * d_C_x[3];
+
+      d_C_y[2] = fyl * drescale * (R0[6] * v - R0[3]) * fxli;
+      d_C_y[3] = drescale * (R0[7] * v - R0[4]);
+      d_C_y[0] = KliP[0] * d_C_y[2];
+      d_C_y[1] = KliP[1] * d_C_y[3];
+
+      d_C_x[0] = (d_C_x[0] + u) * kSCALE_F;
+      d_C_x[1] *= kSCALE_F;
+      d_C_x[2] = (d_C_x[2] + 1) * kSCALE_C;
+      d_C_x[3] *= kSCALE_C;
+
+      d_C_y[0] *= kSCALE_F;
+      d_C_y[1] = (d_C_y[1] + v) * kSCALE_F;
+      d_C_y[2] *= kSCALE_C;
+      d_C_y[3] = (d_C_y[3] + 1) * kSCALE_C;
+
+      d_xi_x[0] = new_idepth * fxl;
+      d_xi_x[1] = 0;
+      d_xi_x[2] = -new_idepth * u * fxl;
+      d_xi_x[3] = -u * v * fxl;
+      d_xi_x[4] = (1 + u * u) * fxl;
+      d_xi_x[5] = -v * fxl;
+
+      d_xi_y[0] = 0;
+      d_xi_y[1] = new_idepth * fyl;
+      d_xi_y[2] = -new_idepth * v * fyl;
+      d_xi_y[3] = -(1 + v * v) * fyl;
+      d_xi_y[4] = u * v * fyl;
+      d_xi_y[5] = u * fyl;
+    }
+    // every weight below depends on ALL taps (through a word that is zero at run time, or-ed from their unused 4th
+    // components), so no consumer can be scheduled between the loads: all of them are in flight before the first wait
+    unsigned zr = 0u;
+#pragma unroll
+    for (int k = 0; k < SPL; k++)
+      zr |= __float_as_uint(t11[k].w) | __float_as_uint(t01[k].w) | __float_as_uint(t10[k].w) | __float_as_uint(t00[k].w);
+    zr &= a.opaque_zero;
+    bad = false;
+#pragma unroll
+    for (int k = 0; k < SPL; k++) {
+      const float x = __uint_as_float(__float_as_uint(Ku[k]) | zr), y = Kv[k];
+      const int ix = (int)x, iy = (int)y;
+      const float dx = x - ix, dy = y - iy;
+      const float dxdy = dx * dy;
+      const float w11 = dxdy, w01 = dy - dxdy, w10 = dx - dxdy, w00 = 1 - dx - dy + dxdy;
+      hit[k].x = w11 * t11[k].x + w01 * t01[k].x + w10 * t10[k].x + w00 * t00[k].x;
+      hit[k].y = w11 * t11[k].y + w01 * t01[k].y + w10 * t10[k].y + w00 * t00[k].y;
+      hit[k].z = w11 * t11[k].z + w01 * t01[k].z + w10 * t10[k].z + w00 * t00[k].z;
+      bad |= !isfinite(hit[k].x);
+    }
+    if (LANES > 1) bad = (__ballot_sync(0xffffffffu, bad) & gmask) != 0u;
+  }
+  const bool reached = s3 && !bad;   // the energies are evaluated (no early OOB return)
+  LIN_TS(3, hit[0].x + hit[SPL - 1].z);
+  // the terms of the running sums, sample by sample: 0 energyLeft, 1..3 JIdx2 (00, 11, 10), 4..7 JabJIdx (00, 01, 10, 11),
+  // 8..10 Jab2 (00, 01, 11), 11 wJI2_sum, 12..16 JI_r[0], JI_r[1], Jab_r[0], Jab_r[1], rr (EFResidual::takeDataF / addPoint)
+  float term[NS][SPL];
+  float *J = nullptr;
+  if (WRITE_J) J = (sel ? a.J1 : a.J0) + (size_t)r * SOSBA_JREC;
+#pragma unroll
+  for (int k = 0; k < SPL; k++) {
+    const int idx = sub * SPL + k;
+    const float3 hc = hit[k];
+    const float residual = hc.x - (float)(affLL0 * color[k] + affLL1);
+    const float drdA = (color[k] - b0);
+    float w = sqrtf(a.outlierTHSum / (a.outlierTHSum + (hc.y * hc.y + hc.z * hc.z)));
+    w = 0.5f * (w + weight[k]);
+    float hw = fabsf(residual) < a.huberTH ? 1 : a.huberTH / fabsf(residual);
+    term[0][k] = w * w * hw * residual * residual * (2 - hw);
+    if (hw < 1) hw = sqrtf(hw);
+    hw = hw * w;
+    const float hx = hc.y * hw, hy = hc.z * hw;
+    const float resF = residual * hw;
+    float jab0 = drdA * hw, jab1 = hw;
+    term[1][k] = hx * hx;
+    term[2][k] = hy * hy;
+    term[3][k] = hx * hy;
+    term[4][k] = drdA * hw * hx;
+    term[5][k] = drdA * hw * hy;
+    term[6][k] = hw * hx;
+    term[7][k] = hw * hy;
+    term[8][k] = drdA * drdA * hw * hw;
+    term[9][k] = drdA * hw * hw;
+    term[10][k] = hw * hw;
+    term[11][k] = hw * hw * (hx * hx + hy * hy);
+    if (a.affModeA < 0) jab0 = 0;
+    if (a.affModeB < 0) jab1 = 0;
+    if (APPLY) {
+      term[12 % NS][k] = resF * hx; term[13 % NS][k] = resF * hy;
+      term[14 % NS][k] = resF * jab0; term[15 % NS][k] = resF * jab1;
+      term[16 % NS][k] = resF * resF;
+    }
+    if (WRITE_J && reached) {
+      J[JR_RES + idx] = resF;
+      J[JR_JIDX0 + idx] = hx;
+      J[JR_JIDX1 + idx] = hy;
+      J[JR_JAB0 + idx] = jab0;
+      J[JR_JAB1 + idx] = jab1;
+      a.proj[(size_t)r * 16 + idx * 2] = Ku[k];
+      a.proj[(size_t)r * 16 + idx * 2 + 1] = Kv[k];
+    }
+  }
+  // in-order sums: lane 0 from zero, lane h continues lane h-1 (whole-warp shuffles at a convergent point)
+  float S[NS];
+#pragma unroll
+  for (int q = 0; q < NS; q++) {
+    float v = 0;
+#pragma unroll
+    for (int k = 0; k < SPL; k++) v += term[q][k];
+    S[q] = v;
+  }
+#pragma unroll
+  for (int hop = 1; hop < LANES; hop++) {
+#pragma unroll
+    for (int q = 0; q < NS; q++) {
+      float v = __shfl_up_sync(0xffffffffu, S[q], 1);
+#pragma unroll
+      for (int k = 0; k < SPL; k++) v += term[q][k];
+      if (sub == hop) S[q] = v;
+    }
+  }
+  LIN_TS(4, S[0] + S[NS - 1]);
+  if (writer && reached) {
+    const float JIdxJIdx_00 = S[1], JIdxJIdx_11 = S[2], JIdxJIdx_10 = S[3];
+    const float JabJIdx_00 = S[4], JabJIdx_01 = S[5], JabJIdx_10 = S[6], JabJIdx_11 = S[7];
+    const float JabJab_00 = S[8], JabJab_01 = S[9], JabJab_11 = S[10], wJI2_sum = S[11];
+    if (WRITE_J) {   // candidate record: PointFrameResidual::J
+      float4 *G = (float4 *)(J + JR_GEO);
+      G[0] = make_float4(d_xi_x[0], d_xi_x[1], d_xi_x[2], d_xi_x[3]);
+      G[1] = make_float4(d_xi_x[4], d_xi_x[5], d_xi_y[0], d_xi_y[1]);
+      G[2] = make_float4(d_xi_y[2], d_xi_y[3], d_xi_y[4], d_xi_y[5]);
+      G[3] = make_float4(d_C_x[0], d_C_x[1], d_C_x[2], d_C_x[3]);
+      G[4] = make_float4(d_C_y[0], d_C_y[1], d_C_y[2], d_C_y[3]);
+      G[5] = make_float4(d_d_x, d_d_y, JIdxJIdx_00, JIdxJIdx_10);
+      G[6] = make_float4(JIdxJIdx_10, JIdxJIdx_11, JabJIdx_00, JabJIdx_01);
+      G[7] = make_float4(JabJIdx_10, JabJIdx_11, JabJab_00, JabJab_01);
+      *(float2 *)(J + JR_JAB2 + 2) = make_float2(JabJab_01, JabJab_11);
+    }
+    float energyLeft = S[0];
+    energyWO = energyLeft;
+    if (energyLeft > th || wJI2_sum < 2) { energyLeft = th; outcome = SOSBA_RES_OUTLIER; }
+    else outcome = SOSBA_RES_IN;
+    ret_energy = energyLeft;
+    if (APPLY && outcome == SOSBA_RES_IN) {   // EFResidual::takeDataF on the registers of this linearisation
+      const float JI_r0 = S[12 % NS], JI_r1 = S[13 % NS], Jab_r0 = S[14 % NS], Jab_r1 = S[15 % NS], rr = S[16 % NS];
+      float4 *rec = (float4 *)(a.rec + (size_t)r * SOSBA_CREC);
+      const float v0 = JIdxJIdx_00 * d_d_x + JIdxJIdx_10 * d_d_y, v1 = JIdxJIdx_10 * d_d_x + JIdxJIdx_11 * d_d_y;
+      float jp[8];
+#pragma unroll
+      for (int i = 0; i < 6; i++) jp[i] = d_xi_x[i] * v0 + d_xi_y[i] * v1;
+      jp[6] = JabJIdx_00 * d_d_x + JabJIdx_01 * d_d_y;
+      jp[7] = JabJIdx_10 * d_d_x + JabJIdx_11 * d_d_y;
+      rec[0] = make_float4(d_C_x[0], d_C_x[1], d_C_x[2], d_C_x[3]);            // CR_X: Jpdc[0], Jpdxi[0]
+      rec[1] = make_float4(d_xi_x[0], d_xi_x[1], d_xi_x[2], d_xi_x[3]);
+      rec[2] = make_float4(d_xi_x[4], d_xi_x[5], d_C_y[0], d_C_y[1]);          // CR_Y = 10: Jpdc[1], Jpdxi[1]
+      rec[3] = make_float4(d_C_y[2], d_C_y[3], d_xi_y[0], d_xi_y[1]);
+      rec[4] = make_float4(d_xi_y[2], d_xi_y[3], d_xi_y[4], d_xi_y[5]);
+      rec[5] = make_float4(JIdxJIdx_00, JIdxJIdx_10, JIdxJIdx_11, JabJIdx_00);  // CR_A = 20, CR_TR = 23
+      rec[6] = make_float4(JabJIdx_01, JabJIdx_10, JabJIdx_11, JI_r0);
+      rec[7] = make_float4(JI_r1, JabJab_00, JabJab_01, Jab_r0);               // CR_BR = 29
+      rec[8] = make_float4(JabJab_11, Jab_r1, rr, d_d_x);                      // CR_JPDD = 35
+      rec[9] = make_float4(d_d_y, 0.f, 0.f, 0.f);
+      rec[10] = make_float4(jp[0], jp[1], jp[2], jp[3]);                       // CR_JPJDF = 40
+      rec[11] = make_float4(jp[4], jp[5], jp[6], jp[7]);
+    }
+    a.r_new_energy[r] = energyLeft;
+    a.center[(size_t)r * 3 + 0] = cKu; a.center[(size_t)r * 3 + 1] = cKv; a.center[(size_t)r * 3 + 2] = c_new_idepth;
+  }
+  if (live) {
+    if (writer) {   // (r_sel was read by every lane of the group at the top, before the first vote)
+      a.r_new_state[r] = (uint8_t)outcome;
+      a.r_new_energy_wo[r] = energyWO;
+      if (APPLY) {
+        if (m_state != SOSBA_RES_OOB) {   // applyRes(true): "can never go back from OOB" (Residuals.cpp:306-309)
+          const bool active = outcome == SOSBA_RES_IN;
+          a.r_is_active[r] = active ? 1 : 0;
+          a.r_state[r] = (uint8_t)outcome;
+          // state_energy = state_NewEnergy, which a linearisation that left early (new state OOB) did not refresh
+          a.r_energy[r] = outcome == SOSBA_RES_OOB ? a.r_new_energy[r] : ret_energy;
+          if (WRITE_J && active) a.r_sel[r] ^= 1;   // std::swap(J, data->J)
+          if (FIX) {
+            if (active) {
+              if (a.r_is_new[r]) {  // FullSystemOptimize.cpp:55-66
+                const float *pc = a.precalc + (size_t)(host * a.nf + target) * SOSBA_PRECALC_FLOATS;
+                const float *KRKi = pc + SOSBA_PC_KRKI, *Kt = pc + SOSBA_PC_KT;
+                const float pu = a.p_u[pt], pv = a.p_v[pt], id = a.p_idepth[pt] * kSCALE_IDEPTH;
+                float inf[3], ptp[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) inf[i] = (KRKi[3 * i] * pu + KRKi[3 * i + 1] * pv) + KRKi[3 * i + 2] * 1.0f;
+#pragma unroll
+                for (int i = 0; i < 3; i++) ptp[i] = inf[i] + Kt[i] * id;
+                const float ex = inf[0] / inf[2] - ptp[0] / ptp[2], ey = inf[1] / inf[2] - ptp[1] / ptp[2];
+                const float relBS = (float)(0.01 * (double)sqrtf(ex * ex + ey * ey));
+                if (relBS > 0.f) atomicMax((int *)&a.p_maxRelBaseline[pt], __float_as_int(relBS));  // positive floats order like ints
+                atomicAdd(&a.p_numGood[pt], 1);
+              }
+            } else { a.r_dropped[r] = 1; removed = 1; }  // toRemove -> ef->dropResidual (FullSystemOptimize.cpp:148-179)
+          }
+        } else if (FIX && !a.r_is_active[r]) { a.r_dropped[r] = 1; removed = 1; }
+      }
+    }
+  }
+  LIN_TS(5, ret_energy);
+  {  // newest-frame energies (input of setNewFrameEnergyTH): one atomic per warp, unordered list
+    const bool app = writer && reached && target == a.nf - 1;
+    const unsigned bal = __ballot_sync(0xffffffffu, app);
+    if (bal) {
+      int base = 0;
+      const int leader = __ffs(bal) - 1;
+      if (lane == leader) base = atomicAdd(a.newE_count, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (app) a.newE[base + __popc(bal & ((1u << lane) - 1))] = energyWO;
+    }
+  }
+  {  // energy and state histogram: warp sums -> CTA sums (fixed order) -> one atomic each
+    const bool cnt = live && writer;
+    double e = cnt ? (double)ret_energy : 0.0;
+    int c0 = cnt && outcome == 0, c1 = cnt && outcome == 1, c2 = cnt && outcome == 2, c3 = removed;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      e += __shfl_xor_sync(0xffffffffu, e, o);
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, o); c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+    }
+    if (lane == 0) { const int w = threadIdx.x >> 5; s_we[w] = e; s_wc[w][0] = c0; s_wc[w][1] = c1; s_wc[w][2] = c2; s_wc[w][3] = c3; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double e = 0.0;
+    int c[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int w = 0; w < LIN_T / 32; w++) { e += s_we[w]; c[0] += s_wc[w][0]; c[1] += s_wc[w][1]; c[2] += s_wc[w][2]; c[3] += s_wc[w][3]; }
+    if (e != 0.0) atomicAdd(&a.stats[0], e);
+    if (c[0]) atomicAdd(&a.counts[0], c[0]);
+    if (c[1]) atomicAdd(&a.counts[1], c[1]);
+    if (c[2]) atomicAdd(&a.counts[2], c[2]);
+    if (FIX && c[3]) atomicAdd(&a.counts[3], c[3]);
+  }
+  LIN_TS(6, 0.f);
+  TRACE_EXIT(a.trace);
+}
+
 __device__ __forceinline__ float bfly8(unsigned mask, float v) {
   v += __shfl_xor_sync(mask, v, 1, 8);
   v += __shfl_xor_sync(mask, v, 2, 8);
@@ -681,15 +1060,53 @@ void launch_make_images(sosba *h, int slot, const float *d_color, const float *d
   }
 }
 
+// SOSBA_LIN_LANES = 8: the round-1 kernels (8 lanes per residual, butterfly-free ordered shuffles); 1, 2, 4: k_linearize_t with
+// that many lanes per residual; unset: 4 lanes below 64k residuals (latency regime), 1 lane above (bandwidth regime)
+static int lin_lanes(int R) {
+  static const int forced = [] { const char *e = getenv("SOSBA_LIN_LANES"); return e ? atoi(e) : 0; }();
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
+  return R < 65536 ? 4 : 1;
+}
+template <bool APPLY, bool WRITE_J, bool FIX>
+static void launch_lin_t(sosba *h, const LinArgs &a, int lanes, bool pdl) {
+  const int blocks = (int)(((long long)a.R * lanes + LIN_T - 1) / LIN_T);
+  auto go = [&](auto kern) {
+    if (pdl) launch_pdl(kern, blocks, LIN_T, 0, h->stream, a);
+    else kern<<<blocks, LIN_T, 0, h->stream>>>(a);
+  };
+  if (lanes == 1) go(k_linearize_t<1, APPLY, WRITE_J, FIX>);
+  else if (lanes == 2) go(k_linearize_t<2, APPLY, WRITE_J, FIX>);
+  else go(k_linearize_t<4, APPLY, WRITE_J, FIX>);
+  h->launches++;
+}
 void launch_linearize(sosba *h, const LinArgs &a) {
   if (a.R == 0) return;
-  const int blocks = (a.R * 8 + 255) / 256;
-  k_linearize<false, true, false><<<blocks, 256, 0, h->stream>>>(a);
-  h->launches++;
+  const int lanes = lin_lanes(a.R);
+  if (lanes == 8) { k_linearize<false, true, false><<<(a.R * 8 + 255) / 256, 256, 0, h->stream>>>(a); h->launches++; }
+  else launch_lin_t<false, true, false>(h, a, lanes, false);
+}
+// linearizeAll(true): linearisation + applyRes(true) + the fixLinearization bookkeeping (FullSystemOptimize.cpp:52-74) in one launch
+void launch_linearize_fix(sosba *h, const LinArgs &a) {
+  if (a.R == 0) return;
+  const int lanes = lin_lanes(a.R);
+  if (lanes == 8) {
+    k_linearize<false, true, false><<<(a.R * 8 + 255) / 256, 256, 0, h->stream>>>(a);
+    k_apply_res<<<(a.R * 8 + 255) / 256, 256, 0, h->stream>>>(a, 1);
+    h->launches += 2;
+    return;
+  }
+  launch_lin_t<true, true, true>(h, a, lanes, false);
 }
 // linearizeAll(false) + setNewFrameEnergyTH + applyRes(true) in one launch (the loop body of FullSystem::optimize)
 void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j, bool th_inline) {
   if (a.R == 0) { if (th_inline) { k_energy_th<<<1, 256, 0, h->stream>>>(a.th, a.gate, 0); h->launches++; } return; }
+  const int lanes = lin_lanes(a.R);
+  if (lanes != 8) {
+    if (write_j) launch_lin_t<true, true, false>(h, a, lanes, true);
+    else launch_lin_t<true, false, false>(h, a, lanes, true);
+    if (th_inline) launch_energy_th(h, a.th, a.gate);   // rare path (no fused accumulation to carry the selection)
+    return;
+  }
   const int blocks = (a.R * 8 + 255) / 256;
   if (write_j) {
     if (th_inline) launch_pdl(k_linearize<true, true, true>, blocks, 256, 0, h->stream, a);

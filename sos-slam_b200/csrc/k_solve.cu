@@ -55,7 +55,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 constexpr int SOLVE_UPD = 256;      // update warps: 16x16 thread grid over the trailing tiles
 constexpr int SOLVE_PAN = 128;      // panel warps: one thread per remaining row
 constexpr int SOLVE_THREADS = SOLVE_UPD + SOLVE_PAN;
-constexpr int BAR_PUB = 1, BAR_LY = 2;   // named barriers (0 is __syncthreads)
+constexpr int BAR_PUB = 1, BAR_LY = 2, BAR_PL = 3;   // named barriers (0 is __syncthreads)
 
 __device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(SOLVE_THREADS) : "memory"); }
 // bar.arrive orders the arriving thread's earlier shared-memory writes before the barrier completes (the PTX ISA's
@@ -86,7 +86,7 @@ __device__ __forceinline__ void update_step(double (&reg)[T][T], const double *_
   }
   if (NA > JP) {
     const double2 y01 = py[0], y23 = py[1];
-    if (dbg) dbg[0] = clock64() + (long long)(y23.y == 123.0);
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64() + (long long)(y23.y == 123.0);
 #pragma unroll
     for (int ia = JP; ia < NA; ia++) {
       const double v = fma(-li[ia][3], y23.y, fma(-li[ia][2], y23.x, fma(-li[ia][1], y01.y, fma(-li[ia][0], y01.x, reg[ia][JP]))));
@@ -94,9 +94,11 @@ __device__ __forceinline__ void update_step(double (&reg)[T][T], const double *_
       if (owner && ty + 16 * (kb + ia) >= k0n + cn) pub[64 * (ia - JP)] = v;   // rows past D are zero tiles landing in the padding
     }
   }
-  if (dbg) dbg[1] = clock64() + (long long)(reg[JP][JP] == 123.0);
+  if (dbg) dbg[threadIdx.x == 0 ? 1 : 4] = clock64() + (long long)(reg[JP][JP] == 123.0);   // [7]: the same moment seen by warp 7
   nb_arrive(BAR_PUB);
-  // the bulk of the rank-4 update runs while the panel warps work on panel p+1
+  // the bulk of the rank-4 update runs while the panel warps work on panel p+1; its shared-memory loads wait until the
+  // panel warps have fetched the new panel (BAR_PL), otherwise those few loads queue behind 64 of ours
+  nb_sync(BAR_PL);
 #pragma unroll
   for (int jb = JP + 1; jb < NA; jb++) {
     const double2 y01 = py[32 * (jb - JP)], y23 = py[32 * (jb - JP) + 1];
@@ -133,11 +135,13 @@ __device__ __forceinline__ void panel_rows(const double *__restrict__ pb, double
   const double2 *pp = (const double2 *)(pb + (size_t)(live ? i : k0) * 4);
   double2 *pl = (double2 *)(Lp + (size_t)i * 4), *py = (double2 *)(Y4 + (size_t)i * 4);
   nb_sync(BAR_PUB);
+  if (dbg) dbg[6] = clock64();   // through the barrier
   const double a00 = pd[0].x;
   const double2 q1 = pd[2], q2a = pd[4], q2b = pd[5], q3a = pd[6], q3b = pd[7];
   const double2 pa = pp[0], pc = pp[1];
   const double a10 = q1.x, a11 = q1.y, a20 = q2a.x, a21 = q2a.y, a22 = q2b.x, a30 = q3a.x, a31 = q3a.y, a32 = q3b.x, a33 = q3b.y;
-  if (dbg) dbg[0] = clock64() + (long long)(a00 == 123.0) + (long long)(pc.y == 123.0);   // panel data landed
+  if (k0 > 0) nb_arrive(BAR_PL);   // our loads are queued: the update warps may start theirs (pairs with the sync in update_step of the panel before)
+  if (dbg) dbg[0] = clock64() + (long long)(a00 == 123.0) + (long long)(pc.y == 123.0);   // panel data landed   // our loads are queued: the update warps may start theirs (pairs with the sync in update_step of panel k0/4 - 1)
   const double r0 = safe_rcp(a00);
   const double l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0, m0 = pa.x * r0;
   const double d1 = fma(-l10, a10, a11), r1 = safe_rcp(d1);
@@ -186,6 +190,50 @@ __device__ __forceinline__ void backsub_segment(double (&w)[W], const double *__
   }
 }
 
+// Back substitution L^T w = z in blocks of 4 rows (one warp; lane l keeps the partially updated rows l, l+32, ...):
+// per block the four finished rows are broadcast, the unit 4x4 triangle is solved redundantly in every lane and the
+// remaining rows take one rank-4 update, so the dependent chain is 4 shuffles + ~4 fma per FOUR rows instead of
+// shuffle + fma per row.  The factor entries of the next block are always in flight.  L[j][i] = M4[off_i + 4 j].
+template <int W>
+__device__ __forceinline__ void backsub_blocked(const double *__restrict__ M4, double *__restrict__ z, const int D, const int PST, const int lane) {
+  double w[W];
+  const double *col[W];   // column (lane + 32 m) of the factor: L[j][i] = col[m][4 j]
+#pragma unroll
+  for (int m = 0; m < W; m++) {
+    const int i = lane + 32 * m;
+    col[m] = M4 + (size_t)(i >> 2) * PST * 4 + (i & 3);
+    w[m] = i < D ? col[m][D * 4] : 0.0;
+  }
+#pragma unroll 1
+  for (int b = (D >> 2) - 1; b >= 0; b--) {
+    const int j0 = 4 * b, mb = j0 >> 5, l0 = j0 & 31;
+    double ws = w[0];
+#pragma unroll
+    for (int m = 1; m < W; m++) ws = mb == m ? w[m] : ws;
+    // the chain: the four finished rows of this block, broadcast ...
+    const double v0 = __shfl_sync(0xffffffffu, ws, l0), v1 = __shfl_sync(0xffffffffu, ws, l0 + 1), v2 = __shfl_sync(0xffffffffu, ws, l0 + 2),
+                 v3 = __shfl_sync(0xffffffffu, ws, l0 + 3);
+    // ... while the factor entries of the block arrive (they do not depend on the chain)
+    const double *d = M4 + ((size_t)b * PST + j0) * 4;   // rows j0..j0+3 of this panel's block: the unit lower 4x4 triangle
+    const double l10 = d[4], l20 = d[8], l21 = d[9], l30 = d[12], l31 = d[13], l32 = d[14];
+    double L[W][4];
+#pragma unroll
+    for (int m = 0; m < W; m++) {
+      const bool on = lane + 32 * m < j0;
+      const double *c = on ? col[m] + j0 * 4 : M4;   // rows at or past the block: any valid address, the value is dropped
+#pragma unroll
+      for (int k = 0; k < 4; k++) { const double t = c[4 * k]; L[m][k] = on ? t : 0.0; }
+    }
+    const double x3 = v3;
+    const double x2 = fma(-l32, x3, v2);
+    const double x1 = fma(-l21, x2, fma(-l31, x3, v1));
+    const double x0 = fma(-l10, x1, fma(-l20, x2, fma(-l30, x3, v0)));
+#pragma unroll
+    for (int m = 0; m < W; m++) w[m] = fma(-L[m][0], x0, fma(-L[m][1], x1, fma(-L[m][2], x2, fma(-L[m][3], x3, w[m]))));
+    if (lane == 0) { *(double2 *)(z + j0) = make_double2(x0, x1); *(double2 *)(z + j0 + 2) = make_double2(x2, x3); }
+  }
+}
+
 template <bool RETARGET>
 __device__ void frame_step_body(const StepArgs &a);
 
@@ -214,7 +262,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
   const int warp = tid >> 5, lane = tid & 31;
   const int ty = tid >> 4, tx = tid & 15;
 #define SOLVE_TS(n) do { if (a.dbg && tid == 0) a.dbg[n] = clock64(); } while (0)
-  PDL_ENTER();
+  PDL_ENTER_T(a.trace);
   if (blockIdx.x == 1) {
     // spare CTA (point shards).  The selection belongs to the linearisation of the previous body, so it runs whenever the
     // loop had not broken BEFORE this launch: body i-1's solve left ctl[1] = i unless the latch was already set (CTA 0 of
@@ -369,10 +417,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
         const int p = 4 * kb + q;
         if (p >= npanels) break;
         if (p + 1 == npanels) { nb_sync(BAR_LY); break; }   // nothing left to update: the rhs row was finished by the panel warps
-        long long *dbg = (a.dbg && tid == 0 && p >= 4 && p < 6) ? a.dbg + 16 + 8 * (p - 4) + 3 : nullptr;
+        long long *dbg = (a.dbg && (tid == 0 || tid == 224) && p >= 4 && p < 6) ? a.dbg + 16 + 8 * (p - 4) + 3 : nullptr;
         UpdateDispatch<T, T>::run(nact, q == 3, reg, M + (size_t)p * PST * 4, Yb + (size_t)(p & 1) * (16 * T) * 4,
                                   pan + (size_t)((p + 1) & 1) * (16 * T) * 4, kb, q, ty, tx, dbg);
-        if (dbg) dbg[2] = clock64() + (long long)(reg[T - 1][T - 1] == 123.0);
+        if (dbg && tid == 0) dbg[2] = clock64() + (long long)(reg[T - 1][T - 1] == 123.0);
       }
       // next 16 columns: tile (a,b) takes over from tile (a+1,b+1)
 #pragma unroll
@@ -396,7 +444,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
   // ---- back substitution L^T w = z in one warp (lane l keeps rows l, l+32, ...), the next row of L always in flight.
   // L[j][i] sits at M4[i >> 2][j][i & 3]; the rhs row D holds z.
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 0 && a.backsub_rowwise == 0) {
+    backsub_blocked<(16 * T + 31) / 32>(M, z, D, PST, lane);
+  } else if (warp == 0) {
     constexpr int W = (16 * T + 31) / 32;
     double w[W];
     int off[W];   // offset of column (lane + 32 m) inside a factor row
@@ -443,6 +493,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
     frame_step_body<false>(a.step);
   }
   SOLVE_TS(8);
+  TRACE_EXIT(a.trace);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,8 +519,11 @@ __device__ void frame_step_body(const StepArgs &a) {
   __shared__ float s_K[4];
   const int nf = a.nf, tid = threadIdx.x;
   const double SC_T = 0.5, SC_R = 1.0, SC_A = 10.0, SC_B = 1000.0, SC_F = 50.0, SC_C = 50.0;
+#define FS_TS(n) do { if (a.trace && tid == 0) a.trace[n] = clock64(); } while (0)
+  FS_TS(0);
   for (int e = tid; e < nf * SOSBA_FS; e += blockDim.x) s_fs[e] = a.fs[e];
   __syncthreads();
+  FS_TS(1);
   if (tid < nf) {
     double *F = s_fs + SOSBA_FS * tid;
     double *G = a.fs + SOSBA_FS * tid;
@@ -525,6 +579,7 @@ __device__ void frame_step_body(const StepArgs &a) {
     a.calib[5] = 1.0f / sf[1];
   }
   __syncthreads();
+  FS_TS(2);
   if (!RETARGET && tid == 64) {  // step norms of doStepFromBackup, float accumulation in frame order
     float sumA = 0, sumB = 0, sumT = 0, sumR = 0;
     for (int f = 0; f < nf; f++) {
@@ -618,6 +673,7 @@ __device__ void frame_step_body(const StepArgs &a) {
     o4[0] = make_float4(sh[0] + st[0], sh[1] + st[1], sh[2] + st[2], sh[3] + st[3]);
     o4[1] = make_float4(sh[4] + st[4], sh[5] + st[5], sh[6] + st[6], sh[7] + st[7]);
   }
+  FS_TS(3);
 }
 
 
@@ -628,9 +684,9 @@ __global__ void __launch_bounds__(256) k_frame_retarget(StepArgs a) { frame_step
 // in the spare last CTA, the frames / calibration / precalc / deltas.  Both only need x from k_solve.
 __global__ void __launch_bounds__(256) k_step(ResubArgs ra, StepArgs sa) {
   __shared__ __align__(16) float s_xad[16 * 16 * 8 + 4];
-  PDL_ENTER();
+  PDL_ENTER_T(ra.trace);
   if (ra.gate && *ra.gate) return;
-  if (blockIdx.x == gridDim.x - 1) { frame_step_body<false>(sa); return; }
+  if (blockIdx.x == gridDim.x - 1) { frame_step_body<false>(sa); if (ra.trace) TRACE_EXIT(ra.trace + 4); return; }   // record + 1: the frame CTA on its own
   // xAd[h*nf+t] = x_h^T adHostF[h+nf*t] + x_t^T adTargetF[h+nf*t] and xc (EnergyFunctional.cpp:509-513): every CTA builds
   // the small table in shared memory (adjoints are L2-resident) instead of waiting for k_solve to do it serially
   {
@@ -652,6 +708,7 @@ __global__ void __launch_bounds__(256) k_step(ResubArgs ra, StepArgs sa) {
     ra.xAd = s_xad;
   }
   resubstitute_body(ra, blockIdx.x, gridDim.x - 1);
+  TRACE_EXIT(ra.trace);
 }
 
 // resubstitute with a caller-provided x: only the xAd part of the kernel above
@@ -705,6 +762,8 @@ static int launch_solve_t(sosba *h, SolveArgs &a) {
 int launch_solve(sosba *h, const SolveArgs &a0) {
   SolveArgs a = a0;
   if ((a.D & 3) || a.D + 1 > 16 * 7) { sosba_set_error("single-CTA solve supports 4 + 8 nf <= 108 (nf <= 13), got D=%d", a.D); return SOSBA_E_ARG; }
+  static const bool rowwise = [] { const char *e = getenv("SOSBA_SOLVE_BACKSUB"); return e && e[0] == 'r'; }();
+  a.backsub_rowwise = rowwise ? 1 : 0;
   int T = (a.D + 1 + 15) / 16;
   if (const char *f = getenv("SOSBA_SOLVE_FORCE_T")) T = std::max(T, atoi(f));   // debug: run a wider instantiation
   if (T <= 3) return launch_solve_t<3>(h, a);

@@ -193,7 +193,7 @@ __device__ __forceinline__ int entry_index(int r, int c) {
 __global__ void __launch_bounds__(XT, 1) k_stitch_xchg(StitchXchgArgs a, Layout L) {
   __shared__ __align__(16) double sm[XS_TOTAL];
   __shared__ __align__(8) unsigned long long mbar;
-  PDL_ENTER();
+  PDL_ENTER_T(a.trace);
   if (a.gate && *a.gate) return;
   const int tid = threadIdx.x, g = tid >> 6, l = tid & 63, i = l >> 3, j = l & 7;
   const int nf = a.nf, D = a.D, bid = blockIdx.x, n2 = nf * nf;
@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(XT, 1) k_stitch_xchg(StitchXchgArgs a, Layout 
   }
   if (!ok && a.err) atomicOr(a.err, 2);   // reported by the caller as SOSBA_E_NCCL (peer exchange timed out)
   if (push) finish_exchange(a, ep);
+  TRACE_EXIT(a.trace);
 }
 
 // The sums of an API-level linearizeAll outside the loop over the ranks (FullSystemOptimize.cpp:125-182: energy, state

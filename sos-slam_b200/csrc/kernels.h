@@ -9,6 +9,18 @@
 // while the current grid drains; every such kernel starts with PDL_ENTER() — let ITS dependents launch early, then wait
 // until the grid it depends on has completed and its memory is visible.  Without the launch attribute both are no-ops.
 #define PDL_ENTER() do { asm volatile("griddepcontrol.launch_dependents;"); asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
+// SOSBA_TRACE=1: device-side timeline of the launches of one sosba_ba_optimize (globaltimer, ns).  Per launch 4 words:
+// [0] first CTA entered, [1] first CTA past the dependency wait, [2] last CTA done.  Null pointer = off (the default).
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PDL_ENTER_T(tr) do { if ((tr) && threadIdx.x == 0) atomicMin((unsigned long long *)(tr), trace_now()); PDL_ENTER(); \
+                             if ((tr) && threadIdx.x == 0) atomicMin((unsigned long long *)(tr) + 1, trace_now()); } while (0)
+#define TRACE_EXIT(tr) do { if ((tr) && threadIdx.x == 0) atomicMax((unsigned long long *)(tr) + 2, trace_now()); } while (0)
+long long *sosba_trace_slot(const char *name);   // sosba_api.cu: next record of the timeline, or nullptr when tracing is off
+
 template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
   cudaLaunchConfig_t cfg = {};
@@ -61,10 +73,13 @@ struct LinArgs {
   const int *gate;    // non-null: skip the launch when *gate != 0 (the loop broke on the device)
   double *zero_buf;   // non-null: zero_n double2 to clear (block tables of the next accumulation)
   int zero_n;
+  long long *trace;       // SOSBA_TRACE record of this launch, or null
+  unsigned opaque_zero;   // always 0; only known at run time (k_linearize_t chains its tap consumers behind the last tap with it)
 };
 
 void launch_make_images(sosba *h, int slot, const float *d_color, const float *d_B);
 void launch_linearize(sosba *h, const LinArgs &a);
+void launch_linearize_fix(sosba *h, const LinArgs &a);   // linearizeAll(true): + applyRes + removal / baseline bookkeeping
 // th_inline: the last CTA runs setNewFrameEnergyTH; otherwise the caller schedules it (spare CTA of the next accumulation)
 void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j, bool th_inline);
 void launch_apply_res(sosba *h, const LinArgs &a, int fix);
@@ -86,6 +101,7 @@ struct StepArgs {
   double *wprior;
   double *iter;          // out: sumA, sumB, sumT, sumR (already / nf)
   double *adHost, *adTarget;   // fp64 adjoints, rewritten by the retarget variant only
+  long long *trace;            // SOSBA_TRACE: 4 clock64 stamps of the frame step (start, states staged, frames done, pairs done), or null
 };
 void launch_frame_retarget(sosba *h, const StepArgs &a);
 
@@ -158,6 +174,7 @@ struct FusedAccArgs {
   ThArgs th;
   const int *gate;
   long long *dbg;      // optional phase timestamps (SOSBA_SOLVE_DEBUG)
+  long long *trace;    // SOSBA_TRACE record of this launch, or null
 };
 bool launch_accumulate_fused(sosba *h, const FusedAccArgs &a, int max_res_per_tile, int tiles_total);
 
@@ -187,6 +204,7 @@ struct StitchXchgArgs {
   int *err;                    // set to 2 when a peer's words did not arrive in time
   unsigned backoff_ns;         // nanosleep between polls of a word that has not arrived (0 = spin)
   long long *dbg;              // optional: globaltimer stamps of one launch (SOSBA_XCHG_DEBUG)
+  long long *trace;            // SOSBA_TRACE record of this launch, or null
 };
 #define SOSBA_XCHG_MAX_NF 13        // k_solve's limit
 #define SOSBA_XCHG_MAX_NEWE 16384   // newest-frame energies per rank a mailbox slot can carry
@@ -226,6 +244,8 @@ struct SolveArgs {
   ThArgs th;
   int do_th;
   int smem_words;              // set by launch_solve: 4-byte words of dynamic shared memory (scratch of the spare CTA)
+  long long *trace;            // SOSBA_TRACE record of this launch, or null
+  int backsub_rowwise;         // set by launch_solve: 1 = row-by-row back substitution (SOSBA_SOLVE_BACKSUB=row), 0 = blocks of 4 rows
 };
 int launch_solve(sosba *h, const SolveArgs &a);
 
@@ -244,6 +264,7 @@ struct ResubArgs {
   double *zero_lin;    // non-null: clear the linearisation sums (2 doubles + 5 ints) for the launch that follows
   float *zero_newE;    // non-null (point shards): clear the newest-frame energy counts (NCCL fallback: all ranks' segments too)
   int zero_newE_n;     // floats + ints to clear, as 4-byte words
+  long long *trace;    // SOSBA_TRACE record of this launch, or null
 };
 void launch_resubstitute(sosba *h, const ResubArgs &a);
 void launch_step(sosba *h, const ResubArgs &ra, const StepArgs &sa);   // resubstitute + frame step, concurrently, one launch

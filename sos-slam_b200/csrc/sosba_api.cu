@@ -32,6 +32,56 @@ int sosba_comm_max_int(sosba *h, int v, int *out);
 static thread_local char g_err[512] = "";
 static long long *g_dbg = nullptr;   // SOSBA_SOLVE_DEBUG: k_solve phase timestamps (clock64), 16 per launch
 static long g_dbg_n = 0;
+// SOSBA_TRACE=1: device-side timeline (globaltimer) of the launches of the last sosba_ba_optimize, printed by sosba_destroy
+static const int TRACE_CAP = 256;
+static long long *g_trace = nullptr;
+static int g_trace_n = 0;
+static const char *g_trace_name[TRACE_CAP];
+static bool trace_on() { static const bool v = getenv("SOSBA_TRACE") != nullptr; return v; }
+long long *sosba_trace_slot(const char *name) {
+  if (!trace_on() || !g_trace || g_trace_n >= TRACE_CAP) return nullptr;
+  g_trace_name[g_trace_n] = name;
+  return g_trace + 4 * (g_trace_n++);
+}
+static void trace_begin(sosba *h) {   // start of a traced sosba_ba_optimize: empty records
+  if (!trace_on()) return;
+  static long long init[4 * TRACE_CAP];
+  if (!g_trace) cudaMalloc(&g_trace, sizeof(init));
+  for (int i = 0; i < TRACE_CAP; i++) { init[4 * i] = init[4 * i + 1] = 0x7fffffffffffffffLL; init[4 * i + 2] = init[4 * i + 3] = 0; }
+  cudaMemcpyAsync(g_trace, init, sizeof(init), cudaMemcpyHostToDevice, h->stream);
+  g_trace_n = 0;
+}
+static void trace_print() {
+  if (!g_trace || g_trace_n == 0) return;
+  std::vector<long long> t(4 * (size_t)TRACE_CAP);
+  cudaMemcpy(t.data(), g_trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  long long t0 = 0x7fffffffffffffffLL;
+  for (int i = 0; i < g_trace_n; i++) if (t[4 * i + 2] && g_trace_name[i][0] != '#' && g_trace_name[i][0] != '%') t0 = std::min(t0, t[4 * i]);
+  fprintf(stderr, "SOSBA_TRACE: launches of the last sosba_ba_optimize, ns from the first entry: [entered, past the dependency wait, done] (done - past wait)\n");
+  long long prev_done = 0;
+  for (int i = 0; i < g_trace_n; i++) {
+    if (!t[4 * i + 2] && g_trace_name[i][0] != '#' && g_trace_name[i][0] != '%') { fprintf(stderr, "  %-28s (not run)\n", g_trace_name[i]); continue; }
+    if (g_trace_name[i][0] == '%') {   // frame step: 4 clock64 stamps
+      fprintf(stderr, "  %-28s cycles: stage states %lld | frames %lld | pairs %lld\n", g_trace_name[i], t[4 * i + 1] - t[4 * i], t[4 * i + 2] - t[4 * i + 1], t[4 * i + 3] - t[4 * i + 2]);
+      continue;
+    }
+    if (g_trace_name[i][0] == '#') {   // raw clock64 stamps: cycles between consecutive phases
+      if (g_trace_name[i][1]) {
+        fprintf(stderr, "  %-28s cycles: ids", g_trace_name[i]);
+        static const char *ph[] = {"geometry+point loads", "projections", "taps+interp", "terms+sums", "records", "lists+stats"};
+        for (int k = 1; k < 7; k++) fprintf(stderr, " | %s %lld", ph[k - 1], t[4 * i + k] - t[4 * i + k - 1]);
+        fprintf(stderr, "\n");
+      }
+      continue;
+    }
+    const bool sub = t[4 * i] == 0x7fffffffffffffffLL;   // a sub-record (exit stamp only)
+    if (sub) { fprintf(stderr, "  %-28s                  done %7lld\n", g_trace_name[i], t[4 * i + 2] - t0); continue; }
+    fprintf(stderr, "  %-28s %7lld %7lld %7lld  (%5lld)  gap after previous done %5lld\n", g_trace_name[i], t[4 * i] - t0, t[4 * i + 1] - t0, t[4 * i + 2] - t0,
+            t[4 * i + 2] - t[4 * i + 1], t[4 * i + 1] - t0 - prev_done);
+    prev_done = t[4 * i + 2] - t0;
+  }
+  g_trace_n = 0;
+}
 static long long *g_xdbg = nullptr;   // SOSBA_XCHG_DEBUG: k_stitch_xchg globaltimer stamps, 8 per launch
 static long g_xdbg_n = 0;
 void sosba_set_error(const char *fmt, ...) {
@@ -91,6 +141,7 @@ struct HostSide {
   float *d_imm_host = nullptr;   // KRKi / Kt / aff per host frame + the 6 status counters
   int imm_host_cap = 0;
   std::vector<int> p_host, res_begin, r_point, r_target, r_host_tmp;
+  std::vector<float> delta_tmp;
   std::vector<void *> allocs;
   int n_lin = 0;
   double *pin_d = nullptr;   // pinned scratch: [4096] doubles
@@ -309,7 +360,7 @@ API void sosba_destroy(sosba_t *h) {
     {  // panels 4..6 of the last launch: [panel start, panel done, update start, update done] relative to panel 4's start
       const long long *q = t.data() + 32 * ((g_dbg_n - 1) % 64) + 16;
       fprintf(stderr, "k_solve look-ahead timeline, panels 4,5: [panel: data landed, chain done, stored | update: L/Y landed, published, rest done] (cycles):");
-      for (int i = 0; i < 16; i++) if ((i & 7) < 6) fprintf(stderr, " %lld%s", q[i] - q[0], (i & 7) == 2 ? " |" : (i & 7) == 5 ? " ||" : "");
+      for (int i = 0; i < 16; i++) fprintf(stderr, " %lld%s", q[i] - q[0], (i & 7) == 2 ? " |" : (i & 7) == 5 ? " | through BAR_PUB, published (warp 7):" : (i & 7) == 7 ? " ||" : "");
       fprintf(stderr, "\n");
     }
     {
@@ -320,6 +371,7 @@ API void sosba_destroy(sosba_t *h) {
     }
     g_dbg_n = 0;
   }
+  trace_print();
   if (g_xdbg && g_xdbg_n > 8) {   // per launch: [0] misc CTA start, [1] its values ready, [2] summed; [3],[4] diagonal tile 0 ready / summed; [5],[6] energies start / done
     std::vector<long long> t(64 * 8);
     cudaMemcpy(t.data(), g_xdbg, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -709,21 +761,39 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
   host.resize(n);
   hs->res_begin.assign(P + 1, 0);
   // one pass: validation, host of every residual, CSR counts, and "no point sees a target twice" (what the fused accumulation needs)
-  std::vector<int> &seen = hs->seen_tmp;
-  seen.assign(nf, -1);
+  // (run by run: the residuals of a point are consecutive, so the host lookup, the CSR count and the duplicate-target test
+  // are per point, and the inner loop only checks the target range)
   bool twice = false;
-  int prev = -1;
-  for (int i = 0; i < n; i++) {
-    const int p = r->point[i], t = r->target[i];
-    if (p < 0 || p < prev || p >= P || t < 0 || t >= nf) { sosba_set_error("residual %d: point %d / target %d invalid or not point-major", i, p, t); return SOSBA_E_ARG; }
-    prev = p;
-    host[i] = hs->p_host[p];
-    if (host[i] < 0 || host[i] >= nf) { sosba_set_error("point %d: host %d invalid", p, host[i]); return SOSBA_E_ARG; }
-    hs->res_begin[p + 1]++;
-    twice |= seen[t] == p;
-    seen[t] = p;
+  {
+    const int32_t *pt = r->point, *tg = r->target;
+    const int *p_host = hs->p_host.data();
+    int *rbeg = hs->res_begin.data();
+    int prev = -1;
+    std::vector<int> &seen = hs->seen_tmp;   // only for windows of more than 64 frames
+    if (nf > 64) seen.assign(nf, -1);
+    for (int i = 0; i < n;) {
+      const int p = pt[i];
+      if (p < 0 || p <= prev || p >= P) {
+        sosba_set_error("residual %d: point %d / target %d invalid or not point-major", i, p, tg[i]);
+        return SOSBA_E_ARG;
+      }
+      prev = p;
+      const int hst = p_host[p];
+      if (hst < 0 || hst >= nf) { sosba_set_error("point %d: host %d invalid", p, hst); return SOSBA_E_ARG; }
+      unsigned long long mask = 0ull;
+      int j = i;
+      for (; j < n && pt[j] == p; j++) {
+        const int t = tg[j];
+        if (t < 0 || t >= nf) { sosba_set_error("residual %d: point %d / target %d invalid or not point-major", j, p, t); return SOSBA_E_ARG; }
+        if (nf <= 64) { const unsigned long long bit = 1ull << t; twice |= (mask & bit) != 0; mask |= bit; }
+        else { twice |= seen[t] == p; seen[t] = p; }
+        host[j] = hst;
+      }
+      rbeg[p + 1] = j - i;
+      i = j;
+    }
+    for (int p = 0; p < P; p++) rbeg[p + 1] += rbeg[p];
   }
-  for (int p = 0; p < P; p++) hs->res_begin[p + 1] += hs->res_begin[p];
   {  // the fused accumulation stages the residuals of up to 32 consecutive points of ONE host and lists them per target
     hs->fused_acc_ok = !twice;
     hs->max_res_per_tile = 0;
@@ -820,7 +890,7 @@ static LinArgs lin_args(sosba *h) {
   a.th.thN = h->cfg.frame_energy_th_n; a.th.thFacMedian = h->cfg.frame_energy_th_fac_median; a.th.thConstWeight = h->cfg.frame_energy_th_const_weight;
   a.th.overallWeight = h->cfg.overall_energy_th_weight; a.th.thOut = h->d_thOut;
   a.ticket = h->d_counts + 12;
-  a.gate = nullptr; a.zero_buf = nullptr; a.zero_n = 0;
+  a.gate = nullptr; a.zero_buf = nullptr; a.zero_n = 0; a.opaque_zero = 0u; a.trace = nullptr;
   return a;
 }
 
@@ -869,8 +939,9 @@ static void enqueue_linearize(sosba *h, int fix) {
   cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(double) + 5 * sizeof(int), h->stream);
   clear_gathered_energies(h);
   LinArgs a = lin_args(h);
-  launch_linearize(h, a);   // (the bench roofline brackets the fused launches of the loop, enqueue_linearize_apply)
-  if (fix) launch_apply_res(h, a, 1);
+  a.trace = sosba_trace_slot("k_linearize (API)");
+  if (fix) launch_linearize_fix(h, a);   // + applyRes(true) + removal / baseline bookkeeping in the same launch
+  else launch_linearize(h, a);          // (the bench roofline brackets the fused launches of the loop, enqueue_linearize_apply)
   exchange_lin(h, 1);   // point shards: global energy, state histogram, removals, newest-frame energies
   launch_energy_th(h, a.th);
   clear_gathered_energies(h);
@@ -1059,6 +1130,7 @@ static int enqueue_blocks(sosba *h, bool nccl_reduce, ThArgs *defer_th = nullptr
     f.maxRelBaseline = h->p_maxRelBaseline; f.adHostF = h->d_adHostF; f.adTargetF = h->d_adTargetF; f.accSC = h->d_accSC;
     f.th = lin_args(h).th; f.gate = hs->gate;
     f.dbg = (g_dbg && getenv("SOSBA_SOLVE_DEBUG")) ? g_dbg + 64 * 32 : nullptr;
+    f.trace = sosba_trace_slot("k_accumulate_fused");
     fused = launch_accumulate_fused(h, f, hs->max_res_per_tile, hs->n_tiles);
     if (fused && f.do_th) hs->th_pending = false;
   }
@@ -1137,7 +1209,7 @@ static ResubArgs resub_args(sosba *h, int do_step) {
   r.HcdA = h->p_HcdA; r.HcdL = h->p_HcdL; r.bdSumF = h->p_bdSumF; r.HdiF = h->p_HdiF; r.step = h->p_step;
   r.do_step = do_step; r.idepth = h->p_idepth; r.idepth_zero = h->p_idepth_zero; r.idepth_backup = h->p_idepth_backup; r.deltaF = h->p_deltaF;
   r.stats = HS(h)->d_rstats + 4 * HS(h)->rstats_par - 1;   // the kernel writes stats[1..3]
-  r.gate = HS(h)->gate; r.zero_lin = nullptr; r.zero_newE = nullptr; r.zero_newE_n = 0;
+  r.gate = HS(h)->gate; r.zero_lin = nullptr; r.zero_newE = nullptr; r.zero_newE_n = 0; r.trace = nullptr;
   return r;
 }
 
@@ -1147,7 +1219,7 @@ static StepArgs step_args(sosba *h) {
   st.nf = h->nf; st.stepfac = 1.0f; st.x = h->d_x; st.fs = hs->d_fs; st.cs = hs->d_cs;
   st.precalc = h->d_precalc; st.adHTdeltaF = h->d_adHTdeltaF; st.calib = h->d_calib;
   st.adHostF = h->d_adHostF; st.adTargetF = h->d_adTargetF; st.wprior = h->d_wprior; st.iter = hs->d_iter;
-  st.adHost = h->d_adHost; st.adTarget = h->d_adTarget;
+  st.adHost = h->d_adHost; st.adTarget = h->d_adTarget; st.trace = nullptr;
   return st;
 }
 
@@ -1172,6 +1244,7 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
     if (!g_xdbg) { cudaMalloc(&g_xdbg, 64 * 8 * sizeof(long long)); cudaMemset(g_xdbg, 0, 64 * 8 * sizeof(long long)); }
     x.dbg = g_xdbg + 8 * (g_xdbg_n++ % 64);
   }
+  x.trace = sosba_trace_slot("k_stitch_xchg");
   if ((rc = launch_stitch_xchg(h, x, h->P))) return rc;
   if (th_deferred) hs->th_pending = false;   // runs in the spare CTA of the solve launch below
   SolveArgs s;
@@ -1181,7 +1254,7 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
   s.HM = d_HM; s.bM = d_bM; s.wprior = h->d_wprior; s.cDeltaF = h->d_calib + 6;
   s.x = h->d_x; s.Hfinal = want_final ? Hpart(h, 3) : nullptr; s.bfinal = want_final ? bpart(h, 3) : nullptr;
   s.adHostF = h->d_adHostF; s.adTargetF = h->d_adTargetF; s.xAd = h->d_xAd; s.status = hs->d_ctl + 2;
-  s.dbg = nullptr;
+  s.dbg = nullptr; s.trace = sosba_trace_slot("k_solve");
   if (do_step) s.xAd = nullptr;   // the step launch builds xAd per CTA
   s.do_step = 0;            // the frame step runs in the spare CTA of the step launch, beside the back-substitution
   s.step = step_args(h);    // (k_solve still reads step.iter: the step norms of the previous body, for the loop latch)
@@ -1205,7 +1278,12 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
         else { ra.zero_newE = h->d_newE_all; ra.zero_newE_n = h->world * h->newE_cap + h->world; }
       }
     }
-    if (do_step) launch_step(h, ra, step_args(h));
+    if (do_step) {
+      StepArgs sa = step_args(h);
+      ra.trace = sosba_trace_slot("k_step (points)");
+      if (ra.trace) { sosba_trace_slot("k_step (frame CTA)"); sa.trace = sosba_trace_slot("%  its phases"); }
+      launch_step(h, ra, sa);
+    }
     else launch_resubstitute(h, ra);
   }
   SOSBA_CUDA(cudaGetLastError());
@@ -1551,13 +1629,17 @@ API int sosba_ba_upload(sosba_t *h, const sosba_ba_problem *prob) {
   const auto t1 = now();
   if ((rc = upload_tables(h, ba, true))) return rc;
   const auto t2 = now();
-  if ((rc = sosba_points_set(h, &prob->points))) return rc;
-  const auto t3 = now();
-  {  // EnergyFunctional::setDeltaF: p->deltaF = idepth - idepth_zero (EnergyFunctional.cpp:187-191)
-    std::vector<float> d(prob->points.n);
-    for (int i = 0; i < prob->points.n; i++) d[i] = prob->points.idepth[i] - prob->points.idepth_zero[i];
-    if ((rc = sosba_points_update(h, nullptr, nullptr, d.data()))) return rc;
+  {  // EnergyFunctional::setDeltaF: p->deltaF = idepth - idepth_zero (EnergyFunctional.cpp:187-191), staged with the other point arrays
+    sosba_points pp = prob->points;
+    std::vector<float> &d = HS(h)->delta_tmp;
+    if (pp.n > 0 && pp.idepth && pp.idepth_zero) {
+      d.resize(pp.n);
+      for (int i = 0; i < pp.n; i++) d[i] = pp.idepth[i] - pp.idepth_zero[i];
+      pp.deltaF = d.data();
+    }
+    if ((rc = sosba_points_set(h, &pp))) return rc;
   }
+  const auto t3 = now();
   if ((rc = sosba_residuals_set(h, &prob->residuals))) return rc;
   if (timing) fprintf(stderr, "ba_upload: host tables %ld us, window %ld us, points %ld us, delta+residuals %ld us\n", us(t0, t1), us(t1, t2), us(t2, t3), us(t3, now()));
   const int D = 4 + 8 * prob->nf;
@@ -1650,6 +1732,8 @@ static void enqueue_linearize_apply(sosba *h, bool zero_tables) {
   LinArgs a = lin_args(h);   // the linearisation sums were cleared by the back-substitution launch of this body
   a.gate = hs->gate;
   if (zero_tables) { a.zero_buf = hs->d_scratch; a.zero_n = (int)(hs->scratch_zero_doubles / 2); }
+  a.trace = sosba_trace_slot("k_linearize (fused apply)");
+  if (a.trace) { sosba_trace_slot("#  phases of its middle CTA"); sosba_trace_slot("#"); }   // 7 clock64 stamps (k_linearize_t: LIN_TS)
   // the selection runs in the spare CTA of the next accumulation, or (point shards) behind the next all-reduce
   const bool th_inline = !hs->fused_acc_ok && !(h->comm && h->world > 1);
   if (hs->prof_on) {
@@ -1786,6 +1870,7 @@ API int sosba_ba_optimize(sosba_t *h, int32_t mnumOptIts, sosba_optimize_out *ou
   if (nf < 3) mnumOptIts = 20;
   if (nf < 4) mnumOptIts = 15;
   // Everything below goes onto the stream without a host round trip; ONE synchronisation at the end reads the results.
+  trace_begin(h);
   launch_reset_oob(h, lin_args(h));
   flush_pending_th(h);
   cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(double) + 5 * sizeof(int), h->stream);

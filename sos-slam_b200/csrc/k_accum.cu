@@ -735,10 +735,10 @@ bool launch_accumulate_fused(sosba *h, const FusedAccArgs &a, int max_res_per_ti
                 (size_t)a.nf * 2 * SC_TP * 2 + 2 * (size_t)max_res;
   smem = (smem + 15) & ~(size_t)15;
   if (smem > 200 * 1024) return false;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static bool configured[64] = {};   // the attribute is per device: one flag per device ordinal (several handles in one process)
+  if (smem > 48 * 1024 && !(h->device >= 0 && h->device < 64 && configured[h->device])) {
     if (cudaFuncSetAttribute(k_accumulate_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return false;
-    configured = 200 * 1024;
+    if (h->device >= 0 && h->device < 64) configured[h->device] = true;
   }
   int workers = tiles_total < 2 * h->sm_count ? tiles_total : 2 * h->sm_count;
   launch_pdl(k_accumulate_fused, workers + (a.do_th ? 1 : 0), ACC_THREADS, smem, h->stream, a, DP, DPAD, ntiles4, tiles_total, max_res, (int)(smem / 4));

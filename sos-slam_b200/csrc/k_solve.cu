@@ -127,6 +127,13 @@ struct UpdateDispatch<T, 0> {
 // retire the rows of this and the previous pivot block from Y4 (they must read as zero columns from now on), thread
 // 8 + r owns row k0 + 4 + r.  L goes to the persistent factor storage Lp ([row][4]; row D = the right-hand side,
 // ending as D^-1 L^-1 P b), Y to Y4; thread 0 also stores L11 into the rows of the pivot block.
+// BLOCK (the default): the 4x4 diagonal block is the pivot as a whole (block LDL^T).  Its inverse comes from the adjugate
+// (2x2 minors -> cofactors -> one reciprocal of the determinant), and the row of the factor is W_i = a_i A11^-1, so the
+// dependent chain of a panel is ~12 fp64 operations and ONE reciprocal instead of four reciprocals in sequence; the
+// rank-4 update is S -= W A21^T with A21 = the published panel itself (no Y rows to store).  The right-hand side row ends
+// as A11^-1 (L^-1 P b)_block, the back substitution sees an identity diagonal block.  A singular block (determinant 0)
+// leaves its four columns alone, like Eigen's pivot_is_valid.
+template <bool BLOCK>
 __device__ __forceinline__ void panel_rows(const double *__restrict__ pb, double *__restrict__ Lp, double *__restrict__ Y4, const int D, const int k0,
                                            const int pt, long long *dbg) {
   const double2 *pd = (const double2 *)(pb + (size_t)k0 * 4);
@@ -142,6 +149,31 @@ __device__ __forceinline__ void panel_rows(const double *__restrict__ pb, double
   const double a10 = q1.x, a11 = q1.y, a20 = q2a.x, a21 = q2a.y, a22 = q2b.x, a30 = q3a.x, a31 = q3a.y, a32 = q3b.x, a33 = q3b.y;
   if (k0 > 0) nb_arrive(BAR_PL);   // our loads are queued: the update warps may start theirs (pairs with the sync in update_step of the panel before)
   if (dbg) dbg[0] = clock64() + (long long)(a00 == 123.0) + (long long)(pc.y == 123.0);   // panel data landed   // our loads are queued: the update warps may start theirs (pairs with the sync in update_step of panel k0/4 - 1)
+  if (BLOCK) {
+    const double s0 = fma(a00, a11, -(a10 * a10)), s1 = fma(a00, a21, -(a10 * a20)), s2 = fma(a00, a31, -(a10 * a30));
+    const double s3 = fma(a10, a21, -(a11 * a20)), s4 = fma(a10, a31, -(a11 * a30)), s5 = fma(a20, a31, -(a21 * a30));
+    const double c5 = fma(a22, a33, -(a32 * a32)), c4 = fma(a21, a33, -(a31 * a32)), c3 = fma(a21, a32, -(a31 * a22));
+    const double c2 = fma(a20, a33, -(a30 * a32)), c1 = fma(a20, a32, -(a30 * a22));
+    const double det = fma(s5, s5, fma(-s4, c1, fma(s3, c2, fma(s2, c3, fma(-s1, c4, s0 * c5)))));   // c0 == s5
+    const double rdet = safe_rcp(det);
+    // adjugate (symmetric): i_rc
+    const double i00 = fma(a31, c3, fma(-a21, c4, a11 * c5)), i01 = fma(-a30, c3, fma(a20, c4, -(a10 * c5)));
+    const double i02 = fma(a33, s3, fma(-a32, s4, a31 * s5)), i03 = fma(-a32, s3, fma(a22, s4, -(a21 * s5)));
+    const double i11 = fma(a30, c1, fma(-a20, c2, a00 * c5)), i12 = fma(-a33, s1, fma(a32, s2, -(a30 * s5)));
+    const double i13 = fma(a32, s1, fma(-a22, s2, a20 * s5)), i22 = fma(a33, s0, fma(-a31, s2, a30 * s4));
+    const double i23 = fma(-a32, s0, fma(a21, s2, -(a20 * s4))), i33 = fma(a22, s0, fma(-a21, s1, a20 * s3));
+    // W_i = (a_i adj) / det
+    const double w0 = fma(pc.y, i03, fma(pc.x, i02, fma(pa.y, i01, pa.x * i00))) * rdet;
+    const double w1 = fma(pc.y, i13, fma(pc.x, i12, fma(pa.y, i11, pa.x * i01))) * rdet;
+    const double w2 = fma(pc.y, i23, fma(pc.x, i22, fma(pa.y, i12, pa.x * i02))) * rdet;
+    const double w3 = fma(pc.y, i33, fma(pc.x, i23, fma(pa.y, i13, pa.x * i03))) * rdet;
+    if (dbg) dbg[1] = clock64() + (long long)(w3 == 123.0);   // chain done
+    if (live) {
+      pl[0] = make_double2(w0, w1);
+      pl[1] = make_double2(w2, w3);
+    }
+    return;
+  }
   const double r0 = safe_rcp(a00);
   const double l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0, m0 = pa.x * r0;
   const double d1 = fma(-l10, a10, a11), r1 = safe_rcp(d1);
@@ -418,7 +450,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
         if (p >= npanels) break;
         if (p + 1 == npanels) { nb_sync(BAR_LY); break; }   // nothing left to update: the rhs row was finished by the panel warps
         long long *dbg = (a.dbg && (tid == 0 || tid == 224) && p >= 4 && p < 6) ? a.dbg + 16 + 8 * (p - 4) + 3 : nullptr;
-        UpdateDispatch<T, T>::run(nact, q == 3, reg, M + (size_t)p * PST * 4, Yb + (size_t)(p & 1) * (16 * T) * 4,
+        // Y operand of the rank-4 update: block pivots -> the published panel itself (A21), else the Y rows of the panel warps
+        // Y operand of the rank-4 update: block pivots -> the published panel itself (A21), else the Y rows of the panel warps
+        UpdateDispatch<T, T>::run(nact, q == 3, reg, M + (size_t)p * PST * 4, (a.block_pivots ? pan : Yb) + (size_t)(p & 1) * (16 * T) * 4,
                                   pan + (size_t)((p + 1) & 1) * (16 * T) * 4, kb, q, ty, tx, dbg);
         if (dbg && tid == 0) dbg[2] = clock64() + (long long)(reg[T - 1][T - 1] == 123.0);
       }
@@ -435,7 +469,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
 #pragma unroll 1
     for (int p = 0; p < npanels; p++) {
       long long *dbg = (a.dbg && pt == 8 && p >= 4 && p < 6) ? a.dbg + 16 + 8 * (p - 4) : nullptr;
-      panel_rows(pan + (size_t)(p & 1) * (16 * T) * 4, M + (size_t)p * PST * 4, Yb + (size_t)(p & 1) * (16 * T) * 4, D, 4 * p, pt, dbg);
+      if (a.block_pivots) panel_rows<true>(pan + (size_t)(p & 1) * (16 * T) * 4, M + (size_t)p * PST * 4, Yb + (size_t)(p & 1) * (16 * T) * 4, D, 4 * p, pt, dbg);
+      else panel_rows<false>(pan + (size_t)(p & 1) * (16 * T) * 4, M + (size_t)p * PST * 4, Yb + (size_t)(p & 1) * (16 * T) * 4, D, 4 * p, pt, dbg);
       if (dbg) dbg[2] = clock64();
       nb_arrive(BAR_LY);
     }
@@ -733,17 +768,20 @@ static size_t solve_smem_base(int D, int T) {   // factor storage, As, six D-vec
 
 template <int T>
 static int launch_solve_t(sosba *h, SolveArgs &a) {
-  static size_t dyn_max = 0;   // per instantiation: opt-in limit minus the kernel's static shared memory
-  if (!dyn_max) {
-    int dev = 0, optin = 0;
+  // per instantiation AND per device (the attribute belongs to the device's copy of the kernel): opt-in limit minus the
+  // kernel's static shared memory
+  static size_t dyn_max_dev[64] = {};
+  const int di = (h->device >= 0 && h->device < 64) ? h->device : 0;
+  if (!dyn_max_dev[di] || di != h->device) {
+    int optin = 0;
     cudaFuncAttributes fa;
-    SOSBA_CUDA(cudaGetDevice(&dev));
-    SOSBA_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    SOSBA_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     SOSBA_CUDA(cudaFuncGetAttributes(&fa, k_solve<T>));
     const size_t lim = (size_t)optin - fa.sharedSizeBytes - 1024;
     SOSBA_CUDA(cudaFuncSetAttribute(k_solve<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
-    dyn_max = lim;
+    dyn_max_dev[di] = lim;
   }
+  const size_t dyn_max = dyn_max_dev[di];
   const int D = a.D;
   // stage accSC (and HM) in shared memory when they fit beside the factor
   size_t smem = solve_smem_base(D, T);
@@ -764,6 +802,8 @@ int launch_solve(sosba *h, const SolveArgs &a0) {
   if ((a.D & 3) || a.D + 1 > 16 * 7) { sosba_set_error("single-CTA solve supports 4 + 8 nf <= 108 (nf <= 13), got D=%d", a.D); return SOSBA_E_ARG; }
   static const bool rowwise = [] { const char *e = getenv("SOSBA_SOLVE_BACKSUB"); return e && e[0] == 'r'; }();
   a.backsub_rowwise = rowwise ? 1 : 0;
+  static const bool scalar_pivots = [] { const char *e = getenv("SOSBA_SOLVE_PIVOTS"); return e && e[0] == 's'; }();   // "scalar": column-by-column LDL^T
+  a.block_pivots = scalar_pivots ? 0 : 1;
   int T = (a.D + 1 + 15) / 16;
   if (const char *f = getenv("SOSBA_SOLVE_FORCE_T")) T = std::max(T, atoi(f));   // debug: run a wider instantiation
   if (T <= 3) return launch_solve_t<3>(h, a);

@@ -395,13 +395,16 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accumulate_fused(FusedAccArgs a
           }
         }
         __syncwarp();
+        ACC_TS2(7);
 #pragma unroll
         for (int l = 0; l < 2; l++) {
           if (cnt[l] == 0) continue;
           LaneAcc A = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 2
           for (int n = 0; n < cnt[l]; n++) lane_accumulate(Rs + (size_t)lst[l * SC_TP + n] * SOSBA_CREC, LE, A);
+          if (a.dbg && blockIdx.x == 0 && tid == 288) a.dbg[8] = clock64() + (long long)(A.q0 == 123.f);
           lane_flush(a.accTop + ((size_t)l * nf * nf + host + t * nf) * SOSBA_TOPB, lane, LE, A, cnt[l]);
+          ACC_TS2(9);
         }
         nA += cnt[0]; nL += cnt[1];
       }

@@ -838,6 +838,20 @@ __global__ void k_reset_oob(LinArgs a) {
   a.r_new_state[r] = SOSBA_RES_OUTLIER; a.r_state[r] = SOSBA_RES_IN;
 }
 
+// members of a freshly uploaded residual that follow from the uploaded ones (PointFrameResidual constructor + resetOOB
+// defaults, Residuals.cpp:62-78): host frame of its point, state_NewEnergy = state_energy, state_NewEnergyWithOutlier = -1,
+// state_NewState = OUTLIER, candidate record selector 0, not dropped
+__global__ void k_residual_init(LinArgs a, const int *__restrict__ p_host) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.R) return;
+  const_cast<int *>(a.r_host)[r] = p_host[a.r_point[r]];
+  a.r_new_energy[r] = a.r_energy[r];
+  a.r_new_energy_wo[r] = -1.f;
+  a.r_new_state[r] = SOSBA_RES_OUTLIER;
+  a.r_sel[r] = 0;
+  a.r_dropped[r] = 0;
+}
+
 __device__ __forceinline__ float dot6(const float *x, const float *y) {
   float s = x[0] * y[0];
   for (int i = 1; i < 6; i++) s += x[i] * y[i];
@@ -1120,6 +1134,11 @@ void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j, bool th_in
 void launch_apply_res(sosba *h, const LinArgs &a, int fix) {
   if (a.R == 0) return;
   k_apply_res<<<(a.R * 8 + 255) / 256, 256, 0, h->stream>>>(a, fix);
+  h->launches++;
+}
+void launch_residual_init(sosba *h, const LinArgs &a, const int *p_host) {
+  if (a.R == 0) return;
+  k_residual_init<<<(a.R + 255) / 256, 256, 0, h->stream>>>(a, p_host);
   h->launches++;
 }
 void launch_reset_oob(sosba *h, const LinArgs &a) {

@@ -84,6 +84,7 @@ void launch_linearize_fix(sosba *h, const LinArgs &a);   // linearizeAll(true): 
 void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j, bool th_inline);
 void launch_apply_res(sosba *h, const LinArgs &a, int fix);
 void launch_reset_oob(sosba *h, const LinArgs &a);
+void launch_residual_init(sosba *h, const LinArgs &a, const int *p_host);   // derived residual members after an upload (sosba_residuals_set)
 void launch_fix_linearization(sosba *h, const LinArgs &a, const int *d_ids, int n);
 // mode 1: linearised residuals (resApprox = res_toZeroF + J*delta), mode 2: marginalisation (res_toZeroF);
 // list==nullptr -> all residuals.  Rewrites the commit record of every selected residual.

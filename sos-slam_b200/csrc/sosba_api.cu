@@ -142,6 +142,7 @@ struct HostSide {
   int imm_host_cap = 0;
   std::vector<int> p_host, res_begin, r_point, r_target, r_host_tmp;
   std::vector<float> delta_tmp;
+  bool r_host_copy = false;   // r_point / r_target mirror the device arrays
   std::vector<void *> allocs;
   int n_lin = 0;
   double *pin_d = nullptr;   // pinned scratch: [4096] doubles
@@ -364,10 +365,10 @@ API void sosba_destroy(sosba_t *h) {
       fprintf(stderr, "\n");
     }
     {
-      long long q[8];
+      long long q[16];
       cudaMemcpy(q, g_dbg + 64 * 32, sizeof(q), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "k_accumulate_fused CTA 0 phase cycles (last launch): setup %lld | top (warp 9) %lld || points (warp 1) %lld | barrier %lld schur %lld flush %lld\n",
-              q[1] - q[0], q[2] - q[1], q[6] - q[1], q[3] - q[6], q[4] - q[3], q[5] - q[4]);
+      fprintf(stderr, "k_accumulate_fused CTA 0 phase cycles (last launch): setup %lld | top (warp 9) %lld [lists %lld, sums %lld, red %lld] || points (warp 1) %lld | barrier %lld schur %lld flush %lld\n",
+              q[1] - q[0], q[2] - q[1], q[7] - q[1], q[8] - q[7], q[9] - q[8], q[6] - q[1], q[3] - q[6], q[4] - q[3], q[5] - q[4]);
     }
     g_dbg_n = 0;
   }
@@ -735,17 +736,22 @@ static int ensure_residuals(sosba *h, int R) {
   h->R_alloc = (int)n;
   return SOSBA_OK;
 }
-// arena of N = round_up(n, 64) residuals: [point|target|host] int, [energy|new_energy|new_energy_wo] float, then 7 byte planes
+// arena of N = round_up(n, 64) residuals.  Uploaded part (16 N bytes, one H2D): [point|target] int, [energy] float, the byte
+// planes [state|is_lin|is_active|is_new]; derived part, filled on the device by k_residual_init: [host] int,
+// [new_energy|new_energy_wo] float, the byte planes [new_state|sel|dropped]
 static void carve_residuals(sosba *h, size_t N) {
   unsigned char *b = HS(h)->r_arena;
-  h->r_point = (int *)b; h->r_target = (int *)(b + 4 * N); h->r_host = (int *)(b + 8 * N);
-  h->r_energy = (float *)(b + 12 * N); h->r_new_energy = (float *)(b + 16 * N); h->r_new_energy_wo = (float *)(b + 20 * N);
-  unsigned char *u = b + 24 * N;
-  h->r_state = u; h->r_is_lin = u + N; h->r_is_active = u + 2 * N; h->r_is_new = u + 3 * N; h->r_new_state = u + 4 * N; h->r_sel = u + 5 * N;
-  h->r_dropped = u + 6 * N;
+  h->r_point = (int *)b; h->r_target = (int *)(b + 4 * N);
+  h->r_energy = (float *)(b + 8 * N);
+  unsigned char *u = b + 12 * N;
+  h->r_state = u; h->r_is_lin = u + N; h->r_is_active = u + 2 * N; h->r_is_new = u + 3 * N;
+  unsigned char *d = b + 16 * N;
+  h->r_host = (int *)d; h->r_new_energy = (float *)(d + 4 * N); h->r_new_energy_wo = (float *)(d + 8 * N);
+  h->r_new_state = d + 12 * N; h->r_sel = d + 13 * N; h->r_dropped = d + 14 * N;
 }
 
 static void clear_gathered_energies(sosba *h);
+static LinArgs lin_args(sosba *h);
 API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
   CHECK_H(h);
   if (!r || r->n < 0 || h->nf <= 0) { sosba_set_error("residuals_set needs window_set/points_set first"); return SOSBA_E_STATE; }
@@ -755,8 +761,7 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
   HostSide *hs = HS(h);
   const int n = r->n, nf = h->nf, P = h->P;
   h->R = n;
-  hs->r_point.assign(r->point, r->point + n);
-  hs->r_target.assign(r->target, r->target + n);
+  hs->r_host_copy = false;   // the host mirror of point / target (marginalisation only) is fetched on demand
   std::vector<int> &host = hs->r_host_tmp;   // scratch vectors live in the handle: no allocation per keyframe
   host.resize(n);
   hs->res_begin.assign(P + 1, 0);
@@ -833,23 +838,24 @@ API int sosba_residuals_set(sosba_t *h, const sosba_residuals *r) {
   }
   hs->n_lin = 0;
   if (n > 0) {
-    const size_t N = ((size_t)n + 63) & ~(size_t)63, bytes = 31 * N;
+    const size_t N = ((size_t)n + 63) & ~(size_t)63, bytes = 16 * N;   // the uploaded half of the arena (carve_residuals)
     carve_residuals(h, N);
     char *blk = nullptr;
     if (bytes <= hs->stage_cap / 2) { if ((rc = stage_reserve(h, bytes, &blk))) return rc; }
     else { hs->big_stage.resize(bytes); blk = hs->big_stage.data(); }
     int *si = (int *)blk;
-    float *sf = (float *)(blk + 12 * N);
-    unsigned char *su = (unsigned char *)blk + 24 * N;
-    memcpy(si, r->point, 4 * (size_t)n); memcpy(si + N, r->target, 4 * (size_t)n); memcpy(si + 2 * N, host.data(), 4 * (size_t)n);
-    if (r->state_energy) { memcpy(sf, r->state_energy, 4 * (size_t)n); memcpy(sf + N, r->state_energy, 4 * (size_t)n); }
-    else memset(sf, 0, 8 * N);
-    for (int i = 0; i < n; i++) sf[2 * N + i] = -1.f;   // state_NewEnergyWithOutlier = -1 until linearised (Residuals.cpp:78)
+    float *sf = (float *)(blk + 8 * N);
+    unsigned char *su = (unsigned char *)blk + 12 * N;
+    memcpy(si, r->point, 4 * (size_t)n); memcpy(si + N, r->target, 4 * (size_t)n);
+    if (r->state_energy) memcpy(sf, r->state_energy, 4 * (size_t)n);
+    else memset(sf, 0, 4 * N);
     auto flag = [&](unsigned char *dst, const uint8_t *src, uint8_t dflt) { if (src) memcpy(dst, src, n); else memset(dst, dflt, n); };
     flag(su, r->state, SOSBA_RES_IN); flag(su + N, r->is_linearized, 0); flag(su + 2 * N, r->is_active, 0); flag(su + 3 * N, r->is_new, 1);
-    memset(su + 4 * N, SOSBA_RES_OUTLIER, N); memset(su + 5 * N, 0, 2 * N);
     SOSBA_CUDA(cudaMemcpyAsync(hs->r_arena, blk, bytes, cudaMemcpyHostToDevice, h->stream));
     if (blk == hs->big_stage.data()) { if ((rc = sync(h))) return rc; }
+    // host of every residual, state_NewEnergy = state_energy, state_NewEnergyWithOutlier = -1 (Residuals.cpp:78), new state
+    // OUTLIER, nothing committed, nothing dropped: derived on the device instead of being staged and copied
+    launch_residual_init(h, lin_args(h), h->p_host);
   }
   if ((rc = up(h, h->p_res_begin, hs->res_begin.data(), P + 1))) return rc;
   if (!hs->fused_acc_ok) {   // only the un-fused accumulation walks the residuals in (host, target)-block order
@@ -1332,6 +1338,12 @@ API int sosba_marginalize_points(sosba_t *h, const int32_t *ids, int32_t n, doub
   HostSide *hs = HS(h);
   const int nf = h->nf, D = 4 + 8 * nf;
   const size_t HB = (size_t)D * D + D;
+  if (!hs->r_host_copy && h->R > 0) {   // host mirror of point / target for the block ordering below (not kept per upload)
+    hs->r_point.resize(h->R); hs->r_target.resize(h->R);
+    int rc0;
+    if ((rc0 = fetch(h, hs->r_point.data(), h->r_point, h->R)) || (rc0 = fetch(h, hs->r_target.data(), h->r_target, h->R)) || (rc0 = sync(h))) return rc0;
+    hs->r_host_copy = true;
+  }
   // residual list of the chosen points, ordered by block
   std::vector<int> rl;
   for (int i = 0; i < n; i++) {

@@ -830,8 +830,12 @@ __global__ void __launch_bounds__(256) k_apply_res(LinArgs a, int fix) {
 }
 
 // PointFrameResidual::resetOOB (Residuals.h:81-86) over activeResiduals (FullSystemOptimize.cpp:316-329)
-__global__ void k_reset_oob(LinArgs a) {
+__global__ void k_reset_oob(LinArgs a, int *zero_words, int n_zero, int *zero_ctl) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0) {
+    if (zero_words && (int)threadIdx.x < n_zero) zero_words[threadIdx.x] = 0;
+    if (zero_ctl && threadIdx.x >= 32 && threadIdx.x < 36) zero_ctl[threadIdx.x - 32] = 0;
+  }
   if (r >= a.R) return;
   if (a.r_is_lin[r] | a.r_dropped[r]) return;
   a.r_new_energy[r] = 0.f; a.r_energy[r] = 0.f;
@@ -1141,9 +1145,9 @@ void launch_residual_init(sosba *h, const LinArgs &a, const int *p_host) {
   k_residual_init<<<(a.R + 255) / 256, 256, 0, h->stream>>>(a, p_host);
   h->launches++;
 }
-void launch_reset_oob(sosba *h, const LinArgs &a) {
-  if (a.R == 0) return;
-  k_reset_oob<<<(a.R + 255) / 256, 256, 0, h->stream>>>(a);
+void launch_reset_oob(sosba *h, const LinArgs &a, int *zero_words, int n_zero, int *zero_ctl) {
+  if (a.R == 0 && !zero_words && !zero_ctl) return;
+  k_reset_oob<<<a.R > 0 ? (a.R + 255) / 256 : 1, 256, 0, h->stream>>>(a, zero_words, n_zero, zero_ctl);
   h->launches++;
 }
 void launch_fix_linearization(sosba *h, const LinArgs &a, const int *d_ids, int n) {

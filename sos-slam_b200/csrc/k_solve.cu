@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
     if (s_stop) return;
   }
   if (tid == 0 && a.res_out) a.res_out[0] = a.res_in[0];
+  if (a.stash_dst && tid >= 32 && tid < 44) a.stash_dst[tid - 32] = a.stash_src[tid - 32];   // sums of the first linearisation (the step launch clears them)
   if (a.zero_rstats && tid < 4) a.zero_rstats[tid] = 0.0;   // the back-substitution sums of this body (k_resubstitute follows)
 
   // ---- stage the inputs in shared memory: one thread issues the bulk copies, everyone waits on the mbarrier ------
@@ -713,7 +714,16 @@ __device__ void frame_step_body(const StepArgs &a) {
 
 
 // the new evaluation point of the newest keyframe at the end of FullSystem::optimize, with all dependent window tables
-__global__ void __launch_bounds__(256) k_frame_retarget(StepArgs a) { frame_step_body<true>(a); }
+__global__ void __launch_bounds__(256) k_frame_retarget(StepArgs a, ThArgs th, int do_th, int *zero_words, int n_zero) {
+  if (blockIdx.x == 1) {   // spare CTA: the pending threshold selection of the last linearisation, then the sums of the next one
+    energy_th_body(th);
+    __syncthreads();
+    if (zero_words && (int)threadIdx.x < n_zero) zero_words[threadIdx.x] = 0;
+    return;
+  }
+  if (!do_th && zero_words && (int)threadIdx.x < n_zero) zero_words[threadIdx.x] = 0;
+  frame_step_body<true>(a);
+}
 
 // The step of one loop body in ONE launch: the points (back-substitution + doStepFromBackup, CTAs 0..n-2) and, concurrently
 // in the spare last CTA, the frames / calibration / precalc / deltas.  Both only need x from k_solve.
@@ -816,8 +826,10 @@ void launch_make_xad(sosba *h, const double *d_x, int nf, const float *adHostF, 
   h->launches++;
 }
 
-void launch_frame_retarget(sosba *h, const StepArgs &a) {
-  k_frame_retarget<<<1, 256, 0, h->stream>>>(a);
+void launch_frame_retarget(sosba *h, const StepArgs &a, const ThArgs *th, int *zero_words, int n_zero) {
+  ThArgs t = {};
+  if (th) t = *th;
+  k_frame_retarget<<<th ? 2 : 1, 256, 0, h->stream>>>(a, t, th ? 1 : 0, zero_words, n_zero);
   h->launches++;
 }
 

@@ -83,7 +83,9 @@ void launch_linearize_fix(sosba *h, const LinArgs &a);   // linearizeAll(true): 
 // th_inline: the last CTA runs setNewFrameEnergyTH; otherwise the caller schedules it (spare CTA of the next accumulation)
 void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j, bool th_inline);
 void launch_apply_res(sosba *h, const LinArgs &a, int fix);
-void launch_reset_oob(sosba *h, const LinArgs &a);
+// zero_words != nullptr: the first block also clears n_zero 4-byte words there (linearisation sums) and 4 ints at zero_ctl
+// (loop control) - the memsets that would otherwise sit on the stream in front of the first linearisation
+void launch_reset_oob(sosba *h, const LinArgs &a, int *zero_words = nullptr, int n_zero = 0, int *zero_ctl = nullptr);
 void launch_residual_init(sosba *h, const LinArgs &a, const int *p_host);   // derived residual members after an upload (sosba_residuals_set)
 void launch_fix_linearization(sosba *h, const LinArgs &a, const int *d_ids, int n);
 // mode 1: linearised residuals (resApprox = res_toZeroF + J*delta), mode 2: marginalisation (res_toZeroF);
@@ -104,7 +106,9 @@ struct StepArgs {
   double *adHost, *adTarget;   // fp64 adjoints, rewritten by the retarget variant only
   long long *trace;            // SOSBA_TRACE: 4 clock64 stamps of the frame step (start, states staged, frames done, pairs done), or null
 };
-void launch_frame_retarget(sosba *h, const StepArgs &a);
+// th != nullptr: a second CTA runs the pending setNewFrameEnergyTH selection beside the retarget and then clears the n_zero
+// 4-byte words at zero_words (the sums of the linearisation that follows); th == nullptr: CTA 0 clears them
+void launch_frame_retarget(sosba *h, const StepArgs &a, const ThArgs *th = nullptr, int *zero_words = nullptr, int n_zero = 0);
 
 // tracker / scale optimizer (calcResPose / calcResScale): writes the 8 warped SoA arrays (masked, not
 // compacted: invalid points carry weight 0) and the sums
@@ -240,6 +244,8 @@ struct SolveArgs {
   const int *res_in;           // resInA of the accumulation this solve consumes ...
   int *res_out;                // ... copied where the table clearing of the next linearisation does not reach
   double *zero_rstats;         // non-null: clear the 4 back-substitution sums the following k_resubstitute accumulates into
+  const double *stash_src;     // non-null (first body of a loop): the sums of the first linearisation ...
+  double *stash_dst;           // ... are kept here (12 doubles) before the step launch clears them
   // point shards: setNewFrameEnergyTH of the previous linearisation (its energies arrived with the all-reduce in front of
   // this launch) runs in a second CTA beside the solve instead of as a launch of its own
   ThArgs th;

@@ -143,6 +143,7 @@ struct HostSide {
   std::vector<int> p_host, res_begin, r_point, r_target, r_host_tmp;
   std::vector<float> delta_tmp;
   bool r_host_copy = false;   // r_point / r_target mirror the device arrays
+  bool stash_pending = false; // the next k_solve keeps the sums of the first linearisation of sosba_ba_optimize
   std::vector<void *> allocs;
   int n_lin = 0;
   double *pin_d = nullptr;   // pinned scratch: [4096] doubles
@@ -940,9 +941,9 @@ static void flush_pending_th(sosba *h) {
 }
 
 // enqueue linearizeAll on the stream (no host sync)
-static void enqueue_linearize(sosba *h, int fix) {
+static void enqueue_linearize(sosba *h, int fix, bool clear_sums = true) {
   flush_pending_th(h);
-  cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(double) + 5 * sizeof(int), h->stream);
+  if (clear_sums) cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(double) + 5 * sizeof(int), h->stream);
   clear_gathered_energies(h);
   LinArgs a = lin_args(h);
   a.trace = sosba_trace_slot("k_linearize (API)");
@@ -1269,6 +1270,8 @@ static int enqueue_solve(sosba *h, const double *d_HM, const double *d_bM, int d
   s.prev_rstats = hs->d_rstats + 4 * (hs->rstats_par ^ 1);
   s.res_in = hs->d_cnt; s.res_out = hs->d_ctl + 3;
   s.zero_rstats = hs->d_rstats + 4 * hs->rstats_par;
+  s.stash_src = nullptr; s.stash_dst = nullptr;
+  if (hs->stash_pending) { s.stash_src = h->d_stats; s.stash_dst = hs->d_stash; hs->stash_pending = false; }
   static const bool solve_debug = getenv("SOSBA_SOLVE_DEBUG") != nullptr;
   if (solve_debug) {   // phase timestamps of the last 64 launches, no host sync: read back and printed by sosba_destroy
     if (!g_dbg) cudaMalloc(&g_dbg, (64 * 32 + 16) * sizeof(long long));
@@ -1883,29 +1886,43 @@ API int sosba_ba_optimize(sosba_t *h, int32_t mnumOptIts, sosba_optimize_out *ou
   if (nf < 4) mnumOptIts = 15;
   // Everything below goes onto the stream without a host round trip; ONE synchronisation at the end reads the results.
   trace_begin(h);
-  launch_reset_oob(h, lin_args(h));
   flush_pending_th(h);
-  cudaMemsetAsync(h->d_stats, 0, 2 * sizeof(double) + 5 * sizeof(int), h->stream);
+  // resetOOB; the same launch clears the linearisation sums (2 doubles + 5 ints) and the loop control words, so no memset
+  // and no copy sits between the launches below (each would break the programmatic launch chain)
+  launch_reset_oob(h, lin_args(h), (int *)h->d_stats, 9, hs->d_ctl);
   clear_gathered_energies(h);
   enqueue_linearize_apply(h, false);   // linearizeAll(false) + applyRes, fused
-  // energy | pad | counts[16] | thOut of the first linearisation: stashed on the device, read at the end
-  cudaMemcpyAsync(hs->d_stash, h->d_stats, 12 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
-  // the whole loop: k_solve of body i latches "converged" from the step norms of body i-1 (doStepFromBackup's canbreak,
+  // energy | pad | counts[16] | thOut of the first linearisation: stashed on the device by the first k_solve, read at the end.
+  // The whole loop: k_solve of body i latches "converged" from the step norms of body i-1 (doStepFromBackup's canbreak,
   // iteration >= setting_minOptIterations) and every later launch returns immediately
-  cudaMemsetAsync(hs->d_ctl, 0, 4 * sizeof(int), h->stream);
   hs->gate = hs->d_ctl;
+  hs->stash_pending = true;
   for (int iteration = 0; iteration < mnumOptIts; iteration++) {
     hs->loop_iter = iteration;
     if ((rc = enqueue_iteration(h))) { hs->gate = nullptr; hs->loop_iter = -1; return rc; }
   }
-  flush_pending_th(h);
+  const bool sharded_loop = h->comm && h->world > 1;
+  if (hs->stash_pending) {   // no loop body ran: keep the sums of the first linearisation with a plain copy
+    cudaMemcpyAsync(hs->d_stash, h->d_stats, 12 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+    hs->stash_pending = false;
+  }
   hs->gate = nullptr; hs->loop_iter = -1;
   hs->tables_clean = false;   // a loop that broke early leaves partial block tables behind
   // new evaluation point for the newest frame (FullSystemOptimize.cpp:415-423) with its adjoints / precalc / deltas, on
-  // the device; then linearizeAll(true)
-  launch_frame_retarget(h, step_args(h));
-  ba->mirror_stale = true;    // the host mirror (ba->st) is refreshed by download_frame_state
-  enqueue_linearize(h, 1);
+  // the device; then linearizeAll(true).  One GPU: the pending threshold selection of the loop's last linearisation runs in
+  // a second CTA of the retarget launch, which also clears the sums of the linearisation that follows.
+  if (!sharded_loop && mnumOptIts > 0) {
+    const ThArgs th = lin_args(h).th;
+    launch_frame_retarget(h, step_args(h), hs->th_pending ? &th : nullptr, (int *)h->d_stats, 9);
+    hs->th_pending = false;
+    ba->mirror_stale = true;
+    enqueue_linearize(h, 1, false);
+  } else {
+    flush_pending_th(h);
+    launch_frame_retarget(h, step_args(h));
+    ba->mirror_stale = true;    // the host mirror (ba->st) is refreshed by download_frame_state
+    enqueue_linearize(h, 1);
+  }
   SOSBA_CUDA(cudaGetLastError());
   const int D = 4 + 8 * nf;
   if ((rc = down(h, hs->pin_i, hs->d_ctl, 4)) || (rc = down(h, hs->pin_d + 16, hs->d_stash, 12)) || (rc = down(h, hs->pin_d + 32, h->d_x, D))) return rc;

@@ -377,36 +377,38 @@ __global__ void __launch_bounds__(ACC_THREADS) k_accumulate_fused(FusedAccArgs a
       phase ^= 1;
     }
     ACC_TS(1);
-    // ---- top blocks: warp w compacts the residuals of target t = w, w+8, ... (a point has at most one) and sums them
+    // ---- top blocks: warp w owns target t = w, w+8, ...  Lane lp looks up the residual of ITS point towards t (a point has
+    // at most one: a scan of its <= nf-1 entries), a vote compacts the hits into lane order = residual order (the tile is
+    // point-major), and the warp sums them: no shared-memory lists, the same deterministic order as the reference's loop.
     if (warp >= 8) {
       int nA = 0, nL = 0;
-      for (int t = warp - 8; t < nf; t += 8) {
-        unsigned short *lst = s_list + (size_t)t * 2 * SC_TP;
-        int cnt[2] = {0, 0};
-        for (int base = 0; base < nres; base += 32) {
-          const int i = base + lane;
-          const int f = i < nres && s_tgt[i] == t ? s_flag[i] : 0;
+      const int lb = lane < np ? s_rb[lane] : 0, le = lane < np ? s_rb[lane + 1] : 0;
+      int deg = le - lb;
 #pragma unroll
-          for (int l = 0; l < 2; l++) {
-            const bool m = (f & 1) && ((f >> 1) == l);
-            const unsigned bal = __ballot_sync(0xffffffffu, m);
-            if (m) lst[l * SC_TP + cnt[l] + __popc(bal & ((1u << lane) - 1))] = (unsigned short)i;
-            cnt[l] += __popc(bal);
-          }
+      for (int o = 16; o > 0; o >>= 1) deg = max(deg, __shfl_xor_sync(0xffffffffu, deg, o));
+      for (int t = warp - 8; t < nf; t += 8) {
+        int idx = 0, f = 0;
+        for (int k = 0; k < deg; k++) {
+          const int i = lb + k;
+          if (i < le && s_tgt[i] == t) { idx = i; f = s_flag[i]; }
         }
-        __syncwarp();
-        ACC_TS2(7);
 #pragma unroll
         for (int l = 0; l < 2; l++) {
-          if (cnt[l] == 0) continue;
+          const bool m = (f & 1) && ((f >> 1) == l);
+          const unsigned bal = __ballot_sync(0xffffffffu, m);
+          const int c = __popc(bal);
+          if (c == 0) continue;
+          // lane j takes the residual of the j-th voting lane
+          const int src = lane < c ? (int)__fns(bal, 0, lane + 1) : 0;
+          const int cidx = __shfl_sync(0xffffffffu, idx, src);
           LaneAcc A = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 2
-          for (int n = 0; n < cnt[l]; n++) lane_accumulate(Rs + (size_t)lst[l * SC_TP + n] * SOSBA_CREC, LE, A);
-          if (a.dbg && blockIdx.x == 0 && tid == 288) a.dbg[8] = clock64() + (long long)(A.q0 == 123.f);
-          lane_flush(a.accTop + ((size_t)l * nf * nf + host + t * nf) * SOSBA_TOPB, lane, LE, A, cnt[l]);
-          ACC_TS2(9);
+#pragma unroll 4
+          for (int n = 0; n < c; n++) lane_accumulate(Rs + (size_t)__shfl_sync(0xffffffffu, cidx, n) * SOSBA_CREC, LE, A);
+          if (l == 0 && a.dbg && blockIdx.x == 0 && tid == 288) a.dbg[8] = clock64() + (long long)(A.q0 == 123.f);
+          lane_flush(a.accTop + ((size_t)l * nf * nf + host + t * nf) * SOSBA_TOPB, lane, LE, A, c);
+          if (l == 0) nA += c; else nL += c;
         }
-        nA += cnt[0]; nL += cnt[1];
+        ACC_TS2(9);
       }
       if (lane == 0) { if (nA) atomicAdd(&s_nacc[0], nA); if (nL) atomicAdd(&s_nacc[1], nL); }
       ACC_TS2(2);

@@ -1079,11 +1079,13 @@ void launch_make_images(sosba *h, int slot, const float *d_color, const float *d
 }
 
 // SOSBA_LIN_LANES = 8: the round-1 kernels (8 lanes per residual, butterfly-free ordered shuffles); 1, 2, 4: k_linearize_t with
-// that many lanes per residual; unset: 4 lanes below 64k residuals (latency regime), 1 lane above (bandwidth regime)
+// that many lanes per residual; unset: 4 lanes below 32k residuals (one partial wave: the launch lasts as long as one
+// thread's chain), 2 lanes above (measured, fused loop launches, us: 13 672 residuals 13.3 / 9.2 / 8.8 for 1 / 2 / 4 lanes
+// in the device timeline; 109 k residuals 38.0 / 32.7 / 43.9; 875 k residuals 235 / 187 / 275)
 static int lin_lanes(int R) {
   static const int forced = [] { const char *e = getenv("SOSBA_LIN_LANES"); return e ? atoi(e) : 0; }();
   if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
-  return R < 65536 ? 4 : 1;
+  return R < 32768 ? 4 : 2;
 }
 template <bool APPLY, bool WRITE_J, bool FIX>
 static void launch_lin_t(sosba *h, const LinArgs &a, int lanes, bool pdl) {

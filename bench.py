@@ -52,6 +52,7 @@ WORKLOADS = {"configB": WORKLOAD,
              "euroc_imu": "EuRoC-shaped 752x480 stereo+IMU, 8-KF window, 2000 active points: visual system on the device, IMU/KKT widening and "
                           "solve on the host with a stand-in IMU Hessian of the reference's shape (BASELINE.json configs[2])"}
 _workload = "configB"
+PROF_EVERY = 4
 
 
 def get_scene(synth, n_points_factor=1):
@@ -527,13 +528,16 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    h.profile_enable(True)
+    h.profile_enable(1)
     l0 = h.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     nres_local = 0
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)           # evict the window from L2 (126 MB) between steps
+        # the per-launch CUDA-event brackets of the roofline kernel ride on every PROF_EVERY-th timed step: a bracket breaks the
+        # programmatic launch chain on both sides of the kernel (about 4 us per launch), which is not part of the product
+        h.profile_enable(2 if k % PROF_EVERY == 0 else 0)
         ev[k][0].record(stream)
         out = h.ba_optimize(ITERS)
         ev[k][1].record(stream)
@@ -542,7 +546,7 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     launches = h.launch_count() - l0
     lin_ms, lin_n = h.profile_read()
-    h.profile_enable(False)
+    h.profile_enable(0)
     step_ms = [a.elapsed_time(b) for a, b in ev]
     tot_ms = sum(step_ms)
     clocks = sampler.stop()
@@ -759,6 +763,24 @@ def main():
                                       and shard_parity["energy_final_rel"] < 1e-3 and dev < 5e-3 and did < 2e-3 and shard_parity["frame_energy_th_rel"] < 1e-3)
         barrier()
 
+    # ---- the same launches inside the programmatic launch chain: device-side timeline (globaltimer stamps in the kernels) ----
+    timeline = None
+    try:
+        h.trace_enable(True)
+        tl = {}
+        for _ in range(3):
+            flush.fill_(7)
+            h.ba_optimize(ITERS)
+            for kname in ("k_linearize", "k_accumulate_fused", "k_stitch_xchg", "k_solve", "k_step (points)"):
+                ns, n = h.trace_read(kname, 1 if kname == "k_linearize" else 0)
+                if n:
+                    tl.setdefault(kname, []).append(ns * 1e-3)
+        h.trace_enable(False)
+        timeline = {k.replace(" (points)", ""): float(np.mean(v)) for k, v in tl.items()}
+    except Exception as e:   # the timeline is a diagnostic, never a reason to lose the bench line
+        timeline = {"error": str(e)}
+    barrier()
+
     # ---- roofline of the dominant kernel (linearize) ---------------------------------------------------
     peak, peak_src = measured_peak()
     R_lin = out["reserved0"]
@@ -774,7 +796,13 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_linearize", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "launch_us": lin_us, "launches_timed": lin_n,
                 "algorithmic_bytes_per_launch": BYTES_LINEARIZE * R_lin,
-                "note": "fused linearize+applyRes launches of the GN loop (6 of the 8 linearisations of a step); 8.4 MB per launch = one partial wave: latency-bound at this size (DESIGN.md section 5; points sweep in profiles/)"}
+                "note": "fused linearize+applyRes launches (7 of the 8 linearisations of a step), CUDA events around each launch on every "
+                        f"{PROF_EVERY}th timed step; the bracket itself costs the launch latency the programmatic launch chain otherwise hides, "
+                        "so in_chain_us (device timeline, first CTA past its dependency wait .. last CTA done) is given next to it; 8.4 MB per "
+                        "launch = one partial wave: latency-bound at this size (DESIGN.md section 5; points sweep in profiles/)"}
+    if timeline and "k_linearize" in timeline:
+        roofline["in_chain_us"] = timeline["k_linearize"]
+        roofline["in_chain_frac"] = BYTES_LINEARIZE * R_lin / (timeline["k_linearize"] * 1e-6) / 1e9 / peak
 
     # ---- CPU baseline (rank 0, bounded sample) ---------------------------------------------------------
     cpu = None
@@ -861,7 +889,7 @@ def main():
                 "shard_parity": shard_parity,
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                                           "ms_per_step": e2e_ms / args.steps},
-                "e2e_raw_frame": e2e_raw, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "other_kernels": other,
+                "e2e_raw_frame": e2e_raw, "gpu_launches": int(launches), "roofline": roofline, "device_timeline_us": timeline, "cpu_baseline": cpu, "other_kernels": other,
                 "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps, "final_rmse": out["rmse"]}
         print(json.dumps(line), flush=True)
     h.close()

@@ -151,9 +151,19 @@ int sosba_synchronize(sosba_t *h);
 /* Number of kernel launches issued by this handle since creation (bench `gpu_launches`). */
 int64_t sosba_launch_count(const sosba_t *h);
 /* CUDA-event bracket around every PointFrameResidual::linearize kernel launch, on its launch stream:
- * enable, run, then read the summed duration and the number of launches (the bench roofline). */
+ * enable, run, then read the summed duration and the number of launches (the bench roofline).
+ * on = 1 starts a new measurement, 0 pauses it, 2 resumes it without dropping what was recorded (a bracket breaks the
+ * programmatic launch chain around the kernel, so the bench samples every few steps instead of all of them). */
 int sosba_profile_enable(sosba_t *h, int32_t on);
 int sosba_profile_read(sosba_t *h, double *ms_total, int32_t *launches);
+/* Device-side timeline of the kernels of the Gauss-Newton loop (globaltimer stamps taken inside the kernels: first CTA
+ * past its dependency wait .. last CTA done), i.e. the duration of a launch as it runs in the programmatic launch chain,
+ * which a CUDA-event bracket cannot see (the event record breaks the chain and adds the launch latency).  Enable, run
+ * sosba_ba_optimize / sosba_optimize, read the mean of the launches whose name starts with `kernel`
+ * ("k_linearize", "k_accumulate_fused", "k_stitch_xchg", "k_solve", "k_step"); process-global; SOSBA_TRACE=1 prints
+ * the whole timeline at sosba_destroy. */
+int sosba_trace_enable(sosba_t *h, int32_t on);
+int sosba_trace_read(sosba_t *h, const char *kernel, int32_t skip_first, double *mean_ns, int32_t *launches);
 /* sosba_frame_make_images with the irradiance image (and B, or NULL) already in device memory. */
 int sosba_frame_make_images_dev(sosba_t *h, int32_t slot, const float *color_dev, const float *B_dev);
 int32_t sosba_pyr_levels(const sosba_t *h);

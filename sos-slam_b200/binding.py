@@ -731,13 +731,23 @@ class Handle:
         self._ck(self.lib.f("ba_optimize")(self.h, C.c_int32(max_iterations), C.byref(out)), "ba_optimize")
         return {n: getattr(out, n) for n, _ in OptimizeOut._fields_ if n != "reserved1"}
 
-    def profile_enable(self, on: bool):
-        self._ck(self.lib.f("profile_enable")(self.h, C.c_int32(1 if on else 0)), "profile_enable")
+    def profile_enable(self, on):
+        """True / 1: start a new measurement, False / 0: pause, 2: resume without dropping the recorded brackets"""
+        self._ck(self.lib.f("profile_enable")(self.h, C.c_int32(int(on))), "profile_enable")
 
     def profile_read(self):
         ms, n = C.c_double(0), C.c_int32(0)
         self._ck(self.lib.f("profile_read")(self.h, C.byref(ms), C.byref(n)), "profile_read")
         return ms.value, n.value
+
+    def trace_enable(self, on: bool):
+        self._ck(self.lib.f("trace_enable")(self.h, C.c_int32(1 if on else 0)), "trace_enable")
+
+    def trace_read(self, kernel: str, skip_first: int = 0):
+        """-> (mean ns of a launch inside the programmatic launch chain, launches) for the kernels whose name starts with `kernel`"""
+        ns, n = C.c_double(0), C.c_int32(0)
+        self._ck(self.lib.f("trace_read")(self.h, kernel.encode(), C.c_int32(skip_first), C.byref(ns), C.byref(n)), "trace_read")
+        return ns.value, n.value
 
     def frame_make_images_dev(self, slot, color_ptr: int, B_ptr: int = 0):
         self._ck(self.lib.f("frame_make_images_dev")(self.h, C.c_int32(slot), C.c_void_p(color_ptr), C.c_void_p(B_ptr or None)), "frame_make_images_dev")

@@ -37,7 +37,8 @@ static const int TRACE_CAP = 256;
 static long long *g_trace = nullptr;
 static int g_trace_n = 0;
 static const char *g_trace_name[TRACE_CAP];
-static bool trace_on() { static const bool v = getenv("SOSBA_TRACE") != nullptr; return v; }
+static bool g_trace_enabled = getenv("SOSBA_TRACE") != nullptr;   // also switched by sosba_trace_enable
+static bool trace_on() { return g_trace_enabled; }
 long long *sosba_trace_slot(const char *name) {
   if (!trace_on() || !g_trace || g_trace_n >= TRACE_CAP) return nullptr;
   g_trace_name[g_trace_n] = name;
@@ -408,8 +409,10 @@ API int sosba_synchronize(sosba_t *h) { CHECK_H(h); return sync(h); }
 API int sosba_profile_enable(sosba_t *h, int32_t on) {
   CHECK_H(h);
   HostSide *hs = HS(h);
-  for (cudaEvent_t e : hs->prof_ev) cudaEventDestroy(e);
-  hs->prof_ev.clear();
+  if (on == 1) {   // 1: start a new measurement; 2: resume (keep what was recorded); 0: pause (sosba_profile_read collects and clears)
+    for (cudaEvent_t e : hs->prof_ev) cudaEventDestroy(e);
+    hs->prof_ev.clear();
+  }
   hs->prof_on = on != 0;
   return SOSBA_OK;
 }
@@ -428,6 +431,40 @@ API int sosba_profile_read(sosba_t *h, double *ms_total, int32_t *launches) {
   if (launches) *launches = (int32_t)(hs->prof_ev.size() / 2);
   for (cudaEvent_t e : hs->prof_ev) cudaEventDestroy(e);
   hs->prof_ev.clear();
+  return SOSBA_OK;
+}
+// device-side timeline (globaltimer stamps inside the kernels of the Gauss-Newton loop) of the next sosba_ba_optimize calls
+API int sosba_trace_enable(sosba_t *h, int32_t on) {
+  CHECK_H(h);
+  int rc = sync(h);
+  if (rc) return rc;
+  g_trace_enabled = on != 0;
+  if (!on) g_trace_n = 0;
+  return SOSBA_OK;
+}
+// mean of (last CTA done - first CTA past its dependency wait), in ns, over the launches of the last traced
+// sosba_ba_optimize whose record name starts with `kernel` ("k_linearize", "k_solve", ...); skip_first leaves out that many
+// leading matches (the first linearisation of a step runs on a cold L2)
+API int sosba_trace_read(sosba_t *h, const char *kernel, int32_t skip_first, double *mean_ns, int32_t *launches) {
+  CHECK_H(h);
+  if (!kernel) return SOSBA_E_ARG;
+  int rc = sync(h);
+  if (rc) return rc;
+  double tot = 0;
+  int n = 0, seen = 0;
+  if (g_trace && g_trace_n > 0) {
+    std::vector<long long> t(4 * (size_t)TRACE_CAP);
+    SOSBA_CUDA(cudaMemcpy(t.data(), g_trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    const size_t len = strlen(kernel);
+    for (int i = 0; i < g_trace_n; i++) {
+      if (strncmp(g_trace_name[i], kernel, len) != 0 || !t[4 * i + 2] || t[4 * i] == 0x7fffffffffffffffLL) continue;
+      if (seen++ < skip_first) continue;
+      tot += (double)(t[4 * i + 2] - t[4 * i + 1]);
+      n++;
+    }
+  }
+  if (mean_ns) *mean_ns = n ? tot / n : 0.0;
+  if (launches) *launches = n;
   return SOSBA_OK;
 }
 API int64_t sosba_launch_count(const sosba_t *h) { return h ? h->launches : 0; }

@@ -920,6 +920,7 @@ __global__ void __launch_bounds__(256) k_prep_records(LinArgs a, int mode, const
 // setNewFrameEnergyTH: energy_th.cuh
 __global__ void __launch_bounds__(1024) k_energy_th(ThArgs a, const int *gate, int cache_words) {
   extern __shared__ unsigned s_cache[];   // lists beyond 8 energies per thread (point shards of many ranks) are staged here
+  PDL_ENTER();
   if (gate && *gate) return;
   energy_th_body(a, s_cache, cache_words);
 }
@@ -1115,7 +1116,7 @@ void launch_linearize_fix(sosba *h, const LinArgs &a) {
     h->launches += 2;
     return;
   }
-  launch_lin_t<true, true, true>(h, a, lanes, false);
+  launch_lin_t<true, true, true>(h, a, lanes, true);
 }
 // linearizeAll(false) + setNewFrameEnergyTH + applyRes(true) in one launch (the loop body of FullSystem::optimize)
 void launch_linearize_apply(sosba *h, const LinArgs &a, bool write_j, bool th_inline) {
@@ -1166,7 +1167,7 @@ void launch_energy_th(sosba *h, const ThArgs &a, const int *gate) {
   // a single rank's list fits the registers (8 per thread); the gathered list of many point shards is staged in shared memory
   const int words = a.nseg > 1 ? 36 * 1024 : 0;
   if (words) cudaFuncSetAttribute(k_energy_th, cudaFuncAttributeMaxDynamicSharedMemorySize, words * 4);   // per device: set on every launch
-  k_energy_th<<<1, 1024, (size_t)words * 4, h->stream>>>(a, gate, words);
+  launch_pdl(k_energy_th, 1, 1024, (size_t)words * 4, h->stream, a, gate, words);
   h->launches++;
 }
 void launch_track_res(sosba *h, const TrackResArgs &a) {

@@ -303,6 +303,22 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
     return;
   }
   SOLVE_TS(0);
+  // ---- stage the inputs in shared memory: one thread issues the bulk copies (first thing, so they overlap the loop-control
+  // check below), everyone waits on the mbarrier -----------------------------------------------------------------
+  const double *Hsrc = M, *Ssrc = a.accSC, *HMsrc = a.HM;
+  const unsigned bytesH = (unsigned)((size_t)D * D * 8), bytesS = (unsigned)((((size_t)DP * DP + 1) & ~(size_t)1) * 8);
+  double *Ss = stage, *Hm = stage + (bytesS >> 3);
+  if (a.stage_sc) Ssrc = Ss;
+  if (a.HM && a.stage_hm) HMsrc = Hm;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const unsigned total = bytesH + (a.stage_sc ? bytesS : 0u) + ((a.HM && a.stage_hm) ? bytesH : 0u);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(total) : "memory");
+    bulk_g2s(M, a.Htop, bytesH, &mbar);
+    if (a.stage_sc) bulk_g2s(Ss, a.accSC, bytesS, &mbar);
+    if (a.HM && a.stage_hm) bulk_g2s(Hm, a.HM, bytesH, &mbar);
+  }
   if (a.ctl) {   // did the previous loop body converge?  (doStepFromBackup's return value, FullSystemOptimize.cpp:238-256)
     __shared__ int s_stop;
     if (tid == 0) {
@@ -320,27 +336,17 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
       s_stop = stop;
     }
     __syncthreads();
-    if (s_stop) return;
+    if (s_stop) {   // the copies into this CTA's shared memory must land before it exits
+      unsigned done = 0;
+      while (!done)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
+      return;
+    }
   }
   if (tid == 0 && a.res_out) a.res_out[0] = a.res_in[0];
   if (a.stash_dst && tid >= 32 && tid < 44) a.stash_dst[tid - 32] = a.stash_src[tid - 32];   // sums of the first linearisation (the step launch clears them)
   if (a.zero_rstats && tid < 4) a.zero_rstats[tid] = 0.0;   // the back-substitution sums of this body (k_resubstitute follows)
 
-  // ---- stage the inputs in shared memory: one thread issues the bulk copies, everyone waits on the mbarrier ------
-  const double *Hsrc = M, *Ssrc = a.accSC, *HMsrc = a.HM;
-  const unsigned bytesH = (unsigned)((size_t)D * D * 8), bytesS = (unsigned)((((size_t)DP * DP + 1) & ~(size_t)1) * 8);
-  double *Ss = stage, *Hm = stage + (bytesS >> 3);
-  if (a.stage_sc) Ssrc = Ss;
-  if (a.HM && a.stage_hm) HMsrc = Hm;
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const unsigned total = bytesH + (a.stage_sc ? bytesS : 0u) + ((a.HM && a.stage_hm) ? bytesH : 0u);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(total) : "memory");
-    bulk_g2s(M, a.Htop, bytesH, &mbar);
-    if (a.stage_sc) bulk_g2s(Ss, a.accSC, bytesS, &mbar);
-    if (a.HM && a.stage_hm) bulk_g2s(Hm, a.HM, bytesH, &mbar);
-  }
   for (int i = tid; i < 4 * (16 * T) * 4; i += SOLVE_THREADS) pan[i] = 0.0;   // panel + Y buffers: rows past D must read as zero
   for (int i = tid; i < D; i += SOLVE_THREADS) delta[i] = i < 4 ? (double)a.cDeltaF[i] : fdelta[i - 4];
   double pr = 0.0, dpr = 0.0, bt = 0.0, bm = 0.0;   // per-row inputs that stay in global memory: fetch them under the copies
@@ -715,6 +721,7 @@ __device__ void frame_step_body(const StepArgs &a) {
 
 // the new evaluation point of the newest keyframe at the end of FullSystem::optimize, with all dependent window tables
 __global__ void __launch_bounds__(256) k_frame_retarget(StepArgs a, ThArgs th, int do_th, int *zero_words, int n_zero) {
+  PDL_ENTER();
   if (blockIdx.x == 1) {   // spare CTA: the pending threshold selection of the last linearisation, then the sums of the next one
     energy_th_body(th);
     __syncthreads();
@@ -829,7 +836,7 @@ void launch_make_xad(sosba *h, const double *d_x, int nf, const float *adHostF, 
 void launch_frame_retarget(sosba *h, const StepArgs &a, const ThArgs *th, int *zero_words, int n_zero) {
   ThArgs t = {};
   if (th) t = *th;
-  k_frame_retarget<<<th ? 2 : 1, 256, 0, h->stream>>>(a, t, th ? 1 : 0, zero_words, n_zero);
+  launch_pdl(k_frame_retarget, th ? 2 : 1, 256, 0, h->stream, a, t, th ? 1 : 0, zero_words, n_zero);
   h->launches++;
 }
 

@@ -403,7 +403,16 @@ API void sosba_destroy(sosba_t *h) {
   delete h;
 }
 
-API int sosba_set_stream(sosba_t *h, void *s) { CHECK_H(h); h->stream = s ? (cudaStream_t)s : h->own_stream; return SOSBA_OK; }
+API int sosba_set_stream(sosba_t *h, void *s) {
+  CHECK_H(h);
+  cudaStream_t ns = s ? (cudaStream_t)s : h->own_stream;
+  if (ns != h->stream) {   // copies queued on the old stream still read the staging ring: let them finish before the ring is reused from the new one
+    int rc = sync(h);
+    if (rc) return rc;
+    h->stream = ns;
+  }
+  return SOSBA_OK;
+}
 API int sosba_synchronize(sosba_t *h) { CHECK_H(h); return sync(h); }
 // CUDA-event timing of the dominant kernel (linearize) on its launch stream, for the bench roofline.
 API int sosba_profile_enable(sosba_t *h, int32_t on) {
@@ -602,6 +611,7 @@ static WinLayout win_layout(int nf) {
 static int ensure_window(sosba *h, int nf) {
   if (nf <= h->nf_alloc) return SOSBA_OK;
   HostSide *hs = HS(h);
+  h->nf_alloc = 0;   // (see ensure_residuals)
   dfree(h, hs->w_arena);
   dfree(h, h->d_x); dfree(h, h->d_xAd);
   dfree(h, hs->d_scratch); h->d_accTop = h->d_accSC = h->d_H = nullptr;
@@ -691,6 +701,7 @@ API int sosba_window_update(sosba_t *h, const sosba_window *w) { CHECK_H(h); if 
 static int ensure_points(sosba *h, int P) {
   if (P <= h->P_alloc) return SOSBA_OK;
   HostSide *hs = HS(h);
+  h->P_alloc = 0;   // (see ensure_residuals)
   dfree(h, hs->p_arena); dfree(h, hs->p_zero_arena);
   const size_t n = ((size_t)P + (size_t)P / 4 + 64 + 63) & ~(size_t)63;
   // the uploaded members of the points live in ONE arena in the order points_set stages them (carve_points): one H2D
@@ -763,6 +774,7 @@ API int sosba_points_update(sosba_t *h, const float *idepth, const float *idepth
 static int ensure_residuals(sosba *h, int R) {
   if (R <= h->R_alloc) return SOSBA_OK;
   HostSide *hs = HS(h);
+  h->R_alloc = 0;   // an allocation failure below must not leave the old capacity standing over freed buffers
   dfree(h, hs->r_arena); dfree(h, h->r_by_block);
   dfree(h, h->r_J[0]); dfree(h, h->r_J[1]); dfree(h, h->r_rec); dfree(h, h->r_rtz); dfree(h, h->r_proj); dfree(h, h->r_center); dfree(h, h->d_newE);
   const size_t n = ((size_t)R + (size_t)R / 4 + 64 + 63) & ~(size_t)63;

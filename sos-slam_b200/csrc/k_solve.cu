@@ -56,6 +56,7 @@ constexpr int SOLVE_UPD = 256;      // update warps: 16x16 thread grid over the 
 constexpr int SOLVE_PAN = 128;      // panel warps: one thread per remaining row
 constexpr int SOLVE_THREADS = SOLVE_UPD + SOLVE_PAN;
 constexpr int BAR_PUB = 1, BAR_LY = 2, BAR_PL = 3;   // named barriers (0 is __syncthreads)
+constexpr int BAR_PN = 3;   // pipelined factorisation: the panel warps among themselves (BAR_PL is not used there)
 
 __device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(SOLVE_THREADS) : "memory"); }
 // bar.arrive orders the arriving thread's earlier shared-memory writes before the barrier completes (the PTX ISA's
@@ -200,6 +201,149 @@ __device__ __forceinline__ void panel_rows(const double *__restrict__ pb, double
   }
 }
 
+// ---- pipelined factorisation (experimental, SOSBA_SOLVE_PIPE=1; parity-green, not faster: see launch_solve) ------------------
+// The panel warps keep a sliding window of their row in registers: the current pivot group of 4 columns, the next one, and the
+// one after that as it arrives.  A panel step is then entirely theirs: exchange the current columns of all rows through shared
+// memory (a barrier among the 4 panel warps only), invert the 4x4 pivot block (adjugate, one reciprocal), form W_i, apply it to
+// their own next two groups, go on.  The update warps follow one step behind: with W_p they update the register tiles of the
+// trailing matrix and hand over column group p + 3 — which the panel warps need only one step later, so the hand-off of the old
+// scheme (publish -> barrier -> factor -> barrier -> update, 1.7 k cycles per panel around a 0.4 k chain) is off the critical path.
+//   pan4[p & 3][row][4]   current columns of every row at step p (written by the panel warps; the Y operand of the update warps)
+//   hand[p & 1][row][4]   column group p + 3, updated through panel p (written by the update warps in their step p)
+//   BAR_PN  panel warps only;  BAR_LY  W_p and pan4[p & 3] ready (panel -> update);  BAR_PUB  hand[p & 1] ready (update -> panel;
+//           the first one says "factor storage zeroed")
+template <int T, int NA, bool LATE>
+__device__ __forceinline__ void update_step_pipe(double (&reg)[T][T], const double *__restrict__ Lp, const double *__restrict__ Y4, double *__restrict__ hand,
+                                                 const int kb, const int q, const int ty, const int tx) {
+  constexpr int JP = LATE ? 1 : 0;          // tile column of group p + 3 (q = 0: columns 12..15 of tile column 0; q >= 1: tile column 1)
+  const int off = (4 * q + 12) & 15;        // first column of the group inside its tile column
+  const int k0n = 16 * kb + 4 * q + 12;     // ... and in the matrix
+  const int cn = tx - off;
+  const bool owner = cn >= 0 && cn < 4;
+  const double2 *pl = (const double2 *)(Lp + (size_t)(ty + 16 * (kb + JP)) * 4);
+  const double2 *py = (const double2 *)(Y4 + (size_t)(tx + 16 * (kb + JP)) * 4);
+  double *pub = hand + (size_t)(ty + 16 * (kb + JP)) * 4 + cn;
+  nb_sync(BAR_LY);
+  double li[NA][4];
+#pragma unroll
+  for (int ia = JP; ia < NA; ia++) {
+    const double2 l01 = pl[32 * (ia - JP)], l23 = pl[32 * (ia - JP) + 1];
+    li[ia][0] = l01.x; li[ia][1] = l01.y; li[ia][2] = l23.x; li[ia][3] = l23.y;
+  }
+  if (NA > JP) {
+    const double2 y01 = py[0], y23 = py[1];
+#pragma unroll
+    for (int ia = JP; ia < NA; ia++) {
+      const double v = fma(-li[ia][3], y23.y, fma(-li[ia][2], y23.x, fma(-li[ia][1], y01.y, fma(-li[ia][0], y01.x, reg[ia][JP]))));
+      reg[ia][JP] = v;
+      if (owner && ty + 16 * (kb + ia) >= k0n + cn) pub[64 * (ia - JP)] = v;
+    }
+  }
+  nb_arrive(BAR_PUB);
+#pragma unroll
+  for (int jb = JP + 1; jb < NA; jb++) {
+    const double2 y01 = py[32 * (jb - JP)], y23 = py[32 * (jb - JP) + 1];
+#pragma unroll
+    for (int ia = jb; ia < NA; ia++)
+      reg[ia][jb] = fma(-li[ia][3], y23.y, fma(-li[ia][2], y23.x, fma(-li[ia][1], y01.y, fma(-li[ia][0], y01.x, reg[ia][jb]))));
+  }
+}
+template <int T, int NA>
+struct UpdatePipeDispatch {
+  static __device__ __forceinline__ void run(int nact, bool late, double (&reg)[T][T], const double *Lp, const double *Y4, double *hand, int kb, int q, int ty, int tx) {
+    if (nact == NA) {
+      if (late) update_step_pipe<T, NA, true>(reg, Lp, Y4, hand, kb, q, ty, tx);
+      else update_step_pipe<T, NA, false>(reg, Lp, Y4, hand, kb, q, ty, tx);
+    } else UpdatePipeDispatch<T, NA - 1>::run(nact, late, reg, Lp, Y4, hand, kb, q, ty, tx);
+  }
+};
+template <int T>
+struct UpdatePipeDispatch<T, 0> {
+  static __device__ __forceinline__ void run(int, bool, double (&)[T][T], const double *, const double *, double *, int, int, int, int) {}
+};
+
+// the panel warps of the pipelined factorisation: thread pt owns row pt for the whole factorisation (row D = right-hand side)
+template <int T>
+__device__ __forceinline__ void panel_pipeline(const double *__restrict__ As, double *__restrict__ M, double *__restrict__ pan4, const double *__restrict__ hand,
+                                               const int D, const int PST, const int pt, const int npanels, long long *dbg_base) {
+  const int i = pt;
+  const bool mine = i <= D;
+  double cur[4], nxt[4], nx2[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    cur[c] = (mine && c <= i && c < D) ? As[(size_t)i * D + c] : 0.0;
+    nxt[c] = (mine && 4 + c <= i && 4 + c < D) ? As[(size_t)i * D + 4 + c] : 0.0;
+    nx2[c] = (mine && 8 + c <= i && 8 + c < D) ? As[(size_t)i * D + 8 + c] : 0.0;
+  }
+#pragma unroll 1
+  for (int p = 0; p < npanels; p++) {
+    const int k0 = 4 * p;
+    long long *dbg = (dbg_base && pt == 8 && p >= 4 && p < 6) ? dbg_base + 16 + 8 * (p - 4) : nullptr;
+    double *pb = pan4 + (size_t)(p & 3) * (16 * T) * 4;
+    if (mine) {
+      *(double2 *)(pb + (size_t)i * 4) = make_double2(cur[0], cur[1]);
+      *(double2 *)(pb + (size_t)i * 4 + 2) = make_double2(cur[2], cur[3]);
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(BAR_PN), "r"(SOLVE_PAN) : "memory");
+    const double2 *pd = (const double2 *)(pb + (size_t)k0 * 4);
+    const double a00 = pd[0].x;
+    const double2 q1 = pd[2], q2a = pd[4], q2b = pd[5], q3a = pd[6], q3b = pd[7];
+    const double a10 = q1.x, a11 = q1.y, a20 = q2a.x, a21 = q2a.y, a22 = q2b.x, a30 = q3a.x, a31 = q3a.y, a32 = q3b.x, a33 = q3b.y;
+    if (dbg) dbg[0] = clock64() + (long long)(a00 == 123.0) + (long long)(a33 == 123.0);   // pivot block landed
+    const double s0 = fma(a00, a11, -(a10 * a10)), s1 = fma(a00, a21, -(a10 * a20)), s2 = fma(a00, a31, -(a10 * a30));
+    const double s3 = fma(a10, a21, -(a11 * a20)), s4 = fma(a10, a31, -(a11 * a30)), s5 = fma(a20, a31, -(a21 * a30));
+    const double c5 = fma(a22, a33, -(a32 * a32)), c4 = fma(a21, a33, -(a31 * a32)), c3 = fma(a21, a32, -(a31 * a22));
+    const double c2 = fma(a20, a33, -(a30 * a32)), c1 = fma(a20, a32, -(a30 * a22));
+    const double det = fma(s5, s5, fma(-s4, c1, fma(s3, c2, fma(s2, c3, fma(-s1, c4, s0 * c5)))));   // c0 == s5
+    const double rdet = (mine && i >= k0 + 4) ? safe_rcp(det) : 0.0;   // pivot rows and finished rows take no part
+    const double i00 = fma(a31, c3, fma(-a21, c4, a11 * c5)), i01 = fma(-a30, c3, fma(a20, c4, -(a10 * c5)));
+    const double i02 = fma(a33, s3, fma(-a32, s4, a31 * s5)), i03 = fma(-a32, s3, fma(a22, s4, -(a21 * s5)));
+    const double i11 = fma(a30, c1, fma(-a20, c2, a00 * c5)), i12 = fma(-a33, s1, fma(a32, s2, -(a30 * s5)));
+    const double i13 = fma(a32, s1, fma(-a22, s2, a20 * s5)), i22 = fma(a33, s0, fma(-a31, s2, a30 * s4));
+    const double i23 = fma(-a32, s0, fma(a21, s2, -(a20 * s4))), i33 = fma(a22, s0, fma(-a21, s1, a20 * s3));
+    double w0 = fma(cur[3], i03, fma(cur[2], i02, fma(cur[1], i01, cur[0] * i00))) * rdet;
+    double w1 = fma(cur[3], i13, fma(cur[2], i12, fma(cur[1], i11, cur[0] * i01))) * rdet;
+    double w2 = fma(cur[3], i23, fma(cur[2], i22, fma(cur[1], i12, cur[0] * i02))) * rdet;
+    double w3 = fma(cur[3], i33, fma(cur[2], i23, fma(cur[1], i13, cur[0] * i03))) * rdet;
+    if (!(mine && i >= k0 + 4)) w0 = w1 = w2 = w3 = 0.0;   // (0 * inf of a dead row would be NaN)
+    if (dbg) dbg[1] = clock64() + (long long)(w3 == 123.0);   // chain done
+    // p = 0: the update warps have zeroed the factor storage; p >= 1: their step p - 1 has handed over column group p + 2.
+    // Taken BEFORE this step's BAR_LY arrival on purpose: it proves that every update warp has passed BAR_LY of step p - 1, so
+    // two arrivals of ours can never pile up on that barrier (a named barrier completes as soon as its count is reached).
+    nb_sync(BAR_PUB);
+    if (mine && i >= k0 + 4) {
+      double2 *pl = (double2 *)(M + (size_t)p * PST * 4 + (size_t)i * 4);
+      pl[0] = make_double2(w0, w1);
+      pl[1] = make_double2(w2, w3);
+    }
+    if (dbg) dbg[2] = clock64();
+    nb_arrive(BAR_LY);
+    if (p + 1 < npanels) {   // my next group: columns k0+4 .. k0+7, rows of those columns = A21 of this panel
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const double2 r01 = *(const double2 *)(pb + (size_t)(k0 + 4 + c) * 4), r23 = *(const double2 *)(pb + (size_t)(k0 + 4 + c) * 4 + 2);
+        nxt[c] = fma(-w3, r23.y, fma(-w2, r23.x, fma(-w1, r01.y, fma(-w0, r01.x, nxt[c]))));
+      }
+    }
+    if (p >= 1) {   // column group p + 2 as the update warps left it after panel p - 1
+      if (mine) {
+        const double2 h01 = *(const double2 *)(hand + (size_t)((p - 1) & 1) * (16 * T) * 4 + (size_t)i * 4),
+                      h23 = *(const double2 *)(hand + (size_t)((p - 1) & 1) * (16 * T) * 4 + (size_t)i * 4 + 2);
+        nx2[0] = h01.x; nx2[1] = h01.y; nx2[2] = h23.x; nx2[3] = h23.y;
+      }
+    }
+    if (p + 2 < npanels) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const double2 r01 = *(const double2 *)(pb + (size_t)(k0 + 8 + c) * 4), r23 = *(const double2 *)(pb + (size_t)(k0 + 8 + c) * 4 + 2);
+        nx2[c] = fma(-w3, r23.y, fma(-w2, r23.x, fma(-w1, r01.y, fma(-w0, r01.x, nx2[c]))));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) { cur[c] = nxt[c]; nxt[c] = nx2[c]; }
+  }
+}
+
 // Back substitution L^T w = z, rows jhi..jlo (descending), all inside lane-register block MT (j >> 5 == MT): the step
 // chain is shuffle (w_j) -> fma; the factor row of the next step is always in flight.  L[j][i] = M4[off_i + 4 j].
 template <int W, int MT>
@@ -284,8 +428,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
   double *key = delta + D;                 // [D]
   double *z = key + D;                     // [D]
   double *pan = z + D;                     // [2][16T*4] panel, double buffered, rows past D stay zero
-  double *Yb = pan + 2 * (size_t)(16 * T) * 4;   // [2][16T*4] Y rows of the current panel, double buffered
-  double *stage = Yb + 2 * (size_t)(16 * T) * 4; // optional: accSC [(D+1)^2 (+1)], then HM [D*D]
+  double *Yb = pan + 2 * (size_t)(16 * T) * 4;   // [2][16T*4] Y rows of the current panel, double buffered (pipelined scheme: pan[2..3])
+  double *hand = Yb + 2 * (size_t)(16 * T) * 4;  // [2][16T*4] pipelined scheme: column group p + 3 on its way to the panel warps
+  double *stage = hand + 2 * (size_t)(16 * T) * 4; // optional: accSC [(D+1)^2 (+1)], then HM [D*D]
   __shared__ int perm[144];
   __shared__ __align__(8) unsigned long long mbar;
   const double lambda = 1e-5;                               // EnergyFunctional.cpp:1031
@@ -347,7 +492,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
   if (a.stash_dst && tid >= 32 && tid < 44) a.stash_dst[tid - 32] = a.stash_src[tid - 32];   // sums of the first linearisation (the step launch clears them)
   if (a.zero_rstats && tid < 4) a.zero_rstats[tid] = 0.0;   // the back-substitution sums of this body (k_resubstitute follows)
 
-  for (int i = tid; i < 4 * (16 * T) * 4; i += SOLVE_THREADS) pan[i] = 0.0;   // panel + Y buffers: rows past D must read as zero
+  for (int i = tid; i < 6 * (16 * T) * 4; i += SOLVE_THREADS) pan[i] = 0.0;   // panel + Y + hand-over buffers: rows past D must read as zero
   for (int i = tid; i < D; i += SOLVE_THREADS) delta[i] = i < 4 ? (double)a.cDeltaF[i] : fdelta[i - 4];
   double pr = 0.0, dpr = 0.0, bt = 0.0, bm = 0.0;   // per-row inputs that stay in global memory: fetch them under the copies
   if (tid < D) {
@@ -439,7 +584,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
         const int i = ty + 16 * ia, j = tx + 16 * jb;
         reg[ia][jb] = (jb <= ia && i <= D && j < D && j <= i) ? As[i * D + j] : 0.0;
       }
-    if (tx < 4) {
+    if (!a.pipe && tx < 4) {
 #pragma unroll
       for (int ia = 0; ia < T; ia++) {
         const int i = ty + 16 * ia;
@@ -457,7 +602,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
         if (p >= npanels) break;
         if (p + 1 == npanels) { nb_sync(BAR_LY); break; }   // nothing left to update: the rhs row was finished by the panel warps
         long long *dbg = (a.dbg && (tid == 0 || tid == 224) && p >= 4 && p < 6) ? a.dbg + 16 + 8 * (p - 4) + 3 : nullptr;
-        // Y operand of the rank-4 update: block pivots -> the published panel itself (A21), else the Y rows of the panel warps
+        if (a.pipe) {
+          if (dbg && tid == 0) dbg[0] = clock64();
+          UpdatePipeDispatch<T, T>::run(nact, q >= 1, reg, M + (size_t)p * PST * 4, pan + (size_t)(p & 3) * (16 * T) * 4, hand + (size_t)(p & 1) * (16 * T) * 4, kb, q, ty, tx);
+          if (dbg && tid == 0) dbg[2] = clock64() + (long long)(reg[T - 1][T - 1] == 123.0);
+          continue;
+        }
         // Y operand of the rank-4 update: block pivots -> the published panel itself (A21), else the Y rows of the panel warps
         UpdateDispatch<T, T>::run(nact, q == 3, reg, M + (size_t)p * PST * 4, (a.block_pivots ? pan : Yb) + (size_t)(p & 1) * (16 * T) * 4,
                                   pan + (size_t)((p + 1) & 1) * (16 * T) * 4, kb, q, ty, tx, dbg);
@@ -473,6 +623,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SolveArgs a) {
     }
   } else {
     const int pt = tid - SOLVE_UPD;
+    if (a.pipe) panel_pipeline<T>(As, M, pan, hand, D, PST, pt, npanels, a.dbg);
+    else
 #pragma unroll 1
     for (int p = 0; p < npanels; p++) {
       long long *dbg = (a.dbg && pt == 8 && p >= 4 && p < 6) ? a.dbg + 16 + 8 * (p - 4) : nullptr;
@@ -780,7 +932,7 @@ __global__ void __launch_bounds__(256) k_make_xad(const double *__restrict__ x, 
 }  // namespace
 
 static size_t solve_smem_base(int D, int T) {   // factor storage, As, six D-vectors, panel + Y buffers (all even counts: 16-byte alignment holds)
-  return ((size_t)D * (16 * T + 1) + (size_t)(D + 1) * D + 6 * (size_t)D + 4 * (size_t)(16 * T) * 4) * sizeof(double);
+  return ((size_t)D * (16 * T + 1) + (size_t)(D + 1) * D + 6 * (size_t)D + 6 * (size_t)(16 * T) * 4) * sizeof(double);
 }
 
 template <int T>
@@ -821,6 +973,10 @@ int launch_solve(sosba *h, const SolveArgs &a0) {
   a.backsub_rowwise = rowwise ? 1 : 0;
   static const bool scalar_pivots = [] { const char *e = getenv("SOSBA_SOLVE_PIVOTS"); return e && e[0] == 's'; }();   // "scalar": column-by-column LDL^T
   a.block_pivots = scalar_pivots ? 0 : 1;
+  // measured at D = 68: factorisation 25.2 k cycles pipelined against 24.2 k with the hand-off scheme (the panel warps' own
+  // window updates, one warp per scheduler beside two update warps, take the time the hand-off took) -> opt-in
+  static const bool want_pipe = [] { const char *e = getenv("SOSBA_SOLVE_PIPE"); return e && e[0] == '1'; }();
+  a.pipe = (a.block_pivots && want_pipe) ? 1 : 0;
   int T = (a.D + 1 + 15) / 16;
   if (const char *f = getenv("SOSBA_SOLVE_FORCE_T")) T = std::max(T, atoi(f));   // debug: run a wider instantiation
   if (T <= 3) return launch_solve_t<3>(h, a);

@@ -253,6 +253,7 @@ struct SolveArgs {
   int smem_words;              // set by launch_solve: 4-byte words of dynamic shared memory (scratch of the spare CTA)
   long long *trace;            // SOSBA_TRACE record of this launch, or null
   int block_pivots;            // set by launch_solve: 1 = 4x4 block pivots (block LDL^T, the default), 0 = scalar pivots (SOSBA_SOLVE_PIVOTS=scalar)
+  int pipe;                    // set by launch_solve: 1 = pipelined factorisation (panel warps keep a sliding window of their rows; opt-in with SOSBA_SOLVE_PIPE=1)
   int backsub_rowwise;         // set by launch_solve: 1 = row-by-row back substitution (SOSBA_SOLVE_BACKSUB=row), 0 = blocks of 4 rows
 };
 int launch_solve(sosba *h, const SolveArgs &a);

@@ -3,7 +3,8 @@
 // stitched-space Schur Gram matrix, the priors and (optionally) the marginalisation prior HM, bM:
 //   HFinal = Htop + priors (+HM), b = btop + prior*delta_prior (+bM + HM*delta); diag *= (1+1e-5);
 //   HFinal -= H_sc/(1+1e-5); b -= b_sc; Jacobi scaling 1/sqrt(diag+10); LDL^T with the transposition order of
-//   Eigen::LDLT (the solver called at :1147-1148); back-substitution; x = S * y; then
+//   Eigen::LDLT (the solver called at :1147-1148), factorised with 4x4 pivot blocks (panel_rows<true>; scalar pivots with
+//   SOSBA_SOLVE_PIVOTS=scalar); back-substitution in blocks of 4 rows; x = S * y; then
 //   xAd[h*nf+t] = x_h^T adHostF[h+nf*t] + x_t^T adTargetF[h+nf*t] for resubstituteF_MT (:496-524).
 // D = 4 + 8*nf <= 132; the (D+1)^2 augmented matrix lives in shared memory.
 #include <math.h>
@@ -149,7 +150,7 @@ __device__ __forceinline__ void panel_rows(const double *__restrict__ pb, double
   const double2 pa = pp[0], pc = pp[1];
   const double a10 = q1.x, a11 = q1.y, a20 = q2a.x, a21 = q2a.y, a22 = q2b.x, a30 = q3a.x, a31 = q3a.y, a32 = q3b.x, a33 = q3b.y;
   if (k0 > 0) nb_arrive(BAR_PL);   // our loads are queued: the update warps may start theirs (pairs with the sync in update_step of the panel before)
-  if (dbg) dbg[0] = clock64() + (long long)(a00 == 123.0) + (long long)(pc.y == 123.0);   // panel data landed   // our loads are queued: the update warps may start theirs (pairs with the sync in update_step of panel k0/4 - 1)
+  if (dbg) dbg[0] = clock64() + (long long)(a00 == 123.0) + (long long)(pc.y == 123.0);   // panel data landed
   if (BLOCK) {
     const double s0 = fma(a00, a11, -(a10 * a10)), s1 = fma(a00, a21, -(a10 * a20)), s2 = fma(a00, a31, -(a10 * a30));
     const double s3 = fma(a10, a21, -(a11 * a20)), s4 = fma(a10, a31, -(a11 * a30)), s5 = fma(a20, a31, -(a21 * a30));

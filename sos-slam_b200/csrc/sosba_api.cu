@@ -280,6 +280,8 @@ API void sosba_config_default(sosba_config *c, int32_t w, int32_t h) {
 API const char *sosba_last_error(void) { return g_err; }
 
 // ---- lifetime -----------------------------------------------------------------------------------
+static int create_body(sosba *h, const sosba_config *cfg, int device);
+API void sosba_destroy(sosba_t *h);
 API int sosba_create(const sosba_config *cfg, int32_t device, sosba_t **out) {
   if (!cfg || !out || cfg->w <= 0 || cfg->h <= 0) { sosba_set_error("bad config"); return SOSBA_E_ARG; }
   int ndev = 0;
@@ -294,6 +296,12 @@ API int sosba_create(const sosba_config *cfg, int32_t device, sosba_t **out) {
   if (!h) return SOSBA_E_ARG;
   h->cfg = *cfg;
   h->device = device;
+  const int rc = create_body(h, cfg, device);
+  if (rc) { sosba_destroy(h); return rc; }   // a failure half-way must not leak the handle, its stream, or the pinned buffers
+  *out = h;
+  return SOSBA_OK;
+}
+static int create_body(sosba *h, const sosba_config *cfg, int device) {
   cudaDeviceProp prop;
   SOSBA_CUDA(cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
@@ -333,10 +341,7 @@ API int sosba_create(const sosba_config *cfg, int32_t device, sosba_t **out) {
   DALLOC(h, h->t_acc, 64);
   DALLOC(h, hs->d_status, 4);
   h->ba = new BA();
-  int rc = sync(h);
-  if (rc) return rc;
-  *out = h;
-  return SOSBA_OK;
+  return sync(h);
 }
 
 int sosba_comm_destroy(sosba_t *h);

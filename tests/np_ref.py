@@ -1239,3 +1239,54 @@ def distance_map_ref(w1, h1, KRKi, Kt, host, u, v, idepth):
             reach |= sh
         d[reach & (d > k)] = k
     return d
+
+
+# ---- the solver of k_solve.cu, restated ---------------------------------------------------------------------
+def _adjugate4(A):
+    """adjugate and determinant of a symmetric 4x4 block from its 2x2 minors, the formula sheet of panel_rows<true> / panel_pipeline"""
+    a00, a10, a11, a20, a21, a22, a30, a31, a32, a33 = A[0, 0], A[1, 0], A[1, 1], A[2, 0], A[2, 1], A[2, 2], A[3, 0], A[3, 1], A[3, 2], A[3, 3]
+    s0 = a00 * a11 - a10 * a10; s1 = a00 * a21 - a10 * a20; s2 = a00 * a31 - a10 * a30
+    s3 = a10 * a21 - a11 * a20; s4 = a10 * a31 - a11 * a30; s5 = a20 * a31 - a21 * a30
+    c5 = a22 * a33 - a32 * a32; c4 = a21 * a33 - a31 * a32; c3 = a21 * a32 - a31 * a22
+    c2 = a20 * a33 - a30 * a32; c1 = a20 * a32 - a30 * a22
+    det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * s5
+    i00 = a11 * c5 - a21 * c4 + a31 * c3; i01 = -a10 * c5 + a20 * c4 - a30 * c3
+    i02 = a31 * s5 - a32 * s4 + a33 * s3; i03 = -a21 * s5 + a22 * s4 - a32 * s3
+    i11 = a00 * c5 - a20 * c2 + a30 * c1; i12 = -a30 * s5 + a32 * s2 - a33 * s1
+    i13 = a20 * s5 - a22 * s2 + a32 * s1; i22 = a30 * s4 - a31 * s2 + a33 * s0
+    i23 = -a20 * s4 + a21 * s2 - a32 * s0; i33 = a20 * s3 - a21 * s1 + a22 * s0
+    adj = np.array([[i00, i01, i02, i03], [i01, i11, i12, i13], [i02, i12, i22, i23], [i03, i13, i23, i33]])
+    return adj, det
+
+
+def block_ldlt_solve(Hf, bf):
+    """The solve of k_solve.cu on an assembled system (EnergyFunctional.cpp:1141-1149 solves the same one with Eigen::LDLT):
+    Jacobi scaling 1/sqrt(diag + 10); pivot order = descending |scaled diagonal| (ties by index); right-looking block LDL^T
+    with 4x4 pivot blocks inverted through their adjugate (a singular block leaves its columns alone); the right-hand side
+    rides along as an extra row and ends as A11^-1 (L^-1 P b) per block; back substitution block by block; x = S * P^T w."""
+    D = len(bf)
+    assert D % 4 == 0
+    Hf = np.tril(Hf) + np.tril(Hf, -1).T      # Eigen::LDLT and the kernel's assembly both read entry (max(i,j), min(i,j))
+    S = 1.0 / np.sqrt(np.diag(Hf) + 10)
+    A = S[:, None] * Hf * S[None, :]
+    key = np.abs(np.diag(A))
+    perm = np.array(sorted(range(D), key=lambda i: (-key[i], i)))
+    M = np.zeros((D + 1, D))
+    M[:D] = A[np.ix_(perm, perm)]
+    M[D] = (S * bf)[perm]
+    W = np.zeros((D + 1, D))
+    for k0 in range(0, D, 4):
+        adj, det = _adjugate4(M[k0:k0 + 4, k0:k0 + 4])
+        rdet = 1.0 / det if det != 0 and np.isfinite(1.0 / det) else 0.0
+        rows = np.arange(k0 + 4, D + 1)
+        A21 = M[rows, k0:k0 + 4].copy()
+        Wr = (A21 @ adj) * rdet
+        W[rows, k0:k0 + 4] = Wr
+        cols = np.arange(k0 + 4, D)
+        M[np.ix_(rows, cols)] -= Wr @ M[cols, k0:k0 + 4].T
+    w = W[D].copy()
+    for k0 in range(D - 4, -1, -4):
+        w[:k0] -= W[k0:k0 + 4, :k0].T @ w[k0:k0 + 4]     # rows of the block carry their coupling to every earlier column
+    x = np.zeros(D)
+    x[perm] = w
+    return S * x

@@ -258,6 +258,38 @@ def test_accumulate_vs_dense_fp64(orc, threads):
     h.close()
 
 
+@pytest.mark.parametrize("case", ["tiny", "configB"])
+def test_block_pivot_solver_restatement(orc, case):
+    """The device solver (k_solve.cu) factorises with 4x4 pivot blocks inverted through their adjugate instead of Eigen's column
+    by column LDL^T.  Its numpy restatement (np_ref.block_ldlt_solve, same pivot order, same formula sheet) must reproduce the
+    oracle's solveSystemF on the very system the oracle solved, far inside the tolerance the GPU parity test grants the kernel
+    (1e-3 in the H-norm), also with a singular pivot block."""
+    from sos_slam_b200 import problem
+    from _scenes import CONFIG_B
+    sc = scene(**(TINY if case == "tiny" else CONFIG_B))
+    frames = problem.frames_of(sc)
+    val, val0 = problem.calib_of(sc)
+    win = np_ref.window_tables(frames, val, val0)
+    h = open_handle(orc, sc, threads=1)
+    h.window_set(win); h.points_set(problem.points_of(sc)); h.residuals_set(problem.residuals_of(sc))
+    h.reset_oob(); h.linearize_all(False); h.apply_res()
+    h.accumulate()
+    x, Hf, bf = h.solve_system()
+    h.close()
+    xb = np_ref.block_ldlt_solve(Hf, bf)
+    d = xb - x
+    assert np.sqrt(abs(d @ Hf @ d)) <= 1e-10 * np.sqrt(abs(x @ Hf @ x))
+    # a decoupled, exactly singular 4x4 pivot block: its columns are left alone, everything else is solved as before
+    D = len(bf)
+    Hs, bs = np.zeros((D + 4, D + 4)), np.zeros(D + 4)
+    Hs[:D, :D], bs[:D] = Hf, bf
+    Hs[D:, D:] = 1e12 * np.ones((4, 4)) - 10 * np.eye(4)      # rank 1 after the "+ 10" of the scaling: largest diagonal, first pivot block
+    xs = np_ref.block_ldlt_solve(Hs, bs)
+    assert np.all(np.isfinite(xs)) and np.allclose(xs[D:], 0.0)
+    d = xs[:D] - x
+    assert np.sqrt(abs(d @ Hf @ d)) <= 1e-10 * np.sqrt(abs(x @ Hf @ x))
+
+
 def test_thread_count_invariance(orc):
     """stitchDouble (serial) == stitchDoubleMT (6 workers) up to float summation order."""
     sc = scene(**SMALLC)

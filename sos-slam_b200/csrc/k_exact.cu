@@ -71,6 +71,105 @@ __global__ void __launch_bounds__(256) k_pyr(const float *__restrict__ src, int 
   plane[idx] = I;
 }
 
+// a1, ALL LEVELS IN ONE LAUNCH (the default where the shape allows it, launch_make_images): a CTA owns a 64 x 32 tile of level 0 and everything below it.  The
+// irradiance tile plus a halo of 2^(levels-1) pixels is staged in shared memory by TMA bulk copies (one cp.async.bulk per row,
+// completion on an mbarrier), the 2x2 means of every level are formed there (same expression, same float values as the
+// level-by-level kernel reads back from its planar copies), and each level's {I, dx, dy, absSquaredGrad} texels are written
+// from shared-memory neighbours.  The only values a tile cannot see are the flat-index neighbours of the first / last column
+// (the reference differentiates over a flat index, so they sit at the other end of the neighbouring row): those few are
+// rebuilt from the level-0 image with the same expression tree.
+constexpr int PYR_TW = 64, PYR_TH = 32, PYR_MAXL = 5;
+struct PyrArgs {
+  const float *src;          // level-0 irradiance, w * h
+  float4 *img[PYR_MAXL];     // per level
+  int w, h, levels, gamma;
+  const float *B;
+};
+__device__ float pyr_level_value(const float *__restrict__ src, int w0, int l, int x, int y) {   // I_l(x, y) from level 0
+  if (l == 0) return __ldg(src + (size_t)y * w0 + x);
+  const float a = pyr_level_value(src, w0, l - 1, 2 * x, 2 * y), b = pyr_level_value(src, w0, l - 1, 2 * x + 1, 2 * y);
+  const float c = pyr_level_value(src, w0, l - 1, 2 * x, 2 * y + 1), d = pyr_level_value(src, w0, l - 1, 2 * x + 1, 2 * y + 1);
+  return 0.25f * (((a + b) + c) + d);
+}
+__global__ void __launch_bounds__(256) k_pyr_fused(PyrArgs a) {
+  extern __shared__ __align__(16) float s_pl[];   // planes of the levels, each (SW >> l) x (SH >> l), level 0 first
+  __shared__ __align__(8) unsigned long long mbar;
+  const int L = a.levels, H = 1 << (L - 1);
+  const int SW = PYR_TW + 2 * H, SH = PYR_TH + 2 * H;
+  const int X0 = blockIdx.x * PYR_TW - H, Y0 = blockIdx.y * PYR_TH - H;   // level-0 coordinates of the staged region's corner
+  const int tid = threadIdx.x;
+  // ---- stage level 0: rows inside the image, columns clipped to the image (all multiples of 4 floats)
+  const int xs = max(X0, 0), xe = min(X0 + SW, a.w), ys = max(Y0, 0), ye = min(Y0 + SH, a.h);
+  const unsigned row_bytes = (unsigned)(xe - xs) * 4u;
+  const unsigned mb = (unsigned)__cvta_generic_to_shared(&mbar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(row_bytes * (unsigned)(ye - ys)) : "memory");
+  }
+  __syncthreads();
+  for (int r = ys + tid; r < ye; r += blockDim.x) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(s_pl + (size_t)(r - Y0) * SW + (xs - X0));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(a.src + (size_t)r * a.w + xs), "r"(row_bytes), "r"(mb)
+                 : "memory");
+  }
+  {
+    unsigned done = 0;
+    while (!done) asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(mb), "r"(0u) : "memory");
+  }
+  // ---- the 2x2 means, level by level, over the part of the staged region that lies inside the image
+  int off_prev = 0;
+  for (int l = 1; l < L; l++) {
+    const int wp = SW >> (l - 1), wl = SW >> l, hl = SH >> l;
+    const int off = off_prev + wp * (SH >> (l - 1));
+    const int gx0 = X0 >> l, gy0 = Y0 >> l, gw = a.w >> l, gh = a.h >> l;   // (X0, Y0 are multiples of 2^l)
+    for (int e = tid; e < wl * hl; e += blockDim.x) {
+      const int x = e % wl, y = e / wl;
+      const int gx = gx0 + x, gy = gy0 + y;
+      if (gx < 0 || gy < 0 || gx >= gw || gy >= gh) continue;
+      const float *p = s_pl + off_prev + 2 * x + 2 * y * wp;
+      s_pl[off + e] = 0.25f * (((p[0] + p[1]) + p[wp]) + p[1 + wp]);
+    }
+    off_prev = off;
+    __syncthreads();
+  }
+  // ---- texels of every level
+  int off = 0;
+  for (int l = 0; l < L; l++) {
+    const int wl = SW >> l, tw = PYR_TW >> l, th = PYR_TH >> l, hh = H >> l;
+    const int gw = a.w >> l, gh = a.h >> l;
+    const int gx0 = (X0 + H) >> l, gy0 = (Y0 + H) >> l;   // first level-l pixel of this tile
+    float4 *img = a.img[l];
+    for (int e = tid; e < tw * th; e += blockDim.x) {
+      const int x = e % tw, y = e / tw;
+      const int gx = gx0 + x, gy = gy0 + y;
+      if (gx >= gw || gy >= gh) continue;
+      const float *c = s_pl + off + (x + hh) + (y + hh) * wl;
+      const float I = c[0];
+      float dx = 0.f, dy = 0.f, ab = 0.f;
+      if (gy >= 1 && gy <= gh - 2) {
+        const float left = gx > 0 ? c[-1] : pyr_level_value(a.src, a.w, l, gw - 1, gy - 1);        // flat index - 1
+        const float right = gx < gw - 1 ? c[1] : pyr_level_value(a.src, a.w, l, 0, gy + 1);        // flat index + 1
+        dx = 0.5f * (right - left);
+        dy = 0.5f * (c[wl] - c[-wl]);
+        if (!isfinite(dx)) dx = 0.f;
+        if (!isfinite(dy)) dy = 0.f;
+        ab = dx * dx + dy * dy;
+        if (a.gamma == 1 && a.B != nullptr) {  // CalibHessian::getBGradOnly, HessianBlocks.h:519-526
+          int ci = (int)(I + 0.5f);
+          if (ci < 5) ci = 5;
+          if (ci > 250) ci = 250;
+          const float gwt = a.B[ci + 1] - a.B[ci];
+          ab *= gwt * gwt;
+        }
+      }
+      img[(size_t)gy * gw + gx] = make_float4(I, dx, dy, ab);
+    }
+    off += wl * (SH >> l);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // globalFuncs.h:68-82 on the float4 image: weights and summation order verbatim.
 __device__ __forceinline__ float3 interp33(const float4 *__restrict__ img, float x, float y, int width) {
@@ -1069,6 +1168,22 @@ void launch_undistort(sosba *h, const UndistortArgs &a) {
 
 // ------------------------------------------------------------------------------------------------
 void launch_make_images(sosba *h, int slot, const float *d_color, const float *d_B) {
+  // all levels in one launch when the shape allows the tiling (SOSBA_PYR_FUSED=0: one launch per level): 3 to 5 levels (the halo
+  // 2^(levels-1) must be a multiple of 4 texels for the 16-byte alignment of the bulk copies), width a multiple of 4, both
+  // sides divisible by 2^(levels-1), a 16-byte aligned source
+  static const bool fused = [] { const char *e = getenv("SOSBA_PYR_FUSED"); return !(e && e[0] == '0'); }();
+  const int L = h->levels, w0 = h->cfg.w, h0 = h->cfg.h, m = (1 << (L - 1)) - 1;
+  if (fused && L >= 3 && L <= PYR_MAXL && (w0 & 3) == 0 && (w0 & m) == 0 && (h0 & m) == 0 && ((uintptr_t)d_color & 15) == 0) {
+    PyrArgs a;
+    a.src = d_color; a.w = w0; a.h = h0; a.levels = L; a.gamma = h->cfg.gamma_weights_pixel_select; a.B = d_B;
+    for (int l = 0; l < PYR_MAXL; l++) a.img[l] = l < L ? h->slot_img[slot] + h->lvl_off[l] : nullptr;
+    const int H = 1 << (L - 1), SW = PYR_TW + 2 * H, SH = PYR_TH + 2 * H;
+    size_t floats = 0;
+    for (int l = 0; l < L; l++) floats += (size_t)(SW >> l) * (SH >> l);
+    k_pyr_fused<<<dim3((w0 + PYR_TW - 1) / PYR_TW, (h0 + PYR_TH - 1) / PYR_TH), 256, floats * sizeof(float), h->stream>>>(a);
+    h->launches++;
+    return;
+  }
   for (int l = 0; l < h->levels; l++) {
     const int w = h->wl[l], hh = h->hl[l], n = w * hh;
     const float *src = l == 0 ? d_color : h->slot_plane[slot] + h->lvl_off[l - 1];

@@ -47,7 +47,7 @@ long long *sosba_trace_slot(const char *name) {
 static void trace_begin(sosba *h) {   // start of a traced sosba_ba_optimize: empty records
   if (!trace_on()) return;
   static long long init[4 * TRACE_CAP];
-  if (!g_trace) cudaMalloc(&g_trace, sizeof(init));
+  if (!g_trace) cudaMalloc(&g_trace, sizeof(init) + 16 * sizeof(long long));   // (+ the phase stamps a linearisation writes behind its own record)
   for (int i = 0; i < TRACE_CAP; i++) { init[4 * i] = init[4 * i + 1] = 0x7fffffffffffffffLL; init[4 * i + 2] = init[4 * i + 3] = 0; }
   cudaMemcpyAsync(g_trace, init, sizeof(init), cudaMemcpyHostToDevice, h->stream);
   g_trace_n = 0;
